@@ -1,0 +1,800 @@
+/*
+ * fhe_oracle.c -- CPU restatement of the Phantom-FHE RNS hot path.  TEST INFRASTRUCTURE ONLY
+ * (see fhe_oracle.h for who may load this and how its parity is pinned).
+ *
+ * Plain C99 + unsigned __int128.  Everything is written as "obviously correct" modular arithmetic that
+ * produces canonical residues; the NTT uses SEAL-style Harvey lazy butterflies over the same bit-reversed
+ * tables the reference's host code generates, because that is also the "SEAL-style CPU path" timed as
+ * cpu_baseline by bench.py (OpenMP over limbs).
+ */
+#include "fhe_oracle.h"
+
+#include <stdlib.h>
+#include <string.h>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+typedef unsigned __int128 u128;
+typedef uint64_t u64;
+
+static int g_threads = 1;
+void orc_set_threads(int nthreads) { g_threads = nthreads < 1 ? 1 : nthreads; }
+int orc_get_threads(void) { return g_threads; }
+
+/* ------------------------------------------------------------------------------------------------------
+ * scalar modular arithmetic
+ * ---------------------------------------------------------------------------------------------------- */
+u64 orc_mulmod(u64 a, u64 b, u64 q) { return (u64)(((u128)a * b) % q); }
+
+static u64 powmod(u64 a, u64 e, u64 q) {
+    u64 r = 1 % q;
+    a %= q;
+    while (e) {
+        if (e & 1) r = orc_mulmod(r, a, q);
+        a = orc_mulmod(a, a, q);
+        e >>= 1;
+    }
+    return r;
+}
+
+/* try_invert_uint_mod (src/host/uintarithsmallmod.cu): a^-1 mod q, q need not be prime -> extended Euclid */
+u64 orc_invmod(u64 a, u64 q) {
+    __int128 t0 = 0, t1 = 1;
+    u64 r0 = q, r1 = a % q;
+    while (r1) {
+        u64 k = r0 / r1;
+        __int128 t2 = t0 - (__int128)k * t1;
+        t0 = t1;
+        t1 = t2;
+        u64 r2 = r0 - k * r1;
+        r0 = r1;
+        r1 = r2;
+    }
+    if (r0 != 1) return 0; /* not invertible */
+    if (t0 < 0) t0 += q;
+    return (u64)t0;
+}
+
+/* compute_shoup: floor(w * 2^64 / q), include/host/uintarithsmallmod.h:119-124 */
+u64 orc_shoup(u64 w, u64 q) { return (u64)((((u128)w) << 64) / q); }
+
+/* Modulus::set_value, src/host/modulus.cu:28-41: floor(2^128 / q) as two words + remainder */
+void orc_barrett_ratio(u64 q, u64 ratio[3]) {
+    /* long division of [0,0,1] (base 2^64) by q */
+    u64 rem = 1; /* top word 1 < q */
+    u128 cur = ((u128)rem << 64);
+    u64 q1 = (u64)(cur / q);
+    rem = (u64)(cur % q);
+    cur = ((u128)rem << 64);
+    u64 q0 = (u64)(cur / q);
+    rem = (u64)(cur % q);
+    ratio[0] = q0;
+    ratio[1] = q1;
+    ratio[2] = rem;
+}
+
+/* Shoup multiplication, canonical result (uintmodmath.cuh:207-216) */
+static inline u64 mul_shoup(u64 x, u64 w, u64 ws, u64 q) {
+    u64 hi = (u64)(((u128)x * ws) >> 64);
+    u64 r = x * w - hi * q;
+    return r >= q ? r - q : r;
+}
+/* lazy variant -> [0, 2q) (uintmodmath.cuh:226-231) */
+static inline u64 mul_shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
+    u64 hi = (u64)(((u128)x * ws) >> 64);
+    return x * w - hi * q;
+}
+
+static inline u64 addmod(u64 a, u64 b, u64 q) {
+    u64 r = a + b;
+    return r >= q ? r - q : r;
+}
+static inline u64 submod(u64 a, u64 b, u64 q) { return a >= b ? a - b : a + q - b; }
+
+/* is_prime: the reference runs Miller-Rabin with random bases (src/host/numth.cu:160-204); the outcome for
+ * 64-bit inputs is the deterministic primality predicate, computed here with the first 12 prime bases. */
+int orc_is_prime(u64 v) {
+    static const u64 bases[12] = {2, 3, 5, 7, 11, 13, 17, 19, 23, 29, 31, 37};
+    if (v < 2) return 0;
+    for (int i = 0; i < 12; i++) {
+        if (v == bases[i]) return 1;
+        if (v % bases[i] == 0) return 0;
+    }
+    u64 d = v - 1;
+    int r = 0;
+    while (!(d & 1)) {
+        d >>= 1;
+        r++;
+    }
+    for (int i = 0; i < 12; i++) {
+        u64 x = powmod(bases[i], d, v);
+        if (x == 1 || x == v - 1) continue;
+        int comp = 1;
+        for (int k = 1; k < r; k++) {
+            x = orc_mulmod(x, x, v);
+            if (x == v - 1) {
+                comp = 0;
+                break;
+            }
+        }
+        if (comp) return 0;
+    }
+    return 1;
+}
+
+/* CoeffModulus::Create (src/host/modulus.cu:79-110) over get_primes (src/host/numth.cu:207-233):
+ * per distinct bit size, primes are found downwards from 2^bits - 2n + 1 in steps of 2n; the list is then
+ * consumed from the BACK, so for repeated sizes the later list position gets the larger prime. */
+int orc_create_primes(u64 n, const int *bit_sizes, int count, u64 *out) {
+    if (count <= 0 || count > 64) return -1;
+    int done[64];
+    memset(done, 0, sizeof(done));
+    for (int i = 0; i < count; i++) {
+        if (done[i]) continue;
+        int bits = bit_sizes[i];
+        if (bits < 2 || bits > 61) return -1;
+        int pos[64], npos = 0;
+        for (int j = i; j < count; j++)
+            if (bit_sizes[j] == bits) {
+                pos[npos++] = j;
+                done[j] = 1;
+            }
+        u64 found[64];
+        int nf = 0;
+        u64 factor = 2 * n;
+        u64 value = ((u64)1 << bits);
+        if (value < factor) return -1;
+        value = value - factor + 1;
+        u64 lower = (u64)1 << (bits - 1);
+        while (nf < npos && value > lower) {
+            if (orc_is_prime(value)) found[nf++] = value;
+            value -= factor;
+        }
+        if (nf < npos) return -1;
+        /* result.emplace_back(prime_table[size].back()); pop_back() */
+        for (int k = 0; k < npos; k++) out[pos[k]] = found[npos - 1 - k];
+    }
+    return 0;
+}
+
+/* try_minimal_primitive_root (src/host/numth.cu:309-331) */
+u64 orc_minimal_primitive_root(u64 degree, u64 q) {
+    if ((q - 1) % degree) return 0;
+    u64 quot = (q - 1) / degree;
+    u64 root = 0;
+    for (u64 x = 2; x < q; x++) {
+        u64 g = powmod(x, quot, q);
+        if (powmod(g, degree >> 1, q) == q - 1) {
+            root = g;
+            break;
+        }
+    }
+    if (!root) return 0;
+    u64 gsq = orc_mulmod(root, root, q);
+    u64 cur = root, best = root;
+    for (u64 i = 0; i < degree / 2; i++) {
+        if (cur < best) best = cur;
+        cur = orc_mulmod(cur, gsq, q);
+    }
+    return best;
+}
+
+static inline uint32_t bitrev32(uint32_t x, int bits) {
+    uint32_t r = 0;
+    for (int i = 0; i < bits; i++) {
+        r = (r << 1) | (x & 1);
+        x >>= 1;
+    }
+    return r;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * context
+ * ---------------------------------------------------------------------------------------------------- */
+struct orc_ctx {
+    int scheme;
+    u64 n;
+    int logn;
+    int size_QP, size_P, size_Q;
+    u64 t;
+    u64 *primes;                 /* [size_QP] */
+    u64 *tw, *tws, *itw, *itws;  /* [size_QP][n] */
+    u64 *ninv, *ninvs;           /* [size_QP] */
+};
+
+orc_ctx *orc_create(int scheme, u64 n, const u64 *primes, int size_QP, int size_P, u64 t) {
+    int logn = 0;
+    while (((u64)1 << logn) < n) logn++;
+    if (((u64)1 << logn) != n || size_QP < 1 || size_P < 0 || size_P >= size_QP + (size_P == 0)) return NULL;
+    orc_ctx *c = (orc_ctx *)calloc(1, sizeof(orc_ctx));
+    c->scheme = scheme;
+    c->n = n;
+    c->logn = logn;
+    c->size_QP = size_QP;
+    c->size_P = size_P;
+    c->size_Q = size_QP - size_P;
+    c->t = t;
+    c->primes = (u64 *)malloc(sizeof(u64) * size_QP);
+    memcpy(c->primes, primes, sizeof(u64) * size_QP);
+    size_t tab = (size_t)size_QP * n;
+    c->tw = (u64 *)malloc(tab * 8);
+    c->tws = (u64 *)malloc(tab * 8);
+    c->itw = (u64 *)malloc(tab * 8);
+    c->itws = (u64 *)malloc(tab * 8);
+    c->ninv = (u64 *)malloc(sizeof(u64) * size_QP);
+    c->ninvs = (u64 *)malloc(sizeof(u64) * size_QP);
+    int ok = 1;
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic)
+    for (int i = 0; i < size_QP; i++) {
+        u64 q = primes[i];
+        /* NTT::NTT, src/host/ntt.cu:10-56 */
+        u64 root = orc_minimal_primitive_root(2 * n, q);
+        if (!root) {
+            ok = 0;
+            continue;
+        }
+        u64 iroot = orc_invmod(root, q);
+        u64 *tw = c->tw + (size_t)i * n, *tws = c->tws + (size_t)i * n;
+        u64 *itw = c->itw + (size_t)i * n, *itws = c->itws + (size_t)i * n;
+        u64 p = root, ip = iroot;
+        for (u64 k = 1; k < n; k++) {
+            uint32_t r = bitrev32((uint32_t)k, logn);
+            tw[r] = p;
+            tws[r] = orc_shoup(p, q);
+            itw[r] = ip;
+            itws[r] = orc_shoup(ip, q);
+            p = orc_mulmod(p, root, q);
+            ip = orc_mulmod(ip, iroot, q);
+        }
+        tw[0] = 1;
+        tws[0] = orc_shoup(1, q);
+        itw[0] = 1;
+        itws[0] = orc_shoup(1, q);
+        u64 ninv = orc_invmod(n % q, q);
+        c->ninv[i] = ninv;
+        c->ninvs[i] = orc_shoup(ninv, q);
+        /* inv_root_powers_[1] *= n^-1 (src/host/ntt.cu:53-55) */
+        itw[1] = orc_mulmod(itw[1], ninv, q);
+        itws[1] = orc_shoup(itw[1], q);
+    }
+    if (!ok) {
+        orc_destroy(c);
+        return NULL;
+    }
+    return c;
+}
+
+void orc_destroy(orc_ctx *c) {
+    if (!c) return;
+    free(c->primes);
+    free(c->tw);
+    free(c->tws);
+    free(c->itw);
+    free(c->itws);
+    free(c->ninv);
+    free(c->ninvs);
+    free(c);
+}
+
+u64 orc_n(const orc_ctx *c) { return c->n; }
+int orc_size_QP(const orc_ctx *c) { return c->size_QP; }
+int orc_size_P(const orc_ctx *c) { return c->size_P; }
+const u64 *orc_twiddle(const orc_ctx *c, int i) { return c->tw + (size_t)i * c->n; }
+const u64 *orc_twiddle_shoup(const orc_ctx *c, int i) { return c->tws + (size_t)i * c->n; }
+const u64 *orc_itwiddle(const orc_ctx *c, int i) { return c->itw + (size_t)i * c->n; }
+const u64 *orc_itwiddle_shoup(const orc_ctx *c, int i) { return c->itws + (size_t)i * c->n; }
+u64 orc_n_inv(const orc_ctx *c, int i) { return c->ninv[i]; }
+u64 orc_prime(const orc_ctx *c, int i) { return c->primes[i]; }
+
+/* key-level prime index of position j in the packed data-level base Ql ∪ P (fntt_2d.cu:434-436) */
+static inline int qlp_index(const orc_ctx *c, int l, int j) { return j < l ? j : c->size_Q + (j - l); }
+
+/* ------------------------------------------------------------------------------------------------------
+ * NTT
+ * ---------------------------------------------------------------------------------------------------- */
+/* forward negacyclic NTT, natural -> bit-reversed order (ntt_1d.cu:41-73; butterfly.cuh:10-22 semantics:
+ * Harvey lazy CT butterfly, x,y in [0,4q) -> [0,4q)), final reduction to [0,q) (fntt_2d.cu:187-193). */
+static void ntt_fwd_limb(u64 *a, u64 n, const u64 *tw, const u64 *tws, u64 q) {
+    u64 two_q = 2 * q;
+    for (u64 m = 1; m < n; m <<= 1) {
+        u64 gap = n / (2 * m);
+        for (u64 i = 0; i < m; i++) {
+            u64 w = tw[m + i], ws = tws[m + i];
+            u64 *x = a + 2 * i * gap, *y = x + gap;
+            for (u64 j = 0; j < gap; j++) {
+                u64 X = x[j];
+                if (X >= two_q) X -= two_q;
+                u64 T = mul_shoup_lazy(y[j], w, ws, q);
+                x[j] = X + T;
+                y[j] = X + two_q - T;
+            }
+        }
+    }
+    for (u64 j = 0; j < n; j++) {
+        u64 v = a[j];
+        if (v >= two_q) v -= two_q;
+        if (v >= q) v -= q;
+        a[j] = v;
+    }
+}
+
+/* inverse negacyclic NTT, bit-reversed -> natural (ntt_1d.cu:220-254; butterfly.cuh:28-37: GS butterfly,
+ * x,y in [0,2q) -> [0,2q)); lower half times n^-1, the upper half got it through itw[1]
+ * (intt_2d.cu:195-198); final reduction to [0,q) (intt_2d.cu:203). */
+static void ntt_inv_limb(u64 *a, u64 n, const u64 *itw, const u64 *itws, u64 ninv, u64 ninvs, u64 q) {
+    u64 two_q = 2 * q;
+    for (u64 m = n >> 1; m >= 1; m >>= 1) {
+        u64 gap = n / (2 * m);
+        for (u64 i = 0; i < m; i++) {
+            u64 w = itw[m + i], ws = itws[m + i];
+            u64 *x = a + 2 * i * gap, *y = x + gap;
+            for (u64 j = 0; j < gap; j++) {
+                u64 X = x[j], Y = y[j];
+                u64 S = X + Y;
+                if (S >= two_q) S -= two_q;
+                u64 D = X + two_q - Y;
+                x[j] = S;
+                y[j] = mul_shoup_lazy(D, w, ws, q);
+            }
+        }
+    }
+    for (u64 j = 0; j < n / 2; j++) a[j] = mul_shoup(a[j], ninv, ninvs, q);
+    for (u64 j = n / 2; j < n; j++) {
+        u64 v = a[j];
+        if (v >= q) v -= q;
+        a[j] = v;
+    }
+}
+
+void orc_ntt_forward(const orc_ctx *c, u64 *data, int limbs, const int *table_idx) {
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic)
+    for (int i = 0; i < limbs; i++) {
+        int k = table_idx[i];
+        ntt_fwd_limb(data + (size_t)i * c->n, c->n, c->tw + (size_t)k * c->n, c->tws + (size_t)k * c->n,
+                     c->primes[k]);
+    }
+}
+
+void orc_ntt_inverse(const orc_ctx *c, u64 *data, int limbs, const int *table_idx) {
+#pragma omp parallel for num_threads(g_threads) schedule(dynamic)
+    for (int i = 0; i < limbs; i++) {
+        int k = table_idx[i];
+        ntt_inv_limb(data + (size_t)i * c->n, c->n, c->itw + (size_t)k * c->n, c->itws + (size_t)k * c->n,
+                     c->ninv[k], c->ninvs[k], c->primes[k]);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * dyadic kernels
+ * ---------------------------------------------------------------------------------------------------- */
+void orc_tensor_2x2(const orc_ctx *c, const u64 *a, const u64 *b, u64 *out, int l) {
+    size_t n = c->n, poly = (size_t)l * n;
+#pragma omp parallel for num_threads(g_threads)
+    for (int i = 0; i < l; i++) {
+        u64 q = c->primes[i];
+        for (size_t j = 0; j < n; j++) {
+            size_t k = (size_t)i * n + j;
+            u64 a0 = a[k], a1 = a[k + poly], b0 = b[k], b1 = b[k + poly];
+            u64 d0 = orc_mulmod(a0, b0, q);
+            u64 d2 = orc_mulmod(a1, b1, q);
+            /* (c0+c1)(c0'+c1') - d0 - d2 (polymath.cu:489-493); the sums are taken unreduced there too */
+            u64 d1 = (u64)(((u128)(a0 + a1) * (b0 + b1)) % q);
+            d1 = submod(submod(d1, d0, q), d2, q);
+            out[k] = d0;
+            out[k + poly] = d1;
+            out[k + 2 * poly] = d2;
+        }
+    }
+}
+
+void orc_tensor_square_2x2(const orc_ctx *c, const u64 *a, u64 *out, int l) {
+    size_t n = c->n, poly = (size_t)l * n;
+#pragma omp parallel for num_threads(g_threads)
+    for (int i = 0; i < l; i++) {
+        u64 q = c->primes[i];
+        for (size_t j = 0; j < n; j++) {
+            size_t k = (size_t)i * n + j;
+            u64 a0 = a[k], a1 = a[k + poly];
+            u64 d0 = orc_mulmod(a0, a0, q);
+            u64 d1 = (u64)((((u128)a0 * a1) << 1) % q);
+            u64 d2 = orc_mulmod(a1, a1, q);
+            out[k] = d0;
+            out[k + poly] = d1;
+            out[k + 2 * poly] = d2;
+        }
+    }
+}
+
+#define ELEMENTWISE(name, expr)                                                                          \
+    void name(const orc_ctx *c, const u64 *a, const u64 *b, u64 *out, int l) {                           \
+        size_t n = c->n;                                                                                 \
+        for (int i = 0; i < l; i++) {                                                                    \
+            u64 q = c->primes[i];                                                                        \
+            for (size_t j = 0; j < n; j++) {                                                             \
+                size_t k = (size_t)i * n + j;                                                            \
+                out[k] = (expr);                                                                         \
+            }                                                                                            \
+        }                                                                                                \
+    }
+ELEMENTWISE(orc_poly_add, addmod(a[k], b[k], q))
+ELEMENTWISE(orc_poly_sub, submod(a[k], b[k], q))
+ELEMENTWISE(orc_poly_mul, orc_mulmod(a[k], b[k], q))
+
+void orc_poly_negate(const orc_ctx *c, const u64 *a, u64 *out, int l) {
+    size_t n = c->n;
+    for (int i = 0; i < l; i++) {
+        u64 q = c->primes[i];
+        for (size_t j = 0; j < n; j++) {
+            size_t k = (size_t)i * n + j;
+            out[k] = a[k] ? q - a[k] : 0;
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * fast base conversion helpers (src/host/rns.cu:282-337,438-497; src/rns_bconv.cu:22-60,143-168)
+ * ---------------------------------------------------------------------------------------------------- */
+/* punctured product of ibase except i, modulo p */
+static u64 qhat_mod(const u64 *ibase, int ni, int i, u64 p) {
+    u64 r = 1 % p;
+    for (int k = 0; k < ni; k++)
+        if (k != i) r = orc_mulmod(r, ibase[k] % p, p);
+    return r;
+}
+
+/* out[j][x] = sum_i (in[i][x] * qhatinv_i mod q_i) * (qhat_i mod p_j) mod p_j  (bConv_BEHZ,
+ * rns_bconv.cu:212-229).  If prescaled != 0 the input has already been multiplied by qhatinv_i. */
+static void bconv(const u64 *ibase, int ni, const u64 *obase, int no, const u64 *const *in, u64 *const *out,
+                  size_t n, int prescaled) {
+    u64 hinv[64], hinvs[64];
+    for (int i = 0; i < ni; i++) {
+        hinv[i] = orc_invmod(qhat_mod(ibase, ni, i, ibase[i]), ibase[i]);
+        hinvs[i] = orc_shoup(hinv[i], ibase[i]);
+    }
+#pragma omp parallel for num_threads(g_threads)
+    for (int j = 0; j < no; j++) {
+        u64 p = obase[j];
+        u64 mat[64];
+        for (int i = 0; i < ni; i++) mat[i] = qhat_mod(ibase, ni, i, p);
+        for (size_t x = 0; x < n; x++) {
+            u128 acc = 0; /* <= 64 terms of < 2^122 each is not representable in general, reduce per term */
+            for (int i = 0; i < ni; i++) {
+                u64 y = prescaled ? in[i][x] : mul_shoup(in[i][x], hinv[i], hinvs[i], ibase[i]);
+                acc += (u128)y * mat[i];
+                if ((i & 3) == 3) acc %= p;
+            }
+            out[j][x] = (u64)(acc % p);
+        }
+    }
+}
+
+int orc_beta(const orc_ctx *c, int l) { return c->size_P ? (l + c->size_P - 1) / c->size_P : 0; }
+
+/* ------------------------------------------------------------------------------------------------------
+ * key switching
+ * ---------------------------------------------------------------------------------------------------- */
+void orc_modup(const orc_ctx *c, int l, const u64 *cks, u64 *t_mod_up) {
+    size_t n = c->n;
+    int alpha = c->size_P, m = l + alpha, beta = orc_beta(c, l);
+    int is_bfv = c->scheme == ORC_SCHEME_BFV;
+
+    /* t_cks: coefficient-domain copy of cks (rns_bconv.cu:544-560) */
+    u64 *t_cks = (u64 *)malloc((size_t)l * n * 8);
+    memcpy(t_cks, cks, (size_t)l * n * 8);
+    if (!is_bfv) {
+        int idx[64];
+        for (int i = 0; i < l; i++) idx[i] = i;
+        orc_ntt_inverse(c, t_cks, l, idx);
+    }
+
+    for (int d = 0; d < beta; d++) {
+        int start = alpha * d;
+        int size_part = (d == beta - 1) ? (l - alpha * (beta - 1)) : alpha;
+        int end = start + size_part;
+        u64 *dst = t_mod_up + (size_t)d * m * n;
+
+        u64 ibase[64], obase[64];
+        const u64 *in[64];
+        u64 *out[64];
+        int oidx[64];
+        for (int i = 0; i < size_part; i++) {
+            ibase[i] = c->primes[start + i];
+            in[i] = t_cks + (size_t)(start + i) * n;
+        }
+        int no = 0;
+        for (int j = 0; j < m; j++) {
+            if (j >= start && j < end) continue;
+            int k = qlp_index(c, l, j);
+            obase[no] = c->primes[k];
+            out[no] = dst + (size_t)j * n;
+            oidx[no] = k;
+            no++;
+        }
+        /* alpha == 1: copy / reduce (modup_bconv_single_p_kernel, rns_bconv.cu:432-453) == bconv with
+         * qhat = qhatinv = 1; alpha > 1: scale by partQlHatInv (rns_bconv.cu:558 / :598) then matmul
+         * (bconv_matmul_padded_unroll2_kernel, :455-485) */
+        bconv(ibase, size_part, obase, no, in, out, n, 0);
+
+        /* the digit's own limbs: raw copy of cks (modup_copy_partQl_kernel :522-528 / single_p :450) */
+        for (int j = start; j < end; j++) memcpy(dst + (size_t)j * n, cks + (size_t)j * n, n * 8);
+
+        if (!is_bfv) {
+            /* NTT on the converted limbs only (..._exclude_range, rns_bconv.cu:618) */
+            for (int k = 0; k < no; k++) orc_ntt_forward(c, out[k], 1, &oidx[k]);
+        } else {
+            /* BFV: all l+alpha limbs go to NTT form (rns_bconv.cu:622) */
+            for (int j = 0; j < m; j++) {
+                int k = qlp_index(c, l, j);
+                orc_ntt_forward(c, dst + (size_t)j * n, 1, &k);
+            }
+        }
+    }
+    free(t_cks);
+}
+
+void orc_inner_prod(const orc_ctx *c, int l, const u64 *t_mod_up, const u64 *evk, u64 *cx) {
+    size_t n = c->n;
+    int alpha = c->size_P, m = l + alpha, beta = orc_beta(c, l);
+    size_t qp_n = (size_t)c->size_QP * n, m_n = (size_t)m * n;
+#pragma omp parallel for num_threads(g_threads)
+    for (int j = 0; j < m; j++) {
+        int twr = qlp_index(c, l, j);
+        u64 q = c->primes[twr];
+        for (size_t x = 0; x < n; x++) {
+            u128 a0 = 0, a1 = 0;
+            for (int d = 0; d < beta; d++) {
+                u64 v = t_mod_up[(size_t)d * m_n + (size_t)j * n + x];
+                const u64 *k = evk + (size_t)d * 2 * qp_n + (size_t)twr * n + x;
+                a0 = (a0 + (u128)v * k[0]) % q;
+                a1 = (a1 + (u128)v * k[qp_n]) % q;
+            }
+            cx[(size_t)j * n + x] = (u64)a0;
+            cx[m_n + (size_t)j * n + x] = (u64)a1;
+        }
+    }
+}
+
+/* P -> Ql conversion used by mod-down: delta[j] = sum_i (x_i * Phatinv_i) * (Phat_i mod q_j)
+ * (alpha == 1: x mod q_j, moddown_bconv_single_p_kernel rns_bconv.cu:691-707) */
+static void p_to_ql(const orc_ctx *c, int l, const u64 *xp, u64 *delta) {
+    size_t n = c->n;
+    u64 ibase[64], obase[64];
+    const u64 *in[64];
+    u64 *out[64];
+    for (int i = 0; i < c->size_P; i++) {
+        ibase[i] = c->primes[c->size_Q + i];
+        in[i] = xp + (size_t)i * n;
+    }
+    for (int j = 0; j < l; j++) {
+        obase[j] = c->primes[j];
+        out[j] = delta + (size_t)j * n;
+    }
+    bconv(ibase, c->size_P, obase, l, in, out, n, 0);
+}
+
+static u64 bigP_mod(const orc_ctx *c, u64 q) {
+    u64 r = 1 % q;
+    for (int i = 0; i < c->size_P; i++) r = orc_mulmod(r, c->primes[c->size_Q + i] % q, q);
+    return r;
+}
+
+void orc_moddown_from_ntt(const orc_ctx *c, int l, u64 *cx_i, u64 *ct_i) {
+    size_t n = c->n;
+    int alpha = c->size_P, m = l + alpha;
+    int idx[64];
+    u64 *delta = (u64 *)malloc((size_t)l * n * 8);
+
+    if (c->scheme == ORC_SCHEME_CKKS) {
+        for (int i = 0; i < alpha; i++) idx[i] = c->size_Q + i;
+        orc_ntt_inverse(c, cx_i + (size_t)l * n, alpha, idx); /* rns_bconv.cu:788 */
+    } else {
+        for (int j = 0; j < m; j++) idx[j] = qlp_index(c, l, j);
+        orc_ntt_inverse(c, cx_i, m, idx); /* :792 */
+    }
+    p_to_ql(c, l, cx_i + (size_t)l * n, delta); /* :796-802 */
+
+    if (c->scheme == ORC_SCHEME_BGV) {
+        /* base_P_to_t_conv_.bConv_BEHZ + bgv_moddown_kernel (rns_bconv.cu:636-652,804-817) */
+        u64 t = c->t;
+        u64 *cp_t = (u64 *)malloc(n * 8);
+        u64 ibase[64];
+        const u64 *in[64];
+        for (int i = 0; i < alpha; i++) {
+            ibase[i] = c->primes[c->size_Q + i];
+            in[i] = cx_i + (size_t)(l + i) * n;
+        }
+        u64 *outp[1] = {cp_t};
+        bconv(ibase, alpha, &t, 1, in, outp, n, 0);
+        u64 pinv_t = orc_invmod(bigP_mod(c, t), t);
+        for (int j = 0; j < l; j++) {
+            u64 q = c->primes[j];
+            u64 P = bigP_mod(c, q), Pinv = orc_invmod(P, q);
+            for (size_t x = 0; x < n; x++) {
+                u64 tmp = orc_mulmod(cp_t[x], pinv_t, t);
+                u64 corr = orc_mulmod(tmp, P, q);
+                u64 v = submod(cx_i[(size_t)j * n + x], delta[(size_t)j * n + x], q);
+                v = addmod(v, corr, q);
+                ct_i[(size_t)j * n + x] = orc_mulmod(v, Pinv, q);
+            }
+        }
+        for (int j = 0; j < l; j++) idx[j] = j;
+        orc_ntt_forward(c, ct_i, l, idx);
+        free(cp_t);
+    } else {
+        if (c->scheme == ORC_SCHEME_CKKS) {
+            for (int j = 0; j < l; j++) idx[j] = j;
+            orc_ntt_forward(c, delta, l, idx); /* fused in nwt_2d_radix8_forward_inplace_fuse_moddown :820 */
+        }
+        /* (cx - delta) * P^-1 mod q_j  (ntt_moddown.cu:210-213 / moddown_kernel rns_bconv.cu:680-689) */
+        for (int j = 0; j < l; j++) {
+            u64 q = c->primes[j];
+            u64 Pinv = orc_invmod(bigP_mod(c, q), q);
+            for (size_t x = 0; x < n; x++) {
+                u64 v = submod(cx_i[(size_t)j * n + x], delta[(size_t)j * n + x], q);
+                ct_i[(size_t)j * n + x] = orc_mulmod(v, Pinv, q);
+            }
+        }
+    }
+    free(delta);
+}
+
+void orc_keyswitch(const orc_ctx *c, int l, u64 *ct, const u64 *c2, const u64 *evk) {
+    size_t n = c->n;
+    int m = l + c->size_P, beta = orc_beta(c, l);
+    u64 *t_mod_up = (u64 *)malloc((size_t)beta * m * n * 8);
+    u64 *cx = (u64 *)malloc((size_t)2 * m * n * 8);
+    u64 *res = (u64 *)malloc((size_t)l * n * 8);
+    orc_modup(c, l, c2, t_mod_up);
+    orc_inner_prod(c, l, t_mod_up, evk, cx);
+    for (int k = 0; k < 2; k++) {
+        /* the reference calls moddown_from_NTT(cx_i, cx_i, ...): the result lands in cx_i[0..l) and is then
+         * added to ct_i (add_to_ct_kernel, rns_bconv.cu:763-769) */
+        orc_moddown_from_ntt(c, l, cx + (size_t)k * m * n, res);
+        orc_poly_add(c, ct + (size_t)k * l * n, res, ct + (size_t)k * l * n, l);
+    }
+    free(t_mod_up);
+    free(cx);
+    free(res);
+}
+
+void orc_multiply_relin(const orc_ctx *c, int l, const u64 *ct1, const u64 *ct2, const u64 *rlk, u64 *out) {
+    size_t poly = (size_t)l * c->n;
+    u64 *d = (u64 *)malloc(3 * poly * 8);
+    orc_tensor_2x2(c, ct1, ct2, d, l);
+    orc_keyswitch(c, l, d, d + 2 * poly, rlk);
+    memcpy(out, d, 2 * poly * 8);
+    free(d);
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * Galois
+ * ---------------------------------------------------------------------------------------------------- */
+uint32_t orc_galois_elt_from_step(int step, u64 n) {
+    uint32_t m32 = (uint32_t)(2 * n);
+    if (step == 0) return m32 - 1;
+    int sign = step < 0;
+    uint32_t pos = (uint32_t)(step < 0 ? -step : step);
+    if (pos >= (n >> 1)) return 0;
+    pos &= m32 - 1;
+    int s = sign ? (int)(n >> 1) - (int)pos : (int)pos;
+    u64 elt = 1;
+    while (s--) {
+        elt *= 5;
+        elt &= (u64)m32 - 1;
+    }
+    return (uint32_t)elt;
+}
+
+void orc_galois_table(u64 n, uint32_t elt, uint32_t *table) {
+    int logn = 0;
+    while (((u64)1 << logn) < n) logn++;
+    for (u64 i = n; i < 2 * n; i++) {
+        uint32_t rev = bitrev32((uint32_t)i, logn + 1);
+        u64 raw = ((u64)elt * rev) >> 1;
+        raw &= n - 1;
+        table[i - n] = bitrev32((uint32_t)raw, logn);
+    }
+}
+
+void orc_apply_galois_ntt(const orc_ctx *c, const u64 *src, u64 *dst, int l, const uint32_t *table) {
+    size_t n = c->n;
+    for (int i = 0; i < l; i++)
+        for (size_t j = 0; j < n; j++) dst[(size_t)i * n + j] = src[(size_t)i * n + table[j]];
+}
+
+void orc_apply_galois(const orc_ctx *c, int l, u64 *ct, uint32_t elt, const u64 *glk) {
+    size_t n = c->n, poly = (size_t)l * n;
+    uint32_t *table = (uint32_t *)malloc(n * 4);
+    u64 *tmp = (u64 *)malloc(poly * 8);
+    orc_galois_table(n, elt, table);
+    orc_apply_galois_ntt(c, ct, tmp, l, table);
+    memcpy(ct, tmp, poly * 8);
+    orc_apply_galois_ntt(c, ct + poly, tmp, l, table);
+    memset(ct + poly, 0, poly * 8);
+    orc_keyswitch(c, l, ct, tmp, glk);
+    free(table);
+    free(tmp);
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * rescale / mod switch
+ * ---------------------------------------------------------------------------------------------------- */
+void orc_rescale(const orc_ctx *c, int l, u64 *in, int size, u64 *out) {
+    size_t n = c->n;
+    int nl = l - 1;
+    u64 qlast = c->primes[l - 1];
+    for (int s = 0; s < size; s++) {
+        u64 *ci = in + (size_t)s * l * n, *co = out + (size_t)s * nl * n;
+        int last = l - 1;
+        orc_ntt_inverse(c, ci + (size_t)last * n, 1, &last); /* rns.cu:1171 */
+        for (int j = 0; j < nl; j++) {
+            u64 q = c->primes[j];
+            for (size_t x = 0; x < n; x++) co[(size_t)j * n + x] = ci[(size_t)last * n + x] % q; /* :1174 */
+        }
+        int idx[64];
+        for (int j = 0; j < nl; j++) idx[j] = j;
+        orc_ntt_forward(c, co, nl, idx); /* :1178 */
+        for (int j = 0; j < nl; j++) {
+            u64 q = c->primes[j];
+            u64 inv = orc_invmod(qlast % q, q);
+            for (size_t x = 0; x < n; x++) {
+                size_t k = (size_t)j * n + x;
+                co[k] = orc_mulmod(submod(ci[k], co[k], q), inv, q); /* :1154-1155 */
+            }
+        }
+    }
+}
+
+void orc_mod_switch_drop(const orc_ctx *c, int l, const u64 *in, int size, u64 *out) {
+    size_t n = c->n;
+    for (int s = 0; s < size; s++)
+        memcpy(out + (size_t)s * (l - 1) * n, in + (size_t)s * l * n, (size_t)(l - 1) * n * 8);
+}
+
+void orc_divide_round_q_last(const orc_ctx *c, int l, const u64 *in, int size, u64 *out) {
+    size_t n = c->n;
+    int nl = l - 1;
+    u64 qlast = c->primes[l - 1];
+    for (int s = 0; s < size; s++) {
+        const u64 *ci = in + (size_t)s * l * n;
+        u64 *co = out + (size_t)s * nl * n;
+        for (int j = 0; j < nl; j++) {
+            u64 q = c->primes[j];
+            u64 inv = orc_invmod(qlast % q, q);
+            for (size_t x = 0; x < n; x++) {
+                u64 r = ci[(size_t)nl * n + x] % q;
+                co[(size_t)j * n + x] = orc_mulmod(submod(ci[(size_t)j * n + x], r, q), inv, q);
+            }
+        }
+    }
+}
+
+void orc_bgv_mod_switch(const orc_ctx *c, int l, u64 *in, int size, u64 *out) {
+    size_t n = c->n;
+    int nl = l - 1;
+    u64 qlast = c->primes[l - 1], t = c->t;
+    u64 inv_qlast_t = orc_invmod(qlast % t, t);
+    int idx[64];
+    for (int j = 0; j < l; j++) idx[j] = j;
+    for (int s = 0; s < size; s++) {
+        u64 *ci = in + (size_t)s * l * n, *co = out + (size_t)s * nl * n;
+        orc_ntt_inverse(c, ci, l, idx);
+        const u64 *clast = ci + (size_t)nl * n;
+        for (int j = 0; j < nl; j++) {
+            u64 q = c->primes[j];
+            u64 inv = orc_invmod(qlast % q, q);
+            u64 qlast_q = qlast % q;
+            for (size_t x = 0; x < n; x++) {
+                u64 v = clast[x];
+                u64 delta = v % q;
+                u64 tmp = orc_mulmod(v % t, inv_qlast_t, t);
+                u64 corr = orc_mulmod(tmp, qlast_q, q);
+                u64 r = submod(ci[(size_t)j * n + x], delta, q);
+                r = addmod(r, corr, q);
+                co[(size_t)j * n + x] = orc_mulmod(r, inv, q);
+            }
+        }
+        orc_ntt_forward(c, co, nl, idx);
+    }
+}

@@ -1,0 +1,429 @@
+/*
+ * ref_shim.cu -- thin C-ABI harness around the UNMODIFIED reference (encryptorion-lab/phantom-fhe).
+ * TEST / BENCH INFRASTRUCTURE ONLY.  Compiled by oracle/Makefile.ref together with the reference's own
+ * sources (from /root/reference, never copied) into oracle/_ref/libphantom_ref.so.
+ *
+ * Purpose: (1) host-only table generators (primes, NTT tables, base-conversion matrices) to pin the CPU
+ * oracle in this GPU-less container, (2) on the GPU box: run the reference's public API
+ * (multiply_inplace, relinearize_inplace, rotate_inplace, rescale_to_next, mod_switch_to_next,
+ * nwt_2d_radix8_*) on caller-supplied words so the B200 engine can be compared bit for bit, and time the
+ * same calls with the reference's own method (cudaEvent pair around the op on a fresh copy,
+ * benchmark/ckks_bench.cu:167-176).  Contains no arithmetic of its own.
+ */
+#include <algorithm>
+#include <chrono>
+#include <cstring>
+#include <memory>
+#include <vector>
+
+#include "phantom.h"
+
+using namespace phantom;
+using namespace phantom::arith;
+using namespace phantom::util;
+
+#define SHIM_TRY try {
+#define SHIM_CATCH                                                                                       \
+    }                                                                                                    \
+    catch (const std::exception &e) {                                                                    \
+        snprintf(g_err, sizeof(g_err), "%s", e.what());                                                  \
+        return -1;                                                                                       \
+    }
+
+static char g_err[512] = {0};
+
+struct RefCtx {
+    std::unique_ptr<PhantomContext> ctx;
+    std::unique_ptr<PhantomSecretKey> sk;
+    std::unique_ptr<PhantomRelinKey> rlk;
+    std::unique_ptr<PhantomGaloisKey> glk;
+    scheme_type scheme;
+    size_t n, size_QP, size_P;
+    double scale;
+};
+
+static PhantomCiphertext make_ct(RefCtx *h, size_t chain_index, size_t size, const uint64_t *host, bool ntt) {
+    const auto &s = cudaStreamPerThread;
+    PhantomCiphertext ct;
+    ct.resize(*h->ctx, chain_index, size, s);
+    ct.set_ntt_form(ntt);
+    ct.set_scale(h->scale);
+    size_t words = size * ct.coeff_modulus_size() * ct.poly_modulus_degree();
+    cudaMemcpyAsync(ct.data(), host, words * sizeof(uint64_t), cudaMemcpyHostToDevice, s);
+    cudaStreamSynchronize(s);
+    return ct;
+}
+
+static void fetch_ct(const PhantomCiphertext &ct, uint64_t *host) {
+    size_t words = ct.size() * ct.coeff_modulus_size() * ct.poly_modulus_degree();
+    cudaStreamSynchronize(cudaStreamPerThread);
+    cudaMemcpy(host, ct.data(), words * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+}
+
+extern "C" {
+
+const char *ref_last_error() { return g_err; }
+
+/* ---------------------------------------------------------------------------------------------------
+ * host-only (no CUDA calls; usable without a GPU)
+ * ------------------------------------------------------------------------------------------------- */
+int ref_host_create_primes(size_t n, const int *bit_sizes, int count, uint64_t *out) {
+    SHIM_TRY
+    std::vector<int> bits(bit_sizes, bit_sizes + count);
+    auto mods = CoeffModulus::Create(n, bits);
+    for (int i = 0; i < count; i++) out[i] = mods[i].value();
+    return 0;
+    SHIM_CATCH
+}
+
+/* tw/tws/itw/itws: n words each; misc = {root, n_inv, n_inv_shoup, ratio0, ratio1, ratio2} */
+int ref_host_ntt_table(int log_n, uint64_t q, uint64_t *tw, uint64_t *tws, uint64_t *itw, uint64_t *itws,
+                       uint64_t *misc) {
+    SHIM_TRY
+    Modulus mod(q);
+    NTT t(log_n, mod);
+    size_t n = size_t(1) << log_n;
+    memcpy(tw, t.get_from_root_powers().data(), n * 8);
+    memcpy(tws, t.get_from_root_powers_shoup().data(), n * 8);
+    memcpy(itw, t.get_from_inv_root_powers().data(), n * 8);
+    memcpy(itws, t.get_from_inv_root_powers_shoup().data(), n * 8);
+    misc[0] = t.get_root();
+    misc[1] = t.inv_degree_modulo();
+    misc[2] = t.inv_degree_modulo_shoup();
+    misc[3] = mod.const_ratio()[0];
+    misc[4] = mod.const_ratio()[1];
+    misc[5] = mod.const_ratio()[2];
+    return 0;
+    SHIM_CATCH
+}
+
+/* BaseConverter(ibase, obase): qhat_mod_p = [no][ni], qhatinv_mod_q = [ni] */
+int ref_host_bconv_tables(const uint64_t *ibase, int ni, const uint64_t *obase, int no, uint64_t *qhat_mod_p,
+                          uint64_t *qhatinv_mod_q) {
+    SHIM_TRY
+    std::vector<Modulus> iv, ov;
+    for (int i = 0; i < ni; i++) iv.emplace_back(ibase[i]);
+    for (int j = 0; j < no; j++) ov.emplace_back(obase[j]);
+    RNSBase ib(iv), ob(ov);
+    BaseConverter conv(ib, ob);
+    for (int j = 0; j < no; j++)
+        for (int i = 0; i < ni; i++) qhat_mod_p[j * ni + i] = conv.QHatModp(j)[i];
+    for (int i = 0; i < ni; i++) qhatinv_mod_q[i] = ib.QHatInvModq()[i];
+    return 0;
+    SHIM_CATCH
+}
+
+uint32_t ref_host_galois_elt(int step, size_t n) { return get_elt_from_step(step, n); }
+
+/* ---------------------------------------------------------------------------------------------------
+ * GPU side
+ * ------------------------------------------------------------------------------------------------- */
+void *ref_create(int scheme, size_t n, const uint64_t *primes, int size_QP, int size_P, uint64_t plain_mod,
+                 int mul_tech, const int *galois_steps, int n_steps, double scale, int gen_keys) {
+    try {
+        auto h = new RefCtx();
+        h->scheme = static_cast<scheme_type>(scheme);
+        EncryptionParameters parms(h->scheme);
+        parms.set_poly_modulus_degree(n);
+        std::vector<Modulus> mods;
+        for (int i = 0; i < size_QP; i++) mods.emplace_back(primes[i]);
+        parms.set_coeff_modulus(mods);
+        parms.set_special_modulus_size(size_P);
+        if (h->scheme != scheme_type::ckks) parms.set_plain_modulus(Modulus(plain_mod));
+        if (h->scheme == scheme_type::bfv) parms.set_mul_tech(static_cast<mul_tech_type>(mul_tech));
+        if (n_steps > 0) {
+            std::vector<int> steps(galois_steps, galois_steps + n_steps);
+            parms.set_galois_elts(get_elts_from_steps(steps, n));
+        }
+        h->ctx = std::make_unique<PhantomContext>(parms);
+        h->n = n;
+        h->size_QP = size_QP;
+        h->size_P = size_P;
+        h->scale = scale;
+        if (gen_keys) {
+            h->sk = std::make_unique<PhantomSecretKey>(*h->ctx);
+            h->rlk = std::make_unique<PhantomRelinKey>(h->sk->gen_relinkey(*h->ctx));
+            if (n_steps > 0) h->glk = std::make_unique<PhantomGaloisKey>(h->sk->create_galois_keys(*h->ctx));
+        }
+        cudaStreamSynchronize(cudaStreamPerThread);
+        return h;
+    } catch (const std::exception &e) {
+        snprintf(g_err, sizeof(g_err), "%s", e.what());
+        return nullptr;
+    }
+}
+
+void ref_destroy(void *p) { delete static_cast<RefCtx *>(p); }
+
+int ref_dnum(void *p) {
+    auto h = static_cast<RefCtx *>(p);
+    auto &tool = h->ctx->get_context_data(1).gpu_rns_tool();
+    return (int) tool.v_base_part_Ql_to_compl_part_QlP_conv().size();
+}
+
+int ref_galois_count(void *p) {
+    auto h = static_cast<RefCtx *>(p);
+    return (int) h->ctx->key_galois_tool_->galois_elts().size();
+}
+
+uint32_t ref_galois_elt_at(void *p, int idx) {
+    auto h = static_cast<RefCtx *>(p);
+    return h->ctx->key_galois_tool_->galois_elts().at(idx);
+}
+
+/* key digit d = [2][size_QP][n] words.  which < 0: relin key; which >= 0: galois key index. dir 0 = get. */
+static int key_xfer(RefCtx *h, int which, int d, uint64_t *host, int dir) {
+    uint64_t *const *dev_ptrs =
+            which < 0 ? h->rlk->public_keys_ptr() : h->glk->get_relin_keys(which).public_keys_ptr();
+    uint64_t *ptr = nullptr;
+    cudaMemcpy(&ptr, dev_ptrs + d, sizeof(uint64_t *), cudaMemcpyDeviceToHost);
+    size_t bytes = 2 * h->size_QP * h->n * sizeof(uint64_t);
+    if (dir == 0) cudaMemcpy(host, ptr, bytes, cudaMemcpyDeviceToHost);
+    else cudaMemcpy(ptr, host, bytes, cudaMemcpyHostToDevice);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+}
+
+int ref_key_get(void *p, int which, int d, uint64_t *host) {
+    SHIM_TRY return key_xfer(static_cast<RefCtx *>(p), which, d, host, 0);
+    SHIM_CATCH
+}
+
+int ref_key_set(void *p, int which, int d, const uint64_t *host) {
+    SHIM_TRY return key_xfer(static_cast<RefCtx *>(p), which, d, const_cast<uint64_t *>(host), 1);
+    SHIM_CATCH
+}
+
+/* forward / inverse NTT of `limbs` limbs starting at table row start_idx (in place on host data) */
+int ref_ntt(void *p, uint64_t *host, size_t limbs, size_t start_idx, int inverse) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    size_t words = limbs * h->n;
+    auto buf = make_cuda_auto_ptr<uint64_t>(words, s);
+    cudaMemcpyAsync(buf.get(), host, words * 8, cudaMemcpyHostToDevice, s);
+    if (inverse) nwt_2d_radix8_backward_inplace(buf.get(), h->ctx->gpu_rns_tables(), limbs, start_idx, s);
+    else nwt_2d_radix8_forward_inplace(buf.get(), h->ctx->gpu_rns_tables(), limbs, start_idx, s);
+    cudaMemcpyAsync(host, buf.get(), words * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+/* multiply_inplace + relinearize_inplace (evaluate.cu:1029-1057,1342-1374).  ct = [2][l][n] */
+int ref_multiply_relin(void *p, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    bool ntt = h->scheme != scheme_type::bfv;
+    auto a = make_ct(h, chain_index, 2, ct1, ntt);
+    auto b = make_ct(h, chain_index, 2, ct2, ntt);
+    multiply_inplace(*h->ctx, a, b);
+    relinearize_inplace(*h->ctx, a, *h->rlk);
+    fetch_ct(a, out);
+    return 0;
+    SHIM_CATCH
+}
+
+/* multiply_inplace only: out = [3][l][n] */
+int ref_multiply(void *p, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    bool ntt = h->scheme != scheme_type::bfv;
+    auto a = make_ct(h, chain_index, 2, ct1, ntt);
+    auto b = make_ct(h, chain_index, 2, ct2, ntt);
+    multiply_inplace(*h->ctx, a, b);
+    fetch_ct(a, out);
+    return 0;
+    SHIM_CATCH
+}
+
+/* stage-wise key-switch taps (eval_key_switch.cu:95-182) for differential debugging */
+int ref_modup(void *p, size_t chain_index, const uint64_t *c2, uint64_t *t_mod_up) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto &tool = h->ctx->get_context_data(chain_index).gpu_rns_tool();
+    size_t l = tool.base_Ql().size(), m = l + h->size_P, beta = tool.v_base_part_Ql_to_compl_part_QlP_conv().size();
+    auto in = make_cuda_auto_ptr<uint64_t>(l * h->n, s);
+    auto out = make_cuda_auto_ptr<uint64_t>(beta * m * h->n, s);
+    cudaMemcpyAsync(in.get(), c2, l * h->n * 8, cudaMemcpyHostToDevice, s);
+    tool.modup(out.get(), in.get(), h->ctx->gpu_rns_tables(), h->scheme, s);
+    cudaMemcpyAsync(t_mod_up, out.get(), beta * m * h->n * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return 0;
+    SHIM_CATCH
+}
+
+int ref_inner_prod(void *p, size_t chain_index, int which_key, const uint64_t *t_mod_up, uint64_t *cx) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto &tool = h->ctx->get_context_data(chain_index).gpu_rns_tool();
+    size_t l = tool.base_Ql().size(), m = l + h->size_P, beta = tool.v_base_part_Ql_to_compl_part_QlP_conv().size();
+    auto in = make_cuda_auto_ptr<uint64_t>(beta * m * h->n, s);
+    auto out = make_cuda_auto_ptr<uint64_t>(2 * m * h->n, s);
+    cudaMemcpyAsync(in.get(), t_mod_up, beta * m * h->n * 8, cudaMemcpyHostToDevice, s);
+    auto keys = which_key < 0 ? h->rlk->public_keys_ptr() : h->glk->get_relin_keys(which_key).public_keys_ptr();
+    key_switch_inner_prod(out.get(), in.get(), keys, tool, h->ctx->gpu_rns_tables().modulus(), 0, s);
+    cudaMemcpyAsync(cx, out.get(), 2 * m * h->n * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return 0;
+    SHIM_CATCH
+}
+
+/* moddown_from_NTT(cx_i, cx_i): returns the first l limbs */
+int ref_moddown(void *p, size_t chain_index, const uint64_t *cx_i, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto &tool = h->ctx->get_context_data(chain_index).gpu_rns_tool();
+    size_t l = tool.base_Ql().size(), m = l + h->size_P;
+    auto buf = make_cuda_auto_ptr<uint64_t>(m * h->n, s);
+    cudaMemcpyAsync(buf.get(), cx_i, m * h->n * 8, cudaMemcpyHostToDevice, s);
+    tool.moddown_from_NTT(buf.get(), buf.get(), h->ctx->gpu_rns_tables(), h->scheme, s);
+    cudaMemcpyAsync(out, buf.get(), l * h->n * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return 0;
+    SHIM_CATCH
+}
+
+/* rotate_inplace (evaluate.cu:1633-1668) */
+int ref_rotate(void *p, size_t chain_index, const uint64_t *ct, int step, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto a = make_ct(h, chain_index, 2, ct, h->scheme != scheme_type::bfv);
+    rotate_inplace(*h->ctx, a, step, *h->glk);
+    fetch_ct(a, out);
+    return 0;
+    SHIM_CATCH
+}
+
+/* rescale_to_next (CKKS) / mod_switch_to_next; out = [size][l-1][n] */
+int ref_rescale(void *p, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto a = make_ct(h, chain_index, size, ct, h->scheme != scheme_type::bfv);
+    auto r = rescale_to_next(*h->ctx, a);
+    fetch_ct(r, out);
+    return 0;
+    SHIM_CATCH
+}
+
+int ref_mod_switch(void *p, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto a = make_ct(h, chain_index, size, ct, h->scheme != scheme_type::bfv);
+    auto r = mod_switch_to_next(*h->ctx, a);
+    fetch_ct(r, out);
+    return 0;
+    SHIM_CATCH
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * timing, the reference's own method: cudaEvent pair around the op on a fresh copy
+ * (include/cuda_wrapper.cuh:191-283, benchmark/ckks_bench.cu:167-176).  times_us has `trials` entries.
+ * op: 0 = multiply+relin, 1 = rotate(step), 2 = rescale (after mult+relin outside the timer as in the
+ * bench), 3 = forward NTT of `aux` limbs, 4 = inverse NTT of `aux` limbs
+ * mode 0: device-resident inputs (the reference bench's timed region)
+ * mode 1: end-to-end from pinned host buffers: H2D of the inputs, op, D2H of the result, all inside the
+ *         timed region (wall clock around stream sync).
+ * ------------------------------------------------------------------------------------------------- */
+int ref_time_op(void *p, int op, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, int aux, int mode,
+                int trials, double *times_us) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    bool ntt = h->scheme != scheme_type::bfv;
+    cudaEvent_t e0, e1;
+    cudaEventCreate(&e0);
+    cudaEventCreate(&e1);
+    if (op == 3 || op == 4) {
+        size_t limbs = aux, words = limbs * h->n;
+        auto buf = make_cuda_auto_ptr<uint64_t>(words, s);
+        cudaMemsetAsync(buf.get(), 0, words * 8, s);
+        for (int t = 0; t < trials; t++) {
+            cudaEventRecord(e0, s);
+            if (op == 3) nwt_2d_radix8_forward_inplace(buf.get(), h->ctx->gpu_rns_tables(), limbs, 0, s);
+            else nwt_2d_radix8_backward_inplace(buf.get(), h->ctx->gpu_rns_tables(), limbs, 0, s);
+            cudaEventRecord(e1, s);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            times_us[t] = ms * 1000.0;
+        }
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        return 0;
+    }
+    auto a0 = make_ct(h, chain_index, 2, ct1, ntt);
+    auto b0 = make_ct(h, chain_index, 2, ct2 ? ct2 : ct1, ntt);
+    size_t words = 2 * a0.coeff_modulus_size() * h->n;
+    uint64_t *pin_a = nullptr, *pin_b = nullptr, *pin_o = nullptr;
+    if (mode == 1) {
+        cudaMallocHost(&pin_a, words * 8);
+        cudaMallocHost(&pin_b, words * 8);
+        cudaMallocHost(&pin_o, words * 8);
+        memcpy(pin_a, ct1, words * 8);
+        memcpy(pin_b, ct2 ? ct2 : ct1, words * 8);
+    }
+    for (int t = 0; t < trials; t++) {
+        if (mode == 0) {
+            PhantomCiphertext tmp(a0);
+            if (op == 2) {
+                multiply_inplace(*h->ctx, tmp, b0);
+                relinearize_inplace(*h->ctx, tmp, *h->rlk);
+            }
+            cudaEventRecord(e0, s);
+            if (op == 0) {
+                multiply_inplace(*h->ctx, tmp, b0);
+                relinearize_inplace(*h->ctx, tmp, *h->rlk);
+            } else if (op == 1) {
+                rotate_inplace(*h->ctx, tmp, aux, *h->glk);
+            } else if (op == 2) {
+                auto r = rescale_to_next(*h->ctx, tmp);
+            }
+            cudaEventRecord(e1, s);
+            cudaEventSynchronize(e1);
+            float ms;
+            cudaEventElapsedTime(&ms, e0, e1);
+            times_us[t] = ms * 1000.0;
+        } else {
+            cudaStreamSynchronize(s);
+            auto w0 = std::chrono::steady_clock::now();
+            PhantomCiphertext a, b;
+            a.resize(*h->ctx, chain_index, 2, s);
+            a.set_ntt_form(ntt);
+            a.set_scale(h->scale);
+            cudaMemcpyAsync(a.data(), pin_a, words * 8, cudaMemcpyHostToDevice, s);
+            size_t out_words = words;
+            if (op == 0) {
+                b.resize(*h->ctx, chain_index, 2, s);
+                b.set_ntt_form(ntt);
+                b.set_scale(h->scale);
+                cudaMemcpyAsync(b.data(), pin_b, words * 8, cudaMemcpyHostToDevice, s);
+                multiply_inplace(*h->ctx, a, b);
+                relinearize_inplace(*h->ctx, a, *h->rlk);
+                cudaMemcpyAsync(pin_o, a.data(), out_words * 8, cudaMemcpyDeviceToHost, s);
+            } else if (op == 1) {
+                rotate_inplace(*h->ctx, a, aux, *h->glk);
+                cudaMemcpyAsync(pin_o, a.data(), out_words * 8, cudaMemcpyDeviceToHost, s);
+            } else {
+                auto r = rescale_to_next(*h->ctx, a);
+                out_words = 2 * r.coeff_modulus_size() * h->n;
+                cudaMemcpyAsync(pin_o, r.data(), out_words * 8, cudaMemcpyDeviceToHost, s);
+                cudaStreamSynchronize(s);
+            }
+            cudaStreamSynchronize(s);
+            auto w1 = std::chrono::steady_clock::now();
+            times_us[t] = std::chrono::duration<double, std::micro>(w1 - w0).count();
+        }
+    }
+    if (pin_a) cudaFreeHost(pin_a);
+    if (pin_b) cudaFreeHost(pin_b);
+    if (pin_o) cudaFreeHost(pin_o);
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+} // extern "C"
