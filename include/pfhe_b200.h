@@ -1,0 +1,153 @@
+/*
+ * pfhe_b200.h -- C-ABI of the B200-native RNS polynomial-arithmetic engine (libpfhe_b200.so).
+ *
+ * Drop-in boundary for the hot path of encryptorion-lab/phantom-fhe: every entry
+ * point replaces one reference function and keeps its argument meaning; the reference-side binding a
+ * maintainer would add is shown in INTEGRATION.md.  Conventions (same as the reference's kernel-level
+ * interface, include/ntt.cuh:157-226, include/rns.cuh:156-205, include/evaluate.cuh:18-32):
+ *
+ *   - all data pointers are DEVICE pointers to uint64 words laid out [poly][limb][coeff]
+ *     (include/ciphertext.h:15-25); `stream` is a cudaStream_t passed as void*;
+ *   - calls enqueue work on `stream` and return without synchronising;
+ *   - `chain_index` follows PhantomCiphertext::chain_index(): 1 = top data level, level c has
+ *     size_Q - (c - 1) limbs (src/context.cu:145-159, src/eval_key_switch.cu:125,130);
+ *   - switching keys are passed exactly as PhantomRelinKey::public_keys_ptr() (include/secretkey.h:102-127):
+ *     a DEVICE array of dnum device pointers, each to a [2][size_QP][N] buffer in NTT form;
+ *   - errors: the reference throws std::invalid_argument / std::logic_error / std::runtime_error("CUDA
+ *     Runtime Error"); here every call returns a status code and pfhe_last_error() holds the message so the
+ *     C++ shim can re-throw the same exception type.
+ *   - the *_host entry points take HOST buffers and perform the host<->device copies on `stream`
+ *     (used for end-to-end measurement; pass pinned memory for asynchronous copies).
+ *
+ * There is no CPU fallback: without a CUDA device every call fails with PFHE_ERR_CUDA.
+ */
+#ifndef PFHE_B200_H
+#define PFHE_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pfhe_engine pfhe_engine;
+
+enum {
+    PFHE_OK = 0,
+    PFHE_ERR_INVALID_ARGUMENT = 1, /* reference: std::invalid_argument */
+    PFHE_ERR_LOGIC = 2,            /* reference: std::logic_error      */
+    PFHE_ERR_CUDA = 3,             /* reference: std::runtime_error("CUDA Runtime Error") */
+    PFHE_ERR_UNSUPPORTED = 4
+};
+
+enum { PFHE_SCHEME_BGV = 1, PFHE_SCHEME_BFV = 2, PFHE_SCHEME_CKKS = 3 }; /* host/encryptionparams.h:14-22 */
+
+/* thread-local message of the last failing call */
+const char *pfhe_last_error(void);
+
+/* ---- context (replaces PhantomContext::PhantomContext, src/context.cu:121-232, for this path) -------- */
+/* CoeffModulus::Create (src/host/modulus.cu:79-110): primes for the given bit sizes, host output */
+int pfhe_create_primes(uint64_t n, const int *bit_sizes, int count, uint64_t *primes_out);
+/* primes = key-level chain: size_QP - size_P data primes followed by size_P special primes
+ * (EncryptionParameters::set_coeff_modulus + set_special_modulus_size, host/encryptionparams.h:92-135);
+ * galois_elts as EncryptionParameters::set_galois_elts (may be NULL/0) */
+int pfhe_engine_create(pfhe_engine **out, int scheme, uint64_t n, const uint64_t *primes, int size_QP, int size_P,
+                       uint64_t plain_modulus, const uint32_t *galois_elts, int n_galois);
+void pfhe_engine_destroy(pfhe_engine *e);
+uint64_t pfhe_poly_degree(const pfhe_engine *e);
+int pfhe_size_QP(const pfhe_engine *e);
+int pfhe_size_P(const pfhe_engine *e);
+int pfhe_dnum(const pfhe_engine *e, size_t chain_index); /* beta at that level, src/rns.cu:152 */
+/* get_elt_from_step (include/galois.cuh:16-49) */
+int pfhe_galois_elt_from_step(int step, uint64_t n, uint32_t *elt_out);
+
+/* ---- NTT (replaces include/ntt.cuh:172-226) --------------------------------------------------------- */
+/* nwt_2d_radix8_forward_inplace (src/ntt/fntt_2d.cu:620-653) */
+int pfhe_ntt_forward_inplace(pfhe_engine *e, uint64_t *inout, size_t coeff_modulus_size, size_t start_modulus_idx,
+                             void *stream);
+/* nwt_2d_radix8_backward_inplace (src/ntt/intt_2d.cu:724-757) */
+int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t coeff_modulus_size, size_t start_modulus_idx,
+                              void *stream);
+/* nwt_2d_radix8_backward (out of place, src/ntt/ntt_modup.cu:320-354) */
+int pfhe_ntt_backward(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t coeff_modulus_size,
+                      size_t start_modulus_idx, void *stream);
+/* nwt_2d_radix8_forward_inplace_include_special_mod (src/ntt/fntt_2d.cu:694-736): limbs
+ * [start, start+count) of a packed Ql u P buffer, P limbs use table rows size_QP - size_P + ... */
+int pfhe_ntt_forward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t coeff_modulus_size,
+                                                 size_t start_modulus_idx, size_t size_QP, size_t size_P,
+                                                 void *stream);
+int pfhe_ntt_backward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t coeff_modulus_size,
+                                                  size_t start_modulus_idx, size_t size_QP, size_t size_P,
+                                                  void *stream);
+
+/* ---- dyadic kernels (replace the __global__ symbols evaluate.cu launches, include/polymath.cuh) ------ */
+/* tensor_prod_2x2_rns_poly (src/polymath.cu:463-498); result = [3][l][n], may alias operand1 */
+int pfhe_tensor_prod_2x2(pfhe_engine *e, const uint64_t *operand1, const uint64_t *operand2, uint64_t *result,
+                         size_t coeff_mod_size, void *stream);
+/* tensor_square_2x2_rns_poly (:500-532) */
+int pfhe_tensor_square_2x2(pfhe_engine *e, const uint64_t *operand, uint64_t *result, size_t coeff_mod_size,
+                           void *stream);
+/* add_rns_poly / sub_rns_poly / multiply_rns_poly / negate_rns_poly (:17-173) on `coeff_mod_size` limbs */
+int pfhe_add_rns_poly(pfhe_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *result, size_t coeff_mod_size,
+                      void *stream);
+int pfhe_sub_rns_poly(pfhe_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *result, size_t coeff_mod_size,
+                      void *stream);
+int pfhe_multiply_rns_poly(pfhe_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *result,
+                           size_t coeff_mod_size, void *stream);
+int pfhe_negate_rns_poly(pfhe_engine *e, const uint64_t *a, uint64_t *result, size_t coeff_mod_size, void *stream);
+
+/* ---- key switching (replaces DRNSTool::modup / moddown_from_NTT, key_switch_inner_prod, keyswitch_inplace) */
+/* DRNSTool::modup (src/rns_bconv.cu:530-628): dst = [beta][l+alpha][n] */
+int pfhe_modup(pfhe_engine *e, size_t chain_index, uint64_t *dst, const uint64_t *cks, void *stream);
+/* key_switch_inner_prod (src/eval_key_switch.cu:71-92): p_cx = [2][l+alpha][n] */
+int pfhe_key_switch_inner_prod(pfhe_engine *e, size_t chain_index, uint64_t *p_cx, const uint64_t *p_t_mod_up,
+                               const uint64_t *const *rlk, void *stream);
+/* DRNSTool::moddown_from_NTT (src/rns_bconv.cu:776-828): ct_i = [l][n] result, cx_i = [l+alpha][n] (clobbered) */
+int pfhe_moddown_from_ntt(pfhe_engine *e, size_t chain_index, uint64_t *ct_i, uint64_t *cx_i, void *stream);
+/* keyswitch_inplace (src/eval_key_switch.cu:95-182): encrypted[2][l][n] += key-switch of c2[l][n] */
+int pfhe_keyswitch_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, const uint64_t *c2,
+                           const uint64_t *const *relin_keys, void *stream);
+
+/* ---- scheme level (replace the namespace phantom free functions of include/evaluate.cuh:37-245) --------- */
+/* multiply_inplace + relinearize_inplace (src/evaluate.cu:1029-1057,1342-1374), CKKS/BGV:
+ * encrypted1 = [2][l][n] in/out, encrypted2 = [2][l][n] */
+int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted1,
+                                    const uint64_t *encrypted2, const uint64_t *const *relin_keys, void *stream);
+/* multiply_inplace alone: destination = [3][l][n] */
+int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1, const uint64_t *encrypted2,
+                  uint64_t *destination, void *stream);
+/* relinearize_inplace: encrypted = [3][l][n], the first two polynomials are updated */
+int pfhe_relinearize_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted,
+                             const uint64_t *const *relin_keys, void *stream);
+/* apply_galois_inplace (src/evaluate.cu:1567-1630): galois_key = relin-key pointer array of that element */
+int pfhe_apply_galois_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, uint32_t galois_elt,
+                              const uint64_t *const *galois_key, void *stream);
+/* rotate_inplace (src/evaluate.cu:1633-1668) for a step whose element is in the engine's Galois set */
+int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, int step,
+                        const uint64_t *const *galois_key, void *stream);
+/* rescale_to_next (src/evaluate.cu:1545-1565): destination = [size][l-1][n] */
+int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted, size_t size,
+                         uint64_t *destination, void *stream);
+/* mod_switch_to_next (src/evaluate.cu:1505-1543), CKKS: drops the last limb */
+int pfhe_mod_switch_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted, size_t size,
+                            uint64_t *destination, void *stream);
+
+/* ---- host-buffer variants: H2D of the operands, the op, D2H of the result, all on `stream` --------------- */
+int pfhe_multiply_and_relin_host(pfhe_engine *e, size_t chain_index, const uint64_t *h_encrypted1,
+                                 const uint64_t *h_encrypted2, uint64_t *h_destination,
+                                 const uint64_t *const *relin_keys, void *stream);
+int pfhe_rotate_host(pfhe_engine *e, size_t chain_index, const uint64_t *h_encrypted, int step,
+                     uint64_t *h_destination, const uint64_t *const *galois_key, void *stream);
+int pfhe_rescale_host(pfhe_engine *e, size_t chain_index, const uint64_t *h_encrypted, size_t size,
+                      uint64_t *h_destination, void *stream);
+int pfhe_ntt_forward_host(pfhe_engine *e, const uint64_t *h_in, uint64_t *h_out, size_t coeff_modulus_size,
+                          size_t start_modulus_idx, void *stream);
+
+/* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
+uint64_t pfhe_launch_count(const pfhe_engine *e);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -287,6 +287,41 @@ const u64 *orc_itwiddle_shoup(const orc_ctx *c, int i) { return c->itws + (size_
 u64 orc_n_inv(const orc_ctx *c, int i) { return c->ninv[i]; }
 u64 orc_prime(const orc_ctx *c, int i) { return c->primes[i]; }
 
+/* std::mt19937_64 (ISO C++ [rand.predef]: w=64, n=312, m=156, r=31, a=0xb5026f5aa96619e9, u=29,
+ * d=0x5555555555555555, s=17, b=0x71d67fffeda60000, t=37, c=0xfff7eee000000000, l=43, f=6364136223846793005) */
+void orc_mt19937_64_fill(u64 seed, u64 q, u64 *out, size_t count, int mode) {
+    u64 mt[312];
+    int idx = 312;
+    mt[0] = seed;
+    for (int i = 1; i < 312; i++) mt[i] = 6364136223846793005ULL * (mt[i - 1] ^ (mt[i - 1] >> 62)) + (u64)i;
+    int bits = 0;
+    while (bits < 64 && (q >> bits)) bits++;
+    u64 mask = bits >= 64 ? ~(u64)0 : (((u64)1 << bits) - 1);
+    size_t produced = 0;
+    while (produced < count) {
+        if (idx >= 312) {
+            for (int i = 0; i < 312; i++) {
+                u64 x = (mt[i] & 0xFFFFFFFF80000000ULL) | (mt[(i + 1) % 312] & 0x7FFFFFFFULL);
+                u64 xa = x >> 1;
+                if (x & 1) xa ^= 0xB5026F5AA96619E9ULL;
+                mt[i] = mt[(i + 156) % 312] ^ xa;
+            }
+            idx = 0;
+        }
+        u64 y = mt[idx++];
+        y ^= (y >> 29) & 0x5555555555555555ULL;
+        y ^= (y << 17) & 0x71D67FFFEDA60000ULL;
+        y ^= (y << 37) & 0xFFF7EEE000000000ULL;
+        y ^= (y >> 43);
+        if (mode == 0) {
+            out[produced++] = y % q;
+        } else {
+            y &= mask;
+            if (y < q) out[produced++] = y;
+        }
+    }
+}
+
 /* key-level prime index of position j in the packed data-level base Ql ∪ P (fntt_2d.cu:434-436) */
 static inline int qlp_index(const orc_ctx *c, int l, int j) { return j < l ? j : c->size_Q + (j - l); }
 

@@ -1,0 +1,82 @@
+"""ctypes binding of libpfhe_b200.so (include/pfhe_b200.h).  Fails loudly if the CUDA library is missing."""
+import ctypes
+import os
+
+_here = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_here, "libpfhe_b200.so")
+
+if not os.path.exists(LIB_PATH):
+    raise ImportError(
+        f"{LIB_PATH} not found: build the sm_100a extension first (python -c 'import __graft_entry__ as g; g.build()' "
+        "or make -C phantom-fhe_b200/csrc).  This package has no CPU fallback.")
+
+lib = ctypes.CDLL(LIB_PATH)
+
+u64p = ctypes.POINTER(ctypes.c_uint64)
+u32p = ctypes.POINTER(ctypes.c_uint32)
+i32p = ctypes.POINTER(ctypes.c_int)
+vp = ctypes.c_void_p
+sz = ctypes.c_size_t
+
+_sigs = {
+    "pfhe_last_error": (ctypes.c_char_p, []),
+    "pfhe_create_primes": (ctypes.c_int, [ctypes.c_uint64, i32p, ctypes.c_int, u64p]),
+    "pfhe_engine_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_uint64, u64p, ctypes.c_int,
+                                          ctypes.c_int, ctypes.c_uint64, u32p, ctypes.c_int]),
+    "pfhe_engine_destroy": (None, [vp]),
+    "pfhe_poly_degree": (ctypes.c_uint64, [vp]),
+    "pfhe_size_QP": (ctypes.c_int, [vp]),
+    "pfhe_size_P": (ctypes.c_int, [vp]),
+    "pfhe_dnum": (ctypes.c_int, [vp, sz]),
+    "pfhe_galois_elt_from_step": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, u32p]),
+    "pfhe_ntt_forward_inplace": (ctypes.c_int, [vp, vp, sz, sz, vp]),
+    "pfhe_ntt_backward_inplace": (ctypes.c_int, [vp, vp, sz, sz, vp]),
+    "pfhe_ntt_backward": (ctypes.c_int, [vp, vp, vp, sz, sz, vp]),
+    "pfhe_ntt_forward_inplace_include_special_mod": (ctypes.c_int, [vp, vp, sz, sz, sz, sz, vp]),
+    "pfhe_ntt_backward_inplace_include_special_mod": (ctypes.c_int, [vp, vp, sz, sz, sz, sz, vp]),
+    "pfhe_tensor_prod_2x2": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
+    "pfhe_tensor_square_2x2": (ctypes.c_int, [vp, vp, vp, sz, vp]),
+    "pfhe_add_rns_poly": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
+    "pfhe_sub_rns_poly": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
+    "pfhe_multiply_rns_poly": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
+    "pfhe_negate_rns_poly": (ctypes.c_int, [vp, vp, vp, sz, vp]),
+    "pfhe_modup": (ctypes.c_int, [vp, sz, vp, vp, vp]),
+    "pfhe_key_switch_inner_prod": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
+    "pfhe_moddown_from_ntt": (ctypes.c_int, [vp, sz, vp, vp, vp]),
+    "pfhe_keyswitch_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
+    "pfhe_multiply_and_relin_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
+    "pfhe_multiply": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
+    "pfhe_relinearize_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp]),
+    "pfhe_apply_galois_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_uint32, vp, vp]),
+    "pfhe_rotate_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_int, vp, vp]),
+    "pfhe_rescale_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_mod_switch_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_multiply_and_relin_host": (ctypes.c_int, [vp, sz, vp, vp, vp, vp, vp]),
+    "pfhe_rotate_host": (ctypes.c_int, [vp, sz, vp, ctypes.c_int, vp, vp, vp]),
+    "pfhe_rescale_host": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_ntt_forward_host": (ctypes.c_int, [vp, vp, vp, sz, sz, vp]),
+    "pfhe_launch_count": (ctypes.c_uint64, [vp]),
+}
+for _name, (_res, _args) in _sigs.items():
+    _f = getattr(lib, _name)   # AttributeError if the library does not export a declared symbol
+    _f.restype = _res
+    _f.argtypes = _args
+
+PFHE_OK, PFHE_ERR_INVALID_ARGUMENT, PFHE_ERR_LOGIC, PFHE_ERR_CUDA, PFHE_ERR_UNSUPPORTED = range(5)
+
+
+class PfheError(RuntimeError):
+    """CUDA failure inside the engine (reference: std::runtime_error("CUDA Runtime Error"))."""
+
+
+def check(status):
+    """Re-raise engine status codes as the exception class the reference throws for the same condition:
+    std::invalid_argument -> ValueError, std::logic_error -> RuntimeError."""
+    if status == PFHE_OK:
+        return
+    msg = lib.pfhe_last_error().decode()
+    if status == PFHE_ERR_INVALID_ARGUMENT:
+        raise ValueError(msg)
+    if status in (PFHE_ERR_LOGIC, PFHE_ERR_UNSUPPORTED):
+        raise RuntimeError(msg)
+    raise PfheError(msg)

@@ -1,0 +1,315 @@
+"""Host-side mirror of the reference's interface for the hot path.
+
+Names, argument meaning and error behaviour follow the reference (paths relative to the reference root):
+EncryptionParameters (include/host/encryptionparams.h), CoeffModulus::Create (src/host/modulus.cu:79-110),
+PhantomContext (include/context.cuh), PhantomCiphertext (include/ciphertext.h), PhantomRelinKey /
+PhantomGaloisKey (include/secretkey.h:99-219) and the evaluator free functions (include/evaluate.cuh:37-245).
+Where the reference throws std::invalid_argument this raises ValueError with the same message;
+std::logic_error -> RuntimeError.  All arithmetic happens in libpfhe_b200.so on the current CUDA stream.
+"""
+import ctypes
+import enum
+
+import numpy as np
+import torch
+
+from ._lib import lib, check, u64p, u32p, i32p
+
+
+class scheme_type(enum.IntEnum):  # host/encryptionparams.h:14-22
+    none = 0
+    bgv = 1
+    bfv = 2
+    ckks = 3
+
+
+def _stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr())
+
+
+class CoeffModulus:
+    @staticmethod
+    def Create(poly_modulus_degree, bit_sizes):
+        """CoeffModulus::Create (src/host/modulus.cu:79-110)."""
+        bits = (ctypes.c_int * len(bit_sizes))(*bit_sizes)
+        out = (ctypes.c_uint64 * len(bit_sizes))()
+        check(lib.pfhe_create_primes(poly_modulus_degree, bits, len(bit_sizes), out))
+        return [int(v) for v in out]
+
+
+def get_elt_from_step(step, coeff_count):
+    """include/galois.cuh:16-49"""
+    elt = ctypes.c_uint32()
+    check(lib.pfhe_galois_elt_from_step(int(step), int(coeff_count), ctypes.byref(elt)))
+    return int(elt.value)
+
+
+def get_elts_from_steps(steps, coeff_count):
+    return [get_elt_from_step(s, coeff_count) for s in steps]
+
+
+class EncryptionParameters:
+    """include/host/encryptionparams.h:57-150 (the setters the hot path depends on)."""
+
+    def __init__(self, scheme=scheme_type.none):
+        self.scheme = scheme_type(scheme)
+        self.poly_modulus_degree = 0
+        self.coeff_modulus = []
+        self.special_modulus_size = 1  # reference default, encryptionparams.h:235
+        self.galois_elts = []
+        self.plain_modulus = 0
+
+    def set_poly_modulus_degree(self, n):
+        if self.scheme == scheme_type.none and n:
+            raise RuntimeError("poly_modulus_degree is not supported for this scheme")
+        self.poly_modulus_degree = int(n)
+
+    def set_coeff_modulus(self, primes):
+        if self.scheme == scheme_type.none and primes:
+            raise RuntimeError("coeff_modulus is not supported for this scheme")
+        self.coeff_modulus = [int(p) for p in primes]
+
+    def set_special_modulus_size(self, k):
+        self.special_modulus_size = int(k)
+
+    def set_galois_elts(self, elts):
+        self.galois_elts = [int(e) for e in elts]
+
+    def set_plain_modulus(self, t):
+        if self.scheme not in (scheme_type.bfv, scheme_type.bgv) and t:
+            raise RuntimeError("plain_modulus is not supported for this scheme")
+        self.plain_modulus = int(t)
+
+
+class PhantomContext:
+    """Constant tables of the hot path for one parameter set (reference src/context.cu:121-232)."""
+
+    def __init__(self, params):
+        if not torch.cuda.is_available():
+            raise RuntimeError("CUDA Runtime Error: no CUDA device (phantom-fhe_b200 has no CPU path)")
+        self.parms = params
+        self.poly_degree = params.poly_modulus_degree
+        self.size_QP = len(params.coeff_modulus)
+        self.size_P = params.special_modulus_size
+        self.size_Q = self.size_QP - self.size_P
+        self.scheme = params.scheme
+        primes = (ctypes.c_uint64 * self.size_QP)(*params.coeff_modulus)
+        elts = (ctypes.c_uint32 * max(1, len(params.galois_elts)))(*params.galois_elts)
+        handle = ctypes.c_void_p()
+        check(lib.pfhe_engine_create(ctypes.byref(handle), int(params.scheme), self.poly_degree, primes, self.size_QP,
+                                     self.size_P, params.plain_modulus, elts, len(params.galois_elts)))
+        self._h = handle
+        self.device = torch.device("cuda", torch.cuda.current_device())
+
+    def __del__(self):
+        h = getattr(self, "_h", None)
+        if h:
+            lib.pfhe_engine_destroy(h)
+            self._h = None
+
+    def get_first_index(self):
+        return 1
+
+    def coeff_modulus_size(self, chain_index):
+        if chain_index < 1 or chain_index > self.size_Q:
+            raise ValueError("index is invalid!")
+        return self.size_Q - (chain_index - 1)
+
+    def dnum(self, chain_index=1):
+        return lib.pfhe_dnum(self._h, chain_index)
+
+    def launch_count(self):
+        return int(lib.pfhe_launch_count(self._h))
+
+
+def _to_dev(host_u64, device):
+    a = np.ascontiguousarray(host_u64, dtype=np.uint64)
+    return torch.from_numpy(a.view(np.int64)).to(device)
+
+
+class PhantomCiphertext:
+    """[size][coeff_modulus_size][poly_modulus_degree] uint64 words on the device (include/ciphertext.h:15-25)."""
+
+    def __init__(self, context=None, data=None, chain_index=1, scale=1.0, is_ntt_form=True):
+        self.data = data
+        self.chain_index = chain_index
+        self.scale = scale
+        self.is_ntt_form = is_ntt_form
+        self.correction_factor = 1
+
+    @classmethod
+    def from_host(cls, context, words, chain_index=1, scale=1.0, is_ntt_form=True):
+        l = context.coeff_modulus_size(chain_index)
+        words = np.asarray(words, dtype=np.uint64).reshape(-1, l, context.poly_degree)
+        return cls(context, _to_dev(words, context.device), chain_index, scale, is_ntt_form)
+
+    def to_host(self):
+        torch.cuda.current_stream().synchronize()
+        return self.data.cpu().numpy().view(np.uint64)
+
+    def size(self):
+        return 0 if self.data is None else self.data.shape[0]
+
+    def coeff_modulus_size(self):
+        return self.data.shape[1]
+
+    def clone(self):
+        return PhantomCiphertext(None, self.data.clone(), self.chain_index, self.scale, self.is_ntt_form)
+
+
+class PhantomRelinKey:
+    """dnum device buffers [2][size_QP][N] in NTT form + a device array of their addresses
+    (include/secretkey.h:102-127, public_keys_ptr())."""
+
+    def __init__(self, context, digits_host):
+        self.digits = [_to_dev(np.asarray(d, dtype=np.uint64).reshape(2, context.size_QP, context.poly_degree),
+                               context.device) for d in digits_host]
+        ptrs = np.array([d.data_ptr() for d in self.digits], dtype=np.uint64)
+        self._ptrs = _to_dev(ptrs, context.device)
+
+    def public_keys_ptr(self):
+        return _ptr(self._ptrs)
+
+
+class PhantomGaloisKey:
+    """Relin keys indexed like the context's Galois elements (include/secretkey.h:168-192)."""
+
+    def __init__(self, context, keys_by_elt):
+        self.relin_keys = [PhantomRelinKey(context, digits) for digits in keys_by_elt]
+
+    def get_relin_keys(self, index):
+        return self.relin_keys[index]
+
+
+# ---------------------------------------------------------------------------------------------------------
+# evaluator (include/evaluate.cuh:37-245)
+# ---------------------------------------------------------------------------------------------------------
+def _require_ntt(context, ct):
+    if context.scheme in (scheme_type.ckks, scheme_type.bgv) and not ct.is_ntt_form:
+        name = "CKKS" if context.scheme == scheme_type.ckks else "BGV"
+        raise ValueError(f"{name} encrypted must be in NTT form")
+
+
+def multiply_inplace(context, encrypted1, encrypted2):
+    """multiply_inplace (src/evaluate.cu:1029-1057 -> bgv_ckks_multiply :345-397)."""
+    if not (encrypted1.is_ntt_form and encrypted2.is_ntt_form):
+        raise ValueError("encrypted1 and encrypted2 must be in NTT form")
+    if encrypted1.chain_index != encrypted2.chain_index:
+        raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+    if encrypted1.size() != 2 or encrypted2.size() != 2:
+        raise ValueError("only size-2 operands are on this path")
+    l, n = encrypted1.coeff_modulus_size(), context.poly_degree
+    dst = torch.empty((3, l, n), dtype=torch.int64, device=encrypted1.data.device)
+    a, b = encrypted1.data, encrypted2.data
+    check(lib.pfhe_multiply(context._h, encrypted1.chain_index, _ptr(a), _ptr(a if encrypted1 is encrypted2 else b),
+                            _ptr(dst), _stream()))
+    encrypted1.data = dst
+    if context.scheme == scheme_type.ckks:
+        encrypted1.scale = encrypted1.scale * encrypted2.scale
+
+
+def relinearize_inplace(context, encrypted, relin_keys):
+    """relinearize_inplace (src/evaluate.cu:1342-1374)."""
+    if encrypted.size() != 3:
+        raise ValueError("destination_size must be 3")
+    _require_ntt(context, encrypted)
+    check(lib.pfhe_relinearize_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data),
+                                       relin_keys.public_keys_ptr(), _stream()))
+    encrypted.data = encrypted.data[:2]
+
+
+def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
+    """multiply_and_relin_inplace (src/evaluate.cu:1061-1104), fused tensor + key-switch."""
+    if not (encrypted1.is_ntt_form and encrypted2.is_ntt_form):
+        raise ValueError("encrypted1 and encrypted2 must be in NTT form")
+    if encrypted1.chain_index != encrypted2.chain_index:
+        raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+    check(lib.pfhe_multiply_and_relin_inplace(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
+                                              _ptr(encrypted2.data), relin_keys.public_keys_ptr(), _stream()))
+    if context.scheme == scheme_type.ckks:
+        encrypted1.scale = encrypted1.scale * encrypted2.scale
+
+
+def apply_galois_inplace(context, encrypted, galois_elt, galois_keys):
+    """apply_galois_inplace (src/evaluate.cu:1567-1630)."""
+    if encrypted.size() > 2:
+        raise ValueError("encrypted size must be 2")
+    elts = context.parms.galois_elts
+    if galois_elt not in elts:
+        raise ValueError("Galois elt not present")
+    key = galois_keys.get_relin_keys(elts.index(galois_elt))
+    check(lib.pfhe_apply_galois_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data), galois_elt,
+                                        key.public_keys_ptr(), _stream()))
+
+
+def _naf(value):
+    """non-adjacent form used by rotate_internal (include/host/numth.h:17-34, src/evaluate.cu:1649)."""
+    res = []
+    sign = value < 0
+    value = abs(value)
+    i = 0
+    while value:
+        zi = 0
+        if value & 1:
+            zi = 2 - (value & 3)
+        value = (value - zi) >> 1
+        if zi:
+            res.append((-1 if sign else 1) * zi * (1 << i))
+        i += 1
+    return res
+
+
+def rotate_inplace(context, encrypted, step, galois_key):
+    """rotate_inplace / rotate_internal (src/evaluate.cu:1633-1668)."""
+    n = context.poly_degree
+    elt = get_elt_from_step(step, n)
+    if elt in context.parms.galois_elts:
+        apply_galois_inplace(context, encrypted, elt, galois_key)
+        return
+    naf_steps = _naf(step)
+    if len(naf_steps) == 1:
+        raise ValueError("Galois key not present")
+    for s in naf_steps:
+        if abs(s) != (n >> 1):
+            rotate_inplace(context, encrypted, s, galois_key)
+
+
+def rescale_to_next(context, encrypted):
+    """rescale_to_next (src/evaluate.cu:1545-1565)."""
+    if context.scheme != scheme_type.ckks:
+        raise ValueError("unsupported scheme")
+    if encrypted.chain_index == context.size_Q:
+        raise ValueError("end of modulus switching chain reached")
+    l, n, size = encrypted.coeff_modulus_size(), context.poly_degree, encrypted.size()
+    dst = torch.empty((size, l - 1, n), dtype=torch.int64, device=encrypted.data.device)
+    check(lib.pfhe_rescale_to_next(context._h, encrypted.chain_index, _ptr(encrypted.data), size, _ptr(dst),
+                                   _stream()))
+    q_last = context.parms.coeff_modulus[l - 1]
+    return PhantomCiphertext(None, dst, encrypted.chain_index + 1, encrypted.scale / float(q_last),
+                             encrypted.is_ntt_form)
+
+
+def mod_switch_to_next(context, encrypted):
+    """mod_switch_to_next (src/evaluate.cu:1505-1543)."""
+    if encrypted.chain_index == context.size_Q:
+        raise ValueError("end of modulus switching chain reached")
+    _require_ntt(context, encrypted)
+    l, n, size = encrypted.coeff_modulus_size(), context.poly_degree, encrypted.size()
+    dst = torch.empty((size, l - 1, n), dtype=torch.int64, device=encrypted.data.device)
+    check(lib.pfhe_mod_switch_to_next(context._h, encrypted.chain_index, _ptr(encrypted.data), size, _ptr(dst),
+                                      _stream()))
+    return PhantomCiphertext(None, dst, encrypted.chain_index + 1, encrypted.scale, encrypted.is_ntt_form)
+
+
+def nwt_2d_radix8_forward_inplace(inout, context, coeff_modulus_size, start_modulus_idx):
+    """include/ntt.cuh:172-173 (tensor of [coeff_modulus_size][N] words)."""
+    check(lib.pfhe_ntt_forward_inplace(context._h, _ptr(inout), coeff_modulus_size, start_modulus_idx, _stream()))
+
+
+def nwt_2d_radix8_backward_inplace(inout, context, coeff_modulus_size, start_modulus_idx):
+    """include/ntt.cuh:203-204"""
+    check(lib.pfhe_ntt_backward_inplace(context._h, _ptr(inout), coeff_modulus_size, start_modulus_idx, _stream()))

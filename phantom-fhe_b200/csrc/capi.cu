@@ -1,0 +1,335 @@
+// capi.cu -- extern "C" boundary (include/pfhe_b200.h).  Translates C++ exceptions of the engine into the
+// status codes documented there; no arithmetic lives here.
+#include "../../include/pfhe_b200.h"
+
+#include <cstring>
+#include <string>
+
+#include "engine.hpp"
+#include "hostmath.hpp"
+
+using namespace pfhe;
+
+struct pfhe_engine {
+    Engine impl;
+    template<class... A>
+    explicit pfhe_engine(A &&...a) : impl(std::forward<A>(a)...) {}
+};
+
+static thread_local std::string g_error;
+
+const char *pfhe_last_error(void) { return g_error.c_str(); }
+
+#define API_BEGIN try {
+#define API_END                                                                                           \
+    return PFHE_OK;                                                                                       \
+    }                                                                                                     \
+    catch (const CudaError &ex) {                                                                         \
+        g_error = ex.what();                                                                              \
+        return PFHE_ERR_CUDA;                                                                             \
+    }                                                                                                     \
+    catch (const std::invalid_argument &ex) {                                                             \
+        g_error = ex.what();                                                                              \
+        return PFHE_ERR_INVALID_ARGUMENT;                                                                 \
+    }                                                                                                     \
+    catch (const std::logic_error &ex) {                                                                  \
+        g_error = ex.what();                                                                              \
+        return PFHE_ERR_LOGIC;                                                                            \
+    }                                                                                                     \
+    catch (const std::exception &ex) {                                                                    \
+        g_error = ex.what();                                                                              \
+        return PFHE_ERR_CUDA;                                                                             \
+    }
+
+static cudaStream_t S(void *s) { return static_cast<cudaStream_t>(s); }
+static u64 *U(uint64_t *p) { return reinterpret_cast<u64 *>(p); }
+static const u64 *U(const uint64_t *p) { return reinterpret_cast<const u64 *>(p); }
+static const u64 *const *K(const uint64_t *const *p) { return reinterpret_cast<const u64 *const *>(p); }
+
+static void require(bool ok, const char *msg) {
+    if (!ok) throw std::invalid_argument(msg);
+}
+static void require_ckks_like(const Engine &e) {
+    if (e.scheme() == Scheme::bfv) throw std::invalid_argument("unsupported scheme");   // BFV path: see DESIGN.md
+}
+
+extern "C" {
+
+int pfhe_create_primes(uint64_t n, const int *bit_sizes, int count, uint64_t *primes_out) {
+    API_BEGIN
+    require(bit_sizes && primes_out && count > 0, "bit_sizes is invalid");
+    auto v = host::create_primes(n, std::vector<int>(bit_sizes, bit_sizes + count));
+    for (int i = 0; i < count; i++) primes_out[i] = v[i];
+    API_END
+}
+
+int pfhe_engine_create(pfhe_engine **out, int scheme, uint64_t n, const uint64_t *primes, int size_QP, int size_P,
+                       uint64_t plain_modulus, const uint32_t *galois_elts, int n_galois) {
+    API_BEGIN
+    require(out && primes && size_QP > 0, "coeff_modulus is invalid");
+    require(scheme >= 1 && scheme <= 3, "unsupported scheme");
+    int dev_count = 0;
+    cudaError_t ce = cudaGetDeviceCount(&dev_count);
+    if (ce != cudaSuccess || dev_count == 0)
+        throw CudaError(ce != cudaSuccess ? ce : cudaErrorNoDevice, "pfhe_engine_create: this engine has no CPU path");
+    std::vector<u64> p(primes, primes + size_QP);
+    std::vector<uint32_t> g;
+    if (galois_elts && n_galois > 0) g.assign(galois_elts, galois_elts + n_galois);
+    *out = new pfhe_engine(static_cast<Scheme>(scheme), (size_t) n, p, size_P, (u64) plain_modulus, g);
+    API_END
+}
+
+void pfhe_engine_destroy(pfhe_engine *e) { delete e; }
+uint64_t pfhe_poly_degree(const pfhe_engine *e) { return e->impl.n(); }
+int pfhe_size_QP(const pfhe_engine *e) { return e->impl.size_QP(); }
+int pfhe_size_P(const pfhe_engine *e) { return e->impl.size_P(); }
+int pfhe_dnum(const pfhe_engine *e, size_t chain_index) {
+    try {
+        return e->impl.beta(e->impl.limbs_at(chain_index));
+    } catch (...) { return -1; }
+}
+uint64_t pfhe_launch_count(const pfhe_engine *) { return g_launches.load(); }
+
+int pfhe_galois_elt_from_step(int step, uint64_t n, uint32_t *elt_out) {
+    API_BEGIN
+    // get_elt_from_step, include/galois.cuh:16-49
+    const uint32_t m32 = (uint32_t) (2 * n);
+    if (step == 0) {
+        *elt_out = m32 - 1;
+    } else {
+        const bool neg = step < 0;
+        uint32_t pos = (uint32_t) (neg ? -step : step);
+        require(pos < (n >> 1), "step count too large");
+        pos &= m32 - 1;
+        int s = neg ? (int) (n >> 1) - (int) pos : (int) pos;
+        uint64_t elt = 1;
+        while (s--) elt = (elt * 5) & ((uint64_t) m32 - 1);
+        *elt_out = (uint32_t) elt;
+    }
+    API_END
+}
+
+// ---- NTT --------------------------------------------------------------------------------------------
+int pfhe_ntt_forward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, void *stream) {
+    API_BEGIN
+    require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
+    // reference semantics: limb i of the buffer (0-based from `inout`) uses table row start+i
+    e->impl.ntt_fwd_rows_range(U(inout), (int) count, (int) start, S(stream));
+    API_END
+}
+
+int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, void *stream) {
+    API_BEGIN
+    require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
+    e->impl.ntt_inv_rows_range(U(inout), U(inout), (int) count, (int) start, S(stream));
+    API_END
+}
+
+int pfhe_ntt_backward(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t count, size_t start, void *stream) {
+    API_BEGIN
+    require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
+    e->impl.ntt_inv_rows_range(U(out), U(in), (int) count, (int) start, S(stream));
+    API_END
+}
+
+// the reference's "include_special_mod" launchers address limb (start+i) of the buffer and map it to
+// table row (start+i) if it is below size_Ql = coeff_modulus_size_total - size_P ... : with its calling
+// convention (fntt_2d.cu:434-436) limb index t of the packed buffer uses row t for t < size_QlP - size_P and
+// row size_QP - size_QlP + t otherwise, where size_QlP = start + count at every reference call site.
+static void special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, size_t size_QP, size_t size_P,
+                        bool inverse, void *stream) {
+    require((int) size_QP == e->impl.size_QP() && (int) size_P == e->impl.size_P(), "size_QP/size_P mismatch");
+    const size_t size_QlP = start + count;
+    require(size_QlP >= size_P && size_QlP <= size_QP, "modulus index out of range");
+    e->impl.ntt_special_range(U(inout), (int) count, (int) start, (int) (size_QlP - size_P), inverse, S(stream));
+}
+
+int pfhe_ntt_forward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t start,
+                                                 size_t size_QP, size_t size_P, void *stream) {
+    API_BEGIN
+    special_mod(e, inout, count, start, size_QP, size_P, false, stream);
+    API_END
+}
+
+int pfhe_ntt_backward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t start,
+                                                  size_t size_QP, size_t size_P, void *stream) {
+    API_BEGIN
+    special_mod(e, inout, count, start, size_QP, size_P, true, stream);
+    API_END
+}
+
+// ---- dyadic -----------------------------------------------------------------------------------------
+int pfhe_tensor_prod_2x2(pfhe_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *r, size_t l, void *stream) {
+    API_BEGIN
+    require(l >= 1 && l <= (size_t) e->impl.size_QP(), "coeff_mod_size is invalid");
+    e->impl.tensor_2x2(U(a), U(b), U(r), (int) l, S(stream));
+    API_END
+}
+int pfhe_tensor_square_2x2(pfhe_engine *e, const uint64_t *a, uint64_t *r, size_t l, void *stream) {
+    API_BEGIN
+    require(l >= 1 && l <= (size_t) e->impl.size_QP(), "coeff_mod_size is invalid");
+    e->impl.tensor_square(U(a), U(r), (int) l, S(stream));
+    API_END
+}
+#define EW_API(NAME, OP)                                                                                  \
+    int NAME(pfhe_engine *e, const uint64_t *a, const uint64_t *b, uint64_t *r, size_t l, void *stream) { \
+        API_BEGIN                                                                                         \
+        require(l >= 1 && l <= (size_t) e->impl.size_QP(), "coeff_mod_size is invalid");                  \
+        e->impl.elementwise(OP, U(a), U(b), U(r), (int) l, S(stream));                                    \
+        API_END                                                                                           \
+    }
+EW_API(pfhe_add_rns_poly, EW_ADD)
+EW_API(pfhe_sub_rns_poly, EW_SUB)
+EW_API(pfhe_multiply_rns_poly, EW_MUL)
+int pfhe_negate_rns_poly(pfhe_engine *e, const uint64_t *a, uint64_t *r, size_t l, void *stream) {
+    API_BEGIN
+    require(l >= 1 && l <= (size_t) e->impl.size_QP(), "coeff_mod_size is invalid");
+    e->impl.elementwise(EW_NEG, U(a), nullptr, U(r), (int) l, S(stream));
+    API_END
+}
+
+// ---- key switching ------------------------------------------------------------------------------------
+int pfhe_modup(pfhe_engine *e, size_t chain_index, uint64_t *dst, const uint64_t *cks, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.modup(l, U(dst), U(cks), e->impl.ws().t_cks.p, S(stream));
+    API_END
+}
+int pfhe_key_switch_inner_prod(pfhe_engine *e, size_t chain_index, uint64_t *p_cx, const uint64_t *p_t_mod_up,
+                               const uint64_t *const *rlk, void *stream) {
+    API_BEGIN
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.inner_prod(l, U(p_cx), U(p_t_mod_up), K(rlk), S(stream));
+    API_END
+}
+int pfhe_moddown_from_ntt(pfhe_engine *e, size_t chain_index, uint64_t *ct_i, uint64_t *cx_i, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.moddown(l, U(ct_i), U(cx_i), e->impl.ws().delta.p, 1, nullptr, 0u, S(stream));
+    API_END
+}
+int pfhe_keyswitch_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, const uint64_t *c2,
+                           const uint64_t *const *relin_keys, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.keyswitch(l, U(encrypted), U(c2), K(relin_keys), U(encrypted), S(stream));
+    API_END
+}
+
+// ---- scheme level -------------------------------------------------------------------------------------
+int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct1, const uint64_t *ct2,
+                                    const uint64_t *const *rlk, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.multiply_relin(l, U(ct1), U(ct1), U(ct2), K(rlk), S(stream));
+    API_END
+}
+int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, uint64_t *dst,
+                  void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    if (ct1 == ct2) e->impl.tensor_square(U(ct1), U(dst), l, S(stream));
+    else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
+    API_END
+}
+int pfhe_relinearize_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *const *rlk,
+                             void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    const size_t poly = (size_t) l * e->impl.n();
+    e->impl.keyswitch(l, U(ct), U(ct) + 2 * poly, K(rlk), U(ct), S(stream));
+    API_END
+}
+int pfhe_apply_galois_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, uint32_t elt,
+                              const uint64_t *const *glk, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.apply_galois(l, U(ct), elt, K(glk), S(stream));
+    API_END
+}
+int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, int step, const uint64_t *const *glk,
+                        void *stream) {
+    uint32_t elt = 0;
+    int rc = pfhe_galois_elt_from_step(step, e->impl.n(), &elt);
+    if (rc != PFHE_OK) return rc;
+    return pfhe_apply_galois_inplace(e, chain_index, ct, elt, glk, stream);
+}
+int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *dst,
+                         void *stream) {
+    API_BEGIN
+    require(e->impl.scheme() == Scheme::ckks, "unsupported scheme");
+    require(size >= 1 && size <= 3, "encrypted size is invalid");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.rescale(l, U(dst), U(ct), (int) size, S(stream));
+    API_END
+}
+int pfhe_mod_switch_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *dst,
+                            void *stream) {
+    API_BEGIN
+    require(e->impl.scheme() == Scheme::ckks, "unsupported scheme");   // BFV/BGV variants: DESIGN.md "next"
+    require(size >= 1 && size <= 3, "encrypted size is invalid");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.mod_switch_drop(l, U(dst), U(ct), (int) size, S(stream));
+    API_END
+}
+
+// ---- host-buffer variants ---------------------------------------------------------------------------------
+int pfhe_multiply_and_relin_host(pfhe_engine *e, size_t chain_index, const uint64_t *h1, const uint64_t *h2,
+                                 uint64_t *hout, const uint64_t *const *rlk, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    const size_t words = (size_t) 2 * l * e->impl.n();
+    auto &io = e->impl.host_io(2 * words);
+    PFHE_CUDA(cudaMemcpyAsync(io.p, h1, words * 8, cudaMemcpyHostToDevice, S(stream)));
+    PFHE_CUDA(cudaMemcpyAsync(io.p + words, h2, words * 8, cudaMemcpyHostToDevice, S(stream)));
+    e->impl.multiply_relin(l, io.p, io.p, io.p + words, K(rlk), S(stream));
+    PFHE_CUDA(cudaMemcpyAsync(hout, io.p, words * 8, cudaMemcpyDeviceToHost, S(stream)));
+    API_END
+}
+int pfhe_rotate_host(pfhe_engine *e, size_t chain_index, const uint64_t *h, int step, uint64_t *hout,
+                     const uint64_t *const *glk, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    const size_t words = (size_t) 2 * l * e->impl.n();
+    uint32_t elt = 0;
+    if (pfhe_galois_elt_from_step(step, e->impl.n(), &elt) != PFHE_OK) throw std::invalid_argument(g_error);
+    auto &io = e->impl.host_io(words);
+    PFHE_CUDA(cudaMemcpyAsync(io.p, h, words * 8, cudaMemcpyHostToDevice, S(stream)));
+    e->impl.apply_galois(l, io.p, elt, K(glk), S(stream));
+    PFHE_CUDA(cudaMemcpyAsync(hout, io.p, words * 8, cudaMemcpyDeviceToHost, S(stream)));
+    API_END
+}
+int pfhe_rescale_host(pfhe_engine *e, size_t chain_index, const uint64_t *h, size_t size, uint64_t *hout,
+                      void *stream) {
+    API_BEGIN
+    require(e->impl.scheme() == Scheme::ckks, "unsupported scheme");
+    const int l = e->impl.limbs_at(chain_index);
+    const size_t in_words = size * l * e->impl.n(), out_words = size * (l - 1) * e->impl.n();
+    auto &io = e->impl.host_io(in_words + out_words);
+    PFHE_CUDA(cudaMemcpyAsync(io.p, h, in_words * 8, cudaMemcpyHostToDevice, S(stream)));
+    e->impl.rescale(l, io.p + in_words, io.p, (int) size, S(stream));
+    PFHE_CUDA(cudaMemcpyAsync(hout, io.p + in_words, out_words * 8, cudaMemcpyDeviceToHost, S(stream)));
+    API_END
+}
+int pfhe_ntt_forward_host(pfhe_engine *e, const uint64_t *hin, uint64_t *hout, size_t count, size_t start,
+                          void *stream) {
+    API_BEGIN
+    require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
+    const size_t words = count * e->impl.n();
+    auto &io = e->impl.host_io(words);
+    PFHE_CUDA(cudaMemcpyAsync(io.p, hin, words * 8, cudaMemcpyHostToDevice, S(stream)));
+    e->impl.ntt_fwd_rows_range(io.p, (int) count, (int) start, S(stream));
+    PFHE_CUDA(cudaMemcpyAsync(hout, io.p, words * 8, cudaMemcpyDeviceToHost, S(stream)));
+    API_END
+}
+
+} // extern "C"

@@ -1,0 +1,477 @@
+// engine.cu -- table generation, per-level constants and op sequencing of the B200 RNS engine.
+#include "engine.hpp"
+
+#include <algorithm>
+#include <cstring>
+#include <functional>
+
+#include "hostmath.hpp"
+#include "poly_kernels.cuh"
+
+namespace pfhe {
+
+namespace hm = pfhe::host;
+
+std::atomic<unsigned long long> g_launches{0};
+
+static Tw make_tw(u64 w, u64 q) { return make_ulonglong2(w, hm::shoup(w, q)); }
+
+// launch helper: NTT lists longer than NTT_MAX_LIMBS are cut into chunks
+struct LimbVec {
+    std::vector<short> data, row, src;
+    void push(int d, int r, int s = -1) {
+        data.push_back((short) d), row.push_back((short) r), src.push_back((short) (s < 0 ? d : s));
+    }
+    size_t size() const { return data.size(); }
+    LimbList chunk(size_t begin, size_t &taken) const {
+        LimbList ll{};
+        taken = std::min<size_t>(NTT_MAX_LIMBS, data.size() - begin);
+        ll.count = (int) taken;
+        for (size_t i = 0; i < taken; i++) {
+            ll.data[i] = data[begin + i], ll.row[i] = row[begin + i], ll.src[i] = src[begin + i];
+        }
+        return ll;
+    }
+};
+
+static LimbList single_list(const LimbVec &v) {
+    if (v.size() > NTT_MAX_LIMBS) throw std::logic_error("limb list too long");
+    size_t taken;
+    return v.chunk(0, taken);
+}
+
+// ---------------------------------------------------------------------------------------------------
+Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size_P, u64 plain_modulus,
+               const std::vector<uint32_t> &galois_elts)
+        : scheme_(scheme), n_(n), size_QP_((int) primes.size()), size_P_(size_P), t_(plain_modulus), primes_(primes),
+          galois_elts_(galois_elts) {
+    logn_ = 0;
+    while (((size_t) 1 << logn_) < n_) logn_++;
+    if (((size_t) 1 << logn_) != n_ || logn_ < 12 || logn_ > 17)
+        throw std::invalid_argument("poly_modulus_degree is invalid");   // engine covers the 2-D NTT range 2^12..2^17
+    if (size_QP_ < 1 || size_QP_ > 16384 || size_P_ < 0 || size_P_ >= size_QP_)
+        throw std::invalid_argument("coeff_modulus is invalid");
+    size_Q_ = size_QP_ - size_P_;
+    for (u64 q : primes_) {
+        if (q >> 61 || q < 2 || (q - 1) % (2 * n_) != 0 || !hm::is_prime(q))
+            throw std::invalid_argument("coeff_modulus primes must be NTT-friendly primes of at most 61 bits");
+    }
+    build_tables();
+    levels_.resize(size_Q_ + 1);
+
+    // workspace sized for the top level
+    const size_t alpha = std::max(size_P_, 1);
+    const size_t beta_max = (size_Q_ + alpha - 1) / alpha;
+    ws_.t_cks.alloc((size_t) size_Q_ * n_);
+    ws_.t_mod_up.alloc(beta_max * size_QP_ * n_);
+    ws_.cx.alloc((size_t) 2 * size_QP_ * n_);
+    ws_.delta.alloc((size_t) 2 * size_Q_ * n_);
+    ws_.tmp.alloc((size_t) 3 * size_Q_ * n_);
+
+    // Galois permutation tables (reference include/galois.cuh:98-113)
+    d_perm_.resize(galois_elts_.size());
+    std::vector<uint32_t> table(n_);
+    for (size_t g = 0; g < galois_elts_.size(); g++) {
+        const uint32_t elt = galois_elts_[g];
+        if (!(elt & 1) || elt >= 2 * n_) throw std::invalid_argument("Galois element is not valid");
+        for (size_t i = 0; i < n_; i++) {
+            const uint32_t rev = hm::bit_reverse((uint32_t) (i + n_), logn_ + 1);
+            const u64 raw = (((u64) elt * rev) >> 1) & (n_ - 1);
+            table[i] = hm::bit_reverse((uint32_t) raw, logn_);
+        }
+        d_perm_[g].upload(table);
+    }
+}
+
+Engine::~Engine() = default;
+
+void Engine::build_tables() {
+    std::vector<Tw> tw((size_t) size_QP_ * n_), itw((size_t) size_QP_ * n_), fin((size_t) size_QP_ * 2);
+    std::vector<Modulus> mods(size_QP_);
+    h_ninv_.resize(size_QP_);
+    h_itw1_.resize(size_QP_);
+    for (int i = 0; i < size_QP_; i++) {
+        const u64 q = primes_[i];
+        const auto ratio = hm::barrett_ratio(q);
+        mods[i] = Modulus{q, ratio.lo, ratio.hi};
+        const u64 psi = hm::minimal_primitive_root(2 * n_, q);
+        const u64 ipsi = hm::invmod(psi, q);
+        Tw *f = tw.data() + (size_t) i * n_, *b = itw.data() + (size_t) i * n_;
+        f[0] = b[0] = make_tw(1, q);
+        u64 pw = psi, ipw = ipsi;
+        for (size_t k = 1; k < n_; k++) {
+            // standard position bitrev(k) = 2^s + B  ->  kernel-native position
+            const uint32_t r = hm::bit_reverse((uint32_t) k, logn_);
+            int s = 31 - __builtin_clz(r);
+            const size_t B = r - ((size_t) 1 << s);
+            const size_t pos = tw_native_index(logn_, s, B);
+            f[pos] = make_tw(pw, q);
+            b[pos] = make_tw(ipw, q);
+            if (r == 1) h_itw1_[i] = ipw;
+            pw = hm::mulmod(pw, psi, q);
+            ipw = hm::mulmod(ipw, ipsi, q);
+        }
+        const u64 ninv = hm::invmod(n_ % q, q);
+        h_ninv_[i] = ninv;
+        fin[2 * i] = make_tw(ninv, q);
+        fin[2 * i + 1] = make_tw(hm::mulmod(h_itw1_[i], ninv, q), q);
+    }
+    d_tw_.upload(tw);
+    d_itw_.upload(itw);
+    d_inv_fin_.upload(fin);
+    d_mod_.upload(mods);
+    plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p};
+}
+
+int Engine::limbs_at(size_t chain_index) const {
+    if (chain_index < 1 || chain_index > (size_t) size_Q_) throw std::invalid_argument("index is invalid!");
+    return size_Q_ - (int) (chain_index - 1);
+}
+
+int Engine::galois_index(uint32_t elt) const {
+    auto it = std::find(galois_elts_.begin(), galois_elts_.end(), elt);
+    if (it == galois_elts_.end()) throw std::invalid_argument("Galois elt not present");
+    return (int) (it - galois_elts_.begin());
+}
+
+const Level &Engine::level(int l) const {
+    if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
+    auto &slot = const_cast<Engine *>(this)->levels_[l];
+    if (!slot) const_cast<Engine *>(this)->build_level(l);
+    return *slot;
+}
+
+void Engine::build_level(int l) {
+    auto lv = std::make_unique<Level>();
+    lv->l = l;
+    lv->alpha = size_P_;
+    lv->m = l + size_P_;
+    const int alpha = size_P_;
+    auto row_of = [&](int j) { return j < l ? j : size_Q_ + (j - l); };
+
+    if (alpha > 0) {
+        lv->beta = beta(l);
+        std::vector<Tw> fin((size_t) l * 2), finc(l);
+        std::vector<u64> mat;
+        std::vector<short> omod, olimb;
+        LimbVec ntt_conv;
+        for (int d = 0; d < lv->beta; d++) {
+            const int start = alpha * d;
+            const int size = d == lv->beta - 1 ? l - alpha * (lv->beta - 1) : alpha;
+            std::vector<u64> ibase(primes_.begin() + start, primes_.begin() + start + size);
+            for (int i = 0; i < size; i++) {
+                const u64 q = ibase[i];
+                const u64 hinv = hm::invmod(hm::product_mod(ibase, i, q), q);
+                const u64 c = hm::mulmod(hinv, h_ninv_[start + i], q);
+                fin[2 * (start + i)] = make_tw(c, q);
+                fin[2 * (start + i) + 1] = make_tw(hm::mulmod(c, h_itw1_[start + i], q), q);
+                finc[start + i] = make_tw(hinv, q);
+            }
+            lv->digit_start.push_back(start);
+            lv->digit_size.push_back(size);
+            lv->digit_off.push_back((int) omod.size());
+            int no = 0;
+            for (int j = 0; j < lv->m; j++) {
+                if (j >= start && j < start + size) continue;
+                const int row = row_of(j);
+                for (int i = 0; i < size; i++) mat.push_back(hm::product_mod(ibase, i, primes_[row]));
+                omod.push_back((short) row);
+                olimb.push_back((short) j);
+                ntt_conv.push(d * lv->m + j, row);
+                no++;
+            }
+            lv->digit_no.push_back(no);
+        }
+        lv->modup_fin.upload(fin);
+        lv->modup_fin_coeff.upload(finc);
+        lv->modup_mat.upload(mat);
+        lv->modup_omod.upload(omod);
+        lv->modup_olimb.upload(olimb);
+        lv->modup_ntt_data = ntt_conv.data, lv->modup_ntt_row = ntt_conv.row;
+
+        // mod-down
+        std::vector<u64> pbase(primes_.begin() + size_Q_, primes_.end());
+        std::vector<Tw> dfin((size_t) 2 * alpha * 2);
+        for (int k = 0; k < 2; k++)
+            for (int i = 0; i < alpha; i++) {
+                const u64 p = pbase[i];
+                const u64 hinv = hm::invmod(hm::product_mod(pbase, i, p), p);
+                const u64 c = hm::mulmod(hinv, h_ninv_[size_Q_ + i], p);
+                dfin[2 * (k * alpha + i)] = make_tw(c, p);
+                dfin[2 * (k * alpha + i) + 1] = make_tw(hm::mulmod(c, h_itw1_[size_Q_ + i], p), p);
+            }
+        std::vector<u64> dmat((size_t) l * alpha);
+        std::vector<short> dmod(l), dlimb(l);
+        std::vector<Tw> pinv((size_t) 2 * l);
+        for (int j = 0; j < l; j++) {
+            const u64 q = primes_[j];
+            for (int i = 0; i < alpha; i++) dmat[(size_t) j * alpha + i] = hm::product_mod(pbase, i, q);
+            dmod[j] = (short) j, dlimb[j] = (short) j;
+            pinv[j] = pinv[l + j] = make_tw(hm::invmod(hm::product_mod(pbase, -1, q), q), q);
+        }
+        lv->moddown_fin.upload(dfin);
+        lv->moddown_mat.upload(dmat);
+        lv->moddown_omod.upload(dmod);
+        lv->moddown_olimb.upload(dlimb);
+        lv->pinv_slots.upload(pinv);
+    }
+    if (l >= 2) {
+        std::vector<Tw> qli((size_t) 3 * (l - 1));
+        const u64 qlast = primes_[l - 1];
+        for (int j = 0; j < l - 1; j++)
+            qli[j] = qli[(l - 1) + j] = qli[2 * (l - 1) + j] =
+                    make_tw(hm::invmod(qlast % primes_[j], primes_[j]), primes_[j]);
+        lv->qlast_inv_slots.upload(qli);
+    }
+    levels_[l] = std::move(lv);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// kernel-level ops
+// ---------------------------------------------------------------------------------------------------
+static void check_launch(const char *what) {
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) throw CudaError(e, what);
+}
+
+void Engine::ntt_fwd_list(u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) const {
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    PFHE_CUDA(ntt_forward(plan_, dst, src, ll, st));
+}
+void Engine::ntt_inv_list(u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
+                          cudaStream_t st) const {
+    g_launches.fetch_add(2, std::memory_order_relaxed);
+    PFHE_CUDA(ntt_inverse(plan_, dst, src, ll, fin, by_slot, st));
+}
+
+static void run_chunks(const LimbVec &v, const std::function<void(const LimbList &, size_t)> &fn) {
+    for (size_t b = 0; b < v.size();) {
+        size_t taken;
+        LimbList ll = v.chunk(b, taken);
+        fn(ll, b);
+        b += taken;
+    }
+}
+
+void Engine::ntt_fwd_rows_range(u64 *inout, int count, int start_row, cudaStream_t st) const {
+    LimbVec v;
+    for (int i = 0; i < count; i++) v.push(i, start_row + i);
+    run_chunks(v, [&](const LimbList &ll, size_t) { ntt_fwd_list(inout, inout, ll, st); });
+}
+
+void Engine::ntt_inv_rows_range(u64 *dst, const u64 *src, int count, int start_row, cudaStream_t st) const {
+    LimbVec v;
+    for (int i = 0; i < count; i++) v.push(i, start_row + i);
+    run_chunks(v, [&](const LimbList &ll, size_t) { ntt_inv_list(dst, src, ll, nullptr, 0, st); });
+}
+
+void Engine::ntt_special_range(u64 *inout, int count, int start, int size_Ql, bool inverse, cudaStream_t st) const {
+    LimbVec v;
+    for (int i = 0; i < count; i++) {
+        const int t = start + i;
+        v.push(t, t < size_Ql ? t : size_Q_ + (t - size_Ql));
+    }
+    run_chunks(v, [&](const LimbList &ll, size_t) {
+        if (inverse) ntt_inv_list(inout, inout, ll, nullptr, 0, st);
+        else ntt_fwd_list(inout, inout, ll, st);
+    });
+}
+
+void Engine::tensor_2x2(const u64 *a, const u64 *b, u64 *out, int l, cudaStream_t st) const {
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+    k_tensor_2x2<<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_, l);
+    check_launch("k_tensor_2x2");
+}
+
+void Engine::tensor_square(const u64 *a, u64 *out, int l, cudaStream_t st) const {
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+    k_tensor_square<<<grid, EW_THREADS, 0, st>>>(a, out, d_mod_.p, n_, l);
+    check_launch("k_tensor_square");
+}
+
+void Engine::elementwise(int op, const u64 *a, const u64 *b, u64 *out, int l, cudaStream_t st) const {
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+    switch (op) {
+        case EW_ADD: k_elementwise<EW_ADD><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
+        case EW_SUB: k_elementwise<EW_SUB><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
+        case EW_MUL: k_elementwise<EW_MUL><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
+        case EW_NEG: k_elementwise<EW_NEG><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
+        default: throw std::invalid_argument("unknown elementwise op");
+    }
+    check_launch("k_elementwise");
+}
+
+static void launch_bconv(const BconvBatch &batch, int jobs, int ni, int no_max, const Modulus *mod, size_t n,
+                         cudaStream_t st) {
+    dim3 grid((unsigned) (n / (2 * EW_THREADS)), jobs);
+    const size_t smem = (size_t) no_max * ni * 8 + (size_t) no_max * sizeof(Modulus);
+    switch (ni) {
+        case 1: k_bconv<1><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+        case 2: k_bconv<2><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+        case 3: k_bconv<3><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+        case 4: k_bconv<4><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+        case 5: k_bconv<5><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+        case 6: k_bconv<6><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+        default: k_bconv<0><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+    }
+    check_launch("k_bconv");
+}
+
+// DRNSTool::modup (reference src/rns_bconv.cu:530-628), CKKS/BGV form: cks in NTT domain
+void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_t st) const {
+    const Level &lv = level(l);
+    if (lv.alpha == 0) throw std::logic_error("key switching needs special primes");
+    // 1. inverse NTT fused with the n^-1 * qhat_i^-1 scaling (iNTT+scale, rns_bconv.cu:558)
+    {
+        LimbVec v;
+        for (int i = 0; i < l; i++) v.push(i, i);
+        run_chunks(v, [&](const LimbList &ll, size_t b) { ntt_inv_list(t_cks, cks, ll, lv.modup_fin.p + 2 * b, 1, st); });
+    }
+    // 2. each digit: own limbs copied (modup_copy_partQl_kernel :522-528), other limbs converted (:455-485)
+    for (int d = 0; d < lv.beta;) {
+        BconvBatch batch{};
+        int jobs = 0, no_max = 0;
+        const int ni = lv.digit_size[d];
+        while (d < lv.beta && jobs < BCONV_MAX_JOBS && lv.digit_size[d] == ni) {
+            const int start = lv.digit_start[d], off = lv.digit_off[d];
+            u64 *dst = t_mod_up + (size_t) d * lv.m * n_;
+            PFHE_CUDA(cudaMemcpyAsync(dst + (size_t) start * n_, cks + (size_t) start * n_, (size_t) ni * n_ * 8,
+                                      cudaMemcpyDeviceToDevice, st));
+            // matrix offset: digits before d contributed digit_no * digit_size entries each
+            size_t moff = 0;
+            for (int e = 0; e < d; e++) moff += (size_t) lv.digit_no[e] * lv.digit_size[e];
+            batch.job[jobs] = BconvJob{t_cks + (size_t) start * n_, dst, lv.modup_mat.p + moff, lv.modup_omod.p + off,
+                                       lv.modup_olimb.p + off, ni, lv.digit_no[d]};
+            no_max = std::max(no_max, lv.digit_no[d]);
+            jobs++, d++;
+        }
+        launch_bconv(batch, jobs, ni, no_max, d_mod_.p, n_, st);
+    }
+    // 3. forward NTT of the converted limbs only (..._exclude_range, rns_bconv.cu:618)
+    {
+        LimbVec v;
+        v.data = lv.modup_ntt_data, v.row = lv.modup_ntt_row, v.src = lv.modup_ntt_data;
+        run_chunks(v, [&](const LimbList &ll, size_t) { ntt_fwd_list(t_mod_up, t_mod_up, ll, st); });
+    }
+}
+
+void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st) const {
+    const Level &lv = level(l);
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), lv.m);
+    k_inner_prod<<<grid, EW_THREADS, 0, st>>>(cx, t_mod_up, evk, d_mod_.p, n_, l, lv.m, size_Q_, size_QP_, lv.beta);
+    check_launch("k_inner_prod");
+}
+
+// DRNSTool::moddown_from_NTT (reference src/rns_bconv.cu:776-828), CKKS form, for npoly polynomials laid
+// out as cx[k] = [m][n]:  out[k][j] = (cx[k][j] - NTT(bconv_{P->q_j}(iNTT(cx[k][P])))) * P^-1  (+ addend[k][j])
+void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 *addend, unsigned add_mask,
+                     cudaStream_t st) const {
+    const Level &lv = level(l);
+    const int alpha = lv.alpha, m = lv.m;
+    if (npoly < 1 || npoly > 2) throw std::invalid_argument("moddown handles 1 or 2 polynomials");
+    // 1. inverse NTT of the P limbs, fused with n^-1 * phat_i^-1 (iNTT :788 + bconv_mult :40-60)
+    {
+        LimbVec v;
+        for (int k = 0; k < npoly; k++)
+            for (int i = 0; i < alpha; i++) v.push(k * m + l + i, size_Q_ + i);
+        ntt_inv_list(cx, cx, single_list(v), lv.moddown_fin.p, 1, st);
+    }
+    // 2. P -> Ql conversion (bConv_BEHZ matmul :143-168 / single-P :691-707)
+    {
+        BconvBatch batch{};
+        for (int k = 0; k < npoly; k++)
+            batch.job[k] = BconvJob{cx + ((size_t) k * m + l) * n_, delta + (size_t) k * l * n_, lv.moddown_mat.p,
+                                    lv.moddown_omod.p, lv.moddown_olimb.p, alpha, l};
+        launch_bconv(batch, npoly, alpha, l, d_mod_.p, n_, st);
+    }
+    // 3. forward NTT of delta with the fused (cx - delta) * P^-1 (+ ct) epilogue (:820, ntt_moddown.cu:106-216)
+    {
+        LimbVec v;
+        for (int k = 0; k < npoly; k++)
+            for (int j = 0; j < l; j++) v.push(k * l + j, j);
+        run_chunks(v, [&](const LimbList &ll, size_t b) {
+            EpiArgs ea{};
+            ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p + b;
+            for (int s = 0; s < ll.count; s++) {
+                const int k = (int) ((b + s) / l), j = (int) ((b + s) % l);
+                ea.sub[s] = (short) (k * m + j);
+                ea.out[s] = (short) (k * l + j);
+                ea.add[s] = (short) ((addend && ((add_mask >> k) & 1)) ? k * l + j : -1);
+            }
+            g_launches.fetch_add(2, std::memory_order_relaxed);
+            PFHE_CUDA(ntt_forward_epilogue(plan_, delta, ll, ea, st));
+        });
+    }
+}
+
+// keyswitch_inplace (reference src/eval_key_switch.cu:95-182): out[2][l][n] = addend + moddown(<modup(c2), evk>)
+void Engine::keyswitch(int l, u64 *out, const u64 *c2, const u64 *const *evk, const u64 *addend, cudaStream_t st) {
+    modup(l, ws_.t_mod_up.p, c2, ws_.t_cks.p, st);
+    inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
+    moddown(l, out, ws_.cx.p, ws_.delta.p, 2, addend, addend ? 3u : 0u, st);
+}
+
+// multiply_inplace + relinearize_inplace for CKKS/BGV (reference src/evaluate.cu:345-397,1342-1374)
+void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st) {
+    u64 *d = ws_.tmp.p;
+    tensor_2x2(ct1, ct2, d, l, st);
+    keyswitch(l, out, d + (size_t) 2 * l * n_, rlk, d, st);
+}
+
+// apply_galois_inplace for CKKS/BGV (reference src/evaluate.cu:1567-1630)
+void Engine::apply_galois(int l, u64 *ct, uint32_t galois_elt, const u64 *const *glk, cudaStream_t st) {
+    const int gi = galois_index(galois_elt);
+    u64 *tmp = ws_.tmp.p;   // [2][l][n]: permuted c0, c1
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), 2 * l);
+    k_galois_ntt<<<grid, EW_THREADS, 0, st>>>(tmp, ct, d_perm_[gi].p, n_);
+    check_launch("k_galois_ntt");
+    // ct0 = perm(c0) + ks0, ct1 = 0 + ks1: the "wipe c1" memset of the reference is folded away by
+    // pointing poly 1 at a zero addend, i.e. no addend at all.
+    modup(l, ws_.t_mod_up.p, tmp + (size_t) l * n_, ws_.t_cks.p, st);
+    inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, glk, st);
+    moddown(l, ct, ws_.cx.p, ws_.delta.p, 2, tmp, 1u, st);
+}
+
+// rescale_to_next for CKKS (reference src/evaluate.cu:1376-1427 + divide_and_round_q_last_ntt rns.cu:1160-1184)
+void Engine::rescale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) {
+    if (l < 2) throw std::invalid_argument("end of modulus switching chain reached");
+    const Level &lv = level(l);
+    const int nl = l - 1;
+    u64 *last = ws_.t_cks.p;   // [size][n] coefficient form of the dropped limb
+    {
+        LimbVec v;
+        for (int s = 0; s < size; s++) v.push(s, l - 1, s * l + (l - 1));
+        ntt_inv_list(last, in, single_list(v), nullptr, 0, st);
+    }
+    for (int s = 0; s < size; s++) {
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), nl);
+        k_reduce_last<<<grid, EW_THREADS, 0, st>>>(out + (size_t) s * nl * n_, last + (size_t) s * n_, d_mod_.p, n_);
+        check_launch("k_reduce_last");
+    }
+    LimbVec v;
+    for (int s = 0; s < size; s++)
+        for (int j = 0; j < nl; j++) v.push(s * nl + j, j);
+    run_chunks(v, [&](const LimbList &ll, size_t b) {
+        EpiArgs ea{};
+        ea.sub_base = in, ea.out_base = out, ea.add_base = nullptr, ea.mulc = lv.qlast_inv_slots.p + b;
+        for (int k = 0; k < ll.count; k++) {
+            const int s = (int) ((b + k) / nl), j = (int) ((b + k) % nl);
+            ea.sub[k] = (short) (s * l + j);
+            ea.out[k] = (short) (s * nl + j);
+            ea.add[k] = -1;
+        }
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+            PFHE_CUDA(ntt_forward_epilogue(plan_, out, ll, ea, st));
+    });
+}
+
+// mod_switch_drop_to_next for CKKS (reference src/evaluate.cu:1429-1472): keep the first l-1 limbs
+void Engine::mod_switch_drop(int l, u64 *out, const u64 *in, int size, cudaStream_t st) const {
+    if (l < 2) throw std::invalid_argument("end of modulus switching chain reached");
+    for (int s = 0; s < size; s++)
+        PFHE_CUDA(cudaMemcpyAsync(out + (size_t) s * (l - 1) * n_, in + (size_t) s * l * n_, (size_t) (l - 1) * n_ * 8,
+                                  cudaMemcpyDeviceToDevice, st));
+}
+
+} // namespace pfhe

@@ -1,0 +1,85 @@
+// modarith.cuh -- 64-bit modular arithmetic for the B200 RNS engine (device side).
+//
+// Semantics follow the reference's include/uintmodmath.cuh (file:line cited per function) but the code is
+// organised around *lazy* value ranges tracked at compile time by the NTT kernels, so that conditional
+// subtractions are only issued where a 64-bit overflow would otherwise occur.  Every value that leaves a
+// kernel is a canonical residue in [0, q) -- the reference's store invariant.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+namespace pfhe {
+
+using u64 = unsigned long long;
+using u32 = unsigned int;
+
+// {q, floor(2^128/q) lo, hi} -- same content as the reference's DModulus (include/ntt.cuh:6-32)
+struct __align__(8) Modulus {
+    u64 q;
+    u64 mu_lo;
+    u64 mu_hi;
+};
+
+// (w, floor(w * 2^64 / q)) pair, 16 bytes so that one 128-bit load fetches both (the reference keeps two
+// separate arrays, include/ntt.cuh:40-44)
+using Tw = ulonglong2;
+
+__device__ __forceinline__ u64 mulhi(u64 a, u64 b) { return __umul64hi(a, b); }
+
+// x - q if x >= q  (csub_q, uintmodmath.cuh:18-21), branch-free min trick: valid for x < 2q, q < 2^63
+__device__ __forceinline__ u64 csub(u64 x, u64 q) {
+    u64 t = x - q;
+    return (long long) t < 0 ? x : t;
+}
+
+// Shoup product, result in [0, 2q) for ANY 64-bit x (multiply_and_reduce_shoup_lazy, uintmodmath.cuh:226-231)
+__device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
+    u64 hi = mulhi(x, ws);
+    return x * w - hi * q;
+}
+
+// canonical Shoup product (multiply_and_reduce_shoup, uintmodmath.cuh:207-216)
+__device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 ws, u64 q) { return csub(mul_shoup_lazy(x, w, ws, q), q); }
+__device__ __forceinline__ u64 mul_shoup(u64 x, Tw w, u64 q) { return csub(mul_shoup_lazy(x, w.x, w.y, q), q); }
+
+__device__ __forceinline__ u64 add_mod(u64 a, u64 b, u64 q) { return csub(a + b, q); }          // :36-42
+__device__ __forceinline__ u64 sub_mod(u64 a, u64 b, u64 q) { return csub(a + q - b, q); }      // :47-53
+
+// 128-bit value -> [0, q) (barrett_reduce_uint128_uint64, uintmodmath.cuh:96-136).  Valid for any
+// (hi, lo) with q < 2^61: the quotient estimate is at most one too small.
+__device__ __forceinline__ u64 barrett128(u64 lo, u64 hi, const Modulus &m) {
+    // floor(((hi:lo) * (mu_hi:mu_lo)) / 2^128), low 64 bits only
+    u64 t0 = mulhi(lo, m.mu_lo);
+    u64 p1lo = lo * m.mu_hi, p1hi = mulhi(lo, m.mu_hi);
+    u64 p2lo = hi * m.mu_lo, p2hi = mulhi(hi, m.mu_lo);
+    u64 s = t0 + p1lo;
+    u64 c1 = s < t0;
+    u64 s2 = s + p2lo;
+    u64 c2 = s2 < s;
+    u64 quo = hi * m.mu_hi + p1hi + p2hi + c1 + c2;
+    u64 r = lo - quo * m.q;
+    return csub(r, m.q);
+}
+
+// a * b mod q, canonical (multiply_and_barrett_reduce_uint64, uintmodmath.cuh:160-198)
+__device__ __forceinline__ u64 mul_mod(u64 a, u64 b, const Modulus &m) {
+    return barrett128(a * b, mulhi(a, b), m);
+}
+
+// x mod q for a single word (barrett_reduce_uint64_uint64, uintmodmath.cuh:144-151)
+__device__ __forceinline__ u64 barrett64(u64 x, const Modulus &m) {
+    u64 s = mulhi(m.mu_hi, x);
+    return csub(x - s * m.q, m.q);
+}
+
+// 128-bit accumulator for inner products / base conversion (uintmath.cuh add_uint128_uint128)
+struct Acc128 {
+    u64 lo, hi;
+    __device__ __forceinline__ void mac(u64 a, u64 b) {
+        u64 pl = a * b, ph = mulhi(a, b);
+        lo += pl;
+        hi += ph + (lo < pl);
+    }
+};
+
+} // namespace pfhe

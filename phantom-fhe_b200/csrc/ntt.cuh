@@ -1,0 +1,365 @@
+// ntt.cuh -- negacyclic NTT kernels for sm_100a (forward: natural -> bit-reversed, inverse: the converse).
+//
+// Replaces the reference's nwt_2d_radix8_* family (include/ntt.cuh:157-226, src/ntt/*.cu).  Same transform
+// (NTT(x)[k] = sum_j x_j psi^{j(2 bitrev(k)+1)}), different organisation:
+//
+//  * N = 2^P1 * 2^P2.  A "column pass" runs the P1 stages whose butterfly span is >= 2^P2 on tiles of
+//    2^P1 rows x C adjacent columns, a "row pass" runs the remaining P2 stages on tiles of C contiguous rows.
+//    Every CTA owns a 4096-element tile (256 threads x 16 elements); each thread keeps its 16 elements in
+//    registers and runs up to 4 merged stages (radix-16) per round, rounds exchange through a skewed,
+//    bank-conflict-free shared-memory tile, so a 2^16-point transform is 2 passes x 2 rounds.
+//  * Lazy ranges are tracked at compile time: forward butterflies issue a conditional subtraction only on
+//    every second stage (values < 8q < 2^64 for q < 2^61), the result is made canonical once at the end.
+//  * Twiddles are (w, floor(w 2^64/q)) pairs fetched with one 128-bit load; the table is stored in a
+//    kernel-native order so that the warp that owns a contiguous butterfly span reads contiguous twiddles
+//    (the last row-pass round, where every butterfly has its own twiddle, is stored transposed).
+//  * Prologue / epilogue functors fuse the neighbouring element-wise steps (n^-1 and digit scaling, the
+//    mod-down epilogue, ...) into the passes.
+#pragma once
+#include <type_traits>
+#include "modarith.cuh"
+
+namespace pfhe {
+
+constexpr int NTT_THREADS = 256;
+constexpr int NTT_EPT = 16;
+constexpr int NTT_LOG_TILE = 12;
+constexpr int NTT_TILE = 1 << NTT_LOG_TILE;
+constexpr int NTT_SMEM_WORDS = NTT_TILE + (NTT_TILE >> 4);
+constexpr int NTT_MAX_LIMBS = 128;
+
+// which limbs a launch touches: slot i works on data limb `data[i]` (units of N words from the base
+// pointer) with the constant tables of key-level prime `row[i]`.  This one descriptor covers the
+// reference's start_modulus_idx / include_special_mod / include_temp_mod / exclude_range variants.
+struct LimbList {
+    int count;
+    short data[NTT_MAX_LIMBS];   // destination limb (and source limb when src_same)
+    short row[NTT_MAX_LIMBS];    // key-level prime row
+    short src[NTT_MAX_LIMBS];    // source limb of the first pass (out-of-place launches)
+};
+
+// epilogue of the fused forward row pass:  out = (sub - NTT(x)) * mulc  (+ add)   mod q
+// (nwt_2d_radix8_forward_inplace_fuse_moddown, reference src/ntt/ntt_moddown.cu:106-216,
+//  + add_to_ct_kernel rns_bconv.cu:763-769; also divide_and_round_ntt_inv_scalar_kernel rns.cu:1141-1158)
+struct EpiArgs {
+    const u64 *sub_base;
+    u64 *out_base;
+    const u64 *add_base;
+    const Tw *mulc;              // per slot
+    short sub[NTT_MAX_LIMBS];
+    short out[NTT_MAX_LIMBS];
+    short add[NTT_MAX_LIMBS];    // -1: nothing to add
+};
+
+// round schedule of a pass with P stages: ceil(P/4) rounds of 3..4 (or fewer) stages
+template<int P>
+struct Sched {
+    static constexpr int NR = (P + 3) / 4;
+    static constexpr int r(int i) { return P / NR + (i < P % NR ? 1 : 0); }
+    static constexpr int s0(int i) {
+        int s = 0;
+        for (int j = 0; j < i; j++) s += r(j);
+        return s;
+    }
+};
+
+__host__ __device__ constexpr int ntt_p1(int logn) { return logn / 2; }
+__host__ __device__ constexpr int ntt_p2(int logn) { return logn - logn / 2; }
+
+// position of the twiddle for global stage s, block B inside the per-limb table (host + device)
+__host__ __device__ inline size_t tw_native_index(int logn, int s, size_t B) {
+    const int p1 = ntt_p1(logn), p2 = ntt_p2(logn);
+    const int nr = (p2 + 3) / 4;
+    const int rlast = p2 / nr;               // the last round never gets a remainder stage
+    const int s0last = p2 - rlast;
+    if (s < p1 + s0last) return ((size_t) 1 << s) + B;
+    const int sigma = s - p1, u = sigma - s0last;
+    const size_t row = B >> sigma, bl = B & (((size_t) 1 << sigma) - 1);
+    const size_t hi = bl >> u, b = bl & (((size_t) 1 << u) - 1);
+    return ((size_t) 1 << s) + (row << sigma) + (b << s0last) + hi;
+}
+
+__device__ __forceinline__ int skew(int i) { return i + (i >> 4); }
+
+// ----------------------------------------------------------------------------------------------------
+// element <-> thread mapping of one round
+// ----------------------------------------------------------------------------------------------------
+template<int P, int RI, bool ROWS>
+struct RoundMap {
+    static constexpr int R = Sched<P>::r(RI);
+    static constexpr int S0 = Sched<P>::s0(RI);
+    static constexpr int LAM = P - S0 - R;           // bits of the low index
+    static constexpr int GAM = NTT_LOG_TILE - P;     // bits of the batch index (columns resp. rows per tile)
+    static constexpr int GB = 4 - R;
+    static constexpr int G = 1 << GB;                // independent radix-2^R groups per thread
+    static constexpr int T = 1 << P;
+    static constexpr int C = 1 << GAM;
+    static constexpr bool LAST = (RI == Sched<P>::NR - 1);
+    // groups of one thread use the same twiddles?
+    static constexpr bool SHARE = ROWS ? (LAM >= GB) : (GAM + LAM >= GB);
+
+    __device__ static __forceinline__ void decode(int mu, int &hi, int &lo, int &c) {
+        if constexpr (!ROWS) {
+            c = mu & (C - 1);
+            lo = (mu >> GAM) & ((1 << LAM) - 1);
+            hi = mu >> (GAM + LAM);
+        } else {
+            lo = mu & ((1 << LAM) - 1);
+            hi = (mu >> LAM) & ((1 << S0) - 1);
+            c = mu >> (LAM + S0);
+        }
+    }
+    __device__ static __forceinline__ int elem(int hi, int k, int lo) { return (hi << (P - S0)) | (k << LAM) | lo; }
+    __device__ static __forceinline__ int sidx(int e, int c) { return skew(ROWS ? c * T + e : e * C + c); }
+};
+
+// ----------------------------------------------------------------------------------------------------
+// butterflies
+// ----------------------------------------------------------------------------------------------------
+// forward (Cooley-Tukey, Harvey lazy; butterfly.cuh:10-22 semantics with a relaxed reduction schedule)
+template<bool CSUB>
+__device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, const Tw w, const u64 q, const u64 q2, const u64 q4) {
+    u64 X = x;
+    if constexpr (CSUB) X = csub(X, q4);
+    const u64 t = mul_shoup_lazy(y, w.x, w.y, q);
+    x = X + t;
+    y = X + q2 - t;
+}
+// forward stage s takes inputs < 4q (s = 0), < 6q (odd s) or < 8q (even s >= 2) and reduces on even s >= 2
+__host__ __device__ constexpr bool fwd_csub(int s) { return s >= 2 && (s % 2) == 0; }
+
+// inverse (Gentleman-Sande, butterfly.cuh:28-37): inputs and outputs in [0, 2q)
+__device__ __forceinline__ void gs_bfly(u64 &x, u64 &y, const Tw w, const u64 q, const u64 q2) {
+    const u64 s = csub(x + y, q2);
+    const u64 d = x + q2 - y;
+    x = s;
+    y = mul_shoup_lazy(d, w.x, w.y, q);
+}
+// last inverse stage: folds n^-1 (and an optional per-limb scalar) into both outputs, canonical results
+// (replaces intt_2d.cu:195-203 "lower half times n^-1, upper half through itw[1]")
+__device__ __forceinline__ void gs_bfly_last(u64 &x, u64 &y, const Tw cx, const Tw cy, const u64 q, const u64 q2) {
+    const u64 s = x + y;
+    const u64 d = x + q2 - y;
+    x = mul_shoup(s, cx, q);
+    y = mul_shoup(d, cy, q);
+}
+
+// twiddle index of (stage S0+u, hi, b) for this tile
+template<class M, bool ROWS, int LOGN>
+__device__ __forceinline__ int tw_index(int u, int hi, int b, int row) {
+    if constexpr (!ROWS) {
+        return (1 << (M::S0 + u)) + ((hi << u) | b);
+    } else {
+        constexpr int P1 = ntt_p1(LOGN);
+        const int s = P1 + M::S0 + u;
+        const int base = (1 << s) + (row << (M::S0 + u));
+        if constexpr (M::LAST) return base + (b << M::S0) + hi;
+        else return base + ((hi << u) | b);
+    }
+}
+
+// one forward round on the 16 registers of a thread: x[g * 2^R + k]
+template<class M, bool ROWS, int LOGN, int SBASE>
+__device__ __forceinline__ void fwd_round(u64 (&x)[16], const Tw *__restrict__ tw, const int (&hi)[M::G],
+                                          const int (&row)[M::G], u64 q, u64 q2, u64 q4) {
+    constexpr int R = M::R;
+#pragma unroll
+    for (int u = 0; u < R; u++) {
+        const int half = 1 << (R - 1 - u);
+#pragma unroll
+        for (int b = 0; b < (1 << u); b++) {
+            Tw w[M::G];
+#pragma unroll
+            for (int g = 0; g < M::G; g++) {
+                if (g == 0 || !M::SHARE) w[g] = __ldg(&tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, row[g])]);
+                else w[g] = w[0];
+            }
+#pragma unroll
+            for (int g = 0; g < M::G; g++) {
+#pragma unroll
+                for (int t = 0; t < half; t++) {
+                    const int i0 = (g << R) + b * 2 * half + t;
+                    // compile-time reduction schedule (all loop variables are unrolled constants)
+                    if (fwd_csub(SBASE + M::S0 + u)) ct_bfly<true>(x[i0], x[i0 + half], w[g], q, q2, q4);
+                    else ct_bfly<false>(x[i0], x[i0 + half], w[g], q, q2, q4);
+                }
+            }
+        }
+    }
+}
+
+// one inverse round (stages S0+R-1 down to S0).  FINAL marks the round containing global stage 0.
+template<class M, bool ROWS, int LOGN, bool FINAL>
+__device__ __forceinline__ void inv_round(u64 (&x)[16], const Tw *__restrict__ tw, const int (&hi)[M::G],
+                                          const int (&row)[M::G], u64 q, u64 q2, Tw fin_x, Tw fin_y) {
+    constexpr int R = M::R;
+#pragma unroll
+    for (int u = R - 1; u >= 0; u--) {
+        const int half = 1 << (R - 1 - u);
+#pragma unroll
+        for (int b = 0; b < (1 << u); b++) {
+            Tw w[M::G];
+            if (!(FINAL && u == 0)) {
+#pragma unroll
+                for (int g = 0; g < M::G; g++) {
+                    if (g == 0 || !M::SHARE) w[g] = __ldg(&tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, row[g])]);
+                    else w[g] = w[0];
+                }
+            }
+#pragma unroll
+            for (int g = 0; g < M::G; g++) {
+#pragma unroll
+                for (int t = 0; t < half; t++) {
+                    const int i0 = (g << R) + b * 2 * half + t;
+                    if (FINAL && u == 0) gs_bfly_last(x[i0], x[i0 + half], fin_x, fin_y, q, q2);
+                    else gs_bfly(x[i0], x[i0 + half], w[g], q, q2);
+                }
+            }
+        }
+    }
+}
+
+// ----------------------------------------------------------------------------------------------------
+// pass drivers.  IO functors:
+//   load(slot, data_limb, coeff_index) -> u64      value entering the transform
+//   store(slot, data_limb, coeff_index, value)     value leaving the pass
+// ----------------------------------------------------------------------------------------------------
+// context shared by the rounds of one pass
+struct PassCtx {
+    const Tw *tw;     // table of this limb
+    u64 q, q2, q4;
+    int tile;         // tile index inside the limb (column block resp. row block)
+    Tw fin_x, fin_y;  // constants of the last inverse stage
+};
+
+template<int P, bool ROWS, int LOGN>
+__device__ __forceinline__ size_t gl_index(int e, int c, int tile) {
+    constexpr int GAM = NTT_LOG_TILE - P;
+    if constexpr (!ROWS) {
+        constexpr int LOGN2 = LOGN - P;
+        return ((size_t) e << LOGN2) + (tile << GAM) + c;
+    } else {
+        return ((size_t) ((tile << GAM) + c) << P) + e;
+    }
+}
+
+// Forward pass over one tile.  Load/Store are functors taking the coefficient index inside the limb.
+template<int P, bool ROWS, int LOGN, int SBASE, class Load, class Store>
+__device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load load, Store store) {
+    constexpr int NR = Sched<P>::NR;
+    u64 x[16];
+    const int tid = threadIdx.x;
+
+    auto run_round = [&](auto ri_tag) {
+        constexpr int RI = decltype(ri_tag)::value;
+        using M = RoundMap<P, RI, ROWS>;
+        int hi[M::G], lo[M::G], c[M::G], row[M::G];
+#pragma unroll
+        for (int g = 0; g < M::G; g++) {
+            M::decode((tid << M::GB) | g, hi[g], lo[g], c[g]);
+            row[g] = (cx.tile << M::GAM) + c[g];
+        }
+        // gather
+#pragma unroll
+        for (int g = 0; g < M::G; g++)
+#pragma unroll
+            for (int k = 0; k < (1 << M::R); k++) {
+                const int e = M::elem(hi[g], k, lo[g]);
+                if constexpr (RI == 0) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
+                else x[(g << M::R) + k] = smem[M::sidx(e, c[g])];
+            }
+        fwd_round<M, ROWS, LOGN, SBASE>(x, cx.tw, hi, row, cx.q, cx.q2, cx.q4);
+        // scatter
+        constexpr bool DIRECT_OUT = (RI == NR - 1) && !ROWS;
+        if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
+#pragma unroll
+        for (int g = 0; g < M::G; g++)
+#pragma unroll
+            for (int k = 0; k < (1 << M::R); k++) {
+                const int e = M::elem(hi[g], k, lo[g]);
+                if constexpr (DIRECT_OUT) store(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile), x[(g << M::R) + k]);
+                else smem[M::sidx(e, c[g])] = x[(g << M::R) + k];
+            }
+        if constexpr (!DIRECT_OUT) __syncthreads();
+    };
+
+    run_round(std::integral_constant<int, 0>{});
+    if constexpr (NR > 1) run_round(std::integral_constant<int, 1>{});
+    if constexpr (NR > 2) run_round(std::integral_constant<int, 2>{});
+
+    if constexpr (ROWS) {
+        // the tile is contiguous in global memory: flat, fully coalesced copy-out
+        const size_t base = (size_t) cx.tile << NTT_LOG_TILE;
+#pragma unroll
+        for (int i = 0; i < NTT_EPT; i++) {
+            const int j = i * NTT_THREADS + tid;
+            store(base + j, smem[skew(j)]);
+        }
+    }
+}
+
+// Inverse pass over one tile (rounds in reverse order).
+template<int P, bool ROWS, int LOGN, bool FINAL, class Load, class Store>
+__device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx &cx, Load load, Store store) {
+    constexpr int NR = Sched<P>::NR;
+    u64 x[16];
+    const int tid = threadIdx.x;
+
+    if constexpr (ROWS) {
+        // flat coalesced copy-in, the first inverse round then reads its 16 contiguous elements from smem
+        const size_t base = (size_t) cx.tile << NTT_LOG_TILE;
+#pragma unroll
+        for (int i = 0; i < NTT_EPT; i++) {
+            const int j = i * NTT_THREADS + tid;
+            smem[skew(j)] = load(base + j);
+        }
+        __syncthreads();
+    }
+
+    auto run_round = [&](auto ri_tag) {
+        constexpr int RI = decltype(ri_tag)::value;
+        using M = RoundMap<P, RI, ROWS>;
+        int hi[M::G], lo[M::G], c[M::G], row[M::G];
+#pragma unroll
+        for (int g = 0; g < M::G; g++) {
+            M::decode((tid << M::GB) | g, hi[g], lo[g], c[g]);
+            row[g] = (cx.tile << M::GAM) + c[g];
+        }
+        constexpr bool DIRECT_IN = (RI == NR - 1) && !ROWS;
+#pragma unroll
+        for (int g = 0; g < M::G; g++)
+#pragma unroll
+            for (int k = 0; k < (1 << M::R); k++) {
+                const int e = M::elem(hi[g], k, lo[g]);
+                if constexpr (DIRECT_IN) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
+                else x[(g << M::R) + k] = smem[M::sidx(e, c[g])];
+            }
+        inv_round<M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, row, cx.q, cx.q2, cx.fin_x, cx.fin_y);
+        if constexpr (RI == 0) {
+            // first round in index order = last in time: values leave the pass
+#pragma unroll
+            for (int g = 0; g < M::G; g++)
+#pragma unroll
+                for (int k = 0; k < (1 << M::R); k++) {
+                    const int e = M::elem(hi[g], k, lo[g]);
+                    store(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile), x[(g << M::R) + k]);
+                }
+        } else {
+            if constexpr (!DIRECT_IN) __syncthreads();
+#pragma unroll
+            for (int g = 0; g < M::G; g++)
+#pragma unroll
+                for (int k = 0; k < (1 << M::R); k++) {
+                    const int e = M::elem(hi[g], k, lo[g]);
+                    smem[M::sidx(e, c[g])] = x[(g << M::R) + k];
+                }
+            __syncthreads();
+        }
+    };
+
+    if constexpr (NR > 2) run_round(std::integral_constant<int, 2>{});
+    if constexpr (NR > 1) run_round(std::integral_constant<int, 1>{});
+    run_round(std::integral_constant<int, 0>{});
+}
+
+} // namespace pfhe

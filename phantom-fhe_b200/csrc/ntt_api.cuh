@@ -1,0 +1,27 @@
+// ntt_api.cuh -- host-callable NTT launchers.
+#pragma once
+#include "ntt.cuh"
+
+namespace pfhe {
+
+struct NttPlan {
+    int logn;
+    const Tw *tw;        // [size_QP][N] forward twiddles, kernel-native order (tw_native_index)
+    const Tw *itw;       // [size_QP][N] inverse twiddles, same order
+    const Modulus *mod;  // [size_QP]
+    const Tw *inv_fin;   // [size_QP][2]: {n^-1, itw[1] * n^-1} for the last inverse stage
+};
+
+// forward negacyclic NTT of the limbs in `ll` (replaces nwt_2d_radix8_forward_inplace and its
+// include_special_mod / include_temp_mod / exclude_range variants, reference include/ntt.cuh:172-201)
+cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st);
+
+// forward NTT of `data` (in place, ll.src must equal ll.data) whose row pass ends in the EpiArgs epilogue
+cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st);
+
+// inverse NTT incl. n^-1; `fin` (optional) = per-slot or per-row {c, itw1*c} pairs with c = n^-1 * scalar
+// (replaces nwt_2d_radix8_backward[_inplace][_scale] and variants, include/ntt.cuh:206-226)
+cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
+                        cudaStream_t st);
+
+} // namespace pfhe

@@ -1,0 +1,141 @@
+// ntt_kernels.cu -- kernels and launchers built on the pass drivers of ntt.cuh.
+#include "ntt_api.cuh"
+
+namespace pfhe {
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, const Tw *tw,
+                                                           const Modulus *mod) {
+    __shared__ u64 smem[NTT_SMEM_WORDS];
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    const size_t off = (size_t) ll.data[slot] << LOGN;
+    const u64 q = mod[row].q;
+    PassCtx cx{tw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
+    const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
+    u64 *d = dst + off;
+    forward_pass<ntt_p1(LOGN), false, LOGN, 0>(
+            smem, cx, [&](size_t i) { return s[i]; }, [&](size_t i, u64 v) { d[i] = v; });
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_rows(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod) {
+    __shared__ u64 smem[NTT_SMEM_WORDS];
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    const size_t off = (size_t) ll.data[slot] << LOGN;
+    const u64 q = mod[row].q;
+    PassCtx cx{tw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
+    u64 *d = data + off;
+    forward_pass<ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+            smem, cx, [&](size_t i) { return d[i]; },
+            [&](size_t i, u64 v) { d[i] = csub(csub(csub(v, 4 * q), 2 * q), q); });
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_fwd_rows_epi(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod,
+                                                               EpiArgs ea) {
+    __shared__ u64 smem[NTT_SMEM_WORDS];
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    const u64 q = mod[row].q;
+    PassCtx cx{tw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
+    const u64 *d = data + ((size_t) ll.data[slot] << LOGN);
+    const u64 *sub = ea.sub_base + ((size_t) ea.sub[slot] << LOGN);
+    u64 *out = ea.out_base + ((size_t) ea.out[slot] << LOGN);
+    const int addl = ea.add[slot];
+    const u64 *add = addl >= 0 ? ea.add_base + ((size_t) addl << LOGN) : nullptr;
+    const Tw k = ea.mulc[slot];
+    forward_pass<ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+            smem, cx, [&](size_t i) { return d[i]; },
+            [&](size_t i, u64 v) {
+                v = csub(csub(csub(v, 4 * q), 2 * q), q);
+                u64 r = mul_shoup(sub[i] + q - v, k, q);
+                if (add) r = add_mod(r, add[i], q);
+                out[i] = r;
+            });
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_inv_rows(u64 *dst, const u64 *src, LimbList ll, const Tw *itw,
+                                                           const Modulus *mod) {
+    __shared__ u64 smem[NTT_SMEM_WORDS];
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    const size_t off = (size_t) ll.data[slot] << LOGN;
+    const u64 q = mod[row].q;
+    PassCtx cx{itw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
+    const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
+    u64 *d = dst + off;
+    inverse_pass<ntt_p2(LOGN), true, LOGN, false>(
+            smem, cx, [&](size_t i) { return s[i]; }, [&](size_t i, u64 v) { d[i] = v; });
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS) k_inv_cols(u64 *data, LimbList ll, const Tw *itw, const Modulus *mod,
+                                                           const Tw *fin, int fin_by_slot) {
+    __shared__ u64 smem[NTT_SMEM_WORDS];
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    const size_t off = (size_t) ll.data[slot] << LOGN;
+    const u64 q = mod[row].q;
+    const int f = fin_by_slot ? slot : row;
+    PassCtx cx{itw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, fin[2 * f], fin[2 * f + 1]};
+    u64 *d = data + off;
+    inverse_pass<ntt_p1(LOGN), false, LOGN, true>(
+            smem, cx, [&](size_t i) { return d[i]; }, [&](size_t i, u64 v) { d[i] = v; });
+}
+
+template<int LOGN>
+static void fwd_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) {
+    dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
+    k_fwd_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, src, ll, p.tw, p.mod);
+    k_fwd_rows<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, ll, p.tw, p.mod);
+}
+
+template<int LOGN>
+static void fwd_epi_impl(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st) {
+    dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
+    k_fwd_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(data, data, ll, p.tw, p.mod);
+    k_fwd_rows_epi<LOGN><<<grid, NTT_THREADS, 0, st>>>(data, ll, p.tw, p.mod, ea);
+}
+
+template<int LOGN>
+static void inv_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
+                     cudaStream_t st) {
+    dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
+    k_inv_rows<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, src, ll, p.itw, p.mod);
+    k_inv_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, ll, p.itw, p.mod, fin ? fin : p.inv_fin, fin ? by_slot : 0);
+}
+
+#define PFHE_DISPATCH_LOGN(FN, ...)                                                                       \
+    switch (p.logn) {                                                                                     \
+        case 12: FN<12>(__VA_ARGS__); break;                                                              \
+        case 13: FN<13>(__VA_ARGS__); break;                                                              \
+        case 14: FN<14>(__VA_ARGS__); break;                                                              \
+        case 15: FN<15>(__VA_ARGS__); break;                                                              \
+        case 16: FN<16>(__VA_ARGS__); break;                                                              \
+        case 17: FN<17>(__VA_ARGS__); break;                                                              \
+        default: return cudaErrorInvalidValue;                                                            \
+    }
+
+cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) {
+    if (ll.count == 0) return cudaSuccess;
+    PFHE_DISPATCH_LOGN(fwd_impl, p, dst, src, ll, st)
+    return cudaGetLastError();
+}
+
+cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st) {
+    if (ll.count == 0) return cudaSuccess;
+    PFHE_DISPATCH_LOGN(fwd_epi_impl, p, data, ll, ea, st)
+    return cudaGetLastError();
+}
+
+cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
+                        cudaStream_t st) {
+    if (ll.count == 0) return cudaSuccess;
+    PFHE_DISPATCH_LOGN(inv_impl, p, dst, src, ll, fin, by_slot, st)
+    return cudaGetLastError();
+}
+
+} // namespace pfhe

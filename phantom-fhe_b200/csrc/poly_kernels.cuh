@@ -1,0 +1,200 @@
+// poly_kernels.cuh -- dyadic, base-conversion and key-switch inner-product kernels.
+//
+// Layout everywhere: uint64 words, row-major [poly][limb][coeff] (reference include/ciphertext.h:15-25).
+// All kernels are HBM/L2-bound integer streams: 128-bit vectorised accesses, one pass over the data,
+// constants (moduli, conversion matrices) in registers / shared memory.
+#pragma once
+#include "engine.hpp"
+#include "modarith.cuh"
+
+namespace pfhe {
+
+constexpr int EW_THREADS = 256;
+
+__device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+__device__ __forceinline__ ulonglong2 ld2_nc(const u64 *p) { return __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
+__device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
+
+// ---------------------------------------------------------------------------------------------------
+// (c0,c1) x (c0',c1') -> (d0,d1,d2): d0 = c0c0', d2 = c1c1', d1 = (c0+c1)(c0'+c1') - d0 - d2
+// (tensor_prod_2x2_rns_poly, reference src/polymath.cu:463-498).  out may alias a.
+// grid.y = limb, grid.x * EW_THREADS * 2 = n
+// ---------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u64 *b, u64 *out, const Modulus *mod,
+                                                            size_t n, int l) {
+    const int limb = blockIdx.y;
+    const Modulus m = mod[limb];
+    const size_t poly = (size_t) l * n;
+    const size_t i = (size_t) limb * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const ulonglong2 a0 = ld2(a + i), a1 = ld2(a + i + poly), b0 = ld2(b + i), b1 = ld2(b + i + poly);
+    u64 d0[2], d1[2], d2[2];
+    const u64 A0[2] = {a0.x, a0.y}, A1[2] = {a1.x, a1.y}, B0[2] = {b0.x, b0.y}, B1[2] = {b1.x, b1.y};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        d0[k] = mul_mod(A0[k], B0[k], m);
+        d2[k] = mul_mod(A1[k], B1[k], m);
+        const u64 t = mul_mod(A0[k] + A1[k], B0[k] + B1[k], m);   // sums < 2q < 2^62: product < 2^124
+        d1[k] = sub_mod(sub_mod(t, d0[k], m.q), d2[k], m.q);
+    }
+    st2(out + i, d0[0], d0[1]);
+    st2(out + i + poly, d1[0], d1[1]);
+    st2(out + i + 2 * poly, d2[0], d2[1]);
+}
+
+// tensor_square_2x2_rns_poly (src/polymath.cu:500-532)
+__global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 *out, const Modulus *mod, size_t n,
+                                                               int l) {
+    const int limb = blockIdx.y;
+    const Modulus m = mod[limb];
+    const size_t poly = (size_t) l * n;
+    const size_t i = (size_t) limb * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const ulonglong2 a0 = ld2(a + i), a1 = ld2(a + i + poly);
+    const u64 A0[2] = {a0.x, a0.y}, A1[2] = {a1.x, a1.y};
+    u64 d0[2], d1[2], d2[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        d0[k] = mul_mod(A0[k], A0[k], m);
+        const u64 t = mul_mod(A0[k], A1[k], m);
+        d1[k] = add_mod(t, t, m.q);
+        d2[k] = mul_mod(A1[k], A1[k], m);
+    }
+    st2(out + i, d0[0], d0[1]);
+    st2(out + i + poly, d1[0], d1[1]);
+    st2(out + i + 2 * poly, d2[0], d2[1]);
+}
+
+// generic two-operand limb-wise op (add_rns_poly / sub_rns_poly / multiply_rns_poly, polymath.cu:41-173)
+template<int OP>
+__global__ void __launch_bounds__(EW_THREADS) k_elementwise(const u64 *a, const u64 *b, u64 *out, const Modulus *mod,
+                                                             size_t n) {
+    const int limb = blockIdx.y;
+    const Modulus m = mod[limb];
+    const size_t i = (size_t) limb * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const ulonglong2 x = ld2(a + i);
+    ulonglong2 y = make_ulonglong2(0, 0);
+    if (OP != EW_NEG) y = ld2(b + i);
+    u64 r0, r1;
+    if (OP == EW_ADD) r0 = add_mod(x.x, y.x, m.q), r1 = add_mod(x.y, y.y, m.q);
+    else if (OP == EW_SUB) r0 = sub_mod(x.x, y.x, m.q), r1 = sub_mod(x.y, y.y, m.q);
+    else if (OP == EW_MUL) r0 = mul_mod(x.x, y.x, m), r1 = mul_mod(x.y, y.y, m);
+    else r0 = x.x ? m.q - x.x : 0, r1 = x.y ? m.q - x.y : 0;
+    st2(out + i, r0, r1);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// Fast base conversion, matrix phase (bconv_matmul_*_kernel, reference src/rns_bconv.cu:109-210,455-485):
+//   out[j][x] = sum_i y[i][x] * M[j][i]  mod p_j,   y already scaled by qhat_i^-1 (folded into the iNTT).
+// One thread owns two adjacent coefficients, loads the NI inputs ONCE and produces every output limb
+// (the reference re-reads all inputs per output limb).  Matrix + output moduli staged in shared memory.
+// out_limb[j] gives the destination limb (units of n) so the mod-up "leap over own digit" layout and the
+// plain P->Ql layout share this kernel.  grid.y = problem instance (digit or polynomial).
+// ---------------------------------------------------------------------------------------------------
+struct BconvJob {
+    const u64 *in;        // [ni][n], limb stride n
+    u64 *out;             // base pointer of the output limbs
+    const u64 *mat;       // [no][ni]
+    const short *omod;    // [no] key-level prime row of each output limb
+    const short *olimb;   // [no] output limb index (units of n from `out`)
+    int ni, no;
+};
+constexpr int BCONV_MAX_IN = 8;   // alpha <= 8 per digit on this path (larger digits use the generic loop)
+constexpr int BCONV_MAX_JOBS = 16;
+struct BconvBatch {
+    BconvJob job[BCONV_MAX_JOBS];
+};
+
+template<int NI>
+__global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Modulus *mod, size_t n) {
+    extern __shared__ u64 s_mem[];
+    const BconvJob jb = batch.job[blockIdx.y];
+    const int ni = NI > 0 ? NI : jb.ni;
+    u64 *s_mat = s_mem;                                   // [no][ni]
+    Modulus *s_mod = reinterpret_cast<Modulus *>(s_mem + jb.no * ni);
+    for (int i = threadIdx.x; i < jb.no * ni; i += blockDim.x) s_mat[i] = jb.mat[i];
+    for (int i = threadIdx.x; i < jb.no; i += blockDim.x) s_mod[i] = mod[jb.omod[i]];
+    __syncthreads();
+    const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    if (NI > 0) {
+        u64 y0[NI > 0 ? NI : 1], y1[NI > 0 ? NI : 1];
+#pragma unroll
+        for (int i = 0; i < NI; i++) {
+            const ulonglong2 v = ld2(jb.in + (size_t) i * n + x);
+            y0[i] = v.x, y1[i] = v.y;
+        }
+        for (int j = 0; j < jb.no; j++) {
+            Acc128 a0{0, 0}, a1{0, 0};
+#pragma unroll
+            for (int i = 0; i < NI; i++) {
+                const u64 mji = s_mat[j * NI + i];
+                a0.mac(y0[i], mji);
+                a1.mac(y1[i], mji);
+            }
+            const Modulus m = s_mod[j];
+            st2(jb.out + (size_t) jb.olimb[j] * n + x, barrett128(a0.lo, a0.hi, m), barrett128(a1.lo, a1.hi, m));
+        }
+    } else {
+        for (int j = 0; j < jb.no; j++) {
+            Acc128 a0{0, 0}, a1{0, 0};
+            for (int i = 0; i < ni; i++) {
+                const ulonglong2 v = ld2(jb.in + (size_t) i * n + x);
+                const u64 mji = s_mat[j * ni + i];
+                a0.mac(v.x, mji);
+                a1.mac(v.y, mji);
+            }
+            const Modulus m = s_mod[j];
+            st2(jb.out + (size_t) jb.olimb[j] * n + x, barrett128(a0.lo, a0.hi, m), barrett128(a1.lo, a1.hi, m));
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// key-switch inner product (key_switch_inner_prod_c2_and_evk, reference src/eval_key_switch.cu:14-69):
+//   cx[k][j][x] = sum_{d<beta} t[d][j][x] * evk[d][k][row(j)][x] mod p_row(j),  k = 0,1
+// t = [beta][m][n]; evk = beta device pointers to [2][size_QP][n]; row(j) = j < l ? j : size_Q + (j - l).
+// Streams the key exactly once; 128-bit accumulation, one Barrett reduction per output.
+// grid.y = j, 2 coefficients per thread.
+// ---------------------------------------------------------------------------------------------------
+constexpr int KS_MAX_BETA = 64;
+__global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
+                                                            const Modulus *mod, size_t n, int l, int m, int size_Q,
+                                                            int size_QP, int beta) {
+    const int j = blockIdx.y;
+    const int row = j < l ? j : size_Q + (j - l);
+    const Modulus md = mod[row];
+    const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const size_t m_n = (size_t) m * n, qp_n = (size_t) size_QP * n;
+    Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+    for (int d = 0; d < beta; d++) {
+        const u64 *k0 = evk[d] + (size_t) row * n + x;
+        const ulonglong2 v = ld2(t + (size_t) d * m_n + (size_t) j * n + x);
+        const ulonglong2 e0 = ld2_nc(k0), e1 = ld2_nc(k0 + qp_n);
+        a00.mac(v.x, e0.x);
+        a01.mac(v.y, e0.y);
+        a10.mac(v.x, e1.x);
+        a11.mac(v.y, e1.y);
+    }
+    st2(cx + (size_t) j * n + x, barrett128(a00.lo, a00.hi, md), barrett128(a01.lo, a01.hi, md));
+    st2(cx + m_n + (size_t) j * n + x, barrett128(a10.lo, a10.hi, md), barrett128(a11.lo, a11.hi, md));
+}
+
+// dst[limb i] = src[perm...] helpers -------------------------------------------------------------------
+
+// apply_galois_ntt_permutation (reference src/galois.cu:11-18): dst[l][i] = src[l][perm[i]]
+__global__ void __launch_bounds__(EW_THREADS) k_galois_ntt(u64 *dst, const u64 *src, const uint32_t *perm, size_t n) {
+    const size_t limb = blockIdx.y;
+    const size_t i = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const uint2 p = *reinterpret_cast<const uint2 *>(perm + i);
+    st2(dst + limb * n + i, src[limb * n + p.x], src[limb * n + p.y]);
+}
+
+// CKKS rescale pieces (divide_and_round_q_last_ntt, reference src/rns.cu:1128-1184)
+// r[j][x] = last[x] mod q_j
+__global__ void __launch_bounds__(EW_THREADS) k_reduce_last(u64 *dst, const u64 *last, const Modulus *mod, size_t n) {
+    const int j = blockIdx.y;
+    const Modulus m = mod[j];
+    const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const ulonglong2 v = ld2(last + x);
+    st2(dst + (size_t) j * n + x, barrett64(v.x, m), barrett64(v.y, m));
+}
+
+} // namespace pfhe
