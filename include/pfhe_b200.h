@@ -69,6 +69,12 @@ int pfhe_ntt_forward_inplace(pfhe_engine *e, uint64_t *inout, size_t coeff_modul
 /* nwt_2d_radix8_backward_inplace (src/ntt/intt_2d.cu:724-757) */
 int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t coeff_modulus_size, size_t start_modulus_idx,
                               void *stream);
+/* same transforms for n_poly polynomials laid out [n_poly][coeff_modulus_size][N] in ONE launch pair (the
+ * reference loops over polynomials on the host, e.g. src/rns.cu:1165-1183) */
+int pfhe_ntt_forward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_poly, size_t coeff_modulus_size,
+                                   size_t start_modulus_idx, void *stream);
+int pfhe_ntt_backward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_poly, size_t coeff_modulus_size,
+                                    size_t start_modulus_idx, void *stream);
 /* nwt_2d_radix8_backward (out of place, src/ntt/ntt_modup.cu:320-354) */
 int pfhe_ntt_backward(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t coeff_modulus_size,
                       size_t start_modulus_idx, void *stream);
@@ -137,6 +143,10 @@ int pfhe_mod_switch_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *
 int pfhe_multiply_and_relin_host(pfhe_engine *e, size_t chain_index, const uint64_t *h_encrypted1,
                                  const uint64_t *h_encrypted2, uint64_t *h_destination,
                                  const uint64_t *const *relin_keys, void *stream);
+/* `count` independent ops; copies are double-buffered on internal streams so they overlap the kernels */
+int pfhe_multiply_and_relin_host_batch(pfhe_engine *e, size_t chain_index, const uint64_t *const *h_encrypted1,
+                                       const uint64_t *const *h_encrypted2, uint64_t *const *h_destination,
+                                       size_t count, const uint64_t *const *relin_keys, void *stream);
 int pfhe_rotate_host(pfhe_engine *e, size_t chain_index, const uint64_t *h_encrypted, int step,
                      uint64_t *h_destination, const uint64_t *const *galois_key, void *stream);
 int pfhe_rescale_host(pfhe_engine *e, size_t chain_index, const uint64_t *h_encrypted, size_t size,

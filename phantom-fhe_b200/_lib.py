@@ -31,6 +31,8 @@ _sigs = {
     "pfhe_galois_elt_from_step": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, u32p]),
     "pfhe_ntt_forward_inplace": (ctypes.c_int, [vp, vp, sz, sz, vp]),
     "pfhe_ntt_backward_inplace": (ctypes.c_int, [vp, vp, sz, sz, vp]),
+    "pfhe_ntt_forward_inplace_batch": (ctypes.c_int, [vp, vp, sz, sz, sz, vp]),
+    "pfhe_ntt_backward_inplace_batch": (ctypes.c_int, [vp, vp, sz, sz, sz, vp]),
     "pfhe_ntt_backward": (ctypes.c_int, [vp, vp, vp, sz, sz, vp]),
     "pfhe_ntt_forward_inplace_include_special_mod": (ctypes.c_int, [vp, vp, sz, sz, sz, sz, vp]),
     "pfhe_ntt_backward_inplace_include_special_mod": (ctypes.c_int, [vp, vp, sz, sz, sz, sz, vp]),
@@ -52,6 +54,7 @@ _sigs = {
     "pfhe_rescale_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_mod_switch_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_multiply_and_relin_host": (ctypes.c_int, [vp, sz, vp, vp, vp, vp, vp]),
+    "pfhe_multiply_and_relin_host_batch": (ctypes.c_int, [vp, sz, vp, vp, vp, sz, vp, vp]),
     "pfhe_rotate_host": (ctypes.c_int, [vp, sz, vp, ctypes.c_int, vp, vp, vp]),
     "pfhe_rescale_host": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_ntt_forward_host": (ctypes.c_int, [vp, vp, vp, sz, sz, vp]),

@@ -125,6 +125,22 @@ int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, siz
     API_END
 }
 
+int pfhe_ntt_forward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_poly, size_t count, size_t start,
+                                   void *stream) {
+    API_BEGIN
+    require(start + count <= (size_t) e->impl.size_QP() && n_poly * count < 32768, "modulus index out of range");
+    e->impl.ntt_batch(U(inout), (int) n_poly, (int) count, (int) start, false, S(stream));
+    API_END
+}
+
+int pfhe_ntt_backward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_poly, size_t count, size_t start,
+                                    void *stream) {
+    API_BEGIN
+    require(start + count <= (size_t) e->impl.size_QP() && n_poly * count < 32768, "modulus index out of range");
+    e->impl.ntt_batch(U(inout), (int) n_poly, (int) count, (int) start, true, S(stream));
+    API_END
+}
+
 int pfhe_ntt_backward(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t count, size_t start, void *stream) {
     API_BEGIN
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
@@ -292,6 +308,18 @@ int pfhe_multiply_and_relin_host(pfhe_engine *e, size_t chain_index, const uint6
     PFHE_CUDA(cudaMemcpyAsync(io.p + words, h2, words * 8, cudaMemcpyHostToDevice, S(stream)));
     e->impl.multiply_relin(l, io.p, io.p, io.p + words, K(rlk), S(stream));
     PFHE_CUDA(cudaMemcpyAsync(hout, io.p, words * 8, cudaMemcpyDeviceToHost, S(stream)));
+    API_END
+}
+int pfhe_multiply_and_relin_host_batch(pfhe_engine *e, size_t chain_index, const uint64_t *const *h1,
+                                       const uint64_t *const *h2, uint64_t *const *hout, size_t count,
+                                       const uint64_t *const *rlk, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    require(h1 && h2 && hout, "null batch pointers");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.multiply_relin_host_batch(l, reinterpret_cast<const u64 *const *>(h1),
+                                      reinterpret_cast<const u64 *const *>(h2), reinterpret_cast<u64 *const *>(hout),
+                                      count, K(rlk), S(stream));
     API_END
 }
 int pfhe_rotate_host(pfhe_engine *e, size_t chain_index, const uint64_t *h, int step, uint64_t *hout,

@@ -83,7 +83,15 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
     }
 }
 
-Engine::~Engine() = default;
+Engine::~Engine() {
+    for (int i = 0; i < 2; i++) {
+        if (ev_in_[i]) cudaEventDestroy(ev_in_[i]);
+        if (ev_comp_[i]) cudaEventDestroy(ev_comp_[i]);
+        if (ev_out_[i]) cudaEventDestroy(ev_out_[i]);
+    }
+    if (s_in_) cudaStreamDestroy(s_in_);
+    if (s_out_) cudaStreamDestroy(s_out_);
+}
 
 void Engine::build_tables() {
     std::vector<Tw> tw((size_t) size_QP_ * n_), itw((size_t) size_QP_ * n_), fin((size_t) size_QP_ * 2);
@@ -266,6 +274,16 @@ void Engine::ntt_inv_rows_range(u64 *dst, const u64 *src, int count, int start_r
     run_chunks(v, [&](const LimbList &ll, size_t) { ntt_inv_list(dst, src, ll, nullptr, 0, st); });
 }
 
+void Engine::ntt_batch(u64 *inout, int n_poly, int count, int start_row, bool inverse, cudaStream_t st) const {
+    LimbVec v;
+    for (int p = 0; p < n_poly; p++)
+        for (int i = 0; i < count; i++) v.push(p * count + i, start_row + i);
+    run_chunks(v, [&](const LimbList &ll, size_t) {
+        if (inverse) ntt_inv_list(inout, inout, ll, nullptr, 0, st);
+        else ntt_fwd_list(inout, inout, ll, st);
+    });
+}
+
 void Engine::ntt_special_range(u64 *inout, int count, int start, int size_Ql, bool inverse, cudaStream_t st) const {
     LimbVec v;
     for (int i = 0; i < count; i++) {
@@ -417,6 +435,43 @@ void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, con
     u64 *d = ws_.tmp.p;
     tensor_2x2(ct1, ct2, d, l, st);
     keyswitch(l, out, d + (size_t) 2 * l * n_, rlk, d, st);
+}
+
+void Engine::multiply_relin_host_batch(int l, const u64 *const *h1, const u64 *const *h2, u64 *const *hout,
+                                       size_t count, const u64 *const *rlk, cudaStream_t st) {
+    const size_t words = (size_t) 2 * l * n_;
+    if (!s_in_) {
+        PFHE_CUDA(cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking));
+        PFHE_CUDA(cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking));
+        for (int i = 0; i < 2; i++) {
+            PFHE_CUDA(cudaEventCreateWithFlags(&ev_in_[i], cudaEventDisableTiming));
+            PFHE_CUDA(cudaEventCreateWithFlags(&ev_comp_[i], cudaEventDisableTiming));
+            PFHE_CUDA(cudaEventCreateWithFlags(&ev_out_[i], cudaEventDisableTiming));
+        }
+    }
+    for (int i = 0; i < 2; i++) {
+        if (pipe_in_[i].count < 2 * words) pipe_in_[i].alloc(2 * words);
+        if (pipe_out_[i].count < words) pipe_out_[i].alloc(words);
+    }
+    // side streams start after whatever the caller already queued on `st`
+    PFHE_CUDA(cudaEventRecord(ev_comp_[0], st));
+    PFHE_CUDA(cudaStreamWaitEvent(s_in_, ev_comp_[0], 0));
+    PFHE_CUDA(cudaStreamWaitEvent(s_out_, ev_comp_[0], 0));
+    for (size_t i = 0; i < count; i++) {
+        const int b = (int) (i & 1);
+        if (i >= 2) PFHE_CUDA(cudaStreamWaitEvent(s_in_, ev_comp_[b], 0));   // input buffer b consumed
+        PFHE_CUDA(cudaMemcpyAsync(pipe_in_[b].p, h1[i], words * 8, cudaMemcpyHostToDevice, s_in_));
+        PFHE_CUDA(cudaMemcpyAsync(pipe_in_[b].p + words, h2[i], words * 8, cudaMemcpyHostToDevice, s_in_));
+        PFHE_CUDA(cudaEventRecord(ev_in_[b], s_in_));
+        PFHE_CUDA(cudaStreamWaitEvent(st, ev_in_[b], 0));
+        if (i >= 2) PFHE_CUDA(cudaStreamWaitEvent(st, ev_out_[b], 0));       // output buffer b drained
+        multiply_relin(l, pipe_out_[b].p, pipe_in_[b].p, pipe_in_[b].p + words, rlk, st);
+        PFHE_CUDA(cudaEventRecord(ev_comp_[b], st));
+        PFHE_CUDA(cudaStreamWaitEvent(s_out_, ev_comp_[b], 0));
+        PFHE_CUDA(cudaMemcpyAsync(hout[i], pipe_out_[b].p, words * 8, cudaMemcpyDeviceToHost, s_out_));
+        PFHE_CUDA(cudaEventRecord(ev_out_[b], s_out_));
+    }
+    for (int b = 0; b < 2 && (size_t) b < count; b++) PFHE_CUDA(cudaStreamWaitEvent(st, ev_out_[b], 0));
 }
 
 // apply_galois_inplace for CKKS/BGV (reference src/evaluate.cu:1567-1630)

@@ -38,6 +38,11 @@ __device__ __forceinline__ u64 mul_shoup_lazy(u64 x, u64 w, u64 ws, u64 q) {
     return x * w - hi * q;
 }
 
+// same with the negated modulus nq = 2^64 - q: one multiply-accumulate chain, no subtraction
+__device__ __forceinline__ u64 mul_shoup_lazy_neg(u64 x, u64 w, u64 ws, u64 nq) {
+    return x * w + mulhi(x, ws) * nq;
+}
+
 // canonical Shoup product (multiply_and_reduce_shoup, uintmodmath.cuh:207-216)
 __device__ __forceinline__ u64 mul_shoup(u64 x, u64 w, u64 ws, u64 q) { return csub(mul_shoup_lazy(x, w, ws, q), q); }
 __device__ __forceinline__ u64 mul_shoup(u64 x, Tw w, u64 q) { return csub(mul_shoup_lazy(x, w.x, w.y, q), q); }

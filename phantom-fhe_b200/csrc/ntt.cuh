@@ -5,9 +5,10 @@
 //
 //  * N = 2^P1 * 2^P2.  A "column pass" runs the P1 stages whose butterfly span is >= 2^P2 on tiles of
 //    2^P1 rows x C adjacent columns, a "row pass" runs the remaining P2 stages on tiles of C contiguous rows.
-//    Every CTA owns a 4096-element tile (256 threads x 16 elements); each thread keeps its 16 elements in
-//    registers and runs up to 4 merged stages (radix-16) per round, rounds exchange through a skewed,
-//    bank-conflict-free shared-memory tile, so a 2^16-point transform is 2 passes x 2 rounds.
+//    Every CTA owns a 2048-element tile (256 threads x 8 elements); each thread keeps its 8 elements in
+//    registers and runs up to 3 merged stages (radix-8) per round, rounds exchange through a skewed,
+//    bank-conflict-free shared-memory tile, so a 2^16-point transform is 2 passes x 3 rounds.  (A 16-element
+//    / radix-16 variant was measured first: fewer exchanges but half the warps, IPC 0.43 -- see DESIGN.md.)
 //  * Lazy ranges are tracked at compile time: forward butterflies issue a conditional subtraction only on
 //    every second stage (values < 8q < 2^64 for q < 2^61), the result is made canonical once at the end.
 //  * Twiddles are (w, floor(w 2^64/q)) pairs fetched with one 128-bit load; the table is stored in a
@@ -21,11 +22,13 @@
 
 namespace pfhe {
 
-constexpr int NTT_THREADS = 256;
-constexpr int NTT_EPT = 16;
-constexpr int NTT_LOG_TILE = 12;
+constexpr int NTT_LOG_THREADS = 8;
+constexpr int NTT_THREADS = 1 << NTT_LOG_THREADS;
+constexpr int NTT_LOG_EPT = 3;                       // elements per thread = one radix-8 group
+constexpr int NTT_EPT = 1 << NTT_LOG_EPT;
+constexpr int NTT_LOG_TILE = NTT_LOG_THREADS + NTT_LOG_EPT;
 constexpr int NTT_TILE = 1 << NTT_LOG_TILE;
-constexpr int NTT_SMEM_WORDS = NTT_TILE + (NTT_TILE >> 4);
+constexpr int NTT_SMEM_WORDS = NTT_TILE;
 constexpr int NTT_MAX_LIMBS = 128;
 
 // which limbs a launch touches: slot i works on data limb `data[i]` (units of N words from the base
@@ -51,10 +54,10 @@ struct EpiArgs {
     short add[NTT_MAX_LIMBS];    // -1: nothing to add
 };
 
-// round schedule of a pass with P stages: ceil(P/4) rounds of 3..4 (or fewer) stages
+// round schedule of a pass with P stages: ceil(P/LOG_EPT) rounds, the earlier rounds take the remainder
 template<int P>
 struct Sched {
-    static constexpr int NR = (P + 3) / 4;
+    static constexpr int NR = (P + NTT_LOG_EPT - 1) / NTT_LOG_EPT;
     static constexpr int r(int i) { return P / NR + (i < P % NR ? 1 : 0); }
     static constexpr int s0(int i) {
         int s = 0;
@@ -69,7 +72,7 @@ __host__ __device__ constexpr int ntt_p2(int logn) { return logn - logn / 2; }
 // position of the twiddle for global stage s, block B inside the per-limb table (host + device)
 __host__ __device__ inline size_t tw_native_index(int logn, int s, size_t B) {
     const int p1 = ntt_p1(logn), p2 = ntt_p2(logn);
-    const int nr = (p2 + 3) / 4;
+    const int nr = (p2 + NTT_LOG_EPT - 1) / NTT_LOG_EPT;
     const int rlast = p2 / nr;               // the last round never gets a remainder stage
     const int s0last = p2 - rlast;
     if (s < p1 + s0last) return ((size_t) 1 << s) + B;
@@ -79,7 +82,13 @@ __host__ __device__ inline size_t tw_native_index(int logn, int s, size_t B) {
     return ((size_t) 1 << s) + (row << sigma) + (b << s0last) + hi;
 }
 
-__device__ __forceinline__ int skew(int i) { return i + (i >> 4); }
+// XOR swizzle of the exchange tile (64-bit words, 16 words per shared-memory wavefront).  The access
+// patterns of the radix-8 rounds are: 16 contiguous words; 4 contiguous x 4 blocks 32 apart; 16 lanes 4
+// apart; 8 contiguous x 2 blocks 32 apart.  Folding bits 4..6 into bits 0..3 makes all of them hit 16
+// distinct bank pairs (derivation in DESIGN.md); it is a bijection inside every aligned 128-word block.
+__device__ __forceinline__ int skew(int i) {
+    return i ^ ((i >> 4) & 3) ^ (((i >> 5) & 1) << 3) ^ (((i >> 6) & 1) << 2);
+}
 
 // ----------------------------------------------------------------------------------------------------
 // element <-> thread mapping of one round
@@ -90,13 +99,15 @@ struct RoundMap {
     static constexpr int S0 = Sched<P>::s0(RI);
     static constexpr int LAM = P - S0 - R;           // bits of the low index
     static constexpr int GAM = NTT_LOG_TILE - P;     // bits of the batch index (columns resp. rows per tile)
-    static constexpr int GB = 4 - R;
+    static constexpr int GB = NTT_LOG_EPT - R;
     static constexpr int G = 1 << GB;                // independent radix-2^R groups per thread
     static constexpr int T = 1 << P;
     static constexpr int C = 1 << GAM;
     static constexpr bool LAST = (RI == Sched<P>::NR - 1);
-    // groups of one thread use the same twiddles?
-    static constexpr bool SHARE = ROWS ? (LAM >= GB) : (GAM + LAM >= GB);
+    // a thread's G groups sit NTT_THREADS apart in the packed (hi, lo, batch) index, i.e. they differ in its
+    // top bits; they use the same twiddles only when those bits belong to the low index
+    static constexpr bool SHARE = !ROWS && S0 == 0 && LAM >= GB;
+    __device__ static __forceinline__ int mu(int tid, int g) { return (g << NTT_LOG_THREADS) | tid; }
 
     __device__ static __forceinline__ void decode(int mu, int &hi, int &lo, int &c) {
         if constexpr (!ROWS) {
@@ -121,7 +132,7 @@ template<bool CSUB>
 __device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, const Tw w, const u64 q, const u64 q2, const u64 q4) {
     u64 X = x;
     if constexpr (CSUB) X = csub(X, q4);
-    const u64 t = mul_shoup_lazy(y, w.x, w.y, q);
+    const u64 t = mul_shoup_lazy_neg(y, w.x, w.y, 0 - q);
     x = X + t;
     y = X + q2 - t;
 }
@@ -133,7 +144,7 @@ __device__ __forceinline__ void gs_bfly(u64 &x, u64 &y, const Tw w, const u64 q,
     const u64 s = csub(x + y, q2);
     const u64 d = x + q2 - y;
     x = s;
-    y = mul_shoup_lazy(d, w.x, w.y, q);
+    y = mul_shoup_lazy_neg(d, w.x, w.y, 0 - q);
 }
 // last inverse stage: folds n^-1 (and an optional per-limb scalar) into both outputs, canonical results
 // (replaces intt_2d.cu:195-203 "lower half times n^-1, upper half through itw[1]")
@@ -160,7 +171,7 @@ __device__ __forceinline__ int tw_index(int u, int hi, int b, int row) {
 
 // one forward round on the 16 registers of a thread: x[g * 2^R + k]
 template<class M, bool ROWS, int LOGN, int SBASE>
-__device__ __forceinline__ void fwd_round(u64 (&x)[16], const Tw *__restrict__ tw, const int (&hi)[M::G],
+__device__ __forceinline__ void fwd_round(u64 (&x)[NTT_EPT], const Tw *__restrict__ tw, const int (&hi)[M::G],
                                           const int (&row)[M::G], u64 q, u64 q2, u64 q4) {
     constexpr int R = M::R;
 #pragma unroll
@@ -190,7 +201,7 @@ __device__ __forceinline__ void fwd_round(u64 (&x)[16], const Tw *__restrict__ t
 
 // one inverse round (stages S0+R-1 down to S0).  FINAL marks the round containing global stage 0.
 template<class M, bool ROWS, int LOGN, bool FINAL>
-__device__ __forceinline__ void inv_round(u64 (&x)[16], const Tw *__restrict__ tw, const int (&hi)[M::G],
+__device__ __forceinline__ void inv_round(u64 (&x)[NTT_EPT], const Tw *__restrict__ tw, const int (&hi)[M::G],
                                           const int (&row)[M::G], u64 q, u64 q2, Tw fin_x, Tw fin_y) {
     constexpr int R = M::R;
 #pragma unroll
@@ -247,7 +258,7 @@ __device__ __forceinline__ size_t gl_index(int e, int c, int tile) {
 template<int P, bool ROWS, int LOGN, int SBASE, class Load, class Store>
 __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load load, Store store) {
     constexpr int NR = Sched<P>::NR;
-    u64 x[16];
+    u64 x[NTT_EPT];
     const int tid = threadIdx.x;
 
     auto run_round = [&](auto ri_tag) {
@@ -256,7 +267,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load 
         int hi[M::G], lo[M::G], c[M::G], row[M::G];
 #pragma unroll
         for (int g = 0; g < M::G; g++) {
-            M::decode((tid << M::GB) | g, hi[g], lo[g], c[g]);
+            M::decode(M::mu(tid, g), hi[g], lo[g], c[g]);
             row[g] = (cx.tile << M::GAM) + c[g];
         }
         // gather
@@ -302,7 +313,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load 
 template<int P, bool ROWS, int LOGN, bool FINAL, class Load, class Store>
 __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx &cx, Load load, Store store) {
     constexpr int NR = Sched<P>::NR;
-    u64 x[16];
+    u64 x[NTT_EPT];
     const int tid = threadIdx.x;
 
     if constexpr (ROWS) {
@@ -322,7 +333,7 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx &cx, Load 
         int hi[M::G], lo[M::G], c[M::G], row[M::G];
 #pragma unroll
         for (int g = 0; g < M::G; g++) {
-            M::decode((tid << M::GB) | g, hi[g], lo[g], c[g]);
+            M::decode(M::mu(tid, g), hi[g], lo[g], c[g]);
             row[g] = (cx.tile << M::GAM) + c[g];
         }
         constexpr bool DIRECT_IN = (RI == NR - 1) && !ROWS;

@@ -4,7 +4,7 @@
 namespace pfhe {
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, const Tw *tw,
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, const Tw *tw,
                                                            const Modulus *mod) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
@@ -19,7 +19,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_cols(u64 *dst, const u64 *s
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_fwd_rows(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
@@ -33,7 +33,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_rows(u64 *data, LimbList ll
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_fwd_rows_epi(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod,
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows_epi(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod,
                                                                EpiArgs ea) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
@@ -57,7 +57,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_fwd_rows_epi(u64 *data, LimbLis
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_inv_rows(u64 *dst, const u64 *src, LimbList ll, const Tw *itw,
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_rows(u64 *dst, const u64 *src, LimbList ll, const Tw *itw,
                                                            const Modulus *mod) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
@@ -72,7 +72,7 @@ __global__ void __launch_bounds__(NTT_THREADS) k_inv_rows(u64 *dst, const u64 *s
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS) k_inv_cols(u64 *data, LimbList ll, const Tw *itw, const Modulus *mod,
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_cols(u64 *data, LimbList ll, const Tw *itw, const Modulus *mod,
                                                            const Tw *fin, int fin_by_slot) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;

@@ -1,0 +1,76 @@
+"""Host-side logic of the mirror interface that needs no GPU: NAF rotation decomposition, parameter plumbing,
+batch sharding (incl. a world_size-2 gloo run)."""
+import os
+import subprocess
+import sys
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_naf_matches_reference_definition():
+    from phantom_fhe_b200.api import _naf
+    for v in list(range(-70, 71)) + [1000, -1234, 32767]:
+        parts = _naf(v)
+        assert sum(parts) == v
+        mags = sorted(abs(p) for p in parts)
+        assert all(m & (m - 1) == 0 for m in mags)            # powers of two
+        assert all(b >= 4 * a or b >= 2 * a for a, b in zip(mags, mags[1:]))
+        for a, b in zip(mags, mags[1:]):
+            assert b != 2 * a                                   # non-adjacent
+    assert _naf(3) == [-1, 4] and _naf(7) == [-1, 8] and _naf(0) == []
+
+
+def test_encryption_parameters_errors():
+    import phantom_fhe_b200 as pf
+    p = pf.EncryptionParameters()
+    with pytest.raises(RuntimeError):
+        p.set_coeff_modulus([97])
+    p = pf.EncryptionParameters(pf.scheme_type.ckks)
+    with pytest.raises(RuntimeError):
+        p.set_plain_modulus(65537)
+    p.set_special_modulus_size(4)
+    assert p.special_modulus_size == 4
+
+
+def test_shard_range_partitions_everything():
+    from phantom_fhe_b200.shard import shard_range
+    for total in (0, 1, 7, 8, 1024, 1000):
+        for world in (1, 2, 3, 4, 8):
+            got = []
+            for r in range(world):
+                b, e = shard_range(total, r, world)
+                assert 0 <= b <= e <= total
+                got.extend(range(b, e))
+            assert got == list(range(total))
+    with pytest.raises(ValueError):
+        shard_range(4, 2, 2)
+
+
+WORKER = r"""
+import os, sys
+sys.path.insert(0, {root!r})
+import torch, torch.distributed as dist
+from phantom_fhe_b200.shard import shard_range, max_over_ranks
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:{port}", rank=int(sys.argv[1]), world_size=2)
+rank = dist.get_rank()
+b, e = shard_range(1024, rank, 2)
+mine = torch.zeros(1024, dtype=torch.int64); mine[b:e] = 1
+dist.all_reduce(mine)
+assert int(mine.sum()) == 1024 and int(mine.max()) == 1          # disjoint cover, no collective on the data path
+t = max_over_ranks(10.0 + rank, dist)
+assert t == 11.0
+dist.barrier(); dist.destroy_process_group()
+print("ok", rank)
+"""
+
+
+def test_two_rank_gloo_sharding(tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER.format(root=ROOT, port=29000 + os.getpid() % 2000))
+    procs = [subprocess.Popen([sys.executable, str(script), str(r)], stdout=subprocess.PIPE, stderr=subprocess.STDOUT,
+                              text=True) for r in range(2)]
+    outs = [p.communicate(timeout=240)[0] for p in procs]
+    for p, o in zip(procs, outs):
+        assert p.returncode == 0, o

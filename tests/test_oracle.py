@@ -1,0 +1,207 @@
+"""CPU tests of the oracle (test infrastructure): golden fixtures generated from the reference's own host code
+(tests/golden/host_tables.json, make_golden.py), the survey's known-answer anchor, algebraic properties, and --
+when oracle/_ref was built -- a live comparison with the reference host library."""
+import ctypes
+import hashlib
+import json
+import os
+
+import numpy as np
+import pytest
+
+import harness as H
+from harness import P
+
+GOLD = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "host_tables.json")))
+
+
+def test_prime_chains_match_reference_create():
+    o = H.oracle()
+    for name, cfg in GOLD["configs"].items():
+        bits = (ctypes.c_int * len(cfg["bits"]))(*cfg["bits"])
+        out = np.zeros(len(cfg["bits"]), dtype=np.uint64)
+        assert o.orc_create_primes(cfg["n"], bits, len(cfg["bits"]), P(out)) == 0
+        assert [int(v) for v in out] == cfg["primes"], name
+
+
+def test_ntt_tables_match_reference_host_ntt():
+    o = H.oracle()
+    for key, t in GOLD["tables"].items():
+        logn, q = (int(x) for x in key.split(":"))
+        n = 1 << logn
+        pr = np.array([q], dtype=np.uint64)
+        c = o.orc_create(3, n, P(pr), 1, 0, 0)
+        assert c
+        assert o.orc_minimal_primitive_root(2 * n, q) == t["root"]
+        assert o.orc_n_inv(c, 0) == t["n_inv"]
+        assert o.orc_shoup(t["n_inv"], q) == t["n_inv_shoup"]
+        ratio = np.zeros(3, dtype=np.uint64)
+        o.orc_barrett_ratio(q, P(ratio))
+        assert [int(v) for v in ratio] == t["ratio"]
+        for i, f in enumerate(("orc_twiddle", "orc_twiddle_shoup", "orc_itwiddle", "orc_itwiddle_shoup")):
+            arr = np.ctypeslib.as_array(getattr(o, f)(c, 0), shape=(n,))
+            assert [int(v) for v in arr[:8]] == t[["tw_head", "tws_head", "itw_head", "itws_head"][i]]
+            assert hashlib.sha256(arr.tobytes()).hexdigest() == t["sha256"][i], (key, f)
+        o.orc_destroy(c)
+
+
+def test_galois_elements():
+    o = H.oracle()
+    for n, table in GOLD["galois"].items():
+        for step, elt in table.items():
+            assert o.orc_galois_elt_from_step(int(step), int(n)) == elt
+
+
+def test_known_answer_config1():
+    """x_j = mt19937_64(1)() % q at N=4096, q=1125899906826241."""
+    o = H.oracle()
+    ps = H.params_c1()
+    x = np.zeros(ps.n, dtype=np.uint64)
+    o.orc_mt19937_64_fill(1, int(ps.primes[0]), P(x), ps.n, 0)
+    assert int(x[0]) == 2469588189546311528 % 1125899906826241  # first mt19937_64(1) output
+    y = x.copy()
+    idx = (ctypes.c_int * 1)(0)
+    o.orc_ntt_forward(ps.octx(), P(y), 1, idx)
+    assert [int(v) for v in y[:4]] == [213908721093404, 678455973401121, 1034267331304760, 457393895113370]
+    o.orc_ntt_inverse(ps.octx(), P(y), 1, idx)
+    assert np.array_equal(x, y)
+
+
+def test_ntt_is_negacyclic_convolution():
+    """NTT(a) * NTT(b) = NTT(a * b mod X^N + 1): pins the transform against schoolbook multiplication."""
+    o = H.oracle()
+    ps = H.ParamSet("tiny", 4096, [40], 0)
+    q = int(ps.primes[0])
+    rng = np.random.default_rng(5)
+    n = ps.n
+    a = np.zeros(n, dtype=np.uint64)
+    b = np.zeros(n, dtype=np.uint64)
+    ia, ib = rng.integers(0, n, 6), rng.integers(0, n, 5)
+    a[ia] = rng.integers(1, q, 6).astype(np.uint64)
+    b[ib] = rng.integers(1, q, 5).astype(np.uint64)
+    want = [0] * n
+    for i in np.nonzero(a)[0]:
+        for j in np.nonzero(b)[0]:
+            k, v = int(i + j), int(a[i]) * int(b[j])
+            if k >= n:
+                k, v = k - n, -v
+            want[k] = (want[k] + v) % q
+    fa, fb = a.copy(), b.copy()
+    idx = (ctypes.c_int * 1)(0)
+    o.orc_ntt_forward(ps.octx(), P(fa), 1, idx)
+    o.orc_ntt_forward(ps.octx(), P(fb), 1, idx)
+    prod = np.array([(int(x) * int(y)) % q for x, y in zip(fa, fb)], dtype=np.uint64)
+    o.orc_ntt_inverse(ps.octx(), P(prod), 1, idx)
+    assert [int(v) for v in prod] == want
+
+
+def _crt_poly(ps, limbs):
+    """centered CRT lift of [l][n] residues (python ints)"""
+    primes = [int(p) for p in ps.primes[: limbs.shape[0]]]
+    Q = 1
+    for p in primes:
+        Q *= p
+    vals = [0] * limbs.shape[1]
+    for i, p in enumerate(primes):
+        Qi = Q // p
+        c = (Qi * pow(Qi, -1, p)) % Q
+        for x in range(limbs.shape[1]):
+            vals[x] = (vals[x] + int(limbs[i, x]) * c) % Q
+    return vals, Q
+
+
+def test_keyswitch_is_hybrid_keyswitch():
+    """Semantic pin of modup/inner-product/moddown: with evk_d = (P * qhat_d * qhat_d^-1-ish gadget) * s' the output of
+    the path must equal c2 * s' up to the rounding error of mod-down -- checked through a noise-free gadget key:
+    evk_d[0] = P * g_d * s2 (no mask), evk_d[1] = 0, so keyswitch(c2) = (round-ish(c2 * s2), 0)."""
+    o = H.oracle()
+    ps = H.params_small(4096, l=4, alpha=2)
+    oc, n, l = ps.octx(), ps.n, ps.limbs()
+    m, beta = l + ps.size_P, ps.beta()
+    primes = [int(p) for p in ps.primes]
+    Qs, Ps = primes[:l], primes[ps.size_Q:]
+    Pbig = 1
+    for p in Ps:
+        Pbig *= p
+    rng = np.random.default_rng(3)
+    # s2: small ternary polynomial in NTT form over all QP limbs
+    s_coeff = rng.integers(-1, 2, n)
+    s_ntt = np.zeros((ps.size_QP, n), dtype=np.uint64)
+    for r, p in enumerate(primes):
+        s_ntt[r] = np.array([(int(v) % p) for v in s_coeff], dtype=np.uint64)
+    idx_all = (ctypes.c_int * ps.size_QP)(*range(ps.size_QP))
+    o.orc_ntt_forward(oc, P(s_ntt), ps.size_QP, idx_all)
+    # gadget: g_d = Qhat_d * (Qhat_d^-1 mod Q_d) where Q_d = product of digit d's primes
+    Q = 1
+    for p in Qs:
+        Q *= p
+    evk = np.zeros((beta, 2, ps.size_QP, n), dtype=np.uint64)
+    for d in range(beta):
+        dig = Qs[d * ps.size_P:(d + 1) * ps.size_P]
+        Qd = 1
+        for p in dig:
+            Qd *= p
+        Qhat = Q // Qd
+        g = Pbig * Qhat * pow(Qhat, -1, Qd)
+        for r, p in enumerate(primes):
+            gm = g % p
+            evk[d, 0, r] = np.array([(int(v) * gm) % p for v in s_ntt[r]], dtype=np.uint64)
+    c2 = H.uniform_limbs(ps, list(range(l)), 77)[0]
+    ct = np.zeros((2, l, n), dtype=np.uint64)
+    o.orc_keyswitch(oc, l, P(ct), P(c2), P(evk))
+    assert not ct[1].any()
+    # expected: c2 * s2 mod Q (negacyclic), compare in coefficient domain with tolerance from mod-down rounding
+    idx = (ctypes.c_int * l)(*range(l))
+    got = ct[0].copy()
+    o.orc_ntt_inverse(oc, P(got), l, idx)
+    prod = np.zeros((l, n), dtype=np.uint64)
+    for r in range(l):
+        p = primes[r]
+        prod[r] = np.array([(int(x) * int(y)) % p for x, y in zip(c2[r], s_ntt[r])], dtype=np.uint64)
+    o.orc_ntt_inverse(oc, P(prod), l, idx)
+    gv, Qm = _crt_poly(ps, got[:, :64])
+    pv, _ = _crt_poly(ps, prod[:, :64])
+    for x in range(64):
+        diff = (gv[x] - pv[x]) % Qm
+        diff = min(diff, Qm - diff)
+        assert diff <= beta * ps.size_P * n, diff  # fast-base-conversion overflow + floor error, tiny vs Q
+
+
+def test_rescale_divides_by_last_prime():
+    o = H.oracle()
+    ps = H.params_small(4096, l=3, alpha=1)
+    oc, n, l = ps.octx(), ps.n, ps.limbs()
+    ct = H.ciphertext(ps, 4, polys=1)
+    out = np.zeros((1, l - 1, n), dtype=np.uint64)
+    src = ct.copy()
+    o.orc_rescale(oc, l, P(src), 1, P(out))
+    idx = (ctypes.c_int * l)(*range(l))
+    coeff = ct[0].copy()
+    o.orc_ntt_inverse(oc, P(coeff), l, idx)
+    res = out[0].copy()
+    o.orc_ntt_inverse(oc, P(res), l - 1, idx)
+    v, Q = _crt_poly(ps, coeff[:, :32])
+    w, Q2 = _crt_poly(ps, res[:, :32])
+    ql = int(ps.primes[l - 1])
+    for x in range(32):
+        assert (v[x] - (v[x] % ql)) // ql % Q2 == w[x]  # floor division by q_last (rns.cu:1141-1158)
+
+
+@pytest.mark.skipif(H.reference() is None, reason="oracle/_ref not built")
+def test_live_against_reference_host_code():
+    r, o = H.reference(), H.oracle()
+    bits = [60] + [40] * 15 + [60] * 4
+    arr = (ctypes.c_int * len(bits))(*bits)
+    a, b = np.zeros(20, dtype=np.uint64), np.zeros(20, dtype=np.uint64)
+    assert r.ref_host_create_primes(65536, arr, 20, P(a)) == 0
+    assert o.orc_create_primes(65536, arr, 20, P(b)) == 0
+    assert np.array_equal(a, b)
+    for case in GOLD["bconv"]:
+        ib, ob = case["ibase"], case["obase"]
+        for j, p in enumerate(ob):
+            for i in range(len(ib)):
+                want = 1
+                for k, qk in enumerate(ib):
+                    if k != i:
+                        want = want * qk % p
+                assert case["qhat_mod_p"][j * len(ib) + i] == want
