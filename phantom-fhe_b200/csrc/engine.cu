@@ -2,6 +2,7 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <cstdlib>
 #include <cstring>
 #include <functional>
 
@@ -13,6 +14,12 @@ namespace pfhe {
 namespace hm = pfhe::host;
 
 std::atomic<unsigned long long> g_launches{0};
+
+static int ceil_log2(int v) {
+    int g = 0;
+    while ((1 << g) < v) g++;
+    return g;
+}
 
 static Tw make_tw(u64 w, u64 q) { return make_ulonglong2(w, hm::shoup(w, q)); }
 
@@ -93,7 +100,30 @@ Engine::~Engine() {
     if (s_out_) cudaStreamDestroy(s_out_);
 }
 
+Tw Engine::make_tw_row(int row, u64 w) const {
+    const u64 q = primes_[row];
+    if (!is_fp_[row]) return make_tw(w, q);
+    const double dw = (double) w, dq = (double) q;
+    const double winv = dw / dq;
+    u64 a, b;
+    std::memcpy(&a, &dw, 8);
+    std::memcpy(&b, &winv, 8);
+    return make_ulonglong2(a, b);
+}
+
 void Engine::build_tables() {
+    // FP64 butterflies need |values| < 2^51 over up to 17 lazy stages: q < 2^46.  PFHE_FP64_NTT=0
+    // forces the integer path everywhere (A/B measurements).
+    const char *env = std::getenv("PFHE_FP64_NTT");
+    const bool allow_fp = !(env && env[0] == '0');
+    is_fp_.assign(size_QP_, 0);
+    std::vector<double2> fpc(size_QP_);
+    for (int i = 0; i < size_QP_; i++) {
+        is_fp_[i] = allow_fp && (primes_[i] >> 46) == 0;
+        fpc[i] = make_double2((double) primes_[i], 1.0 / (double) primes_[i]);
+    }
+    d_is_fp_.upload(is_fp_);
+    d_fpc_.upload(fpc);
     std::vector<Tw> tw((size_t) size_QP_ * n_), itw((size_t) size_QP_ * n_), fin((size_t) size_QP_ * 2);
     std::vector<Modulus> mods(size_QP_);
     h_ninv_.resize(size_QP_);
@@ -105,7 +135,7 @@ void Engine::build_tables() {
         const u64 psi = hm::minimal_primitive_root(2 * n_, q);
         const u64 ipsi = hm::invmod(psi, q);
         Tw *f = tw.data() + (size_t) i * n_, *b = itw.data() + (size_t) i * n_;
-        f[0] = b[0] = make_tw(1, q);
+        f[0] = b[0] = make_tw_row(i, 1);
         u64 pw = psi, ipw = ipsi;
         for (size_t k = 1; k < n_; k++) {
             // standard position bitrev(k) = 2^s + B  ->  kernel-native position
@@ -113,22 +143,44 @@ void Engine::build_tables() {
             int s = 31 - __builtin_clz(r);
             const size_t B = r - ((size_t) 1 << s);
             const size_t pos = tw_native_index(logn_, s, B);
-            f[pos] = make_tw(pw, q);
-            b[pos] = make_tw(ipw, q);
+            f[pos] = make_tw_row(i, pw);
+            b[pos] = make_tw_row(i, ipw);
             if (r == 1) h_itw1_[i] = ipw;
             pw = hm::mulmod(pw, psi, q);
             ipw = hm::mulmod(ipw, ipsi, q);
         }
         const u64 ninv = hm::invmod(n_ % q, q);
         h_ninv_[i] = ninv;
-        fin[2 * i] = make_tw(ninv, q);
-        fin[2 * i + 1] = make_tw(hm::mulmod(h_itw1_[i], ninv, q), q);
+        fin[2 * i] = make_tw_row(i, ninv);
+        fin[2 * i + 1] = make_tw_row(i, hm::mulmod(h_itw1_[i], ninv, q));
     }
     d_tw_.upload(tw);
     d_itw_.upload(itw);
     d_inv_fin_.upload(fin);
     d_mod_.upload(mods);
-    plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p};
+    // single-word Barrett constants: growth class g covers values < 2^(2k+g), k = bit length of q
+    std::vector<BarG> bars((size_t) 64 * size_QP_);
+    for (int g = 0; g < 64; g++)
+        for (int i = 0; i < size_QP_; i++) {
+            const u64 q = primes_[i];
+            const int k = 64 - __builtin_clzll(q);
+            BarG b{0, 0xffu, 0};
+            if (k + g <= 63) {
+                const int sh = std::max(0, 2 * k + g - 64);
+                b.sh = (u32) sh;
+                b.mu = (u64) ((((unsigned __int128) 1) << (64 + sh)) / q);   // < 2^64 because sh <= k - 1
+            }
+            bars[(size_t) g * size_QP_ + i] = b;
+        }
+    d_bar_.upload(bars);
+    plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p, d_is_fp_.p, d_fpc_.p};
+}
+
+const BarG *Engine::bar(int terms, int extra_bits) const {
+    int g = extra_bits;
+    while ((1 << (g - extra_bits)) < terms) g++;
+    if (g > 63) g = 63;   // classes that do not apply to a modulus fall back to the two-word Barrett
+    return d_bar_.p + (size_t) g * size_QP_;
 }
 
 int Engine::limbs_at(size_t chain_index) const {
@@ -171,8 +223,8 @@ void Engine::build_level(int l) {
                 const u64 q = ibase[i];
                 const u64 hinv = hm::invmod(hm::product_mod(ibase, i, q), q);
                 const u64 c = hm::mulmod(hinv, h_ninv_[start + i], q);
-                fin[2 * (start + i)] = make_tw(c, q);
-                fin[2 * (start + i) + 1] = make_tw(hm::mulmod(c, h_itw1_[start + i], q), q);
+                fin[2 * (start + i)] = make_tw_row(start + i, c);
+                fin[2 * (start + i) + 1] = make_tw_row(start + i, hm::mulmod(c, h_itw1_[start + i], q));
                 finc[start + i] = make_tw(hinv, q);
             }
             lv->digit_start.push_back(start);
@@ -205,8 +257,8 @@ void Engine::build_level(int l) {
                 const u64 p = pbase[i];
                 const u64 hinv = hm::invmod(hm::product_mod(pbase, i, p), p);
                 const u64 c = hm::mulmod(hinv, h_ninv_[size_Q_ + i], p);
-                dfin[2 * (k * alpha + i)] = make_tw(c, p);
-                dfin[2 * (k * alpha + i) + 1] = make_tw(hm::mulmod(c, h_itw1_[size_Q_ + i], p), p);
+                dfin[2 * (k * alpha + i)] = make_tw_row(size_Q_ + i, c);
+                dfin[2 * (k * alpha + i) + 1] = make_tw_row(size_Q_ + i, hm::mulmod(c, h_itw1_[size_Q_ + i], p));
             }
         std::vector<u64> dmat((size_t) l * alpha);
         std::vector<short> dmod(l), dlimb(l);
@@ -298,40 +350,40 @@ void Engine::ntt_special_range(u64 *inout, int count, int start, int size_Ql, bo
 
 void Engine::tensor_2x2(const u64 *a, const u64 *b, u64 *out, int l, cudaStream_t st) const {
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
-    k_tensor_2x2<<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_, l);
+    k_tensor_2x2<<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 2), n_, l);
     check_launch("k_tensor_2x2");
 }
 
 void Engine::tensor_square(const u64 *a, u64 *out, int l, cudaStream_t st) const {
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
-    k_tensor_square<<<grid, EW_THREADS, 0, st>>>(a, out, d_mod_.p, n_, l);
+    k_tensor_square<<<grid, EW_THREADS, 0, st>>>(a, out, d_mod_.p, bar(1, 0), n_, l);
     check_launch("k_tensor_square");
 }
 
 void Engine::elementwise(int op, const u64 *a, const u64 *b, u64 *out, int l, cudaStream_t st) const {
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
     switch (op) {
-        case EW_ADD: k_elementwise<EW_ADD><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
-        case EW_SUB: k_elementwise<EW_SUB><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
-        case EW_MUL: k_elementwise<EW_MUL><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
-        case EW_NEG: k_elementwise<EW_NEG><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, n_); break;
+        case EW_ADD: k_elementwise<EW_ADD><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
+        case EW_SUB: k_elementwise<EW_SUB><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
+        case EW_MUL: k_elementwise<EW_MUL><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
+        case EW_NEG: k_elementwise<EW_NEG><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
         default: throw std::invalid_argument("unknown elementwise op");
     }
     check_launch("k_elementwise");
 }
 
-static void launch_bconv(const BconvBatch &batch, int jobs, int ni, int no_max, const Modulus *mod, size_t n,
-                         cudaStream_t st) {
+static void launch_bconv(const BconvBatch &batch, int jobs, int ni, int no_max, const Modulus *mod, const BarG *bar,
+                         int size_QP, size_t n, cudaStream_t st) {
     dim3 grid((unsigned) (n / (2 * EW_THREADS)), jobs);
-    const size_t smem = (size_t) no_max * ni * 8 + (size_t) no_max * sizeof(Modulus);
+    const size_t smem = (size_t) no_max * ni * 8 + (size_t) no_max * (sizeof(Modulus) + sizeof(BarG));
     switch (ni) {
-        case 1: k_bconv<1><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
-        case 2: k_bconv<2><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
-        case 3: k_bconv<3><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
-        case 4: k_bconv<4><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
-        case 5: k_bconv<5><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
-        case 6: k_bconv<6><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
-        default: k_bconv<0><<<grid, EW_THREADS, smem, st>>>(batch, mod, n); break;
+        case 1: k_bconv<1><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
+        case 2: k_bconv<2><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
+        case 3: k_bconv<3><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
+        case 4: k_bconv<4><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
+        case 5: k_bconv<5><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
+        case 6: k_bconv<6><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
+        default: k_bconv<0><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
     }
     check_launch("k_bconv");
 }
@@ -359,12 +411,14 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
             // matrix offset: digits before d contributed digit_no * digit_size entries each
             size_t moff = 0;
             for (int e = 0; e < d; e++) moff += (size_t) lv.digit_no[e] * lv.digit_size[e];
+            int kin = 0;
+            for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(primes_[start + i]));
             batch.job[jobs] = BconvJob{t_cks + (size_t) start * n_, dst, lv.modup_mat.p + moff, lv.modup_omod.p + off,
-                                       lv.modup_olimb.p + off, ni, lv.digit_no[d]};
+                                       lv.modup_olimb.p + off, ni, lv.digit_no[d], kin + ceil_log2(ni)};
             no_max = std::max(no_max, lv.digit_no[d]);
             jobs++, d++;
         }
-        launch_bconv(batch, jobs, ni, no_max, d_mod_.p, n_, st);
+        launch_bconv(batch, jobs, ni, no_max, d_mod_.p, d_bar_.p, size_QP_, n_, st);
     }
     // 3. forward NTT of the converted limbs only (..._exclude_range, rns_bconv.cu:618)
     {
@@ -377,7 +431,8 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
 void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st) const {
     const Level &lv = level(l);
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), lv.m);
-    k_inner_prod<<<grid, EW_THREADS, 0, st>>>(cx, t_mod_up, evk, d_mod_.p, n_, l, lv.m, size_Q_, size_QP_, lv.beta);
+    k_inner_prod<<<grid, EW_THREADS, 0, st>>>(cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), n_, l, lv.m, size_Q_, size_QP_,
+                                               lv.beta);
     check_launch("k_inner_prod");
 }
 
@@ -397,11 +452,13 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
     }
     // 2. P -> Ql conversion (bConv_BEHZ matmul :143-168 / single-P :691-707)
     {
+        int pbits = 0;
+        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(primes_[size_Q_ + i]));
         BconvBatch batch{};
         for (int k = 0; k < npoly; k++)
             batch.job[k] = BconvJob{cx + ((size_t) k * m + l) * n_, delta + (size_t) k * l * n_, lv.moddown_mat.p,
-                                    lv.moddown_omod.p, lv.moddown_olimb.p, alpha, l};
-        launch_bconv(batch, npoly, alpha, l, d_mod_.p, n_, st);
+                                    lv.moddown_omod.p, lv.moddown_olimb.p, alpha, l, pbits + ceil_log2(alpha)};
+        launch_bconv(batch, npoly, alpha, l, d_mod_.p, d_bar_.p, size_QP_, n_, st);
     }
     // 3. forward NTT of delta with the fused (cx - delta) * P^-1 (+ ct) epilogue (:820, ntt_moddown.cu:106-216)
     {

@@ -77,11 +77,52 @@ __device__ __forceinline__ u64 barrett64(u64 x, const Modulus &m) {
     return csub(x - s * m.q, m.q);
 }
 
+// full 64x64 -> 128 product from four 32x32+64 multiply-adds (the compiler's a*b and __umul64hi(a,b) do not
+// share partial products: 5 wide + 2 narrow multiplies instead of 4 wide)
+__device__ __forceinline__ void mul128(u64 a, u64 b, u64 &lo, u64 &hi) {
+    const u32 a0 = (u32) a, a1 = (u32) (a >> 32), b0 = (u32) b, b1 = (u32) (b >> 32);
+    u64 A, B, C, D;
+    asm("mul.wide.u32 %0, %1, %2;" : "=l"(A) : "r"(a0), "r"(b0));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(B) : "r"(a1), "r"(b0), "l"(A >> 32));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(C) : "r"(a0), "r"(b1), "l"(B & 0xffffffffull));
+    asm("mad.wide.u32 %0, %1, %2, %3;" : "=l"(D) : "r"(a1), "r"(b1), "l"(B >> 32));
+    lo = (A & 0xffffffffull) | (C << 32);
+    hi = D + (C >> 32);
+}
+
+// Single-word Barrett for values known to be < 2^(2k+g) (k = bit length of q, g = growth bits of a sum of
+// products): take the 64 bits of x starting at bit sh = max(0, 2k+g-64), one high multiply by
+// mu = floor(2^(64+sh)/q), one low multiply, two conditional subtractions.  Valid when k + g <= 63
+// (sh <= k-1, so the quotient estimate is at most 2 too small; derivation in DESIGN.md).  Same canonical
+// result as barrett_reduce_uint128_uint64 (uintmodmath.cuh:96-136) at about a third of the multiplies.
+struct BarG {
+    u64 mu;
+    u32 sh;      // 0..64, 0xff = not applicable for this modulus/growth: use the two-word Barrett
+    u32 pad;
+};
+__device__ __forceinline__ u64 barrett_g(u64 lo, u64 hi, const BarG &b, const Modulus &m) {
+    if (b.sh == 0xffu) return barrett128(lo, hi, m);   // CTA-uniform
+    u64 x;
+    if (b.sh == 0) x = lo;
+    else if (b.sh == 64) x = hi;
+    else x = (lo >> b.sh) | (hi << (64 - b.sh));
+    const u64 q3 = mulhi(x, b.mu);
+    u64 r = lo - q3 * m.q;
+    r = csub(r, 2 * m.q);
+    return csub(r, m.q);
+}
+__device__ __forceinline__ u64 mul_mod_g(u64 a, u64 b, const BarG &bg, const Modulus &m) {
+    u64 lo, hi;
+    mul128(a, b, lo, hi);
+    return barrett_g(lo, hi, bg, m);
+}
+
 // 128-bit accumulator for inner products / base conversion (uintmath.cuh add_uint128_uint128)
 struct Acc128 {
     u64 lo, hi;
     __device__ __forceinline__ void mac(u64 a, u64 b) {
-        u64 pl = a * b, ph = mulhi(a, b);
+        u64 pl, ph;
+        mul128(a, b, pl, ph);
         lo += pl;
         hi += ph + (lo < pl);
     }

@@ -125,35 +125,118 @@ struct RoundMap {
 };
 
 // ----------------------------------------------------------------------------------------------------
-// butterflies
+// arithmetic policies.  Two exact implementations of the same modular butterflies:
+//
+//  IntArith  -- 64-bit Shoup multiplication on the integer pipe, any q < 2^61 (reference butterfly.cuh:10-37
+//               semantics with a relaxed reduction schedule).
+//  FpArith   -- for q < 2^46: values are kept as exact integers in FP64 registers and the modular product is an
+//               error-free FMA sequence (p = y*w rounded, e = fma(y,w,-p) its exact error, k = rint(y*w/q),
+//               r = fma(-k,q,p) + e exactly).  On B200 DFMA issues at the full 64 lanes/clk/SM and on its own
+//               pipe, while a 64x64->128 integer product costs ~10 IMAD slots; measured 9.7 vs 3.9 modmuls/clk/SM
+//               (tools/microbench.cu, profiles/).  Results are the same canonical residues bit for bit.
 // ----------------------------------------------------------------------------------------------------
-// forward (Cooley-Tukey, Harvey lazy; butterfly.cuh:10-22 semantics with a relaxed reduction schedule)
-template<bool CSUB>
-__device__ __forceinline__ void ct_bfly(u64 &x, u64 &y, const Tw w, const u64 q, const u64 q2, const u64 q4) {
-    u64 X = x;
-    if constexpr (CSUB) X = csub(X, q4);
-    const u64 t = mul_shoup_lazy_neg(y, w.x, w.y, 0 - q);
-    x = X + t;
-    y = X + q2 - t;
-}
 // forward stage s takes inputs < 4q (s = 0), < 6q (odd s) or < 8q (even s >= 2) and reduces on even s >= 2
 __host__ __device__ constexpr bool fwd_csub(int s) { return s >= 2 && (s % 2) == 0; }
 
-// inverse (Gentleman-Sande, butterfly.cuh:28-37): inputs and outputs in [0, 2q)
-__device__ __forceinline__ void gs_bfly(u64 &x, u64 &y, const Tw w, const u64 q, const u64 q2) {
-    const u64 s = csub(x + y, q2);
-    const u64 d = x + q2 - y;
-    x = s;
-    y = mul_shoup_lazy_neg(d, w.x, w.y, 0 - q);
-}
-// last inverse stage: folds n^-1 (and an optional per-limb scalar) into both outputs, canonical results
-// (replaces intt_2d.cu:195-203 "lower half times n^-1, upper half through itw[1]")
-__device__ __forceinline__ void gs_bfly_last(u64 &x, u64 &y, const Tw cx, const Tw cy, const u64 q, const u64 q2) {
-    const u64 s = x + y;
-    const u64 d = x + q2 - y;
-    x = mul_shoup(s, cx, q);
-    y = mul_shoup(d, cy, q);
-}
+struct IntArith {
+    using T = u64;
+    struct Consts {
+        u64 q, q2, q4, nq;
+    };
+    __device__ static __forceinline__ Consts consts(const Modulus &m, const double2 &) {
+        return Consts{m.q, 2 * m.q, 4 * m.q, 0 - m.q};
+    }
+    __device__ static __forceinline__ T load(u64 canonical, const Consts &) { return canonical; }
+    __device__ static __forceinline__ u64 raw(T v) { return v; }
+    __device__ static __forceinline__ T from_raw(u64 bits) { return bits; }
+    // forward (Cooley-Tukey, Harvey lazy)
+    template<bool CSUB>
+    __device__ static __forceinline__ void fwd(T &x, T &y, const Tw w, const Consts &c) {
+        u64 X = x;
+        if constexpr (CSUB) X = csub(X, c.q4);
+        const u64 t = mul_shoup_lazy_neg(y, w.x, w.y, c.nq);
+        x = X + t;
+        y = X + c.q2 - t;
+    }
+    __device__ static __forceinline__ u64 canon_fwd(T v, const Consts &c) {   // < 8q -> [0, q)
+        return csub(csub(csub(v, c.q4), c.q2), c.q);
+    }
+    // inverse (Gentleman-Sande): inputs and outputs in [0, 2q)
+    __device__ static __forceinline__ void inv(T &x, T &y, const Tw w, const Consts &c) {
+        const u64 s = csub(x + y, c.q2);
+        const u64 d = x + c.q2 - y;
+        x = s;
+        y = mul_shoup_lazy_neg(d, w.x, w.y, c.nq);
+    }
+    // last inverse stage: folds n^-1 (and an optional per-limb scalar) into both outputs, canonical results
+    // (replaces intt_2d.cu:195-203 "lower half times n^-1, upper half through itw[1]")
+    __device__ static __forceinline__ void inv_last(T &x, T &y, const Tw cx, const Tw cy, const Consts &c) {
+        const u64 s = x + y;
+        const u64 d = x + c.q2 - y;
+        x = mul_shoup(s, cx, c.q);
+        y = mul_shoup(d, cy, c.q);
+    }
+    __device__ static __forceinline__ void inv_round_end(T &, const Consts &) {}
+    __device__ static __forceinline__ u64 canon_inv(T v, const Consts &) { return v; }
+};
+
+struct FpArith {
+    using T = double;
+    struct Consts {
+        double q, qinv;
+    };
+    static constexpr double TWO52 = 4503599627370496.0;          // 2^52
+    static constexpr double MAGIC = 6755399441055744.0;          // 1.5 * 2^52: round-to-nearest-integer trick
+    __device__ static __forceinline__ Consts consts(const Modulus &, const double2 &f) { return Consts{f.x, f.y}; }
+    __device__ static __forceinline__ T load(u64 canonical, const Consts &) {   // exact for values < 2^52
+        return __longlong_as_double((long long) (canonical | 0x4330000000000000ull)) - TWO52;
+    }
+    __device__ static __forceinline__ u64 raw(T v) { return (u64) __double_as_longlong(v); }
+    __device__ static __forceinline__ T from_raw(u64 bits) { return __longlong_as_double((long long) bits); }
+    __device__ static __forceinline__ u64 to_u64(T nonneg_int) {                // exact for 0 <= v < 2^52
+        return ((u64) __double_as_longlong(nonneg_int + TWO52)) & 0x000fffffffffffffull;
+    }
+    // y * w mod q, result in (-0.62q, 0.62q); exact for |y| < 2^51, w < q < 2^47 (tests/test_fp_modmul.py)
+    __device__ static __forceinline__ T mulmod(T y, const Tw w, const Consts &c) {
+        const double wv = __longlong_as_double((long long) w.x), wi = __longlong_as_double((long long) w.y);
+        const double k = __fma_rn(y, wi, MAGIC) - MAGIC;
+        const double p = y * wv;
+        const double e = __fma_rn(y, wv, -p);
+        const double r = __fma_rn(-k, c.q, p);
+        return r + e;
+    }
+    __device__ static __forceinline__ T reduce(T v, const Consts &c) {           // -> [-q/2, q/2]
+        const double k = __fma_rn(v, c.qinv, MAGIC) - MAGIC;
+        return __fma_rn(-k, c.q, v);
+    }
+    template<bool CSUB>
+    __device__ static __forceinline__ void fwd(T &x, T &y, const Tw w, const Consts &c) {
+        const double t = mulmod(y, w, c);   // |values| grow by < 0.62q per stage: < 12q < 2^50 after 17 stages
+        const double X = x;
+        x = X + t;
+        y = X - t;
+    }
+    __device__ static __forceinline__ u64 canon_fwd(T v, const Consts &c) {
+        double r = reduce(v, c);
+        if (r < 0.0) r += c.q;
+        return to_u64(r);
+    }
+    __device__ static __forceinline__ void inv(T &x, T &y, const Tw w, const Consts &c) {
+        const double s = x + y, d = x - y;
+        x = s;
+        y = mulmod(d, w, c);
+    }
+    __device__ static __forceinline__ void inv_last(T &x, T &y, const Tw cx, const Tw cy, const Consts &c) {
+        const double s = x + y, d = x - y;
+        double a = mulmod(s, cx, c), b = mulmod(d, cy, c);
+        if (a < 0.0) a += c.q;
+        if (b < 0.0) b += c.q;
+        x = a, y = b;
+    }
+    // only the all-sums element of a radix-2^R group can grow by 2^R per round: fold it back
+    __device__ static __forceinline__ void inv_round_end(T &x0, const Consts &c) { x0 = reduce(x0, c); }
+    __device__ static __forceinline__ u64 canon_inv(T v, const Consts &) { return to_u64(v); }
+};
 
 // twiddle index of (stage S0+u, hi, b) for this tile
 template<class M, bool ROWS, int LOGN>
@@ -169,10 +252,19 @@ __device__ __forceinline__ int tw_index(int u, int hi, int b, int row) {
     }
 }
 
-// one forward round on the 16 registers of a thread: x[g * 2^R + k]
-template<class M, bool ROWS, int LOGN, int SBASE>
-__device__ __forceinline__ void fwd_round(u64 (&x)[NTT_EPT], const Tw *__restrict__ tw, const int (&hi)[M::G],
-                                          const int (&row)[M::G], u64 q, u64 q2, u64 q4) {
+template<class A>
+struct PassCtx {
+    const Tw *tw;               // table of this limb
+    typename A::Consts c;
+    int tile;                   // tile index inside the limb (column block resp. row block)
+    Tw fin_x, fin_y;            // constants of the last inverse stage
+};
+
+// one forward round on the registers of a thread: x[g * 2^R + k]
+template<class A, class M, bool ROWS, int LOGN, int SBASE>
+__device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw *__restrict__ tw,
+                                          const int (&hi)[M::G], const int (&row)[M::G],
+                                          const typename A::Consts &c) {
     constexpr int R = M::R;
 #pragma unroll
     for (int u = 0; u < R; u++) {
@@ -191,8 +283,8 @@ __device__ __forceinline__ void fwd_round(u64 (&x)[NTT_EPT], const Tw *__restric
                 for (int t = 0; t < half; t++) {
                     const int i0 = (g << R) + b * 2 * half + t;
                     // compile-time reduction schedule (all loop variables are unrolled constants)
-                    if (fwd_csub(SBASE + M::S0 + u)) ct_bfly<true>(x[i0], x[i0 + half], w[g], q, q2, q4);
-                    else ct_bfly<false>(x[i0], x[i0 + half], w[g], q, q2, q4);
+                    if (fwd_csub(SBASE + M::S0 + u)) A::template fwd<true>(x[i0], x[i0 + half], w[g], c);
+                    else A::template fwd<false>(x[i0], x[i0 + half], w[g], c);
                 }
             }
         }
@@ -200,9 +292,10 @@ __device__ __forceinline__ void fwd_round(u64 (&x)[NTT_EPT], const Tw *__restric
 }
 
 // one inverse round (stages S0+R-1 down to S0).  FINAL marks the round containing global stage 0.
-template<class M, bool ROWS, int LOGN, bool FINAL>
-__device__ __forceinline__ void inv_round(u64 (&x)[NTT_EPT], const Tw *__restrict__ tw, const int (&hi)[M::G],
-                                          const int (&row)[M::G], u64 q, u64 q2, Tw fin_x, Tw fin_y) {
+template<class A, class M, bool ROWS, int LOGN, bool FINAL>
+__device__ __forceinline__ void inv_round(typename A::T (&x)[NTT_EPT], const Tw *__restrict__ tw,
+                                          const int (&hi)[M::G], const int (&row)[M::G],
+                                          const typename A::Consts &c, Tw fin_x, Tw fin_y) {
     constexpr int R = M::R;
 #pragma unroll
     for (int u = R - 1; u >= 0; u--) {
@@ -222,26 +315,17 @@ __device__ __forceinline__ void inv_round(u64 (&x)[NTT_EPT], const Tw *__restric
 #pragma unroll
                 for (int t = 0; t < half; t++) {
                     const int i0 = (g << R) + b * 2 * half + t;
-                    if (FINAL && u == 0) gs_bfly_last(x[i0], x[i0 + half], fin_x, fin_y, q, q2);
-                    else gs_bfly(x[i0], x[i0 + half], w[g], q, q2);
+                    if (FINAL && u == 0) A::inv_last(x[i0], x[i0 + half], fin_x, fin_y, c);
+                    else A::inv(x[i0], x[i0 + half], w[g], c);
                 }
             }
         }
     }
+    if constexpr (!FINAL) {
+#pragma unroll
+        for (int g = 0; g < M::G; g++) A::inv_round_end(x[g << R], c);
+    }
 }
-
-// ----------------------------------------------------------------------------------------------------
-// pass drivers.  IO functors:
-//   load(slot, data_limb, coeff_index) -> u64      value entering the transform
-//   store(slot, data_limb, coeff_index, value)     value leaving the pass
-// ----------------------------------------------------------------------------------------------------
-// context shared by the rounds of one pass
-struct PassCtx {
-    const Tw *tw;     // table of this limb
-    u64 q, q2, q4;
-    int tile;         // tile index inside the limb (column block resp. row block)
-    Tw fin_x, fin_y;  // constants of the last inverse stage
-};
 
 template<int P, bool ROWS, int LOGN>
 __device__ __forceinline__ size_t gl_index(int e, int c, int tile) {
@@ -254,11 +338,14 @@ __device__ __forceinline__ size_t gl_index(int e, int c, int tile) {
     }
 }
 
-// Forward pass over one tile.  Load/Store are functors taking the coefficient index inside the limb.
-template<int P, bool ROWS, int LOGN, int SBASE, class Load, class Store>
-__device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load load, Store store) {
+// ----------------------------------------------------------------------------------------------------
+// pass drivers.  load(coeff_index) -> A::T is the value entering the pass, store(coeff_index, A::T) the
+// value leaving it (the kernels decide about raw / canonical representation and fused epilogues).
+// ----------------------------------------------------------------------------------------------------
+template<class A, int P, bool ROWS, int LOGN, int SBASE, class Load, class Store>
+__device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Load load, Store store) {
     constexpr int NR = Sched<P>::NR;
-    u64 x[NTT_EPT];
+    typename A::T x[NTT_EPT];
     const int tid = threadIdx.x;
 
     auto run_round = [&](auto ri_tag) {
@@ -277,9 +364,9 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load 
             for (int k = 0; k < (1 << M::R); k++) {
                 const int e = M::elem(hi[g], k, lo[g]);
                 if constexpr (RI == 0) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
-                else x[(g << M::R) + k] = smem[M::sidx(e, c[g])];
+                else x[(g << M::R) + k] = A::from_raw(smem[M::sidx(e, c[g])]);
             }
-        fwd_round<M, ROWS, LOGN, SBASE>(x, cx.tw, hi, row, cx.q, cx.q2, cx.q4);
+        fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, row, cx.c);
         // scatter
         constexpr bool DIRECT_OUT = (RI == NR - 1) && !ROWS;
         if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
@@ -289,7 +376,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load 
             for (int k = 0; k < (1 << M::R); k++) {
                 const int e = M::elem(hi[g], k, lo[g]);
                 if constexpr (DIRECT_OUT) store(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile), x[(g << M::R) + k]);
-                else smem[M::sidx(e, c[g])] = x[(g << M::R) + k];
+                else smem[M::sidx(e, c[g])] = A::raw(x[(g << M::R) + k]);
             }
         if constexpr (!DIRECT_OUT) __syncthreads();
     };
@@ -297,6 +384,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load 
     run_round(std::integral_constant<int, 0>{});
     if constexpr (NR > 1) run_round(std::integral_constant<int, 1>{});
     if constexpr (NR > 2) run_round(std::integral_constant<int, 2>{});
+    if constexpr (NR > 3) run_round(std::integral_constant<int, 3>{});
 
     if constexpr (ROWS) {
         // the tile is contiguous in global memory: flat, fully coalesced copy-out
@@ -304,25 +392,25 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx &cx, Load 
 #pragma unroll
         for (int i = 0; i < NTT_EPT; i++) {
             const int j = i * NTT_THREADS + tid;
-            store(base + j, smem[skew(j)]);
+            store(base + j, A::from_raw(smem[skew(j)]));
         }
     }
 }
 
 // Inverse pass over one tile (rounds in reverse order).
-template<int P, bool ROWS, int LOGN, bool FINAL, class Load, class Store>
-__device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx &cx, Load load, Store store) {
+template<class A, int P, bool ROWS, int LOGN, bool FINAL, class Load, class Store>
+__device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Load load, Store store) {
     constexpr int NR = Sched<P>::NR;
-    u64 x[NTT_EPT];
+    typename A::T x[NTT_EPT];
     const int tid = threadIdx.x;
 
     if constexpr (ROWS) {
-        // flat coalesced copy-in, the first inverse round then reads its 16 contiguous elements from smem
+        // flat coalesced copy-in, the first inverse round then reads its contiguous elements from smem
         const size_t base = (size_t) cx.tile << NTT_LOG_TILE;
 #pragma unroll
         for (int i = 0; i < NTT_EPT; i++) {
             const int j = i * NTT_THREADS + tid;
-            smem[skew(j)] = load(base + j);
+            smem[skew(j)] = A::raw(load(base + j));
         }
         __syncthreads();
     }
@@ -343,9 +431,9 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx &cx, Load 
             for (int k = 0; k < (1 << M::R); k++) {
                 const int e = M::elem(hi[g], k, lo[g]);
                 if constexpr (DIRECT_IN) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
-                else x[(g << M::R) + k] = smem[M::sidx(e, c[g])];
+                else x[(g << M::R) + k] = A::from_raw(smem[M::sidx(e, c[g])]);
             }
-        inv_round<M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, row, cx.q, cx.q2, cx.fin_x, cx.fin_y);
+        inv_round<A, M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, row, cx.c, cx.fin_x, cx.fin_y);
         if constexpr (RI == 0) {
             // first round in index order = last in time: values leave the pass
 #pragma unroll
@@ -362,12 +450,13 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx &cx, Load 
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++) {
                     const int e = M::elem(hi[g], k, lo[g]);
-                    smem[M::sidx(e, c[g])] = x[(g << M::R) + k];
+                    smem[M::sidx(e, c[g])] = A::raw(x[(g << M::R) + k]);
                 }
             __syncthreads();
         }
     };
 
+    if constexpr (NR > 3) run_round(std::integral_constant<int, 3>{});
     if constexpr (NR > 2) run_round(std::integral_constant<int, 2>{});
     if constexpr (NR > 1) run_round(std::integral_constant<int, 1>{});
     run_round(std::integral_constant<int, 0>{});

@@ -10,6 +10,9 @@ struct NttPlan {
     const Tw *itw;       // [size_QP][N] inverse twiddles, same order
     const Modulus *mod;  // [size_QP]
     const Tw *inv_fin;   // [size_QP][2]: {n^-1, itw[1] * n^-1} for the last inverse stage
+    // rows with q < 2^46 run the FP64 butterflies: their table entries hold (double(w), double(w)/double(q))
+    const unsigned char *is_fp;   // [size_QP]
+    const double2 *fpc;           // [size_QP] {double(q), 1/double(q)}
 };
 
 // forward negacyclic NTT of the limbs in `ll` (replaces nwt_2d_radix8_forward_inplace and its

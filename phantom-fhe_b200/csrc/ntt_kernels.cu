@@ -3,109 +3,124 @@
 
 namespace pfhe {
 
+// every kernel picks the arithmetic of its limb (CTA-uniform): FP64 butterflies for q < 2^46, integer otherwise
+#define PFHE_ARITH_DISPATCH(ROW, ...)                                                                     \
+    if (p.is_fp[ROW]) {                                                                                   \
+        using A = FpArith;                                                                                \
+        __VA_ARGS__                                                                                       \
+    } else {                                                                                              \
+        using A = IntArith;                                                                               \
+        __VA_ARGS__                                                                                       \
+    }
+
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, const Tw *tw,
-                                                           const Modulus *mod) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, NttPlan p) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    const size_t off = (size_t) ll.data[slot] << LOGN;
-    const u64 q = mod[row].q;
-    PassCtx cx{tw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
     const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
-    u64 *d = dst + off;
-    forward_pass<ntt_p1(LOGN), false, LOGN, 0>(
-            smem, cx, [&](size_t i) { return s[i]; }, [&](size_t i, u64 v) { d[i] = v; });
+    u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
+    PFHE_ARITH_DISPATCH(row, {
+        const typename A::Consts c = A::consts(p.mod[row], p.fpc[row]);
+        PassCtx<A> cx{p.tw + ((size_t) row << LOGN), c, (int) blockIdx.x, {}, {}};
+        forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
+                smem, cx, [&](size_t i) { return A::load(s[i], c); }, [&](size_t i, typename A::T v) { d[i] = A::raw(v); });
+    })
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows(u64 *data, LimbList ll, NttPlan p) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    const size_t off = (size_t) ll.data[slot] << LOGN;
-    const u64 q = mod[row].q;
-    PassCtx cx{tw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
-    u64 *d = data + off;
-    forward_pass<ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
-            smem, cx, [&](size_t i) { return d[i]; },
-            [&](size_t i, u64 v) { d[i] = csub(csub(csub(v, 4 * q), 2 * q), q); });
+    u64 *d = data + ((size_t) ll.data[slot] << LOGN);
+    PFHE_ARITH_DISPATCH(row, {
+        const typename A::Consts c = A::consts(p.mod[row], p.fpc[row]);
+        PassCtx<A> cx{p.tw + ((size_t) row << LOGN), c, (int) blockIdx.x, {}, {}};
+        forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+                smem, cx, [&](size_t i) { return A::from_raw(d[i]); },
+                [&](size_t i, typename A::T v) { d[i] = A::canon_fwd(v, c); });
+    })
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows_epi(u64 *data, LimbList ll, const Tw *tw, const Modulus *mod,
-                                                               EpiArgs ea) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows_epi(u64 *data, LimbList ll, NttPlan p, EpiArgs ea) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    const u64 q = mod[row].q;
-    PassCtx cx{tw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
+    const u64 q = p.mod[row].q;
     const u64 *d = data + ((size_t) ll.data[slot] << LOGN);
     const u64 *sub = ea.sub_base + ((size_t) ea.sub[slot] << LOGN);
     u64 *out = ea.out_base + ((size_t) ea.out[slot] << LOGN);
     const int addl = ea.add[slot];
     const u64 *add = addl >= 0 ? ea.add_base + ((size_t) addl << LOGN) : nullptr;
     const Tw k = ea.mulc[slot];
-    forward_pass<ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
-            smem, cx, [&](size_t i) { return d[i]; },
-            [&](size_t i, u64 v) {
-                v = csub(csub(csub(v, 4 * q), 2 * q), q);
-                u64 r = mul_shoup(sub[i] + q - v, k, q);
-                if (add) r = add_mod(r, add[i], q);
-                out[i] = r;
-            });
+    PFHE_ARITH_DISPATCH(row, {
+        const typename A::Consts c = A::consts(p.mod[row], p.fpc[row]);
+        PassCtx<A> cx{p.tw + ((size_t) row << LOGN), c, (int) blockIdx.x, {}, {}};
+        forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+                smem, cx, [&](size_t i) { return A::from_raw(d[i]); },
+                [&](size_t i, typename A::T v) {
+                    const u64 t = A::canon_fwd(v, c);
+                    u64 r = mul_shoup(sub[i] + q - t, k, q);
+                    if (add) r = add_mod(r, add[i], q);
+                    out[i] = r;
+                });
+    })
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_rows(u64 *dst, const u64 *src, LimbList ll, const Tw *itw,
-                                                           const Modulus *mod) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_rows(u64 *dst, const u64 *src, LimbList ll, NttPlan p) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    const size_t off = (size_t) ll.data[slot] << LOGN;
-    const u64 q = mod[row].q;
-    PassCtx cx{itw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, {}, {}};
     const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
-    u64 *d = dst + off;
-    inverse_pass<ntt_p2(LOGN), true, LOGN, false>(
-            smem, cx, [&](size_t i) { return s[i]; }, [&](size_t i, u64 v) { d[i] = v; });
+    u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
+    PFHE_ARITH_DISPATCH(row, {
+        const typename A::Consts c = A::consts(p.mod[row], p.fpc[row]);
+        PassCtx<A> cx{p.itw + ((size_t) row << LOGN), c, (int) blockIdx.x, {}, {}};
+        inverse_pass<A, ntt_p2(LOGN), true, LOGN, false>(
+                smem, cx, [&](size_t i) { return A::load(s[i], c); }, [&](size_t i, typename A::T v) { d[i] = A::raw(v); });
+    })
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_cols(u64 *data, LimbList ll, const Tw *itw, const Modulus *mod,
-                                                           const Tw *fin, int fin_by_slot) {
+__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_cols(u64 *data, LimbList ll, NttPlan p, const Tw *fin,
+                                                              int fin_by_slot) {
     __shared__ u64 smem[NTT_SMEM_WORDS];
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    const size_t off = (size_t) ll.data[slot] << LOGN;
-    const u64 q = mod[row].q;
     const int f = fin_by_slot ? slot : row;
-    PassCtx cx{itw + ((size_t) row << LOGN), q, 2 * q, 4 * q, (int) blockIdx.x, fin[2 * f], fin[2 * f + 1]};
-    u64 *d = data + off;
-    inverse_pass<ntt_p1(LOGN), false, LOGN, true>(
-            smem, cx, [&](size_t i) { return d[i]; }, [&](size_t i, u64 v) { d[i] = v; });
+    u64 *d = data + ((size_t) ll.data[slot] << LOGN);
+    PFHE_ARITH_DISPATCH(row, {
+        const typename A::Consts c = A::consts(p.mod[row], p.fpc[row]);
+        PassCtx<A> cx{p.itw + ((size_t) row << LOGN), c, (int) blockIdx.x, fin[2 * f], fin[2 * f + 1]};
+        inverse_pass<A, ntt_p1(LOGN), false, LOGN, true>(
+                smem, cx, [&](size_t i) { return A::from_raw(d[i]); },
+                [&](size_t i, typename A::T v) { d[i] = A::canon_inv(v, c); });
+    })
 }
 
 template<int LOGN>
 static void fwd_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) {
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    k_fwd_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, src, ll, p.tw, p.mod);
-    k_fwd_rows<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, ll, p.tw, p.mod);
+    k_fwd_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, src, ll, p);
+    k_fwd_rows<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, ll, p);
 }
 
 template<int LOGN>
 static void fwd_epi_impl(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st) {
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    k_fwd_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(data, data, ll, p.tw, p.mod);
-    k_fwd_rows_epi<LOGN><<<grid, NTT_THREADS, 0, st>>>(data, ll, p.tw, p.mod, ea);
+    k_fwd_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(data, data, ll, p);
+    k_fwd_rows_epi<LOGN><<<grid, NTT_THREADS, 0, st>>>(data, ll, p, ea);
 }
 
 template<int LOGN>
 static void inv_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
                      cudaStream_t st) {
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    k_inv_rows<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, src, ll, p.itw, p.mod);
-    k_inv_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, ll, p.itw, p.mod, fin ? fin : p.inv_fin, fin ? by_slot : 0);
+    k_inv_rows<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, src, ll, p);
+    k_inv_cols<LOGN><<<grid, NTT_THREADS, 0, st>>>(dst, ll, p, fin ? fin : p.inv_fin, fin ? by_slot : 0);
 }
 
 #define PFHE_DISPATCH_LOGN(FN, ...)                                                                       \

@@ -21,9 +21,10 @@ __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ul
 // grid.y = limb, grid.x * EW_THREADS * 2 = n
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u64 *b, u64 *out, const Modulus *mod,
-                                                            size_t n, int l) {
+                                                            const BarG *bar, size_t n, int l) {
     const int limb = blockIdx.y;
     const Modulus m = mod[limb];
+    const BarG bg = bar[limb];   // growth class 2: (c0+c1)(c0'+c1') < 4 q^2
     const size_t poly = (size_t) l * n;
     const size_t i = (size_t) limb * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const ulonglong2 a0 = ld2(a + i), a1 = ld2(a + i + poly), b0 = ld2(b + i), b1 = ld2(b + i + poly);
@@ -31,9 +32,9 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u
     const u64 A0[2] = {a0.x, a0.y}, A1[2] = {a1.x, a1.y}, B0[2] = {b0.x, b0.y}, B1[2] = {b1.x, b1.y};
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        d0[k] = mul_mod(A0[k], B0[k], m);
-        d2[k] = mul_mod(A1[k], B1[k], m);
-        const u64 t = mul_mod(A0[k] + A1[k], B0[k] + B1[k], m);   // sums < 2q < 2^62: product < 2^124
+        d0[k] = mul_mod_g(A0[k], B0[k], bg, m);
+        d2[k] = mul_mod_g(A1[k], B1[k], bg, m);
+        const u64 t = mul_mod_g(A0[k] + A1[k], B0[k] + B1[k], bg, m);   // sums < 2q < 2^62: product < 2^124
         d1[k] = sub_mod(sub_mod(t, d0[k], m.q), d2[k], m.q);
     }
     st2(out + i, d0[0], d0[1]);
@@ -42,10 +43,11 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u
 }
 
 // tensor_square_2x2_rns_poly (src/polymath.cu:500-532)
-__global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 *out, const Modulus *mod, size_t n,
-                                                               int l) {
+__global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 *out, const Modulus *mod,
+                                                               const BarG *bar, size_t n, int l) {
     const int limb = blockIdx.y;
     const Modulus m = mod[limb];
+    const BarG bg = bar[limb];
     const size_t poly = (size_t) l * n;
     const size_t i = (size_t) limb * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const ulonglong2 a0 = ld2(a + i), a1 = ld2(a + i + poly);
@@ -53,10 +55,10 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 
     u64 d0[2], d1[2], d2[2];
 #pragma unroll
     for (int k = 0; k < 2; k++) {
-        d0[k] = mul_mod(A0[k], A0[k], m);
-        const u64 t = mul_mod(A0[k], A1[k], m);
+        d0[k] = mul_mod_g(A0[k], A0[k], bg, m);
+        const u64 t = mul_mod_g(A0[k], A1[k], bg, m);
         d1[k] = add_mod(t, t, m.q);
-        d2[k] = mul_mod(A1[k], A1[k], m);
+        d2[k] = mul_mod_g(A1[k], A1[k], bg, m);
     }
     st2(out + i, d0[0], d0[1]);
     st2(out + i + poly, d1[0], d1[1]);
@@ -66,9 +68,10 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 
 // generic two-operand limb-wise op (add_rns_poly / sub_rns_poly / multiply_rns_poly, polymath.cu:41-173)
 template<int OP>
 __global__ void __launch_bounds__(EW_THREADS) k_elementwise(const u64 *a, const u64 *b, u64 *out, const Modulus *mod,
-                                                             size_t n) {
+                                                             const BarG *bar, size_t n) {
     const int limb = blockIdx.y;
     const Modulus m = mod[limb];
+    const BarG bg = bar[limb];
     const size_t i = (size_t) limb * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const ulonglong2 x = ld2(a + i);
     ulonglong2 y = make_ulonglong2(0, 0);
@@ -76,7 +79,7 @@ __global__ void __launch_bounds__(EW_THREADS) k_elementwise(const u64 *a, const 
     u64 r0, r1;
     if (OP == EW_ADD) r0 = add_mod(x.x, y.x, m.q), r1 = add_mod(x.y, y.y, m.q);
     else if (OP == EW_SUB) r0 = sub_mod(x.x, y.x, m.q), r1 = sub_mod(x.y, y.y, m.q);
-    else if (OP == EW_MUL) r0 = mul_mod(x.x, y.x, m), r1 = mul_mod(x.y, y.y, m);
+    else if (OP == EW_MUL) r0 = mul_mod_g(x.x, y.x, bg, m), r1 = mul_mod_g(x.y, y.y, bg, m);
     else r0 = x.x ? m.q - x.x : 0, r1 = x.y ? m.q - x.y : 0;
     st2(out + i, r0, r1);
 }
@@ -96,6 +99,8 @@ struct BconvJob {
     const short *omod;    // [no] key-level prime row of each output limb
     const short *olimb;   // [no] output limb index (units of n from `out`)
     int ni, no;
+    int xbits;            // bit length bound of the accumulated sum minus the output modulus' own bits:
+                          // max input-prime bits + ceil(log2 ni); selects the Barrett class per output limb
 };
 constexpr int BCONV_MAX_IN = 8;   // alpha <= 8 per digit on this path (larger digits use the generic loop)
 constexpr int BCONV_MAX_JOBS = 16;
@@ -104,14 +109,22 @@ struct BconvBatch {
 };
 
 template<int NI>
-__global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Modulus *mod, size_t n) {
+__global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Modulus *mod, const BarG *bar,
+                                                       int size_QP, size_t n) {
     extern __shared__ u64 s_mem[];
     const BconvJob jb = batch.job[blockIdx.y];
     const int ni = NI > 0 ? NI : jb.ni;
     u64 *s_mat = s_mem;                                   // [no][ni]
     Modulus *s_mod = reinterpret_cast<Modulus *>(s_mem + jb.no * ni);
+    BarG *s_bar = reinterpret_cast<BarG *>(s_mod + jb.no);
     for (int i = threadIdx.x; i < jb.no * ni; i += blockDim.x) s_mat[i] = jb.mat[i];
-    for (int i = threadIdx.x; i < jb.no; i += blockDim.x) s_mod[i] = mod[jb.omod[i]];
+    for (int i = threadIdx.x; i < jb.no; i += blockDim.x) {
+        const Modulus mo = mod[jb.omod[i]];
+        s_mod[i] = mo;
+        // sum < 2^(xbits + k_out): class = xbits - k_out above the same-modulus case 2 k_out
+        const int cls = max(0, jb.xbits - (64 - __clzll((long long) mo.q)));
+        s_bar[i] = bar[(size_t) min(cls, 63) * size_QP + jb.omod[i]];
+    }
     __syncthreads();
     const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     if (NI > 0) {
@@ -130,7 +143,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Mo
                 a1.mac(y1[i], mji);
             }
             const Modulus m = s_mod[j];
-            st2(jb.out + (size_t) jb.olimb[j] * n + x, barrett128(a0.lo, a0.hi, m), barrett128(a1.lo, a1.hi, m));
+            const BarG bg = s_bar[j];
+            st2(jb.out + (size_t) jb.olimb[j] * n + x, barrett_g(a0.lo, a0.hi, bg, m), barrett_g(a1.lo, a1.hi, bg, m));
         }
     } else {
         for (int j = 0; j < jb.no; j++) {
@@ -142,7 +156,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Mo
                 a1.mac(v.y, mji);
             }
             const Modulus m = s_mod[j];
-            st2(jb.out + (size_t) jb.olimb[j] * n + x, barrett128(a0.lo, a0.hi, m), barrett128(a1.lo, a1.hi, m));
+            const BarG bg = s_bar[j];
+            st2(jb.out + (size_t) jb.olimb[j] * n + x, barrett_g(a0.lo, a0.hi, bg, m), barrett_g(a1.lo, a1.hi, bg, m));
         }
     }
 }
@@ -156,14 +171,16 @@ __global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Mo
 // ---------------------------------------------------------------------------------------------------
 constexpr int KS_MAX_BETA = 64;
 __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
-                                                            const Modulus *mod, size_t n, int l, int m, int size_Q,
-                                                            int size_QP, int beta) {
+                                                            const Modulus *mod, const BarG *bar, size_t n, int l, int m,
+                                                            int size_Q, int size_QP, int beta) {
     const int j = blockIdx.y;
     const int row = j < l ? j : size_Q + (j - l);
     const Modulus md = mod[row];
+    const BarG bg = bar[row];   // growth class ceil(log2 beta)
     const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const size_t m_n = (size_t) m * n, qp_n = (size_t) size_QP * n;
     Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+#pragma unroll 4
     for (int d = 0; d < beta; d++) {
         const u64 *k0 = evk[d] + (size_t) row * n + x;
         const ulonglong2 v = ld2(t + (size_t) d * m_n + (size_t) j * n + x);
@@ -173,8 +190,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
         a10.mac(v.x, e1.x);
         a11.mac(v.y, e1.y);
     }
-    st2(cx + (size_t) j * n + x, barrett128(a00.lo, a00.hi, md), barrett128(a01.lo, a01.hi, md));
-    st2(cx + m_n + (size_t) j * n + x, barrett128(a10.lo, a10.hi, md), barrett128(a11.lo, a11.hi, md));
+    st2(cx + (size_t) j * n + x, barrett_g(a00.lo, a00.hi, bg, md), barrett_g(a01.lo, a01.hi, bg, md));
+    st2(cx + m_n + (size_t) j * n + x, barrett_g(a10.lo, a10.hi, bg, md), barrett_g(a11.lo, a11.hi, bg, md));
 }
 
 // dst[limb i] = src[perm...] helpers -------------------------------------------------------------------
