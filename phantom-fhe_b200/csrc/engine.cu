@@ -7,6 +7,7 @@
 #include <functional>
 
 #include "hostmath.hpp"
+#include "launch.hpp"
 #include "poly_kernels.cuh"
 
 namespace pfhe {
@@ -21,6 +22,13 @@ static int ceil_log2(int v) {
     return g;
 }
 
+// FP64 form of a base-conversion matrix entry for an output modulus p: {M, M/p} and {M * 2^30 mod p, that / p}
+static void push_matf(std::vector<double2> &v, u64 M, u64 p) {
+    const u64 M2 = hm::mulmod(M, ((u64) 1 << fp::SPLIT_BITS) % p, p);
+    v.push_back(make_double2((double) M, (double) M / (double) p));
+    v.push_back(make_double2((double) M2, (double) M2 / (double) p));
+}
+
 static Tw make_tw(u64 w, u64 q) { return make_ulonglong2(w, hm::shoup(w, q)); }
 
 // launch helper: NTT lists longer than NTT_MAX_LIMBS are cut into chunks
@@ -30,21 +38,22 @@ struct LimbVec {
         data.push_back((short) d), row.push_back((short) r), src.push_back((short) (s < 0 ? d : s));
     }
     size_t size() const { return data.size(); }
-    LimbList chunk(size_t begin, size_t &taken) const {
+    LimbList chunk(size_t begin, size_t &taken, const std::vector<u64> &primes) const {
         LimbList ll{};
         taken = std::min<size_t>(NTT_MAX_LIMBS, data.size() - begin);
         ll.count = (int) taken;
         for (size_t i = 0; i < taken; i++) {
             ll.data[i] = data[begin + i], ll.row[i] = row[begin + i], ll.src[i] = src[begin + i];
+            ll.q[i] = primes[row[begin + i]];
         }
         return ll;
     }
 };
 
-static LimbList single_list(const LimbVec &v) {
+static LimbList single_list(const LimbVec &v, const std::vector<u64> &primes) {
     if (v.size() > NTT_MAX_LIMBS) throw std::logic_error("limb list too long");
     size_t taken;
-    return v.chunk(0, taken);
+    return v.chunk(0, taken, primes);
 }
 
 // ---------------------------------------------------------------------------------------------------
@@ -122,6 +131,8 @@ void Engine::build_tables() {
         is_fp_[i] = allow_fp && (primes_[i] >> 46) == 0;
         fpc[i] = make_double2((double) primes_[i], 1.0 / (double) primes_[i]);
     }
+    for (int i = 0; i < size_QP_ && i < 128; i++)
+        if (is_fp_[i]) fp_mask_[i >> 6] |= 1ull << (i & 63);
     d_is_fp_.upload(is_fp_);
     d_fpc_.upload(fpc);
     std::vector<Tw> tw((size_t) size_QP_ * n_), itw((size_t) size_QP_ * n_), fin((size_t) size_QP_ * 2);
@@ -173,7 +184,7 @@ void Engine::build_tables() {
             bars[(size_t) g * size_QP_ + i] = b;
         }
     d_bar_.upload(bars);
-    plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p, d_is_fp_.p, d_fpc_.p};
+    plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p, d_is_fp_.p, d_fpc_.p, allow_fp ? 1 : 0};
 }
 
 const BarG *Engine::bar(int terms, int extra_bits) const {
@@ -213,6 +224,7 @@ void Engine::build_level(int l) {
         lv->beta = beta(l);
         std::vector<Tw> fin((size_t) l * 2), finc(l);
         std::vector<u64> mat;
+        std::vector<double2> matf;
         std::vector<short> omod, olimb;
         LimbVec ntt_conv;
         for (int d = 0; d < lv->beta; d++) {
@@ -234,17 +246,26 @@ void Engine::build_level(int l) {
             for (int j = 0; j < lv->m; j++) {
                 if (j >= start && j < start + size) continue;
                 const int row = row_of(j);
-                for (int i = 0; i < size; i++) mat.push_back(hm::product_mod(ibase, i, primes_[row]));
+                for (int i = 0; i < size; i++) {
+                    const u64 M = hm::product_mod(ibase, i, primes_[row]);
+                    mat.push_back(M);
+                    push_matf(matf, M, primes_[row]);
+                }
                 omod.push_back((short) row);
                 olimb.push_back((short) j);
                 ntt_conv.push(d * lv->m + j, row);
                 no++;
             }
             lv->digit_no.push_back(no);
+            unsigned big = 0;
+            for (int i = 0; i < size; i++)
+                if (ibase[i] >> fp::MAX_BITS) big |= 1u << i;
+            lv->digit_big.push_back(big);
         }
         lv->modup_fin.upload(fin);
         lv->modup_fin_coeff.upload(finc);
         lv->modup_mat.upload(mat);
+        lv->modup_matf.upload(matf);
         lv->modup_omod.upload(omod);
         lv->modup_olimb.upload(olimb);
         lv->modup_ntt_data = ntt_conv.data, lv->modup_ntt_row = ntt_conv.row;
@@ -261,16 +282,23 @@ void Engine::build_level(int l) {
                 dfin[2 * (k * alpha + i) + 1] = make_tw_row(size_Q_ + i, hm::mulmod(c, h_itw1_[size_Q_ + i], p));
             }
         std::vector<u64> dmat((size_t) l * alpha);
+        std::vector<double2> dmatf;
+        for (int i = 0; i < alpha; i++)
+            if (pbase[i] >> fp::MAX_BITS) lv->moddown_big |= 1u << i;
         std::vector<short> dmod(l), dlimb(l);
         std::vector<Tw> pinv((size_t) 2 * l);
         for (int j = 0; j < l; j++) {
             const u64 q = primes_[j];
-            for (int i = 0; i < alpha; i++) dmat[(size_t) j * alpha + i] = hm::product_mod(pbase, i, q);
+            for (int i = 0; i < alpha; i++) {
+                dmat[(size_t) j * alpha + i] = hm::product_mod(pbase, i, q);
+                push_matf(dmatf, dmat[(size_t) j * alpha + i], q);
+            }
             dmod[j] = (short) j, dlimb[j] = (short) j;
             pinv[j] = pinv[l + j] = make_tw(hm::invmod(hm::product_mod(pbase, -1, q), q), q);
         }
         lv->moddown_fin.upload(dfin);
         lv->moddown_mat.upload(dmat);
+        lv->moddown_matf.upload(dmatf);
         lv->moddown_omod.upload(dmod);
         lv->moddown_olimb.upload(dlimb);
         lv->pinv_slots.upload(pinv);
@@ -305,10 +333,11 @@ void Engine::ntt_inv_list(u64 *dst, const u64 *src, const LimbList &ll, const Tw
     PFHE_CUDA(ntt_inverse(plan_, dst, src, ll, fin, by_slot, st));
 }
 
-static void run_chunks(const LimbVec &v, const std::function<void(const LimbList &, size_t)> &fn) {
+static void run_chunks(const LimbVec &v, const std::vector<u64> &primes,
+                       const std::function<void(const LimbList &, size_t)> &fn) {
     for (size_t b = 0; b < v.size();) {
         size_t taken;
-        LimbList ll = v.chunk(b, taken);
+        LimbList ll = v.chunk(b, taken, primes);
         fn(ll, b);
         b += taken;
     }
@@ -317,20 +346,20 @@ static void run_chunks(const LimbVec &v, const std::function<void(const LimbList
 void Engine::ntt_fwd_rows_range(u64 *inout, int count, int start_row, cudaStream_t st) const {
     LimbVec v;
     for (int i = 0; i < count; i++) v.push(i, start_row + i);
-    run_chunks(v, [&](const LimbList &ll, size_t) { ntt_fwd_list(inout, inout, ll, st); });
+    run_chunks(v, primes_, [&](const LimbList &ll, size_t) { ntt_fwd_list(inout, inout, ll, st); });
 }
 
 void Engine::ntt_inv_rows_range(u64 *dst, const u64 *src, int count, int start_row, cudaStream_t st) const {
     LimbVec v;
     for (int i = 0; i < count; i++) v.push(i, start_row + i);
-    run_chunks(v, [&](const LimbList &ll, size_t) { ntt_inv_list(dst, src, ll, nullptr, 0, st); });
+    run_chunks(v, primes_, [&](const LimbList &ll, size_t) { ntt_inv_list(dst, src, ll, nullptr, 0, st); });
 }
 
 void Engine::ntt_batch(u64 *inout, int n_poly, int count, int start_row, bool inverse, cudaStream_t st) const {
     LimbVec v;
     for (int p = 0; p < n_poly; p++)
         for (int i = 0; i < count; i++) v.push(p * count + i, start_row + i);
-    run_chunks(v, [&](const LimbList &ll, size_t) {
+    run_chunks(v, primes_, [&](const LimbList &ll, size_t) {
         if (inverse) ntt_inv_list(inout, inout, ll, nullptr, 0, st);
         else ntt_fwd_list(inout, inout, ll, st);
     });
@@ -342,7 +371,7 @@ void Engine::ntt_special_range(u64 *inout, int count, int start, int size_Ql, bo
         const int t = start + i;
         v.push(t, t < size_Ql ? t : size_Q_ + (t - size_Ql));
     }
-    run_chunks(v, [&](const LimbList &ll, size_t) {
+    run_chunks(v, primes_, [&](const LimbList &ll, size_t) {
         if (inverse) ntt_inv_list(inout, inout, ll, nullptr, 0, st);
         else ntt_fwd_list(inout, inout, ll, st);
     });
@@ -350,40 +379,41 @@ void Engine::ntt_special_range(u64 *inout, int count, int start, int size_Ql, bo
 
 void Engine::tensor_2x2(const u64 *a, const u64 *b, u64 *out, int l, cudaStream_t st) const {
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
-    k_tensor_2x2<<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 2), n_, l);
+    launch_pdl(k_tensor_2x2, grid, EW_THREADS, 0, st, a, b, out, d_mod_.p, bar(1, 2), RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, n_, l);
     check_launch("k_tensor_2x2");
 }
 
 void Engine::tensor_square(const u64 *a, u64 *out, int l, cudaStream_t st) const {
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
-    k_tensor_square<<<grid, EW_THREADS, 0, st>>>(a, out, d_mod_.p, bar(1, 0), n_, l);
+    launch_pdl(k_tensor_square, grid, EW_THREADS, 0, st, a, out, d_mod_.p, bar(1, 0), n_, l);
     check_launch("k_tensor_square");
 }
 
 void Engine::elementwise(int op, const u64 *a, const u64 *b, u64 *out, int l, cudaStream_t st) const {
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
     switch (op) {
-        case EW_ADD: k_elementwise<EW_ADD><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
-        case EW_SUB: k_elementwise<EW_SUB><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
-        case EW_MUL: k_elementwise<EW_MUL><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
-        case EW_NEG: k_elementwise<EW_NEG><<<grid, EW_THREADS, 0, st>>>(a, b, out, d_mod_.p, bar(1, 0), n_); break;
+        case EW_ADD: launch_pdl(k_elementwise<EW_ADD>, grid, EW_THREADS, 0, st, a, b, out, d_mod_.p, bar(1, 0), n_); break;
+        case EW_SUB: launch_pdl(k_elementwise<EW_SUB>, grid, EW_THREADS, 0, st, a, b, out, d_mod_.p, bar(1, 0), n_); break;
+        case EW_MUL: launch_pdl(k_elementwise<EW_MUL>, grid, EW_THREADS, 0, st, a, b, out, d_mod_.p, bar(1, 0), n_); break;
+        case EW_NEG: launch_pdl(k_elementwise<EW_NEG>, grid, EW_THREADS, 0, st, a, b, out, d_mod_.p, bar(1, 0), n_); break;
         default: throw std::invalid_argument("unknown elementwise op");
     }
     check_launch("k_elementwise");
 }
 
 static void launch_bconv(const BconvBatch &batch, int jobs, int ni, int no_max, const Modulus *mod, const BarG *bar,
-                         int size_QP, size_t n, cudaStream_t st) {
+                         RowArith ra, int size_QP, size_t n, cudaStream_t st) {
     dim3 grid((unsigned) (n / (2 * EW_THREADS)), jobs);
-    const size_t smem = (size_t) no_max * ni * 8 + (size_t) no_max * (sizeof(Modulus) + sizeof(BarG));
+    const size_t smem = (size_t) no_max * ni * (8 + 2 * sizeof(double2)) +
+                        (size_t) no_max * (sizeof(Modulus) + sizeof(BarG) + sizeof(double2) + sizeof(int)) + 16;
     switch (ni) {
-        case 1: k_bconv<1><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
-        case 2: k_bconv<2><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
-        case 3: k_bconv<3><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
-        case 4: k_bconv<4><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
-        case 5: k_bconv<5><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
-        case 6: k_bconv<6><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
-        default: k_bconv<0><<<grid, EW_THREADS, smem, st>>>(batch, mod, bar, size_QP, n); break;
+        case 1: launch_pdl(k_bconv<1>, grid, EW_THREADS, smem, st, batch, mod, bar, ra, size_QP, n); break;
+        case 2: launch_pdl(k_bconv<2>, grid, EW_THREADS, smem, st, batch, mod, bar, ra, size_QP, n); break;
+        case 3: launch_pdl(k_bconv<3>, grid, EW_THREADS, smem, st, batch, mod, bar, ra, size_QP, n); break;
+        case 4: launch_pdl(k_bconv<4>, grid, EW_THREADS, smem, st, batch, mod, bar, ra, size_QP, n); break;
+        case 5: launch_pdl(k_bconv<5>, grid, EW_THREADS, smem, st, batch, mod, bar, ra, size_QP, n); break;
+        case 6: launch_pdl(k_bconv<6>, grid, EW_THREADS, smem, st, batch, mod, bar, ra, size_QP, n); break;
+        default: launch_pdl(k_bconv<0>, grid, EW_THREADS, smem, st, batch, mod, bar, ra, size_QP, n); break;
     }
     check_launch("k_bconv");
 }
@@ -396,7 +426,7 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
     {
         LimbVec v;
         for (int i = 0; i < l; i++) v.push(i, i);
-        run_chunks(v, [&](const LimbList &ll, size_t b) { ntt_inv_list(t_cks, cks, ll, lv.modup_fin.p + 2 * b, 1, st); });
+        run_chunks(v, primes_, [&](const LimbList &ll, size_t b) { ntt_inv_list(t_cks, cks, ll, lv.modup_fin.p + 2 * b, 1, st); });
     }
     // 2. each digit: own limbs copied (modup_copy_partQl_kernel :522-528), other limbs converted (:455-485)
     for (int d = 0; d < lv.beta;) {
@@ -414,25 +444,26 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
             int kin = 0;
             for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(primes_[start + i]));
             batch.job[jobs] = BconvJob{t_cks + (size_t) start * n_, dst, lv.modup_mat.p + moff, lv.modup_omod.p + off,
-                                       lv.modup_olimb.p + off, ni, lv.digit_no[d], kin + ceil_log2(ni)};
+                                       lv.modup_olimb.p + off, ni, lv.digit_no[d], kin + ceil_log2(ni),
+                                       lv.modup_matf.p + 2 * moff, lv.digit_big[d]};
             no_max = std::max(no_max, lv.digit_no[d]);
             jobs++, d++;
         }
-        launch_bconv(batch, jobs, ni, no_max, d_mod_.p, d_bar_.p, size_QP_, n_, st);
+        launch_bconv(batch, jobs, ni, no_max, d_mod_.p, d_bar_.p, RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, size_QP_, n_, st);
     }
     // 3. forward NTT of the converted limbs only (..._exclude_range, rns_bconv.cu:618)
     {
         LimbVec v;
         v.data = lv.modup_ntt_data, v.row = lv.modup_ntt_row, v.src = lv.modup_ntt_data;
-        run_chunks(v, [&](const LimbList &ll, size_t) { ntt_fwd_list(t_mod_up, t_mod_up, ll, st); });
+        run_chunks(v, primes_, [&](const LimbList &ll, size_t) { ntt_fwd_list(t_mod_up, t_mod_up, ll, st); });
     }
 }
 
 void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st) const {
     const Level &lv = level(l);
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), lv.m);
-    k_inner_prod<<<grid, EW_THREADS, 0, st>>>(cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), n_, l, lv.m, size_Q_, size_QP_,
-                                               lv.beta);
+    launch_pdl(k_inner_prod, grid, EW_THREADS, 0, st, cx, t_mod_up, evk, d_mod_.p, bar(lv.beta),
+               RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, n_, l, lv.m, size_Q_, size_QP_, lv.beta);
     check_launch("k_inner_prod");
 }
 
@@ -448,7 +479,7 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
         LimbVec v;
         for (int k = 0; k < npoly; k++)
             for (int i = 0; i < alpha; i++) v.push(k * m + l + i, size_Q_ + i);
-        ntt_inv_list(cx, cx, single_list(v), lv.moddown_fin.p, 1, st);
+        ntt_inv_list(cx, cx, single_list(v, primes_), lv.moddown_fin.p, 1, st);
     }
     // 2. P -> Ql conversion (bConv_BEHZ matmul :143-168 / single-P :691-707)
     {
@@ -457,15 +488,16 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
         BconvBatch batch{};
         for (int k = 0; k < npoly; k++)
             batch.job[k] = BconvJob{cx + ((size_t) k * m + l) * n_, delta + (size_t) k * l * n_, lv.moddown_mat.p,
-                                    lv.moddown_omod.p, lv.moddown_olimb.p, alpha, l, pbits + ceil_log2(alpha)};
-        launch_bconv(batch, npoly, alpha, l, d_mod_.p, d_bar_.p, size_QP_, n_, st);
+                                    lv.moddown_omod.p, lv.moddown_olimb.p, alpha, l, pbits + ceil_log2(alpha),
+                                    lv.moddown_matf.p, lv.moddown_big};
+        launch_bconv(batch, npoly, alpha, l, d_mod_.p, d_bar_.p, RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, size_QP_, n_, st);
     }
     // 3. forward NTT of delta with the fused (cx - delta) * P^-1 (+ ct) epilogue (:820, ntt_moddown.cu:106-216)
     {
         LimbVec v;
         for (int k = 0; k < npoly; k++)
             for (int j = 0; j < l; j++) v.push(k * l + j, j);
-        run_chunks(v, [&](const LimbList &ll, size_t b) {
+        run_chunks(v, primes_, [&](const LimbList &ll, size_t b) {
             EpiArgs ea{};
             ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p + b;
             for (int s = 0; s < ll.count; s++) {
@@ -536,7 +568,7 @@ void Engine::apply_galois(int l, u64 *ct, uint32_t galois_elt, const u64 *const 
     const int gi = galois_index(galois_elt);
     u64 *tmp = ws_.tmp.p;   // [2][l][n]: permuted c0, c1
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), 2 * l);
-    k_galois_ntt<<<grid, EW_THREADS, 0, st>>>(tmp, ct, d_perm_[gi].p, n_);
+    launch_pdl(k_galois_ntt, grid, EW_THREADS, 0, st, tmp, ct, d_perm_[gi].p, n_);
     check_launch("k_galois_ntt");
     // ct0 = perm(c0) + ks0, ct1 = 0 + ks1: the "wipe c1" memset of the reference is folded away by
     // pointing poly 1 at a zero addend, i.e. no addend at all.
@@ -554,17 +586,17 @@ void Engine::rescale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) 
     {
         LimbVec v;
         for (int s = 0; s < size; s++) v.push(s, l - 1, s * l + (l - 1));
-        ntt_inv_list(last, in, single_list(v), nullptr, 0, st);
+        ntt_inv_list(last, in, single_list(v, primes_), nullptr, 0, st);
     }
     for (int s = 0; s < size; s++) {
         dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), nl);
-        k_reduce_last<<<grid, EW_THREADS, 0, st>>>(out + (size_t) s * nl * n_, last + (size_t) s * n_, d_mod_.p, n_);
+        launch_pdl(k_reduce_last, grid, EW_THREADS, 0, st, out + (size_t) s * nl * n_, last + (size_t) s * n_, d_mod_.p, n_);
         check_launch("k_reduce_last");
     }
     LimbVec v;
     for (int s = 0; s < size; s++)
         for (int j = 0; j < nl; j++) v.push(s * nl + j, j);
-    run_chunks(v, [&](const LimbList &ll, size_t b) {
+    run_chunks(v, primes_, [&](const LimbList &ll, size_t b) {
         EpiArgs ea{};
         ea.sub_base = in, ea.out_base = out, ea.add_base = nullptr, ea.mulc = lv.qlast_inv_slots.p + b;
         for (int k = 0; k < ll.count; k++) {

@@ -10,6 +10,13 @@
 
 namespace pfhe {
 
+// Programmatic dependent launch (sm_90+): every kernel of the engine lets its successor in the stream start
+// launching right away (pdl_launch_dependents) and waits for its predecessor's results only after its own
+// prologue (pdl_wait).  Kernels are launched with cudaLaunchAttributeProgrammaticStreamSerialization (launch.hpp),
+// so the ~4 us drain + launch gap between the 12 dependent kernels of a key switch overlaps with useful work.
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;"); }
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+
 using u64 = unsigned long long;
 using u32 = unsigned int;
 
@@ -127,5 +134,45 @@ struct Acc128 {
         hi += ph + (lo < pl);
     }
 };
+
+// ---------------------------------------------------------------------------------------------------
+// FP64-pipe modular arithmetic for moduli below 2^46: values are exact integers held in doubles, products are
+// error-free FMA sequences (see FpArith in ntt.cuh and tests/fp_modmul_check.c).  Used by every kernel for the
+// small limbs of a chain; the results are converted back to the same canonical residues.
+// ---------------------------------------------------------------------------------------------------
+namespace fp {
+constexpr double TWO52 = 4503599627370496.0;   // 2^52
+constexpr double MAGIC = 6755399441055744.0;   // 1.5 * 2^52
+constexpr int MAX_BITS = 46;
+constexpr int SPLIT_BITS = 30;                 // operands from a >= 2^46 modulus enter as two 30/31-bit halves
+
+__device__ __forceinline__ double from_u64(u64 v) {   // exact for v < 2^52
+    return __longlong_as_double((long long) (v | 0x4330000000000000ull)) - TWO52;
+}
+__device__ __forceinline__ u64 to_u64(double v) {     // exact for integers 0 <= v < 2^52
+    return ((u64) __double_as_longlong(v + TWO52)) & 0x000fffffffffffffull;
+}
+__device__ __forceinline__ double reduce(double v, double q, double qinv) {   // -> [-q/2, q/2]
+    const double k = __fma_rn(v, qinv, MAGIC) - MAGIC;
+    return __fma_rn(-k, q, v);
+}
+// y * w mod q for a constant w with precomputed winv = w/q: result in (-0.63q, 0.63q)
+__device__ __forceinline__ double mulmod_c(double y, double w, double winv, double q) {
+    const double k = __fma_rn(y, winv, MAGIC) - MAGIC;
+    const double p = y * w;
+    const double e = __fma_rn(y, w, -p);
+    return __fma_rn(-k, q, p) + e;
+}
+// a * b mod q, both variable, |a|,|b| < 2^47
+__device__ __forceinline__ double mulmod_v(double a, double b, double q, double qinv) {
+    const double p = a * b;
+    const double e = __fma_rn(a, b, -p);
+    const double k = __fma_rn(p, qinv, MAGIC) - MAGIC;
+    return __fma_rn(-k, q, p) + e;
+}
+__device__ __forceinline__ u64 canon(double v, double q) {   // v in (-q, q) -> [0, q)
+    return to_u64(v < 0.0 ? v + q : v);
+}
+} // namespace fp
 
 } // namespace pfhe

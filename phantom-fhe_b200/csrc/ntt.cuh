@@ -19,6 +19,7 @@
 #pragma once
 #include <type_traits>
 #include "modarith.cuh"
+#include "tma.cuh"
 
 namespace pfhe {
 
@@ -39,6 +40,8 @@ struct LimbList {
     short data[NTT_MAX_LIMBS];   // destination limb (and source limb when src_same)
     short row[NTT_MAX_LIMBS];    // key-level prime row
     short src[NTT_MAX_LIMBS];    // source limb of the first pass (out-of-place launches)
+    u64 q[NTT_MAX_LIMBS];        // the modulus itself: kernels derive every per-limb constant from it without a
+                                 // dependent global load at kernel start (q < 2^46 selects the FP64 butterflies)
 };
 
 // epilogue of the fused forward row pass:  out = (sub - NTT(x)) * mulc  (+ add)   mod q
@@ -86,9 +89,10 @@ __host__ __device__ inline size_t tw_native_index(int logn, int s, size_t B) {
 // patterns of the radix-8 rounds are: 16 contiguous words; 4 contiguous x 4 blocks 32 apart; 16 lanes 4
 // apart; 8 contiguous x 2 blocks 32 apart.  Folding bits 4..6 into bits 0..3 makes all of them hit 16
 // distinct bank pairs (derivation in DESIGN.md); it is a bijection inside every aligned 128-word block.
-__device__ __forceinline__ int skew(int i) {
-    return i ^ ((i >> 4) & 3) ^ (((i >> 5) & 1) << 3) ^ (((i >> 6) & 1) << 2);
+__host__ __device__ constexpr int skew_bits(int i) {   // GF(2)-linear in bits 4..6 of i, lands in bits 0..3
+    return ((i >> 4) & 3) ^ (((i >> 5) & 1) << 3) ^ (((i >> 6) & 1) << 2);
 }
+__host__ __device__ constexpr int skew(int i) { return i ^ skew_bits(i); }
 
 // ----------------------------------------------------------------------------------------------------
 // element <-> thread mapping of one round
@@ -121,7 +125,14 @@ struct RoundMap {
         }
     }
     __device__ static __forceinline__ int elem(int hi, int k, int lo) { return (hi << (P - S0)) | (k << LAM) | lo; }
-    __device__ static __forceinline__ int sidx(int e, int c) { return skew(ROWS ? c * T + e : e * C + c); }
+    // exchange-tile position of element k of a group: the k field occupies its own bits of the linear index, the
+    // swizzle is XOR-linear, hence position = sidx0 ^ KC(k) with a compile-time KC -- one LOP per access
+    static constexpr int KSHIFT = ROWS ? LAM : LAM + GAM;
+    __device__ static __forceinline__ int sidx0(int hi, int lo, int c) {
+        const int e = (hi << (P - S0)) | lo;
+        return skew(ROWS ? (c << P) | e : (e << GAM) | c);
+    }
+    __host__ __device__ static constexpr int kc(int k) { return skew(k << KSHIFT); }
 };
 
 // ----------------------------------------------------------------------------------------------------
@@ -143,9 +154,7 @@ struct IntArith {
     struct Consts {
         u64 q, q2, q4, nq;
     };
-    __device__ static __forceinline__ Consts consts(const Modulus &m, const double2 &) {
-        return Consts{m.q, 2 * m.q, 4 * m.q, 0 - m.q};
-    }
+    __device__ static __forceinline__ Consts consts(u64 q) { return Consts{q, 2 * q, 4 * q, 0 - q}; }
     __device__ static __forceinline__ T load(u64 canonical, const Consts &) { return canonical; }
     __device__ static __forceinline__ u64 raw(T v) { return v; }
     __device__ static __forceinline__ T from_raw(u64 bits) { return bits; }
@@ -187,7 +196,10 @@ struct FpArith {
     };
     static constexpr double TWO52 = 4503599627370496.0;          // 2^52
     static constexpr double MAGIC = 6755399441055744.0;          // 1.5 * 2^52: round-to-nearest-integer trick
-    __device__ static __forceinline__ Consts consts(const Modulus &, const double2 &f) { return Consts{f.x, f.y}; }
+    __device__ static __forceinline__ Consts consts(u64 q) {   // same values as the host table: IEEE division
+        const double qd = (double) q;
+        return Consts{qd, 1.0 / qd};
+    }
     __device__ static __forceinline__ T load(u64 canonical, const Consts &) {   // exact for values < 2^52
         return __longlong_as_double((long long) (canonical | 0x4330000000000000ull)) - TWO52;
     }
@@ -238,23 +250,48 @@ struct FpArith {
     __device__ static __forceinline__ u64 canon_inv(T v, const Consts &) { return to_u64(v); }
 };
 
-// twiddle index of (stage S0+u, hi, b) for this tile
+// Twiddles of a tile are staged in shared memory by TMA bulk copies (stage_twiddles below); position of the
+// twiddle of (stage S0+u, hi, b) in that staging area.  Column pass: the 2^P1 - 1 twiddles of the first P1 stages
+// in table order.  Row pass: per stage sigma the C rows of the tile are contiguous in the table
+// (C * 2^sigma entries starting at 2^(P1+sigma) + row0 * 2^sigma), stored back to back: offset C * (2^sigma - 1).
 template<class M, bool ROWS, int LOGN>
-__device__ __forceinline__ int tw_index(int u, int hi, int b, int row) {
+__device__ __forceinline__ int tw_index(int u, int hi, int b, int c) {
     if constexpr (!ROWS) {
         return (1 << (M::S0 + u)) + ((hi << u) | b);
     } else {
-        constexpr int P1 = ntt_p1(LOGN);
-        const int s = P1 + M::S0 + u;
-        const int base = (1 << s) + (row << (M::S0 + u));
+        const int sigma = M::S0 + u;
+        const int base = M::C * ((1 << sigma) - 1) + (c << sigma);
         if constexpr (M::LAST) return base + (b << M::S0) + hi;
         else return base + ((hi << u) | b);
     }
 }
 
+constexpr int NTT_STW_ENTRIES = NTT_TILE;   // upper bound of staged twiddles per tile (C * (2^P - 1) < 2^LOG_TILE)
+
+// issue the bulk copies of this tile's twiddles (one thread); completion is signalled on `bar`
+template<int P, bool ROWS, int LOGN>
+__device__ __forceinline__ void stage_twiddles(Tw *stw, const Tw *tw_limb, int tile, uint64_t *bar) {
+    if constexpr (!ROWS) {
+        constexpr uint32_t bytes = (1u << P) * sizeof(Tw);
+        mbar_expect_tx(bar, bytes);
+        tma_load_1d(stw, tw_limb, bytes, bar);
+    } else {
+        constexpr int P1 = LOGN - P;
+        constexpr int C = 1 << (NTT_LOG_TILE - P);
+        constexpr uint32_t total = C * ((1u << P) - 1) * sizeof(Tw);
+        mbar_expect_tx(bar, total);
+#pragma unroll
+        for (int sigma = 0; sigma < P; sigma++) {
+            const size_t src = ((size_t) 1 << (P1 + sigma)) + ((size_t) (tile * C) << sigma);
+            tma_load_1d(stw + C * ((1 << sigma) - 1), tw_limb + src, (uint32_t) (C << sigma) * sizeof(Tw), bar);
+        }
+    }
+}
+
 template<class A>
 struct PassCtx {
-    const Tw *tw;               // table of this limb
+    const Tw *tw;               // this tile's twiddles, staged in shared memory (tw_index order)
+    uint64_t *bar;              // mbarrier the staging copies complete on
     typename A::Consts c;
     int tile;                   // tile index inside the limb (column block resp. row block)
     Tw fin_x, fin_y;            // constants of the last inverse stage
@@ -262,8 +299,8 @@ struct PassCtx {
 
 // one forward round on the registers of a thread: x[g * 2^R + k]
 template<class A, class M, bool ROWS, int LOGN, int SBASE>
-__device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw *__restrict__ tw,
-                                          const int (&hi)[M::G], const int (&row)[M::G],
+__device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw *tw,
+                                          const int (&hi)[M::G], const int (&cc)[M::G],
                                           const typename A::Consts &c) {
     constexpr int R = M::R;
 #pragma unroll
@@ -274,7 +311,7 @@ __device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw 
             Tw w[M::G];
 #pragma unroll
             for (int g = 0; g < M::G; g++) {
-                if (g == 0 || !M::SHARE) w[g] = __ldg(&tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, row[g])]);
+                if (g == 0 || !M::SHARE) w[g] = tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g])];
                 else w[g] = w[0];
             }
 #pragma unroll
@@ -293,8 +330,8 @@ __device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw 
 
 // one inverse round (stages S0+R-1 down to S0).  FINAL marks the round containing global stage 0.
 template<class A, class M, bool ROWS, int LOGN, bool FINAL>
-__device__ __forceinline__ void inv_round(typename A::T (&x)[NTT_EPT], const Tw *__restrict__ tw,
-                                          const int (&hi)[M::G], const int (&row)[M::G],
+__device__ __forceinline__ void inv_round(typename A::T (&x)[NTT_EPT], const Tw *tw,
+                                          const int (&hi)[M::G], const int (&cc)[M::G],
                                           const typename A::Consts &c, Tw fin_x, Tw fin_y) {
     constexpr int R = M::R;
 #pragma unroll
@@ -306,7 +343,7 @@ __device__ __forceinline__ void inv_round(typename A::T (&x)[NTT_EPT], const Tw 
             if (!(FINAL && u == 0)) {
 #pragma unroll
                 for (int g = 0; g < M::G; g++) {
-                    if (g == 0 || !M::SHARE) w[g] = __ldg(&tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, row[g])]);
+                    if (g == 0 || !M::SHARE) w[g] = tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g])];
                     else w[g] = w[0];
                 }
             }
@@ -351,11 +388,11 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
     auto run_round = [&](auto ri_tag) {
         constexpr int RI = decltype(ri_tag)::value;
         using M = RoundMap<P, RI, ROWS>;
-        int hi[M::G], lo[M::G], c[M::G], row[M::G];
+        int hi[M::G], lo[M::G], c[M::G], s0[M::G];
 #pragma unroll
         for (int g = 0; g < M::G; g++) {
             M::decode(M::mu(tid, g), hi[g], lo[g], c[g]);
-            row[g] = (cx.tile << M::GAM) + c[g];
+            s0[g] = M::sidx0(hi[g], lo[g], c[g]);
         }
         // gather
 #pragma unroll
@@ -364,9 +401,10 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
             for (int k = 0; k < (1 << M::R); k++) {
                 const int e = M::elem(hi[g], k, lo[g]);
                 if constexpr (RI == 0) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
-                else x[(g << M::R) + k] = A::from_raw(smem[M::sidx(e, c[g])]);
+                else x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
             }
-        fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, row, cx.c);
+        if constexpr (RI == 0) mbar_wait(cx.bar, 0);   // twiddles landed (copies overlapped the gather above)
+        fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, c, cx.c);
         // scatter
         constexpr bool DIRECT_OUT = (RI == NR - 1) && !ROWS;
         if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
@@ -376,7 +414,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
             for (int k = 0; k < (1 << M::R); k++) {
                 const int e = M::elem(hi[g], k, lo[g]);
                 if constexpr (DIRECT_OUT) store(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile), x[(g << M::R) + k]);
-                else smem[M::sidx(e, c[g])] = A::raw(x[(g << M::R) + k]);
+                else smem[s0[g] ^ M::kc(k)] = A::raw(x[(g << M::R) + k]);
             }
         if constexpr (!DIRECT_OUT) __syncthreads();
     };
@@ -388,12 +426,10 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
 
     if constexpr (ROWS) {
         // the tile is contiguous in global memory: flat, fully coalesced copy-out
-        const size_t base = (size_t) cx.tile << NTT_LOG_TILE;
+        const size_t base = ((size_t) cx.tile << NTT_LOG_TILE) + tid;
+        const int st = skew(tid);   // i * NTT_THREADS only touches bits >= 8: the swizzle term is per thread
 #pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) {
-            const int j = i * NTT_THREADS + tid;
-            store(base + j, A::from_raw(smem[skew(j)]));
-        }
+        for (int i = 0; i < NTT_EPT; i++) store(base + i * NTT_THREADS, A::from_raw(smem[st + i * NTT_THREADS]));
     }
 }
 
@@ -406,23 +442,21 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
 
     if constexpr (ROWS) {
         // flat coalesced copy-in, the first inverse round then reads its contiguous elements from smem
-        const size_t base = (size_t) cx.tile << NTT_LOG_TILE;
+        const size_t base = ((size_t) cx.tile << NTT_LOG_TILE) + tid;
+        const int st = skew(tid);
 #pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) {
-            const int j = i * NTT_THREADS + tid;
-            smem[skew(j)] = A::raw(load(base + j));
-        }
+        for (int i = 0; i < NTT_EPT; i++) smem[st + i * NTT_THREADS] = A::raw(load(base + i * NTT_THREADS));
         __syncthreads();
     }
 
     auto run_round = [&](auto ri_tag) {
         constexpr int RI = decltype(ri_tag)::value;
         using M = RoundMap<P, RI, ROWS>;
-        int hi[M::G], lo[M::G], c[M::G], row[M::G];
+        int hi[M::G], lo[M::G], c[M::G], s0[M::G];
 #pragma unroll
         for (int g = 0; g < M::G; g++) {
             M::decode(M::mu(tid, g), hi[g], lo[g], c[g]);
-            row[g] = (cx.tile << M::GAM) + c[g];
+            s0[g] = M::sidx0(hi[g], lo[g], c[g]);
         }
         constexpr bool DIRECT_IN = (RI == NR - 1) && !ROWS;
 #pragma unroll
@@ -431,9 +465,10 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
             for (int k = 0; k < (1 << M::R); k++) {
                 const int e = M::elem(hi[g], k, lo[g]);
                 if constexpr (DIRECT_IN) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
-                else x[(g << M::R) + k] = A::from_raw(smem[M::sidx(e, c[g])]);
+                else x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
             }
-        inv_round<A, M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, row, cx.c, cx.fin_x, cx.fin_y);
+        if constexpr (RI == NR - 1) mbar_wait(cx.bar, 0);
+        inv_round<A, M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, c, cx.c, cx.fin_x, cx.fin_y);
         if constexpr (RI == 0) {
             // first round in index order = last in time: values leave the pass
 #pragma unroll
@@ -450,7 +485,7 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++) {
                     const int e = M::elem(hi[g], k, lo[g]);
-                    smem[M::sidx(e, c[g])] = A::raw(x[(g << M::R) + k]);
+                    smem[s0[g] ^ M::kc(k)] = A::raw(x[(g << M::R) + k]);
                 }
             __syncthreads();
         }

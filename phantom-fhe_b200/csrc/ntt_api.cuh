@@ -13,6 +13,7 @@ struct NttPlan {
     // rows with q < 2^46 run the FP64 butterflies: their table entries hold (double(w), double(w)/double(q))
     const unsigned char *is_fp;   // [size_QP]
     const double2 *fpc;           // [size_QP] {double(q), 1/double(q)}
+    int fp_enabled;               // 0: integer butterflies everywhere (PFHE_FP64_NTT=0)
 };
 
 // forward negacyclic NTT of the limbs in `ll` (replaces nwt_2d_radix8_forward_inplace and its

@@ -11,6 +11,18 @@ namespace pfhe {
 
 constexpr int EW_THREADS = 256;
 
+// per-row arithmetic selector shared with the NTT kernels: rows below 2^46 use the FP64 pipe
+struct RowArith {
+    const unsigned char *is_fp;   // [size_QP]
+    const double2 *fpc;           // [size_QP] {q, 1/q}
+    u64 mask0, mask1;             // the same flags for rows 0..127 as a by-value bit mask: no dependent load
+    int use_mask;
+    __device__ __forceinline__ bool fp(int row) const {
+        if (use_mask) return ((row < 64 ? mask0 >> row : mask1 >> (row - 64)) & 1) != 0;
+        return is_fp[row] != 0;
+    }
+};
+
 __device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
 __device__ __forceinline__ ulonglong2 ld2_nc(const u64 *p) { return __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
 __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
@@ -21,7 +33,9 @@ __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ul
 // grid.y = limb, grid.x * EW_THREADS * 2 = n
 // ---------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u64 *b, u64 *out, const Modulus *mod,
-                                                            const BarG *bar, size_t n, int l) {
+                                                            const BarG *bar, RowArith ra, size_t n, int l) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int limb = blockIdx.y;
     const Modulus m = mod[limb];
     const BarG bg = bar[limb];   // growth class 2: (c0+c1)(c0'+c1') < 4 q^2
@@ -30,6 +44,23 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u
     const ulonglong2 a0 = ld2(a + i), a1 = ld2(a + i + poly), b0 = ld2(b + i), b1 = ld2(b + i + poly);
     u64 d0[2], d1[2], d2[2];
     const u64 A0[2] = {a0.x, a0.y}, A1[2] = {a1.x, a1.y}, B0[2] = {b0.x, b0.y}, B1[2] = {b1.x, b1.y};
+    if (ra.fp(limb)) {   // CTA-uniform: small limb, FP64 pipe
+        const double q = ra.fpc[limb].x, qi = ra.fpc[limb].y;
+#pragma unroll
+        for (int k = 0; k < 2; k++) {
+            const double x0 = fp::from_u64(A0[k]), x1 = fp::from_u64(A1[k]);
+            const double y0 = fp::from_u64(B0[k]), y1 = fp::from_u64(B1[k]);
+            const double e0 = fp::mulmod_v(x0, y0, q, qi), e2 = fp::mulmod_v(x1, y1, q, qi);
+            const double t = fp::mulmod_v(x0 + x1, y0 + y1, q, qi);
+            d0[k] = fp::canon(e0, q);
+            d2[k] = fp::canon(e2, q);
+            d1[k] = fp::canon(fp::reduce(t - e0 - e2, q, qi), q);
+        }
+        st2(out + i, d0[0], d0[1]);
+        st2(out + i + poly, d1[0], d1[1]);
+        st2(out + i + 2 * poly, d2[0], d2[1]);
+        return;
+    }
 #pragma unroll
     for (int k = 0; k < 2; k++) {
         d0[k] = mul_mod_g(A0[k], B0[k], bg, m);
@@ -45,6 +76,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u
 // tensor_square_2x2_rns_poly (src/polymath.cu:500-532)
 __global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 *out, const Modulus *mod,
                                                                const BarG *bar, size_t n, int l) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int limb = blockIdx.y;
     const Modulus m = mod[limb];
     const BarG bg = bar[limb];
@@ -69,6 +102,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 
 template<int OP>
 __global__ void __launch_bounds__(EW_THREADS) k_elementwise(const u64 *a, const u64 *b, u64 *out, const Modulus *mod,
                                                              const BarG *bar, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int limb = blockIdx.y;
     const Modulus m = mod[limb];
     const BarG bg = bar[limb];
@@ -101,6 +136,8 @@ struct BconvJob {
     int ni, no;
     int xbits;            // bit length bound of the accumulated sum minus the output modulus' own bits:
                           // max input-prime bits + ceil(log2 ni); selects the Barrett class per output limb
+    const double2 *matf;  // [no][ni][2] FP64 form for outputs below 2^46: {M, M/p} and {M 2^30 mod p, that/p}
+    unsigned in_big;      // bit i set: input limb i comes from a modulus >= 2^46 and enters as two 30-bit halves
 };
 constexpr int BCONV_MAX_IN = 8;   // alpha <= 8 per digit on this path (larger digits use the generic loop)
 constexpr int BCONV_MAX_JOBS = 16;
@@ -110,41 +147,85 @@ struct BconvBatch {
 
 template<int NI>
 __global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Modulus *mod, const BarG *bar,
-                                                       int size_QP, size_t n) {
-    extern __shared__ u64 s_mem[];
+                                                       RowArith ra, int size_QP, size_t n) {
+    pdl_launch_dependents();
+    extern __shared__ __align__(16) unsigned char s_raw[];
     const BconvJob jb = batch.job[blockIdx.y];
     const int ni = NI > 0 ? NI : jb.ni;
-    u64 *s_mat = s_mem;                                   // [no][ni]
-    Modulus *s_mod = reinterpret_cast<Modulus *>(s_mem + jb.no * ni);
-    BarG *s_bar = reinterpret_cast<BarG *>(s_mod + jb.no);
-    for (int i = threadIdx.x; i < jb.no * ni; i += blockDim.x) s_mat[i] = jb.mat[i];
+    // shared (16-byte types first): [matf: no*ni*2 double2][fpc: no double2][bar: no][mat: no*ni u64][mod: no][fp flag: no]
+    double2 *s_matf = reinterpret_cast<double2 *>(s_raw);
+    double2 *s_fpc = s_matf + jb.no * ni * 2;
+    BarG *s_bar = reinterpret_cast<BarG *>(s_fpc + jb.no);
+    u64 *s_mat = reinterpret_cast<u64 *>(s_bar + jb.no);
+    Modulus *s_mod = reinterpret_cast<Modulus *>(s_mat + jb.no * ni);
+    int *s_isfp = reinterpret_cast<int *>(s_mod + jb.no);
+    for (int i = threadIdx.x; i < jb.no * ni; i += blockDim.x) {
+        s_mat[i] = jb.mat[i];
+        s_matf[2 * i] = jb.matf[2 * i];
+        s_matf[2 * i + 1] = jb.matf[2 * i + 1];
+    }
     for (int i = threadIdx.x; i < jb.no; i += blockDim.x) {
-        const Modulus mo = mod[jb.omod[i]];
+        const int row = jb.omod[i];
+        const Modulus mo = mod[row];
         s_mod[i] = mo;
         // sum < 2^(xbits + k_out): class = xbits - k_out above the same-modulus case 2 k_out
         const int cls = max(0, jb.xbits - (64 - __clzll((long long) mo.q)));
-        s_bar[i] = bar[(size_t) min(cls, 63) * size_QP + jb.omod[i]];
+        s_bar[i] = bar[(size_t) min(cls, 63) * size_QP + row];
+        s_fpc[i] = ra.fpc[row];
+        s_isfp[i] = ra.fp(row);
     }
+    pdl_wait();
     __syncthreads();
     const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     if (NI > 0) {
-        u64 y0[NI > 0 ? NI : 1], y1[NI > 0 ? NI : 1];
+        constexpr int NN = NI > 0 ? NI : 1;
+        u64 y0[NN], y1[NN];
+        double l0[NN], h0[NN], l1[NN], h1[NN];
 #pragma unroll
         for (int i = 0; i < NI; i++) {
             const ulonglong2 v = ld2(jb.in + (size_t) i * n + x);
             y0[i] = v.x, y1[i] = v.y;
+            if ((jb.in_big >> i) & 1) {
+                const u64 msk = (1ull << fp::SPLIT_BITS) - 1;
+                l0[i] = fp::from_u64(v.x & msk), h0[i] = fp::from_u64(v.x >> fp::SPLIT_BITS);
+                l1[i] = fp::from_u64(v.y & msk), h1[i] = fp::from_u64(v.y >> fp::SPLIT_BITS);
+            } else {
+                l0[i] = fp::from_u64(v.x), l1[i] = fp::from_u64(v.y);
+                h0[i] = h1[i] = 0.0;
+            }
         }
         for (int j = 0; j < jb.no; j++) {
-            Acc128 a0{0, 0}, a1{0, 0};
+            u64 r0, r1;
+            if (s_isfp[j]) {   // CTA-uniform per output limb
+                const double q = s_fpc[j].x, qi = s_fpc[j].y;
+                double a0 = 0.0, a1 = 0.0;
 #pragma unroll
-            for (int i = 0; i < NI; i++) {
-                const u64 mji = s_mat[j * NI + i];
-                a0.mac(y0[i], mji);
-                a1.mac(y1[i], mji);
+                for (int i = 0; i < NI; i++) {
+                    const double2 m0 = s_matf[2 * (j * NI + i)];
+                    a0 += fp::mulmod_c(l0[i], m0.x, m0.y, q);
+                    a1 += fp::mulmod_c(l1[i], m0.x, m0.y, q);
+                    if ((jb.in_big >> i) & 1) {
+                        const double2 m1 = s_matf[2 * (j * NI + i) + 1];
+                        a0 += fp::mulmod_c(h0[i], m1.x, m1.y, q);
+                        a1 += fp::mulmod_c(h1[i], m1.x, m1.y, q);
+                    }
+                }
+                r0 = fp::canon(fp::reduce(a0, q, qi), q);
+                r1 = fp::canon(fp::reduce(a1, q, qi), q);
+            } else {
+                Acc128 a0{0, 0}, a1{0, 0};
+#pragma unroll
+                for (int i = 0; i < NI; i++) {
+                    const u64 mji = s_mat[j * NI + i];
+                    a0.mac(y0[i], mji);
+                    a1.mac(y1[i], mji);
+                }
+                const Modulus m = s_mod[j];
+                const BarG bg = s_bar[j];
+                r0 = barrett_g(a0.lo, a0.hi, bg, m);
+                r1 = barrett_g(a1.lo, a1.hi, bg, m);
             }
-            const Modulus m = s_mod[j];
-            const BarG bg = s_bar[j];
-            st2(jb.out + (size_t) jb.olimb[j] * n + x, barrett_g(a0.lo, a0.hi, bg, m), barrett_g(a1.lo, a1.hi, bg, m));
+            st2(jb.out + (size_t) jb.olimb[j] * n + x, r0, r1);
         }
     } else {
         for (int j = 0; j < jb.no; j++) {
@@ -171,14 +252,34 @@ __global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Mo
 // ---------------------------------------------------------------------------------------------------
 constexpr int KS_MAX_BETA = 64;
 __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
-                                                            const Modulus *mod, const BarG *bar, size_t n, int l, int m,
-                                                            int size_Q, int size_QP, int beta) {
+                                                            const Modulus *mod, const BarG *bar, RowArith ra, size_t n,
+                                                            int l, int m, int size_Q, int size_QP, int beta) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.y;
     const int row = j < l ? j : size_Q + (j - l);
     const Modulus md = mod[row];
     const BarG bg = bar[row];   // growth class ceil(log2 beta)
     const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const size_t m_n = (size_t) m * n, qp_n = (size_t) size_QP * n;
+    if (ra.fp(row)) {   // CTA-uniform: every term is reduced on the FP64 pipe, the small residues are summed
+        const double q = ra.fpc[row].x, qi = ra.fpc[row].y;
+        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+#pragma unroll 4
+        for (int d = 0; d < beta; d++) {
+            const u64 *k0 = evk[d] + (size_t) row * n + x;
+            const ulonglong2 v = ld2(t + (size_t) d * m_n + (size_t) j * n + x);
+            const ulonglong2 e0 = ld2_nc(k0), e1 = ld2_nc(k0 + qp_n);
+            const double vx = fp::from_u64(v.x), vy = fp::from_u64(v.y);
+            s00 += fp::mulmod_v(vx, fp::from_u64(e0.x), q, qi);
+            s01 += fp::mulmod_v(vy, fp::from_u64(e0.y), q, qi);
+            s10 += fp::mulmod_v(vx, fp::from_u64(e1.x), q, qi);
+            s11 += fp::mulmod_v(vy, fp::from_u64(e1.y), q, qi);
+        }
+        st2(cx + (size_t) j * n + x, fp::canon(fp::reduce(s00, q, qi), q), fp::canon(fp::reduce(s01, q, qi), q));
+        st2(cx + m_n + (size_t) j * n + x, fp::canon(fp::reduce(s10, q, qi), q), fp::canon(fp::reduce(s11, q, qi), q));
+        return;
+    }
     Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
 #pragma unroll 4
     for (int d = 0; d < beta; d++) {
@@ -198,6 +299,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
 
 // apply_galois_ntt_permutation (reference src/galois.cu:11-18): dst[l][i] = src[l][perm[i]]
 __global__ void __launch_bounds__(EW_THREADS) k_galois_ntt(u64 *dst, const u64 *src, const uint32_t *perm, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const size_t limb = blockIdx.y;
     const size_t i = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const uint2 p = *reinterpret_cast<const uint2 *>(perm + i);
@@ -207,6 +310,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_galois_ntt(u64 *dst, const u64 *
 // CKKS rescale pieces (divide_and_round_q_last_ntt, reference src/rns.cu:1128-1184)
 // r[j][x] = last[x] mod q_j
 __global__ void __launch_bounds__(EW_THREADS) k_reduce_last(u64 *dst, const u64 *last, const Modulus *mod, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
     const int j = blockIdx.y;
     const Modulus m = mod[j];
     const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
