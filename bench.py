@@ -208,13 +208,13 @@ def main():
 
     def device_step(i):
         k = i % N_PAIRS
-        # multiply_inplace + relinearize_inplace overwrite encrypted1: operate on a fresh copy like ckks_bench.cu does
-        check(lib.pfhe_multiply_and_relin_inplace(ctx._h, 1, work[k].data_ptr(), db[k].data_ptr(), rlk.public_keys_ptr(),
-                                                  st))
+        # multiply + relinearize of pair k; the result goes to its own buffer (the reference's in-place form
+        # reallocates the ciphertext, include/ciphertext.h:44-72), operands stay intact
+        check(lib.pfhe_multiply_and_relin(ctx._h, 1, da[k].data_ptr(), db[k].data_ptr(), work[k].data_ptr(),
+                                          rlk.public_keys_ptr(), st))
 
     def refill():
-        for k in range(N_PAIRS):
-            work[k].copy_(da[k])
+        pass
 
     def barrier():
         torch.cuda.synchronize()

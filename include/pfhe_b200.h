@@ -120,6 +120,11 @@ int pfhe_keyswitch_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypt
  * encrypted1 = [2][l][n] in/out, encrypted2 = [2][l][n] */
 int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted1,
                                     const uint64_t *encrypted2, const uint64_t *const *relin_keys, void *stream);
+/* same, result written to a separate [2][l][n] buffer (no operand copy; what the in-place form's resize does in
+ * the reference, include/ciphertext.h:44-72, is left to the caller) */
+int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
+                            const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
+                            void *stream);
 /* multiply_inplace alone: destination = [3][l][n] */
 int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1, const uint64_t *encrypted2,
                   uint64_t *destination, void *stream);

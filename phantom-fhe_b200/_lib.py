@@ -3,7 +3,7 @@ import ctypes
 import os
 
 _here = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_here, "libpfhe_b200.so")
+LIB_PATH = os.environ.get("PFHE_B200_LIB") or os.path.join(_here, "libpfhe_b200.so")   # override: A/B builds
 
 if not os.path.exists(LIB_PATH):
     raise ImportError(
@@ -47,6 +47,7 @@ _sigs = {
     "pfhe_moddown_from_ntt": (ctypes.c_int, [vp, sz, vp, vp, vp]),
     "pfhe_keyswitch_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
     "pfhe_multiply_and_relin_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
+    "pfhe_multiply_and_relin": (ctypes.c_int, [vp, sz, vp, vp, vp, vp, vp]),
     "pfhe_multiply": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
     "pfhe_relinearize_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp]),
     "pfhe_apply_galois_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_uint32, vp, vp]),

@@ -228,8 +228,10 @@ def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
         raise ValueError("encrypted1 and encrypted2 must be in NTT form")
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
-    check(lib.pfhe_multiply_and_relin_inplace(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
-                                              _ptr(encrypted2.data), relin_keys.public_keys_ptr(), _stream()))
+    dst = torch.empty_like(encrypted1.data)
+    check(lib.pfhe_multiply_and_relin(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
+                                      _ptr(encrypted2.data), _ptr(dst), relin_keys.public_keys_ptr(), _stream()))
+    encrypted1.data = dst   # like the reference's resize: the ciphertext now owns a new buffer
     if context.scheme == scheme_type.ckks:
         encrypted1.scale = encrypted1.scale * encrypted2.scale
 

@@ -244,6 +244,14 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
     e->impl.multiply_relin(l, U(ct1), U(ct1), U(ct2), K(rlk), S(stream));
     API_END
 }
+int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2,
+                            uint64_t *dst, const uint64_t *const *rlk, void *stream) {
+    API_BEGIN
+    require_ckks_like(e->impl);
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.multiply_relin(l, U(dst), U(ct1), U(ct2), K(rlk), S(stream));
+    API_END
+}
 int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, uint64_t *dst,
                   void *stream) {
     API_BEGIN

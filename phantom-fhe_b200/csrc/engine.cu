@@ -459,11 +459,16 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
     }
 }
 
-void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st) const {
+void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st,
+                        const u64 *own_c2, const TensorSrc *ts) const {
     const Level &lv = level(l);
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), lv.m);
-    launch_pdl(k_inner_prod, grid, EW_THREADS, 0, st, cx, t_mod_up, evk, d_mod_.p, bar(lv.beta),
-               RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, n_, l, lv.m, size_Q_, size_QP_, lv.beta);
+    OwnSrc os{nullptr, nullptr, nullptr, 0};
+    if (own_c2) os = OwnSrc{own_c2, nullptr, nullptr, lv.alpha};
+    else if (ts) os = OwnSrc{nullptr, ts->a + (size_t) ts->l * n_, ts->b + (size_t) ts->l * n_, lv.alpha};
+    launch_pdl(k_inner_prod, grid, EW_THREADS, 0, st, cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), bar(1, 0),
+               RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, n_, l, lv.m, size_Q_,
+               size_QP_, lv.beta);
     check_launch("k_inner_prod");
 }
 
@@ -512,18 +517,135 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
     }
 }
 
+// Fused key switch (same result as keyswitch(): modup -> inner product -> moddown -> add):
+//   inverse NTT (+ digit scaling, optionally of a1*b1)  ->  [bconv | forward NTT] of the converted limbs
+//   ->  inner product (own-digit limbs straight from c2 / a1*b1)  ->  inverse NTT of the P limbs
+//   ->  [bconv | forward NTT | (cx - delta) P^-1 + addend]          9 kernels, no copies, no t_cks->t_mod_up pass
+void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts, const u64 *const *evk,
+                             const u64 *addend, unsigned add_mask, cudaStream_t st) {
+    const Level &lv = level(l);
+    const int alpha = lv.alpha, m = lv.m;
+    if (alpha == 0) throw std::logic_error("key switching needs special primes");
+    if (alpha > FUSE_MAX_IN || (size_t) lv.beta * m > NTT_MAX_LIMBS || 2 * l > NTT_MAX_LIMBS) {
+        // shapes outside the fused kernels' limits take the modular path
+        const u64 *src = c2;
+        if (ts) {
+            tensor_2x2(ts->a, ts->b, ws_.tmp.p, l, st);
+            src = ws_.tmp.p + (size_t) 2 * l * n_;
+            addend = ws_.tmp.p, add_mask = 3u;
+        }
+        modup(l, ws_.t_mod_up.p, src, ws_.t_cks.p, st);
+        inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
+        moddown(l, out, ws_.cx.p, ws_.delta.p, 2, addend, add_mask, st);
+        return;
+    }
+    u64 *t_cks = ws_.t_cks.p, *t_mod_up = ws_.t_mod_up.p, *cx = ws_.cx.p, *delta = ws_.delta.p;
+    // 1. inverse NTT fused with n^-1 * qhat_i^-1 (and with the a1*b1 product for HMult)
+    {
+        LimbVec v;
+        for (int i = 0; i < l; i++) v.push(i, i);
+        const LimbList ll = single_list(v, primes_);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        if (ts) PFHE_CUDA(ntt_inverse_mul(plan_, t_cks, *ts, bar(1, 0), ll, lv.modup_fin.p, 1, st));
+        else PFHE_CUDA(ntt_inverse(plan_, t_cks, c2, ll, lv.modup_fin.p, 1, st));
+    }
+    // 2. mod-up: convert + forward NTT, one launch pair per group of digits of equal size
+    for (int d0 = 0; d0 < lv.beta;) {
+        const int ni = lv.digit_size[d0];
+        int d1 = d0;
+        while (d1 < lv.beta && lv.digit_size[d1] == ni) d1++;
+        LimbList ll{};
+        BconvLoad bl{};
+        size_t moff = 0;
+        for (int e = 0; e < d0; e++) moff += (size_t) lv.digit_no[e] * lv.digit_size[e];
+        bl.in_base = t_cks, bl.mat = lv.modup_mat.p + moff, bl.matf = lv.modup_matf.p + 2 * moff;
+        bl.bar = d_bar_.p, bl.size_QP = size_QP_, bl.ni = ni;
+        int kin = 0, cnt = 0;
+        for (int d = d0; d < d1; d++) {
+            const int start = lv.digit_start[d];
+            for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(primes_[start + i]));
+            int jo = 0;
+            for (int j = 0; j < m; j++) {
+                if (j >= start && j < start + ni) continue;
+                const int row = j < l ? j : size_Q_ + (j - l);
+                ll.data[cnt] = ll.src[cnt] = (short) (d * m + j);
+                ll.row[cnt] = (short) row;
+                ll.q[cnt] = primes_[row];
+                bl.in_limb[cnt] = (short) start;
+                bl.mat_row[cnt] = (short) (lv.digit_off[d] - lv.digit_off[d0] + jo);
+                bl.in_big[cnt] = (unsigned char) lv.digit_big[d];
+                cnt++, jo++;
+            }
+        }
+        ll.count = cnt;
+        bl.xbits = kin + ceil_log2(ni);
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        PFHE_CUDA(ntt_forward_bconv(plan_, t_mod_up, ll, bl, nullptr, nullptr, nullptr, st));
+        d0 = d1;
+    }
+    // 3. inner product; the digit's own limbs are read from c2 (or formed as a1*b1)
+    inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts);
+    // 4. inverse NTT of the P limbs fused with n^-1 * phat_i^-1
+    {
+        LimbVec v;
+        for (int k = 0; k < 2; k++)
+            for (int i = 0; i < alpha; i++) v.push(k * m + l + i, size_Q_ + i);
+        ntt_inv_list(cx, cx, single_list(v, primes_), lv.moddown_fin.p, 1, st);
+    }
+    // 5. mod-down: convert P -> q_j, forward NTT, (cx - delta) * P^-1 + addend
+    {
+        LimbList ll{};
+        BconvLoad bl{};
+        EpiArgs ea{};
+        int pbits = 0;
+        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(primes_[size_Q_ + i]));
+        bl.in_base = cx, bl.mat = lv.moddown_mat.p, bl.matf = lv.moddown_matf.p, bl.bar = d_bar_.p;
+        bl.size_QP = size_QP_, bl.ni = alpha, bl.xbits = pbits + ceil_log2(alpha);
+        ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p;
+        int cnt = 0;
+        for (int k = 0; k < 2; k++)
+            for (int j = 0; j < l; j++) {
+                ll.data[cnt] = ll.src[cnt] = (short) (k * l + j);
+                ll.row[cnt] = (short) j;
+                ll.q[cnt] = primes_[j];
+                bl.in_limb[cnt] = (short) (k * m + l);
+                bl.mat_row[cnt] = (short) j;
+                bl.in_big[cnt] = (unsigned char) lv.moddown_big;
+                ea.sub[cnt] = (short) (k * m + j);
+                ea.out[cnt] = (short) (k * l + j);
+                ea.add[cnt] = ts ? (short) k : (short) ((addend && ((add_mask >> k) & 1)) ? k * l + j : -1);
+                cnt++;
+            }
+        ll.count = cnt;
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), st));
+    }
+}
+
 // keyswitch_inplace (reference src/eval_key_switch.cu:95-182): out[2][l][n] = addend + moddown(<modup(c2), evk>)
 void Engine::keyswitch(int l, u64 *out, const u64 *c2, const u64 *const *evk, const u64 *addend, cudaStream_t st) {
-    modup(l, ws_.t_mod_up.p, c2, ws_.t_cks.p, st);
-    inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
-    moddown(l, out, ws_.cx.p, ws_.delta.p, 2, addend, addend ? 3u : 0u, st);
+    keyswitch_fused(l, out, c2, nullptr, evk, addend, addend ? 3u : 0u, st);
 }
 
 // multiply_inplace + relinearize_inplace for CKKS/BGV (reference src/evaluate.cu:345-397,1342-1374)
 void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st) {
-    u64 *d = ws_.tmp.p;
-    tensor_2x2(ct1, ct2, d, l, st);
-    keyswitch(l, out, d + (size_t) 2 * l * n_, rlk, d, st);
+    if (out == ct1 || out == ct2) {
+        // the fused epilogue reads a0, a1, b0, b1 while writing out: keep the operands alive in the workspace
+        const size_t words = (size_t) 2 * l * n_;
+        u64 *keep = ws_.tmp.p;   // [2][l][n] copy of whichever operand aliases the output
+        if (out == ct1) {
+            PFHE_CUDA(cudaMemcpyAsync(keep, ct1, words * 8, cudaMemcpyDeviceToDevice, st));
+            const TensorSrc ts{keep, ct2 == ct1 ? keep : ct2, l};
+            keyswitch_fused(l, out, nullptr, &ts, rlk, nullptr, 0u, st);
+        } else {
+            PFHE_CUDA(cudaMemcpyAsync(keep, ct2, words * 8, cudaMemcpyDeviceToDevice, st));
+            const TensorSrc ts{ct1, keep, l};
+            keyswitch_fused(l, out, nullptr, &ts, rlk, nullptr, 0u, st);
+        }
+        return;
+    }
+    const TensorSrc ts{ct1, ct2, l};
+    keyswitch_fused(l, out, nullptr, &ts, rlk, nullptr, 0u, st);
 }
 
 void Engine::multiply_relin_host_batch(int l, const u64 *const *h1, const u64 *const *h2, u64 *const *hout,
@@ -572,9 +694,7 @@ void Engine::apply_galois(int l, u64 *ct, uint32_t galois_elt, const u64 *const 
     check_launch("k_galois_ntt");
     // ct0 = perm(c0) + ks0, ct1 = 0 + ks1: the "wipe c1" memset of the reference is folded away by
     // pointing poly 1 at a zero addend, i.e. no addend at all.
-    modup(l, ws_.t_mod_up.p, tmp + (size_t) l * n_, ws_.t_cks.p, st);
-    inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, glk, st);
-    moddown(l, ct, ws_.cx.p, ws_.delta.p, 2, tmp, 1u, st);
+    keyswitch_fused(l, ct, tmp + (size_t) l * n_, nullptr, glk, tmp, 1u, st);
 }
 
 // rescale_to_next for CKKS (reference src/evaluate.cu:1376-1427 + divide_and_round_q_last_ntt rns.cu:1160-1184)

@@ -94,6 +94,33 @@ __host__ __device__ constexpr int skew_bits(int i) {   // GF(2)-linear in bits 4
 }
 __host__ __device__ constexpr int skew(int i) { return i ^ skew_bits(i); }
 
+// Fused prologues / epilogues of the key-switch pipeline (engine.cu: Engine::keyswitch_fused) -----------
+// Base conversion folded into the load of the forward column pass: slot s converts the `ni` coefficient-form
+// limbs starting at limb in_limb[s] of in_base with matrix row mat_row[s] (bconv_matmul_*, reference
+// src/rns_bconv.cu:109-210,455-485), so the converted polynomial never goes through memory before its NTT.
+constexpr int FUSE_MAX_IN = 4;
+struct BconvLoad {
+    const u64 *in_base;
+    const u64 *mat;          // [rows][ni] qhat_i mod p_j
+    const double2 *matf;     // [rows][ni][2] FP64 form (see BconvJob::matf)
+    const BarG *bar;         // [64][size_QP] single-word Barrett table
+    int size_QP;
+    int ni;                  // inputs per output (same for every slot of the launch), <= FUSE_MAX_IN
+    int xbits;               // max input-prime bits + ceil(log2 ni)
+    short in_limb[NTT_MAX_LIMBS];
+    short mat_row[NTT_MAX_LIMBS];
+    unsigned char in_big[NTT_MAX_LIMBS];   // per slot: bit i set = input i comes from a modulus >= 2^46
+};
+
+// HMult folded into the key switch: the tensor product d = (a0 b0, a0 b1 + a1 b0, a1 b1) is never stored;
+// d2 is formed in the load of the first inverse pass, d0 / d1 in the epilogue of the last forward pass
+// (tensor_prod_2x2_rns_poly, reference src/polymath.cu:463-498: same residues).
+struct TensorSrc {
+    const u64 *a;            // [2][l][n]
+    const u64 *b;            // [2][l][n]
+    int l;
+};
+
 // ----------------------------------------------------------------------------------------------------
 // element <-> thread mapping of one round
 // ----------------------------------------------------------------------------------------------------
@@ -106,6 +133,7 @@ struct RoundMap {
     static constexpr int GB = NTT_LOG_EPT - R;
     static constexpr int G = 1 << GB;                // independent radix-2^R groups per thread
     static constexpr int T = 1 << P;
+    static constexpr int T_LOG = P;
     static constexpr int C = 1 << GAM;
     static constexpr bool LAST = (RI == Sched<P>::NR - 1);
     // a thread's G groups sit NTT_THREADS apart in the packed (hi, lo, batch) index, i.e. they differ in its
@@ -255,43 +283,36 @@ struct FpArith {
 // in table order.  Row pass: per stage sigma the C rows of the tile are contiguous in the table
 // (C * 2^sigma entries starting at 2^(P1+sigma) + row0 * 2^sigma), stored back to back: offset C * (2^sigma - 1).
 template<class M, bool ROWS, int LOGN>
-__device__ __forceinline__ int tw_index(int u, int hi, int b, int c) {
+__device__ __forceinline__ int tw_index(int u, int hi, int b, int c, int tile) {
     if constexpr (!ROWS) {
-        return (1 << (M::S0 + u)) + ((hi << u) | b);
+        return (1 << (M::S0 + u)) + ((hi << u) | b);          // staged copy of the table head: same positions
     } else {
+        // row pass: every twiddle is used by exactly one thread of the grid, so it is read straight from the table
+        // (kernel-native order: contiguous across the lanes of a warp in the last round)
+        constexpr int P1 = LOGN - M::T_LOG;
         const int sigma = M::S0 + u;
-        const int base = M::C * ((1 << sigma) - 1) + (c << sigma);
+        const int row = (tile << M::GAM) + c;
+        const int base = (1 << (P1 + sigma)) + (row << sigma);
         if constexpr (M::LAST) return base + (b << M::S0) + hi;
         else return base + ((hi << u) | b);
     }
 }
 
-constexpr int NTT_STW_ENTRIES = NTT_TILE;   // upper bound of staged twiddles per tile (C * (2^P - 1) < 2^LOG_TILE)
+constexpr int NTT_STW_ENTRIES = 256;   // column pass: the 2^P1 <= 256 leading table entries are staged per tile
 
-// issue the bulk copies of this tile's twiddles (one thread); completion is signalled on `bar`
-template<int P, bool ROWS, int LOGN>
-__device__ __forceinline__ void stage_twiddles(Tw *stw, const Tw *tw_limb, int tile, uint64_t *bar) {
-    if constexpr (!ROWS) {
-        constexpr uint32_t bytes = (1u << P) * sizeof(Tw);
-        mbar_expect_tx(bar, bytes);
-        tma_load_1d(stw, tw_limb, bytes, bar);
-    } else {
-        constexpr int P1 = LOGN - P;
-        constexpr int C = 1 << (NTT_LOG_TILE - P);
-        constexpr uint32_t total = C * ((1u << P) - 1) * sizeof(Tw);
-        mbar_expect_tx(bar, total);
-#pragma unroll
-        for (int sigma = 0; sigma < P; sigma++) {
-            const size_t src = ((size_t) 1 << (P1 + sigma)) + ((size_t) (tile * C) << sigma);
-            tma_load_1d(stw + C * ((1 << sigma) - 1), tw_limb + src, (uint32_t) (C << sigma) * sizeof(Tw), bar);
-        }
-    }
+// issue the bulk copy of the column-pass twiddles (one thread); completion is signalled on `bar`
+template<int P>
+__device__ __forceinline__ void stage_twiddles(Tw *stw, const Tw *tw_limb, uint64_t *bar) {
+    constexpr uint32_t bytes = (1u << P) * sizeof(Tw);
+    static_assert((1 << P) <= NTT_STW_ENTRIES, "staging area too small");
+    mbar_expect_tx(bar, bytes);
+    tma_load_1d(stw, tw_limb, bytes, bar);
 }
 
 template<class A>
 struct PassCtx {
-    const Tw *tw;               // this tile's twiddles, staged in shared memory (tw_index order)
-    uint64_t *bar;              // mbarrier the staging copies complete on
+    const Tw *tw;               // column pass: twiddles staged in shared memory; row pass: this limb's table
+    uint64_t *bar;              // mbarrier the staging copy completes on (column pass)
     typename A::Consts c;
     int tile;                   // tile index inside the limb (column block resp. row block)
     Tw fin_x, fin_y;            // constants of the last inverse stage
@@ -300,7 +321,7 @@ struct PassCtx {
 // one forward round on the registers of a thread: x[g * 2^R + k]
 template<class A, class M, bool ROWS, int LOGN, int SBASE>
 __device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw *tw,
-                                          const int (&hi)[M::G], const int (&cc)[M::G],
+                                          const int (&hi)[M::G], const int (&cc)[M::G], int tile,
                                           const typename A::Consts &c) {
     constexpr int R = M::R;
 #pragma unroll
@@ -311,7 +332,7 @@ __device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw 
             Tw w[M::G];
 #pragma unroll
             for (int g = 0; g < M::G; g++) {
-                if (g == 0 || !M::SHARE) w[g] = tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g])];
+                if (g == 0 || !M::SHARE) w[g] = ROWS ? __ldg(&tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g], tile)]) : tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g], tile)];
                 else w[g] = w[0];
             }
 #pragma unroll
@@ -331,7 +352,7 @@ __device__ __forceinline__ void fwd_round(typename A::T (&x)[NTT_EPT], const Tw 
 // one inverse round (stages S0+R-1 down to S0).  FINAL marks the round containing global stage 0.
 template<class A, class M, bool ROWS, int LOGN, bool FINAL>
 __device__ __forceinline__ void inv_round(typename A::T (&x)[NTT_EPT], const Tw *tw,
-                                          const int (&hi)[M::G], const int (&cc)[M::G],
+                                          const int (&hi)[M::G], const int (&cc)[M::G], int tile,
                                           const typename A::Consts &c, Tw fin_x, Tw fin_y) {
     constexpr int R = M::R;
 #pragma unroll
@@ -343,7 +364,7 @@ __device__ __forceinline__ void inv_round(typename A::T (&x)[NTT_EPT], const Tw 
             if (!(FINAL && u == 0)) {
 #pragma unroll
                 for (int g = 0; g < M::G; g++) {
-                    if (g == 0 || !M::SHARE) w[g] = tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g])];
+                    if (g == 0 || !M::SHARE) w[g] = ROWS ? __ldg(&tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g], tile)]) : tw[tw_index<M, ROWS, LOGN>(u, hi[g], b, cc[g], tile)];
                     else w[g] = w[0];
                 }
             }
@@ -403,8 +424,8 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
                 if constexpr (RI == 0) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
                 else x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
             }
-        if constexpr (RI == 0) mbar_wait(cx.bar, 0);   // twiddles landed (copies overlapped the gather above)
-        fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, c, cx.c);
+        if constexpr (RI == 0 && !ROWS) mbar_wait(cx.bar, 0);   // staged twiddles landed (overlapped the gather)
+        fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, c, cx.tile, cx.c);
         // scatter
         constexpr bool DIRECT_OUT = (RI == NR - 1) && !ROWS;
         if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
@@ -467,8 +488,8 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
                 if constexpr (DIRECT_IN) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
                 else x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
             }
-        if constexpr (RI == NR - 1) mbar_wait(cx.bar, 0);
-        inv_round<A, M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, c, cx.c, cx.fin_x, cx.fin_y);
+        if constexpr (RI == NR - 1 && !ROWS) mbar_wait(cx.bar, 0);
+        inv_round<A, M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, c, cx.tile, cx.c, cx.fin_x, cx.fin_y);
         if constexpr (RI == 0) {
             // first round in index order = last in time: values leave the pass
 #pragma unroll

@@ -23,6 +23,14 @@ cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbLi
 // forward NTT of `data` (in place, ll.src must equal ll.data) whose row pass ends in the EpiArgs epilogue
 cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st);
 
+// inverse NTT whose input is the limb-wise product a1 * b1 (HMult fused into the key switch)
+cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, const BarG *bar0, const LimbList &ll,
+                            const Tw *fin, int by_slot, cudaStream_t st);
+
+// forward NTT of base-converted inputs (BconvLoad) written to `dst`; optional epilogue (ea) and tensor addend (ts)
+cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
+                              const TensorSrc *ts, const BarG *bar1, cudaStream_t st);
+
 // inverse NTT incl. n^-1; `fin` (optional) = per-slot or per-row {c, itw1*c} pairs with c = n^-1 * scalar
 // (replaces nwt_2d_radix8_backward[_inplace][_scale] and variants, include/ntt.cuh:206-226)
 cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,

@@ -2,6 +2,10 @@
 #include "ntt_api.cuh"
 #include "launch.hpp"
 
+#ifndef NTT_MIN_BLOCKS
+#define NTT_MIN_BLOCKS 4
+#endif
+
 namespace pfhe {
 
 // every kernel picks the arithmetic of its limb (CTA-uniform): FP64 butterflies for q < 2^46, integer otherwise
@@ -15,10 +19,11 @@ namespace pfhe {
         __VA_ARGS__                                                                                       \
     }
 
-// dynamic shared memory of every NTT kernel: [exchange tile | staged twiddles | mbarrier]
-constexpr size_t NTT_DYN_SMEM = NTT_TILE * sizeof(u64) + NTT_STW_ENTRIES * sizeof(Tw) + 16;
+// dynamic shared memory: column passes [exchange tile | staged twiddles | mbarrier], row passes [exchange tile]
+constexpr size_t NTT_SMEM_COLS = NTT_TILE * sizeof(u64) + NTT_STW_ENTRIES * sizeof(Tw) + 16;
+constexpr size_t NTT_SMEM_ROWS = NTT_TILE * sizeof(u64);
 
-#define PFHE_NTT_SMEM(P, ROWS, TABLE)                                                                     \
+#define PFHE_NTT_SMEM_COLS(P, TABLE)                                                                      \
     extern __shared__ __align__(128) unsigned char dyn_smem[];                                            \
     u64 *smem = reinterpret_cast<u64 *>(dyn_smem);                                                        \
     Tw *stw = reinterpret_cast<Tw *>(smem + NTT_TILE);                                                    \
@@ -26,14 +31,22 @@ constexpr size_t NTT_DYN_SMEM = NTT_TILE * sizeof(u64) + NTT_STW_ENTRIES * sizeo
     if (threadIdx.x == 0) mbar_init(bar, 1);                                                              \
     __syncthreads();                                                                                      \
     pdl_launch_dependents();                                                                              \
-    if (threadIdx.x == 0) stage_twiddles<P, ROWS, LOGN>(stw, (TABLE) + ((size_t) row << LOGN), (int) blockIdx.x, bar); \
+    if (threadIdx.x == 0) stage_twiddles<P>(stw, (TABLE) + ((size_t) row << LOGN), bar);                  \
+    pdl_wait();
+
+#define PFHE_NTT_SMEM_ROWS(TABLE)                                                                         \
+    extern __shared__ __align__(128) unsigned char dyn_smem[];                                            \
+    u64 *smem = reinterpret_cast<u64 *>(dyn_smem);                                                        \
+    const Tw *stw = (TABLE) + ((size_t) row << LOGN);                                                     \
+    uint64_t *bar = nullptr;                                                                              \
+    pdl_launch_dependents();                                                                              \
     pdl_wait();
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, NttPlan p) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, NttPlan p) {
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    PFHE_NTT_SMEM(ntt_p1(LOGN), false, p.tw)
+    PFHE_NTT_SMEM_COLS(ntt_p1(LOGN), p.tw)
     const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
     u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
     PFHE_ARITH_DISPATCH(row, {
@@ -45,10 +58,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_cols(u64 *dst, const u64
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows(u64 *data, LimbList ll, NttPlan p) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows(u64 *data, LimbList ll, NttPlan p) {
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    PFHE_NTT_SMEM(ntt_p2(LOGN), true, p.tw)
+    PFHE_NTT_SMEM_ROWS(p.tw)
     u64 *d = data + ((size_t) ll.data[slot] << LOGN);
     PFHE_ARITH_DISPATCH(row, {
         const typename A::Consts c = A::consts(q);
@@ -60,10 +73,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows(u64 *data, LimbList
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows_epi(u64 *data, LimbList ll, NttPlan p, EpiArgs ea) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows_epi(u64 *data, LimbList ll, NttPlan p, EpiArgs ea) {
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    PFHE_NTT_SMEM(ntt_p2(LOGN), true, p.tw)
+    PFHE_NTT_SMEM_ROWS(p.tw)
     const u64 *d = data + ((size_t) ll.data[slot] << LOGN);
     const u64 *sub = ea.sub_base + ((size_t) ea.sub[slot] << LOGN);
     u64 *out = ea.out_base + ((size_t) ea.out[slot] << LOGN);
@@ -85,10 +98,10 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_fwd_rows_epi(u64 *data, Limb
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_rows(u64 *dst, const u64 *src, LimbList ll, NttPlan p) {
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_rows(u64 *dst, const u64 *src, LimbList ll, NttPlan p) {
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    PFHE_NTT_SMEM(ntt_p2(LOGN), true, p.itw)
+    PFHE_NTT_SMEM_ROWS(p.itw)
     const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
     u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
     PFHE_ARITH_DISPATCH(row, {
@@ -100,11 +113,11 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_rows(u64 *dst, const u64
 }
 
 template<int LOGN>
-__global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_cols(u64 *data, LimbList ll, NttPlan p, const Tw *fin,
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_cols(u64 *data, LimbList ll, NttPlan p, const Tw *fin,
                                                               int fin_by_slot) {
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
-    PFHE_NTT_SMEM(ntt_p1(LOGN), false, p.itw)
+    PFHE_NTT_SMEM_COLS(ntt_p1(LOGN), p.itw)
     const int f = fin_by_slot ? slot : row;
     u64 *d = data + ((size_t) ll.data[slot] << LOGN);
     PFHE_ARITH_DISPATCH(row, {
@@ -116,9 +129,184 @@ __global__ void __launch_bounds__(NTT_THREADS, 4) k_inv_cols(u64 *data, LimbList
     })
 }
 
+// ---- fused variants -----------------------------------------------------------------------------------
+// a * b mod q in the representation of arithmetic A (value entering an inverse pass)
+template<class A>
+__device__ __forceinline__ typename A::T mul_in(u64 x, u64 y, const typename A::Consts &c, const BarG &bg, u64 q) {
+    if constexpr (std::is_same<A, FpArith>::value) {
+        return fp::mulmod_v(fp::from_u64(x), fp::from_u64(y), c.q, c.qinv);
+    } else {
+        const Modulus m{q, 0, 0};
+        return mul_mod_g(x, y, bg, m);
+    }
+}
+
+// first inverse pass of HMult+Relin: loads a1 * b1 (the d2 component of the tensor product)
+template<class A, int LOGN>
+__device__ __forceinline__ void inv_rows_mul_body(u64 *smem, const Tw *stw, uint64_t *bar, u64 q, const u64 *a1, const u64 *b1,
+                                                  u64 *d, const BarG bg) {
+    const typename A::Consts c = A::consts(q);
+    PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
+    inverse_pass<A, ntt_p2(LOGN), true, LOGN, false>(
+            smem, cx, [&](size_t i) { return mul_in<A>(a1[i], b1[i], c, bg, q); },
+            [&](size_t i, typename A::T v) { d[i] = A::raw(v); });
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_rows_mul(u64 *dst, TensorSrc ts, const BarG *bar0, LimbList ll,
+                                                                  NttPlan p) {
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    PFHE_NTT_SMEM_ROWS(p.itw)
+    const size_t poly = (size_t) ts.l << LOGN;
+    const u64 *a1 = ts.a + poly + ((size_t) ll.src[slot] << LOGN);
+    const u64 *b1 = ts.b + poly + ((size_t) ll.src[slot] << LOGN);
+    u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
+    const BarG bg = bar0[row];
+    const u64 q = ll.q[slot];
+    if (p.fp_enabled && (q >> fp::MAX_BITS) == 0) inv_rows_mul_body<FpArith, LOGN>(smem, stw, bar, q, a1, b1, d, bg);
+    else inv_rows_mul_body<IntArith, LOGN>(smem, stw, bar, q, a1, b1, d, bg);
+}
+
+// forward column pass whose input is produced by the fast base conversion of `ni` coefficient-form limbs
+template<class A, int LOGN>
+__device__ __forceinline__ void fwd_cols_bconv_body(u64 *smem, const Tw *stw, uint64_t *bar, u64 q, int row, int slot,
+                                                    const u64 *in, u64 *d, const BconvLoad &bl, const Modulus *mod) {
+    const typename A::Consts c = A::consts(q);
+    PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
+    const int ni = bl.ni;
+    const unsigned big = bl.in_big[slot];
+    if constexpr (std::is_same<A, FpArith>::value) {
+        double2 mf[2 * FUSE_MAX_IN];
+#pragma unroll
+        for (int i = 0; i < FUSE_MAX_IN; i++)
+            if (i < ni) {
+                mf[2 * i] = bl.matf[2 * ((size_t) bl.mat_row[slot] * ni + i)];
+                mf[2 * i + 1] = bl.matf[2 * ((size_t) bl.mat_row[slot] * ni + i) + 1];
+            }
+        forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
+                smem, cx,
+                [&](size_t idx) {
+                    double acc = 0.0;
+#pragma unroll
+                    for (int i = 0; i < FUSE_MAX_IN; i++)
+                        if (i < ni) {
+                            const u64 y = in[((size_t) i << LOGN) + idx];
+                            if ((big >> i) & 1) {
+                                const u64 msk = (1ull << fp::SPLIT_BITS) - 1;
+                                acc += fp::mulmod_c(fp::from_u64(y & msk), mf[2 * i].x, mf[2 * i].y, c.q);
+                                acc += fp::mulmod_c(fp::from_u64(y >> fp::SPLIT_BITS), mf[2 * i + 1].x, mf[2 * i + 1].y,
+                                                    c.q);
+                            } else {
+                                acc += fp::mulmod_c(fp::from_u64(y), mf[2 * i].x, mf[2 * i].y, c.q);
+                            }
+                        }
+                    return acc;   // |acc| < 2 ni * 0.63 q, fine for the lazy FP64 butterflies
+                },
+                [&](size_t i, double v) { d[i] = A::raw(v); });
+    } else {
+        u64 mi[FUSE_MAX_IN];
+#pragma unroll
+        for (int i = 0; i < FUSE_MAX_IN; i++)
+            if (i < ni) mi[i] = bl.mat[(size_t) bl.mat_row[slot] * ni + i];
+        const int cls = max(0, bl.xbits - (64 - __clzll((long long) q)));
+        const BarG bg = bl.bar[(size_t) min(cls, 63) * bl.size_QP + row];
+        const Modulus m = mod[row];
+        forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
+                smem, cx,
+                [&](size_t idx) {
+                    Acc128 acc{0, 0};
+#pragma unroll
+                    for (int i = 0; i < FUSE_MAX_IN; i++)
+                        if (i < ni) acc.mac(in[((size_t) i << LOGN) + idx], mi[i]);
+                    return barrett_g(acc.lo, acc.hi, bg, m);
+                },
+                [&](size_t i, u64 v) { d[i] = v; });
+    }
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_cols_bconv(u64 *dst, LimbList ll, NttPlan p, BconvLoad bl) {
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    PFHE_NTT_SMEM_COLS(ntt_p1(LOGN), p.tw)
+    u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
+    const u64 *in = bl.in_base + ((size_t) bl.in_limb[slot] << LOGN);
+    const u64 q = ll.q[slot];
+    if (p.fp_enabled && (q >> fp::MAX_BITS) == 0)
+        fwd_cols_bconv_body<FpArith, LOGN>(smem, stw, bar, q, row, slot, in, d, bl, p.mod);
+    else fwd_cols_bconv_body<IntArith, LOGN>(smem, stw, bar, q, row, slot, in, d, bl, p.mod);
+}
+
+// last forward pass of HMult+Relin: out = (cx - NTT(delta)) * P^-1 + d_k with d_0 = a0 b0, d_1 = a0 b1 + a1 b0
+struct EpiTensorPtrs {
+    const u64 *d, *sub, *a0, *a1, *b0, *b1;
+    u64 *out;
+    int kpoly;
+    Tw k;
+    BarG bg;
+    Modulus m;
+};
+
+template<class A, int LOGN>
+__device__ __forceinline__ void fwd_rows_epi_tensor_body(u64 *smem, const Tw *stw, uint64_t *bar, u64 q,
+                                                         const EpiTensorPtrs &e) {
+    const typename A::Consts c = A::consts(q);
+    PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
+    forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+            smem, cx, [&](size_t i) { return A::from_raw(e.d[i]); },
+            [&](size_t i, typename A::T v) {
+                const u64 t = A::canon_fwd(v, c);
+                const u64 r = mul_shoup(e.sub[i] + q - t, e.k, q);
+                u64 dk;
+                if constexpr (std::is_same<A, FpArith>::value) {
+                    const double x0 = fp::from_u64(e.a0[i]), y0 = fp::from_u64(e.b0[i]);
+                    if (e.kpoly == 0) {
+                        dk = fp::canon(fp::mulmod_v(x0, y0, c.q, c.qinv), c.q);
+                    } else {
+                        const double s = fp::mulmod_v(x0, fp::from_u64(e.b1[i]), c.q, c.qinv) +
+                                         fp::mulmod_v(fp::from_u64(e.a1[i]), y0, c.q, c.qinv);
+                        dk = fp::canon(fp::reduce(s, c.q, c.qinv), c.q);
+                    }
+                } else {
+                    if (e.kpoly == 0) {
+                        dk = mul_mod_g(e.a0[i], e.b0[i], e.bg, e.m);
+                    } else {
+                        Acc128 acc{0, 0};
+                        acc.mac(e.a0[i], e.b1[i]);
+                        acc.mac(e.a1[i], e.b0[i]);
+                        dk = barrett_g(acc.lo, acc.hi, e.bg, e.m);
+                    }
+                }
+                e.out[i] = add_mod(r, dk, q);
+            });
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows_epi_tensor(u64 *data, LimbList ll, NttPlan p, EpiArgs ea,
+                                                                         TensorSrc ts, const BarG *bar1) {
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    PFHE_NTT_SMEM_ROWS(p.tw)
+    const size_t poly = (size_t) ts.l << LOGN;
+    const size_t off = (size_t) row << LOGN;   // limb j of the data level == row j
+    EpiTensorPtrs e;
+    e.d = data + ((size_t) ll.data[slot] << LOGN);
+    e.sub = ea.sub_base + ((size_t) ea.sub[slot] << LOGN);
+    e.out = ea.out_base + ((size_t) ea.out[slot] << LOGN);
+    e.kpoly = ea.add[slot];   // here: which polynomial (0 / 1) this slot produces
+    e.a0 = ts.a + off, e.a1 = ts.a + poly + off, e.b0 = ts.b + off, e.b1 = ts.b + poly + off;
+    e.k = ea.mulc[slot];
+    e.bg = bar1[row];   // growth class 1: sum of two products
+    e.m = p.mod[row];
+    const u64 q = ll.q[slot];
+    if (p.fp_enabled && (q >> fp::MAX_BITS) == 0) fwd_rows_epi_tensor_body<FpArith, LOGN>(smem, stw, bar, q, e);
+    else fwd_rows_epi_tensor_body<IntArith, LOGN>(smem, stw, bar, q, e);
+}
+
 template<class K>
 static void opt_in_smem(K kernel) {
-    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) NTT_DYN_SMEM);
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) NTT_SMEM_COLS);
 }
 template<int LOGN>
 static void opt_in_all() {
@@ -129,6 +317,9 @@ static void opt_in_all() {
     opt_in_smem(k_fwd_rows_epi<LOGN>);
     opt_in_smem(k_inv_rows<LOGN>);
     opt_in_smem(k_inv_cols<LOGN>);
+    opt_in_smem(k_inv_rows_mul<LOGN>);
+    opt_in_smem(k_fwd_cols_bconv<LOGN>);
+    opt_in_smem(k_fwd_rows_epi_tensor<LOGN>);
     done = true;
 }
 
@@ -136,16 +327,16 @@ template<int LOGN>
 static void fwd_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) {
     opt_in_all<LOGN>();
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    launch_pdl(k_fwd_cols<LOGN>, grid, NTT_THREADS, NTT_DYN_SMEM, st, dst, src, ll, p);
-    launch_pdl(k_fwd_rows<LOGN>, grid, NTT_THREADS, NTT_DYN_SMEM, st, dst, ll, p);
+    launch_pdl(k_fwd_cols<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, src, ll, p);
+    launch_pdl(k_fwd_rows<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
 }
 
 template<int LOGN>
 static void fwd_epi_impl(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st) {
     opt_in_all<LOGN>();
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    launch_pdl(k_fwd_cols<LOGN>, grid, NTT_THREADS, NTT_DYN_SMEM, st, data, data, ll, p);
-    launch_pdl(k_fwd_rows_epi<LOGN>, grid, NTT_THREADS, NTT_DYN_SMEM, st, data, ll, p, ea);
+    launch_pdl(k_fwd_cols<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, data, data, ll, p);
+    launch_pdl(k_fwd_rows_epi<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, data, ll, p, ea);
 }
 
 template<int LOGN>
@@ -153,8 +344,8 @@ static void inv_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList 
                      cudaStream_t st) {
     opt_in_all<LOGN>();
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    launch_pdl(k_inv_rows<LOGN>, grid, NTT_THREADS, NTT_DYN_SMEM, st, dst, src, ll, p);
-    launch_pdl(k_inv_cols<LOGN>, grid, NTT_THREADS, NTT_DYN_SMEM, st, dst, ll, p, fin ? fin : p.inv_fin, fin ? by_slot : 0);
+    launch_pdl(k_inv_rows<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, src, ll, p);
+    launch_pdl(k_inv_cols<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, fin ? fin : p.inv_fin, fin ? by_slot : 0);
 }
 
 #define PFHE_DISPATCH_LOGN(FN, ...)                                                                       \
@@ -177,6 +368,40 @@ cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbLi
 cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st) {
     if (ll.count == 0) return cudaSuccess;
     PFHE_DISPATCH_LOGN(fwd_epi_impl, p, data, ll, ea, st)
+    return cudaGetLastError();
+}
+
+template<int LOGN>
+static void inv_mul_impl(const NttPlan &p, u64 *dst, const TensorSrc &ts, const BarG *bar0, const LimbList &ll,
+                         const Tw *fin, int by_slot, cudaStream_t st) {
+    opt_in_all<LOGN>();
+    dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
+    launch_pdl(k_inv_rows_mul<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ts, bar0, ll, p);
+    launch_pdl(k_inv_cols<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, fin ? fin : p.inv_fin, fin ? by_slot : 0);
+}
+
+template<int LOGN>
+static void fwd_bconv_impl(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
+                           const TensorSrc *ts, const BarG *bar1, cudaStream_t st) {
+    opt_in_all<LOGN>();
+    dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
+    launch_pdl(k_fwd_cols_bconv<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, bl);
+    if (!ea) launch_pdl(k_fwd_rows<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
+    else if (!ts) launch_pdl(k_fwd_rows_epi<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p, *ea);
+    else launch_pdl(k_fwd_rows_epi_tensor<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p, *ea, *ts, bar1);
+}
+
+cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, const BarG *bar0, const LimbList &ll,
+                            const Tw *fin, int by_slot, cudaStream_t st) {
+    if (ll.count == 0) return cudaSuccess;
+    PFHE_DISPATCH_LOGN(inv_mul_impl, p, dst, ts, bar0, ll, fin, by_slot, st)
+    return cudaGetLastError();
+}
+
+cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
+                              const TensorSrc *ts, const BarG *bar1, cudaStream_t st) {
+    if (ll.count == 0) return cudaSuccess;
+    PFHE_DISPATCH_LOGN(fwd_bconv_impl, p, dst, ll, bl, ea, ts, bar1, st)
     return cudaGetLastError();
 }
 

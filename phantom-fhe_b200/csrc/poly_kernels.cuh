@@ -251,9 +251,17 @@ __global__ void __launch_bounds__(EW_THREADS) k_bconv(BconvBatch batch, const Mo
 // grid.y = j, 2 coefficients per thread.
 // ---------------------------------------------------------------------------------------------------
 constexpr int KS_MAX_BETA = 64;
+// where the digit's own limbs come from when mod-up no longer copies them into t_mod_up (fused pipeline):
+// c2 in NTT form, or -- HMult fused -- the product a1 * b1 formed on the fly.  alpha = 0: everything is in t.
+struct OwnSrc {
+    const u64 *c2;
+    const u64 *a1, *b1;
+    int alpha;
+};
 __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
-                                                            const Modulus *mod, const BarG *bar, RowArith ra, size_t n,
-                                                            int l, int m, int size_Q, int size_QP, int beta) {
+                                                            const Modulus *mod, const BarG *bar, const BarG *bar0,
+                                                            RowArith ra, OwnSrc os, size_t n, int l, int m, int size_Q,
+                                                            int size_QP, int beta) {
     pdl_launch_dependents();
     pdl_wait();
     const int j = blockIdx.y;
@@ -262,15 +270,32 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
     const BarG bg = bar[row];   // growth class ceil(log2 beta)
     const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const size_t m_n = (size_t) m * n, qp_n = (size_t) size_QP * n;
+    const int own_d = (os.alpha > 0 && j < l) ? j / os.alpha : -1;   // digit whose own limb this is
     if (ra.fp(row)) {   // CTA-uniform: every term is reduced on the FP64 pipe, the small residues are summed
         const double q = ra.fpc[row].x, qi = ra.fpc[row].y;
         double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+        double ox = 0.0, oy = 0.0;
+        if (own_d >= 0) {
+            if (os.c2) {
+                const ulonglong2 v = ld2(os.c2 + (size_t) j * n + x);
+                ox = fp::from_u64(v.x), oy = fp::from_u64(v.y);
+            } else {
+                const ulonglong2 va = ld2(os.a1 + (size_t) j * n + x), vb = ld2(os.b1 + (size_t) j * n + x);
+                ox = fp::mulmod_v(fp::from_u64(va.x), fp::from_u64(vb.x), q, qi);
+                oy = fp::mulmod_v(fp::from_u64(va.y), fp::from_u64(vb.y), q, qi);
+            }
+        }
 #pragma unroll 4
         for (int d = 0; d < beta; d++) {
             const u64 *k0 = evk[d] + (size_t) row * n + x;
-            const ulonglong2 v = ld2(t + (size_t) d * m_n + (size_t) j * n + x);
             const ulonglong2 e0 = ld2_nc(k0), e1 = ld2_nc(k0 + qp_n);
-            const double vx = fp::from_u64(v.x), vy = fp::from_u64(v.y);
+            double vx, vy;
+            if (d == own_d) {
+                vx = ox, vy = oy;
+            } else {
+                const ulonglong2 v = ld2(t + (size_t) d * m_n + (size_t) j * n + x);
+                vx = fp::from_u64(v.x), vy = fp::from_u64(v.y);
+            }
             s00 += fp::mulmod_v(vx, fp::from_u64(e0.x), q, qi);
             s01 += fp::mulmod_v(vy, fp::from_u64(e0.y), q, qi);
             s10 += fp::mulmod_v(vx, fp::from_u64(e1.x), q, qi);
@@ -281,10 +306,20 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
         return;
     }
     Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+    ulonglong2 own = make_ulonglong2(0, 0);
+    if (own_d >= 0) {
+        if (os.c2) {
+            own = ld2(os.c2 + (size_t) j * n + x);
+        } else {
+            const ulonglong2 va = ld2(os.a1 + (size_t) j * n + x), vb = ld2(os.b1 + (size_t) j * n + x);
+            const BarG b0 = bar0[row];
+            own = make_ulonglong2(mul_mod_g(va.x, vb.x, b0, md), mul_mod_g(va.y, vb.y, b0, md));
+        }
+    }
 #pragma unroll 4
     for (int d = 0; d < beta; d++) {
         const u64 *k0 = evk[d] + (size_t) row * n + x;
-        const ulonglong2 v = ld2(t + (size_t) d * m_n + (size_t) j * n + x);
+        const ulonglong2 v = d == own_d ? own : ld2(t + (size_t) d * m_n + (size_t) j * n + x);
         const ulonglong2 e0 = ld2_nc(k0), e1 = ld2_nc(k0 + qp_n);
         a00.mac(v.x, e0.x);
         a01.mac(v.y, e0.y);

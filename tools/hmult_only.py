@@ -25,7 +25,7 @@ st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 work = ca.data.clone()
 torch.cuda.synchronize()
 for _ in range(reps):
-    pf.check(pf.lib.pfhe_multiply_and_relin_inplace(ctx._h, 1, work.data_ptr(), cb.data.data_ptr(),
-                                                    rlk.public_keys_ptr(), st))
+    pf.check(pf.lib.pfhe_multiply_and_relin(ctx._h, 1, ca.data.data_ptr(), cb.data.data_ptr(), work.data_ptr(),
+                                            rlk.public_keys_ptr(), st))
 torch.cuda.synchronize()
 print("ok")
