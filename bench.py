@@ -59,7 +59,7 @@ class ClockSampler:
              "clocks_event_reasons.sw_power_cap")
         try:
             self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
@@ -154,8 +154,8 @@ def run_reference(args, ps, a, b, rank, world):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
-    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--steps", type=int, default=400)
+    ap.add_argument("--warmup", type=int, default=10)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
@@ -254,13 +254,12 @@ def main():
         done += chunk
     launches = ctx.launch_count() - launches0
     dev_ms = max_over_ranks(total_ms)
-    clocks = sampler.stop() if rank == 0 else None
 
     # ---- end to end from pinned host memory ---------------------------------------------------------------
     pin_a = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in a]
     pin_b = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in b]
     pin_o = [torch.empty((2, l, n), dtype=torch.int64).pin_memory() for _ in range(N_PAIRS)]
-    e2e_steps = args.steps
+    e2e_steps = min(args.steps, 100)
     PtrArr = ctypes.c_void_p * e2e_steps
     pa = PtrArr(*[pin_a[i % N_PAIRS].data_ptr() for i in range(e2e_steps)])
     pb = PtrArr(*[pin_b[i % N_PAIRS].data_ptr() for i in range(e2e_steps)])
@@ -275,6 +274,7 @@ def main():
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     wall_ms = (time.perf_counter() - t0) * 1e3
+    clocks = sampler.stop() if rank == 0 else None
 
     # ---- roofline of the dominant kernel: forward NTT at the mod-up shape (64 limb-NTTs per launch pair) -------
     roof = None

@@ -397,9 +397,32 @@ __device__ __forceinline__ size_t gl_index(int e, int c, int tile) {
 }
 
 // ----------------------------------------------------------------------------------------------------
-// pass drivers.  load(coeff_index) -> A::T is the value entering the pass, store(coeff_index, A::T) the
-// value leaving it (the kernels decide about raw / canonical representation and fused epilogues).
+// pass drivers.  Values enter through load.gather(idx[8], x[8]) and leave through store.scatter(idx[8], x[8]):
+// the functor sees all eight coefficient indices of a thread at once so that it can issue every global load
+// before the first use (memory-level parallelism; a per-element callback with data-dependent work in between
+// serialised the loads -- profiles/r1_hmult_full.md, long_scoreboard).  per_elem() adapts a simple lambda.
 // ----------------------------------------------------------------------------------------------------
+template<class T, class F>
+struct PerElemLoad {
+    F f;
+    __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], T (&x)[NTT_EPT]) const {
+#pragma unroll
+        for (int k = 0; k < NTT_EPT; k++) x[k] = f(idx[k]);
+    }
+};
+template<class T, class F>
+struct PerElemStore {
+    F f;
+    __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const T (&x)[NTT_EPT]) const {
+#pragma unroll
+        for (int k = 0; k < NTT_EPT; k++) f(idx[k], x[k]);
+    }
+};
+template<class T, class F>
+__device__ __forceinline__ PerElemLoad<T, F> per_elem_load(F f) { return PerElemLoad<T, F>{f}; }
+template<class T, class F>
+__device__ __forceinline__ PerElemStore<T, F> per_elem_store(F f) { return PerElemStore<T, F>{f}; }
+
 template<class A, int P, bool ROWS, int LOGN, int SBASE, class Load, class Store>
 __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Load load, Store store) {
     constexpr int NR = Sched<P>::NR;
@@ -416,28 +439,40 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
             s0[g] = M::sidx0(hi[g], lo[g], c[g]);
         }
         // gather
+        if constexpr (RI == 0) {
+            size_t gi[NTT_EPT];
 #pragma unroll
-        for (int g = 0; g < M::G; g++)
+            for (int g = 0; g < M::G; g++)
 #pragma unroll
-            for (int k = 0; k < (1 << M::R); k++) {
-                const int e = M::elem(hi[g], k, lo[g]);
-                if constexpr (RI == 0) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
-                else x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
-            }
+                for (int k = 0; k < (1 << M::R); k++)
+                    gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
+            load.gather(gi, x);
+        } else {
+#pragma unroll
+            for (int g = 0; g < M::G; g++)
+#pragma unroll
+                for (int k = 0; k < (1 << M::R); k++) x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
+        }
         if constexpr (RI == 0 && !ROWS) mbar_wait(cx.bar, 0);   // staged twiddles landed (overlapped the gather)
         fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, c, cx.tile, cx.c);
         // scatter
         constexpr bool DIRECT_OUT = (RI == NR - 1) && !ROWS;
         if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
+        if constexpr (DIRECT_OUT) {
+            size_t gi[NTT_EPT];
 #pragma unroll
-        for (int g = 0; g < M::G; g++)
+            for (int g = 0; g < M::G; g++)
 #pragma unroll
-            for (int k = 0; k < (1 << M::R); k++) {
-                const int e = M::elem(hi[g], k, lo[g]);
-                if constexpr (DIRECT_OUT) store(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile), x[(g << M::R) + k]);
-                else smem[s0[g] ^ M::kc(k)] = A::raw(x[(g << M::R) + k]);
-            }
-        if constexpr (!DIRECT_OUT) __syncthreads();
+                for (int k = 0; k < (1 << M::R); k++)
+                    gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
+            store.scatter(gi, x);
+        } else {
+#pragma unroll
+            for (int g = 0; g < M::G; g++)
+#pragma unroll
+                for (int k = 0; k < (1 << M::R); k++) smem[s0[g] ^ M::kc(k)] = A::raw(x[(g << M::R) + k]);
+            __syncthreads();
+        }
     };
 
     run_round(std::integral_constant<int, 0>{});
@@ -449,8 +484,13 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
         // the tile is contiguous in global memory: flat, fully coalesced copy-out
         const size_t base = ((size_t) cx.tile << NTT_LOG_TILE) + tid;
         const int st = skew(tid);   // i * NTT_THREADS only touches bits >= 8: the swizzle term is per thread
+        size_t gi[NTT_EPT];
 #pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) store(base + i * NTT_THREADS, A::from_raw(smem[st + i * NTT_THREADS]));
+        for (int i = 0; i < NTT_EPT; i++) {
+            gi[i] = base + i * NTT_THREADS;
+            x[i] = A::from_raw(smem[st + i * NTT_THREADS]);
+        }
+        store.scatter(gi, x);
     }
 }
 
@@ -465,8 +505,12 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
         // flat coalesced copy-in, the first inverse round then reads its contiguous elements from smem
         const size_t base = ((size_t) cx.tile << NTT_LOG_TILE) + tid;
         const int st = skew(tid);
+        size_t gi[NTT_EPT];
 #pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) smem[st + i * NTT_THREADS] = A::raw(load(base + i * NTT_THREADS));
+        for (int i = 0; i < NTT_EPT; i++) gi[i] = base + i * NTT_THREADS;
+        load.gather(gi, x);
+#pragma unroll
+        for (int i = 0; i < NTT_EPT; i++) smem[st + i * NTT_THREADS] = A::raw(x[i]);
         __syncthreads();
     }
 
@@ -480,25 +524,31 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
             s0[g] = M::sidx0(hi[g], lo[g], c[g]);
         }
         constexpr bool DIRECT_IN = (RI == NR - 1) && !ROWS;
+        if constexpr (DIRECT_IN) {
+            size_t gi[NTT_EPT];
 #pragma unroll
-        for (int g = 0; g < M::G; g++)
+            for (int g = 0; g < M::G; g++)
 #pragma unroll
-            for (int k = 0; k < (1 << M::R); k++) {
-                const int e = M::elem(hi[g], k, lo[g]);
-                if constexpr (DIRECT_IN) x[(g << M::R) + k] = load(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile));
-                else x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
-            }
+                for (int k = 0; k < (1 << M::R); k++)
+                    gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
+            load.gather(gi, x);
+        } else {
+#pragma unroll
+            for (int g = 0; g < M::G; g++)
+#pragma unroll
+                for (int k = 0; k < (1 << M::R); k++) x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
+        }
         if constexpr (RI == NR - 1 && !ROWS) mbar_wait(cx.bar, 0);
         inv_round<A, M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, c, cx.tile, cx.c, cx.fin_x, cx.fin_y);
         if constexpr (RI == 0) {
             // first round in index order = last in time: values leave the pass
+            size_t gi[NTT_EPT];
 #pragma unroll
             for (int g = 0; g < M::G; g++)
 #pragma unroll
-                for (int k = 0; k < (1 << M::R); k++) {
-                    const int e = M::elem(hi[g], k, lo[g]);
-                    store(gl_index<P, ROWS, LOGN>(e, c[g], cx.tile), x[(g << M::R) + k]);
-                }
+                for (int k = 0; k < (1 << M::R); k++)
+                    gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
+            store.scatter(gi, x);
         } else {
             if constexpr (!DIRECT_IN) __syncthreads();
 #pragma unroll

@@ -42,6 +42,32 @@ constexpr size_t NTT_SMEM_ROWS = NTT_TILE * sizeof(u64);
     pdl_launch_dependents();                                                                              \
     pdl_wait();
 
+// epilogue of the fused forward row pass, all operand loads of a thread's eight outputs issued up front
+template<class A>
+struct EpiStore {
+    const u64 *sub, *add;
+    u64 *out;
+    Tw k;
+    typename A::Consts c;
+    u64 q;
+    __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const typename A::T (&x)[NTT_EPT]) const {
+        u64 s[NTT_EPT], a[NTT_EPT];
+#pragma unroll
+        for (int i = 0; i < NTT_EPT; i++) s[i] = sub[idx[i]];
+        if (add) {
+#pragma unroll
+            for (int i = 0; i < NTT_EPT; i++) a[i] = add[idx[i]];
+        }
+#pragma unroll
+        for (int i = 0; i < NTT_EPT; i++) {
+            const u64 t = A::canon_fwd(x[i], c);
+            u64 r = mul_shoup(s[i] + q - t, k, q);
+            if (add) r = add_mod(r, a[i], q);
+            out[idx[i]] = r;
+        }
+    }
+};
+
 template<int LOGN>
 __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_cols(u64 *dst, const u64 *src, LimbList ll, NttPlan p) {
     const int slot = blockIdx.y;
@@ -53,7 +79,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_cols(u64 *d
         const typename A::Consts c = A::consts(q);
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
         forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
-                smem, cx, [&](size_t i) { return A::load(s[i], c); }, [&](size_t i, typename A::T v) { d[i] = A::raw(v); });
+                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::load(s[i], c); }),
+                per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::raw(v); }));
     })
 }
 
@@ -67,8 +94,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows(u64 *d
         const typename A::Consts c = A::consts(q);
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
         forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
-                smem, cx, [&](size_t i) { return A::from_raw(d[i]); },
-                [&](size_t i, typename A::T v) { d[i] = A::canon_fwd(v, c); });
+                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(d[i]); }),
+                per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::canon_fwd(v, c); }));
     })
 }
 
@@ -87,13 +114,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows_epi(u6
         const typename A::Consts c = A::consts(q);
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
         forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
-                smem, cx, [&](size_t i) { return A::from_raw(d[i]); },
-                [&](size_t i, typename A::T v) {
-                    const u64 t = A::canon_fwd(v, c);
-                    u64 r = mul_shoup(sub[i] + q - t, k, q);
-                    if (add) r = add_mod(r, add[i], q);
-                    out[i] = r;
-                });
+                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(d[i]); }),
+                EpiStore<A>{sub, add, out, k, c, q});
     })
 }
 
@@ -108,7 +130,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_rows(u64 *d
         const typename A::Consts c = A::consts(q);
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
         inverse_pass<A, ntt_p2(LOGN), true, LOGN, false>(
-                smem, cx, [&](size_t i) { return A::load(s[i], c); }, [&](size_t i, typename A::T v) { d[i] = A::raw(v); });
+                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::load(s[i], c); }),
+                per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::raw(v); }));
     })
 }
 
@@ -124,8 +147,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_cols(u64 *d
         const typename A::Consts c = A::consts(q);
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, fin[2 * f], fin[2 * f + 1]};
         inverse_pass<A, ntt_p1(LOGN), false, LOGN, true>(
-                smem, cx, [&](size_t i) { return A::from_raw(d[i]); },
-                [&](size_t i, typename A::T v) { d[i] = A::canon_inv(v, c); });
+                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(d[i]); }),
+                per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::canon_inv(v, c); }));
     })
 }
 
@@ -141,6 +164,21 @@ __device__ __forceinline__ typename A::T mul_in(u64 x, u64 y, const typename A::
     }
 }
 
+template<class A>
+struct MulLoad {
+    const u64 *a1, *b1;
+    typename A::Consts c;
+    BarG bg;
+    u64 q;
+    __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], typename A::T (&x)[NTT_EPT]) const {
+        u64 u[NTT_EPT], v[NTT_EPT];
+#pragma unroll
+        for (int i = 0; i < NTT_EPT; i++) u[i] = a1[idx[i]], v[i] = b1[idx[i]];
+#pragma unroll
+        for (int i = 0; i < NTT_EPT; i++) x[i] = mul_in<A>(u[i], v[i], c, bg, q);
+    }
+};
+
 // first inverse pass of HMult+Relin: loads a1 * b1 (the d2 component of the tensor product)
 template<class A, int LOGN>
 __device__ __forceinline__ void inv_rows_mul_body(u64 *smem, const Tw *stw, uint64_t *bar, u64 q, const u64 *a1, const u64 *b1,
@@ -148,8 +186,8 @@ __device__ __forceinline__ void inv_rows_mul_body(u64 *smem, const Tw *stw, uint
     const typename A::Consts c = A::consts(q);
     PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
     inverse_pass<A, ntt_p2(LOGN), true, LOGN, false>(
-            smem, cx, [&](size_t i) { return mul_in<A>(a1[i], b1[i], c, bg, q); },
-            [&](size_t i, typename A::T v) { d[i] = A::raw(v); });
+            smem, cx, MulLoad<A>{a1, b1, c, bg, q},
+            per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::raw(v); }));
 }
 
 template<int LOGN>
@@ -168,6 +206,66 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_rows_mul(u6
     else inv_rows_mul_body<IntArith, LOGN>(smem, stw, bar, q, a1, b1, d, bg);
 }
 
+// base conversion as the gather of a column pass: inputs outer, elements inner, so the eight loads of one input
+// limb are in flight together and the uniform "split this input" branch sits outside the element loop
+template<int LOGN>
+struct BconvGatherFp {
+    const u64 *in;
+    const double2 *mf;   // [ni][2]
+    int ni;
+    unsigned big;
+    double q;
+    __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], double (&x)[NTT_EPT]) const {
+#pragma unroll
+        for (int k = 0; k < NTT_EPT; k++) x[k] = 0.0;
+#pragma unroll
+        for (int i = 0; i < FUSE_MAX_IN; i++) {
+            if (i < ni) {
+                u64 y[NTT_EPT];
+#pragma unroll
+                for (int k = 0; k < NTT_EPT; k++) y[k] = in[((size_t) i << LOGN) + idx[k]];
+                const double2 m0 = mf[2 * i], m1 = mf[2 * i + 1];
+                if ((big >> i) & 1) {
+                    const u64 msk = (1ull << fp::SPLIT_BITS) - 1;
+#pragma unroll
+                    for (int k = 0; k < NTT_EPT; k++) {
+                        x[k] += fp::mulmod_c(fp::from_u64(y[k] & msk), m0.x, m0.y, q);
+                        x[k] += fp::mulmod_c(fp::from_u64(y[k] >> fp::SPLIT_BITS), m1.x, m1.y, q);
+                    }
+                } else {
+#pragma unroll
+                    for (int k = 0; k < NTT_EPT; k++) x[k] += fp::mulmod_c(fp::from_u64(y[k]), m0.x, m0.y, q);
+                }
+            }
+        }
+    }
+};
+template<int LOGN>
+struct BconvGatherInt {
+    const u64 *in;
+    const u64 *mi;       // [ni]
+    int ni;
+    BarG bg;
+    Modulus m;
+    __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], u64 (&x)[NTT_EPT]) const {
+        Acc128 acc[NTT_EPT];
+#pragma unroll
+        for (int k = 0; k < NTT_EPT; k++) acc[k] = Acc128{0, 0};
+#pragma unroll
+        for (int i = 0; i < FUSE_MAX_IN; i++) {
+            if (i < ni) {
+                u64 y[NTT_EPT];
+#pragma unroll
+                for (int k = 0; k < NTT_EPT; k++) y[k] = in[((size_t) i << LOGN) + idx[k]];
+#pragma unroll
+                for (int k = 0; k < NTT_EPT; k++) acc[k].mac(y[k], mi[i]);
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < NTT_EPT; k++) x[k] = barrett_g(acc[k].lo, acc[k].hi, bg, m);
+    }
+};
+
 // forward column pass whose input is produced by the fast base conversion of `ni` coefficient-form limbs
 template<class A, int LOGN>
 __device__ __forceinline__ void fwd_cols_bconv_body(u64 *smem, const Tw *stw, uint64_t *bar, u64 q, int row, int slot,
@@ -185,25 +283,8 @@ __device__ __forceinline__ void fwd_cols_bconv_body(u64 *smem, const Tw *stw, ui
                 mf[2 * i + 1] = bl.matf[2 * ((size_t) bl.mat_row[slot] * ni + i) + 1];
             }
         forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
-                smem, cx,
-                [&](size_t idx) {
-                    double acc = 0.0;
-#pragma unroll
-                    for (int i = 0; i < FUSE_MAX_IN; i++)
-                        if (i < ni) {
-                            const u64 y = in[((size_t) i << LOGN) + idx];
-                            if ((big >> i) & 1) {
-                                const u64 msk = (1ull << fp::SPLIT_BITS) - 1;
-                                acc += fp::mulmod_c(fp::from_u64(y & msk), mf[2 * i].x, mf[2 * i].y, c.q);
-                                acc += fp::mulmod_c(fp::from_u64(y >> fp::SPLIT_BITS), mf[2 * i + 1].x, mf[2 * i + 1].y,
-                                                    c.q);
-                            } else {
-                                acc += fp::mulmod_c(fp::from_u64(y), mf[2 * i].x, mf[2 * i].y, c.q);
-                            }
-                        }
-                    return acc;   // |acc| < 2 ni * 0.63 q, fine for the lazy FP64 butterflies
-                },
-                [&](size_t i, double v) { d[i] = A::raw(v); });
+                smem, cx, BconvGatherFp<LOGN>{in, mf, ni, big, c.q},
+                per_elem_store<double>([&](size_t i, double v) { d[i] = A::raw(v); }));
     } else {
         u64 mi[FUSE_MAX_IN];
 #pragma unroll
@@ -213,15 +294,8 @@ __device__ __forceinline__ void fwd_cols_bconv_body(u64 *smem, const Tw *stw, ui
         const BarG bg = bl.bar[(size_t) min(cls, 63) * bl.size_QP + row];
         const Modulus m = mod[row];
         forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
-                smem, cx,
-                [&](size_t idx) {
-                    Acc128 acc{0, 0};
-#pragma unroll
-                    for (int i = 0; i < FUSE_MAX_IN; i++)
-                        if (i < ni) acc.mac(in[((size_t) i << LOGN) + idx], mi[i]);
-                    return barrett_g(acc.lo, acc.hi, bg, m);
-                },
-                [&](size_t i, u64 v) { d[i] = v; });
+                smem, cx, BconvGatherInt<LOGN>{in, mi, ni, bg, m},
+                per_elem_store<u64>([&](size_t i, u64 v) { d[i] = v; }));
     }
 }
 
@@ -248,38 +322,58 @@ struct EpiTensorPtrs {
     Modulus m;
 };
 
+template<class A>
+struct EpiTensorStore {
+    EpiTensorPtrs e;
+    typename A::Consts c;
+    u64 q;
+    __device__ __forceinline__ u64 dk0(u64 x0, u64 y0) const {
+        if constexpr (std::is_same<A, FpArith>::value)
+            return fp::canon(fp::mulmod_v(fp::from_u64(x0), fp::from_u64(y0), c.q, c.qinv), c.q);
+        else return mul_mod_g(x0, y0, e.bg, e.m);
+    }
+    __device__ __forceinline__ u64 dk1(u64 x0, u64 x1, u64 y0, u64 y1) const {
+        if constexpr (std::is_same<A, FpArith>::value) {
+            const double s = fp::mulmod_v(fp::from_u64(x0), fp::from_u64(y1), c.q, c.qinv) +
+                             fp::mulmod_v(fp::from_u64(x1), fp::from_u64(y0), c.q, c.qinv);
+            return fp::canon(fp::reduce(s, c.q, c.qinv), c.q);
+        } else {
+            Acc128 acc{0, 0};
+            acc.mac(x0, y1);
+            acc.mac(x1, y0);
+            return barrett_g(acc.lo, acc.hi, e.bg, e.m);
+        }
+    }
+    // two half-batches of four outputs: all operand loads of a half are issued before the arithmetic
+    __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const typename A::T (&x)[NTT_EPT]) const {
+#pragma unroll
+        for (int h = 0; h < NTT_EPT; h += 4) {
+            u64 s[4], x0[4], y0[4], x1[4], y1[4];
+#pragma unroll
+            for (int i = 0; i < 4; i++) s[i] = e.sub[idx[h + i]], x0[i] = e.a0[idx[h + i]], y0[i] = e.b0[idx[h + i]];
+            if (e.kpoly != 0) {
+#pragma unroll
+                for (int i = 0; i < 4; i++) x1[i] = e.a1[idx[h + i]], y1[i] = e.b1[idx[h + i]];
+            }
+#pragma unroll
+            for (int i = 0; i < 4; i++) {
+                const u64 t = A::canon_fwd(x[h + i], c);
+                const u64 r = mul_shoup(s[i] + q - t, e.k, q);
+                const u64 dk = e.kpoly == 0 ? dk0(x0[i], y0[i]) : dk1(x0[i], x1[i], y0[i], y1[i]);
+                e.out[idx[h + i]] = add_mod(r, dk, q);
+            }
+        }
+    }
+};
+
 template<class A, int LOGN>
 __device__ __forceinline__ void fwd_rows_epi_tensor_body(u64 *smem, const Tw *stw, uint64_t *bar, u64 q,
                                                          const EpiTensorPtrs &e) {
     const typename A::Consts c = A::consts(q);
     PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
     forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
-            smem, cx, [&](size_t i) { return A::from_raw(e.d[i]); },
-            [&](size_t i, typename A::T v) {
-                const u64 t = A::canon_fwd(v, c);
-                const u64 r = mul_shoup(e.sub[i] + q - t, e.k, q);
-                u64 dk;
-                if constexpr (std::is_same<A, FpArith>::value) {
-                    const double x0 = fp::from_u64(e.a0[i]), y0 = fp::from_u64(e.b0[i]);
-                    if (e.kpoly == 0) {
-                        dk = fp::canon(fp::mulmod_v(x0, y0, c.q, c.qinv), c.q);
-                    } else {
-                        const double s = fp::mulmod_v(x0, fp::from_u64(e.b1[i]), c.q, c.qinv) +
-                                         fp::mulmod_v(fp::from_u64(e.a1[i]), y0, c.q, c.qinv);
-                        dk = fp::canon(fp::reduce(s, c.q, c.qinv), c.q);
-                    }
-                } else {
-                    if (e.kpoly == 0) {
-                        dk = mul_mod_g(e.a0[i], e.b0[i], e.bg, e.m);
-                    } else {
-                        Acc128 acc{0, 0};
-                        acc.mac(e.a0[i], e.b1[i]);
-                        acc.mac(e.a1[i], e.b0[i]);
-                        dk = barrett_g(acc.lo, acc.hi, e.bg, e.m);
-                    }
-                }
-                e.out[i] = add_mod(r, dk, q);
-            });
+            smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(e.d[i]); }),
+            EpiTensorStore<A>{e, c, q});
 }
 
 template<int LOGN>

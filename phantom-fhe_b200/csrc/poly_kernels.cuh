@@ -271,60 +271,76 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
     const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const size_t m_n = (size_t) m * n, qp_n = (size_t) size_QP * n;
     const int own_d = (os.alpha > 0 && j < l) ? j / os.alpha : -1;   // digit whose own limb this is
+    // own-digit operand (fused pipeline): from c2, or a1 * b1; otherwise unused
+    ulonglong2 own = make_ulonglong2(0, 0), ownb = make_ulonglong2(0, 0);
+    if (own_d >= 0) {
+        if (os.c2) own = ld2(os.c2 + (size_t) j * n + x);
+        else own = ld2(os.a1 + (size_t) j * n + x), ownb = ld2(os.b1 + (size_t) j * n + x);
+    }
+    const u64 *tj = t + (size_t) j * n + x;
+    const size_t krow = (size_t) row * n + x;
+    constexpr int CH = 4;   // digits per batch: 12 independent 16-byte loads in flight per thread
     if (ra.fp(row)) {   // CTA-uniform: every term is reduced on the FP64 pipe, the small residues are summed
         const double q = ra.fpc[row].x, qi = ra.fpc[row].y;
-        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-        double ox = 0.0, oy = 0.0;
-        if (own_d >= 0) {
-            if (os.c2) {
-                const ulonglong2 v = ld2(os.c2 + (size_t) j * n + x);
-                ox = fp::from_u64(v.x), oy = fp::from_u64(v.y);
-            } else {
-                const ulonglong2 va = ld2(os.a1 + (size_t) j * n + x), vb = ld2(os.b1 + (size_t) j * n + x);
-                ox = fp::mulmod_v(fp::from_u64(va.x), fp::from_u64(vb.x), q, qi);
-                oy = fp::mulmod_v(fp::from_u64(va.y), fp::from_u64(vb.y), q, qi);
-            }
+        double ox = fp::from_u64(own.x), oy = fp::from_u64(own.y);
+        if (own_d >= 0 && !os.c2) {
+            ox = fp::mulmod_v(ox, fp::from_u64(ownb.x), q, qi);
+            oy = fp::mulmod_v(oy, fp::from_u64(ownb.y), q, qi);
         }
-#pragma unroll 4
-        for (int d = 0; d < beta; d++) {
-            const u64 *k0 = evk[d] + (size_t) row * n + x;
-            const ulonglong2 e0 = ld2_nc(k0), e1 = ld2_nc(k0 + qp_n);
-            double vx, vy;
-            if (d == own_d) {
-                vx = ox, vy = oy;
-            } else {
-                const ulonglong2 v = ld2(t + (size_t) d * m_n + (size_t) j * n + x);
-                vx = fp::from_u64(v.x), vy = fp::from_u64(v.y);
+        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
+        for (int d0 = 0; d0 < beta; d0 += CH) {
+            ulonglong2 v[CH], e0[CH], e1[CH];
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int d = min(d0 + c, beta - 1);   // clamp: tail lanes re-read the last digit, masked below
+                const u64 *k0 = evk[d] + krow;
+                v[c] = ld2(tj + (size_t) d * m_n);
+                e0[c] = ld2_nc(k0);
+                e1[c] = ld2_nc(k0 + qp_n);
             }
-            s00 += fp::mulmod_v(vx, fp::from_u64(e0.x), q, qi);
-            s01 += fp::mulmod_v(vy, fp::from_u64(e0.y), q, qi);
-            s10 += fp::mulmod_v(vx, fp::from_u64(e1.x), q, qi);
-            s11 += fp::mulmod_v(vy, fp::from_u64(e1.y), q, qi);
+#pragma unroll
+            for (int c = 0; c < CH; c++) {
+                const int d = d0 + c;
+                if (d < beta) {
+                    const double vx = d == own_d ? ox : fp::from_u64(v[c].x);
+                    const double vy = d == own_d ? oy : fp::from_u64(v[c].y);
+                    s00 += fp::mulmod_v(vx, fp::from_u64(e0[c].x), q, qi);
+                    s01 += fp::mulmod_v(vy, fp::from_u64(e0[c].y), q, qi);
+                    s10 += fp::mulmod_v(vx, fp::from_u64(e1[c].x), q, qi);
+                    s11 += fp::mulmod_v(vy, fp::from_u64(e1[c].y), q, qi);
+                }
+            }
         }
         st2(cx + (size_t) j * n + x, fp::canon(fp::reduce(s00, q, qi), q), fp::canon(fp::reduce(s01, q, qi), q));
         st2(cx + m_n + (size_t) j * n + x, fp::canon(fp::reduce(s10, q, qi), q), fp::canon(fp::reduce(s11, q, qi), q));
         return;
     }
-    Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
-    ulonglong2 own = make_ulonglong2(0, 0);
-    if (own_d >= 0) {
-        if (os.c2) {
-            own = ld2(os.c2 + (size_t) j * n + x);
-        } else {
-            const ulonglong2 va = ld2(os.a1 + (size_t) j * n + x), vb = ld2(os.b1 + (size_t) j * n + x);
-            const BarG b0 = bar0[row];
-            own = make_ulonglong2(mul_mod_g(va.x, vb.x, b0, md), mul_mod_g(va.y, vb.y, b0, md));
-        }
+    if (own_d >= 0 && !os.c2) {
+        const BarG b0 = bar0[row];
+        own = make_ulonglong2(mul_mod_g(own.x, ownb.x, b0, md), mul_mod_g(own.y, ownb.y, b0, md));
     }
-#pragma unroll 4
-    for (int d = 0; d < beta; d++) {
-        const u64 *k0 = evk[d] + (size_t) row * n + x;
-        const ulonglong2 v = d == own_d ? own : ld2(t + (size_t) d * m_n + (size_t) j * n + x);
-        const ulonglong2 e0 = ld2_nc(k0), e1 = ld2_nc(k0 + qp_n);
-        a00.mac(v.x, e0.x);
-        a01.mac(v.y, e0.y);
-        a10.mac(v.x, e1.x);
-        a11.mac(v.y, e1.y);
+    Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+    for (int d0 = 0; d0 < beta; d0 += CH) {
+        ulonglong2 v[CH], e0[CH], e1[CH];
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int d = min(d0 + c, beta - 1);
+            const u64 *k0 = evk[d] + krow;
+            v[c] = ld2(tj + (size_t) d * m_n);
+            e0[c] = ld2_nc(k0);
+            e1[c] = ld2_nc(k0 + qp_n);
+        }
+#pragma unroll
+        for (int c = 0; c < CH; c++) {
+            const int d = d0 + c;
+            if (d < beta) {
+                const ulonglong2 w = d == own_d ? own : v[c];
+                a00.mac(w.x, e0[c].x);
+                a01.mac(w.y, e0[c].y);
+                a10.mac(w.x, e1[c].x);
+                a11.mac(w.y, e1[c].y);
+            }
+        }
     }
     st2(cx + (size_t) j * n + x, barrett_g(a00.lo, a00.hi, bg, md), barrett_g(a01.lo, a01.hi, bg, md));
     st2(cx + m_n + (size_t) j * n + x, barrett_g(a10.lo, a10.hi, bg, md), barrett_g(a11.lo, a11.hi, bg, md));
