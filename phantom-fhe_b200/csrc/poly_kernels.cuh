@@ -25,6 +25,20 @@ struct RowArith {
 
 __device__ __forceinline__ ulonglong2 ld2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
 __device__ __forceinline__ ulonglong2 ld2_nc(const u64 *p) { return __ldg(reinterpret_cast<const ulonglong2 *>(p)); }
+// streaming load: read once, do not keep in L1, first candidate for eviction in L2 (the 80 MiB switching key
+// must not push the mod-up digits out of L2 between the NTT that wrote them and the inner product)
+__device__ __forceinline__ u64 l2_evict_first_policy() {
+    u64 pol;
+    asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
+__device__ __forceinline__ ulonglong2 ld2_stream(const u64 *p, u64 pol) {
+    ulonglong2 v;
+    asm volatile("ld.global.nc.L1::no_allocate.L2::cache_hint.v2.u64 {%0,%1}, [%2], %3;"
+                 : "=l"(v.x), "=l"(v.y)
+                 : "l"(p), "l"(pol));
+    return v;
+}
 __device__ __forceinline__ void st2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
 
 // ---------------------------------------------------------------------------------------------------
@@ -258,7 +272,7 @@ struct OwnSrc {
     const u64 *a1, *b1;
     int alpha;
 };
-__global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
+__global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
                                                             const Modulus *mod, const BarG *bar, const BarG *bar0,
                                                             RowArith ra, OwnSrc os, size_t n, int l, int m, int size_Q,
                                                             int size_QP, int beta) {
@@ -279,7 +293,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
     }
     const u64 *tj = t + (size_t) j * n + x;
     const size_t krow = (size_t) row * n + x;
-    constexpr int CH = 4;   // digits per batch: 12 independent 16-byte loads in flight per thread
+    constexpr int CH = 2;   // digits per batch: 6 independent 16-byte loads in flight per thread, 4 CTAs/SM
+    const u64 pol = l2_evict_first_policy();
     if (ra.fp(row)) {   // CTA-uniform: every term is reduced on the FP64 pipe, the small residues are summed
         const double q = ra.fpc[row].x, qi = ra.fpc[row].y;
         double ox = fp::from_u64(own.x), oy = fp::from_u64(own.y);
@@ -295,8 +310,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
                 const int d = min(d0 + c, beta - 1);   // clamp: tail lanes re-read the last digit, masked below
                 const u64 *k0 = evk[d] + krow;
                 v[c] = ld2(tj + (size_t) d * m_n);
-                e0[c] = ld2_nc(k0);
-                e1[c] = ld2_nc(k0 + qp_n);
+                e0[c] = ld2_stream(k0, pol);
+                e1[c] = ld2_stream(k0 + qp_n, pol);
             }
 #pragma unroll
             for (int c = 0; c < CH; c++) {
@@ -327,8 +342,8 @@ __global__ void __launch_bounds__(EW_THREADS) k_inner_prod(u64 *cx, const u64 *t
             const int d = min(d0 + c, beta - 1);
             const u64 *k0 = evk[d] + krow;
             v[c] = ld2(tj + (size_t) d * m_n);
-            e0[c] = ld2_nc(k0);
-            e1[c] = ld2_nc(k0 + qp_n);
+            e0[c] = ld2_stream(k0, pol);
+            e1[c] = ld2_stream(k0 + qp_n, pol);
         }
 #pragma unroll
         for (int c = 0; c < CH; c++) {
