@@ -137,6 +137,11 @@ int pfhe_apply_galois_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encr
 /* rotate_inplace (src/evaluate.cu:1633-1668) for a step whose element is in the engine's Galois set */
 int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, int step,
                         const uint64_t *const *galois_key, void *stream);
+/* hoisting_inplace (src/evaluate.cu:1670-1865): encrypted <- sum_i rotate(encrypted, steps[i]) with one shared mod-up
+ * and one mod-down; galois_keys[i] = PhantomGaloisKey::get_relin_keys(index of steps[i]).public_keys_ptr() (host
+ * array of n_steps device pointer arrays) */
+int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, const int *steps, size_t n_steps,
+                          const uint64_t *const *const *galois_keys, void *stream);
 /* rescale_to_next (src/evaluate.cu:1545-1565): destination = [size][l-1][n] */
 int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted, size_t size,
                          uint64_t *destination, void *stream);

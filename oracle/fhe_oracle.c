@@ -738,11 +738,35 @@ void orc_apply_galois_ntt(const orc_ctx *c, const u64 *src, u64 *dst, int l, con
         for (size_t j = 0; j < n; j++) dst[(size_t)i * n + j] = src[(size_t)i * n + table[j]];
 }
 
+/* apply_galois_permutation, galois.cu:20-39 (coefficient domain, BFV) */
+void orc_apply_galois_coeff(const orc_ctx *c, const u64 *src, u64 *dst, int l, uint32_t elt) {
+    size_t n = c->n;
+    for (int i = 0; i < l; i++) {
+        u64 q = c->primes[i];
+        for (size_t j = 0; j < n; j++) {
+            u64 idx = ((u64)j * elt) & (2 * n - 1);
+            u64 v = src[(size_t)i * n + j];
+            if (idx >= n) v = v ? q - v : 0;
+            dst[(size_t)i * n + (idx & (n - 1))] = v;
+        }
+    }
+}
+
 void orc_apply_galois(const orc_ctx *c, int l, u64 *ct, uint32_t elt, const u64 *glk) {
     size_t n = c->n, poly = (size_t)l * n;
     uint32_t *table = (uint32_t *)malloc(n * 4);
     u64 *tmp = (u64 *)malloc(poly * 8);
     orc_galois_table(n, elt, table);
+    if (c->scheme == ORC_SCHEME_BFV) { /* evaluate.cu:1596-1609 */
+        orc_apply_galois_coeff(c, ct, tmp, l, elt);
+        memcpy(ct, tmp, poly * 8);
+        orc_apply_galois_coeff(c, ct + poly, tmp, l, elt);
+        memset(ct + poly, 0, poly * 8);
+        orc_keyswitch(c, l, ct, tmp, glk);
+        free(table);
+        free(tmp);
+        return;
+    }
     orc_apply_galois_ntt(c, ct, tmp, l, table);
     memcpy(ct, tmp, poly * 8);
     orc_apply_galois_ntt(c, ct + poly, tmp, l, table);
@@ -750,6 +774,39 @@ void orc_apply_galois(const orc_ctx *c, int l, u64 *ct, uint32_t elt, const u64 
     orc_keyswitch(c, l, ct, tmp, glk);
     free(table);
     free(tmp);
+}
+
+/* hoisting_inplace (CKKS/BGV), evaluate.cu:1670-1865: sum over elts of the rotated ciphertext with one shared
+ * mod-up and one mod-down.  glk[i] = switching key of elts[i] ([dnum][2][size_QP][n]) */
+void orc_hoisting(const orc_ctx *c, int l, u64 *ct, const uint32_t *elts, int n_elts, const u64 *const *glk) {
+    size_t n = c->n, poly = (size_t)l * n;
+    int m = l + c->size_P, beta = orc_beta(c, l);
+    size_t m_n = (size_t)m * n;
+    uint32_t *table = (uint32_t *)malloc(n * 4);
+    u64 *acc_c0 = (u64 *)calloc(poly, 8), *tmp = (u64 *)malloc(poly * 8);
+    u64 *up = (u64 *)malloc((size_t)beta * m_n * 8), *pup = (u64 *)malloc((size_t)beta * m_n * 8);
+    u64 *acc = (u64 *)calloc(2 * m_n, 8), *cx = (u64 *)malloc(2 * m_n * 8);
+    u64 *res = (u64 *)malloc(poly * 8);
+    orc_modup(c, l, ct + poly, up);
+    for (int e = 0; e < n_elts; e++) {
+        orc_galois_table(n, elts[e], table);
+        orc_apply_galois_ntt(c, ct, tmp, l, table);
+        orc_poly_add(c, acc_c0, tmp, acc_c0, l);
+        /* the same index permutation on every limb of every digit (:1775-1778); moduli do not matter here */
+        for (int b = 0; b < beta * m; b++)
+            for (size_t j = 0; j < n; j++) pup[(size_t)b * n + j] = up[(size_t)b * n + table[j]];
+        orc_inner_prod(c, l, pup, glk[e], cx);
+        for (int k = 0; k < 2; k++)
+            for (int j = 0; j < m; j++) {
+                u64 q = c->primes[qlp_index(c, l, j)];
+                u64 *a = acc + (size_t)k * m_n + (size_t)j * n, *b = cx + (size_t)k * m_n + (size_t)j * n;
+                for (size_t x = 0; x < n; x++) a[x] = addmod(a[x], b[x], q);
+            }
+    }
+    orc_moddown_from_ntt(c, l, acc, res);
+    orc_poly_add(c, acc_c0, res, ct, l);
+    orc_moddown_from_ntt(c, l, acc + m_n, ct + poly);
+    free(table); free(acc_c0); free(tmp); free(up); free(pup); free(acc); free(cx); free(res);
 }
 
 /* ------------------------------------------------------------------------------------------------------

@@ -52,6 +52,7 @@ _sigs = {
     "pfhe_relinearize_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp]),
     "pfhe_apply_galois_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_uint32, vp, vp]),
     "pfhe_rotate_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_int, vp, vp]),
+    "pfhe_hoisting_inplace": (ctypes.c_int, [vp, sz, vp, i32p, sz, vp, vp]),
     "pfhe_rescale_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_mod_switch_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_multiply_and_relin_host": (ctypes.c_int, [vp, sz, vp, vp, vp, vp, vp]),

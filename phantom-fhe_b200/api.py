@@ -192,6 +192,8 @@ def _require_ntt(context, ct):
     if context.scheme in (scheme_type.ckks, scheme_type.bgv) and not ct.is_ntt_form:
         name = "CKKS" if context.scheme == scheme_type.ckks else "BGV"
         raise ValueError(f"{name} encrypted must be in NTT form")
+    if context.scheme == scheme_type.bfv and ct.is_ntt_form:
+        raise ValueError("BFV encrypted cannot be in NTT form")
 
 
 def multiply_inplace(context, encrypted1, encrypted2):
@@ -224,7 +226,7 @@ def relinearize_inplace(context, encrypted, relin_keys):
 
 def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
     """multiply_and_relin_inplace (src/evaluate.cu:1061-1104), fused tensor + key-switch."""
-    if not (encrypted1.is_ntt_form and encrypted2.is_ntt_form):
+    if context.scheme != scheme_type.bfv and not (encrypted1.is_ntt_form and encrypted2.is_ntt_form):
         raise ValueError("encrypted1 and encrypted2 must be in NTT form")
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
@@ -278,6 +280,22 @@ def rotate_inplace(context, encrypted, step, galois_key):
     for s in naf_steps:
         if abs(s) != (n >> 1):
             rotate_inplace(context, encrypted, s, galois_key)
+
+
+def hoisting_inplace(context, ct, glk, steps):
+    """hoisting_inplace (src/evaluate.cu:1670-1865)."""
+    if ct.size() > 2:
+        raise ValueError("ciphertext size must be 2")
+    elts = context.parms.galois_elts
+    ptrs = []
+    for s in steps:
+        e = get_elt_from_step(s, context.poly_degree)
+        if e not in elts:
+            raise RuntimeError("Galois key not present in hoisting")
+        ptrs.append(glk.get_relin_keys(elts.index(e)).public_keys_ptr().value)
+    arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
+    st = (ctypes.c_int * len(steps))(*steps)
+    check(lib.pfhe_hoisting_inplace(context._h, ct.chain_index, _ptr(ct.data), st, len(steps), arr, _stream()))
 
 
 def rescale_to_next(context, encrypted):

@@ -207,7 +207,6 @@ int pfhe_negate_rns_poly(pfhe_engine *e, const uint64_t *a, uint64_t *r, size_t 
 // ---- key switching ------------------------------------------------------------------------------------
 int pfhe_modup(pfhe_engine *e, size_t chain_index, uint64_t *dst, const uint64_t *cks, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     e->impl.modup(l, U(dst), U(cks), e->impl.ws().t_cks.p, S(stream));
     API_END
@@ -221,15 +220,14 @@ int pfhe_key_switch_inner_prod(pfhe_engine *e, size_t chain_index, uint64_t *p_c
 }
 int pfhe_moddown_from_ntt(pfhe_engine *e, size_t chain_index, uint64_t *ct_i, uint64_t *cx_i, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
-    e->impl.moddown(l, U(ct_i), U(cx_i), e->impl.ws().delta.p, 1, nullptr, 0u, S(stream));
+    if (e->impl.scheme() == Scheme::ckks) e->impl.moddown(l, U(ct_i), U(cx_i), e->impl.ws().delta.p, 1, nullptr, 0u, S(stream));
+    else e->impl.moddown_generic(l, U(ct_i), U(cx_i), 1, nullptr, 0u, S(stream));
     API_END
 }
 int pfhe_keyswitch_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, const uint64_t *c2,
                            const uint64_t *const *relin_keys, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     e->impl.keyswitch(l, U(encrypted), U(c2), K(relin_keys), U(encrypted), S(stream));
     API_END
@@ -255,7 +253,7 @@ int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *
 int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, uint64_t *dst,
                   void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
+    require(e->impl.scheme() != Scheme::bfv, "BFV multiplication (BEHZ/HPS) is not on this engine yet: unsupported scheme");
     const int l = e->impl.limbs_at(chain_index);
     if (ct1 == ct2) e->impl.tensor_square(U(ct1), U(dst), l, S(stream));
     else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
@@ -264,7 +262,6 @@ int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const
 int pfhe_relinearize_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *const *rlk,
                              void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     const size_t poly = (size_t) l * e->impl.n();
     e->impl.keyswitch(l, U(ct), U(ct) + 2 * poly, K(rlk), U(ct), S(stream));
@@ -273,7 +270,6 @@ int pfhe_relinearize_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, c
 int pfhe_apply_galois_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, uint32_t elt,
                               const uint64_t *const *glk, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     e->impl.apply_galois(l, U(ct), elt, K(glk), S(stream));
     API_END
@@ -284,6 +280,20 @@ int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, int st
     int rc = pfhe_galois_elt_from_step(step, e->impl.n(), &elt);
     if (rc != PFHE_OK) return rc;
     return pfhe_apply_galois_inplace(e, chain_index, ct, elt, glk, stream);
+}
+int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const int *steps, size_t n_steps,
+                          const uint64_t *const *const *galois_keys, void *stream) {
+    API_BEGIN
+    require(steps && galois_keys && n_steps > 0, "steps is empty");
+    const int l = e->impl.limbs_at(chain_index);
+    std::vector<uint32_t> elts(n_steps);
+    std::vector<const u64 *const *> keys(n_steps);
+    for (size_t i = 0; i < n_steps; i++) {
+        if (pfhe_galois_elt_from_step(steps[i], e->impl.n(), &elts[i]) != PFHE_OK) throw std::invalid_argument(g_error);
+        keys[i] = K(galois_keys[i]);
+    }
+    e->impl.hoisting(l, U(ct), elts, keys, S(stream));
+    API_END
 }
 int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *dst,
                          void *stream) {
@@ -297,10 +307,10 @@ int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *ct,
 int pfhe_mod_switch_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *dst,
                             void *stream) {
     API_BEGIN
-    require(e->impl.scheme() == Scheme::ckks, "unsupported scheme");   // BFV/BGV variants: DESIGN.md "next"
     require(size >= 1 && size <= 3, "encrypted size is invalid");
     const int l = e->impl.limbs_at(chain_index);
-    e->impl.mod_switch_drop(l, U(dst), U(ct), (int) size, S(stream));
+    if (e->impl.scheme() == Scheme::ckks) e->impl.mod_switch_drop(l, U(dst), U(ct), (int) size, S(stream));
+    else e->impl.mod_switch_scale(l, U(dst), U(ct), (int) size, S(stream));   // BFV / BGV: with scaling
     API_END
 }
 

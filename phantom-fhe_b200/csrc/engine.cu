@@ -2,6 +2,7 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <numeric>
 #include <cstdlib>
 #include <cstring>
 #include <functional>
@@ -81,7 +82,7 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
     ws_.t_cks.alloc((size_t) size_Q_ * n_);
     ws_.t_mod_up.alloc(beta_max * size_QP_ * n_);
     ws_.cx.alloc((size_t) 2 * size_QP_ * n_);
-    ws_.delta.alloc((size_t) 2 * size_Q_ * n_);
+    ws_.delta.alloc((size_t) 2 * (size_Q_ + 1) * n_);
     ws_.tmp.alloc((size_t) 3 * size_Q_ * n_);
 
     // Galois permutation tables (reference include/galois.cuh:98-113)
@@ -125,18 +126,24 @@ void Engine::build_tables() {
     // forces the integer path everywhere (A/B measurements).
     const char *env = std::getenv("PFHE_FP64_NTT");
     const bool allow_fp = !(env && env[0] == '0');
-    is_fp_.assign(size_QP_, 0);
-    std::vector<double2> fpc(size_QP_);
+    mod_rows_ = size_QP_ + (t_ > 1 ? 1 : 0);
+    is_fp_.assign(mod_rows_, 0);
+    std::vector<double2> fpc(mod_rows_);
     for (int i = 0; i < size_QP_; i++) {
         is_fp_[i] = allow_fp && (primes_[i] >> 46) == 0;
         fpc[i] = make_double2((double) primes_[i], 1.0 / (double) primes_[i]);
     }
+    if (t_ > 1) fpc[size_QP_] = make_double2((double) t_, 1.0 / (double) t_);   // integer path for the t row
     for (int i = 0; i < size_QP_ && i < 128; i++)
         if (is_fp_[i]) fp_mask_[i >> 6] |= 1ull << (i & 63);
     d_is_fp_.upload(is_fp_);
     d_fpc_.upload(fpc);
     std::vector<Tw> tw((size_t) size_QP_ * n_), itw((size_t) size_QP_ * n_), fin((size_t) size_QP_ * 2);
-    std::vector<Modulus> mods(size_QP_);
+    std::vector<Modulus> mods(mod_rows_);
+    if (t_ > 1) {
+        const auto rt = hm::barrett_ratio(t_);
+        mods[size_QP_] = Modulus{t_, rt.lo, rt.hi};
+    }
     h_ninv_.resize(size_QP_);
     h_itw1_.resize(size_QP_);
     for (int i = 0; i < size_QP_; i++) {
@@ -170,10 +177,10 @@ void Engine::build_tables() {
     d_inv_fin_.upload(fin);
     d_mod_.upload(mods);
     // single-word Barrett constants: growth class g covers values < 2^(2k+g), k = bit length of q
-    std::vector<BarG> bars((size_t) 64 * size_QP_);
+    std::vector<BarG> bars((size_t) 64 * mod_rows_);
     for (int g = 0; g < 64; g++)
-        for (int i = 0; i < size_QP_; i++) {
-            const u64 q = primes_[i];
+        for (int i = 0; i < mod_rows_; i++) {
+            const u64 q = mods[i].q;
             const int k = 64 - __builtin_clzll(q);
             BarG b{0, 0xffu, 0};
             if (k + g <= 63) {
@@ -181,7 +188,7 @@ void Engine::build_tables() {
                 b.sh = (u32) sh;
                 b.mu = (u64) ((((unsigned __int128) 1) << (64 + sh)) / q);   // < 2^64 because sh <= k - 1
             }
-            bars[(size_t) g * size_QP_ + i] = b;
+            bars[(size_t) g * mod_rows_ + i] = b;
         }
     d_bar_.upload(bars);
     plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p, d_is_fp_.p, d_fpc_.p, allow_fp ? 1 : 0};
@@ -191,7 +198,7 @@ const BarG *Engine::bar(int terms, int extra_bits) const {
     int g = extra_bits;
     while ((1 << (g - extra_bits)) < terms) g++;
     if (g > 63) g = 63;   // classes that do not apply to a modulus fall back to the two-word Barrett
-    return d_bar_.p + (size_t) g * size_QP_;
+    return d_bar_.p + (size_t) g * mod_rows_;
 }
 
 int Engine::limbs_at(size_t chain_index) const {
@@ -297,6 +304,45 @@ void Engine::build_level(int l) {
             pinv[j] = pinv[l + j] = make_tw(hm::invmod(hm::product_mod(pbase, -1, q), q), q);
         }
         lv->moddown_fin.upload(dfin);
+        {   // all limbs of cx[k]: plain n^-1 for the Q limbs, n^-1 * phat_i^-1 for the P limbs
+            std::vector<Tw> fall((size_t) 2 * lv->m * 2);
+            for (int k = 0; k < 2; k++)
+                for (int j = 0; j < lv->m; j++) {
+                    const int row = row_of(j);
+                    const u64 q = primes_[row];
+                    u64 c = h_ninv_[row];
+                    if (j >= l) c = hm::mulmod(c, hm::invmod(hm::product_mod(pbase, j - l, q), q), q);
+                    fall[2 * ((size_t) k * lv->m + j)] = make_tw_row(row, c);
+                    fall[2 * ((size_t) k * lv->m + j) + 1] = make_tw_row(row, hm::mulmod(c, h_itw1_[row], q));
+                }
+            lv->moddown_fin_all.upload(fall);
+        }
+        {
+            std::vector<Tw> pmq(l);
+            for (int j = 0; j < l; j++) pmq[j] = make_tw(hm::product_mod(pbase, -1, primes_[j]), primes_[j]);
+            lv->P_mod_q.upload(pmq);
+        }
+        if (t_ > 1) {
+            std::vector<u64> tm;
+            std::vector<double2> tmf;
+            std::vector<short> tomod, tolimb;
+            for (int j = 0; j <= l; j++) {
+                const u64 q = j < l ? primes_[j] : t_;
+                for (int i = 0; i < alpha; i++) {
+                    const u64 M = hm::product_mod(pbase, i, q);
+                    tm.push_back(M);
+                    push_matf(tmf, M, q);
+                }
+                tomod.push_back((short) (j < l ? j : size_QP_));
+                tolimb.push_back((short) j);
+            }
+            lv->moddown_mat_t.upload(tm);
+            lv->moddown_matf_t.upload(tmf);
+            lv->moddown_omod_t.upload(tomod);
+            lv->moddown_olimb_t.upload(tolimb);
+            const u64 Pt = hm::product_mod(pbase, -1, t_);
+            if (std::gcd(Pt, t_) == 1) lv->pinv_t = make_tw(hm::invmod(Pt, t_), t_);
+        }
         lv->moddown_mat.upload(dmat);
         lv->moddown_matf.upload(dmatf);
         lv->moddown_omod.upload(dmod);
@@ -310,6 +356,10 @@ void Engine::build_level(int l) {
             qli[j] = qli[(l - 1) + j] = qli[2 * (l - 1) + j] =
                     make_tw(hm::invmod(qlast % primes_[j], primes_[j]), primes_[j]);
         lv->qlast_inv_slots.upload(qli);
+        std::vector<Tw> qlm(l - 1);
+        for (int j = 0; j < l - 1; j++) qlm[j] = make_tw(qlast % primes_[j], primes_[j]);
+        lv->qlast_mod_q.upload(qlm);
+        if (t_ > 1 && std::gcd(qlast % t_, t_) == 1) lv->inv_qlast_t = make_tw(hm::invmod(qlast % t_, t_), t_);
     }
     levels_[l] = std::move(lv);
 }
@@ -422,11 +472,17 @@ static void launch_bconv(const BconvBatch &batch, int jobs, int ni, int no_max, 
 void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_t st) const {
     const Level &lv = level(l);
     if (lv.alpha == 0) throw std::logic_error("key switching needs special primes");
-    // 1. inverse NTT fused with the n^-1 * qhat_i^-1 scaling (iNTT+scale, rns_bconv.cu:558)
-    {
+    const bool bfv = scheme_ == Scheme::bfv;
+    if (!bfv) {
+        // 1. inverse NTT fused with the n^-1 * qhat_i^-1 scaling (iNTT+scale, rns_bconv.cu:558)
         LimbVec v;
         for (int i = 0; i < l; i++) v.push(i, i);
         run_chunks(v, primes_, [&](const LimbList &ll, size_t b) { ntt_inv_list(t_cks, cks, ll, lv.modup_fin.p + 2 * b, 1, st); });
+    } else {
+        // BFV: cks is already in coefficient form, only the qhat_i^-1 scaling (bconv_mult_kernel, :598)
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+        launch_pdl(k_scale_limbs, grid, EW_THREADS, 0, st, t_cks, cks, lv.modup_fin_coeff.p, d_mod_.p, n_);
+        check_launch("k_scale_limbs");
     }
     // 2. each digit: own limbs copied (modup_copy_partQl_kernel :522-528), other limbs converted (:455-485)
     for (int d = 0; d < lv.beta;) {
@@ -449,26 +505,31 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
             no_max = std::max(no_max, lv.digit_no[d]);
             jobs++, d++;
         }
-        launch_bconv(batch, jobs, ni, no_max, d_mod_.p, d_bar_.p, RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, size_QP_, n_, st);
+        launch_bconv(batch, jobs, ni, no_max, d_mod_.p, d_bar_.p, RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], mod_rows_ <= 128}, mod_rows_, n_, st);
     }
-    // 3. forward NTT of the converted limbs only (..._exclude_range, rns_bconv.cu:618)
+    // 3. forward NTT of the converted limbs only (..._exclude_range, rns_bconv.cu:618); BFV: of every limb (:622)
     {
         LimbVec v;
-        v.data = lv.modup_ntt_data, v.row = lv.modup_ntt_row, v.src = lv.modup_ntt_data;
+        if (!bfv) {
+            v.data = lv.modup_ntt_data, v.row = lv.modup_ntt_row, v.src = lv.modup_ntt_data;
+        } else {
+            for (int d = 0; d < lv.beta; d++)
+                for (int j = 0; j < lv.m; j++) v.push(d * lv.m + j, j < l ? j : size_Q_ + (j - l));
+        }
         run_chunks(v, primes_, [&](const LimbList &ll, size_t) { ntt_fwd_list(t_mod_up, t_mod_up, ll, st); });
     }
 }
 
 void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st,
-                        const u64 *own_c2, const TensorSrc *ts) const {
+                        const u64 *own_c2, const TensorSrc *ts, const uint32_t *perm, bool accumulate) const {
     const Level &lv = level(l);
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), lv.m);
     OwnSrc os{nullptr, nullptr, nullptr, 0};
     if (own_c2) os = OwnSrc{own_c2, nullptr, nullptr, lv.alpha};
     else if (ts) os = OwnSrc{nullptr, ts->a + (size_t) ts->l * n_, ts->b + (size_t) ts->l * n_, lv.alpha};
     launch_pdl(k_inner_prod, grid, EW_THREADS, 0, st, cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), bar(1, 0),
-               RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, n_, l, lv.m, size_Q_,
-               size_QP_, lv.beta);
+               RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, perm, accumulate ? 1 : 0,
+               n_, l, lv.m, size_Q_, size_QP_, lv.beta);
     check_launch("k_inner_prod");
 }
 
@@ -495,7 +556,7 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
             batch.job[k] = BconvJob{cx + ((size_t) k * m + l) * n_, delta + (size_t) k * l * n_, lv.moddown_mat.p,
                                     lv.moddown_omod.p, lv.moddown_olimb.p, alpha, l, pbits + ceil_log2(alpha),
                                     lv.moddown_matf.p, lv.moddown_big};
-        launch_bconv(batch, npoly, alpha, l, d_mod_.p, d_bar_.p, RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, size_QP_, n_, st);
+        launch_bconv(batch, npoly, alpha, l, d_mod_.p, d_bar_.p, RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], mod_rows_ <= 128}, mod_rows_, n_, st);
     }
     // 3. forward NTT of delta with the fused (cx - delta) * P^-1 (+ ct) epilogue (:820, ntt_moddown.cu:106-216)
     {
@@ -559,24 +620,30 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         size_t moff = 0;
         for (int e = 0; e < d0; e++) moff += (size_t) lv.digit_no[e] * lv.digit_size[e];
         bl.in_base = t_cks, bl.mat = lv.modup_mat.p + moff, bl.matf = lv.modup_matf.p + 2 * moff;
-        bl.bar = d_bar_.p, bl.size_QP = size_QP_, bl.ni = ni;
+        bl.bar = d_bar_.p, bl.size_QP = mod_rows_, bl.ni = ni;
         int kin = 0, cnt = 0;
-        for (int d = d0; d < d1; d++) {
-            const int start = lv.digit_start[d];
-            for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(primes_[start + i]));
-            int jo = 0;
-            for (int j = 0; j < m; j++) {
-                if (j >= start && j < start + ni) continue;
-                const int row = j < l ? j : size_Q_ + (j - l);
-                ll.data[cnt] = ll.src[cnt] = (short) (d * m + j);
-                ll.row[cnt] = (short) row;
-                ll.q[cnt] = primes_[row];
-                bl.in_limb[cnt] = (short) start;
-                bl.mat_row[cnt] = (short) (lv.digit_off[d] - lv.digit_off[d0] + jo);
-                bl.in_big[cnt] = (unsigned char) lv.digit_big[d];
-                cnt++, jo++;
+        // slots whose modulus takes the (slower) integer path are issued first: longest tiles start earliest
+        for (int pass = 0; pass < 2; pass++)
+            for (int d = d0; d < d1; d++) {
+                const int start = lv.digit_start[d];
+                for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(primes_[start + i]));
+                int jo = 0;
+                for (int j = 0; j < m; j++) {
+                    if (j >= start && j < start + ni) continue;
+                    const int row = j < l ? j : size_Q_ + (j - l);
+                    const bool slow = !is_fp_[row];
+                    if (slow == (pass == 0)) {
+                        ll.data[cnt] = ll.src[cnt] = (short) (d * m + j);
+                        ll.row[cnt] = (short) row;
+                        ll.q[cnt] = primes_[row];
+                        bl.in_limb[cnt] = (short) start;
+                        bl.mat_row[cnt] = (short) (lv.digit_off[d] - lv.digit_off[d0] + jo);
+                        bl.in_big[cnt] = (unsigned char) lv.digit_big[d];
+                        cnt++;
+                    }
+                    jo++;
+                }
             }
-        }
         ll.count = cnt;
         bl.xbits = kin + ceil_log2(ni);
         g_launches.fetch_add(2, std::memory_order_relaxed);
@@ -600,11 +667,13 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         int pbits = 0;
         for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(primes_[size_Q_ + i]));
         bl.in_base = cx, bl.mat = lv.moddown_mat.p, bl.matf = lv.moddown_matf.p, bl.bar = d_bar_.p;
-        bl.size_QP = size_QP_, bl.ni = alpha, bl.xbits = pbits + ceil_log2(alpha);
+        bl.size_QP = mod_rows_, bl.ni = alpha, bl.xbits = pbits + ceil_log2(alpha);
         ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p;
         int cnt = 0;
+        for (int pass = 0; pass < 2; pass++)
         for (int k = 0; k < 2; k++)
             for (int j = 0; j < l; j++) {
+                if ((!is_fp_[j]) != (pass == 0)) continue;   // integer-path limbs first
                 ll.data[cnt] = ll.src[cnt] = (short) (k * l + j);
                 ll.row[cnt] = (short) j;
                 ll.q[cnt] = primes_[j];
@@ -624,11 +693,112 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
 
 // keyswitch_inplace (reference src/eval_key_switch.cu:95-182): out[2][l][n] = addend + moddown(<modup(c2), evk>)
 void Engine::keyswitch(int l, u64 *out, const u64 *c2, const u64 *const *evk, const u64 *addend, cudaStream_t st) {
-    keyswitch_fused(l, out, c2, nullptr, evk, addend, addend ? 3u : 0u, st);
+    if (scheme_ == Scheme::ckks) {
+        keyswitch_fused(l, out, c2, nullptr, evk, addend, addend ? 3u : 0u, st);
+        return;
+    }
+    // BGV (NTT-form input, plain-modulus correction) and BFV (coefficient-form input and output)
+    modup(l, ws_.t_mod_up.p, c2, ws_.t_cks.p, st);
+    inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
+    moddown_generic(l, out, ws_.cx.p, 2, addend, addend ? 3u : 0u, st);
+}
+
+void Engine::moddown_generic(int l, u64 *out, u64 *cx, int npoly, const u64 *addend, unsigned add_mask,
+                             cudaStream_t st) {
+    const Level &lv = level(l);
+    const int alpha = lv.alpha, m = lv.m;
+    const bool bgv = scheme_ == Scheme::bgv;
+    if (bgv && (t_ <= 1 || lv.pinv_t.x == 0)) throw std::logic_error("invalid rns bases when computing pjInv_mod_t");
+    // 1. every limb of cx back to coefficient form (rns_bconv.cu:790-794), P limbs also scaled by phat_i^-1
+    {
+        LimbVec v;
+        for (int k = 0; k < npoly; k++)
+            for (int j = 0; j < m; j++) v.push(k * m + j, j < l ? j : size_Q_ + (j - l));
+        run_chunks(v, primes_, [&](const LimbList &ll, size_t b) { ntt_inv_list(cx, cx, ll, lv.moddown_fin_all.p + 2 * b, 1, st); });
+    }
+    // 2. P -> Ql (and, BGV, P -> t) conversion
+    u64 *delta = ws_.delta.p;
+    const int no = bgv ? l + 1 : l;
+    {
+        int pbits = 0;
+        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(primes_[size_Q_ + i]));
+        BconvBatch batch{};
+        for (int k = 0; k < npoly; k++) {
+            if (bgv)
+                batch.job[k] = BconvJob{cx + ((size_t) k * m + l) * n_, delta + (size_t) k * (l + 1) * n_,
+                                        lv.moddown_mat_t.p, lv.moddown_omod_t.p, lv.moddown_olimb_t.p, alpha, no,
+                                        pbits + ceil_log2(alpha), lv.moddown_matf_t.p, lv.moddown_big};
+            else
+                batch.job[k] = BconvJob{cx + ((size_t) k * m + l) * n_, delta + (size_t) k * (l + 1) * n_,
+                                        lv.moddown_mat.p, lv.moddown_omod.p, lv.moddown_olimb.p, alpha, no,
+                                        pbits + ceil_log2(alpha), lv.moddown_matf.p, lv.moddown_big};
+        }
+        launch_bconv(batch, npoly, alpha, no, d_mod_.p, d_bar_.p,
+                     RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], mod_rows_ <= 128}, mod_rows_, n_, st);
+    }
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+    for (int k = 0; k < npoly; k++) {
+        const u64 *add = (addend && ((add_mask >> k) & 1)) ? addend + (size_t) k * l * n_ : nullptr;
+        u64 *dk = delta + (size_t) k * (l + 1) * n_;
+        u64 *ok = out + (size_t) k * l * n_;
+        if (!bgv) {
+            // BFV: result stays in the coefficient domain (moddown_kernel :680-689 + add_to_ct :763-769)
+            launch_pdl(k_moddown_coeff, grid, EW_THREADS, 0, st, ok, cx + (size_t) k * m * n_, dk, lv.pinv_slots.p, add,
+                       d_mod_.p, n_);
+            check_launch("k_moddown_coeff");
+        } else {
+            // BGV: plain-modulus correction, back to NTT form, then add (bgv_moddown_kernel :636-652, :810-817)
+            u64 *tmp = ws_.t_cks.p;   // [l][n]
+            launch_pdl(k_bgv_moddown, grid, EW_THREADS, 0, st, tmp, cx + (size_t) k * m * n_, dk, dk + (size_t) l * n_,
+                       lv.P_mod_q.p, lv.pinv_slots.p, lv.pinv_t, t_, d_mod_.p, n_);
+            check_launch("k_bgv_moddown");
+            ntt_fwd_rows_range(tmp, l, 0, st);
+            if (add) elementwise(EW_ADD, tmp, add, ok, l, st);
+            else PFHE_CUDA(cudaMemcpyAsync(ok, tmp, (size_t) l * n_ * 8, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+}
+
+void Engine::mod_switch_scale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) {
+    if (l < 2) throw std::invalid_argument("end of modulus switching chain reached");
+    const Level &lv = level(l);
+    const int nl = l - 1;
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), nl);
+    for (int s = 0; s < size; s++) {
+        const u64 *ci = in + (size_t) s * l * n_;
+        u64 *co = out + (size_t) s * nl * n_;
+        if (scheme_ == Scheme::bfv) {
+            launch_pdl(k_divide_round_last, grid, EW_THREADS, 0, st, co, ci, lv.qlast_inv_slots.p, d_mod_.p, n_, nl);
+            check_launch("k_divide_round_last");
+        } else {   // BGV
+            if (t_ <= 1 || lv.inv_qlast_t.x == 0) throw std::logic_error("invalid rns bases");
+            u64 *tmp = ws_.tmp.p;   // coefficient form of all l limbs
+            ntt_inv_rows_range(tmp, ci, l, 0, st);
+            launch_pdl(k_bgv_mod_t_divide, grid, EW_THREADS, 0, st, co, tmp, tmp + (size_t) nl * n_, lv.qlast_mod_q.p,
+                       lv.qlast_inv_slots.p, lv.inv_qlast_t, Modulus{t_, 0, hm::barrett_ratio(t_).hi}, d_mod_.p, n_);
+            check_launch("k_bgv_mod_t_divide");
+            ntt_fwd_rows_range(co, nl, 0, st);
+        }
+    }
+}
+
+void Engine::galois_coeff(u64 *dst, const u64 *src, uint32_t elt, int l, int npoly, cudaStream_t st) const {
+    dim3 grid((unsigned) (n_ / EW_THREADS), npoly * l);
+    launch_pdl(k_galois_coeff, grid, EW_THREADS, 0, st, dst, src, d_mod_.p, elt, n_, l);
+    check_launch("k_galois_coeff");
 }
 
 // multiply_inplace + relinearize_inplace for CKKS/BGV (reference src/evaluate.cu:345-397,1342-1374)
 void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st) {
+    if (scheme_ == Scheme::bfv)
+        throw std::invalid_argument("BFV multiplication (BEHZ/HPS) is not on this engine yet: unsupported scheme");
+    if (scheme_ == Scheme::bgv) {
+        u64 *d = ws_.tmp.p;
+        tensor_2x2(ct1, ct2, d, l, st);
+        keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
+        PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
+        return;
+    }
     if (out == ct1 || out == ct2) {
         // the fused epilogue reads a0, a1, b0, b1 while writing out: keep the operands alive in the workspace
         const size_t words = (size_t) 2 * l * n_;
@@ -689,12 +859,53 @@ void Engine::multiply_relin_host_batch(int l, const u64 *const *h1, const u64 *c
 void Engine::apply_galois(int l, u64 *ct, uint32_t galois_elt, const u64 *const *glk, cudaStream_t st) {
     const int gi = galois_index(galois_elt);
     u64 *tmp = ws_.tmp.p;   // [2][l][n]: permuted c0, c1
-    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), 2 * l);
-    launch_pdl(k_galois_ntt, grid, EW_THREADS, 0, st, tmp, ct, d_perm_[gi].p, n_);
-    check_launch("k_galois_ntt");
+    if (scheme_ == Scheme::bfv) {
+        galois_coeff(tmp, ct, galois_elt, l, 2, st);
+    } else {
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), 2 * l);
+        launch_pdl(k_galois_ntt, grid, EW_THREADS, 0, st, tmp, ct, d_perm_[gi].p, n_);
+        check_launch("k_galois_ntt");
+    }
+    if (scheme_ != Scheme::ckks) {
+        // ct0 = perm(c0) + ks0, ct1 = ks1
+        PFHE_CUDA(cudaMemcpyAsync(ct, tmp, (size_t) l * n_ * 8, cudaMemcpyDeviceToDevice, st));
+        PFHE_CUDA(cudaMemsetAsync(ct + (size_t) l * n_, 0, (size_t) l * n_ * 8, st));
+        // tmp[1] (the key-switch input) must survive modup's use of the workspace: it only touches t_cks/t_mod_up/cx
+        keyswitch(l, ct, tmp + (size_t) l * n_, glk, ct, st);
+        return;
+    }
     // ct0 = perm(c0) + ks0, ct1 = 0 + ks1: the "wipe c1" memset of the reference is folded away by
     // pointing poly 1 at a zero addend, i.e. no addend at all.
     keyswitch_fused(l, ct, tmp + (size_t) l * n_, nullptr, glk, tmp, 1u, st);
+}
+
+// hoisting_inplace (reference src/evaluate.cu:1670-1865), CKKS/BGV
+void Engine::hoisting(int l, u64 *ct, const std::vector<uint32_t> &elts, const std::vector<const u64 *const *> &keys,
+                      cudaStream_t st) {
+    if (scheme_ == Scheme::bfv) throw std::invalid_argument("unsupported scheme");
+    if (elts.empty() || elts.size() != keys.size()) throw std::invalid_argument("steps / keys mismatch");
+    const Level &lv = level(l);
+    const size_t poly = (size_t) l * n_;
+    u64 *acc_c0 = ws_.tmp.p;                 // [l][n]
+    u64 *c0 = ws_.tmp.p + poly, *c1 = ws_.tmp.p + 2 * poly;   // private copies: ct is overwritten at the end
+    PFHE_CUDA(cudaMemcpyAsync(c0, ct, 2 * poly * 8, cudaMemcpyDeviceToDevice, st));
+    // one mod-up of c1 for all rotations (:1761)
+    modup(l, ws_.t_mod_up.p, c1, ws_.t_cks.p, st);
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+    for (size_t i = 0; i < elts.size(); i++) {
+        int gi;
+        try {
+            gi = galois_index(elts[i]);
+        } catch (const std::invalid_argument &) { throw std::logic_error("Galois key not present in hoisting"); }
+        if (i == 0) launch_pdl(k_galois_ntt, grid, EW_THREADS, 0, st, acc_c0, c0, d_perm_[gi].p, n_);
+        else launch_pdl(k_galois_ntt_acc, grid, EW_THREADS, 0, st, acc_c0, c0, d_perm_[gi].p, d_mod_.p, n_);
+        check_launch("k_galois_ntt");
+        // automorphism of the digits + inner product + accumulation in one kernel
+        inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, keys[i], st, nullptr, nullptr, d_perm_[gi].p, i > 0);
+    }
+    // one mod-down per polynomial; new c0 = acc_c0 + moddown(cx0), new c1 = moddown(cx1)
+    if (scheme_ == Scheme::ckks) moddown(l, ct, ws_.cx.p, ws_.delta.p, 2, acc_c0, 1u, st);
+    else moddown_generic(l, ct, ws_.cx.p, 2, acc_c0, 1u, st);
 }
 
 // rescale_to_next for CKKS (reference src/evaluate.cu:1376-1427 + divide_and_round_q_last_ntt rns.cu:1160-1184)

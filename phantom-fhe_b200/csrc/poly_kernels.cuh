@@ -274,8 +274,8 @@ struct OwnSrc {
 };
 __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
                                                             const Modulus *mod, const BarG *bar, const BarG *bar0,
-                                                            RowArith ra, OwnSrc os, size_t n, int l, int m, int size_Q,
-                                                            int size_QP, int beta) {
+                                                            RowArith ra, OwnSrc os, const uint32_t *perm, int accumulate,
+                                                            size_t n, int l, int m, int size_Q, int size_QP, int beta) {
     pdl_launch_dependents();
     pdl_wait();
     const int j = blockIdx.y;
@@ -291,8 +291,22 @@ __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64
         if (os.c2) own = ld2(os.c2 + (size_t) j * n + x);
         else own = ld2(os.a1 + (size_t) j * n + x), ownb = ld2(os.b1 + (size_t) j * n + x);
     }
-    const u64 *tj = t + (size_t) j * n + x;
+    // hoisting (reference src/evaluate.cu:1775-1835): the digits are read through the Galois permutation and the
+    // result is accumulated into cx, instead of materialising the permuted digits and a temporary cx
+    size_t px0 = x, px1 = x + 1;
+    if (perm) {
+        const uint2 pp = *reinterpret_cast<const uint2 *>(perm + x);
+        px0 = pp.x, px1 = pp.y;
+    }
+    const u64 *tj = t + (size_t) j * n;
     const size_t krow = (size_t) row * n + x;
+    auto load_t = [&](int d) -> ulonglong2 {
+        const u64 *base = tj + (size_t) d * m_n;
+        if (perm) return make_ulonglong2(base[px0], base[px1]);
+        return ld2(base + x);
+    };
+    ulonglong2 old0 = make_ulonglong2(0, 0), old1 = make_ulonglong2(0, 0);
+    if (accumulate) old0 = ld2(cx + (size_t) j * n + x), old1 = ld2(cx + m_n + (size_t) j * n + x);
     constexpr int CH = 2;   // digits per batch: 6 independent 16-byte loads in flight per thread, 4 CTAs/SM
     const u64 pol = l2_evict_first_policy();
     if (ra.fp(row)) {   // CTA-uniform: every term is reduced on the FP64 pipe, the small residues are summed
@@ -309,7 +323,7 @@ __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64
             for (int c = 0; c < CH; c++) {
                 const int d = min(d0 + c, beta - 1);   // clamp: tail lanes re-read the last digit, masked below
                 const u64 *k0 = evk[d] + krow;
-                v[c] = ld2(tj + (size_t) d * m_n);
+                v[c] = load_t(d);
                 e0[c] = ld2_stream(k0, pol);
                 e1[c] = ld2_stream(k0 + qp_n, pol);
             }
@@ -326,6 +340,10 @@ __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64
                 }
             }
         }
+        if (accumulate) {
+            s00 += fp::from_u64(old0.x), s01 += fp::from_u64(old0.y);
+            s10 += fp::from_u64(old1.x), s11 += fp::from_u64(old1.y);
+        }
         st2(cx + (size_t) j * n + x, fp::canon(fp::reduce(s00, q, qi), q), fp::canon(fp::reduce(s01, q, qi), q));
         st2(cx + m_n + (size_t) j * n + x, fp::canon(fp::reduce(s10, q, qi), q), fp::canon(fp::reduce(s11, q, qi), q));
         return;
@@ -341,7 +359,7 @@ __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64
         for (int c = 0; c < CH; c++) {
             const int d = min(d0 + c, beta - 1);
             const u64 *k0 = evk[d] + krow;
-            v[c] = ld2(tj + (size_t) d * m_n);
+            v[c] = load_t(d);
             e0[c] = ld2_stream(k0, pol);
             e1[c] = ld2_stream(k0 + qp_n, pol);
         }
@@ -357,8 +375,110 @@ __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64
             }
         }
     }
-    st2(cx + (size_t) j * n + x, barrett_g(a00.lo, a00.hi, bg, md), barrett_g(a01.lo, a01.hi, bg, md));
-    st2(cx + m_n + (size_t) j * n + x, barrett_g(a10.lo, a10.hi, bg, md), barrett_g(a11.lo, a11.hi, bg, md));
+    u64 r00 = barrett_g(a00.lo, a00.hi, bg, md), r01 = barrett_g(a01.lo, a01.hi, bg, md);
+    u64 r10 = barrett_g(a10.lo, a10.hi, bg, md), r11 = barrett_g(a11.lo, a11.hi, bg, md);
+    if (accumulate) {
+        r00 = add_mod(r00, old0.x, md.q), r01 = add_mod(r01, old0.y, md.q);
+        r10 = add_mod(r10, old1.x, md.q), r11 = add_mod(r11, old1.y, md.q);
+    }
+    st2(cx + (size_t) j * n + x, r00, r01);
+    st2(cx + m_n + (size_t) j * n + x, r10, r11);
+}
+
+// ---------------------------------------------------------------------------------------------------
+// coefficient-domain pieces of the BFV / BGV key switch and modulus switch (integer Shoup constants)
+// ---------------------------------------------------------------------------------------------------
+// bconv_mult_kernel (reference src/rns_bconv.cu:22-31): dst[i][x] = src[i][x] * c[i] mod q_i; grid.y = limb
+__global__ void __launch_bounds__(EW_THREADS) k_scale_limbs(u64 *dst, const u64 *src, const Tw *c, const Modulus *mod,
+                                                             size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.y;
+    const u64 q = mod[i].q;
+    const Tw k = c[i];
+    const size_t x = (size_t) i * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const ulonglong2 v = ld2(src + x);
+    st2(dst + x, mul_shoup(v.x, k, q), mul_shoup(v.y, k, q));
+}
+
+// moddown_kernel (src/rns_bconv.cu:680-689) + add_to_ct_kernel (:763-769): out = (cx - delta) * P^-1 (+ add)
+__global__ void __launch_bounds__(EW_THREADS) k_moddown_coeff(u64 *out, const u64 *cx, const u64 *delta, const Tw *pinv,
+                                                               const u64 *add, const Modulus *mod, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int j = blockIdx.y;
+    const u64 q = mod[j].q;
+    const Tw k = pinv[j];
+    const size_t x = (size_t) j * n + ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const ulonglong2 c = ld2(cx + x), d = ld2(delta + x);
+    u64 r0 = mul_shoup(sub_mod(c.x, d.x, q), k, q), r1 = mul_shoup(sub_mod(c.y, d.y, q), k, q);
+    if (add) {
+        const ulonglong2 a = ld2(add + x);
+        r0 = add_mod(r0, a.x, q), r1 = add_mod(r1, a.y, q);
+    }
+    st2(out + x, r0, r1);
+}
+
+// bgv_moddown_kernel (src/rns_bconv.cu:636-652): dst = ((cx - delta) + [cp_t * P^-1]_t * P) * P^-1 mod q_j
+__global__ void __launch_bounds__(EW_THREADS) k_bgv_moddown(u64 *dst, const u64 *cx, const u64 *delta, const u64 *cp_t,
+                                                             const Tw *P_mod_q, const Tw *pinv, Tw pinv_t, u64 t,
+                                                             const Modulus *mod, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int j = blockIdx.y;
+    const u64 q = mod[j].q;
+    const size_t xo = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const size_t x = (size_t) j * n + xo;
+    const ulonglong2 c = ld2(cx + x), d = ld2(delta + x), ct = ld2(cp_t + xo);
+    const Tw pq = P_mod_q[j], pi = pinv[j];
+    u64 r[2];
+    const u64 cc[2] = {c.x, c.y}, dd[2] = {d.x, d.y}, tt[2] = {ct.x, ct.y};
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const u64 tmp = mul_shoup(tt[k], pinv_t, t);
+        const u64 corr = mul_shoup(tmp, pq, q);
+        r[k] = mul_shoup(add_mod(sub_mod(cc[k], dd[k], q), corr, q), pi, q);
+    }
+    st2(dst + x, r[0], r[1]);
+}
+
+// divide_and_round_q_last_kernel (src/rns.cu:1082-1108), BFV modulus switch in the coefficient domain:
+// dst[j] = (src[j] - (src[last] mod q_j)) * q_last^-1 mod q_j
+__global__ void __launch_bounds__(EW_THREADS) k_divide_round_last(u64 *dst, const u64 *src, const Tw *qlast_inv,
+                                                                   const Modulus *mod, size_t n, int nl) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int j = blockIdx.y;
+    const Modulus m = mod[j];
+    const size_t xo = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const ulonglong2 last = ld2(src + (size_t) nl * n + xo), c = ld2(src + (size_t) j * n + xo);
+    const Tw k = qlast_inv[j];
+    st2(dst + (size_t) j * n + xo, mul_shoup(sub_mod(c.x, barrett64(last.x, m), m.q), k, m.q),
+        mul_shoup(sub_mod(c.y, barrett64(last.y, m), m.q), k, m.q));
+}
+
+// bgv_mod_t_divide_q_kernel (src/rns.cu:1186-1207)
+__global__ void __launch_bounds__(EW_THREADS) k_bgv_mod_t_divide(u64 *dst, const u64 *cx, const u64 *ci_last,
+                                                                  const Tw *qlast_mod_q, const Tw *qlast_inv,
+                                                                  Tw inv_qlast_t, Modulus tm, const Modulus *mod, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int j = blockIdx.y;
+    const Modulus m = mod[j];
+    const size_t xo = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const size_t x = (size_t) j * n + xo;
+    const ulonglong2 last = ld2(ci_last + xo), c = ld2(cx + x);
+    const Tw qm = qlast_mod_q[j], qi = qlast_inv[j];
+    const u64 ll[2] = {last.x, last.y}, cc[2] = {c.x, c.y};
+    u64 r[2];
+#pragma unroll
+    for (int k = 0; k < 2; k++) {
+        const u64 delta = barrett64(ll[k], m);
+        const u64 tmp = mul_shoup(barrett64(ll[k], tm), inv_qlast_t, tm.q);
+        const u64 corr = mul_shoup(tmp, qm, m.q);
+        r[k] = mul_shoup(add_mod(sub_mod(cc[k], delta, m.q), corr, m.q), qi, m.q);
+    }
+    st2(dst + x, r[0], r[1]);
 }
 
 // dst[limb i] = src[perm...] helpers -------------------------------------------------------------------
@@ -371,6 +491,33 @@ __global__ void __launch_bounds__(EW_THREADS) k_galois_ntt(u64 *dst, const u64 *
     const size_t i = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
     const uint2 p = *reinterpret_cast<const uint2 *>(perm + i);
     st2(dst + limb * n + i, src[limb * n + p.x], src[limb * n + p.y]);
+}
+// dst[l][i] += src[l][perm[i]]  (hoisting: accumulated automorphisms of c0, evaluate.cu:1797-1810)
+__global__ void __launch_bounds__(EW_THREADS) k_galois_ntt_acc(u64 *dst, const u64 *src, const uint32_t *perm,
+                                                                const Modulus *mod, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t limb = blockIdx.y;
+    const u64 q = mod[limb].q;
+    const size_t i = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const uint2 p = *reinterpret_cast<const uint2 *>(perm + i);
+    const ulonglong2 a = ld2(dst + limb * n + i);
+    st2(dst + limb * n + i, add_mod(a.x, src[limb * n + p.x], q), add_mod(a.y, src[limb * n + p.y], q));
+}
+
+// apply_galois_permutation (reference src/galois.cu:20-39), coefficient domain (BFV): x^i -> x^(i * elt mod 2n),
+// sign flip when the exponent lands in [n, 2n).  grid.y = poly * l + limb
+__global__ void __launch_bounds__(EW_THREADS) k_galois_coeff(u64 *dst, const u64 *src, const Modulus *mod, uint32_t elt,
+                                                              size_t n, int l) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t pl = blockIdx.y;
+    const u64 q = mod[pl % l].q;
+    const size_t i = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
+    const size_t idx = (i * elt) & (2 * n - 1);
+    u64 v = src[pl * n + i];
+    if (idx >= n) v = v ? q - v : 0;
+    dst[pl * n + (idx & (n - 1))] = v;
 }
 
 // CKKS rescale pieces (divide_and_round_q_last_ntt, reference src/rns.cu:1128-1184)

@@ -59,7 +59,10 @@ def oracle():
         o.orc_galois_elt_from_step.restype = ctypes.c_uint32
         o.orc_galois_elt_from_step.argtypes = [ctypes.c_int, ctypes.c_uint64]
         o.orc_apply_galois.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_uint32, u64p]
+        o.orc_hoisting.argtypes = [vp, ctypes.c_int, u64p, u32p, ctypes.c_int, ctypes.POINTER(u64p)]
         o.orc_rescale.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p]
+        o.orc_divide_round_q_last.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p]
+        o.orc_bgv_mod_switch.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p]
         o.orc_mod_switch_drop.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p]
         for f in ("orc_twiddle", "orc_twiddle_shoup", "orc_itwiddle", "orc_itwiddle_shoup"):
             getattr(o, f).restype = u64p
@@ -160,8 +163,8 @@ def params_secondary():  # {60, 40x15, 60}, alpha=1 (single-P fast paths)
     return ParamSet("secondary", 65536, [60] + [40] * 15 + [60], 1)
 
 
-def params_small(n=4096, l=5, alpha=2, qbits=40, pbits=50):  # oracle-in-seconds sizes
-    return ParamSet(f"small{n}", n, [qbits + 10] + [qbits] * (l - 1) + [pbits] * alpha, alpha)
+def params_small(n=4096, l=5, alpha=2, qbits=40, pbits=50, scheme=3, t=0):  # oracle-in-seconds sizes
+    return ParamSet(f"small{n}", n, [qbits + 10] + [qbits] * (l - 1) + [pbits] * alpha, alpha, scheme, t)
 
 
 # ---------------------------------------------------------------------------------------------------------

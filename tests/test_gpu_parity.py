@@ -27,6 +27,8 @@ def make_context(ps, steps=()):
     parms.set_poly_modulus_degree(ps.n)
     parms.set_coeff_modulus([int(p) for p in ps.primes])
     parms.set_special_modulus_size(ps.size_P)
+    if ps.t:
+        parms.set_plain_modulus(ps.t)
     if steps:
         parms.set_galois_elts(pf.get_elts_from_steps(list(steps), ps.n))
     return pf.PhantomContext(parms)
@@ -248,6 +250,104 @@ def test_multiply_relin_rotate_rescale_small(cfg):
         c = pf.PhantomCiphertext.from_host(ctx, a)
         pf.rotate_inplace(ctx, c, s, glk)
         assert np.array_equal(c.to_host(), want), f"rotate {s}"
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BGV / BFV forms of the key switch and the modulus switch (rns_bconv.cu:583-606,636-652,790-827; rns.cu:1082-1235)
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("scheme", [1, 2])
+@pytest.mark.parametrize("cfg", [dict(n=4096, l=5, alpha=2), dict(n=4096, l=4, alpha=1), dict(n=8192, l=6, alpha=3)])
+def test_bgv_bfv_keyswitch_and_modswitch(scheme, cfg):
+    ps = H.params_small(scheme=scheme, t=65537, **cfg)
+    ctx = make_context(ps, [1])
+    o = H.oracle()
+    oc = ps.octx()
+    l, n = ps.limbs(), ps.n
+    m, beta = l + ps.size_P, ps.beta()
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    key_h = H.switch_key(ps, 100)
+    key = pf.PhantomRelinKey(ctx, list(key_h))
+    c2 = H.uniform_limbs(ps, list(range(l)), 5)[0]
+
+    want_up = np.zeros((beta, m, n), dtype=np.uint64)
+    o.orc_modup(oc, l, P(c2), P(want_up))
+    d_c2 = dev(c2)
+    d_up = torch.empty((beta, m, n), dtype=torch.int64, device="cuda")
+    pf.check(pf.lib.pfhe_modup(ctx._h, 1, d_up.data_ptr(), d_c2.data_ptr(), st))
+    assert np.array_equal(host(d_up), want_up), "modup"
+
+    want_cx = np.zeros((2, m, n), dtype=np.uint64)
+    o.orc_inner_prod(oc, l, P(want_up), P(key_h), P(want_cx))
+    for k in range(2):
+        cxk = want_cx[k].copy()
+        want_ct = np.zeros((l, n), dtype=np.uint64)
+        o.orc_moddown_from_ntt(oc, l, P(cxk), P(want_ct))
+        d_one = dev(want_cx[k])
+        d_ct = torch.empty((l, n), dtype=torch.int64, device="cuda")
+        pf.check(pf.lib.pfhe_moddown_from_ntt(ctx._h, 1, d_ct.data_ptr(), d_one.data_ptr(), st))
+        assert np.array_equal(host(d_ct), want_ct), "moddown"
+
+    ct = H.ciphertext(ps, 9)
+    want = ct.copy()
+    o.orc_keyswitch(oc, l, P(want), P(c2), P(key_h))
+    d_ct = dev(ct)
+    pf.check(pf.lib.pfhe_keyswitch_inplace(ctx._h, 1, d_ct.data_ptr(), d_c2.data_ptr(), key.public_keys_ptr(), st))
+    assert np.array_equal(host(d_ct), want), "keyswitch_inplace"
+
+    # rotation (coefficient-domain permutation for BFV)
+    glk = pf.PhantomGaloisKey(ctx, [list(key_h)])
+    want = ct.copy()
+    o.orc_apply_galois(oc, l, P(want), pf.get_elt_from_step(1, n), P(key_h))
+    c = pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=(scheme != 2))
+    pf.rotate_inplace(ctx, c, 1, glk)
+    assert np.array_equal(c.to_host(), want), "rotate"
+
+    # modulus switch with scaling
+    want = np.zeros((2, l - 1, n), dtype=np.uint64)
+    src = ct.copy()
+    (o.orc_divide_round_q_last if scheme == 2 else o.orc_bgv_mod_switch)(oc, l, P(src), 2, P(want))
+    ms = pf.mod_switch_to_next(ctx, pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=(scheme != 2)))
+    assert np.array_equal(ms.to_host(), want), "mod_switch_to_next"
+
+    if scheme == 1:   # BGV HMult + relin = the CKKS path with the BGV mod-down
+        a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
+        want = np.zeros((2, l, n), dtype=np.uint64)
+        o.orc_multiply_relin(oc, l, P(a), P(b), P(key_h), P(want))
+        ca, cb = pf.PhantomCiphertext.from_host(ctx, a), pf.PhantomCiphertext.from_host(ctx, b)
+        pf.multiply_and_relin_inplace(ctx, ca, cb, key)
+        assert np.array_equal(ca.to_host(), want)
+    else:
+        a = pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=False)
+        with pytest.raises(ValueError, match="unsupported scheme"):
+            pf.multiply_and_relin_inplace(ctx, a, a.clone(), key)
+
+
+@pytest.mark.parametrize("scheme", [3, 1])
+def test_hoisting(scheme):
+    ps = H.params_small(4096, l=5, alpha=2, scheme=scheme, t=65537 if scheme == 1 else 0)
+    steps = [1, 2, 3, -1]
+    ctx = make_context(ps, steps)
+    o = H.oracle()
+    l, n = ps.limbs(), ps.n
+    ct = H.ciphertext(ps, 4)
+    keys_h = [H.switch_key(ps, 1000 * (i + 1)) for i in range(len(steps))]
+    glk = pf.PhantomGaloisKey(ctx, [list(k) for k in keys_h])
+    use = [2, 1, -1]   # a subset, in another order
+    elts = (ctypes.c_uint32 * len(use))(*pf.get_elts_from_steps(use, n))
+    kp = (H.u64p * len(use))(*[P(keys_h[steps.index(s)]) for s in use])
+    want = ct.copy()
+    o.orc_hoisting(ps.octx(), l, P(want), elts, len(use), kp)
+    c = pf.PhantomCiphertext.from_host(ctx, ct)
+    pf.hoisting_inplace(ctx, c, glk, use)
+    assert np.array_equal(c.to_host(), want)
+    # property: hoisting over one step == rotate by that step
+    c1 = pf.PhantomCiphertext.from_host(ctx, ct)
+    c2 = pf.PhantomCiphertext.from_host(ctx, ct)
+    pf.hoisting_inplace(ctx, c1, glk, [3])
+    pf.rotate_inplace(ctx, c2, 3, glk)
+    assert np.array_equal(c1.to_host(), c2.to_host())
+    with pytest.raises(RuntimeError, match="Galois key not present in hoisting"):
+        pf.hoisting_inplace(ctx, c1, glk, [7])
 
 
 def test_error_behaviour():
