@@ -670,10 +670,8 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         bl.size_QP = mod_rows_, bl.ni = alpha, bl.xbits = pbits + ceil_log2(alpha);
         ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p;
         int cnt = 0;
-        for (int pass = 0; pass < 2; pass++)
-        for (int k = 0; k < 2; k++)
+        for (int k = 0; k < 2; k++)   // natural slot order: mulc (P^-1 per slot) is indexed by k * l + j
             for (int j = 0; j < l; j++) {
-                if ((!is_fp_[j]) != (pass == 0)) continue;   // integer-path limbs first
                 ll.data[cnt] = ll.src[cnt] = (short) (k * l + j);
                 ll.row[cnt] = (short) j;
                 ll.q[cnt] = primes_[j];
