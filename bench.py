@@ -304,10 +304,16 @@ def main():
         alg_bytes = limbs_ntt * 16 * n
         peak, how = measured_peaks()
         achieved = alg_bytes / (ntt_us * 1e-6) / 1e9
+        traffic = None
+        tpath = os.path.join(ROOT, "profiles", "ntt_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get("dram_bytes_total")
         roof = {"kernel": "forward negacyclic NTT (k_fwd_cols + k_fwd_rows), 64 limb-NTTs of N=2^16",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": how, "traffic": None, "limb_ntt_per_s": limbs_ntt / (ntt_us * 1e-6),
-                "note": "64-bit modular butterflies are IMAD-issue bound on sm_100a (see DESIGN.md, profiles/)"}
+                "peak_source": how, "traffic": traffic, "algorithmic_bytes": alg_bytes,
+                "launch_us": ntt_us, "limb_ntt_per_s": limbs_ntt / (ntt_us * 1e-6),
+                "note": "not HBM-bound: 64-bit modular butterflies are issue/latency bound on sm_100a (DESIGN.md 4.1, profiles/)"}
         if not args.no_cpu_baseline:
             cb = cpu_baseline(ps, a, b, rlk_h)
 

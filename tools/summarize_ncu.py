@@ -53,6 +53,7 @@ def full(path, out):
     txt = subprocess.check_output(["ncu", "-i", path, "--page", "raw", "--csv"], text=True)
     rows = list(csv.reader(txt.splitlines()))
     hdr = rows[0]
+    units = rows[1]
     with open(out, "w") as f:
         f.write(f"# ncu --set full summary ({path})\n\n")
         for r in rows[2:]:
@@ -60,7 +61,7 @@ def full(path, out):
             f.write(f"## `{name[:110]}`\n\n| metric | value |\n|---|---|\n")
             for k in KEYS:
                 if k in hdr:
-                    f.write(f"| {k} | {r[hdr.index(k)]} |\n")
+                    f.write(f"| {k} | {r[hdr.index(k)]} {units[hdr.index(k)]} |\n")
             stalls = []
             for i, h in enumerate(hdr):
                 if "warps_issue_stalled" in h and h.endswith("_per_issue_active.ratio"):
