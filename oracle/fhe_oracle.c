@@ -810,6 +810,212 @@ void orc_hoisting(const orc_ctx *c, int l, u64 *ct, const uint32_t *elts, int n_
 }
 
 /* ------------------------------------------------------------------------------------------------------
+ * BFV multiplication, BEHZ variant (evaluate.cu:404-548, rns.cu:386-570,1249-1517)
+ * ---------------------------------------------------------------------------------------------------- */
+/* get_primes (numth.cu:207-233): NTT-friendly primes of `bits` bits, descending from 2^bits */
+static int get_primes_desc(u64 n, int bits, int count, u64 *out) {
+    u64 factor = 2 * n, value = ((u64)1 << bits) - factor + 1, lower = (u64)1 << (bits - 1);
+    int k = 0;
+    while (k < count && value > lower) {
+        if (orc_is_prime(value)) out[k++] = value;
+        value -= factor;
+    }
+    return k == count ? 0 : -1;
+}
+
+/* bit length of prod(primes) (get_significant_bit_count_uint of base_Q.big_modulus) */
+static int product_bits(const u64 *primes, int cnt) {
+    u64 acc[64];
+    int len = 1;
+    memset(acc, 0, sizeof(acc));
+    acc[0] = 1;
+    for (int i = 0; i < cnt; i++) {
+        u64 carry = 0;
+        for (int k = 0; k < len; k++) {
+            u128 t = (u128)acc[k] * primes[i] + carry;
+            acc[k] = (u64)t;
+            carry = (u64)(t >> 64);
+        }
+        if (carry) acc[len++] = carry;
+    }
+    int bits = 0;
+    u64 top = acc[len - 1];
+    while (top) {
+        bits++;
+        top >>= 1;
+    }
+    return (len - 1) * 64 + bits;
+}
+
+static u64 prod_mod(const u64 *base, int n, u64 p) {
+    u64 r = 1 % p;
+    for (int k = 0; k < n; k++) r = orc_mulmod(r, base[k] % p, p);
+    return r;
+}
+
+int orc_behz_aux(const orc_ctx *c, u64 *bsk, int *nbsk) {
+    int size_Q = c->size_Q, tb = 0;
+    u64 t = c->t;
+    while (t) {
+        tb++;
+        t >>= 1;
+    }
+    int nB = size_Q;
+    if (32 + tb + product_bits(c->primes, size_Q) >= 61 * size_Q + 61) nB++; /* rns.cu:400-406 */
+    u64 pr[66];
+    if (get_primes_desc(c->n, 61, nB + 1, pr)) return -1;
+    /* first prime = m_sk, then B (rns.cu:414-420); Bsk = B followed by m_sk */
+    for (int i = 0; i < nB; i++) bsk[i] = pr[1 + i];
+    bsk[nB] = pr[0];
+    *nbsk = nB + 1;
+    return 0;
+}
+
+/* out[3][size_Q][n] = BEHZ product of two size-2 BFV ciphertexts (coefficient form, top level) */
+int orc_bfv_multiply_behz(const orc_ctx *c, const u64 *ct1, const u64 *ct2, u64 *out) {
+    const size_t n = c->n;
+    const int lq = c->size_Q;
+    const u64 *Q = c->primes, t = c->t, mt = (u64)1 << 32;
+    u64 bsk[66];
+    int nbsk;
+    if (orc_behz_aux(c, bsk, &nbsk)) return -1;
+    const int nB = nbsk - 1;
+    const u64 msk = bsk[nB];
+    orc_ctx *ax = orc_create(ORC_SCHEME_BFV, n, bsk, nbsk, 0, 0); /* NTT tables of Bsk (rns.cu:435-448) */
+    if (!ax) return -1;
+    int idq[64], idb[66];
+    for (int i = 0; i < lq; i++) idq[i] = i;
+    for (int j = 0; j < nbsk; j++) idb[j] = j;
+    const size_t pq = (size_t)lq * n, pb = (size_t)nbsk * n;
+    u64 *eq[2], *eb[2];
+    u64 *y = (u64 *)malloc(pq * 8), *mtl = (u64 *)malloc(n * 8);
+    for (int s = 0; s < 2; s++) {
+        const u64 *ct = s ? ct2 : ct1;
+        eq[s] = (u64 *)malloc((s ? 2 : 3) * pq * 8);
+        eb[s] = (u64 *)malloc((s ? 2 : 3) * pb * 8);
+        for (int p = 0; p < 2; p++) { /* BEHZ_mul_1, evaluate.cu:404-438 */
+            const u64 *x = ct + p * pq;
+            u64 *xq = eq[s] + p * pq, *xb = eb[s] + p * pb;
+            memcpy(xq, x, pq * 8);
+            orc_ntt_forward(c, xq, lq, idq);
+            /* fastbconv_m_tilde (rns.cu:1249-1277): y = x * (m_tilde * qhatinv) mod q */
+            for (int i = 0; i < lq; i++) {
+                u64 k = orc_mulmod(mt % Q[i], orc_invmod(qhat_mod(Q, lq, i, Q[i]), Q[i]), Q[i]);
+                for (size_t j = 0; j < n; j++) y[(size_t)i * n + j] = orc_mulmod(x[(size_t)i * n + j], k, Q[i]);
+            }
+            for (int jb = 0; jb <= nbsk; jb++) {
+                u64 p_out = jb < nbsk ? bsk[jb] : mt;
+                u64 *dst = jb < nbsk ? xb + (size_t)jb * n : mtl;
+                u64 mat[64];
+                for (int i = 0; i < lq; i++) mat[i] = qhat_mod(Q, lq, i, p_out);
+                for (size_t j = 0; j < n; j++) {
+                    u128 acc = 0;
+                    for (int i = 0; i < lq; i++) acc = (acc + (u128)y[(size_t)i * n + j] * mat[i]) % p_out;
+                    dst[j] = (u64)acc;
+                }
+            }
+            /* sm_mrq (rns.cu:1290-1339) */
+            u64 nqi = (mt - orc_invmod(prod_mod(Q, lq, mt), mt)) % mt;
+            for (int jb = 0; jb < nbsk; jb++) {
+                u64 pj = bsk[jb], qmod = prod_mod(Q, lq, pj), imt = orc_invmod(mt % pj, pj);
+                for (size_t j = 0; j < n; j++) {
+                    u64 r = orc_mulmod(mtl[j], nqi, mt);
+                    if (r >= mt >> 1) r += pj - mt;
+                    u64 v = (u64)(((u128)r * qmod + xb[(size_t)jb * n + j]) % pj);
+                    xb[(size_t)jb * n + j] = orc_mulmod(v, imt, pj);
+                }
+            }
+            orc_ntt_forward(ax, xb, nbsk, idb);
+        }
+    }
+    /* step 4: dyadic products in both bases (evaluate.cu:479-500), result into eq[0]/eb[0] (3 polys) */
+    {
+        u64 *dq = (u64 *)malloc(3 * pq * 8), *db = (u64 *)malloc(3 * pb * 8);
+        orc_tensor_2x2(c, eq[0], eq[1], dq, lq);
+        orc_tensor_2x2(ax, eb[0], eb[1], db, nbsk);
+        memcpy(eq[0], dq, 3 * pq * 8);
+        memcpy(eb[0], db, 3 * pb * 8);
+        free(dq);
+        free(db);
+    }
+    /* steps 5-6: inverse NTT and multiplication by t (evaluate.cu:520-531) */
+    for (int p = 0; p < 3; p++) {
+        u64 *xq = eq[0] + p * pq, *xb = eb[0] + p * pb;
+        orc_ntt_inverse(c, xq, lq, idq);
+        orc_ntt_inverse(ax, xb, nbsk, idb);
+        for (int i = 0; i < lq; i++)
+            for (size_t j = 0; j < n; j++) xq[(size_t)i * n + j] = orc_mulmod(xq[(size_t)i * n + j], t % Q[i], Q[i]);
+        for (int i = 0; i < nbsk; i++)
+            for (size_t j = 0; j < n; j++) xb[(size_t)i * n + j] = orc_mulmod(xb[(size_t)i * n + j], t % bsk[i], bsk[i]);
+    }
+    u64 *fl = (u64 *)malloc(pb * 8), *yb = (u64 *)malloc((size_t)nB * n * 8), *alpha = (u64 *)malloc(n * 8);
+    for (int p = 0; p < 3; p++) {
+        u64 *xq = eq[0] + p * pq, *xb = eb[0] + p * pb, *o = out + p * pq;
+        /* step 7 fast_floor (rns.cu:1343-1419): (in_Bsk - FastBconv(in_q, q -> Bsk)) * Q^-1 mod Bsk */
+        for (int i = 0; i < lq; i++) {
+            u64 k = orc_invmod(qhat_mod(Q, lq, i, Q[i]), Q[i]);
+            for (size_t j = 0; j < n; j++) y[(size_t)i * n + j] = orc_mulmod(xq[(size_t)i * n + j], k, Q[i]);
+        }
+        for (int jb = 0; jb < nbsk; jb++) {
+            u64 pj = bsk[jb], qinv = orc_invmod(prod_mod(Q, lq, pj), pj), mat[64];
+            for (int i = 0; i < lq; i++) mat[i] = qhat_mod(Q, lq, i, pj);
+            for (size_t j = 0; j < n; j++) {
+                u128 acc = 0;
+                for (int i = 0; i < lq; i++) acc = (acc + (u128)y[(size_t)i * n + j] * mat[i]) % pj;
+                fl[(size_t)jb * n + j] = orc_mulmod(submod(xb[(size_t)jb * n + j], (u64)acc, pj), qinv, pj);
+            }
+        }
+        /* step 8 fastbconv_sk (rns.cu:1463-1517) */
+        for (int i = 0; i < nB; i++) {
+            u64 k = orc_invmod(qhat_mod(bsk, nB, i, bsk[i]), bsk[i]);
+            for (size_t j = 0; j < n; j++) yb[(size_t)i * n + j] = orc_mulmod(fl[(size_t)i * n + j], k, bsk[i]);
+        }
+        {
+            u64 binv = orc_invmod(prod_mod(bsk, nB, msk), msk), mat[66];
+            for (int i = 0; i < nB; i++) mat[i] = qhat_mod(bsk, nB, i, msk);
+            for (size_t j = 0; j < n; j++) {
+                u128 acc = 0;
+                for (int i = 0; i < nB; i++) acc = (acc + (u128)yb[(size_t)i * n + j] * mat[i]) % msk;
+                alpha[j] = orc_mulmod(submod((u64)acc, fl[(size_t)nB * n + j], msk), binv, msk);
+            }
+        }
+        for (int k = 0; k < lq; k++) {
+            u64 qk = Q[k], Bq = prod_mod(bsk, nB, qk), mat[66];
+            for (int i = 0; i < nB; i++) mat[i] = qhat_mod(bsk, nB, i, qk);
+            for (size_t j = 0; j < n; j++) {
+                u128 acc = 0;
+                for (int i = 0; i < nB; i++) acc = (acc + (u128)yb[(size_t)i * n + j] * mat[i]) % qk;
+                u64 a = alpha[j], corr; /* multiply_and_negated_add_rns_poly, polymath.cu:606-634 */
+                if (a > msk >> 1) corr = orc_mulmod((msk - a) % qk, Bq, qk);
+                else corr = orc_mulmod(a % qk, qk - Bq, qk);
+                o[(size_t)k * n + j] = addmod((u64)acc, corr, qk);
+            }
+        }
+    }
+    free(fl); free(yb); free(alpha); free(y); free(mtl);
+    for (int s = 0; s < 2; s++) {
+        free(eq[s]);
+        free(eb[s]);
+    }
+    orc_destroy(ax);
+    return 0;
+}
+
+/* multiply_inplace + relinearize_inplace for BFV/BEHZ: out[2][size_Q][n] */
+int orc_bfv_multiply_relin_behz(const orc_ctx *c, const u64 *ct1, const u64 *ct2, const u64 *rlk, u64 *out) {
+    size_t poly = (size_t)c->size_Q * c->n;
+    u64 *d = (u64 *)malloc(3 * poly * 8);
+    if (orc_bfv_multiply_behz(c, ct1, ct2, d)) {
+        free(d);
+        return -1;
+    }
+    orc_keyswitch(c, c->size_Q, d, d + 2 * poly, rlk);
+    memcpy(out, d, 2 * poly * 8);
+    free(d);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------
  * rescale / mod switch
  * ---------------------------------------------------------------------------------------------------- */
 void orc_rescale(const orc_ctx *c, int l, u64 *in, int size, u64 *out) {

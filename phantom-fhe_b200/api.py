@@ -23,6 +23,14 @@ class scheme_type(enum.IntEnum):  # host/encryptionparams.h:14-22
     ckks = 3
 
 
+class mul_tech_type(enum.IntEnum):  # host/encryptionparams.h:25-35
+    none = 0
+    behz = 1
+    hps = 2
+    hps_overq = 3
+    hps_overq_leveled = 4
+
+
 def _stream():
     return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
@@ -62,6 +70,15 @@ class EncryptionParameters:
         self.special_modulus_size = 1  # reference default, encryptionparams.h:235
         self.galois_elts = []
         self.plain_modulus = 0
+        # reference default for BFV is HPS (encryptionparams.h:41-47)
+        self.mul_tech = mul_tech_type.hps if self.scheme == scheme_type.bfv else mul_tech_type.none
+
+    def set_mul_tech(self, mul_tech):
+        if self.scheme != scheme_type.bfv:
+            raise ValueError("mul_tech selection is only supported for BFV")
+        if mul_tech_type(mul_tech) == mul_tech_type.none:
+            raise ValueError("unsupported multiplication technique for BFV")
+        self.mul_tech = mul_tech_type(mul_tech)
 
     def set_poly_modulus_degree(self, n):
         if self.scheme == scheme_type.none and n:
@@ -197,9 +214,9 @@ def _require_ntt(context, ct):
 
 
 def multiply_inplace(context, encrypted1, encrypted2):
-    """multiply_inplace (src/evaluate.cu:1029-1057 -> bgv_ckks_multiply :345-397)."""
-    if not (encrypted1.is_ntt_form and encrypted2.is_ntt_form):
-        raise ValueError("encrypted1 and encrypted2 must be in NTT form")
+    """multiply_inplace (src/evaluate.cu:1029-1057 -> bgv_ckks_multiply :345-397, bfv_multiply_behz :451-548)."""
+    _require_ntt(context, encrypted1)
+    _require_ntt(context, encrypted2)
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
     if encrypted1.size() != 2 or encrypted2.size() != 2:
@@ -207,6 +224,8 @@ def multiply_inplace(context, encrypted1, encrypted2):
     l, n = encrypted1.coeff_modulus_size(), context.poly_degree
     dst = torch.empty((3, l, n), dtype=torch.int64, device=encrypted1.data.device)
     a, b = encrypted1.data, encrypted2.data
+    if context.scheme == scheme_type.bfv and context.parms.mul_tech != mul_tech_type.behz:
+        raise ValueError("unsupported scheme: only mul_tech_type.behz is built for BFV")
     check(lib.pfhe_multiply(context._h, encrypted1.chain_index, _ptr(a), _ptr(a if encrypted1 is encrypted2 else b),
                             _ptr(dst), _stream()))
     encrypted1.data = dst
@@ -226,10 +245,12 @@ def relinearize_inplace(context, encrypted, relin_keys):
 
 def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
     """multiply_and_relin_inplace (src/evaluate.cu:1061-1104), fused tensor + key-switch."""
-    if context.scheme != scheme_type.bfv and not (encrypted1.is_ntt_form and encrypted2.is_ntt_form):
-        raise ValueError("encrypted1 and encrypted2 must be in NTT form")
+    _require_ntt(context, encrypted1)
+    _require_ntt(context, encrypted2)
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+    if context.scheme == scheme_type.bfv and context.parms.mul_tech != mul_tech_type.behz:
+        raise ValueError("unsupported scheme: only mul_tech_type.behz is built for BFV")
     dst = torch.empty_like(encrypted1.data)
     check(lib.pfhe_multiply_and_relin(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
                                       _ptr(encrypted2.data), _ptr(dst), relin_keys.public_keys_ptr(), _stream()))

@@ -1,0 +1,117 @@
+// behz_kernels.cuh -- the two per-coefficient kernels of the BEHZ BFV multiplication.
+//
+// Every step of BEHZ between the NTTs is coefficient-local: all residues of one coefficient are combined with
+// small constant matrices.  Two kernels cover them:
+//   k_behz_lift      fastbconv_m_tilde + sm_mrq  (reference rns.cu:1249-1339): q -> Bsk with the m_tilde correction
+//   k_behz_floor_sk  fast_floor + fastbconv_sk   (reference rns.cu:1343-1517, polymath.cu:596-634): Bsk -> q
+// One thread owns one coefficient; its residues live in a thread-local array, the matrices are warp-uniform
+// read-only loads.  The auxiliary base is 61-bit, so this is integer-pipe work (128-bit accumulate, one Barrett
+// reduction per output residue) -- the same arithmetic as the reference's base-conversion kernels.
+#pragma once
+#include "modarith.cuh"
+
+namespace pfhe {
+
+constexpr int BEHZ_MAX_LIMBS = 64;   // q limbs and Bsk limbs per coefficient (thread-local array size)
+constexpr int BEHZ_THREADS = 128;
+
+struct BehzLiftArgs {
+    const u64 *ct1, *ct2;   // [2][l][n] each, coefficient form
+    u64 *out;               // [4][nbsk][n]: Bsk residues of ct1.c0, ct1.c1, ct2.c0, ct2.c1
+    const Tw *k;            // [l]  m_tilde * qhat_i^-1 mod q_i
+    const u64 *mat;         // [nbsk][l]  qhat_i mod Bsk_j
+    const u32 *mat_mt;      // [l]  qhat_i mod m_tilde
+    const u64 *q_mod_bsk;   // [nbsk]
+    const Tw *inv_mt;       // [nbsk]
+    const Modulus *mod_q, *mod_bsk;
+    u32 neg_inv_q;
+    int l, nbsk;
+    size_t n;
+};
+
+__global__ void __launch_bounds__(BEHZ_THREADS) k_behz_lift(const BehzLiftArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int poly = blockIdx.y;
+    const size_t x = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 *src = (poly < 2 ? a.ct1 : a.ct2) + (size_t) (poly & 1) * a.l * a.n + x;
+    u64 y[BEHZ_MAX_LIMBS];
+    u32 mt = 0;
+    for (int i = 0; i < a.l; i++) {
+        y[i] = mul_shoup(src[(size_t) i * a.n], a.k[i], a.mod_q[i].q);
+        mt += (u32) y[i] * a.mat_mt[i];   // m_tilde = 2^32: the reduction is the wrap-around
+    }
+    // sm_mrq: r = mt * (-Q^-1) mod m_tilde, centred
+    const u32 r = mt * a.neg_inv_q;
+    u64 *dst = a.out + (size_t) poly * a.nbsk * a.n + x;
+    for (int j = 0; j < a.nbsk; j++) {
+        const Modulus m = a.mod_bsk[j];
+        Acc128 acc{0, 0};
+        const u64 *row = a.mat + (size_t) j * a.l;
+        for (int i = 0; i < a.l; i++) acc.mac(y[i], row[i]);
+        const u64 rr = (r >> 31) ? (u64) r + m.q - ((u64) 1 << 32) : (u64) r;
+        acc.mac(rr, a.q_mod_bsk[j]);
+        const u64 v = barrett128(acc.lo, acc.hi, m);
+        dst[(size_t) j * a.n] = mul_shoup(v, a.inv_mt[j], m.q);
+    }
+}
+
+struct BehzFloorArgs {
+    const u64 *xq;          // [3][l][n]     t * tensor result, base q, coefficient form
+    const u64 *xb;          // [3][nbsk][n]  the same in Bsk = [m_sk, B...]
+    u64 *out;               // [3][l][n]
+    const Tw *q_hinv;       // [l]
+    const u64 *q_to_bsk;    // [nbsk][l]
+    const Tw *inv_q_bsk;    // [nbsk]
+    const Tw *b_hinv;       // [nB]
+    const u64 *b_to_q;      // [l][nB]
+    const u64 *b_to_msk;    // [nB]
+    const u64 *B_mod_q;     // [l]
+    Tw inv_B_msk;
+    const Modulus *mod_q, *mod_bsk;
+    int l, nbsk;
+    size_t n;
+};
+
+__global__ void __launch_bounds__(BEHZ_THREADS) k_behz_floor_sk(const BehzFloorArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int poly = blockIdx.y;
+    const size_t x = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 *sq = a.xq + (size_t) poly * a.l * a.n + x;
+    const u64 *sb = a.xb + (size_t) poly * a.nbsk * a.n + x;
+    u64 y[BEHZ_MAX_LIMBS], fl[BEHZ_MAX_LIMBS];
+    // fast_floor: fl_j = (xb_j - FastBconv(xq)_j) * Q^-1 mod Bsk_j
+    for (int i = 0; i < a.l; i++) y[i] = mul_shoup(sq[(size_t) i * a.n], a.q_hinv[i], a.mod_q[i].q);
+    for (int j = 0; j < a.nbsk; j++) {
+        const Modulus m = a.mod_bsk[j];
+        Acc128 acc{0, 0};
+        const u64 *row = a.q_to_bsk + (size_t) j * a.l;
+        for (int i = 0; i < a.l; i++) acc.mac(y[i], row[i]);
+        const u64 v = barrett128(acc.lo, acc.hi, m);
+        fl[j] = mul_shoup(sub_mod(sb[(size_t) j * a.n], v, m.q), a.inv_q_bsk[j], m.q);
+    }
+    // fastbconv_sk: Shenoy-Kumaresan conversion B -> q with alpha_sk from the m_sk residue
+    const int nB = a.nbsk - 1;
+    const Modulus msk = a.mod_bsk[0];
+    Acc128 am{0, 0};
+    for (int i = 0; i < nB; i++) {
+        y[i] = mul_shoup(fl[i + 1], a.b_hinv[i], a.mod_bsk[i + 1].q);
+        am.mac(y[i], a.b_to_msk[i]);
+    }
+    const u64 alpha = mul_shoup(sub_mod(barrett128(am.lo, am.hi, msk), fl[0], msk.q), a.inv_B_msk, msk.q);
+    const bool neg = alpha > (msk.q >> 1);
+    u64 *dst = a.out + (size_t) poly * a.l * a.n + x;
+    for (int k = 0; k < a.l; k++) {
+        const Modulus m = a.mod_q[k];
+        Acc128 acc{0, 0};
+        const u64 *row = a.b_to_q + (size_t) k * nB;
+        for (int i = 0; i < nB; i++) acc.mac(y[i], row[i]);
+        const u64 v = barrett128(acc.lo, acc.hi, m);
+        const u64 Bq = a.B_mod_q[k];
+        const u64 corr = neg ? mul_mod(msk.q - alpha, Bq, m) : mul_mod(alpha, m.q - Bq, m);
+        dst[(size_t) k * a.n] = add_mod(v, corr, m.q);
+    }
+}
+
+} // namespace pfhe

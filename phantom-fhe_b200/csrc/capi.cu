@@ -49,9 +49,6 @@ static const u64 *const *K(const uint64_t *const *p) { return reinterpret_cast<c
 static void require(bool ok, const char *msg) {
     if (!ok) throw std::invalid_argument(msg);
 }
-static void require_ckks_like(const Engine &e) {
-    if (e.scheme() == Scheme::bfv) throw std::invalid_argument("unsupported scheme");   // BFV path: see DESIGN.md
-}
 
 extern "C" {
 
@@ -237,7 +234,6 @@ int pfhe_keyswitch_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypt
 int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct1, const uint64_t *ct2,
                                     const uint64_t *const *rlk, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     e->impl.multiply_relin(l, U(ct1), U(ct1), U(ct2), K(rlk), S(stream));
     API_END
@@ -245,7 +241,6 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2,
                             uint64_t *dst, const uint64_t *const *rlk, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     e->impl.multiply_relin(l, U(dst), U(ct1), U(ct2), K(rlk), S(stream));
     API_END
@@ -253,8 +248,12 @@ int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *
 int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, uint64_t *dst,
                   void *stream) {
     API_BEGIN
-    require(e->impl.scheme() != Scheme::bfv, "BFV multiplication (BEHZ/HPS) is not on this engine yet: unsupported scheme");
     const int l = e->impl.limbs_at(chain_index);
+    if (e->impl.scheme() == Scheme::bfv) {   // mul_tech_type::behz (evaluate.cu:451-548)
+        require(dst != ct1 && dst != ct2, "destination aliases an operand");
+        e->impl.bfv_multiply_behz(l, U(dst), U(ct1), U(ct2), S(stream));
+        return PFHE_OK;
+    }
     if (ct1 == ct2) e->impl.tensor_square(U(ct1), U(dst), l, S(stream));
     else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
     API_END
@@ -318,7 +317,6 @@ int pfhe_mod_switch_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *
 int pfhe_multiply_and_relin_host(pfhe_engine *e, size_t chain_index, const uint64_t *h1, const uint64_t *h2,
                                  uint64_t *hout, const uint64_t *const *rlk, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     const size_t words = (size_t) 2 * l * e->impl.n();
     auto &io = e->impl.host_io(2 * words);
@@ -332,7 +330,6 @@ int pfhe_multiply_and_relin_host_batch(pfhe_engine *e, size_t chain_index, const
                                        const uint64_t *const *h2, uint64_t *const *hout, size_t count,
                                        const uint64_t *const *rlk, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     require(h1 && h2 && hout, "null batch pointers");
     const int l = e->impl.limbs_at(chain_index);
     e->impl.multiply_relin_host_batch(l, reinterpret_cast<const u64 *const *>(h1),
@@ -343,7 +340,6 @@ int pfhe_multiply_and_relin_host_batch(pfhe_engine *e, size_t chain_index, const
 int pfhe_rotate_host(pfhe_engine *e, size_t chain_index, const uint64_t *h, int step, uint64_t *hout,
                      const uint64_t *const *glk, void *stream) {
     API_BEGIN
-    require_ckks_like(e->impl);
     const int l = e->impl.limbs_at(chain_index);
     const size_t words = (size_t) 2 * l * e->impl.n();
     uint32_t elt = 0;

@@ -10,6 +10,7 @@
 #include "hostmath.hpp"
 #include "launch.hpp"
 #include "poly_kernels.cuh"
+#include "behz_kernels.cuh"
 
 namespace pfhe {
 
@@ -75,6 +76,7 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
     }
     build_tables();
     levels_.resize(size_Q_ + 1);
+    behz_.resize(size_Q_ + 1);
 
     // workspace sized for the top level
     const size_t alpha = std::max(size_P_, 1);
@@ -111,7 +113,7 @@ Engine::~Engine() {
 }
 
 Tw Engine::make_tw_row(int row, u64 w) const {
-    const u64 q = primes_[row];
+    const u64 q = rowq_[row];
     if (!is_fp_[row]) return make_tw(w, q);
     const double dw = (double) w, dq = (double) q;
     const double winv = dw / dq;
@@ -126,30 +128,48 @@ void Engine::build_tables() {
     // forces the integer path everywhere (A/B measurements).
     const char *env = std::getenv("PFHE_FP64_NTT");
     const bool allow_fp = !(env && env[0] == '0');
-    mod_rows_ = size_QP_ + (t_ > 1 ? 1 : 0);
+    rowq_ = primes_;
+    if (t_ > 1) rowq_.push_back(t_);
+    row_aux_ = (int) rowq_.size();
+    if (scheme_ == Scheme::bfv && t_ > 1) {
+        // BEHZ auxiliary base (rns.cu:400-420): 61-bit primes downwards from 2^61, the first is m_sk, the next
+        // base_B_size(l) of them are B at level l
+        int tb = 64 - __builtin_clzll(t_), nB_max = 0;
+        for (int l = 1; l <= size_Q_; l++) {
+            std::vector<u64> ql(primes_.begin(), primes_.begin() + l);
+            const int nB = l + ((32 + tb + hm::product_bits(ql) >= 61 * l + 61) ? 1 : 0);
+            nB_max = std::max(nB_max, nB);
+        }
+        naux_ = nB_max + 1;
+        auto aux = hm::create_primes(n_, std::vector<int>(naux_, 61));
+        std::reverse(aux.begin(), aux.end());   // descending, as get_primes returns them
+        for (u64 p : aux) {
+            if (std::find(primes_.begin(), primes_.end(), p) != primes_.end())
+                throw std::invalid_argument("coeff_modulus collides with the BEHZ auxiliary base");
+            rowq_.push_back(p);
+        }
+    }
+    mod_rows_ = (int) rowq_.size();
     is_fp_.assign(mod_rows_, 0);
     std::vector<double2> fpc(mod_rows_);
-    for (int i = 0; i < size_QP_; i++) {
-        is_fp_[i] = allow_fp && (primes_[i] >> 46) == 0;
-        fpc[i] = make_double2((double) primes_[i], 1.0 / (double) primes_[i]);
+    for (int i = 0; i < mod_rows_; i++) {
+        is_fp_[i] = i < size_QP_ && allow_fp && (rowq_[i] >> 46) == 0;   // t and the auxiliary rows: integer path
+        fpc[i] = make_double2((double) rowq_[i], 1.0 / (double) rowq_[i]);
     }
-    if (t_ > 1) fpc[size_QP_] = make_double2((double) t_, 1.0 / (double) t_);   // integer path for the t row
     for (int i = 0; i < size_QP_ && i < 128; i++)
         if (is_fp_[i]) fp_mask_[i >> 6] |= 1ull << (i & 63);
     d_is_fp_.upload(is_fp_);
     d_fpc_.upload(fpc);
-    std::vector<Tw> tw((size_t) size_QP_ * n_), itw((size_t) size_QP_ * n_), fin((size_t) size_QP_ * 2);
+    // twiddle rows exist for every table row; the row of t (no NTT) stays zero
+    std::vector<Tw> tw((size_t) mod_rows_ * n_), itw((size_t) mod_rows_ * n_), fin((size_t) mod_rows_ * 2);
     std::vector<Modulus> mods(mod_rows_);
-    if (t_ > 1) {
-        const auto rt = hm::barrett_ratio(t_);
-        mods[size_QP_] = Modulus{t_, rt.lo, rt.hi};
-    }
-    h_ninv_.resize(size_QP_);
-    h_itw1_.resize(size_QP_);
-    for (int i = 0; i < size_QP_; i++) {
-        const u64 q = primes_[i];
+    h_ninv_.assign(mod_rows_, 0);
+    h_itw1_.assign(mod_rows_, 0);
+    for (int i = 0; i < mod_rows_; i++) {
+        const u64 q = rowq_[i];
         const auto ratio = hm::barrett_ratio(q);
         mods[i] = Modulus{q, ratio.lo, ratio.hi};
+        if (t_ > 1 && i == size_QP_) continue;
         const u64 psi = hm::minimal_primitive_root(2 * n_, q);
         const u64 ipsi = hm::invmod(psi, q);
         Tw *f = tw.data() + (size_t) i * n_, *b = itw.data() + (size_t) i * n_;
@@ -237,7 +257,7 @@ void Engine::build_level(int l) {
         for (int d = 0; d < lv->beta; d++) {
             const int start = alpha * d;
             const int size = d == lv->beta - 1 ? l - alpha * (lv->beta - 1) : alpha;
-            std::vector<u64> ibase(primes_.begin() + start, primes_.begin() + start + size);
+            std::vector<u64> ibase(rowq_.begin() + start, rowq_.begin() + start + size);
             for (int i = 0; i < size; i++) {
                 const u64 q = ibase[i];
                 const u64 hinv = hm::invmod(hm::product_mod(ibase, i, q), q);
@@ -254,9 +274,9 @@ void Engine::build_level(int l) {
                 if (j >= start && j < start + size) continue;
                 const int row = row_of(j);
                 for (int i = 0; i < size; i++) {
-                    const u64 M = hm::product_mod(ibase, i, primes_[row]);
+                    const u64 M = hm::product_mod(ibase, i, rowq_[row]);
                     mat.push_back(M);
-                    push_matf(matf, M, primes_[row]);
+                    push_matf(matf, M, rowq_[row]);
                 }
                 omod.push_back((short) row);
                 olimb.push_back((short) j);
@@ -278,7 +298,7 @@ void Engine::build_level(int l) {
         lv->modup_ntt_data = ntt_conv.data, lv->modup_ntt_row = ntt_conv.row;
 
         // mod-down
-        std::vector<u64> pbase(primes_.begin() + size_Q_, primes_.end());
+        std::vector<u64> pbase(rowq_.begin() + size_Q_, rowq_.begin() + size_QP_);
         std::vector<Tw> dfin((size_t) 2 * alpha * 2);
         for (int k = 0; k < 2; k++)
             for (int i = 0; i < alpha; i++) {
@@ -295,7 +315,7 @@ void Engine::build_level(int l) {
         std::vector<short> dmod(l), dlimb(l);
         std::vector<Tw> pinv((size_t) 2 * l);
         for (int j = 0; j < l; j++) {
-            const u64 q = primes_[j];
+            const u64 q = rowq_[j];
             for (int i = 0; i < alpha; i++) {
                 dmat[(size_t) j * alpha + i] = hm::product_mod(pbase, i, q);
                 push_matf(dmatf, dmat[(size_t) j * alpha + i], q);
@@ -309,7 +329,7 @@ void Engine::build_level(int l) {
             for (int k = 0; k < 2; k++)
                 for (int j = 0; j < lv->m; j++) {
                     const int row = row_of(j);
-                    const u64 q = primes_[row];
+                    const u64 q = rowq_[row];
                     u64 c = h_ninv_[row];
                     if (j >= l) c = hm::mulmod(c, hm::invmod(hm::product_mod(pbase, j - l, q), q), q);
                     fall[2 * ((size_t) k * lv->m + j)] = make_tw_row(row, c);
@@ -319,7 +339,7 @@ void Engine::build_level(int l) {
         }
         {
             std::vector<Tw> pmq(l);
-            for (int j = 0; j < l; j++) pmq[j] = make_tw(hm::product_mod(pbase, -1, primes_[j]), primes_[j]);
+            for (int j = 0; j < l; j++) pmq[j] = make_tw(hm::product_mod(pbase, -1, rowq_[j]), rowq_[j]);
             lv->P_mod_q.upload(pmq);
         }
         if (t_ > 1) {
@@ -327,7 +347,7 @@ void Engine::build_level(int l) {
             std::vector<double2> tmf;
             std::vector<short> tomod, tolimb;
             for (int j = 0; j <= l; j++) {
-                const u64 q = j < l ? primes_[j] : t_;
+                const u64 q = j < l ? rowq_[j] : t_;
                 for (int i = 0; i < alpha; i++) {
                     const u64 M = hm::product_mod(pbase, i, q);
                     tm.push_back(M);
@@ -351,13 +371,13 @@ void Engine::build_level(int l) {
     }
     if (l >= 2) {
         std::vector<Tw> qli((size_t) 3 * (l - 1));
-        const u64 qlast = primes_[l - 1];
+        const u64 qlast = rowq_[l - 1];
         for (int j = 0; j < l - 1; j++)
             qli[j] = qli[(l - 1) + j] = qli[2 * (l - 1) + j] =
-                    make_tw(hm::invmod(qlast % primes_[j], primes_[j]), primes_[j]);
+                    make_tw(hm::invmod(qlast % rowq_[j], rowq_[j]), rowq_[j]);
         lv->qlast_inv_slots.upload(qli);
         std::vector<Tw> qlm(l - 1);
-        for (int j = 0; j < l - 1; j++) qlm[j] = make_tw(qlast % primes_[j], primes_[j]);
+        for (int j = 0; j < l - 1; j++) qlm[j] = make_tw(qlast % rowq_[j], rowq_[j]);
         lv->qlast_mod_q.upload(qlm);
         if (t_ > 1 && std::gcd(qlast % t_, t_) == 1) lv->inv_qlast_t = make_tw(hm::invmod(qlast % t_, t_), t_);
     }
@@ -396,20 +416,20 @@ static void run_chunks(const LimbVec &v, const std::vector<u64> &primes,
 void Engine::ntt_fwd_rows_range(u64 *inout, int count, int start_row, cudaStream_t st) const {
     LimbVec v;
     for (int i = 0; i < count; i++) v.push(i, start_row + i);
-    run_chunks(v, primes_, [&](const LimbList &ll, size_t) { ntt_fwd_list(inout, inout, ll, st); });
+    run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_fwd_list(inout, inout, ll, st); });
 }
 
 void Engine::ntt_inv_rows_range(u64 *dst, const u64 *src, int count, int start_row, cudaStream_t st) const {
     LimbVec v;
     for (int i = 0; i < count; i++) v.push(i, start_row + i);
-    run_chunks(v, primes_, [&](const LimbList &ll, size_t) { ntt_inv_list(dst, src, ll, nullptr, 0, st); });
+    run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_inv_list(dst, src, ll, nullptr, 0, st); });
 }
 
 void Engine::ntt_batch(u64 *inout, int n_poly, int count, int start_row, bool inverse, cudaStream_t st) const {
     LimbVec v;
     for (int p = 0; p < n_poly; p++)
         for (int i = 0; i < count; i++) v.push(p * count + i, start_row + i);
-    run_chunks(v, primes_, [&](const LimbList &ll, size_t) {
+    run_chunks(v, rowq_, [&](const LimbList &ll, size_t) {
         if (inverse) ntt_inv_list(inout, inout, ll, nullptr, 0, st);
         else ntt_fwd_list(inout, inout, ll, st);
     });
@@ -421,7 +441,7 @@ void Engine::ntt_special_range(u64 *inout, int count, int start, int size_Ql, bo
         const int t = start + i;
         v.push(t, t < size_Ql ? t : size_Q_ + (t - size_Ql));
     }
-    run_chunks(v, primes_, [&](const LimbList &ll, size_t) {
+    run_chunks(v, rowq_, [&](const LimbList &ll, size_t) {
         if (inverse) ntt_inv_list(inout, inout, ll, nullptr, 0, st);
         else ntt_fwd_list(inout, inout, ll, st);
     });
@@ -477,7 +497,7 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
         // 1. inverse NTT fused with the n^-1 * qhat_i^-1 scaling (iNTT+scale, rns_bconv.cu:558)
         LimbVec v;
         for (int i = 0; i < l; i++) v.push(i, i);
-        run_chunks(v, primes_, [&](const LimbList &ll, size_t b) { ntt_inv_list(t_cks, cks, ll, lv.modup_fin.p + 2 * b, 1, st); });
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t b) { ntt_inv_list(t_cks, cks, ll, lv.modup_fin.p + 2 * b, 1, st); });
     } else {
         // BFV: cks is already in coefficient form, only the qhat_i^-1 scaling (bconv_mult_kernel, :598)
         dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
@@ -498,7 +518,7 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
             size_t moff = 0;
             for (int e = 0; e < d; e++) moff += (size_t) lv.digit_no[e] * lv.digit_size[e];
             int kin = 0;
-            for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(primes_[start + i]));
+            for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(rowq_[start + i]));
             batch.job[jobs] = BconvJob{t_cks + (size_t) start * n_, dst, lv.modup_mat.p + moff, lv.modup_omod.p + off,
                                        lv.modup_olimb.p + off, ni, lv.digit_no[d], kin + ceil_log2(ni),
                                        lv.modup_matf.p + 2 * moff, lv.digit_big[d]};
@@ -516,7 +536,7 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
             for (int d = 0; d < lv.beta; d++)
                 for (int j = 0; j < lv.m; j++) v.push(d * lv.m + j, j < l ? j : size_Q_ + (j - l));
         }
-        run_chunks(v, primes_, [&](const LimbList &ll, size_t) { ntt_fwd_list(t_mod_up, t_mod_up, ll, st); });
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_fwd_list(t_mod_up, t_mod_up, ll, st); });
     }
 }
 
@@ -545,12 +565,12 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
         LimbVec v;
         for (int k = 0; k < npoly; k++)
             for (int i = 0; i < alpha; i++) v.push(k * m + l + i, size_Q_ + i);
-        ntt_inv_list(cx, cx, single_list(v, primes_), lv.moddown_fin.p, 1, st);
+        ntt_inv_list(cx, cx, single_list(v, rowq_), lv.moddown_fin.p, 1, st);
     }
     // 2. P -> Ql conversion (bConv_BEHZ matmul :143-168 / single-P :691-707)
     {
         int pbits = 0;
-        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(primes_[size_Q_ + i]));
+        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(rowq_[size_Q_ + i]));
         BconvBatch batch{};
         for (int k = 0; k < npoly; k++)
             batch.job[k] = BconvJob{cx + ((size_t) k * m + l) * n_, delta + (size_t) k * l * n_, lv.moddown_mat.p,
@@ -563,7 +583,7 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
         LimbVec v;
         for (int k = 0; k < npoly; k++)
             for (int j = 0; j < l; j++) v.push(k * l + j, j);
-        run_chunks(v, primes_, [&](const LimbList &ll, size_t b) {
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t b) {
             EpiArgs ea{};
             ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p + b;
             for (int s = 0; s < ll.count; s++) {
@@ -605,7 +625,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
     {
         LimbVec v;
         for (int i = 0; i < l; i++) v.push(i, i);
-        const LimbList ll = single_list(v, primes_);
+        const LimbList ll = single_list(v, rowq_);
         g_launches.fetch_add(2, std::memory_order_relaxed);
         if (ts) PFHE_CUDA(ntt_inverse_mul(plan_, t_cks, *ts, bar(1, 0), ll, lv.modup_fin.p, 1, st));
         else PFHE_CUDA(ntt_inverse(plan_, t_cks, c2, ll, lv.modup_fin.p, 1, st));
@@ -626,7 +646,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         for (int pass = 0; pass < 2; pass++)
             for (int d = d0; d < d1; d++) {
                 const int start = lv.digit_start[d];
-                for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(primes_[start + i]));
+                for (int i = 0; i < ni; i++) kin = std::max(kin, 64 - __builtin_clzll(rowq_[start + i]));
                 int jo = 0;
                 for (int j = 0; j < m; j++) {
                     if (j >= start && j < start + ni) continue;
@@ -635,7 +655,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
                     if (slow == (pass == 0)) {
                         ll.data[cnt] = ll.src[cnt] = (short) (d * m + j);
                         ll.row[cnt] = (short) row;
-                        ll.q[cnt] = primes_[row];
+                        ll.q[cnt] = rowq_[row];
                         bl.in_limb[cnt] = (short) start;
                         bl.mat_row[cnt] = (short) (lv.digit_off[d] - lv.digit_off[d0] + jo);
                         bl.in_big[cnt] = (unsigned char) lv.digit_big[d];
@@ -657,7 +677,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         LimbVec v;
         for (int k = 0; k < 2; k++)
             for (int i = 0; i < alpha; i++) v.push(k * m + l + i, size_Q_ + i);
-        ntt_inv_list(cx, cx, single_list(v, primes_), lv.moddown_fin.p, 1, st);
+        ntt_inv_list(cx, cx, single_list(v, rowq_), lv.moddown_fin.p, 1, st);
     }
     // 5. mod-down: convert P -> q_j, forward NTT, (cx - delta) * P^-1 + addend
     {
@@ -665,7 +685,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         BconvLoad bl{};
         EpiArgs ea{};
         int pbits = 0;
-        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(primes_[size_Q_ + i]));
+        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(rowq_[size_Q_ + i]));
         bl.in_base = cx, bl.mat = lv.moddown_mat.p, bl.matf = lv.moddown_matf.p, bl.bar = d_bar_.p;
         bl.size_QP = mod_rows_, bl.ni = alpha, bl.xbits = pbits + ceil_log2(alpha);
         ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p;
@@ -674,7 +694,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
             for (int j = 0; j < l; j++) {
                 ll.data[cnt] = ll.src[cnt] = (short) (k * l + j);
                 ll.row[cnt] = (short) j;
-                ll.q[cnt] = primes_[j];
+                ll.q[cnt] = rowq_[j];
                 bl.in_limb[cnt] = (short) (k * m + l);
                 bl.mat_row[cnt] = (short) j;
                 bl.in_big[cnt] = (unsigned char) lv.moddown_big;
@@ -712,14 +732,14 @@ void Engine::moddown_generic(int l, u64 *out, u64 *cx, int npoly, const u64 *add
         LimbVec v;
         for (int k = 0; k < npoly; k++)
             for (int j = 0; j < m; j++) v.push(k * m + j, j < l ? j : size_Q_ + (j - l));
-        run_chunks(v, primes_, [&](const LimbList &ll, size_t b) { ntt_inv_list(cx, cx, ll, lv.moddown_fin_all.p + 2 * b, 1, st); });
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t b) { ntt_inv_list(cx, cx, ll, lv.moddown_fin_all.p + 2 * b, 1, st); });
     }
     // 2. P -> Ql (and, BGV, P -> t) conversion
     u64 *delta = ws_.delta.p;
     const int no = bgv ? l + 1 : l;
     {
         int pbits = 0;
-        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(primes_[size_Q_ + i]));
+        for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(rowq_[size_Q_ + i]));
         BconvBatch batch{};
         for (int k = 0; k < npoly; k++) {
             if (bgv)
@@ -786,10 +806,138 @@ void Engine::galois_coeff(u64 *dst, const u64 *src, uint32_t elt, int l, int npo
     check_launch("k_galois_coeff");
 }
 
-// multiply_inplace + relinearize_inplace for CKKS/BGV (reference src/evaluate.cu:345-397,1342-1374)
+// ---------------------------------------------------------------------------------------------------
+// BFV multiplication, BEHZ variant
+// ---------------------------------------------------------------------------------------------------
+const Behz &Engine::behz(int l) {
+    if (scheme_ != Scheme::bfv || naux_ == 0) throw std::invalid_argument("unsupported scheme");
+    if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
+    if (behz_[l]) return *behz_[l];
+    auto b = std::make_unique<Behz>();
+    const std::vector<u64> Q(primes_.begin(), primes_.begin() + l);
+    const int tb = 64 - __builtin_clzll(t_);
+    const int nB = l + ((32 + tb + hm::product_bits(Q) >= 61 * l + 61) ? 1 : 0);   // rns.cu:400-406
+    const int nbsk = nB + 1;
+    if (nbsk > naux_ || nbsk > BEHZ_MAX_LIMBS || l > BEHZ_MAX_LIMBS) throw std::logic_error("BEHZ base too large");
+    b->l = l, b->nB = nB, b->nbsk = nbsk;
+    const u64 msk = rowq_[row_aux_];
+    const std::vector<u64> B(rowq_.begin() + row_aux_ + 1, rowq_.begin() + row_aux_ + 1 + nB);
+    const u64 mt = (u64) 1 << 32;
+    auto bsk = [&](int j) { return rowq_[row_aux_ + j]; };   // [m_sk, B_0, ...]
+
+    std::vector<Tw> q_mt_hinv(l), q_hinv(l);
+    std::vector<u32> q_to_mt(l);
+    for (int i = 0; i < l; i++) {
+        const u64 q = Q[i], hinv = hm::invmod(hm::product_mod(Q, i, q), q);
+        q_hinv[i] = make_tw(hinv, q);
+        q_mt_hinv[i] = make_tw(hm::mulmod(mt % q, hinv, q), q);
+        q_to_mt[i] = (u32) hm::product_mod(Q, i, mt);
+    }
+    std::vector<u64> q_to_bsk((size_t) nbsk * l), q_mod_bsk(nbsk);
+    std::vector<Tw> inv_mt(nbsk), inv_q(nbsk);
+    for (int j = 0; j < nbsk; j++) {
+        const u64 p = bsk(j);
+        for (int i = 0; i < l; i++) q_to_bsk[(size_t) j * l + i] = hm::product_mod(Q, i, p);
+        q_mod_bsk[j] = hm::product_mod(Q, -1, p);
+        inv_mt[j] = make_tw(hm::invmod(mt % p, p), p);
+        inv_q[j] = make_tw(hm::invmod(q_mod_bsk[j], p), p);
+    }
+    b->neg_inv_q_mt = (u32) ((mt - hm::invmod(hm::product_mod(Q, -1, mt), mt)) % mt);
+    std::vector<Tw> b_hinv(nB);
+    std::vector<u64> b_to_q((size_t) l * nB), b_to_msk(nB), B_mod_q(l);
+    for (int i = 0; i < nB; i++) {
+        b_hinv[i] = make_tw(hm::invmod(hm::product_mod(B, i, B[i]), B[i]), B[i]);
+        b_to_msk[i] = hm::product_mod(B, i, msk);
+        for (int k = 0; k < l; k++) b_to_q[(size_t) k * nB + i] = hm::product_mod(B, i, Q[k]);
+    }
+    for (int k = 0; k < l; k++) B_mod_q[k] = hm::product_mod(B, -1, Q[k]);
+    b->inv_B_msk = make_tw(hm::invmod(hm::product_mod(B, -1, msk), msk), msk);
+    // last inverse-NTT stage constants with the multiplication by t folded in (evaluate.cu:520-531)
+    std::vector<Tw> fin((size_t) 3 * (l + nbsk) * 2);
+    for (int p = 0; p < 3; p++) {
+        for (int j = 0; j < l + nbsk; j++) {
+            const int slot = j < l ? p * l + j : 3 * l + p * nbsk + (j - l);
+            const int row = j < l ? j : row_aux_ + (j - l);
+            const u64 q = rowq_[row], c = hm::mulmod(h_ninv_[row], t_ % q, q);
+            fin[2 * slot] = make_tw_row(row, c);
+            fin[2 * slot + 1] = make_tw_row(row, hm::mulmod(c, h_itw1_[row], q));
+        }
+    }
+    b->q_mt_hinv.upload(q_mt_hinv), b->q_hinv.upload(q_hinv), b->q_to_bsk.upload(q_to_bsk), b->q_to_mt.upload(q_to_mt);
+    b->q_mod_bsk.upload(q_mod_bsk), b->inv_mt_bsk.upload(inv_mt), b->inv_q_bsk.upload(inv_q);
+    b->b_hinv.upload(b_hinv), b->b_to_q.upload(b_to_q), b->b_to_msk.upload(b_to_msk), b->B_mod_q.upload(B_mod_q);
+    b->fin_t.upload(fin);
+    behz_[l] = std::move(b);
+    return *behz_[l];
+}
+
+void Engine::bfv_multiply_behz(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cudaStream_t st) {
+    const Behz &b = behz(l);
+    const int nbsk = b.nbsk;
+    const size_t need = (size_t) 7 * (l + nbsk) * n_;
+    if (ws_.behz.count < need) ws_.behz.alloc((size_t) 7 * (size_Q_ + naux_) * n_);
+    // workspace: operands in q [4][l], tensor result in q [3][l] and in Bsk [3][nbsk] (adjacent: one inverse-NTT
+    // list), operands in Bsk [4][nbsk]
+    u64 *eq = ws_.behz.p, *dq = eq + (size_t) 4 * l * n_, *db = dq + (size_t) 3 * l * n_,
+        *eb = db + (size_t) 3 * nbsk * n_;
+    // 1. operands to NTT form over q (BEHZ_mul_1, evaluate.cu:404-438)
+    {
+        LimbVec v;
+        for (int p = 0; p < 2; p++)
+            for (int i = 0; i < l; i++) v.push(p * l + i, i);
+        for (int s = 0; s < 2; s++) {
+            u64 *dst = eq + (size_t) s * 2 * l * n_;
+            const u64 *src = s ? ct2 : ct1;
+            run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_fwd_list(dst, src, ll, st); });
+        }
+    }
+    // 2. q -> Bsk with the m_tilde correction (fastbconv_m_tilde + sm_mrq), then NTT over Bsk
+    {
+        BehzLiftArgs a{ct1, ct2, eb, b.q_mt_hinv.p, b.q_to_bsk.p, b.q_to_mt.p, b.q_mod_bsk.p, b.inv_mt_bsk.p,
+                       d_mod_.p, d_mod_.p + row_aux_, b.neg_inv_q_mt, l, nbsk, n_};
+        launch_pdl(k_behz_lift, dim3((unsigned) (n_ / BEHZ_THREADS), 4), BEHZ_THREADS, 0, st, a);
+        check_launch("k_behz_lift");
+        LimbVec v;
+        for (int p = 0; p < 4; p++)
+            for (int j = 0; j < nbsk; j++) v.push(p * nbsk + j, row_aux_ + j);
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_fwd_list(eb, eb, ll, st); });
+    }
+    // 3. dyadic tensor products in both bases (evaluate.cu:479-500)
+    tensor_2x2(eq, eq + (size_t) 2 * l * n_, dq, l, st);
+    {
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), nbsk);
+        launch_pdl(k_tensor_2x2, grid, EW_THREADS, 0, st, (const u64 *) eb, (const u64 *) (eb + (size_t) 2 * nbsk * n_), db,
+                   (const Modulus *) (d_mod_.p + row_aux_), bar(1, 2) + row_aux_,
+                   RowArith{d_is_fp_.p + row_aux_, d_fpc_.p + row_aux_, 0, 0, 0}, n_, nbsk);
+        check_launch("k_tensor_2x2");
+    }
+    // 4. back to coefficient form, times t (folded into the last inverse stage)
+    {
+        LimbVec v;
+        for (int p = 0; p < 3; p++)
+            for (int i = 0; i < l; i++) v.push(p * l + i, i);
+        for (int p = 0; p < 3; p++)
+            for (int j = 0; j < nbsk; j++) v.push(3 * l + p * nbsk + j, row_aux_ + j);
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t bgn) { ntt_inv_list(dq, dq, ll, b.fin_t.p + 2 * bgn, 1, st); });
+    }
+    // 5. floor(t * x / Q) in Bsk and Shenoy-Kumaresan conversion back to q (fast_floor + fastbconv_sk)
+    {
+        BehzFloorArgs a{dq, db, out3, b.q_hinv.p, b.q_to_bsk.p, b.inv_q_bsk.p, b.b_hinv.p, b.b_to_q.p, b.b_to_msk.p,
+                        b.B_mod_q.p, b.inv_B_msk, d_mod_.p, d_mod_.p + row_aux_, l, nbsk, n_};
+        launch_pdl(k_behz_floor_sk, dim3((unsigned) (n_ / BEHZ_THREADS), 3), BEHZ_THREADS, 0, st, a);
+        check_launch("k_behz_floor_sk");
+    }
+}
+
+// multiply_inplace + relinearize_inplace (reference src/evaluate.cu:345-397,451-548,1342-1374)
 void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st) {
-    if (scheme_ == Scheme::bfv)
-        throw std::invalid_argument("BFV multiplication (BEHZ/HPS) is not on this engine yet: unsupported scheme");
+    if (scheme_ == Scheme::bfv) {
+        u64 *d = ws_.tmp.p;
+        bfv_multiply_behz(l, d, ct1, ct2, st);
+        keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
+        PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
+        return;
+    }
     if (scheme_ == Scheme::bgv) {
         u64 *d = ws_.tmp.p;
         tensor_2x2(ct1, ct2, d, l, st);
@@ -915,7 +1063,7 @@ void Engine::rescale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) 
     {
         LimbVec v;
         for (int s = 0; s < size; s++) v.push(s, l - 1, s * l + (l - 1));
-        ntt_inv_list(last, in, single_list(v, primes_), nullptr, 0, st);
+        ntt_inv_list(last, in, single_list(v, rowq_), nullptr, 0, st);
     }
     for (int s = 0; s < size; s++) {
         dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), nl);
@@ -925,7 +1073,7 @@ void Engine::rescale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) 
     LimbVec v;
     for (int s = 0; s < size; s++)
         for (int j = 0; j < nl; j++) v.push(s * nl + j, j);
-    run_chunks(v, primes_, [&](const LimbList &ll, size_t b) {
+    run_chunks(v, rowq_, [&](const LimbList &ll, size_t b) {
         EpiArgs ea{};
         ea.sub_base = in, ea.out_base = out, ea.add_base = nullptr, ea.mulc = lv.qlast_inv_slots.p + b;
         for (int k = 0; k < ll.count; k++) {

@@ -141,4 +141,19 @@ inline u64 product_mod(const std::vector<u64> &base, int skip, u64 p) {
     return r;
 }
 
+// bit length of the product of `base` (base_Q.big_modulus significant bits, rns.cu:400-406)
+inline int product_bits(const std::vector<u64> &base) {
+    std::vector<u64> acc{1};
+    for (u64 p : base) {
+        u64 carry = 0;
+        for (auto &w : acc) {
+            const u128 t = (u128) w * p + carry;
+            w = (u64) t;
+            carry = (u64) (t >> 64);
+        }
+        if (carry) acc.push_back(carry);
+    }
+    return (int) (acc.size() - 1) * 64 + (64 - __builtin_clzll(acc.back()));
+}
+
 } // namespace pfhe::host

@@ -55,6 +55,9 @@ def oracle():
         o.orc_moddown_from_ntt.argtypes = [vp, ctypes.c_int, u64p, u64p]
         o.orc_keyswitch.argtypes = [vp, ctypes.c_int, u64p, u64p, u64p]
         o.orc_multiply_relin.argtypes = [vp, ctypes.c_int, u64p, u64p, u64p, u64p]
+        o.orc_behz_aux.argtypes = [vp, u64p, i32p]
+        o.orc_bfv_multiply_behz.argtypes = [vp, u64p, u64p, u64p]
+        o.orc_bfv_multiply_relin_behz.argtypes = [vp, u64p, u64p, u64p, u64p]
         o.orc_galois_table.argtypes = [ctypes.c_uint64, ctypes.c_uint32, u32p]
         o.orc_galois_elt_from_step.restype = ctypes.c_uint32
         o.orc_galois_elt_from_step.argtypes = [ctypes.c_int, ctypes.c_uint64]
@@ -161,6 +164,17 @@ def params_primary():  # N=2^16, L=16: {60, 40x15, 60x4}, alpha=4
 
 def params_secondary():  # {60, 40x15, 60}, alpha=1 (single-P fast paths)
     return ParamSet("secondary", 65536, [60] + [40] * 15 + [60], 1)
+
+
+def params_bfv_bench(which=0):
+    """BFV parameter sets of benchmark/bfv_bench.cu:303-345 (N=2^14, log QP = 438), t = PlainModulus::Batching(n, 20)"""
+    n = 16384
+    sets = [([54] * 7 + [60], 1), ([36] * 11 + [42], 1), ([36] * 8 + [37, 37, 38, 38], 4)]
+    bits, size_P = sets[which]
+    o = oracle()
+    t = np.zeros(1, dtype=np.uint64)
+    assert o.orc_create_primes(n, (ctypes.c_int * 1)(20), 1, P(t)) == 0
+    return ParamSet(f"bfv14_{which}", n, bits, size_P, scheme=2, t=int(t[0]))
 
 
 def params_small(n=4096, l=5, alpha=2, qbits=40, pbits=50, scheme=3, t=0):  # oracle-in-seconds sizes

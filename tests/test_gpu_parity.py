@@ -316,10 +316,102 @@ def test_bgv_bfv_keyswitch_and_modswitch(scheme, cfg):
         ca, cb = pf.PhantomCiphertext.from_host(ctx, a), pf.PhantomCiphertext.from_host(ctx, b)
         pf.multiply_and_relin_inplace(ctx, ca, cb, key)
         assert np.array_equal(ca.to_host(), want)
-    else:
+    else:   # BFV: the default mul_tech (HPS) is not built and says so
         a = pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=False)
         with pytest.raises(ValueError, match="unsupported scheme"):
             pf.multiply_and_relin_inplace(ctx, a, a.clone(), key)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# BFV multiplication, BEHZ (evaluate.cu:404-548; rns.cu:386-570,1249-1517)
+# ---------------------------------------------------------------------------------------------------------
+def make_bfv_context(ps, steps=()):
+    parms = pf.EncryptionParameters(pf.scheme_type.bfv)
+    parms.set_poly_modulus_degree(ps.n)
+    parms.set_coeff_modulus([int(p) for p in ps.primes])
+    parms.set_special_modulus_size(ps.size_P)
+    parms.set_plain_modulus(ps.t)
+    parms.set_mul_tech(pf.mul_tech_type.behz)
+    if steps:
+        parms.set_galois_elts(pf.get_elts_from_steps(list(steps), ps.n))
+    return pf.PhantomContext(parms)
+
+
+@pytest.mark.parametrize("cfg", [dict(n=4096, l=3, alpha=1, qbits=36, pbits=42), dict(n=4096, l=5, alpha=2, qbits=44, pbits=60),
+                                 dict(n=8192, l=4, alpha=1, qbits=50, pbits=60)])
+def test_bfv_behz_multiply(cfg):
+    ps = H.params_small(scheme=2, t=65537, **cfg)
+    ctx = make_bfv_context(ps)
+    o, oc = H.oracle(), ps.octx()
+    l, n = ps.limbs(), ps.n
+    key_h = H.switch_key(ps, 100)
+    key = pf.PhantomRelinKey(ctx, list(key_h))
+    a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
+    want3 = np.zeros((3, l, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_behz(oc, P(a), P(b), P(want3)) == 0
+    ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+    cb = pf.PhantomCiphertext.from_host(ctx, b, is_ntt_form=False)
+    pf.multiply_inplace(ctx, ca, cb)
+    assert ca.size() == 3
+    assert np.array_equal(ca.to_host(), want3), "bfv_multiply_behz"
+    want = np.zeros((2, l, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_relin_behz(oc, P(a), P(b), P(key_h), P(want)) == 0
+    pf.relinearize_inplace(ctx, ca, key)
+    assert np.array_equal(ca.to_host(), want), "relinearize after BEHZ"
+    ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+    pf.multiply_and_relin_inplace(ctx, ca, cb, key)
+    assert np.array_equal(ca.to_host(), want), "multiply_and_relin (BEHZ)"
+    # squaring through the same entry point
+    want_sq = np.zeros((3, l, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_behz(oc, P(a), P(a), P(want_sq)) == 0
+    ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+    pf.multiply_inplace(ctx, ca, ca)
+    assert np.array_equal(ca.to_host(), want_sq), "BEHZ square"
+    # edge vectors: all-zero and all-(q-1) operands
+    for vec in H.edge_vectors(ps, list(range(l)))[:2]:
+        e = np.stack([vec, vec])
+        assert o.orc_bfv_multiply_behz(oc, P(e), P(a), P(want3)) == 0
+        ce = pf.PhantomCiphertext.from_host(ctx, e, is_ntt_form=False)
+        pf.multiply_inplace(ctx, ce, pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False))
+        assert np.array_equal(ce.to_host(), want3), "BEHZ edge vector"
+
+
+def test_bfv_behz_against_unmodified_reference():
+    """BFV HMult+Relin at the bfv_bench.cu N=2^14 parameter sets: reference kernels vs engine vs oracle."""
+    r = H.reference()
+    if r is None:
+        pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    for which in (0, 2):
+        ps = H.params_bfv_bench(which)
+        h = r.ref_create(2, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, 1, None, 0, 1.0, 1)
+        assert h, r.ref_last_error()
+        try:
+            l, n = ps.limbs(), ps.n
+            dnum = r.ref_dnum(h)
+            assert dnum == ps.beta()
+            rlk_h = np.zeros((dnum, 2, ps.size_QP, n), dtype=np.uint64)
+            for d in range(dnum):
+                assert r.ref_key_get(h, -1, d, P(rlk_h[d])) == 0
+            ctx = make_bfv_context(ps)
+            rlk = pf.PhantomRelinKey(ctx, list(rlk_h))
+            a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
+            want3 = np.zeros((3, l, n), dtype=np.uint64)
+            assert r.ref_multiply(h, 1, P(a), P(b), P(want3)) == 0, r.ref_last_error()
+            ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+            cb = pf.PhantomCiphertext.from_host(ctx, b, is_ntt_form=False)
+            pf.multiply_inplace(ctx, ca, cb)
+            assert np.array_equal(ca.to_host(), want3), "BEHZ multiply vs reference"
+            if which == 0:   # the oracle pinned against the reference at full size
+                orc3 = np.zeros((3, l, n), dtype=np.uint64)
+                assert H.oracle().orc_bfv_multiply_behz(ps.octx(), P(a), P(b), P(orc3)) == 0
+                assert np.array_equal(orc3, want3), "oracle BEHZ vs reference"
+            want = np.zeros((2, l, n), dtype=np.uint64)
+            assert r.ref_multiply_relin(h, 1, P(a), P(b), P(want)) == 0, r.ref_last_error()
+            ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+            pf.multiply_and_relin_inplace(ctx, ca, cb, rlk)
+            assert np.array_equal(ca.to_host(), want), "BEHZ HMult+Relin vs reference"
+        finally:
+            r.ref_destroy(h)
 
 
 @pytest.mark.parametrize("scheme", [3, 1])

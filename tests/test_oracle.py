@@ -205,3 +205,57 @@ def test_live_against_reference_host_code():
                     if k != i:
                         want = want * qk % p
                 assert case["qhat_mod_p"][j * len(ib) + i] == want
+
+
+def test_behz_multiply_decrypts_to_the_plaintext_product():
+    """BEHZ restatement (oracle/fhe_oracle.c, evaluate.cu:451-548): noiseless-key sanity. Trivial encryptions
+    (Delta*m + e, 0) must multiply to a ciphertext whose c0 decodes to m1*m2 mod (X^n+1, t) and whose c1, c2 are 0."""
+    o = H.oracle()
+    t = 65537
+    ps = H.ParamSet("bfv_sem", 64, [40, 40, 40, 50], 1, scheme=2, t=t)
+    n, lq = ps.n, ps.size_Q
+    Q = 1
+    for p in ps.primes[:lq]:
+        Q *= int(p)
+    delta = Q // t
+    rng = np.random.default_rng(1)
+    m1, m2 = rng.integers(0, t, n), rng.integers(0, t, n)
+
+    def enc(m):
+        ct = np.zeros((2, lq, n), dtype=np.uint64)
+        e = rng.integers(-5, 6, n)
+        for i in range(lq):
+            q = int(ps.primes[i])
+            ct[0, i] = [(delta * int(v) + int(x)) % q for v, x in zip(m, e)]
+        return ct
+
+    c1, c2 = enc(m1), enc(m2)
+    out = np.zeros((3, lq, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_behz(ps.octx(), H.P(c1), H.P(c2), H.P(out)) == 0
+    exp = [0] * n
+    for i in range(n):
+        for j in range(n):
+            v = int(m1[i]) * int(m2[j])
+            if i + j >= n:
+                exp[i + j - n] -= v
+            else:
+                exp[i + j] += v
+    exp = [v % t for v in exp]
+    dec = []
+    for j in range(n):
+        x = 0
+        for i in range(lq):
+            q = int(ps.primes[i])
+            qh = Q // q
+            x += int(out[0, i, j]) * pow(qh, -1, q) % q * qh
+        x %= Q
+        dec.append(((t * x + Q // 2) // Q) % t)
+    assert dec == exp
+    assert not out[1].any() and not out[2].any()
+    # the auxiliary base: m_sk is the largest 61-bit NTT prime, B the next ones (rns.cu:414-420)
+    bsk = np.zeros(66, dtype=np.uint64)
+    nb = ctypes.c_int()
+    assert o.orc_behz_aux(ps.octx(), H.P(bsk), ctypes.byref(nb)) == 0
+    assert nb.value in (lq + 1, lq + 2)
+    assert int(bsk[nb.value - 1]) == max(int(v) for v in bsk[:nb.value])
+    assert all(int(v) % (2 * n) == 1 and int(v).bit_length() == 61 for v in bsk[:nb.value])
