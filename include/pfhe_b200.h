@@ -116,8 +116,9 @@ int pfhe_keyswitch_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypt
                            const uint64_t *const *relin_keys, void *stream);
 
 /* ---- scheme level (replace the namespace phantom free functions of include/evaluate.cuh:37-245) --------- */
-/* multiply_inplace + relinearize_inplace (src/evaluate.cu:1029-1057,1342-1374), CKKS/BGV:
- * encrypted1 = [2][l][n] in/out, encrypted2 = [2][l][n] */
+/* multiply_inplace + relinearize_inplace (src/evaluate.cu:1029-1104,1342-1374):
+ * encrypted1 = [2][l][n] in/out, encrypted2 = [2][l][n].  CKKS/BGV: NTT form (bgv_ckks_multiply :345-397);
+ * BFV: coefficient form, BEHZ multiplication (bfv_multiply_behz :451-548, mul_tech_type::behz) */
 int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted1,
                                     const uint64_t *encrypted2, const uint64_t *const *relin_keys, void *stream);
 /* same, result written to a separate [2][l][n] buffer (no operand copy; what the in-place form's resize does in
@@ -125,7 +126,7 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
                             const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
                             void *stream);
-/* multiply_inplace alone: destination = [3][l][n] */
+/* multiply_inplace alone: destination = [3][l][n] (BFV: must not alias an operand) */
 int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1, const uint64_t *encrypted2,
                   uint64_t *destination, void *stream);
 /* relinearize_inplace: encrypted = [3][l][n], the first two polynomials are updated */
@@ -145,7 +146,8 @@ int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypte
 /* rescale_to_next (src/evaluate.cu:1545-1565): destination = [size][l-1][n] */
 int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted, size_t size,
                          uint64_t *destination, void *stream);
-/* mod_switch_to_next (src/evaluate.cu:1505-1543), CKKS: drops the last limb */
+/* mod_switch_to_next (src/evaluate.cu:1505-1543): CKKS drops the last limb (:1429-1472); BFV divide_and_round_q_last
+ * (src/rns.cu:1082-1126); BGV mod_t_and_divide_q_last_ntt (src/rns.cu:1186-1235) */
 int pfhe_mod_switch_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted, size_t size,
                             uint64_t *destination, void *stream);
 
