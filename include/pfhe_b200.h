@@ -55,6 +55,10 @@ int pfhe_create_primes(uint64_t n, const int *bit_sizes, int count, uint64_t *pr
 int pfhe_engine_create(pfhe_engine **out, int scheme, uint64_t n, const uint64_t *primes, int size_QP, int size_P,
                        uint64_t plain_modulus, const uint32_t *galois_elts, int n_galois);
 void pfhe_engine_destroy(pfhe_engine *e);
+/* EncryptionParameters::set_mul_tech (include/host/encryptionparams.h:25-35,57-69): 1 = behz, 2 = hps (the default
+ * of a BFV engine, like the reference), 3 = hps_overq, 4 = hps_overq_leveled (accepted, but multiplication then
+ * returns PFHE_ERR_INVALID_ARGUMENT "unsupported scheme": not built).  BFV engines only. */
+int pfhe_engine_set_mul_tech(pfhe_engine *e, int mul_tech);
 uint64_t pfhe_poly_degree(const pfhe_engine *e);
 int pfhe_size_QP(const pfhe_engine *e);
 int pfhe_size_P(const pfhe_engine *e);

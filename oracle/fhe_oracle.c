@@ -9,6 +9,7 @@
  */
 #include "fhe_oracle.h"
 
+#include <math.h>
 #include <stdlib.h>
 #include <string.h>
 #ifdef _OPENMP
@@ -1010,6 +1011,189 @@ int orc_bfv_multiply_relin_behz(const orc_ctx *c, const u64 *ct1, const u64 *ct2
         return -1;
     }
     orc_keyswitch(c, c->size_Q, d, d + 2 * poly, rlk);
+    memcpy(out, d, 2 * poly * 8);
+    free(d);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------
+ * BFV multiplication, HPS variant (mul_tech_type::hps; evaluate.cu:647-801, rns.cu:687-792,1699-1745,
+ * rns_bconv.cu:248-372).  The floating-point steps follow the reference's compiled code: nvcc contracts
+ * `acc += double(x) * c` into one fused multiply-add per term, in index order (checked in the SASS of
+ * oracle/_ref: I2F.F64.U64 + DFMA chains), hence fma() below.
+ * ---------------------------------------------------------------------------------------------------- */
+/* little-endian multi-word helpers (the reference uses multiply_uint / divide_uint / modulo_uint) */
+typedef struct {
+    u64 w[72];
+    int len;
+} big_t;
+static void big_mul_word(big_t *a, u64 m) {
+    u64 carry = 0;
+    for (int k = 0; k < a->len; k++) {
+        u128 t = (u128)a->w[k] * m + carry;
+        a->w[k] = (u64)t;
+        carry = (u64)(t >> 64);
+    }
+    if (carry) a->w[a->len++] = carry;
+}
+static u64 big_divmod_word(big_t *a, u64 d) { /* a <- floor(a / d), returns a mod d */
+    u64 rem = 0;
+    for (int k = a->len - 1; k >= 0; k--) {
+        u128 cur = ((u128)rem << 64) | a->w[k];
+        a->w[k] = (u64)(cur / d);
+        rem = (u64)(cur % d);
+    }
+    while (a->len > 1 && a->w[a->len - 1] == 0) a->len--;
+    return rem;
+}
+static u64 big_mod_word(const big_t *a, u64 d) {
+    u64 rem = 0;
+    for (int k = a->len - 1; k >= 0; k--) rem = (u64)((((u128)rem << 64) | a->w[k]) % d);
+    return rem;
+}
+
+/* get_primes_below (numth.cu:235-263) */
+static int get_primes_below(u64 n, u64 upper, int count, u64 *out) {
+    u64 factor = 2 * n;
+    int bits = 0;
+    for (u64 v = upper; v; v >>= 1) bits++;
+    if (upper < factor) return -1;
+    u64 value = upper - factor, lower = (u64)1 << (bits - 1);
+    int k = 0;
+    while (k < count && value > lower) {
+        if (orc_is_prime(value)) out[k++] = value;
+        value -= factor;
+    }
+    return k == count ? 0 : -1;
+}
+
+/* the auxiliary base R of HPS: size_Q + 1 primes below the smallest prime of Q (rns.cu:687-694) */
+int orc_hps_aux(const orc_ctx *c, u64 *R, int *nR) {
+    u64 qmin = c->primes[0];
+    for (int i = 1; i < c->size_Q; i++)
+        if (c->primes[i] < qmin) qmin = c->primes[i];
+    *nR = c->size_Q + 1;
+    return get_primes_below(c->n, qmin, *nR, R);
+}
+
+static u64 sat_u64(double v) { /* static_cast<uint64_t>(double) on the device: cvt.rzi.u64.f64 saturates */
+    if (!(v > 0.0)) return 0;
+    if (v >= 18446744073709551616.0) return ~(u64)0;
+    return (u64)v;
+}
+
+/* bConv_HPS (rns_bconv.cu:354-372): exact-ish conversion with the floating-point overflow estimate */
+static void bconv_hps(const u64 *ibase, int ni, const u64 *obase, int no, const u64 *in, u64 *out, size_t n) {
+    u64 hinv[72], Imod[72];
+    double inv[72];
+    u64 *mat = (u64 *)malloc((size_t)no * ni * 8);
+    for (int i = 0; i < ni; i++) {
+        hinv[i] = orc_invmod(qhat_mod(ibase, ni, i, ibase[i]), ibase[i]);
+        inv[i] = 1.0 / (double)ibase[i]; /* host/rns.cu:319-324 */
+    }
+    for (int j = 0; j < no; j++) {
+        Imod[j] = prod_mod(ibase, ni, obase[j]);
+        for (int i = 0; i < ni; i++) mat[(size_t)j * ni + i] = qhat_mod(ibase, ni, i, obase[j]);
+    }
+#pragma omp parallel for num_threads(g_threads)
+    for (size_t x = 0; x < n; x++) {
+        u64 y[72];
+        double frac = 0.0;
+        for (int i = 0; i < ni; i++) {
+            y[i] = orc_mulmod(in[(size_t)i * n + x], hinv[i], ibase[i]);
+            frac = fma((double)y[i], inv[i], frac);
+        }
+        u64 v = (u64)llround(frac);
+        for (int j = 0; j < no; j++) {
+            u64 p = obase[j];
+            u128 acc = 0;
+            for (int i = 0; i < ni; i++) acc = (acc + (u128)y[i] * mat[(size_t)j * ni + i]) % p;
+            out[(size_t)j * n + x] = submod((u64)acc, orc_mulmod(v % p, Imod[j], p), p); /* alphaQModp[v][j] */
+        }
+    }
+    free(mat);
+}
+
+/* out[3][size_Q][n] = HPS product of two size-2 BFV ciphertexts (coefficient form, top level) */
+int orc_bfv_multiply_hps(const orc_ctx *c, const u64 *ct1, const u64 *ct2, u64 *out) {
+    const size_t n = c->n;
+    const int lq = c->size_Q;
+    const u64 *Q = c->primes, t = c->t;
+    u64 R[72], S[144];
+    int nR;
+    if (lq > 35 || orc_hps_aux(c, R, &nR)) return -1;
+    const int ls = lq + nR;
+    memcpy(S, Q, lq * 8);
+    memcpy(S + lq, R, nR * 8);
+    orc_ctx *sx = orc_create(ORC_SCHEME_BFV, n, S, ls, 0, 0); /* gpu_QlRl_tables (rns.cu:700-714) */
+    if (!sx) return -1;
+    int ids[144];
+    for (int i = 0; i < ls; i++) ids[i] = i;
+    const size_t ps = (size_t)ls * n, pq = (size_t)lq * n;
+    u64 *e[2];
+    for (int s = 0; s < 2; s++) {
+        const u64 *ct = s ? ct2 : ct1;
+        e[s] = (u64 *)malloc(3 * ps * 8);
+        for (int p = 0; p < 2; p++) {
+            u64 *x = e[s] + p * ps;
+            memcpy(x, ct + p * pq, pq * 8);
+            bconv_hps(Q, lq, R, nR, x, x + pq, n);
+            orc_ntt_forward(sx, x, ls, ids);
+        }
+    }
+    u64 *d = (u64 *)malloc(3 * ps * 8);
+    orc_tensor_2x2(sx, e[0], e[1], d, ls);
+    for (int p = 0; p < 3; p++) orc_ntt_inverse(sx, d + p * ps, ls, ids);
+
+    /* scaleAndRound_HPS_QR_R tables (rns.cu:727-789): A_i = t * R * (Shat_i^-1 mod s_i) */
+    double *fr = (double *)malloc(lq * sizeof(double));
+    u64 *tab = (u64 *)malloc((size_t)nR * (lq + 1) * 8);
+    for (int i = 0; i < ls; i++) {
+        big_t A = {{1}, 1};
+        for (int k = 0; k < nR; k++) big_mul_word(&A, R[k]);
+        big_mul_word(&A, t);
+        big_mul_word(&A, orc_invmod(qhat_mod(S, ls, i, S[i]), S[i]));
+        u64 rem = big_divmod_word(&A, S[i]); /* A <- floor(A / s_i) */
+        if (i < lq) {
+            fr[i] = (double)rem / (double)S[i];
+            for (int j = 0; j < nR; j++) tab[(size_t)j * (lq + 1) + i] = big_mod_word(&A, R[j]);
+        } else {
+            tab[(size_t)(i - lq) * (lq + 1) + lq] = big_mod_word(&A, R[i - lq]);
+        }
+    }
+    u64 *tmpR = (u64 *)malloc((size_t)nR * n * 8);
+    for (int p = 0; p < 3; p++) {
+        const u64 *x = d + p * ps;
+        /* scaleAndRound_HPS_QR_R_kernel (rns.cu:1699-1733), including alpha being re-reduced limb after limb */
+#pragma omp parallel for num_threads(g_threads)
+        for (size_t k = 0; k < n; k++) {
+            double nu = 0.5;
+            for (int i = 0; i < lq; i++) nu = fma((double)x[(size_t)i * n + k], fr[i], nu);
+            u64 alpha = sat_u64(nu);
+            for (int j = 0; j < nR; j++) {
+                u64 rj = R[j];
+                u128 cur = 0;
+                for (int i = 0; i < lq; i++) cur = (cur + (u128)x[(size_t)i * n + k] * tab[(size_t)j * (lq + 1) + i]) % rj;
+                cur = (cur + (u128)x[(size_t)(lq + j) * n + k] * tab[(size_t)j * (lq + 1) + lq]) % rj;
+                alpha %= rj;
+                tmpR[(size_t)j * n + k] = addmod((u64)cur, alpha, rj);
+            }
+        }
+        bconv_hps(R, nR, Q, lq, tmpR, out + p * pq, n);
+    }
+    free(tmpR); free(tab); free(fr); free(d); free(e[0]); free(e[1]);
+    orc_destroy(sx);
+    return 0;
+}
+
+int orc_bfv_multiply_relin_hps(const orc_ctx *c, const u64 *ct1, const u64 *ct2, const u64 *rlk, u64 *out) {
+    size_t poly = (size_t)c->size_Q * c->n;
+    u64 *d = (u64 *)malloc(3 * poly * 8);
+    if (orc_bfv_multiply_hps(c, ct1, ct2, d)) {
+        free(d);
+        return -1;
+    }
+    orc_keyswitch(c, c->size_Q, d, d + 2 * poly, rlk); /* bfv_mul_relin_hps tail, evaluate.cu:966-1025 */
     memcpy(out, d, 2 * poly * 8);
     free(d);
     return 0;

@@ -24,6 +24,7 @@ _sigs = {
     "pfhe_engine_create": (ctypes.c_int, [ctypes.POINTER(vp), ctypes.c_int, ctypes.c_uint64, u64p, ctypes.c_int,
                                           ctypes.c_int, ctypes.c_uint64, u32p, ctypes.c_int]),
     "pfhe_engine_destroy": (None, [vp]),
+    "pfhe_engine_set_mul_tech": (ctypes.c_int, [vp, ctypes.c_int]),
     "pfhe_poly_degree": (ctypes.c_uint64, [vp]),
     "pfhe_size_QP": (ctypes.c_int, [vp]),
     "pfhe_size_P": (ctypes.c_int, [vp]),

@@ -120,6 +120,8 @@ class PhantomContext:
         check(lib.pfhe_engine_create(ctypes.byref(handle), int(params.scheme), self.poly_degree, primes, self.size_QP,
                                      self.size_P, params.plain_modulus, elts, len(params.galois_elts)))
         self._h = handle
+        if self.scheme == scheme_type.bfv:
+            check(lib.pfhe_engine_set_mul_tech(handle, int(params.mul_tech)))
         self.device = torch.device("cuda", torch.cuda.current_device())
 
     def __del__(self):
@@ -224,8 +226,6 @@ def multiply_inplace(context, encrypted1, encrypted2):
     l, n = encrypted1.coeff_modulus_size(), context.poly_degree
     dst = torch.empty((3, l, n), dtype=torch.int64, device=encrypted1.data.device)
     a, b = encrypted1.data, encrypted2.data
-    if context.scheme == scheme_type.bfv and context.parms.mul_tech != mul_tech_type.behz:
-        raise ValueError("unsupported scheme: only mul_tech_type.behz is built for BFV")
     check(lib.pfhe_multiply(context._h, encrypted1.chain_index, _ptr(a), _ptr(a if encrypted1 is encrypted2 else b),
                             _ptr(dst), _stream()))
     encrypted1.data = dst
@@ -249,8 +249,6 @@ def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
     _require_ntt(context, encrypted2)
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
-    if context.scheme == scheme_type.bfv and context.parms.mul_tech != mul_tech_type.behz:
-        raise ValueError("unsupported scheme: only mul_tech_type.behz is built for BFV")
     dst = torch.empty_like(encrypted1.data)
     check(lib.pfhe_multiply_and_relin(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
                                       _ptr(encrypted2.data), _ptr(dst), relin_keys.public_keys_ptr(), _stream()))

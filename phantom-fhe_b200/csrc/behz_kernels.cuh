@@ -114,4 +114,101 @@ __global__ void __launch_bounds__(BEHZ_THREADS) k_behz_floor_sk(const BehzFloorA
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// HPS (mul_tech_type::hps).  The floating-point parts reproduce the reference's compiled arithmetic: one
+// I2F.F64.U64 and one DFMA per term, accumulated in index order (nvcc contracts `acc += double(x) * c`), llround for
+// the overflow estimate of bConv_HPS, truncation for the rounding term of scaleAndRound.
+// ---------------------------------------------------------------------------------------------------
+struct HpsLiftArgs {
+    const u64 *ct1, *ct2;   // [2][l][n] each, coefficient form
+    u64 *out;               // [4][nR][n]
+    const Tw *q_hinv;       // [l]
+    const double *q_inv;    // [l]
+    const u64 *mat;         // [nR][l]
+    const u64 *Q_mod_r;     // [nR]
+    const Modulus *mod_q, *mod_r;
+    int l, nR;
+    size_t n;
+};
+
+// bConv_HPS Q -> R (rns_bconv.cu:278-304,354-372)
+__global__ void __launch_bounds__(BEHZ_THREADS) k_hps_lift(const HpsLiftArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int poly = blockIdx.y;
+    const size_t x = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 *src = (poly < 2 ? a.ct1 : a.ct2) + (size_t) (poly & 1) * a.l * a.n + x;
+    u64 y[BEHZ_MAX_LIMBS];
+    double frac = 0.0;
+    for (int i = 0; i < a.l; i++) {
+        y[i] = mul_shoup(src[(size_t) i * a.n], a.q_hinv[i], a.mod_q[i].q);
+        frac = __fma_rn((double) y[i], a.q_inv[i], frac);
+    }
+    const u64 v = (u64) llround(frac);
+    u64 *dst = a.out + (size_t) poly * a.nR * a.n + x;
+    for (int j = 0; j < a.nR; j++) {
+        const Modulus m = a.mod_r[j];
+        Acc128 acc{0, 0};
+        const u64 *row = a.mat + (size_t) j * a.l;
+        for (int i = 0; i < a.l; i++) acc.mac(y[i], row[i]);
+        const u64 r = barrett128(acc.lo, acc.hi, m);
+        dst[(size_t) j * a.n] = sub_mod(r, mul_mod(v, a.Q_mod_r[j], m), m.q);
+    }
+}
+
+struct HpsScaleArgs {
+    const u64 *xq;          // [3][l][n]   tensor result over Q, coefficient form
+    const u64 *xr;          // [3][nR][n]  and over R
+    u64 *out;               // [3][l][n]
+    const double *sr_frac;  // [l]
+    const u64 *sr_tab;      // [nR][l+1]
+    const Tw *r_hinv;       // [nR]
+    const double *r_inv;    // [nR]
+    const u64 *r_to_q;      // [l][nR]
+    const u64 *R_mod_q;     // [l]
+    const Modulus *mod_q, *mod_r;
+    int l, nR;
+    size_t n;
+};
+
+// scaleAndRound_HPS_QR_R (rns.cu:1699-1733) followed by bConv_HPS R -> Q
+__global__ void __launch_bounds__(BEHZ_THREADS) k_hps_scale_round(const HpsScaleArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int poly = blockIdx.y;
+    const size_t x = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 *sq = a.xq + (size_t) poly * a.l * a.n + x;
+    const u64 *sr = a.xr + (size_t) poly * a.nR * a.n + x;
+    u64 xi[BEHZ_MAX_LIMBS], y[BEHZ_MAX_LIMBS];
+    double nu = 0.5;
+    for (int i = 0; i < a.l; i++) {
+        xi[i] = sq[(size_t) i * a.n];
+        nu = __fma_rn((double) xi[i], a.sr_frac[i], nu);
+    }
+    u64 alpha = (u64) nu;   // cvt.rzi.u64.f64 (saturating), as static_cast<uint64_t> compiles to
+    double frac = 0.0;
+    for (int j = 0; j < a.nR; j++) {
+        const Modulus m = a.mod_r[j];
+        const u64 *row = a.sr_tab + (size_t) j * (a.l + 1);
+        Acc128 acc{0, 0};
+        for (int i = 0; i < a.l; i++) acc.mac(xi[i], row[i]);
+        acc.mac(sr[(size_t) j * a.n], row[a.l]);
+        const u64 cur = barrett128(acc.lo, acc.hi, m);
+        alpha = barrett64(alpha, m);   // the reference re-reduces the same variable limb after limb
+        const u64 v = add_mod(cur, alpha, m.q);
+        y[j] = mul_shoup(v, a.r_hinv[j], m.q);
+        frac = __fma_rn((double) y[j], a.r_inv[j], frac);
+    }
+    const u64 v = (u64) llround(frac);
+    u64 *dst = a.out + (size_t) poly * a.l * a.n + x;
+    for (int i = 0; i < a.l; i++) {
+        const Modulus m = a.mod_q[i];
+        Acc128 acc{0, 0};
+        const u64 *row = a.r_to_q + (size_t) i * a.nR;
+        for (int j = 0; j < a.nR; j++) acc.mac(y[j], row[j]);
+        const u64 r = barrett128(acc.lo, acc.hi, m);
+        dst[(size_t) i * a.n] = sub_mod(r, mul_mod(v, a.R_mod_q[i], m), m.q);
+    }
+}
+
 } // namespace pfhe

@@ -77,6 +77,13 @@ int pfhe_engine_create(pfhe_engine **out, int scheme, uint64_t n, const uint64_t
 }
 
 void pfhe_engine_destroy(pfhe_engine *e) { delete e; }
+
+int pfhe_engine_set_mul_tech(pfhe_engine *e, int mul_tech) {
+    API_BEGIN
+    require(e != nullptr, "engine is null");
+    e->impl.set_mul_tech(mul_tech);
+    API_END
+}
 uint64_t pfhe_poly_degree(const pfhe_engine *e) { return e->impl.n(); }
 int pfhe_size_QP(const pfhe_engine *e) { return e->impl.size_QP(); }
 int pfhe_size_P(const pfhe_engine *e) { return e->impl.size_P(); }
@@ -249,9 +256,9 @@ int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const
                   void *stream) {
     API_BEGIN
     const int l = e->impl.limbs_at(chain_index);
-    if (e->impl.scheme() == Scheme::bfv) {   // mul_tech_type::behz (evaluate.cu:451-548)
+    if (e->impl.scheme() == Scheme::bfv) {   // bfv_multiply (evaluate.cu:803-818): BEHZ or HPS by mul_tech
         require(dst != ct1 && dst != ct2, "destination aliases an operand");
-        e->impl.bfv_multiply_behz(l, U(dst), U(ct1), U(ct2), S(stream));
+        e->impl.bfv_multiply(l, U(dst), U(ct1), U(ct2), S(stream));
         return PFHE_OK;
     }
     if (ct1 == ct2) e->impl.tensor_square(U(ct1), U(dst), l, S(stream));

@@ -149,11 +149,25 @@ void Engine::build_tables() {
             rowq_.push_back(p);
         }
     }
+    row_R_ = (int) rowq_.size();
+    if (scheme_ == Scheme::bfv && t_ > 1) {
+        // HPS auxiliary base R (rns.cu:687-694): size_Q + 1 primes below the smallest prime of Q
+        mul_tech_ = 2;
+        const u64 qmin = *std::min_element(primes_.begin(), primes_.begin() + size_Q_);
+        try {
+            for (u64 p : hm::primes_below(n_, qmin, (size_t) size_Q_ + 1)) rowq_.push_back(p);
+            nR_ = size_Q_ + 1;
+        } catch (const std::logic_error &) {
+            nR_ = 0;   // no room below min(q): HPS is reported as unavailable when it is asked for
+            rowq_.resize(row_R_);
+        }
+    }
     mod_rows_ = (int) rowq_.size();
     is_fp_.assign(mod_rows_, 0);
     std::vector<double2> fpc(mod_rows_);
     for (int i = 0; i < mod_rows_; i++) {
-        is_fp_[i] = i < size_QP_ && allow_fp && (rowq_[i] >> 46) == 0;   // t and the auxiliary rows: integer path
+        // the plain modulus row has no NTT; BEHZ rows are 61-bit; Q, P and R rows below 2^46 run on the FP64 pipe
+        is_fp_[i] = !(t_ > 1 && i == size_QP_) && allow_fp && (rowq_[i] >> 46) == 0;
         fpc[i] = make_double2((double) rowq_[i], 1.0 / (double) rowq_[i]);
     }
     for (int i = 0; i < size_QP_ && i < 128; i++)
@@ -929,11 +943,126 @@ void Engine::bfv_multiply_behz(int l, u64 *out3, const u64 *ct1, const u64 *ct2,
     }
 }
 
-// multiply_inplace + relinearize_inplace (reference src/evaluate.cu:345-397,451-548,1342-1374)
+// ---------------------------------------------------------------------------------------------------
+// BFV multiplication, HPS variant
+// ---------------------------------------------------------------------------------------------------
+void Engine::set_mul_tech(int m) {
+    if (scheme_ != Scheme::bfv) throw std::invalid_argument("mul_tech selection is only supported for BFV");
+    if (m < 1 || m > 4) throw std::invalid_argument("unsupported multiplication technique for BFV");
+    mul_tech_ = m;
+}
+
+const Hps &Engine::hps() {
+    if (scheme_ != Scheme::bfv || nR_ == 0) throw std::invalid_argument("unsupported scheme");
+    if (hps_) return *hps_;
+    auto h = std::make_unique<Hps>();
+    const int l = size_Q_, nR = nR_;
+    h->l = l, h->nR = nR;
+    const std::vector<u64> Q(primes_.begin(), primes_.begin() + l);
+    const std::vector<u64> R(rowq_.begin() + row_R_, rowq_.begin() + row_R_ + nR);
+    std::vector<u64> S(Q);
+    S.insert(S.end(), R.begin(), R.end());
+    std::vector<Tw> q_hinv(l), r_hinv(nR);
+    std::vector<double> q_inv(l), r_inv(nR), sr_frac(l);
+    std::vector<u64> q_to_r((size_t) nR * l), Q_mod_r(nR), r_to_q((size_t) l * nR), R_mod_q(l), sr_tab((size_t) nR * (l + 1));
+    for (int i = 0; i < l; i++) {
+        q_hinv[i] = make_tw(hm::invmod(hm::product_mod(Q, i, Q[i]), Q[i]), Q[i]);
+        q_inv[i] = 1.0 / (double) Q[i];   // host/rns.cu:319-324
+        R_mod_q[i] = hm::product_mod(R, -1, Q[i]);
+        for (int j = 0; j < nR; j++) r_to_q[(size_t) i * nR + j] = hm::product_mod(R, j, Q[i]);
+    }
+    for (int j = 0; j < nR; j++) {
+        r_hinv[j] = make_tw(hm::invmod(hm::product_mod(R, j, R[j]), R[j]), R[j]);
+        r_inv[j] = 1.0 / (double) R[j];
+        Q_mod_r[j] = hm::product_mod(Q, -1, R[j]);
+        for (int i = 0; i < l; i++) q_to_r[(size_t) j * l + i] = hm::product_mod(Q, i, R[j]);
+    }
+    // scale-and-round tables (rns.cu:727-789): A_i = t * R * (Shat_i^-1 mod s_i) over S = Q u R
+    for (int i = 0; i < l + nR; i++) {
+        hm::BigUint A;
+        for (u64 r : R) A.mul_word(r);
+        A.mul_word(t_);
+        A.mul_word(hm::invmod(hm::product_mod(S, i, S[i]), S[i]));
+        const u64 rem = A.divmod_word(S[i]);
+        if (i < l) {
+            sr_frac[i] = (double) rem / (double) S[i];
+            for (int j = 0; j < nR; j++) sr_tab[(size_t) j * (l + 1) + i] = A.mod_word(R[j]);
+        } else {
+            sr_tab[(size_t) (i - l) * (l + 1) + l] = A.mod_word(R[i - l]);
+        }
+    }
+    h->q_hinv.upload(q_hinv), h->q_inv.upload(q_inv), h->q_to_r.upload(q_to_r), h->Q_mod_r.upload(Q_mod_r);
+    h->sr_frac.upload(sr_frac), h->sr_tab.upload(sr_tab);
+    h->r_hinv.upload(r_hinv), h->r_inv.upload(r_inv), h->r_to_q.upload(r_to_q), h->R_mod_q.upload(R_mod_q);
+    hps_ = std::move(h);
+    return *hps_;
+}
+
+void Engine::bfv_multiply_hps(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cudaStream_t st) {
+    // the reference always takes the constants of the first data level here (evaluate.cu:672-696)
+    if (l != size_Q_) throw std::invalid_argument("HPS multiplication is defined at the first data level only");
+    const Hps &h = hps();
+    const int nR = h.nR;
+    const size_t need = (size_t) 7 * (l + nR) * n_;
+    if (ws_.behz.count < need) ws_.behz.alloc(std::max(need, (size_t) 7 * (size_Q_ + naux_) * n_));
+    // operands over Q [4][l], tensor result over Q [3][l] and over R [3][nR] (adjacent), operands over R [4][nR]
+    u64 *eq = ws_.behz.p, *dq = eq + (size_t) 4 * l * n_, *dr = dq + (size_t) 3 * l * n_,
+        *er = dr + (size_t) 3 * nR * n_;
+    {   // Q limbs: NTT straight from the ciphertexts (the reference's D2D copy is the out-of-place store)
+        LimbVec v;
+        for (int p = 0; p < 2; p++)
+            for (int i = 0; i < l; i++) v.push(p * l + i, i);
+        for (int s = 0; s < 2; s++) {
+            u64 *dst = eq + (size_t) s * 2 * l * n_;
+            const u64 *src = s ? ct2 : ct1;
+            run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_fwd_list(dst, src, ll, st); });
+        }
+    }
+    {   // Q -> R (bConv_HPS), then NTT over R
+        HpsLiftArgs a{ct1, ct2, er, h.q_hinv.p, h.q_inv.p, h.q_to_r.p, h.Q_mod_r.p, d_mod_.p, d_mod_.p + row_R_, l, nR, n_};
+        launch_pdl(k_hps_lift, dim3((unsigned) (n_ / BEHZ_THREADS), 4), BEHZ_THREADS, 0, st, a);
+        check_launch("k_hps_lift");
+        LimbVec v;
+        for (int p = 0; p < 4; p++)
+            for (int j = 0; j < nR; j++) v.push(p * nR + j, row_R_ + j);
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_fwd_list(er, er, ll, st); });
+    }
+    tensor_2x2(eq, eq + (size_t) 2 * l * n_, dq, l, st);
+    {
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), nR);
+        launch_pdl(k_tensor_2x2, grid, EW_THREADS, 0, st, (const u64 *) er, (const u64 *) (er + (size_t) 2 * nR * n_), dr,
+                   (const Modulus *) (d_mod_.p + row_R_), bar(1, 2) + row_R_,
+                   RowArith{d_is_fp_.p + row_R_, d_fpc_.p + row_R_, 0, 0, 0}, n_, nR);
+        check_launch("k_tensor_2x2");
+    }
+    {
+        LimbVec v;
+        for (int p = 0; p < 3; p++)
+            for (int i = 0; i < l; i++) v.push(p * l + i, i);
+        for (int p = 0; p < 3; p++)
+            for (int j = 0; j < nR; j++) v.push(3 * l + p * nR + j, row_R_ + j);
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_inv_list(dq, dq, ll, nullptr, 0, st); });
+    }
+    {   // t/Q scale-and-round QR -> R, then R -> Q (scaleAndRound_HPS_QR_R + bConv_HPS)
+        HpsScaleArgs a{dq, dr, out3, h.sr_frac.p, h.sr_tab.p, h.r_hinv.p, h.r_inv.p, h.r_to_q.p, h.R_mod_q.p,
+                       d_mod_.p, d_mod_.p + row_R_, l, nR, n_};
+        launch_pdl(k_hps_scale_round, dim3((unsigned) (n_ / BEHZ_THREADS), 3), BEHZ_THREADS, 0, st, a);
+        check_launch("k_hps_scale_round");
+    }
+}
+
+void Engine::bfv_multiply(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cudaStream_t st) {
+    if (scheme_ != Scheme::bfv) throw std::invalid_argument("unsupported scheme");
+    if (mul_tech_ == 1) bfv_multiply_behz(l, out3, ct1, ct2, st);
+    else if (mul_tech_ == 2) bfv_multiply_hps(l, out3, ct1, ct2, st);
+    else throw std::invalid_argument("unsupported scheme: mul_tech hps_overq / hps_overq_leveled are not built");
+}
+
+// multiply_inplace + relinearize_inplace (reference src/evaluate.cu:345-397,451-548,819-1026,1342-1374)
 void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st) {
     if (scheme_ == Scheme::bfv) {
         u64 *d = ws_.tmp.p;
-        bfv_multiply_behz(l, d, ct1, ct2, st);
+        bfv_multiply(l, d, ct1, ct2, st);
         keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
         PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
         return;

@@ -141,6 +141,48 @@ inline u64 product_mod(const std::vector<u64> &base, int skip, u64 p) {
     return r;
 }
 
+// NTT-friendly primes below `upper` (itself 1 mod 2N), descending (get_primes_below, numth.cu:235-263)
+inline std::vector<u64> primes_below(u64 n, u64 upper, size_t count) {
+    const u64 step = 2 * n;
+    if (upper < step) throw std::logic_error("failed to find enough qualifying primes 1");
+    const int bits = 64 - __builtin_clzll(upper);
+    const u64 floor_v = (u64) 1 << (bits - 1);
+    std::vector<u64> out;
+    for (u64 v = upper - step; out.size() < count && v > floor_v; v -= step)
+        if (is_prime(v)) out.push_back(v);
+    if (out.size() < count) throw std::logic_error("failed to find enough qualifying primes 2");
+    return out;
+}
+
+// little-endian multi-word integers for the HPS scale-and-round tables (t * R * x / s needs ~(size_R + 2) words)
+struct BigUint {
+    std::vector<u64> w{1};
+    void mul_word(u64 m) {
+        u64 carry = 0;
+        for (auto &x : w) {
+            const u128 t = (u128) x * m + carry;
+            x = (u64) t;
+            carry = (u64) (t >> 64);
+        }
+        if (carry) w.push_back(carry);
+    }
+    u64 divmod_word(u64 d) {   // *this <- floor(*this / d), returns the remainder
+        u64 rem = 0;
+        for (size_t k = w.size(); k-- > 0;) {
+            const u128 cur = ((u128) rem << 64) | w[k];
+            w[k] = (u64) (cur / d);
+            rem = (u64) (cur % d);
+        }
+        while (w.size() > 1 && w.back() == 0) w.pop_back();
+        return rem;
+    }
+    u64 mod_word(u64 d) const {
+        u64 rem = 0;
+        for (size_t k = w.size(); k-- > 0;) rem = (u64) ((((u128) rem << 64) | w[k]) % d);
+        return rem;
+    }
+};
+
 // bit length of the product of `base` (base_Q.big_modulus significant bits, rns.cu:400-406)
 inline int product_bits(const std::vector<u64> &base) {
     std::vector<u64> acc{1};

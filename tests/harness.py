@@ -55,6 +55,9 @@ def oracle():
         o.orc_moddown_from_ntt.argtypes = [vp, ctypes.c_int, u64p, u64p]
         o.orc_keyswitch.argtypes = [vp, ctypes.c_int, u64p, u64p, u64p]
         o.orc_multiply_relin.argtypes = [vp, ctypes.c_int, u64p, u64p, u64p, u64p]
+        o.orc_hps_aux.argtypes = [vp, u64p, i32p]
+        o.orc_bfv_multiply_hps.argtypes = [vp, u64p, u64p, u64p]
+        o.orc_bfv_multiply_relin_hps.argtypes = [vp, u64p, u64p, u64p, u64p]
         o.orc_behz_aux.argtypes = [vp, u64p, i32p]
         o.orc_bfv_multiply_behz.argtypes = [vp, u64p, u64p, u64p]
         o.orc_bfv_multiply_relin_behz.argtypes = [vp, u64p, u64p, u64p, u64p]

@@ -316,22 +316,23 @@ def test_bgv_bfv_keyswitch_and_modswitch(scheme, cfg):
         ca, cb = pf.PhantomCiphertext.from_host(ctx, a), pf.PhantomCiphertext.from_host(ctx, b)
         pf.multiply_and_relin_inplace(ctx, ca, cb, key)
         assert np.array_equal(ca.to_host(), want)
-    else:   # BFV: the default mul_tech (HPS) is not built and says so
-        a = pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=False)
+    else:   # BFV: the HPS-over-Q variants are not built and say so
+        octx = make_bfv_context(ps, mul_tech=pf.mul_tech_type.hps_overq)
+        a = pf.PhantomCiphertext.from_host(octx, ct, is_ntt_form=False)
         with pytest.raises(ValueError, match="unsupported scheme"):
-            pf.multiply_and_relin_inplace(ctx, a, a.clone(), key)
+            pf.multiply_and_relin_inplace(octx, a, a.clone(), pf.PhantomRelinKey(octx, list(key_h)))
 
 
 # ---------------------------------------------------------------------------------------------------------
 # BFV multiplication, BEHZ (evaluate.cu:404-548; rns.cu:386-570,1249-1517)
 # ---------------------------------------------------------------------------------------------------------
-def make_bfv_context(ps, steps=()):
+def make_bfv_context(ps, steps=(), mul_tech=1):   # mul_tech_type.behz
     parms = pf.EncryptionParameters(pf.scheme_type.bfv)
     parms.set_poly_modulus_degree(ps.n)
     parms.set_coeff_modulus([int(p) for p in ps.primes])
     parms.set_special_modulus_size(ps.size_P)
     parms.set_plain_modulus(ps.t)
-    parms.set_mul_tech(pf.mul_tech_type.behz)
+    parms.set_mul_tech(mul_tech)
     if steps:
         parms.set_galois_elts(pf.get_elts_from_steps(list(steps), ps.n))
     return pf.PhantomContext(parms)
@@ -376,14 +377,50 @@ def test_bfv_behz_multiply(cfg):
         assert np.array_equal(ce.to_host(), want3), "BEHZ edge vector"
 
 
-def test_bfv_behz_against_unmodified_reference():
+@pytest.mark.parametrize("cfg", [dict(n=4096, l=3, alpha=1, qbits=36, pbits=42), dict(n=4096, l=5, alpha=2, qbits=44, pbits=60),
+                                 dict(n=8192, l=4, alpha=1, qbits=50, pbits=60)])
+def test_bfv_hps_multiply(cfg):
+    """mul_tech_type::hps (the reference's default for BFV): bConv_HPS, scaleAndRound_HPS_QR_R, FMA-order-exact."""
+    ps = H.params_small(scheme=2, t=65537, **cfg)
+    ctx = make_bfv_context(ps, mul_tech=pf.mul_tech_type.hps)
+    o, oc = H.oracle(), ps.octx()
+    l, n = ps.limbs(), ps.n
+    key_h = H.switch_key(ps, 100)
+    key = pf.PhantomRelinKey(ctx, list(key_h))
+    a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
+    want3 = np.zeros((3, l, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_hps(oc, P(a), P(b), P(want3)) == 0
+    ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+    cb = pf.PhantomCiphertext.from_host(ctx, b, is_ntt_form=False)
+    pf.multiply_inplace(ctx, ca, cb)
+    assert np.array_equal(ca.to_host(), want3), "bfv_multiply_hps"
+    want = np.zeros((2, l, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_relin_hps(oc, P(a), P(b), P(key_h), P(want)) == 0
+    ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+    pf.multiply_and_relin_inplace(ctx, ca, cb, key)
+    assert np.array_equal(ca.to_host(), want), "bfv_mul_relin_hps"
+    for vec in H.edge_vectors(ps, list(range(l)))[:3]:
+        e = np.stack([vec, vec])
+        assert o.orc_bfv_multiply_hps(oc, P(e), P(a), P(want3)) == 0
+        ce = pf.PhantomCiphertext.from_host(ctx, e, is_ntt_form=False)
+        pf.multiply_inplace(ctx, ce, pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False))
+        assert np.array_equal(ce.to_host(), want3), "HPS edge vector"
+    # below the first data level the reference's HPS has no constants: refused, not guessed
+    low = pf.mod_switch_to_next(ctx, pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False))
+    with pytest.raises(ValueError, match="first data level"):
+        pf.multiply_inplace(ctx, low, low.clone())
+
+
+@pytest.mark.parametrize("mul_tech", [1, 2])
+def test_bfv_multiply_against_unmodified_reference(mul_tech):
     """BFV HMult+Relin at the bfv_bench.cu N=2^14 parameter sets: reference kernels vs engine vs oracle."""
     r = H.reference()
     if r is None:
         pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    orc_mul = H.oracle().orc_bfv_multiply_behz if mul_tech == 1 else H.oracle().orc_bfv_multiply_hps
     for which in (0, 2):
         ps = H.params_bfv_bench(which)
-        h = r.ref_create(2, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, 1, None, 0, 1.0, 1)
+        h = r.ref_create(2, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, mul_tech, None, 0, 1.0, 1)
         assert h, r.ref_last_error()
         try:
             l, n = ps.limbs(), ps.n
@@ -392,7 +429,7 @@ def test_bfv_behz_against_unmodified_reference():
             rlk_h = np.zeros((dnum, 2, ps.size_QP, n), dtype=np.uint64)
             for d in range(dnum):
                 assert r.ref_key_get(h, -1, d, P(rlk_h[d])) == 0
-            ctx = make_bfv_context(ps)
+            ctx = make_bfv_context(ps, mul_tech=pf.mul_tech_type(mul_tech))
             rlk = pf.PhantomRelinKey(ctx, list(rlk_h))
             a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
             want3 = np.zeros((3, l, n), dtype=np.uint64)
@@ -400,16 +437,16 @@ def test_bfv_behz_against_unmodified_reference():
             ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
             cb = pf.PhantomCiphertext.from_host(ctx, b, is_ntt_form=False)
             pf.multiply_inplace(ctx, ca, cb)
-            assert np.array_equal(ca.to_host(), want3), "BEHZ multiply vs reference"
+            assert np.array_equal(ca.to_host(), want3), "BFV multiply vs reference"
             if which == 0:   # the oracle pinned against the reference at full size
                 orc3 = np.zeros((3, l, n), dtype=np.uint64)
-                assert H.oracle().orc_bfv_multiply_behz(ps.octx(), P(a), P(b), P(orc3)) == 0
-                assert np.array_equal(orc3, want3), "oracle BEHZ vs reference"
+                assert orc_mul(ps.octx(), P(a), P(b), P(orc3)) == 0
+                assert np.array_equal(orc3, want3), "oracle BFV multiply vs reference"
             want = np.zeros((2, l, n), dtype=np.uint64)
             assert r.ref_multiply_relin(h, 1, P(a), P(b), P(want)) == 0, r.ref_last_error()
             ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
             pf.multiply_and_relin_inplace(ctx, ca, cb, rlk)
-            assert np.array_equal(ca.to_host(), want), "BEHZ HMult+Relin vs reference"
+            assert np.array_equal(ca.to_host(), want), "BFV HMult+Relin vs reference"
         finally:
             r.ref_destroy(h)
 

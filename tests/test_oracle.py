@@ -207,10 +207,13 @@ def test_live_against_reference_host_code():
                 assert case["qhat_mod_p"][j * len(ib) + i] == want
 
 
-def test_behz_multiply_decrypts_to_the_plaintext_product():
-    """BEHZ restatement (oracle/fhe_oracle.c, evaluate.cu:451-548): noiseless-key sanity. Trivial encryptions
-    (Delta*m + e, 0) must multiply to a ciphertext whose c0 decodes to m1*m2 mod (X^n+1, t) and whose c1, c2 are 0."""
+@pytest.mark.parametrize("tech", ["behz", "hps"])
+def test_bfv_multiply_decrypts_to_the_plaintext_product(tech):
+    """BEHZ / HPS restatements (oracle/fhe_oracle.c; evaluate.cu:451-548,647-801): noiseless-key sanity. Trivial
+    encryptions (Delta*m + e, 0) must multiply to a ciphertext whose c0 decodes to m1*m2 mod (X^n+1, t) and whose
+    c1, c2 are 0."""
     o = H.oracle()
+    mul = o.orc_bfv_multiply_behz if tech == "behz" else o.orc_bfv_multiply_hps
     t = 65537
     ps = H.ParamSet("bfv_sem", 64, [40, 40, 40, 50], 1, scheme=2, t=t)
     n, lq = ps.n, ps.size_Q
@@ -231,7 +234,7 @@ def test_behz_multiply_decrypts_to_the_plaintext_product():
 
     c1, c2 = enc(m1), enc(m2)
     out = np.zeros((3, lq, n), dtype=np.uint64)
-    assert o.orc_bfv_multiply_behz(ps.octx(), H.P(c1), H.P(c2), H.P(out)) == 0
+    assert mul(ps.octx(), H.P(c1), H.P(c2), H.P(out)) == 0
     exp = [0] * n
     for i in range(n):
         for j in range(n):
@@ -252,6 +255,15 @@ def test_behz_multiply_decrypts_to_the_plaintext_product():
         dec.append(((t * x + Q // 2) // Q) % t)
     assert dec == exp
     assert not out[1].any() and not out[2].any()
+    if tech == "hps":   # R: size_Q + 1 NTT primes just below min(q_i) (rns.cu:687-694)
+        R = np.zeros(72, dtype=np.uint64)
+        nr = ctypes.c_int()
+        assert o.orc_hps_aux(ps.octx(), H.P(R), ctypes.byref(nr)) == 0
+        assert nr.value == lq + 1
+        qmin = min(int(p) for p in ps.primes[:lq])
+        assert all(int(v) < qmin and int(v) % (2 * n) == 1 for v in R[:nr.value])
+        assert list(R[:nr.value]) == sorted(R[:nr.value], reverse=True)
+        return
     # the auxiliary base: m_sk is the largest 61-bit NTT prime, B the next ones (rns.cu:414-420)
     bsk = np.zeros(66, dtype=np.uint64)
     nb = ctypes.c_int()

@@ -15,14 +15,14 @@ from harness import P  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 r = H.reference()
-for which in (0, 1, 2):
+for which, tech in [(w, m) for m in (1, 2) for w in (0, 1, 2)]:
     ps = H.params_bfv_bench(which)
     parms = pf.EncryptionParameters(pf.scheme_type.bfv)
     parms.set_poly_modulus_degree(ps.n)
     parms.set_coeff_modulus([int(p) for p in ps.primes])
     parms.set_special_modulus_size(ps.size_P)
     parms.set_plain_modulus(ps.t)
-    parms.set_mul_tech(pf.mul_tech_type.behz)
+    parms.set_mul_tech(pf.mul_tech_type(tech))
     ctx = pf.PhantomContext(parms)
     a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
     rlk = pf.PhantomRelinKey(ctx, list(H.switch_key(ps, 100)))
@@ -46,10 +46,10 @@ for which in (0, 1, 2):
     eng_us = e0.elapsed_time(e1) * 1000 / reps
     ref_us = float("nan")
     if r is not None:
-        h = r.ref_create(2, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, 1, None, 0, 1.0, 1)
+        h = r.ref_create(2, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, tech, None, 0, 1.0, 1)
         times = np.zeros(60, dtype=np.float64)
         assert r.ref_time_op(h, 0, 1, P(a), P(b), 0, 0, 60, times.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
         ref_us = float(np.median(times[10:]))
         r.ref_destroy(h)
-    print(f"bfv set {which}: l={ps.limbs()} alpha={ps.size_P} engine {eng_us:.1f} us  reference {ref_us:.1f} us  "
+    print(f"bfv set {which} {pf.mul_tech_type(tech).name}: l={ps.limbs()} alpha={ps.size_P} engine {eng_us:.1f} us  reference {ref_us:.1f} us  "
           f"speedup {ref_us / eng_us:.2f}x", flush=True)
