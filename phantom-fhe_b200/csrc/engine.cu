@@ -74,6 +74,15 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
         if (q >> 61 || q < 2 || (q - 1) % (2 * n_) != 0 || !hm::is_prime(q))
             throw std::invalid_argument("coeff_modulus primes must be NTT-friendly primes of at most 61 bits");
     }
+    {
+        const char *ov = std::getenv("PFHE_OVERLAP");   // 0: keep the whole key switch on the caller's stream
+        overlap_ = !(ov && ov[0] == '0');
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const char *sc = std::getenv("PFHE_SIDE_CTAS");   // CTAs per SM of the co-running inner product (0: plain grid)
+        side_ctas_ = sms * (sc ? std::atoi(sc) : 2);
+    }
     build_tables();
     levels_.resize(size_Q_ + 1);
     behz_.resize(size_Q_ + 1);
@@ -103,6 +112,9 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
 }
 
 Engine::~Engine() {
+    if (ev_fork_) cudaEventDestroy(ev_fork_);
+    if (ev_join_) cudaEventDestroy(ev_join_);
+    if (s_side_) cudaStreamDestroy(s_side_);
     for (int i = 0; i < 2; i++) {
         if (ev_in_[i]) cudaEventDestroy(ev_in_[i]);
         if (ev_comp_[i]) cudaEventDestroy(ev_comp_[i]);
@@ -555,15 +567,23 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
 }
 
 void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st,
-                        const u64 *own_c2, const TensorSrc *ts, const uint32_t *perm, bool accumulate) const {
+                        const u64 *own_c2, const TensorSrc *ts, const uint32_t *perm, bool accumulate, int j_begin,
+                        int j_count, int persist_ctas) const {
     const Level &lv = level(l);
-    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), lv.m);
+    if (j_count < 0) j_count = lv.m - j_begin;
+    if (j_count == 0) return;
     OwnSrc os{nullptr, nullptr, nullptr, 0};
     if (own_c2) os = OwnSrc{own_c2, nullptr, nullptr, lv.alpha};
     else if (ts) os = OwnSrc{nullptr, ts->a + (size_t) ts->l * n_, ts->b + (size_t) ts->l * n_, lv.alpha};
-    launch_pdl(k_inner_prod, grid, EW_THREADS, 0, st, cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), bar(1, 0),
-               RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, perm, accumulate ? 1 : 0,
-               n_, l, lv.m, size_Q_, size_QP_, lv.beta);
+    const InnerProdArgs A{cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), bar(1, 0),
+                          RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, perm,
+                          accumulate ? 1 : 0, n_, l, lv.m, size_Q_, size_QP_, lv.beta, j_begin, j_count};
+    if (persist_ctas > 0) {
+        launch_pdl(k_inner_prod_persist, dim3((unsigned) persist_ctas), EW_THREADS, 0, st, A);
+    } else {
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), j_count);
+        launch_pdl(k_inner_prod, grid, EW_THREADS, 0, st, A);
+    }
     check_launch("k_inner_prod");
 }
 
@@ -684,14 +704,34 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         PFHE_CUDA(ntt_forward_bconv(plan_, t_mod_up, ll, bl, nullptr, nullptr, nullptr, st));
         d0 = d1;
     }
-    // 3. inner product; the digit's own limbs are read from c2 (or formed as a1*b1)
-    inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts);
+    // 3. inner product; the digit's own limbs are read from c2 (or formed as a1*b1).  Only the P limbs of cx feed
+    //    the mod-down chain (steps 4, 5a); the Q limbs are needed by the epilogue (5b) alone.  So: P limbs first, then
+    //    fork -- the latency-bound chain 4 -> 5a goes to a high-priority side stream, the bandwidth-bound Q-limb half of
+    //    the inner product stays on the caller's stream and fills the SMs the small launches leave idle -- and join
+    //    before the epilogue.
+    const bool fork = overlap_;
+    cudaStream_t sc = st;   // stream of the P-limb chain
+    inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, l, alpha);
+    if (fork) {
+        if (!s_side_) {
+            int least = 0, greatest = 0;
+            PFHE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
+            PFHE_CUDA(cudaStreamCreateWithPriority(&s_side_, cudaStreamNonBlocking, greatest));
+            PFHE_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
+            PFHE_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+        }
+        PFHE_CUDA(cudaEventRecord(ev_fork_, st));
+        PFHE_CUDA(cudaStreamWaitEvent(s_side_, ev_fork_, 0));
+        sc = s_side_;
+    } else {
+        inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l);
+    }
     // 4. inverse NTT of the P limbs fused with n^-1 * phat_i^-1
     {
         LimbVec v;
         for (int k = 0; k < 2; k++)
             for (int i = 0; i < alpha; i++) v.push(k * m + l + i, size_Q_ + i);
-        ntt_inv_list(cx, cx, single_list(v, rowq_), lv.moddown_fin.p, 1, st);
+        ntt_inv_list(cx, cx, single_list(v, rowq_), lv.moddown_fin.p, 1, sc);
     }
     // 5. mod-down: convert P -> q_j, forward NTT, (cx - delta) * P^-1 + addend
     {
@@ -719,7 +759,15 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
             }
         ll.count = cnt;
         g_launches.fetch_add(2, std::memory_order_relaxed);
-        PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), st));
+        if (!fork) {
+            PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), st));
+        } else {
+            PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), sc, 1));   // 5a: column pass
+            PFHE_CUDA(cudaEventRecord(ev_join_, sc));
+            inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l, side_ctas_);   // Q limbs
+            PFHE_CUDA(cudaStreamWaitEvent(st, ev_join_, 0));
+            PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), st, 2));   // 5b: row pass + epilogue
+        }
     }
 }
 

@@ -28,8 +28,10 @@ cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, con
                             const Tw *fin, int by_slot, cudaStream_t st);
 
 // forward NTT of base-converted inputs (BconvLoad) written to `dst`; optional epilogue (ea) and tensor addend (ts)
+// phase: 0 = column pass (with the conversion) then row pass; 1 = column pass only; 2 = row pass only (the two
+// halves may then be enqueued on different streams)
 cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
-                              const TensorSrc *ts, const BarG *bar1, cudaStream_t st);
+                              const TensorSrc *ts, const BarG *bar1, cudaStream_t st, int phase = 0);
 
 // inverse NTT incl. n^-1; `fin` (optional) = per-slot or per-row {c, itw1*c} pairs with c = n^-1 * scalar
 // (replaces nwt_2d_radix8_backward[_inplace][_scale] and variants, include/ntt.cuh:206-226)

@@ -476,10 +476,11 @@ static void inv_mul_impl(const NttPlan &p, u64 *dst, const TensorSrc &ts, const 
 
 template<int LOGN>
 static void fwd_bconv_impl(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
-                           const TensorSrc *ts, const BarG *bar1, cudaStream_t st) {
+                           const TensorSrc *ts, const BarG *bar1, cudaStream_t st, int phase) {
     opt_in_all<LOGN>();
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    launch_pdl(k_fwd_cols_bconv<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, bl);
+    if (phase != 2) launch_pdl(k_fwd_cols_bconv<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, bl);
+    if (phase == 1) return;
     if (!ea) launch_pdl(k_fwd_rows<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
     else if (!ts) launch_pdl(k_fwd_rows_epi<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p, *ea);
     else launch_pdl(k_fwd_rows_epi_tensor<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p, *ea, *ts, bar1);
@@ -493,9 +494,9 @@ cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, con
 }
 
 cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
-                              const TensorSrc *ts, const BarG *bar1, cudaStream_t st) {
+                              const TensorSrc *ts, const BarG *bar1, cudaStream_t st, int phase) {
     if (ll.count == 0) return cudaSuccess;
-    PFHE_DISPATCH_LOGN(fwd_bconv_impl, p, dst, ll, bl, ea, ts, bar1, st)
+    PFHE_DISPATCH_LOGN(fwd_bconv_impl, p, dst, ll, bl, ea, ts, bar1, st, phase)
     return cudaGetLastError();
 }
 

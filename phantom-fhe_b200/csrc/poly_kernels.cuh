@@ -272,17 +272,38 @@ struct OwnSrc {
     const u64 *a1, *b1;
     int alpha;
 };
-__global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64 *t, const u64 *const *evk,
-                                                            const Modulus *mod, const BarG *bar, const BarG *bar0,
-                                                            RowArith ra, OwnSrc os, const uint32_t *perm, int accumulate,
-                                                            size_t n, int l, int m, int size_Q, int size_QP, int beta) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const int j = blockIdx.y;
+struct InnerProdArgs {
+    u64 *cx;
+    const u64 *t;
+    const u64 *const *evk;
+    const Modulus *mod;
+    const BarG *bar, *bar0;
+    RowArith ra;
+    OwnSrc os;
+    const uint32_t *perm;
+    int accumulate;
+    size_t n;
+    int l, m, size_Q, size_QP, beta;
+    int j0, j_count;   // limbs [j0, j0 + j_count) of cx
+};
+
+// one tile: limb j of cx (both polynomials), coefficients [bx * 2 * EW_THREADS, +2 * EW_THREADS)
+__device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const int j, const unsigned bx) {
+    u64 *cx = A.cx;
+    const u64 *t = A.t;
+    const u64 *const *evk = A.evk;
+    const Modulus *mod = A.mod;
+    const BarG *bar = A.bar, *bar0 = A.bar0;
+    const RowArith &ra = A.ra;
+    const OwnSrc &os = A.os;
+    const uint32_t *perm = A.perm;
+    const int accumulate = A.accumulate;
+    const size_t n = A.n;
+    const int l = A.l, m = A.m, size_Q = A.size_Q, size_QP = A.size_QP, beta = A.beta;
     const int row = j < l ? j : size_Q + (j - l);
     const Modulus md = mod[row];
     const BarG bg = bar[row];   // growth class ceil(log2 beta)
-    const size_t x = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const size_t x = ((size_t) bx * EW_THREADS + threadIdx.x) * 2;
     const size_t m_n = (size_t) m * n, qp_n = (size_t) size_QP * n;
     const int own_d = (os.alpha > 0 && j < l) ? j / os.alpha : -1;   // digit whose own limb this is
     // own-digit operand (fused pipeline): from c2, or a1 * b1; otherwise unused
@@ -383,6 +404,23 @@ __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(u64 *cx, const u64
     }
     st2(cx + (size_t) j * n + x, r00, r01);
     st2(cx + m_n + (size_t) j * n + x, r10, r11);
+}
+
+__global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(const InnerProdArgs A) {
+    pdl_launch_dependents();
+    pdl_wait();
+    inner_prod_tile(A, (int) blockIdx.y + A.j0, blockIdx.x);
+}
+
+// the same tiles walked by a grid that leaves room on every SM: used when the inner product runs beside the
+// (latency-bound, higher-priority) mod-down chain of the fused key switch
+__global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod_persist(const InnerProdArgs A) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const unsigned nbx = (unsigned) (A.n / (2 * EW_THREADS));
+    const unsigned total = nbx * (unsigned) A.j_count;
+    for (unsigned tile = blockIdx.x; tile < total; tile += gridDim.x)
+        inner_prod_tile(A, A.j0 + (int) (tile % (unsigned) A.j_count), tile / (unsigned) A.j_count);
 }
 
 // ---------------------------------------------------------------------------------------------------
