@@ -423,11 +423,32 @@ __device__ __forceinline__ PerElemLoad<T, F> per_elem_load(F f) { return PerElem
 template<class T, class F>
 __device__ __forceinline__ PerElemStore<T, F> per_elem_store(F f) { return PerElemStore<T, F>{f}; }
 
+#ifdef PFHE_TIMELINE
+// debug build (make timeline): thread 0 of every CTA of a forward pass leaves cycle stamps of its phases
+static __device__ long long g_tl[(size_t) 2 * 65536 * 16];   // per translation unit: only ntt_kernels.cu uses it
+#define TL_MARK(slot)                                                                                     \
+    if (threadIdx.x == 0) g_tl[tl_base + (slot)] = clock64();
+#else
+#define TL_MARK(slot)
+#endif
+
 template<class A, int P, bool ROWS, int LOGN, int SBASE, class Load, class Store>
 __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Load load, Store store) {
     constexpr int NR = Sched<P>::NR;
     typename A::T x[NTT_EPT];
     const int tid = threadIdx.x;
+#ifdef PFHE_TIMELINE
+    const size_t tl_base = (((size_t) (ROWS ? 1 : 0) << 16) + (size_t) blockIdx.y * gridDim.x + blockIdx.x) * 16;
+    if (threadIdx.x == 0) {
+        long long gt;
+        unsigned sm;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(sm));
+        g_tl[tl_base + 0] = gt;
+        g_tl[tl_base + 1] = sm;
+    }
+    TL_MARK(2)
+#endif
 
     auto run_round = [&](auto ri_tag) {
         constexpr int RI = decltype(ri_tag)::value;
@@ -447,6 +468,11 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
                 for (int k = 0; k < (1 << M::R); k++)
                     gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
             load.gather(gi, x);
+#ifdef PFHE_TIMELINE
+#pragma unroll
+            for (int k = 0; k < NTT_EPT; k++) asm volatile("" ::"l"(A::raw(x[k])));   // wait for the loads here
+            TL_MARK(3)
+#endif
         } else {
 #pragma unroll
             for (int g = 0; g < M::G; g++)
@@ -455,6 +481,11 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
         }
         if constexpr (RI == 0 && !ROWS) mbar_wait(cx.bar, 0);   // staged twiddles landed (overlapped the gather)
         fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, c, cx.tile, cx.c);
+#ifdef PFHE_TIMELINE
+#pragma unroll
+        for (int k = 0; k < NTT_EPT; k++) asm volatile("" ::"l"(A::raw(x[k])));
+        TL_MARK(4 + 2 * RI)
+#endif
         // scatter
         constexpr bool DIRECT_OUT = (RI == NR - 1) && !ROWS;
         if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
@@ -473,6 +504,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
                 for (int k = 0; k < (1 << M::R); k++) smem[s0[g] ^ M::kc(k)] = A::raw(x[(g << M::R) + k]);
             __syncthreads();
         }
+        TL_MARK(5 + 2 * RI)
     };
 
     run_round(std::integral_constant<int, 0>{});
@@ -492,6 +524,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
         }
         store.scatter(gi, x);
     }
+    TL_MARK(12)
 }
 
 // Inverse pass over one tile (rounds in reverse order).
