@@ -130,6 +130,17 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
                             const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
                             void *stream);
+/* `count` independent multiply_and_relin ops on device buffers (arrays of `count` device pointers held in HOST
+ * memory).  The reference runs independent ciphertexts on independent host threads / cudaStreamPerThread
+ * (src/CMakeLists.txt:39, evaluate.cu:1079); here the ops go round-robin over pfhe_engine_lanes() internal streams,
+ * each with its own workspace, forked from and joined back into `stream`.  destination[i] must not alias an operand.
+ * CKKS / BGV. */
+int pfhe_multiply_and_relin_batch(pfhe_engine *e, size_t chain_index, const uint64_t *const *encrypted1,
+                                  const uint64_t *const *encrypted2, uint64_t *const *destination, size_t count,
+                                  const uint64_t *const *relin_keys, void *stream);
+/* number of lanes of the batched entry points (1..4, default 2; 1 = strictly one op at a time) */
+int pfhe_engine_set_lanes(pfhe_engine *e, int lanes);
+int pfhe_engine_lanes(const pfhe_engine *e);
 /* multiply_inplace alone: destination = [3][l][n] (BFV: must not alias an operand) */
 int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1, const uint64_t *encrypted2,
                   uint64_t *destination, void *stream);

@@ -257,6 +257,31 @@ def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
         encrypted1.scale = encrypted1.scale * encrypted2.scale
 
 
+def multiply_and_relin_batch(context, encrypted1, encrypted2, relin_keys):
+    """multiply_and_relin_inplace over lists of independent ciphertext pairs (one C-ABI call, ops interleaved over the
+    engine's lanes); encrypted1[i] receives the product like the in-place form."""
+    if len(encrypted1) != len(encrypted2):
+        raise ValueError("batch sizes differ")
+    if not encrypted1:
+        return
+    ci = encrypted1[0].chain_index
+    for a, b in zip(encrypted1, encrypted2):
+        _require_ntt(context, a)
+        _require_ntt(context, b)
+        if a.chain_index != ci or b.chain_index != ci:
+            raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+    dst = [torch.empty_like(a.data) for a in encrypted1]
+    n = len(dst)
+    arr = ctypes.c_void_p * n
+    check(lib.pfhe_multiply_and_relin_batch(context._h, ci, arr(*[_ptr(a.data) for a in encrypted1]),
+                                            arr(*[_ptr(b.data) for b in encrypted2]), arr(*[_ptr(d) for d in dst]), n,
+                                            relin_keys.public_keys_ptr(), _stream()))
+    for a, b, d in zip(encrypted1, encrypted2, dst):
+        a.data = d
+        if context.scheme == scheme_type.ckks:
+            a.scale = a.scale * b.scale
+
+
 def apply_galois_inplace(context, encrypted, galois_elt, galois_keys):
     """apply_galois_inplace (src/evaluate.cu:1567-1630)."""
     if encrypted.size() > 2:

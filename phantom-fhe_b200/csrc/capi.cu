@@ -344,6 +344,25 @@ int pfhe_multiply_and_relin_host_batch(pfhe_engine *e, size_t chain_index, const
                                       count, K(rlk), S(stream));
     API_END
 }
+int pfhe_multiply_and_relin_batch(pfhe_engine *e, size_t chain_index, const uint64_t *const *ct1,
+                                  const uint64_t *const *ct2, uint64_t *const *dst, size_t count,
+                                  const uint64_t *const *rlk, void *stream) {
+    API_BEGIN
+    require(ct1 && ct2 && dst, "null batch pointers");
+    require(e->impl.scheme() != Scheme::bfv, "batched multiply_and_relin covers CKKS / BGV");
+    for (size_t i = 0; i < count; i++)
+        require(dst[i] && ct1[i] && ct2[i] && dst[i] != ct1[i] && dst[i] != ct2[i], "destination aliases an operand");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.multiply_relin_batch(l, reinterpret_cast<const u64 *const *>(ct1), reinterpret_cast<const u64 *const *>(ct2),
+                                 reinterpret_cast<u64 *const *>(dst), count, K(rlk), S(stream));
+    API_END
+}
+int pfhe_engine_set_lanes(pfhe_engine *e, int lanes) {
+    API_BEGIN
+    e->impl.set_lanes(lanes);
+    API_END
+}
+int pfhe_engine_lanes(const pfhe_engine *e) { return e ? e->impl.lanes() : 0; }
 int pfhe_rotate_host(pfhe_engine *e, size_t chain_index, const uint64_t *h, int step, uint64_t *hout,
                      const uint64_t *const *glk, void *stream) {
     API_BEGIN

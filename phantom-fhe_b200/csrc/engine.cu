@@ -90,11 +90,9 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
     // workspace sized for the top level
     const size_t alpha = std::max(size_P_, 1);
     const size_t beta_max = (size_Q_ + alpha - 1) / alpha;
-    ws_.t_cks.alloc((size_t) size_Q_ * n_);
-    ws_.t_mod_up.alloc(beta_max * size_QP_ * n_);
-    ws_.cx.alloc((size_t) 2 * size_QP_ * n_);
-    ws_.delta.alloc((size_t) 2 * (size_Q_ + 1) * n_);
-    ws_.tmp.alloc((size_t) 3 * size_Q_ * n_);
+    (void) beta_max;
+    alloc_workspace(ws_);
+    if (const char *e = std::getenv("PFHE_LANES")) set_lanes(std::atoi(e));
 
     // Galois permutation tables (reference include/galois.cuh:98-113)
     d_perm_.resize(galois_elts_.size());
@@ -111,7 +109,75 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
     }
 }
 
+void Engine::alloc_workspace(Workspace &w) const {
+    const size_t alpha = std::max(size_P_, 1);
+    const size_t beta_max = (size_Q_ + alpha - 1) / alpha;
+    w.t_cks.alloc((size_t) size_Q_ * n_);
+    w.t_mod_up.alloc(beta_max * size_QP_ * n_);
+    w.cx.alloc((size_t) 2 * size_QP_ * n_);
+    w.delta.alloc((size_t) 2 * (size_Q_ + 1) * n_);
+    w.tmp.alloc((size_t) 3 * size_Q_ * n_);
+}
+
+void Engine::set_lanes(int k) {
+    if (k < 1 || k > MAX_LANES) throw std::invalid_argument("lane count must be 1..4");
+    n_lanes_ = k;
+}
+
+// exchange the engine's active workspace / fork-join objects with those of lane k (k = 0: nothing to do)
+void Engine::swap_lane(int k) {
+    if (k == 0) return;
+    Lane &L = lane_[k];
+    std::swap(ws_, L.ws);
+    std::swap(s_side_, L.s_side);
+    std::swap(ev_fork_, L.ev_fork);
+    std::swap(ev_join_, L.ev_join);
+}
+
+void Engine::multiply_relin_batch(int l, const u64 *const *ct1, const u64 *const *ct2, u64 *const *out, size_t count,
+                                  const u64 *const *rlk, cudaStream_t st) {
+    const int L = (int) std::min<size_t>((size_t) n_lanes_, count);
+    if (L <= 1) {
+        for (size_t i = 0; i < count; i++) multiply_relin(l, out[i], ct1[i], ct2[i], rlk, st);
+        return;
+    }
+    if (!lane_[0].ev_done) PFHE_CUDA(cudaEventCreateWithFlags(&lane_[0].ev_done, cudaEventDisableTiming));
+    for (int k = 1; k < L; k++) {
+        Lane &ln = lane_[k];
+        if (!ln.stream) {
+            PFHE_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
+            PFHE_CUDA(cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming));
+            alloc_workspace(ln.ws);
+        }
+    }
+    // lane 0 is the caller's stream; the others start after whatever the caller already queued on it
+    PFHE_CUDA(cudaEventRecord(lane_[0].ev_done, st));
+    for (int k = 1; k < L; k++) PFHE_CUDA(cudaStreamWaitEvent(lane_[k].stream, lane_[0].ev_done, 0));
+    for (size_t i = 0; i < count; i++) {
+        const int k = (int) (i % (size_t) L);
+        swap_lane(k);
+        try {
+            multiply_relin(l, out[i], ct1[i], ct2[i], rlk, k == 0 ? st : lane_[k].stream);
+        } catch (...) {
+            swap_lane(k);
+            throw;
+        }
+        swap_lane(k);
+    }
+    for (int k = 1; k < L; k++) {
+        PFHE_CUDA(cudaEventRecord(lane_[k].ev_done, lane_[k].stream));
+        PFHE_CUDA(cudaStreamWaitEvent(st, lane_[k].ev_done, 0));
+    }
+}
+
 Engine::~Engine() {
+    for (Lane &ln : lane_) {
+        if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
+        if (ln.ev_join) cudaEventDestroy(ln.ev_join);
+        if (ln.ev_done) cudaEventDestroy(ln.ev_done);
+        if (ln.s_side) cudaStreamDestroy(ln.s_side);
+        if (ln.stream) cudaStreamDestroy(ln.stream);
+    }
     if (ev_fork_) cudaEventDestroy(ev_fork_);
     if (ev_join_) cudaEventDestroy(ev_join_);
     if (s_side_) cudaStreamDestroy(s_side_);

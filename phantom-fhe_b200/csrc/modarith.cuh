@@ -152,13 +152,28 @@ __device__ __forceinline__ double from_u64(u64 v) {   // exact for v < 2^52
 __device__ __forceinline__ u64 to_u64(double v) {     // exact for integers 0 <= v < 2^52
     return ((u64) __double_as_longlong(v + TWO52)) & 0x000fffffffffffffull;
 }
+// rint(y * c): quotient estimate of the FP64 modular product.  Two forms with the same accuracy for our purposes
+// (off by at most one from the exact quotient): one FMA + one add against 1.5 * 2^52 on the FP64 pipe, or one
+// multiply plus FRND.F64, which issues beside the FP64 pipe (tools/microbench.cu).
+#ifndef PFHE_FRND
+#define PFHE_FRND 0
+#endif
+__device__ __forceinline__ double rint_q(double y, double c) {
+#if PFHE_FRND
+    double k;
+    asm("cvt.rni.f64.f64 %0, %1;" : "=d"(k) : "d"(y * c));
+    return k;
+#else
+    return __fma_rn(y, c, MAGIC) - MAGIC;
+#endif
+}
 __device__ __forceinline__ double reduce(double v, double q, double qinv) {   // -> [-q/2, q/2]
-    const double k = __fma_rn(v, qinv, MAGIC) - MAGIC;
+    const double k = rint_q(v, qinv);
     return __fma_rn(-k, q, v);
 }
 // y * w mod q for a constant w with precomputed winv = w/q: result in (-0.63q, 0.63q)
 __device__ __forceinline__ double mulmod_c(double y, double w, double winv, double q) {
-    const double k = __fma_rn(y, winv, MAGIC) - MAGIC;
+    const double k = rint_q(y, winv);
     const double p = y * w;
     const double e = __fma_rn(y, w, -p);
     return __fma_rn(-k, q, p) + e;
@@ -167,7 +182,7 @@ __device__ __forceinline__ double mulmod_c(double y, double w, double winv, doub
 __device__ __forceinline__ double mulmod_v(double a, double b, double q, double qinv) {
     const double p = a * b;
     const double e = __fma_rn(a, b, -p);
-    const double k = __fma_rn(p, qinv, MAGIC) - MAGIC;
+    const double k = rint_q(p, qinv);
     return __fma_rn(-k, q, p) + e;
 }
 __device__ __forceinline__ u64 canon(double v, double q) {   // v in (-q, q) -> [0, q)

@@ -239,14 +239,14 @@ struct FpArith {
     // y * w mod q, result in (-0.62q, 0.62q); exact for |y| < 2^51, w < q < 2^47 (tests/test_fp_modmul.py)
     __device__ static __forceinline__ T mulmod(T y, const Tw w, const Consts &c) {
         const double wv = __longlong_as_double((long long) w.x), wi = __longlong_as_double((long long) w.y);
-        const double k = __fma_rn(y, wi, MAGIC) - MAGIC;
+        const double k = fp::rint_q(y, wi);
         const double p = y * wv;
         const double e = __fma_rn(y, wv, -p);
         const double r = __fma_rn(-k, c.q, p);
         return r + e;
     }
     __device__ static __forceinline__ T reduce(T v, const Consts &c) {           // -> [-q/2, q/2]
-        const double k = __fma_rn(v, c.qinv, MAGIC) - MAGIC;
+        const double k = fp::rint_q(v, c.qinv);
         return __fma_rn(-k, c.q, v);
     }
     template<bool CSUB>

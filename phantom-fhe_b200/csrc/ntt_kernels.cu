@@ -207,15 +207,93 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_rows_mul(u6
 }
 
 // base conversion as the gather of a column pass: inputs outer, elements inner, so the eight loads of one input
-// limb are in flight together and the uniform "split this input" branch sits outside the element loop
+// limb are in flight together and the uniform "split this input" branch sits outside the element loop.
+//
+// FP-limb outputs (p < 2^46) split the work over two pipes: with terms a_t (an input residue, or its 30-bit halves
+// when it comes from a modulus >= 2^46) and matrix entries M_t < p, the quotient K = rint(sum a_t * (M_t / p)) is
+// formed on the FP64 pipe (one conversion and one FMA per term; absolute error < 0.2, proof in DESIGN.md 4.2), the
+// remainder r = sum a_t * M_t - K * p, |r| < 0.7 p, as the low 64 bits of that expression on the integer pipe
+// (3 IMADs per 64-bit term, 2 per half).  r enters the butterflies as a signed FP64 integer; the canonical residues
+// stored at the end of the transform are the same as for any other exact evaluation of bconv_matmul.
+#ifndef PFHE_BCONV_DUAL
+#define PFHE_BCONV_DUAL 0
+#endif
+struct Lo64 {   // low 64 bits of a sum of products; the cross terms go straight into the upper word
+    u32 lo, hi;
+    __device__ __forceinline__ void mac(u64 a, u64 b) {   // full 64-bit a
+        const u32 a0 = (u32) a, a1 = (u32) (a >> 32), b0 = (u32) b, b1 = (u32) (b >> 32);
+        u64 acc = ((u64) hi << 32) | lo;
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a0), "r"(b0));
+        lo = (u32) acc;
+        hi = a1 * b0 + (a0 * b1 + (u32) (acc >> 32));
+    }
+    __device__ __forceinline__ void mac32(u32 a0, u64 b) {   // a < 2^32
+        const u32 b0 = (u32) b, b1 = (u32) (b >> 32);
+        u64 acc = ((u64) hi << 32) | lo;
+        asm("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc) : "r"(a0), "r"(b0));
+        lo = (u32) acc;
+        hi = a0 * b1 + (u32) (acc >> 32);
+    }
+    __device__ __forceinline__ u64 value() const { return ((u64) hi << 32) | lo; }
+};
+
 template<int LOGN>
 struct BconvGatherFp {
     const u64 *in;
-    const double2 *mf;   // [ni][2]
+    const double2 *mf;   // [ni][2], global memory: read where used (CTA-uniform, L1 broadcast) to keep registers free
     int ni;
     unsigned big;
     double q;
     __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], double (&x)[NTT_EPT]) const {
+#if PFHE_BCONV_DUAL
+        constexpr int HB = NTT_EPT / 2;   // two half-batches: accumulators of four elements live at a time
+        const u64 np = 0 - (u64) q;
+        // bits(2^52 + K) carry 0x43300000 in the upper word: its product with the low word of -p is taken out here;
+        // the accumulator starts at bits(1.5 * 2^52) so that the signed remainder converts with one subtraction
+        const u32 h0 = 0x43380000u - 0x43300000u * (u32) np;
+#pragma unroll
+        for (int h = 0; h < NTT_EPT; h += HB) {
+            double s[HB];
+            Lo64 r[HB];
+#pragma unroll
+            for (int k = 0; k < HB; k++) s[k] = 0.0, r[k].lo = 0u, r[k].hi = h0;
+#pragma unroll
+            for (int i = 0; i < FUSE_MAX_IN; i++) {
+                if (i < ni) {
+                    u64 y[HB];
+#pragma unroll
+                    for (int k = 0; k < HB; k++) y[k] = in[((size_t) i << LOGN) + idx[h + k]];
+                    const double2 m0 = __ldg(&mf[2 * i]);
+                    const u64 M0 = (u64) m0.x;
+                    if ((big >> i) & 1) {
+                        const double2 m1 = __ldg(&mf[2 * i + 1]);
+                        const u64 M1 = (u64) m1.x;
+                        const u32 msk = (1u << fp::SPLIT_BITS) - 1;
+#pragma unroll
+                        for (int k = 0; k < HB; k++) {
+                            const u32 ylo = (u32) y[k] & msk, yhi = (u32) (y[k] >> fp::SPLIT_BITS);
+                            s[k] = __fma_rn(fp::from_u64(ylo), m0.y, s[k]);
+                            s[k] = __fma_rn(fp::from_u64(yhi), m1.y, s[k]);
+                            r[k].mac32(ylo, M0);
+                            r[k].mac32(yhi, M1);
+                        }
+                    } else {
+#pragma unroll
+                        for (int k = 0; k < HB; k++) {
+                            s[k] = __fma_rn(fp::from_u64(y[k]), m0.y, s[k]);
+                            r[k].mac(y[k], M0);
+                        }
+                    }
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < HB; k++) {
+                const u64 kb = (u64) __double_as_longlong(s[k] + fp::TWO52);   // 2^52 + K, exact integer
+                r[k].mac(kb, np);
+                x[h + k] = __longlong_as_double((long long) r[k].value()) - fp::MAGIC;
+            }
+        }
+#else
 #pragma unroll
         for (int k = 0; k < NTT_EPT; k++) x[k] = 0.0;
 #pragma unroll
@@ -224,7 +302,7 @@ struct BconvGatherFp {
                 u64 y[NTT_EPT];
 #pragma unroll
                 for (int k = 0; k < NTT_EPT; k++) y[k] = in[((size_t) i << LOGN) + idx[k]];
-                const double2 m0 = mf[2 * i], m1 = mf[2 * i + 1];
+                const double2 m0 = __ldg(&mf[2 * i]), m1 = __ldg(&mf[2 * i + 1]);
                 if ((big >> i) & 1) {
                     const u64 msk = (1ull << fp::SPLIT_BITS) - 1;
 #pragma unroll
@@ -238,6 +316,7 @@ struct BconvGatherFp {
                 }
             }
         }
+#endif
     }
 };
 template<int LOGN>
@@ -275,13 +354,7 @@ __device__ __forceinline__ void fwd_cols_bconv_body(u64 *smem, const Tw *stw, ui
     const int ni = bl.ni;
     const unsigned big = bl.in_big[slot];
     if constexpr (std::is_same<A, FpArith>::value) {
-        double2 mf[2 * FUSE_MAX_IN];
-#pragma unroll
-        for (int i = 0; i < FUSE_MAX_IN; i++)
-            if (i < ni) {
-                mf[2 * i] = bl.matf[2 * ((size_t) bl.mat_row[slot] * ni + i)];
-                mf[2 * i + 1] = bl.matf[2 * ((size_t) bl.mat_row[slot] * ni + i) + 1];
-            }
+        const double2 *mf = bl.matf + 2 * ((size_t) bl.mat_row[slot] * ni);
         forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
                 smem, cx, BconvGatherFp<LOGN>{in, mf, ni, big, c.q},
                 per_elem_store<double>([&](size_t i, double v) { d[i] = A::raw(v); }));

@@ -252,6 +252,44 @@ def test_multiply_relin_rotate_rescale_small(cfg):
         assert np.array_equal(c.to_host(), want), f"rotate {s}"
 
 
+@pytest.mark.parametrize("lanes", [1, 2, 3])
+def test_multiply_relin_batch(lanes):
+    """pfhe_multiply_and_relin_batch: independent pairs interleaved over the engine's lanes give, pair by pair, the
+    words of the one-at-a-time op (and of the oracle); ragged counts, empty batch, mixed with single ops."""
+    ps = H.params_small(**KS_SETS[0])
+    ctx = make_context(ps)
+    pf.check(pf.lib.pfhe_engine_set_lanes(ctx._h, lanes))
+    assert pf.lib.pfhe_engine_lanes(ctx._h) == lanes
+    o = H.oracle()
+    l, n = ps.limbs(), ps.n
+    rlk_h = H.switch_key(ps, 100)
+    rlk = pf.PhantomRelinKey(ctx, list(rlk_h))
+    count = 5
+    a = [H.ciphertext(ps, 10 + 2 * i) for i in range(count)]
+    b = [H.ciphertext(ps, 11 + 2 * i) for i in range(count)]
+    want = []
+    for x, y in zip(a, b):
+        w = np.zeros((2, l, n), dtype=np.uint64)
+        o.orc_multiply_relin(ps.octx(), l, P(x), P(y), P(rlk_h), P(w))
+        want.append(w)
+    pf.multiply_and_relin_batch(ctx, [], [], rlk)   # empty batch is a no-op
+    for cnt in (1, 2, 5):
+        ca = [pf.PhantomCiphertext.from_host(ctx, x) for x in a[:cnt]]
+        cb = [pf.PhantomCiphertext.from_host(ctx, y) for y in b[:cnt]]
+        pf.multiply_and_relin_batch(ctx, ca, cb, rlk)
+        # a single op right behind the batch on the same stream (the batch has joined back into it)
+        single = pf.PhantomCiphertext.from_host(ctx, a[0])
+        pf.multiply_and_relin_inplace(ctx, single, cb[0], rlk)
+        for i in range(cnt):
+            assert np.array_equal(ca[i].to_host(), want[i]), f"batch of {cnt}, pair {i}, lanes {lanes}"
+        assert np.array_equal(single.to_host(), want[0])
+    with pytest.raises(Exception):   # destination aliasing an operand is refused
+        x = dev(a[0])
+        arr = (ctypes.c_void_p * 1)(x.data_ptr())
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        pf.check(pf.lib.pfhe_multiply_and_relin_batch(ctx._h, 1, arr, arr, arr, 1, rlk.public_keys_ptr(), st))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # BGV / BFV forms of the key switch and the modulus switch (rns_bconv.cu:583-606,636-652,790-827; rns.cu:1082-1235)
 # ---------------------------------------------------------------------------------------------------------

@@ -43,8 +43,11 @@ template<int MODE>
 __global__ void __launch_bounds__(256) k(u64 *out, u64 seed, double dseed) {
     u64 a[UNROLL];
     double d[UNROLL];
-    u32 lo[UNROLL], hi[UNROLL];
+    u32 lo[UNROLL], hi[UNROLL], x2[UNROLL];
+    double e2[UNROLL];
     for (int i = 0; i < UNROLL; i++) {
+        x2[i] = i;
+        e2[i] = dseed * 7 + i;
         a[i] = seed + threadIdx.x * 977 + i * 13;
         d[i] = dseed + threadIdx.x * 0.5 + i;
         lo[i] = (u32) a[i];
@@ -86,11 +89,61 @@ __global__ void __launch_bounds__(256) k(u64 *out, u64 seed, double dseed) {
                 a[i] = lo_mac2(a[i], w, mulhi_sloppy(a[i], ws), nq);
             } else if (MODE == 12) {
                 a[i] = a[i] * w + mulhi_mw(a[i], ws) * nq;
+            } else if (MODE == 13) {   // FRND.F64
+                asm volatile("cvt.rni.f64.f64 %0, %0;" : "+d"(d[i]));
+            } else if (MODE == 14) {   // F2I.S64.F64
+                asm volatile("cvt.rni.s64.f64 %0, %1;" : "=l"(a[i]) : "d"(d[i]));
+            } else if (MODE == 15) {   // I2F.F64.S64
+                asm volatile("cvt.rn.f64.s64 %0, %1;" : "=d"(d[i]) : "l"(a[i]));
+            } else if (MODE == 16) {   // DFMA and IMAD.WIDE side by side (independent chains)
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dw), "d"(dq));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(lo[i]), "r"(hi[i]));
+            } else if (MODE == 17) {   // DFMA and FRND side by side
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dw), "d"(dq));
+                asm volatile("cvt.rni.f64.f64 %0, %1;" : "=d"(e2[i]) : "d"(d[i]));
+            } else if (MODE == 18) {   // FP64 modmul with the quotient rounded by FRND (5 fp64 ops + FRND)
+                double y = d[i];
+                double kq;
+                asm("cvt.rni.f64.f64 %0, %1;" : "=d"(kq) : "d"(y * (dinv * dw)));
+                double p = y * dw;
+                double e = __fma_rn(y, dw, -p);
+                double r = __fma_rn(-kq, dq, p);
+                d[i] = r + e;
+            } else if (MODE == 19) {   // dual-pipe modmul: quotient on the FP64 pipe, remainder as low 64 bits on the integer pipe
+                const u64 y = a[i] & 0xfffffffffffull;
+                const double yd = __longlong_as_double((long long) (y | 0x4330000000000000ull)) - 4503599627370496.0;
+                const u64 kb = (u64) __double_as_longlong(__fma_rn(yd, dinv * dw, magic));
+                a[i] = lo_mac2(y, w, kb, nq);
+            } else if (MODE == 20) {   // DFMA + 2 IMAD.WIDE + 2 IADD3-class per iteration
+                asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(d[i]) : "d"(dw), "d"(dq));
+                asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(a[i]) : "r"(lo[i]), "r"(hi[i]));
+                asm volatile("mad.lo.u32 %0, %1, %2, %0;" : "+r"(lo[i]) : "r"(hi[i]), "r"((u32) it));
+                asm volatile("add.u32 %0, %0, %1;" : "+r"(hi[i]) : "r"((u32) it));
+                asm volatile("xor.b32 %0, %0, %1;" : "+r"(x2[i]) : "r"((u32) it));
+            } else if (MODE == 21) {   // two FP64 modmuls + one dual-pipe modmul, independent chains
+                {
+                    double y = d[i];
+                    double kq = __fma_rn(y, dinv * dw, magic) - magic;
+                    double p = y * dw;
+                    double e = __fma_rn(y, dw, -p);
+                    d[i] = __fma_rn(-kq, dq, p) + e;
+                }
+                {
+                    double y = e2[i];
+                    double kq = __fma_rn(y, dinv * dw, magic) - magic;
+                    double p = y * dw;
+                    double e = __fma_rn(y, dw, -p);
+                    e2[i] = __fma_rn(-kq, dq, p) + e;
+                }
+                const u64 y = a[i] & 0xfffffffffffull;
+                const double yd = __longlong_as_double((long long) (y | 0x4330000000000000ull)) - 4503599627370496.0;
+                const u64 kb = (u64) __double_as_longlong(__fma_rn(yd, dinv * dw, magic));
+                a[i] = lo_mac2(y, w, kb, nq);
             }
         }
     }
     u64 acc = 0;
-    for (int i = 0; i < UNROLL; i++) acc += a[i] + (u64) d[i] + lo[i];
+    for (int i = 0; i < UNROLL; i++) acc += a[i] + (u64) d[i] + lo[i] + x2[i] + hi[i] + (u64) e2[i];
     out[blockIdx.x * blockDim.x + threadIdx.x] = acc;
 }
 
@@ -135,5 +188,14 @@ int main() {
     run<11>("Shoup lazy sloppy-hi + lo_mac2", 1);
     run<4>("fma.rn.f64 (DFMA)", 1);
     run<5>("FP64 error-free modmul", 1);
+    run<13>("cvt.rni.f64.f64 (FRND.F64)", 1);
+    run<14>("cvt.rni.s64.f64 (F2I)", 1);
+    run<15>("cvt.rn.f64.s64 (I2F)", 1);
+    run<16>("DFMA + IMAD.WIDE pairs", 1);
+    run<17>("DFMA + FRND pairs", 1);
+    run<18>("FP64 modmul, FRND quotient", 1);
+    run<19>("dual-pipe modmul (FP64 quotient, int lo64)", 1);
+    run<20>("DFMA + IMAD.WIDE + IMAD + 2 ALU groups", 1);
+    run<21>("2 FP64 modmuls + 1 dual-pipe modmul groups", 1);
     return 0;
 }
