@@ -644,12 +644,16 @@ void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *e
     const InnerProdArgs A{cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), bar(1, 0),
                           RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, perm,
                           accumulate ? 1 : 0, n_, l, lv.m, size_Q_, size_QP_, lv.beta, j_begin, j_count};
-    if (persist_ctas > 0) {
-        launch_pdl(k_inner_prod_persist, dim3((unsigned) persist_ctas), EW_THREADS, 0, st, A);
-    } else {
-        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), j_count);
-        launch_pdl(k_inner_prod, grid, EW_THREADS, 0, st, A);
-    }
+    const unsigned tiles = (unsigned) (n_ / IP_TILE) * (unsigned) j_count;
+    const dim3 grid(persist_ctas > 0 ? std::min((unsigned) persist_ctas, tiles) : tiles);
+    const bool plain = !perm && !accumulate;
+    auto go = [&](auto kern) { launch_pdl(kern, grid, EW_THREADS, 0, st, A); };
+    if (!plain) go(k_inner_prod<0, false>);
+    else if (lv.beta == 1) go(k_inner_prod<1, true>);
+    else if (lv.beta == 2) go(k_inner_prod<2, true>);
+    else if (lv.beta == 3) go(k_inner_prod<3, true>);
+    else if (lv.beta == 4) go(k_inner_prod<4, true>);
+    else go(k_inner_prod<0, true>);
     check_launch("k_inner_prod");
 }
 

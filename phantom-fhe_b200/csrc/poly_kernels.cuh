@@ -287,140 +287,155 @@ struct InnerProdArgs {
     int j0, j_count;   // limbs [j0, j0 + j_count) of cx
 };
 
-// one tile: limb j of cx (both polynomials), coefficients [bx * 2 * EW_THREADS, +2 * EW_THREADS)
+// One tile: limb j of cx (both polynomials), IP_PAIRS * 2 * EW_THREADS consecutive coefficients; a thread owns
+// IP_PAIRS coefficient pairs EW_THREADS pairs apart (every warp access is one contiguous 512-byte run).
+// BETA > 0 fixes the digit count at compile time (full unroll, key pointers in registers); PLAIN = no Galois
+// permutation and no accumulation into cx (the key-switch proper; hoisting takes the general form).  Everything that
+// depends only on (j, launch) is set up once per tile, outside the pair loop: with two coefficients per thread and a
+// run-time digit loop the set-up and addressing were 3/4 of the instructions (profiles/r1b_inner_prod_mix.md).
+constexpr int IP_PAIRS = 2;
+constexpr int IP_TILE = IP_PAIRS * 2 * EW_THREADS;
+
+template<int BETA, bool PLAIN>
 __device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const int j, const unsigned bx) {
-    u64 *cx = A.cx;
-    const u64 *t = A.t;
-    const u64 *const *evk = A.evk;
-    const Modulus *mod = A.mod;
-    const BarG *bar = A.bar, *bar0 = A.bar0;
-    const RowArith &ra = A.ra;
-    const OwnSrc &os = A.os;
-    const uint32_t *perm = A.perm;
-    const int accumulate = A.accumulate;
+    const int beta = BETA > 0 ? BETA : A.beta;
     const size_t n = A.n;
-    const int l = A.l, m = A.m, size_Q = A.size_Q, size_QP = A.size_QP, beta = A.beta;
-    const int row = j < l ? j : size_Q + (j - l);
-    const Modulus md = mod[row];
-    const BarG bg = bar[row];   // growth class ceil(log2 beta)
-    const size_t x = ((size_t) bx * EW_THREADS + threadIdx.x) * 2;
-    const size_t m_n = (size_t) m * n, qp_n = (size_t) size_QP * n;
+    const int l = A.l, m = A.m;
+    const int row = j < l ? j : A.size_Q + (j - l);
+    const size_t m_n = (size_t) m * n, qp_n = (size_t) A.size_QP * n;
+    const OwnSrc &os = A.os;
     const int own_d = (os.alpha > 0 && j < l) ? j / os.alpha : -1;   // digit whose own limb this is
-    // own-digit operand (fused pipeline): from c2, or a1 * b1; otherwise unused
-    ulonglong2 own = make_ulonglong2(0, 0), ownb = make_ulonglong2(0, 0);
-    if (own_d >= 0) {
-        if (os.c2) own = ld2(os.c2 + (size_t) j * n + x);
-        else own = ld2(os.a1 + (size_t) j * n + x), ownb = ld2(os.b1 + (size_t) j * n + x);
-    }
-    // hoisting (reference src/evaluate.cu:1775-1835): the digits are read through the Galois permutation and the
-    // result is accumulated into cx, instead of materialising the permuted digits and a temporary cx
-    size_t px0 = x, px1 = x + 1;
-    if (perm) {
-        const uint2 pp = *reinterpret_cast<const uint2 *>(perm + x);
-        px0 = pp.x, px1 = pp.y;
-    }
-    const u64 *tj = t + (size_t) j * n;
-    const size_t krow = (size_t) row * n + x;
-    auto load_t = [&](int d) -> ulonglong2 {
-        const u64 *base = tj + (size_t) d * m_n;
-        if (perm) return make_ulonglong2(base[px0], base[px1]);
-        return ld2(base + x);
-    };
-    ulonglong2 old0 = make_ulonglong2(0, 0), old1 = make_ulonglong2(0, 0);
-    if (accumulate) old0 = ld2(cx + (size_t) j * n + x), old1 = ld2(cx + m_n + (size_t) j * n + x);
-    constexpr int CH = 2;   // digits per batch: 6 independent 16-byte loads in flight per thread, 4 CTAs/SM
+    const bool own_mul = own_d >= 0 && !os.c2;
+    const uint32_t *perm = PLAIN ? nullptr : A.perm;
+    const bool accumulate = PLAIN ? false : A.accumulate != 0;
+    const u64 *tj = A.t + (size_t) j * n;
+    const u64 *ownp = own_d < 0 ? nullptr : (os.c2 ? os.c2 : os.a1) + (size_t) j * n;
+    const u64 *ownq = own_mul ? os.b1 + (size_t) j * n : nullptr;
+    u64 *c0 = A.cx + (size_t) j * n, *c1 = c0 + m_n;
     const u64 pol = l2_evict_first_policy();
-    if (ra.fp(row)) {   // CTA-uniform: every term is reduced on the FP64 pipe, the small residues are summed
-        const double q = ra.fpc[row].x, qi = ra.fpc[row].y;
-        double ox = fp::from_u64(own.x), oy = fp::from_u64(own.y);
-        if (own_d >= 0 && !os.c2) {
-            ox = fp::mulmod_v(ox, fp::from_u64(ownb.x), q, qi);
-            oy = fp::mulmod_v(oy, fp::from_u64(ownb.y), q, qi);
+    // key rows of this limb, one pointer per digit (BETA > 0: registers)
+    const u64 *kp[BETA > 0 ? BETA : 1];
+    if constexpr (BETA > 0) {
+#pragma unroll
+        for (int d = 0; d < BETA; d++) kp[d] = A.evk[d] + (size_t) row * n;
+    }
+    const size_t x_base = ((size_t) bx * IP_PAIRS * EW_THREADS + threadIdx.x) * 2;
+    const bool is_fp = A.ra.fp(row);   // CTA-uniform
+    double q = 0, qi = 0;
+    Modulus md{};
+    BarG bg{}, b0{};
+    if (is_fp) q = A.ra.fpc[row].x, qi = A.ra.fpc[row].y;
+    else md = A.mod[row], bg = A.bar[row], b0 = A.bar0[row];
+
+#pragma unroll 1
+    for (int ip = 0; ip < IP_PAIRS; ip++) {
+        const size_t x = x_base + (size_t) ip * 2 * EW_THREADS;
+        size_t px0 = x, px1 = x + 1;
+        if (perm) {   // hoisting (reference src/evaluate.cu:1775-1835): digits are read through the Galois permutation
+            const uint2 pp = *reinterpret_cast<const uint2 *>(perm + x);
+            px0 = pp.x, px1 = pp.y;
         }
-        double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
-        for (int d0 = 0; d0 < beta; d0 += CH) {
-            ulonglong2 v[CH], e0[CH], e1[CH];
-#pragma unroll
-            for (int c = 0; c < CH; c++) {
-                const int d = min(d0 + c, beta - 1);   // clamp: tail lanes re-read the last digit, masked below
-                const u64 *k0 = evk[d] + krow;
-                v[c] = load_t(d);
-                e0[c] = ld2_stream(k0, pol);
-                e1[c] = ld2_stream(k0 + qp_n, pol);
+        auto load_t = [&](int d) -> ulonglong2 {
+            const u64 *base = tj + (size_t) d * m_n;
+            if (perm) return make_ulonglong2(base[px0], base[px1]);
+            return ld2(base + x);
+        };
+        auto key = [&](int d) -> const u64 * {
+            if constexpr (BETA > 0) return kp[d] + x;
+            else return A.evk[d] + (size_t) row * n + x;
+        };
+        ulonglong2 own = make_ulonglong2(0, 0), ownb = make_ulonglong2(0, 0);
+        if (own_d >= 0) own = ld2(ownp + x);
+        if (own_mul) ownb = ld2(ownq + x);
+        ulonglong2 old0 = make_ulonglong2(0, 0), old1 = make_ulonglong2(0, 0);
+        if (accumulate) old0 = ld2(c0 + x), old1 = ld2(c1 + x);
+        constexpr int CH = 2;   // digits per batch: 6 independent 16-byte loads in flight per thread
+        if (is_fp) {   // every term is reduced on the FP64 pipe, the small residues are summed
+            double ox = fp::from_u64(own.x), oy = fp::from_u64(own.y);
+            if (own_mul) {
+                ox = fp::mulmod_v(ox, fp::from_u64(ownb.x), q, qi);
+                oy = fp::mulmod_v(oy, fp::from_u64(ownb.y), q, qi);
             }
+            double s00 = 0, s01 = 0, s10 = 0, s11 = 0;
 #pragma unroll
-            for (int c = 0; c < CH; c++) {
-                const int d = d0 + c;
-                if (d < beta) {
-                    const double vx = d == own_d ? ox : fp::from_u64(v[c].x);
-                    const double vy = d == own_d ? oy : fp::from_u64(v[c].y);
-                    s00 += fp::mulmod_v(vx, fp::from_u64(e0[c].x), q, qi);
-                    s01 += fp::mulmod_v(vy, fp::from_u64(e0[c].y), q, qi);
-                    s10 += fp::mulmod_v(vx, fp::from_u64(e1[c].x), q, qi);
-                    s11 += fp::mulmod_v(vy, fp::from_u64(e1[c].y), q, qi);
+            for (int d0 = 0; d0 < beta; d0 += CH) {
+                ulonglong2 v[CH], e0[CH], e1[CH];
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int d = min(d0 + c, beta - 1);   // clamp: a tail lane re-reads the last digit, masked below
+                    const u64 *k0 = key(d);
+                    v[c] = d != own_d ? load_t(d) : own;
+                    e0[c] = ld2_stream(k0, pol);
+                    e1[c] = ld2_stream(k0 + qp_n, pol);
+                }
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int d = d0 + c;
+                    if (d < beta) {
+                        const double vx = d == own_d ? ox : fp::from_u64(v[c].x);
+                        const double vy = d == own_d ? oy : fp::from_u64(v[c].y);
+                        s00 += fp::mulmod_v(vx, fp::from_u64(e0[c].x), q, qi);
+                        s01 += fp::mulmod_v(vy, fp::from_u64(e0[c].y), q, qi);
+                        s10 += fp::mulmod_v(vx, fp::from_u64(e1[c].x), q, qi);
+                        s11 += fp::mulmod_v(vy, fp::from_u64(e1[c].y), q, qi);
+                    }
                 }
             }
-        }
-        if (accumulate) {
-            s00 += fp::from_u64(old0.x), s01 += fp::from_u64(old0.y);
-            s10 += fp::from_u64(old1.x), s11 += fp::from_u64(old1.y);
-        }
-        st2(cx + (size_t) j * n + x, fp::canon(fp::reduce(s00, q, qi), q), fp::canon(fp::reduce(s01, q, qi), q));
-        st2(cx + m_n + (size_t) j * n + x, fp::canon(fp::reduce(s10, q, qi), q), fp::canon(fp::reduce(s11, q, qi), q));
-        return;
-    }
-    if (own_d >= 0 && !os.c2) {
-        const BarG b0 = bar0[row];
-        own = make_ulonglong2(mul_mod_g(own.x, ownb.x, b0, md), mul_mod_g(own.y, ownb.y, b0, md));
-    }
-    Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
-    for (int d0 = 0; d0 < beta; d0 += CH) {
-        ulonglong2 v[CH], e0[CH], e1[CH];
-#pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const int d = min(d0 + c, beta - 1);
-            const u64 *k0 = evk[d] + krow;
-            v[c] = load_t(d);
-            e0[c] = ld2_stream(k0, pol);
-            e1[c] = ld2_stream(k0 + qp_n, pol);
-        }
-#pragma unroll
-        for (int c = 0; c < CH; c++) {
-            const int d = d0 + c;
-            if (d < beta) {
-                const ulonglong2 w = d == own_d ? own : v[c];
-                a00.mac(w.x, e0[c].x);
-                a01.mac(w.y, e0[c].y);
-                a10.mac(w.x, e1[c].x);
-                a11.mac(w.y, e1[c].y);
+            if (accumulate) {
+                s00 += fp::from_u64(old0.x), s01 += fp::from_u64(old0.y);
+                s10 += fp::from_u64(old1.x), s11 += fp::from_u64(old1.y);
             }
+            st2(c0 + x, fp::canon(fp::reduce(s00, q, qi), q), fp::canon(fp::reduce(s01, q, qi), q));
+            st2(c1 + x, fp::canon(fp::reduce(s10, q, qi), q), fp::canon(fp::reduce(s11, q, qi), q));
+        } else {
+            if (own_mul) own = make_ulonglong2(mul_mod_g(own.x, ownb.x, b0, md), mul_mod_g(own.y, ownb.y, b0, md));
+            Acc128 a00{0, 0}, a01{0, 0}, a10{0, 0}, a11{0, 0};
+#pragma unroll
+            for (int d0 = 0; d0 < beta; d0 += CH) {
+                ulonglong2 v[CH], e0[CH], e1[CH];
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int d = min(d0 + c, beta - 1);
+                    const u64 *k0 = key(d);
+                    v[c] = d != own_d ? load_t(d) : own;
+                    e0[c] = ld2_stream(k0, pol);
+                    e1[c] = ld2_stream(k0 + qp_n, pol);
+                }
+#pragma unroll
+                for (int c = 0; c < CH; c++) {
+                    const int d = d0 + c;
+                    if (d < beta) {
+                        const ulonglong2 w = d == own_d ? own : v[c];
+                        a00.mac(w.x, e0[c].x);
+                        a01.mac(w.y, e0[c].y);
+                        a10.mac(w.x, e1[c].x);
+                        a11.mac(w.y, e1[c].y);
+                    }
+                }
+            }
+            u64 r00 = barrett_g(a00.lo, a00.hi, bg, md), r01 = barrett_g(a01.lo, a01.hi, bg, md);
+            u64 r10 = barrett_g(a10.lo, a10.hi, bg, md), r11 = barrett_g(a11.lo, a11.hi, bg, md);
+            if (accumulate) {
+                r00 = add_mod(r00, old0.x, md.q), r01 = add_mod(r01, old0.y, md.q);
+                r10 = add_mod(r10, old1.x, md.q), r11 = add_mod(r11, old1.y, md.q);
+            }
+            st2(c0 + x, r00, r01);
+            st2(c1 + x, r10, r11);
         }
     }
-    u64 r00 = barrett_g(a00.lo, a00.hi, bg, md), r01 = barrett_g(a01.lo, a01.hi, bg, md);
-    u64 r10 = barrett_g(a10.lo, a10.hi, bg, md), r11 = barrett_g(a11.lo, a11.hi, bg, md);
-    if (accumulate) {
-        r00 = add_mod(r00, old0.x, md.q), r01 = add_mod(r01, old0.y, md.q);
-        r10 = add_mod(r10, old1.x, md.q), r11 = add_mod(r11, old1.y, md.q);
-    }
-    st2(cx + (size_t) j * n + x, r00, r01);
-    st2(cx + m_n + (size_t) j * n + x, r10, r11);
 }
 
+// grid-stride over the tiles (limb-major); a grid of all tiles runs the loop once, a smaller grid ("persist": leaves
+// room on every SM for the higher-priority mod-down chain of the fused key switch) walks them
+template<int BETA, bool PLAIN>
 __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(const InnerProdArgs A) {
     pdl_launch_dependents();
     pdl_wait();
-    inner_prod_tile(A, (int) blockIdx.y + A.j0, blockIdx.x);
-}
-
-// the same tiles walked by a grid that leaves room on every SM: used when the inner product runs beside the
-// (latency-bound, higher-priority) mod-down chain of the fused key switch
-__global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod_persist(const InnerProdArgs A) {
-    pdl_launch_dependents();
-    pdl_wait();
-    const unsigned nbx = (unsigned) (A.n / (2 * EW_THREADS));
+    const unsigned nbx = (unsigned) (A.n / IP_TILE);   // power of two
+    const unsigned sh = 31u - (unsigned) __clz(nbx);
     const unsigned total = nbx * (unsigned) A.j_count;
     for (unsigned tile = blockIdx.x; tile < total; tile += gridDim.x)
-        inner_prod_tile(A, A.j0 + (int) (tile % (unsigned) A.j_count), tile / (unsigned) A.j_count);
+        inner_prod_tile<BETA, PLAIN>(A, A.j0 + (int) (tile >> sh), tile & (nbx - 1));
 }
 
 // ---------------------------------------------------------------------------------------------------
