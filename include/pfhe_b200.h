@@ -130,6 +130,22 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
                             const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
                             void *stream);
+/* fnwt_1d[_opt] / inwt_1d[_opt] (include/ntt.cuh:157-170, src/ntt/ntt_1d.cu:146-292): single-block negacyclic
+ * transforms for dim <= 2048 on CALLER-SUPPLIED device tables in the reference's order (twiddles[bitrev(i)] = psi^i with
+ * separate Shoup arrays, itwiddles[1] already times n^-1), modulus = DModulus array {value, const_ratio[0], const_ratio[1]}
+ * (include/ntt.cuh:6-32).  Limb i of the call is absolute index start_modulus_idx + i in inout, the tables, modulus and
+ * scalar.  Forward: natural -> bit-reversed, output in [0, q).  Inverse: lower half times scalar[idx] (pass n^-1 for
+ * the plain inverse), upper half unscaled, output in [0, q).  No engine handle: nothing but the tables is needed. */
+int pfhe_fnwt_1d(uint64_t *inout, const uint64_t *twiddles, const uint64_t *twiddles_shoup, const uint64_t *modulus,
+                 size_t dim, size_t coeff_modulus_size, size_t start_modulus_idx, void *stream);
+int pfhe_inwt_1d(uint64_t *inout, const uint64_t *itwiddles, const uint64_t *itwiddles_shoup, const uint64_t *modulus,
+                 const uint64_t *scalar, const uint64_t *scalar_shoup, size_t dim, size_t coeff_modulus_size,
+                 size_t start_modulus_idx, void *stream);
+/* multiply_inplace for ciphertext sizes other than 2 x 2 (bgv_ckks_multiply's tensor_prod_mxn_rns_poly branch,
+ * evaluate.cu:382-386, polymath.cu:546-594): encrypted1 = [size1][l][n], encrypted2 = [size2][l][n], destination =
+ * [size1 + size2 - 1][l][n] (may alias encrypted1, as the reference's in-place form does); sizes up to 8.  CKKS / BGV */
+int pfhe_multiply_sizes(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1, size_t size1,
+                        const uint64_t *encrypted2, size_t size2, uint64_t *destination, void *stream);
 /* `count` independent multiply_and_relin ops on device buffers (arrays of `count` device pointers held in HOST
  * memory).  The reference runs independent ciphertexts on independent host threads / cudaStreamPerThread
  * (src/CMakeLists.txt:39, evaluate.cu:1079); here the ops go round-robin over pfhe_engine_lanes() internal streams,

@@ -401,6 +401,21 @@ void orc_ntt_inverse(const orc_ctx *c, u64 *data, int limbs, const int *table_id
     }
 }
 
+/* fnwt_1d[_opt] / inwt_1d[_opt] (reference src/ntt/ntt_1d.cu:146-292): single-block transforms for dim <= 2048 on
+ * CALLER-SUPPLIED tables.  Limb i of the call is absolute index start + i in inout, in the tables, in the modulus and
+ * scalar arrays (ntt_1d.cu:27-28,208-209).  Inverse: the lower half is multiplied by scalar[idx], the upper half only
+ * carries what the caller folded into itwiddles[1] (ntt_1d.cu:245-248). */
+void orc_fnwt_1d(u64 *inout, const u64 *tw, const u64 *tws, const u64 *q, u64 dim, int count, int start) {
+    for (int i = start; i < start + count; i++)
+        ntt_fwd_limb(inout + (size_t)i * dim, dim, tw + (size_t)i * dim, tws + (size_t)i * dim, q[i]);
+}
+void orc_inwt_1d(u64 *inout, const u64 *itw, const u64 *itws, const u64 *q, const u64 *scalar, const u64 *scalar_shoup,
+                 u64 dim, int count, int start) {
+    for (int i = start; i < start + count; i++)
+        ntt_inv_limb(inout + (size_t)i * dim, dim, itw + (size_t)i * dim, itws + (size_t)i * dim, scalar[i],
+                     scalar_shoup[i], q[i]);
+}
+
 /* ------------------------------------------------------------------------------------------------------
  * dyadic kernels
  * ---------------------------------------------------------------------------------------------------- */
@@ -438,6 +453,31 @@ void orc_tensor_square_2x2(const orc_ctx *c, const u64 *a, u64 *out, int l) {
             out[k] = d0;
             out[k + poly] = d1;
             out[k + 2 * poly] = d2;
+        }
+    }
+}
+
+/* tensor_prod_mxn_rns_poly (reference src/polymath.cu:546-594): out[j] = sum_{i1+i2=j} a[i1] * b[i2] mod q, j <
+ * sa + sb - 1, every sum accumulated in 128 bits and reduced once.  out may alias a (the reference's in-place form):
+ * all operands of a coefficient are read before its results are written. */
+void orc_tensor_mxn(const orc_ctx *c, const u64 *a, int sa, const u64 *b, int sb, u64 *out, int l) {
+    size_t n = c->n, poly = (size_t)l * n;
+    int so = sa + sb - 1;
+#pragma omp parallel for num_threads(g_threads)
+    for (int i = 0; i < l; i++) {
+        u64 q = c->primes[i];
+        u64 c1[ORC_MAX_CT], c2[ORC_MAX_CT], r[2 * ORC_MAX_CT];
+        for (size_t x = 0; x < n; x++) {
+            size_t k = (size_t)i * n + x;
+            for (int u = 0; u < sa; u++) c1[u] = a[k + u * poly];
+            for (int u = 0; u < sb; u++) c2[u] = b[k + u * poly];
+            for (int j = 0; j < so; j++) {
+                int last1 = j < sa - 1 ? j : sa - 1, first2 = j < sb - 1 ? j : sb - 1, first1 = j - first2;
+                u128 acc = 0;
+                for (int u = 0; u <= last1 - first1; u++) acc += (u128)c1[first1 + u] * c2[first2 - u];
+                r[j] = (u64)(acc % q);
+            }
+            for (int j = 0; j < so; j++) out[k + j * poly] = r[j];
         }
     }
 }

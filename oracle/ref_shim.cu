@@ -236,6 +236,78 @@ int ref_multiply(void *p, size_t chain_index, const uint64_t *ct1, const uint64_
     SHIM_CATCH
 }
 
+/* fnwt_1d_opt / inwt_1d_opt on tables built the way test/ntt_test.cu:7-60 builds them: `count` primes of `bits` bits
+ * for degree 2^log_dim, limbs [start, count) transformed in place on the host copy `data` = [count][dim] */
+#define STEP(name)                                                                                       \
+    do {                                                                                                 \
+        cudaError_t e_ = cudaGetLastError();                                                             \
+        if (e_ != cudaSuccess) {                                                                         \
+            snprintf(g_err, sizeof(g_err), "ref_nwt_1d after %s: %s", name, cudaGetErrorString(e_));     \
+            return -1;                                                                                   \
+        }                                                                                                \
+    } while (0)
+int ref_nwt_1d(int log_dim, int count, int bits, int start, uint64_t *data, int inverse) {
+    SHIM_TRY
+    const auto &s = cudaStreamPerThread;
+    cudaGetLastError(); /* start from a clean per-thread error state */
+    size_t dim = size_t(1) << log_dim;
+    const auto h_modulus = CoeffModulus::Create(dim, std::vector<int>(count, bits));
+    auto modulus = make_cuda_auto_ptr<DModulus>(count, s);
+    std::vector<DModulus> hm(count);
+    for (int i = 0; i < count; i++)
+        hm[i] = DModulus(h_modulus[i].value(), h_modulus[i].const_ratio()[0], h_modulus[i].const_ratio()[1]);
+    cudaMemcpyAsync(modulus.get(), hm.data(), count * sizeof(DModulus), cudaMemcpyHostToDevice, s);
+    STEP("modulus");
+    auto tw = make_cuda_auto_ptr<uint64_t>(count * dim, s);
+    auto tws = make_cuda_auto_ptr<uint64_t>(count * dim, s);
+    auto itw = make_cuda_auto_ptr<uint64_t>(count * dim, s);
+    auto itws = make_cuda_auto_ptr<uint64_t>(count * dim, s);
+    auto ninv = make_cuda_auto_ptr<uint64_t>(count, s);
+    auto ninvs = make_cuda_auto_ptr<uint64_t>(count, s);
+    for (int i = 0; i < count; i++) {
+        auto t = NTT(log_dim, h_modulus[i]);
+        cudaMemcpyAsync(tw.get() + i * dim, t.get_from_root_powers().data(), dim * 8, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(tws.get() + i * dim, t.get_from_root_powers_shoup().data(), dim * 8, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(itw.get() + i * dim, t.get_from_inv_root_powers().data(), dim * 8, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(itws.get() + i * dim, t.get_from_inv_root_powers_shoup().data(), dim * 8, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ninv.get() + i, &t.inv_degree_modulo(), 8, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(ninvs.get() + i, &t.inv_degree_modulo_shoup(), 8, cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);   /* the host table dies at the end of the iteration */
+    }
+    STEP("tables");
+    auto d = make_cuda_auto_ptr<uint64_t>(count * dim, s);
+    cudaMemcpyAsync(d.get(), data, count * dim * 8, cudaMemcpyHostToDevice, s);
+    STEP("input");
+    /* fnwt_1d_opt ignores start_modulus_idx (ntt_1d.cu:76-86): the plain form is used when a start index is given */
+    if (inverse) inwt_1d_opt(d.get(), itw.get(), itws.get(), modulus.get(), ninv.get(), ninvs.get(), dim, count - start, start, s);
+    else if (start == 0) fnwt_1d_opt(d.get(), tw.get(), tws.get(), modulus.get(), dim, count, 0, s);
+    else fnwt_1d(d.get(), tw.get(), tws.get(), modulus.get(), dim, count - start, start, s);
+    STEP("launch");
+    cudaMemcpyAsync(data, d.get(), count * dim * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    cudaError_t ce = cudaGetLastError();
+    if (ce != cudaSuccess) {
+        snprintf(g_err, sizeof(g_err), "ref_nwt_1d: %s", cudaGetErrorString(ce));
+        return -1;
+    }
+    return 0;
+    SHIM_CATCH
+}
+
+/* multiply_inplace on ciphertexts of sizes size1 x size2 (tensor_prod_mxn_rns_poly branch): out = [size1+size2-1][l][n] */
+int ref_multiply_sizes(void *p, size_t chain_index, const uint64_t *ct1, size_t size1, const uint64_t *ct2, size_t size2,
+                       uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    bool ntt = h->scheme != scheme_type::bfv;
+    auto a = make_ct(h, chain_index, size1, ct1, ntt);
+    auto b = make_ct(h, chain_index, size2, ct2, ntt);
+    multiply_inplace(*h->ctx, a, b);
+    fetch_ct(a, out);
+    return 0;
+    SHIM_CATCH
+}
+
 /* stage-wise key-switch taps (eval_key_switch.cu:95-182) for differential debugging */
 int ref_modup(void *p, size_t chain_index, const uint64_t *c2, uint64_t *t_mod_up) {
     SHIM_TRY

@@ -56,6 +56,9 @@ _sigs = {
     "pfhe_hoisting_inplace": (ctypes.c_int, [vp, sz, vp, i32p, sz, vp, vp]),
     "pfhe_rescale_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_mod_switch_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_fnwt_1d": (ctypes.c_int, [vp, vp, vp, vp, sz, sz, sz, vp]),
+    "pfhe_inwt_1d": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, sz, sz, sz, vp]),
+    "pfhe_multiply_sizes": (ctypes.c_int, [vp, sz, vp, sz, vp, sz, vp, vp]),
     "pfhe_multiply_and_relin_batch": (ctypes.c_int, [vp, sz, vp, vp, vp, sz, vp, vp]),
     "pfhe_engine_set_lanes": (ctypes.c_int, [vp, ctypes.c_int]),
     "pfhe_engine_lanes": (ctypes.c_int, [vp]),

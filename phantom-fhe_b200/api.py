@@ -221,13 +221,17 @@ def multiply_inplace(context, encrypted1, encrypted2):
     _require_ntt(context, encrypted2)
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
-    if encrypted1.size() != 2 or encrypted2.size() != 2:
-        raise ValueError("only size-2 operands are on this path")
+    if encrypted1.size() != encrypted2.size():
+        raise ValueError("poly number mismatch")   # evaluate.cu:1039-1040
     l, n = encrypted1.coeff_modulus_size(), context.poly_degree
-    dst = torch.empty((3, l, n), dtype=torch.int64, device=encrypted1.data.device)
+    s1, s2 = encrypted1.size(), encrypted2.size()
+    dst = torch.empty((s1 + s2 - 1, l, n), dtype=torch.int64, device=encrypted1.data.device)
     a, b = encrypted1.data, encrypted2.data
-    check(lib.pfhe_multiply(context._h, encrypted1.chain_index, _ptr(a), _ptr(a if encrypted1 is encrypted2 else b),
-                            _ptr(dst), _stream()))
+    if s1 == 2 and s2 == 2:
+        check(lib.pfhe_multiply(context._h, encrypted1.chain_index, _ptr(a), _ptr(a if encrypted1 is encrypted2 else b),
+                                _ptr(dst), _stream()))
+    else:   # tensor_prod_mxn_rns_poly branch of bgv_ckks_multiply (evaluate.cu:382-386)
+        check(lib.pfhe_multiply_sizes(context._h, encrypted1.chain_index, _ptr(a), s1, _ptr(b), s2, _ptr(dst), _stream()))
     encrypted1.data = dst
     if context.scheme == scheme_type.ckks:
         encrypted1.scale = encrypted1.scale * encrypted2.scale

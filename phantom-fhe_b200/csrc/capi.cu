@@ -265,6 +265,39 @@ int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const
     else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
     API_END
 }
+int pfhe_fnwt_1d(uint64_t *inout, const uint64_t *twiddles, const uint64_t *twiddles_shoup, const uint64_t *modulus,
+                 size_t dim, size_t coeff_modulus_size, size_t start_modulus_idx, void *stream) {
+    API_BEGIN
+    require(inout && twiddles && twiddles_shoup && modulus, "null pointer");
+    require(dim >= 2 && dim <= 2048 && (dim & (dim - 1)) == 0, "dim must be a power of two, at most 2048");
+    PFHE_CUDA(ntt_1d(false, U(inout), U(twiddles), U(twiddles_shoup), reinterpret_cast<const Modulus *>(modulus), nullptr,
+                     nullptr, dim, coeff_modulus_size, start_modulus_idx, S(stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    API_END
+}
+int pfhe_inwt_1d(uint64_t *inout, const uint64_t *itwiddles, const uint64_t *itwiddles_shoup, const uint64_t *modulus,
+                 const uint64_t *scalar, const uint64_t *scalar_shoup, size_t dim, size_t coeff_modulus_size,
+                 size_t start_modulus_idx, void *stream) {
+    API_BEGIN
+    require(inout && itwiddles && itwiddles_shoup && modulus && scalar && scalar_shoup, "null pointer");
+    require(dim >= 2 && dim <= 2048 && (dim & (dim - 1)) == 0, "dim must be a power of two, at most 2048");
+    PFHE_CUDA(ntt_1d(true, U(inout), U(itwiddles), U(itwiddles_shoup), reinterpret_cast<const Modulus *>(modulus),
+                     U(scalar), U(scalar_shoup), dim, coeff_modulus_size, start_modulus_idx, S(stream)));
+    g_launches.fetch_add(1, std::memory_order_relaxed);
+    API_END
+}
+int pfhe_multiply_sizes(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, size_t size1, const uint64_t *ct2,
+                        size_t size2, uint64_t *dst, void *stream) {
+    API_BEGIN
+    require(size1 >= 1 && size2 >= 1, "invalid ciphertext size");
+    if (size1 == 2 && size2 == 2) return pfhe_multiply(e, chain_index, ct1, ct2, dst, stream);
+    // BFV goes through BEHZ / HPS, which the reference restricts to dest_size 3 for HPS (evaluate.cu:665-666)
+    require(e->impl.scheme() != Scheme::bfv, "dest_size must be 3 when computing BFV multiplication");
+    require(dst != ct2, "destination aliases the second operand");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.tensor_mxn(U(ct1), (int) size1, U(ct2), (int) size2, U(dst), l, S(stream));
+    API_END
+}
 int pfhe_relinearize_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *const *rlk,
                              void *stream) {
     API_BEGIN

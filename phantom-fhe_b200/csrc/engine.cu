@@ -551,6 +551,13 @@ void Engine::tensor_square(const u64 *a, u64 *out, int l, cudaStream_t st) const
     check_launch("k_tensor_square");
 }
 
+void Engine::tensor_mxn(const u64 *a, int sa, const u64 *b, int sb, u64 *out, int l, cudaStream_t st) const {
+    if (sa < 1 || sb < 1 || sa > MXN_MAX || sb > MXN_MAX) throw std::invalid_argument("ciphertext size is not supported");
+    dim3 grid((unsigned) (n_ / EW_THREADS), l);
+    launch_pdl(k_tensor_mxn, grid, EW_THREADS, 0, st, a, sa, b, sb, out, d_mod_.p, n_, l);
+    check_launch("k_tensor_mxn");
+}
+
 void Engine::elementwise(int op, const u64 *a, const u64 *b, u64 *out, int l, cudaStream_t st) const {
     dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
     switch (op) {

@@ -38,4 +38,9 @@ cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, co
 cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
                         cudaStream_t st);
 
+// single-CTA transforms for dim <= 2048 on caller-supplied reference-order tables (fnwt_1d / inwt_1d,
+// reference include/ntt.cuh:157-170); limb i of the call is absolute index start + i in every array
+cudaError_t ntt_1d(bool inverse, u64 *inout, const u64 *tw, const u64 *tws, const Modulus *mod, const u64 *scalar,
+                   const u64 *scalar_shoup, size_t dim, size_t count, size_t start, cudaStream_t st);
+
 } // namespace pfhe

@@ -573,6 +573,80 @@ cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, co
     return cudaGetLastError();
 }
 
+// ----------------------------------------------------------------------------------------------------
+// single-CTA transforms for dim <= 2048 on caller-supplied tables (fnwt_1d[_opt] / inwt_1d[_opt], reference
+// src/ntt/ntt_1d.cu:146-292; tables in the reference's own order: tw[bitrev(i)] = psi^i, Shoup companions apart).
+// One CTA per limb, one butterfly per thread and stage, the limb lives in shared memory between the first load and
+// the last store.  Limb i of the launch is absolute index start + i in every array, like the reference.
+// ----------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024) k_fnwt_1d(u64 *inout, const u64 *tw, const u64 *tws, const Modulus *mod, int dim,
+                                                  int start) {
+    extern __shared__ __align__(16) u64 s1d[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t limb = (size_t) (blockIdx.x + start);
+    const u64 q = mod[limb].q, q2 = 2 * q;
+    u64 *d = inout + limb * dim;
+    const u64 *w = tw + limb * dim, *ws = tws + limb * dim;
+    const int t = threadIdx.x;
+    for (int m = 1, gap = dim >> 1; m < dim; m <<= 1, gap >>= 1) {
+        const int i = t / gap, j = t - i * gap, idx = 2 * i * gap + j;
+        const u64 X = m == 1 ? d[idx] : s1d[idx], Y = m == 1 ? d[idx + gap] : s1d[idx + gap];
+        // Harvey butterfly, values stay below 4q (reference butterfly.cuh:10-26)
+        const u64 Xr = csub(X, q2);
+        const u64 T = mul_shoup_lazy(Y, w[m + i], ws[m + i], q);
+        const u64 a = Xr + T, b = Xr + q2 - T;
+        if (gap == 1) {
+            d[idx] = csub(csub(a, q2), q);
+            d[idx + 1] = csub(csub(b, q2), q);
+        } else {
+            __syncthreads();   // every thread has read this stage's operands
+            s1d[idx] = a, s1d[idx + gap] = b;
+            __syncthreads();
+        }
+    }
+}
+
+__global__ void __launch_bounds__(1024) k_inwt_1d(u64 *inout, const u64 *itw, const u64 *itws, const Modulus *mod,
+                                                  const u64 *scalar, const u64 *scalar_shoup, int dim, int start) {
+    extern __shared__ __align__(16) u64 s1d[];
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t limb = (size_t) (blockIdx.x + start);
+    const u64 q = mod[limb].q, q2 = 2 * q;
+    u64 *d = inout + limb * dim;
+    const u64 *w = itw + limb * dim, *ws = itws + limb * dim;
+    const int t = threadIdx.x;
+    for (int m = dim >> 1, gap = 1; m >= 1; m >>= 1, gap <<= 1) {
+        const int i = t / gap, j = t - i * gap, idx = 2 * i * gap + j;
+        const bool first = gap == 1;
+        const u64 X = first ? d[idx] : s1d[idx], Y = first ? d[idx + gap] : s1d[idx + gap];
+        // Gentleman-Sande butterfly on [0, 2q) (butterfly.cuh:28-37); canonical inputs are inside that range
+        const u64 S = csub(X + Y, q2);
+        const u64 D = mul_shoup_lazy(X + q2 - Y, w[m + i], ws[m + i], q);
+        if (m == 1) {
+            // lower half times scalar[limb]; the upper half carries only what the caller folded into itw[1]
+            d[idx] = mul_shoup(S, scalar[limb], scalar_shoup[limb], q);
+            d[idx + gap] = csub(D, q);
+        } else {
+            __syncthreads();
+            s1d[idx] = S, s1d[idx + gap] = D;
+            __syncthreads();
+        }
+    }
+}
+
+cudaError_t ntt_1d(bool inverse, u64 *inout, const u64 *tw, const u64 *tws, const Modulus *mod, const u64 *scalar,
+                   const u64 *scalar_shoup, size_t dim, size_t count, size_t start, cudaStream_t st) {
+    if (count == 0) return cudaSuccess;
+    if (dim < 2 || dim > 2048 || (dim & (dim - 1))) return cudaErrorInvalidValue;
+    const dim3 grid((unsigned) count), block((unsigned) (dim / 2));
+    const size_t smem = dim * sizeof(u64);
+    if (inverse) launch_pdl(k_inwt_1d, grid, block, smem, st, inout, tw, tws, mod, scalar, scalar_shoup, (int) dim, (int) start);
+    else launch_pdl(k_fnwt_1d, grid, block, smem, st, inout, tw, tws, mod, (int) dim, (int) start);
+    return cudaGetLastError();
+}
+
 cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
                         cudaStream_t st) {
     if (ll.count == 0) return cudaSuccess;

@@ -87,6 +87,42 @@ __global__ void __launch_bounds__(EW_THREADS) k_tensor_2x2(const u64 *a, const u
     st2(out + i + 2 * poly, d2[0], d2[1]);
 }
 
+// tensor_prod_mxn_rns_poly (reference src/polymath.cu:546-594): ciphertexts of sizes sa x sb (not both 2),
+// out[j] = sum_{i1 + i2 = j} a[i1] * b[i2], each sum accumulated in 128 bits and reduced once.  out may alias a:
+// a thread reads every operand word of its coefficient before it writes.  One coefficient per thread (the
+// operand sets live in registers; the reference allocates them with device-side new), grid.y = limb.
+constexpr int MXN_MAX = 8;
+__global__ void __launch_bounds__(EW_THREADS) k_tensor_mxn(const u64 *a, int sa, const u64 *b, int sb, u64 *out,
+                                                            const Modulus *mod, size_t n, int l) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int limb = blockIdx.y;
+    const Modulus m = mod[limb];
+    const size_t poly = (size_t) l * n;
+    const size_t k = (size_t) limb * n + (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
+    u64 c1[MXN_MAX], c2[MXN_MAX], r[2 * MXN_MAX - 1];
+#pragma unroll
+    for (int u = 0; u < MXN_MAX; u++) {
+        c1[u] = u < sa ? a[k + (size_t) u * poly] : 0;
+        c2[u] = u < sb ? b[k + (size_t) u * poly] : 0;
+    }
+    // zero padding makes every anti-diagonal a fixed-shape sum: the extra terms are 0
+#pragma unroll
+    for (int j = 0; j < 2 * MXN_MAX - 1; j++) {
+        Acc128 acc{0, 0};
+#pragma unroll
+        for (int u = 0; u < MXN_MAX; u++) {
+            const int v = j - u;
+            if (v >= 0 && v < MXN_MAX) acc.mac(c1[u], c2[v]);
+        }
+        r[j] = barrett128(acc.lo, acc.hi, m);
+    }
+    const int so = sa + sb - 1;
+#pragma unroll
+    for (int j = 0; j < 2 * MXN_MAX - 1; j++)
+        if (j < so) out[k + (size_t) j * poly] = r[j];
+}
+
 // tensor_square_2x2_rns_poly (src/polymath.cu:500-532)
 __global__ void __launch_bounds__(EW_THREADS) k_tensor_square(const u64 *a, u64 *out, const Modulus *mod,
                                                                const BarG *bar, size_t n, int l) {

@@ -44,8 +44,11 @@ def oracle():
         o.orc_mt19937_64_fill.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, ctypes.c_size_t, ctypes.c_int]
         o.orc_ntt_forward.argtypes = [vp, u64p, ctypes.c_int, i32p]
         o.orc_ntt_inverse.argtypes = [vp, u64p, ctypes.c_int, i32p]
+        o.orc_fnwt_1d.argtypes = [u64p, u64p, u64p, u64p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
+        o.orc_inwt_1d.argtypes = [u64p, u64p, u64p, u64p, u64p, u64p, ctypes.c_uint64, ctypes.c_int, ctypes.c_int]
         o.orc_tensor_2x2.argtypes = [vp, u64p, u64p, u64p, ctypes.c_int]
         o.orc_tensor_square_2x2.argtypes = [vp, u64p, u64p, ctypes.c_int]
+        o.orc_tensor_mxn.argtypes = [vp, u64p, ctypes.c_int, u64p, ctypes.c_int, u64p, ctypes.c_int]
         for f in ("orc_poly_add", "orc_poly_sub", "orc_poly_mul"):
             getattr(o, f).argtypes = [vp, u64p, u64p, u64p, ctypes.c_int]
         o.orc_poly_negate.argtypes = [vp, u64p, u64p, ctypes.c_int]
@@ -114,6 +117,10 @@ def reference():
         r.ref_ntt.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
         r.ref_multiply_relin.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
         r.ref_multiply.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
+        if hasattr(r, "ref_nwt_1d"):
+            r.ref_nwt_1d.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p, ctypes.c_int]
+        if hasattr(r, "ref_multiply_sizes"):
+            r.ref_multiply_sizes.argtypes = [vp, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p]
         r.ref_modup.argtypes = [vp, ctypes.c_size_t, u64p, u64p]
         r.ref_inner_prod.argtypes = [vp, ctypes.c_size_t, ctypes.c_int, u64p, u64p]
         r.ref_moddown.argtypes = [vp, ctypes.c_size_t, u64p, u64p]

@@ -77,6 +77,86 @@ def test_ntt_forward_inverse(logn, bits):
         assert np.array_equal(host(d), want)
 
 
+def _tables_1d(log_dim, count, bits):
+    """Reference-order tables for `count` primes of `bits` bits at degree 2^log_dim, from the oracle's host number theory
+    (pinned to the reference's host code by tests/test_oracle.py)."""
+    o = H.oracle()
+    dim = 1 << log_dim
+    primes = np.zeros(count, dtype=np.uint64)
+    assert o.orc_create_primes(dim, (ctypes.c_int * count)(*([bits] * count)), count, P(primes)) == 0
+    c = o.orc_create(3, dim, P(primes), count, 0, 0)
+    get = lambda f, i: np.ctypeslib.as_array(getattr(o, f)(c, i), shape=(dim,)).copy()
+    tw = np.stack([get("orc_twiddle", i) for i in range(count)])
+    tws = np.stack([get("orc_twiddle_shoup", i) for i in range(count)])
+    itw = np.stack([get("orc_itwiddle", i) for i in range(count)])
+    itws = np.stack([get("orc_itwiddle_shoup", i) for i in range(count)])
+    ninv = np.array([o.orc_n_inv(c, i) for i in range(count)], dtype=np.uint64)
+    ninvs = np.array([o.orc_shoup(int(ninv[i]), int(primes[i])) for i in range(count)], dtype=np.uint64)
+    mod = np.zeros((count, 3), dtype=np.uint64)
+    for i in range(count):
+        ratio = np.zeros(3, dtype=np.uint64)
+        o.orc_barrett_ratio(int(primes[i]), P(ratio))
+        mod[i] = [primes[i], ratio[0], ratio[1]]
+    o.orc_destroy(c)
+    return primes, tw, tws, itw, itws, ninv, ninvs, mod
+
+
+@pytest.mark.parametrize("log_dim,count,start", [(8, 1, 0), (9, 1, 0), (10, 1, 0), (11, 1, 0), (8, 10, 0), (9, 10, 3),
+                                                 (10, 10, 0), (11, 10, 9), (1, 2, 0), (5, 3, 1)])
+def test_nwt_1d(log_dim, count, start):
+    """pfhe_fnwt_1d / pfhe_inwt_1d (fnwt_1d_opt / inwt_1d_opt, src/ntt/ntt_1d.cu:146-292) vs the oracle on the same
+    tables: the reference's own cases (test/ntt_test.cu:124-143: logN 8..11, 1 and 10 limbs of 50-bit primes, constant
+    input round trip) plus random words, a start index and tiny degrees."""
+    dim = 1 << log_dim
+    bits = 50 if log_dim >= 8 else 30
+    primes, tw, tws, itw, itws, ninv, ninvs, mod = _tables_1d(log_dim, count, bits)
+    o = H.oracle()
+    rng = np.random.default_rng(log_dim * 100 + count)
+    x = np.stack([rng.integers(0, int(primes[i]), dim, dtype=np.uint64) for i in range(count)])
+    x[0, :2] = [int(primes[0]) - 1, 0]
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    d_tw, d_tws, d_itw, d_itws = dev(tw), dev(tws), dev(itw), dev(itws)
+    d_mod, d_ninv, d_ninvs = dev(mod), dev(ninv), dev(ninvs)
+    for data in (x, np.ones_like(x)):
+        want = data.copy()
+        o.orc_fnwt_1d(P(want), P(tw), P(tws), P(primes), dim, count - start, start)
+        d = dev(data)
+        pf.check(pf.lib.pfhe_fnwt_1d(d.data_ptr(), d_tw.data_ptr(), d_tws.data_ptr(), d_mod.data_ptr(), dim,
+                                     count - start, start, st))
+        got = host(d)
+        assert np.array_equal(got, want), "forward 1-D transform"
+        assert np.array_equal(got[:start], data[:start]), "limbs below the start index are untouched"
+        back = want.copy()
+        o.orc_inwt_1d(P(back), P(itw), P(itws), P(primes), P(ninv), P(ninvs), dim, count - start, start)
+        assert np.array_equal(back, data), "oracle round trip"
+        pf.check(pf.lib.pfhe_inwt_1d(d.data_ptr(), d_itw.data_ptr(), d_itws.data_ptr(), d_mod.data_ptr(),
+                                     d_ninv.data_ptr(), d_ninvs.data_ptr(), dim, count - start, start, st))
+        assert np.array_equal(host(d), data), "inverse 1-D transform / round trip"
+    # a scalar other than n^-1 reaches the lower half only (ntt_1d.cu:245-248)
+    sc = np.array([(int(ninv[i]) * 3) % int(primes[i]) for i in range(count)], dtype=np.uint64)
+    scs = np.array([o.orc_shoup(int(sc[i]), int(primes[i])) for i in range(count)], dtype=np.uint64)
+    want = x.copy()
+    o.orc_inwt_1d(P(want), P(itw), P(itws), P(primes), P(sc), P(scs), dim, count - start, start)
+    d, d_sc, d_scs = dev(x), dev(sc), dev(scs)
+    pf.check(pf.lib.pfhe_inwt_1d(d.data_ptr(), d_itw.data_ptr(), d_itws.data_ptr(), d_mod.data_ptr(), d_sc.data_ptr(),
+                                 d_scs.data_ptr(), dim, count - start, start, st))
+    assert np.array_equal(host(d), want)
+    # the unmodified reference on its own tables (same primes and roots: both follow CoeffModulus::Create / NTT)
+    r = H.reference()
+    if r is not None and hasattr(r, "ref_nwt_1d") and log_dim >= 8:
+        for inverse in (0, 1):
+            want = x.copy()
+            assert r.ref_nwt_1d(log_dim, count, bits, start, P(want), inverse) == 0, r.ref_last_error()
+            mine = x.copy()
+            if inverse:
+                o.orc_inwt_1d(P(mine), P(itw), P(itws), P(primes), P(ninv), P(ninvs), dim, count - start, start)
+            else:
+                o.orc_fnwt_1d(P(mine), P(tw), P(tws), P(primes), dim, count - start, start)
+            assert np.array_equal(mine, want), "oracle 1-D transform vs the reference's kernels"
+    with pytest.raises(Exception):
+        pf.check(pf.lib.pfhe_fnwt_1d(d.data_ptr(), d_tw.data_ptr(), d_tws.data_ptr(), d_mod.data_ptr(), 4096, 1, 0, st))
+
+
 def test_ntt_config1_known_answer():
     """SURVEY.md 8c anchor: x_j = mt19937_64(1)() % q, N = 4096, q = 1125899906826241."""
     ps = H.params_c1()
@@ -250,6 +330,71 @@ def test_multiply_relin_rotate_rescale_small(cfg):
         c = pf.PhantomCiphertext.from_host(ctx, a)
         pf.rotate_inplace(ctx, c, s, glk)
         assert np.array_equal(c.to_host(), want), f"rotate {s}"
+
+
+@pytest.mark.parametrize("sizes", [(3, 2), (2, 3), (3, 3), (1, 2), (4, 1), (8, 8)])
+def test_multiply_sizes_mxn(sizes):
+    """multiply_inplace on ciphertexts that are not both of size 2 (tensor_prod_mxn_rns_poly, polymath.cu:546-594):
+    engine vs oracle, out of place and in place (destination aliasing encrypted1, like the reference)."""
+    sa, sb = sizes
+    ps = H.params_small(4096, l=3, alpha=1)
+    ctx = make_context(ps)
+    o = H.oracle()
+    l, n = ps.limbs(), ps.n
+    rng = np.random.default_rng(sa * 16 + sb)
+    def rand_ct(size):
+        return np.stack([np.stack([rng.integers(0, int(ps.primes[i]), n, dtype=np.uint64) for i in range(l)])
+                         for _ in range(size)])
+    a, b = rand_ct(sa), rand_ct(sb)
+    a[0, 0, :4] = [0, int(ps.primes[0]) - 1, 1, int(ps.primes[0]) - 1]   # edge residues
+    b[0, 0, :4] = [int(ps.primes[0]) - 1, int(ps.primes[0]) - 1, 0, 1]
+    so = sa + sb - 1
+    want = np.zeros((so, l, n), dtype=np.uint64)
+    o.orc_tensor_mxn(ps.octx(), P(a), sa, P(b), sb, P(want), l)
+    if (sa, sb) == (3, 2):   # the oracle's 2x2 form agrees with the general form on its own shape
+        w22, g22 = np.zeros((3, l, n), dtype=np.uint64), np.zeros((3, l, n), dtype=np.uint64)
+        o.orc_tensor_2x2(ps.octx(), P(a[:2].copy()), P(b), P(w22), l)
+        o.orc_tensor_mxn(ps.octx(), P(a[:2].copy()), 2, P(b), 2, P(g22), l)
+        assert np.array_equal(w22, g22)
+    ca = pf.PhantomCiphertext.from_host(ctx, a)
+    cb = pf.PhantomCiphertext.from_host(ctx, b)
+    if sa == sb:   # what multiply_inplace itself admits (evaluate.cu:1039-1040); unequal sizes: kernel level only
+        pf.multiply_inplace(ctx, ca, cb)
+        assert ca.size() == so and np.array_equal(ca.to_host(), want)
+    else:
+        with pytest.raises(ValueError):
+            pf.multiply_inplace(ctx, ca, cb)
+    # in place: encrypted1's buffer already has the destination size (ciphertext.resize in the reference)
+    buf = torch.zeros((so, l, n), dtype=torch.int64, device="cuda")
+    buf[:sa] = dev(a)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    pf.check(pf.lib.pfhe_multiply_sizes(ctx._h, 1, buf.data_ptr(), sa, cb.data.data_ptr(), sb, buf.data_ptr(), st))
+    assert np.array_equal(host(buf), want)
+
+
+def test_multiply_3x3_against_unmodified_reference():
+    """sizes 3 x 3 -> 5 through the reference's multiply_inplace (tensor_prod_mxn_rns_poly branch) and the engine.  Small
+    degree: the reference kernel allocates its operand arrays with device-side new and runs out of device heap at
+    N = 2^16 x 16 limbs (polymath.cu:556-562 warns about it)."""
+    r = H.reference()
+    if r is None or not hasattr(r, "ref_multiply_sizes"):
+        pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    ps = H.params_small(4096, l=3, alpha=1)
+    steps = (ctypes.c_int * 1)(1)
+    h = r.ref_create(3, ps.n, P(ps.primes), ps.size_QP, ps.size_P, 0, 0, steps, 0, float(2 ** 30), 0)
+    assert h, r.ref_last_error()
+    try:
+        l, n = ps.limbs(), ps.n
+        ctx = make_context(ps)
+        a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
+        a3, b3 = np.concatenate([a, b[:1]]), np.concatenate([b, a[1:]])
+        want5 = np.zeros((5, l, n), dtype=np.uint64)
+        assert r.ref_multiply_sizes(h, 1, P(a3), 3, P(b3), 3, P(want5)) == 0, r.ref_last_error()
+        c3, d3 = pf.PhantomCiphertext.from_host(ctx, a3), pf.PhantomCiphertext.from_host(ctx, b3)
+        pf.multiply_inplace(ctx, c3, d3)
+        assert c3.size() == 5 and np.array_equal(c3.to_host(), want5), "3x3 multiply vs reference"
+    finally:
+        r.ref_destroy(h)
 
 
 @pytest.mark.parametrize("lanes", [1, 2, 3])
@@ -640,5 +785,6 @@ def test_against_unmodified_reference():
         assert r.ref_rescale(h, 1, P(a), 2, P(want_rs)) == 0, r.ref_last_error()
         rs = pf.rescale_to_next(ctx, pf.PhantomCiphertext.from_host(ctx, a))
         assert np.array_equal(rs.to_host(), want_rs), "rescale vs reference"
+
     finally:
         r.ref_destroy(h)

@@ -110,6 +110,69 @@ def _crt_poly(ps, limbs):
     return vals, Q
 
 
+@pytest.mark.parametrize("log_dim", [8, 11])
+def test_nwt_1d_matches_the_context_transform(log_dim):
+    """orc_fnwt_1d / orc_inwt_1d (ntt_1d.cu:146-292) on explicit tables = the oracle's table-driven transform; the
+    definition NTT(x)[k] = sum_j x_j psi^(j (2 bitrev(k) + 1)) is checked directly at a few outputs."""
+    o = H.oracle()
+    dim, count = 1 << log_dim, 3
+    primes = np.zeros(count, dtype=np.uint64)
+    assert o.orc_create_primes(dim, (ctypes.c_int * count)(50, 50, 50), count, P(primes)) == 0
+    c = o.orc_create(3, dim, P(primes), count, 0, 0)
+    get = lambda f, i: np.ctypeslib.as_array(getattr(o, f)(c, i), shape=(dim,)).copy()
+    tw = np.stack([get("orc_twiddle", i) for i in range(count)])
+    tws = np.stack([get("orc_twiddle_shoup", i) for i in range(count)])
+    itw = np.stack([get("orc_itwiddle", i) for i in range(count)])
+    itws = np.stack([get("orc_itwiddle_shoup", i) for i in range(count)])
+    ninv = np.array([o.orc_n_inv(c, i) for i in range(count)], dtype=np.uint64)
+    ninvs = np.array([o.orc_shoup(int(ninv[i]), int(primes[i])) for i in range(count)], dtype=np.uint64)
+    rng = np.random.default_rng(log_dim)
+    x = np.stack([rng.integers(0, int(primes[i]), dim, dtype=np.uint64) for i in range(count)])
+    a, b = x.copy(), x.copy()
+    o.orc_fnwt_1d(P(a), P(tw), P(tws), P(primes), dim, count - 1, 1)
+    o.orc_ntt_forward(c, P(b[1:].copy()), 0, (ctypes.c_int * 2)(1, 2))
+    bb = x[1:].copy()
+    o.orc_ntt_forward(c, P(bb), 2, (ctypes.c_int * 2)(1, 2))
+    assert np.array_equal(a[0], x[0]) and np.array_equal(a[1:], bb)
+    q = int(primes[1])
+    psi = int(tw[1][1 << (log_dim - 1)]) if False else int(o.orc_minimal_primitive_root(2 * dim, q))
+    rev = lambda v: int(format(v, f"0{log_dim}b")[::-1], 2)
+    for k in (0, 1, dim - 1):
+        e = 2 * rev(k) + 1
+        want = sum(int(x[1][j]) * pow(psi, j * e, q) for j in range(dim)) % q
+        assert int(a[1][k]) == want
+    o.orc_inwt_1d(P(a), P(itw), P(itws), P(primes), P(ninv), P(ninvs), dim, count - 1, 1)
+    assert np.array_equal(a, x)
+    o.orc_destroy(c)
+
+
+@pytest.mark.parametrize("sizes", [(2, 2), (3, 2), (2, 4), (5, 5)])
+def test_tensor_mxn_is_polynomial_product_in_the_key(sizes):
+    """orc_tensor_mxn (polymath.cu:546-594): out[j] = sum_{i1+i2=j} a[i1] b[i2] mod q, against Python integers."""
+    sa, sb = sizes
+    ps = H.params_small(4096, l=2, alpha=1)
+    o = H.oracle()
+    l, n = ps.limbs(), ps.n
+    rng = np.random.default_rng(7 * sa + sb)
+    a = np.stack([np.stack([rng.integers(0, int(ps.primes[i]), n, dtype=np.uint64) for i in range(l)]) for _ in range(sa)])
+    b = np.stack([np.stack([rng.integers(0, int(ps.primes[i]), n, dtype=np.uint64) for i in range(l)]) for _ in range(sb)])
+    a[:, :, 0] = [[int(ps.primes[i]) - 1 for i in range(l)]] * sa   # extreme residues: largest 128-bit sums
+    b[:, :, 0] = [[int(ps.primes[i]) - 1 for i in range(l)]] * sb
+    out = np.zeros((sa + sb - 1, l, n), dtype=np.uint64)
+    o.orc_tensor_mxn(ps.octx(), P(a), sa, P(b), sb, P(out), l)
+    for i in range(l):
+        q = int(ps.primes[i])
+        for x in (0, 1, 17, n - 1):
+            for j in range(sa + sb - 1):
+                want = sum(int(a[u, i, x]) * int(b[j - u, i, x]) for u in range(sa) if 0 <= j - u < sb) % q
+                assert int(out[j, i, x]) == want
+    # in place on the first operand (the reference writes into encrypted1's resized buffer)
+    buf = np.zeros((sa + sb - 1, l, n), dtype=np.uint64)
+    buf[:sa] = a
+    o.orc_tensor_mxn(ps.octx(), P(buf), sa, P(b), sb, P(buf), l)
+    assert np.array_equal(buf, out)
+
+
 def test_keyswitch_is_hybrid_keyswitch():
     """Semantic pin of modup/inner-product/moddown: with evk_d = (P * qhat_d * qhat_d^-1-ish gadget) * s' the output of
     the path must equal c2 * s' up to the rounding error of mod-down -- checked through a noise-free gadget key:
