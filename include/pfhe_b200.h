@@ -130,6 +130,26 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
                             const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
                             void *stream);
+/* ---- BFV with mul_tech_type::hps_overq_leveled (pfhe_engine_set_mul_tech(e, 4)) ---------------------------------
+ * The reference decides per operation how many levels to drop from the ciphertexts' noise-scale degree
+ * (FindLevelsToDrop, evaluate.cu:550-643; the degree lives on PhantomCiphertext, ciphertext.h:21,97-131): the caller
+ * passes multiplicative_depth = max(noiseScaleDeg) - 1 exactly like bfv_multiply_hps (:680-690) / keyswitch_inplace
+ * (eval_key_switch.cu:113-123) do, and hands the result to the three leveled entry points.  All buffers are at the
+ * first data level ([.][size_Q][n], coefficient form).  pfhe_multiply / pfhe_multiply_and_relin with this mul_tech
+ * run with 0 levels dropped (= hps_overq). */
+int pfhe_find_levels_to_drop(pfhe_engine *e, size_t multiplicative_depth, int is_key_switch, int is_asymmetric,
+                             int *levels);
+/* bfv_multiply_hps (evaluate.cu:647-801) with levels_dropped levels: destination = [3][size_Q][n] */
+int pfhe_multiply_leveled(pfhe_engine *e, const uint64_t *encrypted1, const uint64_t *encrypted2, uint64_t *destination,
+                          int levels_dropped, void *stream);
+/* bfv_mul_relin_hps (evaluate.cu:819-1026): destination = [2][size_Q][n] */
+int pfhe_multiply_and_relin_leveled(pfhe_engine *e, const uint64_t *encrypted1, const uint64_t *encrypted2,
+                                    uint64_t *destination, const uint64_t *const *relin_keys, int levels_dropped,
+                                    void *stream);
+/* keyswitch_inplace (eval_key_switch.cu:95-182) with levels dropped: encrypted = [2][size_Q][n] in/out, c2 = [size_Q][n] */
+int pfhe_keyswitch_leveled_inplace(pfhe_engine *e, uint64_t *encrypted, const uint64_t *c2, const uint64_t *const *keys,
+                                   int levels_dropped, void *stream);
+
 /* fnwt_1d[_opt] / inwt_1d[_opt] (include/ntt.cuh:157-170, src/ntt/ntt_1d.cu:146-292): single-block negacyclic
  * transforms for dim <= 2048 on CALLER-SUPPLIED device tables in the reference's order (twiddles[bitrev(i)] = psi^i with
  * separate Shoup arrays, itwiddles[1] already times n^-1), modulus = DModulus array {value, const_ratio[0], const_ratio[1]}

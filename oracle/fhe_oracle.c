@@ -1226,6 +1226,212 @@ int orc_bfv_multiply_hps(const orc_ctx *c, const u64 *ct1, const u64 *ct2, u64 *
     return 0;
 }
 
+/* ------------------------------------------------------------------------------------------------------
+ * BFV multiplication, HPS-over-Q variants (mul_tech_type::hps_overq and, with drop > 0, the arithmetic of
+ * hps_overq_leveled; evaluate.cu:647-801, rns.cu:794-975,1748-1816, rns_bconv.cu:231-246, host/rns.cu:470-495).
+ * Ql = the first size_Q - drop primes of Q, Rl = size_Ql primes below min(Q), QlDrop = the dropped primes.
+ * ---------------------------------------------------------------------------------------------------- */
+/* bConv_BEHZ_var1 (rns_bconv.cu:231-246): y_i = x_i * (-P * qhat_i^-1) mod q_i, out_j = sum_i y_i * (q_i^-1 mod p_j) */
+static void bconv_var1(const u64 *ibase, int ni, const u64 *obase, int no, const u64 *in, u64 *out, size_t n) {
+    u64 c1[72];
+    u64 *mat = (u64 *)malloc((size_t)no * ni * 8);
+    for (int i = 0; i < ni; i++) {
+        u64 qi = ibase[i];
+        u64 PQ = orc_mulmod(prod_mod(obase, no, qi), orc_invmod(qhat_mod(ibase, ni, i, qi), qi), qi);
+        c1[i] = qi - PQ; /* host/rns.cu:481-482: q_i - (P * qhat_i^-1 mod q_i), = q_i when that product is 0 */
+    }
+    for (int j = 0; j < no; j++)
+        for (int i = 0; i < ni; i++) mat[(size_t)j * ni + i] = orc_invmod(ibase[i] % obase[j], obase[j]);
+#pragma omp parallel for num_threads(g_threads)
+    for (size_t x = 0; x < n; x++) {
+        u64 y[72];
+        for (int i = 0; i < ni; i++) y[i] = (u64)(((u128)in[(size_t)i * n + x] * c1[i]) % ibase[i]);
+        for (int j = 0; j < no; j++) {
+            u64 p = obase[j];
+            u128 acc = 0;
+            for (int i = 0; i < ni; i++) acc = (acc + (u128)y[i] * mat[(size_t)j * ni + i]) % p;
+            out[(size_t)j * n + x] = (u64)acc;
+        }
+    }
+    free(mat);
+}
+
+/* scaleAndRound_HPS_QlRl_Ql_kernel (rns.cu:1748-1784), also used as scaleAndRound_HPS_Q_Ql (:1797-1805):
+ * out_i = sum_j xb_j * tab[i][j] + xa_i * tab[i][nb] + alpha  mod a_i,  alpha = trunc(0.5 + sum_j double(xb_j) * frac_j),
+ * re-reduced limb after limb like the reference does.  xa = [na][n] (base A = outputs), xb = [nb][n]. */
+static void scale_round_to_a(const u64 *A, int na, int nb, const u64 *tab, const double *frac, const u64 *xa,
+                             const u64 *xb, u64 *out, size_t n) {
+#pragma omp parallel for num_threads(g_threads)
+    for (size_t k = 0; k < n; k++) {
+        double nu = 0.5;
+        for (int j = 0; j < nb; j++) nu = fma((double)xb[(size_t)j * n + k], frac[j], nu);
+        u64 alpha = sat_u64(nu);
+        u64 xi[72];
+        for (int i = 0; i < na; i++) xi[i] = xa[(size_t)i * n + k]; /* out may alias xa */
+        for (int i = 0; i < na; i++) {
+            u64 q = A[i];
+            u128 cur = 0;
+            for (int j = 0; j < nb; j++) cur = (cur + (u128)xb[(size_t)j * n + k] * tab[(size_t)i * (nb + 1) + j]) % q;
+            cur = (cur + (u128)xi[i] * tab[(size_t)i * (nb + 1) + nb]) % q;
+            alpha %= q;
+            out[(size_t)i * n + k] = addmod((u64)cur, alpha, q);
+        }
+    }
+}
+
+/* tables of the two scale-and-round forms: W_i = mult * prod(num) * (Shat_i^-1 mod s_i) over S = A u B (rns.cu:826-893
+ * with mult = t, num = A; rns.cu:921-968 with mult = 1, num = A, S = Q): frac_j = (W_{na+j} mod b_j) / b_j,
+ * tab[i][j] = floor(W_{na+j} / b_j) mod a_i, tab[i][nb] = floor(W_i / a_i) mod a_i */
+static void scale_round_tables(const u64 *A, int na, const u64 *B, int nb, u64 mult, u64 *tab, double *frac) {
+    u64 S[144];
+    memcpy(S, A, na * 8);
+    memcpy(S + na, B, nb * 8);
+    for (int i = 0; i < na + nb; i++) {
+        big_t W = {{1}, 1};
+        for (int k = 0; k < na; k++) big_mul_word(&W, A[k]);
+        big_mul_word(&W, mult);
+        big_mul_word(&W, orc_invmod(qhat_mod(S, na + nb, i, S[i]), S[i]));
+        u64 rem = big_divmod_word(&W, S[i]); /* W <- floor(W / s_i) */
+        if (i >= na) {
+            frac[i - na] = (double)rem / (double)S[i];
+            for (int a = 0; a < na; a++) tab[(size_t)a * (nb + 1) + (i - na)] = big_mod_word(&W, A[a]);
+        } else {
+            tab[(size_t)i * (nb + 1) + nb] = big_mod_word(&W, A[i]);
+        }
+    }
+}
+
+/* out[3][size_Q][n]; drop = levels dropped (0 for mul_tech hps_overq) */
+int orc_bfv_multiply_hps_overq(const orc_ctx *c, const u64 *ct1, const u64 *ct2, u64 *out, int drop) {
+    const size_t n = c->n;
+    const int lq = c->size_Q, ll = lq - drop;
+    const u64 *Q = c->primes, t = c->t;
+    if (lq > 35 || drop < 0 || ll < 1) return -1;
+    u64 R[72], S[144];
+    u64 qmin = Q[0];
+    for (int i = 1; i < lq; i++)
+        if (Q[i] < qmin) qmin = Q[i];
+    if (get_primes_below(n, qmin, ll, R)) return -1; /* rns.cu:796-801: Rl has as many primes as Ql */
+    const int ls = 2 * ll;
+    memcpy(S, Q, ll * 8);
+    memcpy(S + ll, R, ll * 8);
+    orc_ctx *sx = orc_create(ORC_SCHEME_BFV, n, S, ls, 0, 0);
+    if (!sx) return -1;
+    int ids[144];
+    for (int i = 0; i < ls; i++) ids[i] = i;
+    const size_t ps = (size_t)ls * n, pq = (size_t)lq * n, pl = (size_t)ll * n;
+    /* Q -> Ql scale-and-round tables of the leveled form (rns.cu:921-968) */
+    u64 *dtab = NULL;
+    double *dfrac = NULL;
+    if (drop) {
+        dtab = (u64 *)malloc((size_t)ll * (drop + 1) * 8);
+        dfrac = (double *)malloc(drop * sizeof(double));
+        scale_round_tables(Q, ll, Q + ll, drop, 1, dtab, dfrac);
+    }
+    u64 *e[2];
+    for (int s = 0; s < 2; s++) {
+        const u64 *ct = s ? ct2 : ct1;
+        e[s] = (u64 *)malloc(3 * ps * 8);
+        for (int p = 0; p < 2; p++) {
+            u64 *x = e[s] + p * ps;
+            const u64 *src = ct + p * pq;
+            if (s == 0) { /* evaluate.cu:706-721 */
+                if (drop) scale_round_to_a(Q, ll, drop, dtab, dfrac, src, src + pl, x, n);
+                else memcpy(x, src, pl * 8);
+                bconv_hps(Q, ll, R, ll, x, x + pl, n);
+            } else { /* evaluate.cu:752-758: Q (or Ql) -> Rl by the var1 conversion, then Rl -> Ql */
+                bconv_var1(Q, drop ? lq : ll, R, ll, src, x + pl, n);
+                bconv_hps(R, ll, Q, ll, x + pl, x, n);
+            }
+            orc_ntt_forward(sx, x, ls, ids);
+        }
+    }
+    u64 *d = (u64 *)malloc(3 * ps * 8);
+    orc_tensor_2x2(sx, e[0], e[1], d, ls);
+    for (int p = 0; p < 3; p++) orc_ntt_inverse(sx, d + p * ps, ls, ids);
+    u64 *tab = (u64 *)malloc((size_t)ll * (ll + 1) * 8);
+    double *fr = (double *)malloc(ll * sizeof(double));
+    scale_round_tables(Q, ll, R, ll, t, tab, fr);
+    for (int p = 0; p < 3; p++) {
+        const u64 *x = d + p * ps;
+        u64 *o = out + p * pq;
+        scale_round_to_a(Q, ll, ll, tab, fr, x, x + pl, o, n); /* scaleAndRound_HPS_QlRl_Ql, evaluate.cu:788 */
+        if (drop) { /* ExpandCRTBasis_Ql_Q (rns.cu:1810-1834): times (QlDrop mod q_i), dropped limbs zero */
+            for (int i = 0; i < ll; i++) {
+                u64 f = prod_mod(Q + ll, drop, Q[i]);
+                for (size_t k = 0; k < n; k++) o[(size_t)i * n + k] = orc_mulmod(o[(size_t)i * n + k], f, Q[i]);
+            }
+            memset(o + pl, 0, (pq - pl) * 8);
+        }
+    }
+    free(fr); free(tab); free(d); free(e[0]); free(e[1]); free(dtab); free(dfrac);
+    orc_destroy(sx);
+    return 0;
+}
+
+/* keyswitch_inplace for hps_overq_leveled with `drop` levels dropped (eval_key_switch.cu:109-181): c2 over Q is scaled
+ * down to Ql (scaleAndRound_HPS_Q_Ql; skipped when c2_low: c2 = [ll][n] already lives at Ql, the fused form
+ * evaluate.cu:966-1022), switched at that level, and the result is expanded back to Q and added to ct = [2][size_Q][n] */
+int orc_bfv_keyswitch_leveled(const orc_ctx *c, u64 *ct, const u64 *c2, const u64 *evk, int drop, int c2_low) {
+    const size_t n = c->n;
+    const int lq = c->size_Q, ll = lq - drop;
+    const u64 *Q = c->primes;
+    if (drop < 0 || ll < 1) return -1;
+    if (drop == 0) {
+        orc_keyswitch(c, lq, ct, c2, evk);
+        return 0;
+    }
+    const size_t pl = (size_t)ll * n, pq = (size_t)lq * n;
+    u64 *low = (u64 *)malloc(pl * 8);
+    if (c2_low) memcpy(low, c2, pl * 8);
+    else {
+        u64 *tab = (u64 *)malloc((size_t)ll * (drop + 1) * 8);
+        double *frac = (double *)malloc(drop * sizeof(double));
+        scale_round_tables(Q, ll, Q + ll, drop, 1, tab, frac);
+        scale_round_to_a(Q, ll, drop, tab, frac, c2, c2 + pl, low, n);
+        free(tab); free(frac);
+    }
+    u64 *ks = (u64 *)calloc(2 * pl, 8);
+    orc_keyswitch(c, ll, ks, low, evk);
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < ll; i++) { /* ExpandCRTBasis_Ql_Q + add_to_ct (rns.cu:1810-1856) */
+            u64 f = prod_mod(Q + ll, drop, Q[i]);
+            for (size_t x = 0; x < n; x++) {
+                u64 *o = ct + k * pq + (size_t)i * n + x;
+                *o = addmod(*o, orc_mulmod(ks[k * pl + (size_t)i * n + x], f, Q[i]), Q[i]);
+            }
+        }
+    free(ks); free(low);
+    return 0;
+}
+
+/* bfv_mul_relin_hps for the over-Q variants (evaluate.cu:819-1026): with levels dropped, c0 and c1 are expanded back
+ * to Q, c2 stays at Ql and is switched there */
+int orc_bfv_multiply_relin_hps_overq(const orc_ctx *c, const u64 *ct1, const u64 *ct2, const u64 *rlk, u64 *out,
+                                     int drop) {
+    const size_t n = c->n;
+    const int lq = c->size_Q, ll = lq - drop;
+    const size_t pq = (size_t)lq * n;
+    u64 *d = (u64 *)malloc(3 * pq * 8);
+    if (orc_bfv_multiply_hps_overq(c, ct1, ct2, d, drop)) {
+        free(d);
+        return -1;
+    }
+    if (drop) { /* undo the expansion of c2: its Ql residues are what the fused form switches */
+        for (int i = 0; i < ll; i++) {
+            u64 q = c->primes[i], finv = orc_invmod(prod_mod(c->primes + ll, drop, q), q);
+            for (size_t x = 0; x < n; x++) {
+                u64 *v = d + 2 * pq + (size_t)i * n + x;
+                *v = orc_mulmod(*v, finv, q);
+            }
+        }
+    }
+    int rc = orc_bfv_keyswitch_leveled(c, d, d + 2 * pq, rlk, drop, 1);
+    memcpy(out, d, 2 * pq * 8);
+    free(d);
+    return rc;
+}
+
 int orc_bfv_multiply_relin_hps(const orc_ctx *c, const u64 *ct1, const u64 *ct2, const u64 *rlk, u64 *out) {
     size_t poly = (size_t)c->size_Q * c->n;
     u64 *d = (u64 *)malloc(3 * poly * 8);

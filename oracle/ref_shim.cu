@@ -308,6 +308,28 @@ int ref_multiply_sizes(void *p, size_t chain_index, const uint64_t *ct1, size_t 
     SHIM_CATCH
 }
 
+/* multiply_inplace (relin = 0: out = [3][l][n]), multiply_inplace + relinearize_inplace (1) or multiply_and_relin_inplace
+ * (2) (out = [2][l][n]) on ciphertexts carrying the given noise-scale degrees: what mul_tech hps_overq_leveled reads to
+ * decide how many levels to drop (evaluate.cu:680-690) */
+int ref_multiply_deg(void *p, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, size_t deg1, size_t deg2,
+                     int relin, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    bool ntt = h->scheme != scheme_type::bfv;
+    auto a = make_ct(h, chain_index, 2, ct1, ntt);
+    auto b = make_ct(h, chain_index, 2, ct2, ntt);
+    a.SetNoiseScaleDeg(deg1);
+    b.SetNoiseScaleDeg(deg2);
+    if (relin == 2) multiply_and_relin_inplace(*h->ctx, a, b, *h->rlk);
+    else {
+        multiply_inplace(*h->ctx, a, b);
+        if (relin == 1) relinearize_inplace(*h->ctx, a, *h->rlk);
+    }
+    fetch_ct(a, out);
+    return 0;
+    SHIM_CATCH
+}
+
 /* stage-wise key-switch taps (eval_key_switch.cu:95-182) for differential debugging */
 int ref_modup(void *p, size_t chain_index, const uint64_t *c2, uint64_t *t_mod_up) {
     SHIM_TRY

@@ -159,6 +159,8 @@ class PhantomCiphertext:
         self.scale = scale
         self.is_ntt_form = is_ntt_form
         self.correction_factor = 1
+        self.noise_scale_deg = 1     # noiseScaleDeg_ (include/ciphertext.h:21): read by mul_tech hps_overq_leveled
+        self.is_asymmetric = False   # is_asymmetric_ (:23)
 
     @classmethod
     def from_host(cls, context, words, chain_index=1, scale=1.0, is_ntt_form=True):
@@ -177,7 +179,9 @@ class PhantomCiphertext:
         return self.data.shape[1]
 
     def clone(self):
-        return PhantomCiphertext(None, self.data.clone(), self.chain_index, self.scale, self.is_ntt_form)
+        c = PhantomCiphertext(None, self.data.clone(), self.chain_index, self.scale, self.is_ntt_form)
+        c.correction_factor, c.noise_scale_deg, c.is_asymmetric = self.correction_factor, self.noise_scale_deg, self.is_asymmetric
+        return c
 
 
 class PhantomRelinKey:
@@ -215,6 +219,17 @@ def _require_ntt(context, ct):
         raise ValueError("BFV encrypted cannot be in NTT form")
 
 
+def _leveled(context):
+    return context.scheme == scheme_type.bfv and context.parms.mul_tech == mul_tech_type.hps_overq_leveled
+
+
+def _levels_to_drop(context, depth, is_key_switch, is_asymmetric):
+    """FindLevelsToDrop (src/evaluate.cu:550-643)."""
+    lv = ctypes.c_int()
+    check(lib.pfhe_find_levels_to_drop(context._h, depth, int(is_key_switch), int(is_asymmetric), ctypes.byref(lv)))
+    return lv.value
+
+
 def multiply_inplace(context, encrypted1, encrypted2):
     """multiply_inplace (src/evaluate.cu:1029-1057 -> bgv_ckks_multiply :345-397, bfv_multiply_behz :451-548)."""
     _require_ntt(context, encrypted1)
@@ -227,7 +242,14 @@ def multiply_inplace(context, encrypted1, encrypted2):
     s1, s2 = encrypted1.size(), encrypted2.size()
     dst = torch.empty((s1 + s2 - 1, l, n), dtype=torch.int64, device=encrypted1.data.device)
     a, b = encrypted1.data, encrypted2.data
-    if s1 == 2 and s2 == 2:
+    if _leveled(context):   # bfv_multiply_hps, leveled branch (evaluate.cu:680-690, 798-800)
+        if s1 != 2 or s2 != 2:
+            raise RuntimeError("dest_size must be 3 when computing BFV multiplication using HPS")
+        deg = max(encrypted1.noise_scale_deg, encrypted2.noise_scale_deg)
+        drop = _levels_to_drop(context, deg - 1, False, encrypted1.is_asymmetric)
+        check(lib.pfhe_multiply_leveled(context._h, _ptr(a), _ptr(b), _ptr(dst), drop, _stream()))
+        encrypted1.noise_scale_deg = deg + 1
+    elif s1 == 2 and s2 == 2:
         check(lib.pfhe_multiply(context._h, encrypted1.chain_index, _ptr(a), _ptr(a if encrypted1 is encrypted2 else b),
                                 _ptr(dst), _stream()))
     else:   # tensor_prod_mxn_rns_poly branch of bgv_ckks_multiply (evaluate.cu:382-386)
@@ -242,8 +264,13 @@ def relinearize_inplace(context, encrypted, relin_keys):
     if encrypted.size() != 3:
         raise ValueError("destination_size must be 3")
     _require_ntt(context, encrypted)
-    check(lib.pfhe_relinearize_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data),
-                                       relin_keys.public_keys_ptr(), _stream()))
+    if _leveled(context):   # keyswitch_inplace, leveled branch (eval_key_switch.cu:113-123): is_relin -> not a key switch
+        drop = _levels_to_drop(context, encrypted.noise_scale_deg - 1, False, encrypted.is_asymmetric)
+        check(lib.pfhe_keyswitch_leveled_inplace(context._h, _ptr(encrypted.data), _ptr(encrypted.data[2]),
+                                                 relin_keys.public_keys_ptr(), drop, _stream()))
+    else:
+        check(lib.pfhe_relinearize_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data),
+                                           relin_keys.public_keys_ptr(), _stream()))
     encrypted.data = encrypted.data[:2]
 
 
@@ -254,8 +281,15 @@ def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
     dst = torch.empty_like(encrypted1.data)
-    check(lib.pfhe_multiply_and_relin(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
-                                      _ptr(encrypted2.data), _ptr(dst), relin_keys.public_keys_ptr(), _stream()))
+    if _leveled(context):   # bfv_mul_relin_hps, leveled branch (evaluate.cu:845-856, 962-964)
+        deg = max(encrypted1.noise_scale_deg, encrypted2.noise_scale_deg)
+        drop = _levels_to_drop(context, deg - 1, False, encrypted1.is_asymmetric)
+        check(lib.pfhe_multiply_and_relin_leveled(context._h, _ptr(encrypted1.data), _ptr(encrypted2.data), _ptr(dst),
+                                                  relin_keys.public_keys_ptr(), drop, _stream()))
+        encrypted1.noise_scale_deg = deg + 1
+    else:
+        check(lib.pfhe_multiply_and_relin(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
+                                          _ptr(encrypted2.data), _ptr(dst), relin_keys.public_keys_ptr(), _stream()))
     encrypted1.data = dst   # like the reference's resize: the ciphertext now owns a new buffer
     if context.scheme == scheme_type.ckks:
         encrypted1.scale = encrypted1.scale * encrypted2.scale

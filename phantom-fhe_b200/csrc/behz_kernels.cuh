@@ -211,4 +211,136 @@ __global__ void __launch_bounds__(BEHZ_THREADS) k_hps_scale_round(const HpsScale
     }
 }
 
+// ---------------------------------------------------------------------------------------------------
+// HPS over Q (mul_tech_type::hps_overq, and the arithmetic of hps_overq_leveled; evaluate.cu:647-801).  Three generic
+// thread-per-coefficient kernels on strided [limb][n] views; grid.y = polynomial.
+// ---------------------------------------------------------------------------------------------------
+struct PolyView {        // limb i of polynomial p at base + p * poly_stride + i * n
+    u64 *base;
+    size_t poly_stride;
+};
+
+// bConv_HPS (rns_bconv.cu:278-304,354-372): exact conversion with the floating-point overflow estimate
+struct BconvHpsArgs {
+    PolyView in, out;
+    const Tw *hinv;         // [ni]      ihat_i^-1 mod i_i
+    const double *inv;      // [ni]      1.0 / i_i
+    const u64 *mat;         // [no][ni]  ihat_i mod o_j
+    const u64 *Imod;        // [no]      I mod o_j
+    const Modulus *mod_in, *mod_out;
+    int ni, no;
+    size_t n;
+};
+__global__ void __launch_bounds__(BEHZ_THREADS) k_bconv_hps(const BconvHpsArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t x = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 *src = a.in.base + (size_t) blockIdx.y * a.in.poly_stride + x;
+    u64 y[BEHZ_MAX_LIMBS];
+    double frac = 0.0;
+    for (int i = 0; i < a.ni; i++) {
+        y[i] = mul_shoup(src[(size_t) i * a.n], a.hinv[i], a.mod_in[i].q);
+        frac = __fma_rn((double) y[i], a.inv[i], frac);
+    }
+    const u64 v = (u64) llround(frac);
+    u64 *dst = a.out.base + (size_t) blockIdx.y * a.out.poly_stride + x;
+    for (int j = 0; j < a.no; j++) {
+        const Modulus m = a.mod_out[j];
+        Acc128 acc{0, 0};
+        const u64 *row = a.mat + (size_t) j * a.ni;
+        for (int i = 0; i < a.ni; i++) acc.mac(y[i], row[i]);
+        const u64 r = barrett128(acc.lo, acc.hi, m);
+        dst[(size_t) j * a.n] = sub_mod(r, mul_mod(v, a.Imod[j], m), m.q);
+    }
+}
+
+// bConv_BEHZ_var1 (rns_bconv.cu:231-246): y_i = x_i * (-O * ihat_i^-1) mod i_i, out_j = sum_i y_i * (i_i^-1 mod o_j)
+struct BconvVar1Args {
+    PolyView in, out;
+    const Tw *c1;           // [ni]
+    const u64 *mat;         // [no][ni]
+    const Modulus *mod_in, *mod_out;
+    int ni, no;
+    size_t n;
+};
+__global__ void __launch_bounds__(BEHZ_THREADS) k_bconv_var1(const BconvVar1Args a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t x = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 *src = a.in.base + (size_t) blockIdx.y * a.in.poly_stride + x;
+    u64 y[BEHZ_MAX_LIMBS];
+    for (int i = 0; i < a.ni; i++) {
+        // the constant may equal the modulus itself (host/rns.cu:481-482): reduce through the general product
+        y[i] = mul_mod(src[(size_t) i * a.n], a.c1[i].x, a.mod_in[i]);
+    }
+    u64 *dst = a.out.base + (size_t) blockIdx.y * a.out.poly_stride + x;
+    for (int j = 0; j < a.no; j++) {
+        const Modulus m = a.mod_out[j];
+        Acc128 acc{0, 0};
+        const u64 *row = a.mat + (size_t) j * a.ni;
+        for (int i = 0; i < a.ni; i++) acc.mac(y[i], row[i]);
+        dst[(size_t) j * a.n] = barrett128(acc.lo, acc.hi, m);
+    }
+}
+
+// scaleAndRound_HPS_QlRl_Ql_kernel (rns.cu:1748-1784), also scaleAndRound_HPS_Q_Ql (:1797-1805):
+//   out_i = sum_j xb_j tab[i][j] + xa_i tab[i][nb] + alpha mod a_i,  alpha = trunc(0.5 + sum_j double(xb_j) frac_j),
+// alpha re-reduced limb after limb as the reference does.  Optionally followed by ExpandCRTBasis_Ql_Q (:1810-1834):
+// times expand[i], and `zero` further limbs of the output cleared.
+struct ScaleRoundArgs {
+    PolyView xa, xb, out;
+    const u64 *tab;         // [na][nb + 1]
+    const double *frac;     // [nb]
+    const Tw *expand;       // [na] or null
+    const Modulus *mod_a;
+    int na, nb, zero;
+    size_t n;
+};
+__global__ void __launch_bounds__(BEHZ_THREADS) k_scale_round(const ScaleRoundArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t x = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 *sa = a.xa.base + (size_t) blockIdx.y * a.xa.poly_stride + x;
+    const u64 *sb = a.xb.base + (size_t) blockIdx.y * a.xb.poly_stride + x;
+    u64 xb[BEHZ_MAX_LIMBS], xi[BEHZ_MAX_LIMBS];
+    double nu = 0.5;
+    for (int j = 0; j < a.nb; j++) {
+        xb[j] = sb[(size_t) j * a.n];
+        nu = __fma_rn((double) xb[j], a.frac[j], nu);
+    }
+    for (int i = 0; i < a.na; i++) xi[i] = sa[(size_t) i * a.n];   // out may alias xa
+    u64 alpha = (u64) nu;   // cvt.rzi.u64.f64, as static_cast<uint64_t> compiles to
+    u64 *dst = a.out.base + (size_t) blockIdx.y * a.out.poly_stride + x;
+    for (int i = 0; i < a.na; i++) {
+        const Modulus m = a.mod_a[i];
+        const u64 *row = a.tab + (size_t) i * (a.nb + 1);
+        Acc128 acc{0, 0};
+        for (int j = 0; j < a.nb; j++) acc.mac(xb[j], row[j]);
+        acc.mac(xi[i], row[a.nb]);
+        const u64 cur = barrett128(acc.lo, acc.hi, m);
+        alpha = barrett64(alpha, m);
+        u64 v = add_mod(cur, alpha, m.q);
+        if (a.expand) v = mul_shoup(v, a.expand[i], m.q);
+        dst[(size_t) i * a.n] = v;
+    }
+    for (int i = 0; i < a.zero; i++) dst[(size_t) (a.na + i) * a.n] = 0;
+}
+
+// ExpandCRTBasis_Ql_Q_add_to_ct (rns.cu:1836-1856): ct[p][i] += in[p][i] * expand_i mod q_i for the ll kept limbs;
+// grid.y = polynomial * ll + limb, two coefficients per thread
+__global__ void __launch_bounds__(BEHZ_THREADS) k_expand_add(PolyView ct, PolyView in, const Tw *expand, const Modulus *mod,
+                                                            int ll, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int p = blockIdx.y / ll, i = blockIdx.y % ll;
+    const size_t x = ((size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x) * 2;
+    const u64 q = mod[i].q;
+    const Tw f = expand[i];
+    u64 *d = ct.base + (size_t) p * ct.poly_stride + (size_t) i * n + x;
+    const u64 *s = in.base + (size_t) p * in.poly_stride + (size_t) i * n + x;
+    const ulonglong2 a = *reinterpret_cast<const ulonglong2 *>(d), b = *reinterpret_cast<const ulonglong2 *>(s);
+    *reinterpret_cast<ulonglong2 *>(d) =
+            make_ulonglong2(add_mod(a.x, mul_shoup(b.x, f, q), q), add_mod(a.y, mul_shoup(b.y, f, q), q));
+}
+
 } // namespace pfhe

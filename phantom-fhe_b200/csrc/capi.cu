@@ -265,6 +265,40 @@ int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const
     else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
     API_END
 }
+int pfhe_find_levels_to_drop(pfhe_engine *e, size_t multiplicative_depth, int is_key_switch, int is_asymmetric,
+                             int *levels) {
+    API_BEGIN
+    require(e && levels, "null pointer");
+    *levels = e->impl.find_levels_to_drop(multiplicative_depth, is_key_switch != 0, is_asymmetric != 0);
+    API_END
+}
+static void require_leveled(pfhe_engine *e, int drop) {
+    require(e != nullptr, "engine is null");
+    require(e->impl.scheme() == Scheme::bfv && e->impl.mul_tech() == 4, "needs BFV with mul_tech hps_overq_leveled");
+    require(drop >= 0 && drop < e->impl.size_Q(), "levels dropped out of range");
+}
+int pfhe_multiply_leveled(pfhe_engine *e, const uint64_t *ct1, const uint64_t *ct2, uint64_t *dst, int levels_dropped,
+                          void *stream) {
+    API_BEGIN
+    require_leveled(e, levels_dropped);
+    require(dst != ct1 && dst != ct2, "destination aliases an operand");
+    e->impl.bfv_multiply(e->impl.size_Q(), U(dst), U(ct1), U(ct2), S(stream), levels_dropped);
+    API_END
+}
+int pfhe_multiply_and_relin_leveled(pfhe_engine *e, const uint64_t *ct1, const uint64_t *ct2, uint64_t *dst,
+                                    const uint64_t *const *rlk, int levels_dropped, void *stream) {
+    API_BEGIN
+    require_leveled(e, levels_dropped);
+    e->impl.multiply_relin_leveled(e->impl.size_Q(), U(dst), U(ct1), U(ct2), K(rlk), levels_dropped, S(stream));
+    API_END
+}
+int pfhe_keyswitch_leveled_inplace(pfhe_engine *e, uint64_t *ct, const uint64_t *c2, const uint64_t *const *keys,
+                                   int levels_dropped, void *stream) {
+    API_BEGIN
+    require_leveled(e, levels_dropped);
+    e->impl.keyswitch_leveled(U(ct), U(c2), K(keys), levels_dropped, false, S(stream));
+    API_END
+}
 int pfhe_fnwt_1d(uint64_t *inout, const uint64_t *twiddles, const uint64_t *twiddles_shoup, const uint64_t *modulus,
                  size_t dim, size_t coeff_modulus_size, size_t start_modulus_idx, void *stream) {
     API_BEGIN

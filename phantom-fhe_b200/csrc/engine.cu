@@ -2,6 +2,7 @@
 #include "engine.hpp"
 
 #include <algorithm>
+#include <cmath>
 #include <numeric>
 #include <cstdlib>
 #include <cstring>
@@ -1176,19 +1177,259 @@ void Engine::bfv_multiply_hps(int l, u64 *out3, const u64 *ct1, const u64 *ct2, 
     }
 }
 
-void Engine::bfv_multiply(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cudaStream_t st) {
+// constants of HPS over Q with `drop` dropped levels (reference rns.cu:794-975; host/rns.cu:470-495 for the var1 form)
+const HpsQ &Engine::hpsq(int drop) {
+    if (scheme_ != Scheme::bfv || nR_ == 0) throw std::invalid_argument("unsupported scheme");
+    if (drop < 0 || drop >= size_Q_) throw std::invalid_argument("levels dropped out of range");
+    if ((int) hpsq_.size() <= drop) hpsq_.resize(drop + 1);
+    if (hpsq_[drop]) return *hpsq_[drop];
+    auto h = std::make_unique<HpsQ>();
+    const int ll = size_Q_ - drop;
+    h->ll = ll, h->drop = drop;
+    const std::vector<u64> Qall(primes_.begin(), primes_.begin() + size_Q_);
+    const std::vector<u64> Ql(primes_.begin(), primes_.begin() + ll);
+    const std::vector<u64> Qd(primes_.begin() + ll, primes_.begin() + size_Q_);
+    const std::vector<u64> R(rowq_.begin() + row_R_, rowq_.begin() + row_R_ + ll);   // Rl: as many primes as Ql
+    // bConv_HPS Ql -> Rl and Rl -> Ql
+    std::vector<Tw> q_hinv(ll), r_hinv(ll);
+    std::vector<double> q_inv(ll), r_inv(ll);
+    std::vector<u64> q_to_r((size_t) ll * ll), Ql_mod_r(ll), r_to_q((size_t) ll * ll), Rl_mod_q(ll);
+    for (int i = 0; i < ll; i++) {
+        q_hinv[i] = make_tw(hm::invmod(hm::product_mod(Ql, i, Ql[i]), Ql[i]), Ql[i]);
+        q_inv[i] = 1.0 / (double) Ql[i];
+        r_hinv[i] = make_tw(hm::invmod(hm::product_mod(R, i, R[i]), R[i]), R[i]);
+        r_inv[i] = 1.0 / (double) R[i];
+        Ql_mod_r[i] = hm::product_mod(Ql, -1, R[i]);
+        Rl_mod_q[i] = hm::product_mod(R, -1, Ql[i]);
+        for (int j = 0; j < ll; j++) {
+            q_to_r[(size_t) i * ll + j] = hm::product_mod(Ql, j, R[i]);   // row = output r_i, column = input q_j
+            r_to_q[(size_t) i * ll + j] = hm::product_mod(R, j, Ql[i]);
+        }
+    }
+    // bConv_BEHZ_var1 from Q (levels dropped) or Ql to Rl
+    const std::vector<u64> &I = drop ? Qall : Ql;
+    const int ni = (int) I.size();
+    std::vector<Tw> v1_c(ni);
+    std::vector<u64> v1_mat((size_t) ll * ni);
+    for (int i = 0; i < ni; i++) {
+        const u64 qi = I[i];
+        const u64 pq = hm::mulmod(hm::product_mod(R, -1, qi), hm::invmod(hm::product_mod(I, i, qi), qi), qi);
+        v1_c[i] = make_ulonglong2(qi - pq, 0);   // may equal q_i (host/rns.cu:481-482): used through the general product
+        for (int j = 0; j < ll; j++) v1_mat[(size_t) j * ni + i] = hm::invmod(qi % R[j], R[j]);
+    }
+    // scale-and-round tables: W_i = mult * prod(A) * (Shat_i^-1 mod s_i) over S = A u B
+    auto tables = [&](const std::vector<u64> &A, const std::vector<u64> &B, u64 mult, std::vector<u64> &tab,
+                      std::vector<double> &frac) {
+        const int na = (int) A.size(), nb = (int) B.size();
+        std::vector<u64> S(A);
+        S.insert(S.end(), B.begin(), B.end());
+        tab.assign((size_t) na * (nb + 1), 0);
+        frac.assign(nb, 0.0);
+        for (int i = 0; i < na + nb; i++) {
+            hm::BigUint W;
+            for (u64 a : A) W.mul_word(a);
+            W.mul_word(mult);
+            W.mul_word(hm::invmod(hm::product_mod(S, i, S[i]), S[i]));
+            const u64 rem = W.divmod_word(S[i]);
+            if (i >= na) {
+                frac[i - na] = (double) rem / (double) S[i];
+                for (int a = 0; a < na; a++) tab[(size_t) a * (nb + 1) + (i - na)] = W.mod_word(A[a]);
+            } else {
+                tab[(size_t) i * (nb + 1) + nb] = W.mod_word(A[i]);
+            }
+        }
+    };
+    std::vector<u64> sr_tab, dr_tab;
+    std::vector<double> sr_frac, dr_frac;
+    tables(Ql, R, t_, sr_tab, sr_frac);
+    h->q_hinv.upload(q_hinv), h->q_inv.upload(q_inv), h->q_to_r.upload(q_to_r), h->Ql_mod_r.upload(Ql_mod_r);
+    h->v1_c.upload(v1_c), h->v1_mat.upload(v1_mat);
+    h->r_hinv.upload(r_hinv), h->r_inv.upload(r_inv), h->r_to_q.upload(r_to_q), h->Rl_mod_q.upload(Rl_mod_q);
+    h->sr_tab.upload(sr_tab), h->sr_frac.upload(sr_frac);
+    if (drop) {
+        tables(Ql, Qd, 1, dr_tab, dr_frac);
+        std::vector<Tw> expand(ll);
+        for (int i = 0; i < ll; i++) expand[i] = make_tw(hm::product_mod(Qd, -1, Ql[i]), Ql[i]);
+        h->dr_tab.upload(dr_tab), h->dr_frac.upload(dr_frac), h->expand.upload(expand);
+    }
+    hpsq_[drop] = std::move(h);
+    return *hpsq_[drop];
+}
+
+// bfv_multiply_hps with mul_tech hps_overq / hps_overq_leveled (evaluate.cu:647-801): ct1 keeps its Ql residues (scaled
+// down from Q when levels are dropped) and is lifted to Rl exactly; ct2 goes to Rl through the var1 conversion and
+// comes back to Ql from there; tensor product over Ql u Rl; t/Rl scale-and-round straight to Ql; expansion back to Q.
+void Engine::bfv_multiply_hps_overq(int l, u64 *out3, const u64 *ct1, const u64 *ct2, int drop, cudaStream_t st,
+                                    bool keep_c2_low) {
+    if (l != size_Q_) throw std::invalid_argument("HPS multiplication is defined at the first data level only");
+    const HpsQ &h = hpsq(drop);
+    const int lq = size_Q_, ll = h.ll;
+    if (2 * ll > BEHZ_MAX_LIMBS || lq > BEHZ_MAX_LIMBS) throw std::invalid_argument("too many limbs for the HPS kernels");
+    const size_t need = (size_t) 14 * ll * n_;
+    if (ws_.behz.count < need) ws_.behz.alloc(std::max(need, (size_t) 7 * (size_Q_ + naux_) * n_));
+    const size_t pl = (size_t) ll * n_, pq = (size_t) lq * n_;
+    // operands over Ql [4][ll], tensor result over Ql [3][ll] and over Rl [3][ll] (adjacent), operands over Rl [4][ll]
+    u64 *eq = ws_.behz.p, *dq = eq + 4 * pl, *dr = dq + 3 * pl, *er = dr + 3 * pl;
+    const Modulus *mod_q = d_mod_.p, *mod_r = d_mod_.p + row_R_;
+    const dim3 g2((unsigned) (n_ / BEHZ_THREADS), 2), g3((unsigned) (n_ / BEHZ_THREADS), 3);
+    u64 *c1 = const_cast<u64 *>(ct1), *c2 = const_cast<u64 *>(ct2);
+    // ct1: Ql part (scaleAndRound_HPS_Q_Ql when levels were dropped), then the exact lift Ql -> Rl
+    PolyView ct1_ql{c1, pq};
+    if (drop) {
+        ScaleRoundArgs a{PolyView{c1, pq}, PolyView{c1 + pl, pq}, PolyView{eq, pl}, h.dr_tab.p, h.dr_frac.p, nullptr, mod_q,
+                         ll, drop, 0, n_};
+        launch_pdl(k_scale_round, g2, BEHZ_THREADS, 0, st, a);
+        check_launch("k_scale_round");
+        ct1_ql = PolyView{eq, pl};
+    }
+    {
+        BconvHpsArgs a{ct1_ql, PolyView{er, pl}, h.q_hinv.p, h.q_inv.p, h.q_to_r.p, h.Ql_mod_r.p, mod_q, mod_r, ll, ll, n_};
+        launch_pdl(k_bconv_hps, g2, BEHZ_THREADS, 0, st, a);
+        check_launch("k_bconv_hps");
+    }
+    // ct2: Q (or Ql) -> Rl by bConv_BEHZ_var1, then Rl -> Ql by bConv_HPS
+    {
+        BconvVar1Args a{PolyView{c2, pq}, PolyView{er + 2 * pl, pl}, h.v1_c.p, h.v1_mat.p, mod_q, mod_r, drop ? lq : ll, ll, n_};
+        launch_pdl(k_bconv_var1, g2, BEHZ_THREADS, 0, st, a);
+        check_launch("k_bconv_var1");
+        BconvHpsArgs b{PolyView{er + 2 * pl, pl}, PolyView{eq + 2 * pl, pl}, h.r_hinv.p, h.r_inv.p, h.r_to_q.p, h.Rl_mod_q.p,
+                       mod_r, mod_q, ll, ll, n_};
+        launch_pdl(k_bconv_hps, g2, BEHZ_THREADS, 0, st, b);
+        check_launch("k_bconv_hps");
+    }
+    {   // forward NTTs: ct1's Ql limbs come straight from the ciphertext when nothing was dropped
+        LimbVec v1, v2, vr;
+        for (int p = 0; p < 2; p++)
+            for (int i = 0; i < ll; i++) {
+                v1.push(p * ll + i, i, drop ? p * ll + i : p * lq + i);
+                v2.push(2 * ll + p * ll + i, i);
+            }
+        for (int p = 0; p < 4; p++)
+            for (int j = 0; j < ll; j++) vr.push(p * ll + j, row_R_ + j);
+        run_chunks(v1, rowq_, [&](const LimbList &lst, size_t) { ntt_fwd_list(eq, drop ? eq : ct1, lst, st); });
+        run_chunks(v2, rowq_, [&](const LimbList &lst, size_t) { ntt_fwd_list(eq, eq, lst, st); });
+        run_chunks(vr, rowq_, [&](const LimbList &lst, size_t) { ntt_fwd_list(er, er, lst, st); });
+    }
+    tensor_2x2(eq, eq + 2 * pl, dq, ll, st);
+    {
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), ll);
+        launch_pdl(k_tensor_2x2, grid, EW_THREADS, 0, st, (const u64 *) er, (const u64 *) (er + 2 * pl), dr, mod_r,
+                   bar(1, 2) + row_R_, RowArith{d_is_fp_.p + row_R_, d_fpc_.p + row_R_, 0, 0, 0}, n_, ll);
+        check_launch("k_tensor_2x2");
+    }
+    {
+        LimbVec v;
+        for (int p = 0; p < 3; p++)
+            for (int i = 0; i < ll; i++) v.push(p * ll + i, i);
+        for (int p = 0; p < 3; p++)
+            for (int j = 0; j < ll; j++) v.push(3 * ll + p * ll + j, row_R_ + j);
+        run_chunks(v, rowq_, [&](const LimbList &lst, size_t) { ntt_inv_list(dq, dq, lst, nullptr, 0, st); });
+    }
+    {   // scaleAndRound_HPS_QlRl_Ql (+ ExpandCRTBasis_Ql_Q when levels were dropped)
+        ScaleRoundArgs a{PolyView{dq, pl}, PolyView{dr, pl}, PolyView{out3, pq}, h.sr_tab.p, h.sr_frac.p,
+                         drop ? h.expand.p : nullptr, mod_q, ll, ll, drop, n_};
+        if (!(drop && keep_c2_low)) {
+            launch_pdl(k_scale_round, g3, BEHZ_THREADS, 0, st, a);
+        } else {   // bfv_mul_relin_hps (evaluate.cu:954-956): only c0 and c1 are expanded
+            launch_pdl(k_scale_round, g2, BEHZ_THREADS, 0, st, a);
+            ScaleRoundArgs b = a;
+            b.xa.base += 2 * pl, b.xb.base += 2 * pl, b.out.base += 2 * pq, b.expand = nullptr, b.zero = 0;
+            launch_pdl(k_scale_round, dim3(g2.x, 1), BEHZ_THREADS, 0, st, b);
+        }
+        check_launch("k_scale_round");
+    }
+}
+
+void Engine::keyswitch_leveled(u64 *ct, const u64 *c2, const u64 *const *evk, int drop, bool c2_low, cudaStream_t st) {
+    if (scheme_ != Scheme::bfv) throw std::invalid_argument("unsupported scheme");
+    const int lq = size_Q_;
+    if (drop == 0) {
+        keyswitch(lq, ct, c2, evk, ct, st);
+        return;
+    }
+    const HpsQ &h = hpsq(drop);
+    const int ll = h.ll;
+    const size_t pl = (size_t) ll * n_, pq = (size_t) lq * n_;
+    if (ws_.behz.count < 3 * pl) ws_.behz.alloc(std::max(3 * pl, (size_t) 7 * (size_Q_ + naux_) * n_));
+    u64 *ks = ws_.behz.p, *low = ks + 2 * pl;   // [2][ll][n] key-switch result, [ll][n] c2 at Ql
+    const dim3 g1((unsigned) (n_ / BEHZ_THREADS), 1);
+    u64 *c2m = const_cast<u64 *>(c2);
+    if (!c2_low) {   // scaleAndRound_HPS_Q_Ql (eval_key_switch.cu:139-144)
+        ScaleRoundArgs a{PolyView{c2m, pq}, PolyView{c2m + pl, pq}, PolyView{low, pl}, h.dr_tab.p, h.dr_frac.p, nullptr, d_mod_.p,
+                         ll, drop, 0, n_};
+        launch_pdl(k_scale_round, g1, BEHZ_THREADS, 0, st, a);
+        check_launch("k_scale_round");
+    } else {
+        PFHE_CUDA(cudaMemcpyAsync(low, c2, pl * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    keyswitch(ll, ks, low, evk, nullptr, st);
+    launch_pdl(k_expand_add, dim3((unsigned) (n_ / (2 * BEHZ_THREADS)), 2 * ll), BEHZ_THREADS, 0, st, PolyView{ct, pq},
+               PolyView{ks, pl}, (const Tw *) h.expand.p, (const Modulus *) d_mod_.p, ll, n_);
+    check_launch("k_expand_add");
+}
+
+// FindLevelsToDrop (reference src/evaluate.cu:550-643), same double-precision formulas in the same order
+int Engine::find_levels_to_drop(size_t multiplicativeDepth, bool isKeySwitch, bool isAsymmetric) {
+    if (scheme_ != Scheme::bfv || mul_tech_ != 4)
+        throw std::invalid_argument("FindLevelsToDrop is only used in HPS over Q Leveled");
+    const uint32_t n = (uint32_t) n_;
+    const double sigma = 3.2f, alpha = 36.0f;   // distributionParameter, assuranceMeasure (host/hestdparms.h:152-153)
+    const double p = (double) t_;
+    const uint32_t k = (uint32_t) size_P_;
+    const uint32_t numPartQ = (uint32_t) beta(size_Q_);
+    const double Bkey = 1.0;
+    u64 qmax = 0;
+    for (int i = 0; i < size_Q_; i++) qmax = std::max(qmax, primes_[i]);
+    const double dcrtBits = (double) (64 - __builtin_clzll(qmax));   // qMSB (rns.cu:587)
+    const double Berr = sigma * sqrt(alpha);
+    auto delta = [](uint32_t nn) -> double { return (2. * sqrt(nn)); };
+    auto Vnorm = [&](uint32_t nn) -> double {
+        if (isAsymmetric) return (1. + delta(nn) * Bkey) / 2.;
+        return Berr * (1. + 2. * delta(nn) * Bkey);
+    };
+    auto noiseKS = [&](uint32_t nn) -> double { return k * (numPartQ * delta(nn) * Berr + delta(nn) * Bkey + 1.0) / 2; };
+    auto C1 = [&](uint32_t nn) -> double { return delta(nn) * delta(nn) * p * Bkey; };
+    auto C2 = [&](uint32_t nn) -> double { return delta(nn) * delta(nn) * Bkey * Bkey / 2.0 + noiseKS(nn); };
+    auto logqBFV = [&](uint32_t nn) -> double {
+        if (multiplicativeDepth > 0)
+            return log(4 * p) + (multiplicativeDepth - 1) * log(C1(nn)) +
+                   log(C1(nn) * Vnorm(nn) + multiplicativeDepth * C2(nn));
+        return log(p * (4 * (Vnorm(nn))));
+    };
+    double logqPrev = 6. * log(10);
+    double logq = logqBFV(n);
+    while (fabs(logq - logqPrev) > log(1.001)) {
+        logqPrev = logq;
+        logq = logqBFV(n);
+    }
+    const double loge = logq / log(2) - 2 - log2(p);
+    const double logExtra = isKeySwitch ? log2(noiseKS(n)) : log2(delta(n));
+    int32_t levels = (int32_t) std::floor((loge - 2 * multiplicativeDepth - 16 - logExtra) / dcrtBits);
+    if (levels < 0) levels = 0;
+    else if (levels > size_Q_ - 1) levels = size_Q_ - 1;
+    return levels;
+}
+
+void Engine::bfv_multiply(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cudaStream_t st, int drop) {
     if (scheme_ != Scheme::bfv) throw std::invalid_argument("unsupported scheme");
     if (mul_tech_ == 1) bfv_multiply_behz(l, out3, ct1, ct2, st);
     else if (mul_tech_ == 2) bfv_multiply_hps(l, out3, ct1, ct2, st);
-    else throw std::invalid_argument("unsupported scheme: mul_tech hps_overq / hps_overq_leveled are not built");
+    else if (mul_tech_ == 3) bfv_multiply_hps_overq(l, out3, ct1, ct2, 0, st);
+    else bfv_multiply_hps_overq(l, out3, ct1, ct2, drop, st);   // hps_overq_leveled: the caller supplies the levels
 }
 
 // multiply_inplace + relinearize_inplace (reference src/evaluate.cu:345-397,451-548,819-1026,1342-1374)
 void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st) {
     if (scheme_ == Scheme::bfv) {
         u64 *d = ws_.tmp.p;
-        bfv_multiply(l, d, ct1, ct2, st);
-        keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
+        const int drop = mul_tech_ == 4 ? leveled_drop_ : 0;   // hps_overq_leveled: set by multiply_relin_leveled
+        if (drop) {   // bfv_mul_relin_hps with levels dropped (evaluate.cu:819-1026): c2 stays at Ql and is switched there
+            bfv_multiply_hps_overq(l, d, ct1, ct2, drop, st, true);
+            keyswitch_leveled(d, d + (size_t) 2 * l * n_, rlk, drop, true, st);
+        } else {
+            bfv_multiply(l, d, ct1, ct2, st);
+            keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
+        }
         PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
         return;
     }

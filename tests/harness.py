@@ -60,6 +60,9 @@ def oracle():
         o.orc_multiply_relin.argtypes = [vp, ctypes.c_int, u64p, u64p, u64p, u64p]
         o.orc_hps_aux.argtypes = [vp, u64p, i32p]
         o.orc_bfv_multiply_hps.argtypes = [vp, u64p, u64p, u64p]
+        o.orc_bfv_multiply_hps_overq.argtypes = [vp, u64p, u64p, u64p, ctypes.c_int]
+        o.orc_bfv_keyswitch_leveled.argtypes = [vp, u64p, u64p, u64p, ctypes.c_int, ctypes.c_int]
+        o.orc_bfv_multiply_relin_hps_overq.argtypes = [vp, u64p, u64p, u64p, u64p, ctypes.c_int]
         o.orc_bfv_multiply_relin_hps.argtypes = [vp, u64p, u64p, u64p, u64p]
         o.orc_behz_aux.argtypes = [vp, u64p, i32p]
         o.orc_bfv_multiply_behz.argtypes = [vp, u64p, u64p, u64p]
@@ -117,6 +120,9 @@ def reference():
         r.ref_ntt.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
         r.ref_multiply_relin.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
         r.ref_multiply.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
+        if hasattr(r, "ref_multiply_deg"):
+            r.ref_multiply_deg.argtypes = [vp, ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
+                                           u64p]
         if hasattr(r, "ref_nwt_1d"):
             r.ref_nwt_1d.argtypes = [ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int, u64p, ctypes.c_int]
         if hasattr(r, "ref_multiply_sizes"):

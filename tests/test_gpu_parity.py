@@ -499,11 +499,6 @@ def test_bgv_bfv_keyswitch_and_modswitch(scheme, cfg):
         ca, cb = pf.PhantomCiphertext.from_host(ctx, a), pf.PhantomCiphertext.from_host(ctx, b)
         pf.multiply_and_relin_inplace(ctx, ca, cb, key)
         assert np.array_equal(ca.to_host(), want)
-    else:   # BFV: the HPS-over-Q variants are not built and say so
-        octx = make_bfv_context(ps, mul_tech=pf.mul_tech_type.hps_overq)
-        a = pf.PhantomCiphertext.from_host(octx, ct, is_ntt_form=False)
-        with pytest.raises(ValueError, match="unsupported scheme"):
-            pf.multiply_and_relin_inplace(octx, a, a.clone(), pf.PhantomRelinKey(octx, list(key_h)))
 
 
 # ---------------------------------------------------------------------------------------------------------
@@ -594,13 +589,74 @@ def test_bfv_hps_multiply(cfg):
         pf.multiply_inplace(ctx, low, low.clone())
 
 
-@pytest.mark.parametrize("mul_tech", [1, 2])
+@pytest.mark.parametrize("cfg", [dict(n=4096, l=3, alpha=1, qbits=36, pbits=42), dict(n=4096, l=5, alpha=2, qbits=44, pbits=60),
+                                 dict(n=8192, l=4, alpha=1, qbits=50, pbits=60)])
+def test_bfv_hps_overq_multiply(cfg):
+    """mul_tech hps_overq and hps_overq_leveled (evaluate.cu:647-801,819-1026; eval_key_switch.cu:109-181): engine vs
+    oracle, every number of dropped levels the parameter set allows, multiply / multiply+relin / leveled key switch."""
+    ps = H.params_small(scheme=2, t=65537, **cfg)
+    o, oc = H.oracle(), ps.octx()
+    l, n = ps.limbs(), ps.n
+    key_h = H.switch_key(ps, 100)
+    a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    # hps_overq through the reference-shaped calls
+    ctx = make_bfv_context(ps, mul_tech=pf.mul_tech_type.hps_overq)
+    key = pf.PhantomRelinKey(ctx, list(key_h))
+    want3 = np.zeros((3, l, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_hps_overq(oc, P(a), P(b), P(want3), 0) == 0
+    ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+    cb = pf.PhantomCiphertext.from_host(ctx, b, is_ntt_form=False)
+    pf.multiply_inplace(ctx, ca, cb)
+    assert np.array_equal(ca.to_host(), want3), "bfv_multiply_hps, hps_overq"
+    want = np.zeros((2, l, n), dtype=np.uint64)
+    assert o.orc_bfv_multiply_relin_hps_overq(oc, P(a), P(b), P(key_h), P(want), 0) == 0
+    pf.relinearize_inplace(ctx, ca, key)
+    assert np.array_equal(ca.to_host(), want), "relinearize after hps_overq"
+    ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+    pf.multiply_and_relin_inplace(ctx, ca, cb, key)
+    assert np.array_equal(ca.to_host(), want), "bfv_mul_relin_hps, hps_overq"
+    for vec in H.edge_vectors(ps, list(range(l)))[:3]:
+        e = np.stack([vec, vec])
+        assert o.orc_bfv_multiply_hps_overq(oc, P(e), P(a), P(want3), 0) == 0
+        ce = pf.PhantomCiphertext.from_host(ctx, e, is_ntt_form=False)
+        pf.multiply_inplace(ctx, ce, pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False))
+        assert np.array_equal(ce.to_host(), want3), "hps_overq edge vector"
+    # hps_overq_leveled: the arithmetic for every admissible number of dropped levels
+    lctx = make_bfv_context(ps, mul_tech=pf.mul_tech_type.hps_overq_leveled)
+    lkey = pf.PhantomRelinKey(lctx, list(key_h))
+    da, db = dev(a), dev(b)
+    for drop in range(0, l):
+        assert o.orc_bfv_multiply_hps_overq(oc, P(a), P(b), P(want3), drop) == 0
+        d3 = torch.zeros((3, l, n), dtype=torch.int64, device="cuda")
+        pf.check(pf.lib.pfhe_multiply_leveled(lctx._h, da.data_ptr(), db.data_ptr(), d3.data_ptr(), drop, st))
+        assert np.array_equal(host(d3), want3), f"leveled multiply, {drop} levels dropped"
+        assert o.orc_bfv_multiply_relin_hps_overq(oc, P(a), P(b), P(key_h), P(want), drop) == 0
+        d2 = torch.zeros((2, l, n), dtype=torch.int64, device="cuda")
+        pf.check(pf.lib.pfhe_multiply_and_relin_leveled(lctx._h, da.data_ptr(), db.data_ptr(), d2.data_ptr(),
+                                                        lkey.public_keys_ptr(), drop, st))
+        assert np.array_equal(host(d2), want), f"leveled multiply+relin, {drop} levels dropped"
+        # keyswitch_inplace at a dropped level on its own (what relinearize_inplace does after a leveled multiply)
+        ks = want3[:2].copy()
+        assert o.orc_bfv_keyswitch_leveled(oc, P(ks), P(want3[2].copy()), P(key_h), drop, 0) == 0
+        pf.check(pf.lib.pfhe_keyswitch_leveled_inplace(lctx._h, d3.data_ptr(), d3[2].data_ptr(), lkey.public_keys_ptr(),
+                                                       drop, st))
+        assert np.array_equal(host(d3)[:2], ks), f"leveled key switch, {drop} levels dropped"
+    with pytest.raises(Exception):
+        pf.check(pf.lib.pfhe_multiply_leveled(lctx._h, da.data_ptr(), db.data_ptr(), d3.data_ptr(), l, st))
+    with pytest.raises(Exception):   # the leveled entry points belong to mul_tech hps_overq_leveled
+        pf.check(pf.lib.pfhe_multiply_leveled(ctx._h, da.data_ptr(), db.data_ptr(), d3.data_ptr(), 0, st))
+
+
+@pytest.mark.parametrize("mul_tech", [1, 2, 3, 4])
 def test_bfv_multiply_against_unmodified_reference(mul_tech):
     """BFV HMult+Relin at the bfv_bench.cu N=2^14 parameter sets: reference kernels vs engine vs oracle."""
     r = H.reference()
     if r is None:
         pytest.skip("oracle/_ref/libphantom_ref.so was not built")
     orc_mul = H.oracle().orc_bfv_multiply_behz if mul_tech == 1 else H.oracle().orc_bfv_multiply_hps
+    if mul_tech >= 3:
+        orc_mul = lambda c, x, y, out: H.oracle().orc_bfv_multiply_hps_overq(c, x, y, out, 0)
     for which in (0, 2):
         ps = H.params_bfv_bench(which)
         h = r.ref_create(2, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, mul_tech, None, 0, 1.0, 1)
@@ -630,6 +686,28 @@ def test_bfv_multiply_against_unmodified_reference(mul_tech):
             ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
             pf.multiply_and_relin_inplace(ctx, ca, cb, rlk)
             assert np.array_equal(ca.to_host(), want), "BFV HMult+Relin vs reference"
+            if mul_tech == 4 and hasattr(r, "ref_multiply_deg"):
+                # ciphertexts deep enough for FindLevelsToDrop to drop levels: the same decision and the same words
+                drops = set()
+                for deg in (2, 4, 6):
+                    lv = ctypes.c_int()
+                    pf.check(pf.lib.pfhe_find_levels_to_drop(ctx._h, deg - 1, 0, 0, ctypes.byref(lv)))
+                    drops.add(lv.value)
+                    for relin in (0, 1, 2):
+                        wantd = np.zeros((2 if relin else 3, l, n), dtype=np.uint64)
+                        assert r.ref_multiply_deg(h, 1, P(a), P(b), deg, deg - 1, relin, P(wantd)) == 0, r.ref_last_error()
+                        ca = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+                        cb = pf.PhantomCiphertext.from_host(ctx, b, is_ntt_form=False)
+                        ca.noise_scale_deg, cb.noise_scale_deg = deg, deg - 1
+                        if relin == 2:
+                            pf.multiply_and_relin_inplace(ctx, ca, cb, rlk)
+                        else:
+                            pf.multiply_inplace(ctx, ca, cb)
+                            if relin:
+                                pf.relinearize_inplace(ctx, ca, rlk)
+                        assert ca.noise_scale_deg == deg + 1
+                        assert np.array_equal(ca.to_host(), wantd), f"leveled BFV, degree {deg}, relin {relin}, drop {lv.value}"
+                assert max(drops) > 0, "the chosen degrees never dropped a level"
         finally:
             r.ref_destroy(h)
 

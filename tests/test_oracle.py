@@ -270,13 +270,16 @@ def test_live_against_reference_host_code():
                 assert case["qhat_mod_p"][j * len(ib) + i] == want
 
 
-@pytest.mark.parametrize("tech", ["behz", "hps"])
+@pytest.mark.parametrize("tech", ["behz", "hps", "hps_overq", "hps_overq_drop1"])
 def test_bfv_multiply_decrypts_to_the_plaintext_product(tech):
     """BEHZ / HPS restatements (oracle/fhe_oracle.c; evaluate.cu:451-548,647-801): noiseless-key sanity. Trivial
     encryptions (Delta*m + e, 0) must multiply to a ciphertext whose c0 decodes to m1*m2 mod (X^n+1, t) and whose
     c1, c2 are 0."""
     o = H.oracle()
     mul = o.orc_bfv_multiply_behz if tech == "behz" else o.orc_bfv_multiply_hps
+    if tech.startswith("hps_overq"):   # evaluate.cu:647-801 with mul_tech hps_overq / the leveled arithmetic
+        drop = 1 if tech.endswith("drop1") else 0
+        mul = lambda c, a, b, out: o.orc_bfv_multiply_hps_overq(c, a, b, out, drop)
     t = 65537
     ps = H.ParamSet("bfv_sem", 64, [40, 40, 40, 50], 1, scheme=2, t=t)
     n, lq = ps.n, ps.size_Q
@@ -318,6 +321,10 @@ def test_bfv_multiply_decrypts_to_the_plaintext_product(tech):
         dec.append(((t * x + Q // 2) // Q) % t)
     assert dec == exp
     assert not out[1].any() and not out[2].any()
+    if tech.startswith("hps_overq"):
+        if tech.endswith("drop1"):   # ExpandCRTBasis_Ql_Q leaves the dropped limb at zero (rns.cu:1810-1822)
+            assert not out[0, lq - 1].any() and out[0, :lq - 1].any()
+        return
     if tech == "hps":   # R: size_Q + 1 NTT primes just below min(q_i) (rns.cu:687-694)
         R = np.zeros(72, dtype=np.uint64)
         nr = ctypes.c_int()
