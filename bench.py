@@ -325,16 +325,28 @@ def main():
         alg_bytes = limbs_ntt * 16 * n
         peak, how = measured_peaks()
         achieved = alg_bytes / (ntt_us * 1e-6) / 1e9
-        traffic = None
+        traffic, issue = None, None
         tpath = os.path.join(ROOT, "profiles", "ntt_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
-                traffic = json.load(f).get("dram_bytes_total")
+                prof = json.load(f)
+            traffic = prof.get("dram_bytes_total")
+            if prof.get("warp_instructions"):
+                # what the kernel pair is actually bound by: warp-instruction issue.  Peak = one warp
+                # instruction per scheduler per clock = SMs x 4 x SM clock; FP64 / IMAD instructions hold the dispatch port
+                # for two clocks, so a mix dominated by them tops out near half of that.
+                prop = torch.cuda.get_device_properties(local_rank)
+                peak_inst = prop.multi_processor_count * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None
+                ach_inst = prof["warp_instructions"] / (ntt_us * 1e-6)
+                issue = {"warp_inst_per_launch": prof["warp_instructions"], "achieved_ginst_s": ach_inst / 1e9,
+                         "peak_ginst_s": peak_inst / 1e9 if peak_inst else None,
+                         "frac": ach_inst / peak_inst if peak_inst else None}
         roof = {"kernel": "forward negacyclic NTT (k_fwd_cols + k_fwd_rows), 64 limb-NTTs of N=2^16",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "peak_source": how, "traffic": traffic, "algorithmic_bytes": alg_bytes,
-                "launch_us": ntt_us, "limb_ntt_per_s": limbs_ntt / (ntt_us * 1e-6),
-                "note": "not HBM-bound: 64-bit modular butterflies are issue/latency bound on sm_100a (DESIGN.md 4.1, profiles/)"}
+                "launch_us": ntt_us, "limb_ntt_per_s": limbs_ntt / (ntt_us * 1e-6), "issue": issue,
+                "note": "not HBM-bound: 64-bit modular butterflies are bound by warp-instruction issue on sm_100a "
+                        "(FP64 and IMAD share the dispatch port, 2 clocks each; DESIGN.md 4.1, profiles/r1b_*)"}
         if not args.no_cpu_baseline:
             cb = cpu_baseline(ps, a, b, rlk_h)
 

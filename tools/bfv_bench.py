@@ -1,4 +1,4 @@
-"""BFV HMult+Relin (BEHZ) at the bfv_bench.cu N=2^14 parameter sets: engine vs unmodified reference, device timed."""
+"""BFV HMult+Relin (BEHZ, HPS, HPS over Q) at the bfv_bench.cu N=2^14 parameter sets: engine vs unmodified reference, device timed."""
 import ctypes
 import os
 import sys
@@ -15,7 +15,7 @@ from harness import P  # noqa: E402
 
 reps = int(sys.argv[1]) if len(sys.argv) > 1 else 200
 r = H.reference()
-for which, tech in [(w, m) for m in (1, 2) for w in (0, 1, 2)]:
+for which, tech in [(w, m) for m in (1, 2, 3) for w in (0, 1, 2)]:
     ps = H.params_bfv_bench(which)
     parms = pf.EncryptionParameters(pf.scheme_type.bfv)
     parms.set_poly_modulus_degree(ps.n)
