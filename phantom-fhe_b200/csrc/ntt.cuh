@@ -402,9 +402,13 @@ __device__ __forceinline__ size_t gl_index(int e, int c, int tile) {
 // before the first use (memory-level parallelism; a per-element callback with data-dependent work in between
 // serialised the loads -- profiles/r1_hmult_full.md, long_scoreboard).  per_elem() adapts a simple lambda.
 // ----------------------------------------------------------------------------------------------------
+// RUN = length of the runs of consecutive coefficient indices inside idx[] known at compile time: 1 in the column
+// passes (strided), 2^R >= 4 at the outer end of a row pass, where a thread owns whole contiguous groups and the
+// functors use 16-byte accesses (idx[k] is then even for even k and idx[k + 1] = idx[k] + 1).
 template<class T, class F>
 struct PerElemLoad {
     F f;
+    template<int RUN>
     __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], T (&x)[NTT_EPT]) const {
 #pragma unroll
         for (int k = 0; k < NTT_EPT; k++) x[k] = f(idx[k]);
@@ -413,11 +417,115 @@ struct PerElemLoad {
 template<class T, class F>
 struct PerElemStore {
     F f;
+    template<int RUN>
     __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const T (&x)[NTT_EPT]) const {
 #pragma unroll
         for (int k = 0; k < NTT_EPT; k++) f(idx[k], x[k]);
     }
 };
+__device__ __forceinline__ ulonglong2 ldv2(const u64 *p) { return *reinterpret_cast<const ulonglong2 *>(p); }
+__device__ __forceinline__ void stv2(u64 *p, u64 a, u64 b) { *reinterpret_cast<ulonglong2 *>(p) = make_ulonglong2(a, b); }
+// 256-bit global accesses (sm_100: LDG/STG.E.ENL2.256): one instruction per run of four coefficients, and -- what
+// matters for the stores -- every 32-byte sector is written whole by one instruction (two 16-byte stores per sector
+// from different instructions measured 3.5 % slower than staging the tile through shared memory)
+struct u64x4 {
+    u64 v[4];
+};
+__device__ __forceinline__ u64x4 ldv4(const u64 *p) {
+    u64x4 r;
+    asm volatile("ld.global.v4.u64 {%0,%1,%2,%3}, [%4];" : "=l"(r.v[0]), "=l"(r.v[1]), "=l"(r.v[2]), "=l"(r.v[3]) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ void stv4(u64 *p, u64 a, u64 b, u64 c, u64 d) {
+    asm volatile("st.global.v4.u64 [%0], {%1,%2,%3,%4};" ::"l"(p), "l"(a), "l"(b), "l"(c), "l"(d) : "memory");
+}
+// run of `RUN` consecutive words starting at p into / out of x[0..RUN)
+template<int RUN>
+__device__ __forceinline__ void ld_run(const u64 *p, u64 (&x)[RUN]) {
+    if constexpr (RUN % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < RUN; k += 4) {
+            const u64x4 v = ldv4(p + k);
+            x[k] = v.v[0], x[k + 1] = v.v[1], x[k + 2] = v.v[2], x[k + 3] = v.v[3];
+        }
+    } else {
+#pragma unroll
+        for (int k = 0; k < RUN; k += 2) {
+            const ulonglong2 v = ldv2(p + k);
+            x[k] = v.x, x[k + 1] = v.y;
+        }
+    }
+}
+template<int RUN>
+__device__ __forceinline__ void st_run(u64 *p, const u64 (&x)[RUN]) {
+    if constexpr (RUN % 4 == 0) {
+#pragma unroll
+        for (int k = 0; k < RUN; k += 4) stv4(p + k, x[k], x[k + 1], x[k + 2], x[k + 3]);
+    } else {
+#pragma unroll
+        for (int k = 0; k < RUN; k += 2) stv2(p + k, x[k], x[k + 1]);
+    }
+}
+// all NTT_EPT words of a thread: NTT_EPT / RUN runs starting at idx[0], idx[RUN], ...
+template<int RUN>
+__device__ __forceinline__ void ld_runs(const u64 *base, const size_t (&idx)[NTT_EPT], u64 (&w)[NTT_EPT]) {
+#pragma unroll
+    for (int g = 0; g < NTT_EPT; g += RUN) {
+        u64 t[RUN];
+        ld_run<RUN>(base + idx[g], t);
+#pragma unroll
+        for (int k = 0; k < RUN; k++) w[g + k] = t[k];
+    }
+}
+template<int RUN>
+__device__ __forceinline__ void st_runs(u64 *base, const size_t (&idx)[NTT_EPT], const u64 (&w)[NTT_EPT]) {
+#pragma unroll
+    for (int g = 0; g < NTT_EPT; g += RUN) {
+        u64 t[RUN];
+#pragma unroll
+        for (int k = 0; k < RUN; k++) t[k] = w[g + k];
+        st_run<RUN>(base + idx[g], t);
+    }
+}
+// plain word source / sink with a per-element transform, vectorised over runs
+template<class T, class F>
+struct VecLoad {
+    const u64 *src;
+    F f;   // u64 -> T
+    template<int RUN>
+    __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], T (&x)[NTT_EPT]) const {
+        if constexpr (RUN >= 2) {
+            u64 w[NTT_EPT];
+            ld_runs<RUN>(src, idx, w);
+#pragma unroll
+            for (int k = 0; k < NTT_EPT; k++) x[k] = f(w[k]);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NTT_EPT; k++) x[k] = f(src[idx[k]]);
+        }
+    }
+};
+template<class T, class F>
+struct VecStore {
+    u64 *dst;
+    F f;   // T -> u64
+    template<int RUN>
+    __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const T (&x)[NTT_EPT]) const {
+        if constexpr (RUN >= 2) {
+            u64 w[NTT_EPT];
+#pragma unroll
+            for (int k = 0; k < NTT_EPT; k++) w[k] = f(x[k]);
+            st_runs<RUN>(dst, idx, w);
+        } else {
+#pragma unroll
+            for (int k = 0; k < NTT_EPT; k++) dst[idx[k]] = f(x[k]);
+        }
+    }
+};
+template<class T, class F>
+__device__ __forceinline__ VecLoad<T, F> vec_load(const u64 *src, F f) { return VecLoad<T, F>{src, f}; }
+template<class T, class F>
+__device__ __forceinline__ VecStore<T, F> vec_store(u64 *dst, F f) { return VecStore<T, F>{dst, f}; }
 template<class T, class F>
 __device__ __forceinline__ PerElemLoad<T, F> per_elem_load(F f) { return PerElemLoad<T, F>{f}; }
 template<class T, class F>
@@ -467,7 +575,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++)
                     gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
-            load.gather(gi, x);
+            load.template gather<1>(gi, x);
 #ifdef PFHE_TIMELINE
 #pragma unroll
             for (int k = 0; k < NTT_EPT; k++) asm volatile("" ::"l"(A::raw(x[k])));   // wait for the loads here
@@ -486,8 +594,10 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
         for (int k = 0; k < NTT_EPT; k++) asm volatile("" ::"l"(A::raw(x[k])));
         TL_MARK(4 + 2 * RI)
 #endif
-        // scatter
-        constexpr bool DIRECT_OUT = (RI == NR - 1) && !ROWS;
+        // scatter.  The last round leaves the pass straight from the registers: in a column pass the stores are the
+        // strided 64-byte segments of the tile, in a row pass a thread owns whole runs of 2^R consecutive coefficients
+        // (LAM = 0) and a warp covers one contiguous stretch of a row, so no staging through shared memory is needed
+        constexpr bool DIRECT_OUT = (RI == NR - 1);
         if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
         if constexpr (DIRECT_OUT) {
             size_t gi[NTT_EPT];
@@ -496,7 +606,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++)
                     gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
-            store.scatter(gi, x);
+            store.template scatter<(ROWS ? (1 << M::R) : 1)>(gi, x);
         } else {
 #pragma unroll
             for (int g = 0; g < M::G; g++)
@@ -512,18 +622,6 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
     if constexpr (NR > 2) run_round(std::integral_constant<int, 2>{});
     if constexpr (NR > 3) run_round(std::integral_constant<int, 3>{});
 
-    if constexpr (ROWS) {
-        // the tile is contiguous in global memory: flat, fully coalesced copy-out
-        const size_t base = ((size_t) cx.tile << NTT_LOG_TILE) + tid;
-        const int st = skew(tid);   // i * NTT_THREADS only touches bits >= 8: the swizzle term is per thread
-        size_t gi[NTT_EPT];
-#pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) {
-            gi[i] = base + i * NTT_THREADS;
-            x[i] = A::from_raw(smem[st + i * NTT_THREADS]);
-        }
-        store.scatter(gi, x);
-    }
     TL_MARK(12)
 }
 
@@ -534,19 +632,6 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
     typename A::T x[NTT_EPT];
     const int tid = threadIdx.x;
 
-    if constexpr (ROWS) {
-        // flat coalesced copy-in, the first inverse round then reads its contiguous elements from smem
-        const size_t base = ((size_t) cx.tile << NTT_LOG_TILE) + tid;
-        const int st = skew(tid);
-        size_t gi[NTT_EPT];
-#pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) gi[i] = base + i * NTT_THREADS;
-        load.gather(gi, x);
-#pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) smem[st + i * NTT_THREADS] = A::raw(x[i]);
-        __syncthreads();
-    }
-
     auto run_round = [&](auto ri_tag) {
         constexpr int RI = decltype(ri_tag)::value;
         using M = RoundMap<P, RI, ROWS>;
@@ -556,7 +641,7 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
             M::decode(M::mu(tid, g), hi[g], lo[g], c[g]);
             s0[g] = M::sidx0(hi[g], lo[g], c[g]);
         }
-        constexpr bool DIRECT_IN = (RI == NR - 1) && !ROWS;
+        constexpr bool DIRECT_IN = (RI == NR - 1);   // rows: runs of 2^R consecutive coefficients per thread
         if constexpr (DIRECT_IN) {
             size_t gi[NTT_EPT];
 #pragma unroll
@@ -564,7 +649,7 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++)
                     gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
-            load.gather(gi, x);
+            load.template gather<(ROWS ? (1 << M::R) : 1)>(gi, x);
         } else {
 #pragma unroll
             for (int g = 0; g < M::G; g++)
@@ -581,7 +666,7 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++)
                     gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
-            store.scatter(gi, x);
+            store.template scatter<1>(gi, x);
         } else {
             if constexpr (!DIRECT_IN) __syncthreads();
 #pragma unroll

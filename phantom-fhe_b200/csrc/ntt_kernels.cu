@@ -42,7 +42,25 @@ constexpr size_t NTT_SMEM_ROWS = NTT_TILE * sizeof(u64);
     pdl_launch_dependents();                                                                              \
     pdl_wait();
 
-// epilogue of the fused forward row pass, all operand loads of a thread's eight outputs issued up front
+// epilogue of the fused forward row pass, all operand loads of a thread's eight outputs issued up front (16-byte
+// loads: the row pass hands over runs of consecutive coefficients).  out = (sub - NTT) * k (+ add) mod q.
+// FP64 limbs stay in FP64: v = sub - x (x is the lazy transform value), one error-free product by the constant, the
+// addend, one reduction -- the same canonical residue as the integer form at half the instructions.
+template<class A>
+__device__ __forceinline__ u64 epi_one(u64 s, typename A::T x, bool has_add, u64 a, Tw k, double kd, double ki,
+                                       const typename A::Consts &c, u64 q) {
+    if constexpr (std::is_same<A, FpArith>::value) {
+        double r = fp::mulmod_c(fp::from_u64(s) - x, kd, ki, c.q);
+        if (has_add) r = fp::reduce(r + fp::from_u64(a), c.q, c.qinv);
+        return fp::canon(r, c.q);
+    } else {
+        const u64 t = A::canon_fwd(x, c);
+        u64 r = mul_shoup(s + q - t, k, q);
+        if (has_add) r = add_mod(r, a, q);
+        return r;
+    }
+}
+
 template<class A>
 struct EpiStore {
     const u64 *sub, *add;
@@ -50,21 +68,17 @@ struct EpiStore {
     Tw k;
     typename A::Consts c;
     u64 q;
+    template<int RUN>
     __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const typename A::T (&x)[NTT_EPT]) const {
-        u64 s[NTT_EPT], a[NTT_EPT];
+        static_assert(RUN >= 2, "the epilogue belongs to the row pass");
+        u64 s[NTT_EPT], a[NTT_EPT], r[NTT_EPT];
+        ld_runs<RUN>(sub, idx, s);
+        if (add) ld_runs<RUN>(add, idx, a);
+        double kd = 0, ki = 0;
+        if constexpr (std::is_same<A, FpArith>::value) kd = (double) k.x, ki = kd * c.qinv;
 #pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) s[i] = sub[idx[i]];
-        if (add) {
-#pragma unroll
-            for (int i = 0; i < NTT_EPT; i++) a[i] = add[idx[i]];
-        }
-#pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) {
-            const u64 t = A::canon_fwd(x[i], c);
-            u64 r = mul_shoup(s[i] + q - t, k, q);
-            if (add) r = add_mod(r, a[i], q);
-            out[idx[i]] = r;
-        }
+        for (int i = 0; i < NTT_EPT; i++) r[i] = epi_one<A>(s[i], x[i], add != nullptr, add ? a[i] : 0, k, kd, ki, c, q);
+        st_runs<RUN>(out, idx, r);
     }
 };
 
@@ -95,7 +109,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows(u64 *d
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
         forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
                 smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(d[i]); }),
-                per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::canon_fwd(v, c); }));
+                vec_store<typename A::T>(d, [&](typename A::T v) { return A::canon_fwd(v, c); }));
     })
 }
 
@@ -130,7 +144,7 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_rows(u64 *d
         const typename A::Consts c = A::consts(q);
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
         inverse_pass<A, ntt_p2(LOGN), true, LOGN, false>(
-                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::load(s[i], c); }),
+                smem, cx, vec_load<typename A::T>(s, [&](u64 v) { return A::load(v, c); }),
                 per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::raw(v); }));
     })
 }
@@ -170,10 +184,12 @@ struct MulLoad {
     typename A::Consts c;
     BarG bg;
     u64 q;
+    template<int RUN>
     __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], typename A::T (&x)[NTT_EPT]) const {
+        static_assert(RUN >= 2, "the product load belongs to the row pass");
         u64 u[NTT_EPT], v[NTT_EPT];
-#pragma unroll
-        for (int i = 0; i < NTT_EPT; i++) u[i] = a1[idx[i]], v[i] = b1[idx[i]];
+        ld_runs<RUN>(a1, idx, u);
+        ld_runs<RUN>(b1, idx, v);
 #pragma unroll
         for (int i = 0; i < NTT_EPT; i++) x[i] = mul_in<A>(u[i], v[i], c, bg, q);
     }
@@ -244,6 +260,7 @@ struct BconvGatherFp {
     int ni;
     unsigned big;
     double q;
+    template<int RUN>
     __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], double (&x)[NTT_EPT]) const {
 #if PFHE_BCONV_DUAL
         constexpr int HB = NTT_EPT / 2;   // two half-batches: accumulators of four elements live at a time
@@ -326,6 +343,7 @@ struct BconvGatherInt {
     int ni;
     BarG bg;
     Modulus m;
+    template<int RUN>
     __device__ __forceinline__ void gather(const size_t (&idx)[NTT_EPT], u64 (&x)[NTT_EPT]) const {
         Acc128 acc[NTT_EPT];
 #pragma unroll
@@ -400,41 +418,59 @@ struct EpiTensorStore {
     EpiTensorPtrs e;
     typename A::Consts c;
     u64 q;
-    __device__ __forceinline__ u64 dk0(u64 x0, u64 y0) const {
-        if constexpr (std::is_same<A, FpArith>::value)
-            return fp::canon(fp::mulmod_v(fp::from_u64(x0), fp::from_u64(y0), c.q, c.qinv), c.q);
-        else return mul_mod_g(x0, y0, e.bg, e.m);
-    }
-    __device__ __forceinline__ u64 dk1(u64 x0, u64 x1, u64 y0, u64 y1) const {
+    // one output: (sub - NTT) * k + d_k with d_0 = x0 y0, d_1 = x0 y1 + x1 y0.  FP64 limbs: everything stays in FP64 (the
+    // lazy transform value, the product by the constant, the tensor terms) and is reduced once
+    __device__ __forceinline__ u64 one(u64 s, typename A::T xv, u64 x0, u64 y0, u64 x1, u64 y1, double kd, double ki) const {
         if constexpr (std::is_same<A, FpArith>::value) {
-            const double s = fp::mulmod_v(fp::from_u64(x0), fp::from_u64(y1), c.q, c.qinv) +
-                             fp::mulmod_v(fp::from_u64(x1), fp::from_u64(y0), c.q, c.qinv);
-            return fp::canon(fp::reduce(s, c.q, c.qinv), c.q);
+            double r = fp::mulmod_c(fp::from_u64(s) - xv, kd, ki, c.q);
+            const double a0 = fp::from_u64(x0), b0 = fp::from_u64(y0);
+            if (e.kpoly == 0) {
+                r += fp::mulmod_v(a0, b0, c.q, c.qinv);
+            } else {
+                r += fp::mulmod_v(a0, fp::from_u64(y1), c.q, c.qinv);
+                r += fp::mulmod_v(fp::from_u64(x1), b0, c.q, c.qinv);
+            }
+            return fp::canon(fp::reduce(r, c.q, c.qinv), c.q);
         } else {
-            Acc128 acc{0, 0};
-            acc.mac(x0, y1);
-            acc.mac(x1, y0);
-            return barrett_g(acc.lo, acc.hi, e.bg, e.m);
+            const u64 t = A::canon_fwd(xv, c);
+            const u64 r = mul_shoup(s + q - t, e.k, q);
+            u64 dk;
+            if (e.kpoly == 0) {
+                dk = mul_mod_g(x0, y0, e.bg, e.m);
+            } else {
+                Acc128 acc{0, 0};
+                acc.mac(x0, y1);
+                acc.mac(x1, y0);
+                dk = barrett_g(acc.lo, acc.hi, e.bg, e.m);
+            }
+            return add_mod(r, dk, q);
         }
     }
-    // two half-batches of four outputs: all operand loads of a half are issued before the arithmetic
+    // two half-batches of four outputs: all operand loads of a half (16-byte, runs of consecutive coefficients) are
+    // issued before the arithmetic
+    template<int RUN>
     __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const typename A::T (&x)[NTT_EPT]) const {
+        static_assert(RUN >= 2, "the epilogue belongs to the row pass");
+        double kd = 0, ki = 0;
+        if constexpr (std::is_same<A, FpArith>::value) kd = (double) e.k.x, ki = kd * c.qinv;
+        constexpr int HB = RUN >= 4 ? 4 : 2;   // outputs per half-batch = one run
 #pragma unroll
-        for (int h = 0; h < NTT_EPT; h += 4) {
-            u64 s[4], x0[4], y0[4], x1[4], y1[4];
-#pragma unroll
-            for (int i = 0; i < 4; i++) s[i] = e.sub[idx[h + i]], x0[i] = e.a0[idx[h + i]], y0[i] = e.b0[idx[h + i]];
+        for (int h = 0; h < NTT_EPT; h += HB) {
+            u64 s[HB], x0[HB], y0[HB], x1[HB], y1[HB], r[HB];
+            const size_t j = idx[h];
+            ld_run<HB>(e.sub + j, s);
+            ld_run<HB>(e.a0 + j, x0);
+            ld_run<HB>(e.b0 + j, y0);
             if (e.kpoly != 0) {
+                ld_run<HB>(e.a1 + j, x1);
+                ld_run<HB>(e.b1 + j, y1);
+            } else {
 #pragma unroll
-                for (int i = 0; i < 4; i++) x1[i] = e.a1[idx[h + i]], y1[i] = e.b1[idx[h + i]];
+                for (int i = 0; i < HB; i++) x1[i] = y1[i] = 0;
             }
 #pragma unroll
-            for (int i = 0; i < 4; i++) {
-                const u64 t = A::canon_fwd(x[h + i], c);
-                const u64 r = mul_shoup(s[i] + q - t, e.k, q);
-                const u64 dk = e.kpoly == 0 ? dk0(x0[i], y0[i]) : dk1(x0[i], x1[i], y0[i], y1[i]);
-                e.out[idx[h + i]] = add_mod(r, dk, q);
-            }
+            for (int i = 0; i < HB; i++) r[i] = one(s[i], x[h + i], x0[i], y0[i], x1[i], y1[i], kd, ki);
+            st_run<HB>(e.out + j, r);
         }
     }
 };
@@ -526,14 +562,23 @@ static void inv_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList 
         default: return cudaErrorInvalidValue;                                                            \
     }
 
+// the row passes move runs of four coefficients with 256-bit accesses: every polynomial buffer must be 32-byte aligned
+// (limb offsets are multiples of 8 N bytes, so this is a condition on the base pointers only)
+template<class... Ptr>
+static bool aligned32(Ptr... p) {
+    return ((... | reinterpret_cast<uintptr_t>(p)) & 31u) == 0;
+}
+
 cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) {
     if (ll.count == 0) return cudaSuccess;
+    if (!aligned32(dst, src)) return cudaErrorMisalignedAddress;
     PFHE_DISPATCH_LOGN(fwd_impl, p, dst, src, ll, st)
     return cudaGetLastError();
 }
 
 cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st) {
     if (ll.count == 0) return cudaSuccess;
+    if (!aligned32(data, ea.sub_base, ea.out_base, ea.add_base)) return cudaErrorMisalignedAddress;
     PFHE_DISPATCH_LOGN(fwd_epi_impl, p, data, ll, ea, st)
     return cudaGetLastError();
 }
@@ -562,6 +607,7 @@ static void fwd_bconv_impl(const NttPlan &p, u64 *dst, const LimbList &ll, const
 cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, const BarG *bar0, const LimbList &ll,
                             const Tw *fin, int by_slot, cudaStream_t st) {
     if (ll.count == 0) return cudaSuccess;
+    if (!aligned32(dst, ts.a, ts.b)) return cudaErrorMisalignedAddress;
     PFHE_DISPATCH_LOGN(inv_mul_impl, p, dst, ts, bar0, ll, fin, by_slot, st)
     return cudaGetLastError();
 }
@@ -569,6 +615,9 @@ cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, con
 cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
                               const TensorSrc *ts, const BarG *bar1, cudaStream_t st, int phase) {
     if (ll.count == 0) return cudaSuccess;
+    if (!aligned32(dst, bl.in_base) || (ea && !aligned32(ea->sub_base, ea->out_base, ea->add_base)) ||
+        (ts && !aligned32(ts->a, ts->b)))
+        return cudaErrorMisalignedAddress;
     PFHE_DISPATCH_LOGN(fwd_bconv_impl, p, dst, ll, bl, ea, ts, bar1, st, phase)
     return cudaGetLastError();
 }
@@ -650,6 +699,7 @@ cudaError_t ntt_1d(bool inverse, u64 *inout, const u64 *tw, const u64 *tws, cons
 cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
                         cudaStream_t st) {
     if (ll.count == 0) return cudaSuccess;
+    if (!aligned32(dst, src)) return cudaErrorMisalignedAddress;
     PFHE_DISPATCH_LOGN(inv_impl, p, dst, src, ll, fin, by_slot, st)
     return cudaGetLastError();
 }
