@@ -78,6 +78,8 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
     {
         const char *ov = std::getenv("PFHE_OVERLAP");   // 0: keep the whole key switch on the caller's stream
         overlap_ = !(ov && ov[0] == '0');
+        const char *lz = std::getenv("PFHE_LAZY_T");   // 0: the fused key switch keeps its mod-up digits canonical
+        lazy_t_ = !(lz && lz[0] == '0');
         int dev = 0, sms = 148;
         cudaGetDevice(&dev);
         cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
@@ -642,7 +644,7 @@ void Engine::modup(int l, u64 *t_mod_up, const u64 *cks, u64 *t_cks, cudaStream_
 
 void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *evk, cudaStream_t st,
                         const u64 *own_c2, const TensorSrc *ts, const uint32_t *perm, bool accumulate, int j_begin,
-                        int j_count, int persist_ctas) const {
+                        int j_count, int persist_ctas, bool t_lazy) const {
     const Level &lv = level(l);
     if (j_count < 0) j_count = lv.m - j_begin;
     if (j_count == 0) return;
@@ -651,7 +653,7 @@ void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *e
     else if (ts) os = OwnSrc{nullptr, ts->a + (size_t) ts->l * n_, ts->b + (size_t) ts->l * n_, lv.alpha};
     const InnerProdArgs A{cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), bar(1, 0),
                           RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, perm,
-                          accumulate ? 1 : 0, n_, l, lv.m, size_Q_, size_QP_, lv.beta, j_begin, j_count};
+                          accumulate ? 1 : 0, t_lazy ? 1 : 0, n_, l, lv.m, size_Q_, size_QP_, lv.beta, j_begin, j_count};
     const unsigned tiles = (unsigned) (n_ / IP_TILE) * (unsigned) j_count;
     const dim3 grid(persist_ctas > 0 ? std::min((unsigned) persist_ctas, tiles) : tiles);
     const bool plain = !perm && !accumulate;
@@ -779,7 +781,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         ll.count = cnt;
         bl.xbits = kin + ceil_log2(ni);
         g_launches.fetch_add(2, std::memory_order_relaxed);
-        PFHE_CUDA(ntt_forward_bconv(plan_, t_mod_up, ll, bl, nullptr, nullptr, nullptr, st));
+        PFHE_CUDA(ntt_forward_bconv(plan_, t_mod_up, ll, bl, nullptr, nullptr, nullptr, st, lazy_t_ ? 3 : 0));
         d0 = d1;
     }
     // 3. inner product; the digit's own limbs are read from c2 (or formed as a1*b1).  Only the P limbs of cx feed
@@ -789,7 +791,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
     //    before the epilogue.
     const bool fork = overlap_;
     cudaStream_t sc = st;   // stream of the P-limb chain
-    inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, l, alpha);
+    inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, l, alpha, 0, lazy_t_);
     if (fork) {
         if (!s_side_) {
             int least = 0, greatest = 0;
@@ -802,7 +804,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         PFHE_CUDA(cudaStreamWaitEvent(s_side_, ev_fork_, 0));
         sc = s_side_;
     } else {
-        inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l);
+        inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l, 0, lazy_t_);
     }
     // 4. inverse NTT of the P limbs fused with n^-1 * phat_i^-1
     {
@@ -842,7 +844,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         } else {
             PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), sc, 1));   // 5a: column pass
             PFHE_CUDA(cudaEventRecord(ev_join_, sc));
-            inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l, side_ctas_);   // Q limbs
+            inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l, side_ctas_, lazy_t_);   // Q limbs
             PFHE_CUDA(cudaStreamWaitEvent(st, ev_join_, 0));
             PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), st, 2));   // 5b: row pass + epilogue
         }

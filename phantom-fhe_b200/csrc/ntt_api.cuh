@@ -29,7 +29,7 @@ cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, con
 
 // forward NTT of base-converted inputs (BconvLoad) written to `dst`; optional epilogue (ea) and tensor addend (ts)
 // phase: 0 = column pass (with the conversion) then row pass; 1 = column pass only; 2 = row pass only (the two
-// halves may then be enqueued on different streams)
+// halves may then be enqueued on different streams); 3 = both passes, FP64 limbs left in lazy FP64 form (no epilogue)
 cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, const BconvLoad &bl, const EpiArgs *ea,
                               const TensorSrc *ts, const BarG *bar1, cudaStream_t st, int phase = 0);
 

@@ -98,7 +98,9 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_cols(u64 *d
     })
 }
 
-template<int LOGN>
+// LAZY: FP64 limbs are stored as they leave the butterflies (exact integers in FP64 form, |v| < 12 q), for consumers
+// inside the engine that take them in that form (the key-switch inner product).  Integer limbs are always canonical.
+template<int LOGN, bool LAZY>
 __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows(u64 *data, LimbList ll, NttPlan p) {
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
@@ -109,7 +111,10 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows(u64 *d
         PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
         forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
                 smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(d[i]); }),
-                vec_store<typename A::T>(d, [&](typename A::T v) { return A::canon_fwd(v, c); }));
+                vec_store<typename A::T>(d, [&](typename A::T v) {
+                    if constexpr (LAZY && std::is_same<A, FpArith>::value) return A::raw(v);
+                    else return A::canon_fwd(v, c);
+                }));
     })
 }
 
@@ -516,7 +521,8 @@ static void opt_in_all() {
     static bool done = false;
     if (done) return;
     opt_in_smem(k_fwd_cols<LOGN>);
-    opt_in_smem(k_fwd_rows<LOGN>);
+    opt_in_smem(k_fwd_rows<LOGN, false>);
+    opt_in_smem(k_fwd_rows<LOGN, true>);
     opt_in_smem(k_fwd_rows_epi<LOGN>);
     opt_in_smem(k_inv_rows<LOGN>);
     opt_in_smem(k_inv_cols<LOGN>);
@@ -531,7 +537,7 @@ static void fwd_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList 
     opt_in_all<LOGN>();
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
     launch_pdl(k_fwd_cols<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, src, ll, p);
-    launch_pdl(k_fwd_rows<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
+    launch_pdl(k_fwd_rows<LOGN, false>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
 }
 
 template<int LOGN>
@@ -599,7 +605,8 @@ static void fwd_bconv_impl(const NttPlan &p, u64 *dst, const LimbList &ll, const
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
     if (phase != 2) launch_pdl(k_fwd_cols_bconv<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, bl);
     if (phase == 1) return;
-    if (!ea) launch_pdl(k_fwd_rows<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
+    if (!ea && phase == 3) launch_pdl(k_fwd_rows<LOGN, true>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
+    else if (!ea) launch_pdl(k_fwd_rows<LOGN, false>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
     else if (!ts) launch_pdl(k_fwd_rows_epi<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p, *ea);
     else launch_pdl(k_fwd_rows_epi_tensor<LOGN>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p, *ea, *ts, bar1);
 }

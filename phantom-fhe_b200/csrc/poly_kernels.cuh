@@ -318,6 +318,7 @@ struct InnerProdArgs {
     OwnSrc os;
     const uint32_t *perm;
     int accumulate;
+    int t_lazy;   // FP64 limbs of t hold lazy FP64 words (ntt_forward_bconv phase 3) instead of canonical residues
     size_t n;
     int l, m, size_Q, size_QP, beta;
     int j0, j_count;   // limbs [j0, j0 + j_count) of cx
@@ -329,6 +330,9 @@ struct InnerProdArgs {
 // permutation and no accumulation into cx (the key-switch proper; hoisting takes the general form).  Everything that
 // depends only on (j, launch) is set up once per tile, outside the pair loop: with two coefficients per thread and a
 // run-time digit loop the set-up and addressing were 3/4 of the instructions (profiles/r1b_inner_prod_mix.md).
+#ifndef PFHE_T_EVICT_FIRST
+#define PFHE_T_EVICT_FIRST 1
+#endif
 constexpr int IP_PAIRS = 2;
 constexpr int IP_TILE = IP_PAIRS * 2 * EW_THREADS;
 
@@ -374,7 +378,11 @@ __device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const in
         auto load_t = [&](int d) -> ulonglong2 {
             const u64 *base = tj + (size_t) d * m_n;
             if (perm) return make_ulonglong2(base[px0], base[px1]);
+#if PFHE_T_EVICT_FIRST
+            return ld2_stream(base + x, pol);   // last use of the mod-up digits: do not keep them in L2
+#else
             return ld2(base + x);
+#endif
         };
         auto key = [&](int d) -> const u64 * {
             if constexpr (BETA > 0) return kp[d] + x;
@@ -408,8 +416,8 @@ __device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const in
                 for (int c = 0; c < CH; c++) {
                     const int d = d0 + c;
                     if (d < beta) {
-                        const double vx = d == own_d ? ox : fp::from_u64(v[c].x);
-                        const double vy = d == own_d ? oy : fp::from_u64(v[c].y);
+                        const double vx = d == own_d ? ox : (A.t_lazy ? __longlong_as_double((long long) v[c].x) : fp::from_u64(v[c].x));
+                        const double vy = d == own_d ? oy : (A.t_lazy ? __longlong_as_double((long long) v[c].y) : fp::from_u64(v[c].y));
                         s00 += fp::mulmod_v(vx, fp::from_u64(e0[c].x), q, qi);
                         s01 += fp::mulmod_v(vy, fp::from_u64(e0[c].y), q, qi);
                         s10 += fp::mulmod_v(vx, fp::from_u64(e1[c].x), q, qi);

@@ -157,6 +157,22 @@ def test_nwt_1d(log_dim, count, start):
         pf.check(pf.lib.pfhe_fnwt_1d(d.data_ptr(), d_tw.data_ptr(), d_tws.data_ptr(), d_mod.data_ptr(), 4096, 1, 0, st))
 
 
+def test_ntt_rejects_misaligned_buffers():
+    """The row passes use 256-bit accesses: a polynomial buffer that is not 32-byte aligned is refused (status code),
+    not faulted on."""
+    ps = H.params_small(4096, l=2, alpha=1)
+    ctx = make_context(ps)
+    buf = torch.zeros(2 * ps.n + 4, dtype=torch.int64, device="cuda")
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert buf.data_ptr() % 32 == 0
+    pf.check(pf.lib.pfhe_ntt_forward_inplace(ctx._h, buf.data_ptr(), 2, 0, st))
+    with pytest.raises(pf.PfheError):
+        pf.check(pf.lib.pfhe_ntt_forward_inplace(ctx._h, buf.data_ptr() + 8, 2, 0, st))
+    with pytest.raises(pf.PfheError):
+        pf.check(pf.lib.pfhe_ntt_backward_inplace(ctx._h, buf.data_ptr() + 16, 2, 0, st))
+    torch.cuda.synchronize()
+
+
 def test_ntt_config1_known_answer():
     """SURVEY.md 8c anchor: x_j = mt19937_64(1)() % q, N = 4096, q = 1125899906826241."""
     ps = H.params_c1()
