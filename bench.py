@@ -94,7 +94,7 @@ class ClockSampler:
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons)}
 
 
-def cpu_baseline(ps, a, b, rlk_h, ops=2):
+def cpu_baseline(ps, a, b, rlk_h, ops=None, budget_s=12.0):
     import harness as H
     from harness import P
     o = H.oracle()
@@ -103,6 +103,10 @@ def cpu_baseline(ps, a, b, rlk_h, ops=2):
     l, n = ps.limbs(), ps.n
     out = np.zeros((2, l, n), dtype=np.uint64)
     o.orc_multiply_relin(ps.octx(), l, P(a[0]), P(b[0]), P(rlk_h), P(out))  # warm-up (tables, page faults)
+    if ops is None:   # bounded sample: about budget_s seconds of host work
+        t0 = time.perf_counter()
+        o.orc_multiply_relin(ps.octx(), l, P(a[0]), P(b[0]), P(rlk_h), P(out))
+        ops = max(2, min(200, int(budget_s / max(time.perf_counter() - t0, 1e-3))))
     t0 = time.perf_counter()
     for i in range(ops):
         o.orc_multiply_relin(ps.octx(), l, P(a[i % len(a)]), P(b[i % len(b)]), P(rlk_h), P(out))

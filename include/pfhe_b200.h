@@ -187,6 +187,11 @@ int pfhe_relinearize_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encry
 int pfhe_apply_galois_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, uint32_t galois_elt,
                               const uint64_t *const *galois_key, void *stream);
 /* rotate_inplace (src/evaluate.cu:1633-1668) for a step whose element is in the engine's Galois set */
+/* `count` independent rotate_inplace calls (e.g. the steps of a baby-step / giant-step loop, each on its own copy):
+ * encrypted[i] <- rotate(encrypted[i], steps[i]) with galois_keys[i] = get_relin_keys(idx_i).public_keys_ptr(),
+ * interleaved over the engine's lanes like pfhe_multiply_and_relin_batch.  The ciphertexts must be distinct buffers. */
+int pfhe_rotate_batch(pfhe_engine *e, size_t chain_index, uint64_t *const *encrypted, const int *steps,
+                      const uint64_t *const *const *galois_keys, size_t count, void *stream);
 int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, int step,
                         const uint64_t *const *galois_key, void *stream);
 /* hoisting_inplace (src/evaluate.cu:1670-1865): encrypted <- sum_i rotate(encrypted, steps[i]) with one shared mod-up

@@ -52,6 +52,7 @@ _sigs = {
     "pfhe_multiply": (ctypes.c_int, [vp, sz, vp, vp, vp, vp]),
     "pfhe_relinearize_inplace": (ctypes.c_int, [vp, sz, vp, vp, vp]),
     "pfhe_apply_galois_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_uint32, vp, vp]),
+    "pfhe_rotate_batch": (ctypes.c_int, [vp, sz, vp, i32p, vp, sz, vp]),
     "pfhe_rotate_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_int, vp, vp]),
     "pfhe_hoisting_inplace": (ctypes.c_int, [vp, sz, vp, i32p, sz, vp, vp]),
     "pfhe_rescale_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),

@@ -364,6 +364,31 @@ def rotate_inplace(context, encrypted, step, galois_key):
             rotate_inplace(context, encrypted, s, galois_key)
 
 
+def rotate_batch(context, encrypteds, steps, galois_key):
+    """rotate_inplace over a list of distinct ciphertexts, one step each, in one C-ABI call (ops interleaved over the
+    engine's lanes).  Every step must have its own Galois key (no NAF decomposition here)."""
+    if len(encrypteds) != len(steps):
+        raise ValueError("batch sizes differ")
+    if not encrypteds:
+        return
+    elts = context.parms.galois_elts
+    ci = encrypteds[0].chain_index
+    keys = []
+    for ct, s in zip(encrypteds, steps):
+        if ct.size() > 2:
+            raise ValueError("ciphertext size must be 2")
+        _require_ntt(context, ct)
+        if ct.chain_index != ci:
+            raise ValueError("encrypteds parameter mismatch")
+        e = get_elt_from_step(s, context.poly_degree)
+        if e not in elts:
+            raise ValueError("Galois key not present")
+        keys.append(galois_key.get_relin_keys(elts.index(e)).public_keys_ptr().value)
+    n = len(steps)
+    check(lib.pfhe_rotate_batch(context._h, ci, (ctypes.c_void_p * n)(*[c.data.data_ptr() for c in encrypteds]),
+                                (ctypes.c_int * n)(*steps), (ctypes.c_void_p * n)(*keys), n, _stream()))
+
+
 def hoisting_inplace(context, ct, glk, steps):
     """hoisting_inplace (src/evaluate.cu:1670-1865)."""
     if ct.size() > 2:

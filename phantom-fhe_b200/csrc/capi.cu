@@ -354,6 +354,21 @@ int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, int st
     if (rc != PFHE_OK) return rc;
     return pfhe_apply_galois_inplace(e, chain_index, ct, elt, glk, stream);
 }
+int pfhe_rotate_batch(pfhe_engine *e, size_t chain_index, uint64_t *const *cts, const int *steps,
+                      const uint64_t *const *const *galois_keys, size_t count, void *stream) {
+    API_BEGIN
+    require(cts && steps && galois_keys, "null batch pointers");
+    const int l = e->impl.limbs_at(chain_index);
+    std::vector<uint32_t> elts(count);
+    for (size_t i = 0; i < count; i++) {
+        require(cts[i] && galois_keys[i], "null batch pointers");
+        for (size_t j = 0; j < i; j++) require(cts[i] != cts[j], "the same ciphertext appears twice in the batch");
+        if (pfhe_galois_elt_from_step(steps[i], e->impl.n(), &elts[i]) != PFHE_OK) throw std::invalid_argument(g_error);
+    }
+    e->impl.apply_galois_batch(l, reinterpret_cast<u64 *const *>(cts), elts.data(),
+                               reinterpret_cast<const u64 *const *const *>(galois_keys), count, S(stream));
+    API_END
+}
 int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const int *steps, size_t n_steps,
                           const uint64_t *const *const *galois_keys, void *stream) {
     API_BEGIN

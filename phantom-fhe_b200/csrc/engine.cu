@@ -137,11 +137,12 @@ void Engine::swap_lane(int k) {
     std::swap(ev_join_, L.ev_join);
 }
 
-void Engine::multiply_relin_batch(int l, const u64 *const *ct1, const u64 *const *ct2, u64 *const *out, size_t count,
-                                  const u64 *const *rlk, cudaStream_t st) {
+// independent ops round-robin over the lanes: lane 0 is the caller's stream, lane k > 0 an internal stream with its own
+// workspace; forks from and joins back into `st`
+void Engine::run_lanes(size_t count, cudaStream_t st, const std::function<void(size_t, cudaStream_t)> &op) {
     const int L = (int) std::min<size_t>((size_t) n_lanes_, count);
     if (L <= 1) {
-        for (size_t i = 0; i < count; i++) multiply_relin(l, out[i], ct1[i], ct2[i], rlk, st);
+        for (size_t i = 0; i < count; i++) op(i, st);
         return;
     }
     if (!lane_[0].ev_done) PFHE_CUDA(cudaEventCreateWithFlags(&lane_[0].ev_done, cudaEventDisableTiming));
@@ -153,14 +154,13 @@ void Engine::multiply_relin_batch(int l, const u64 *const *ct1, const u64 *const
             alloc_workspace(ln.ws);
         }
     }
-    // lane 0 is the caller's stream; the others start after whatever the caller already queued on it
     PFHE_CUDA(cudaEventRecord(lane_[0].ev_done, st));
     for (int k = 1; k < L; k++) PFHE_CUDA(cudaStreamWaitEvent(lane_[k].stream, lane_[0].ev_done, 0));
     for (size_t i = 0; i < count; i++) {
         const int k = (int) (i % (size_t) L);
         swap_lane(k);
         try {
-            multiply_relin(l, out[i], ct1[i], ct2[i], rlk, k == 0 ? st : lane_[k].stream);
+            op(i, k == 0 ? st : lane_[k].stream);
         } catch (...) {
             swap_lane(k);
             throw;
@@ -171,6 +171,16 @@ void Engine::multiply_relin_batch(int l, const u64 *const *ct1, const u64 *const
         PFHE_CUDA(cudaEventRecord(lane_[k].ev_done, lane_[k].stream));
         PFHE_CUDA(cudaStreamWaitEvent(st, lane_[k].ev_done, 0));
     }
+}
+
+void Engine::multiply_relin_batch(int l, const u64 *const *ct1, const u64 *const *ct2, u64 *const *out, size_t count,
+                                  const u64 *const *rlk, cudaStream_t st) {
+    run_lanes(count, st, [&](size_t i, cudaStream_t s) { multiply_relin(l, out[i], ct1[i], ct2[i], rlk, s); });
+}
+
+void Engine::apply_galois_batch(int l, u64 *const *ct, const uint32_t *elts, const u64 *const *const *glk, size_t count,
+                                cudaStream_t st) {
+    run_lanes(count, st, [&](size_t i, cudaStream_t s) { apply_galois(l, ct[i], elts[i], glk[i], s); });
 }
 
 Engine::~Engine() {

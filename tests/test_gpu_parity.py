@@ -451,6 +451,34 @@ def test_multiply_relin_batch(lanes):
         pf.check(pf.lib.pfhe_multiply_and_relin_batch(ctx._h, 1, arr, arr, arr, 1, rlk.public_keys_ptr(), st))
 
 
+@pytest.mark.parametrize("scheme,lanes", [(3, 2), (3, 3), (1, 2), (2, 2)])
+def test_rotate_batch(scheme, lanes):
+    """pfhe_rotate_batch: independent rotations (one step each, own Galois key) interleaved over the lanes give the words
+    of rotate_inplace one at a time = the oracle's; CKKS, BGV and BFV (coefficient-domain permutation)."""
+    ps = H.params_small(4096, l=4, alpha=2, scheme=scheme, t=65537 if scheme != 3 else 0)
+    steps = [1, 2, -1, 3, 5]
+    ctx = make_bfv_context(ps, steps) if scheme == 2 else make_context(ps, steps)
+    pf.check(pf.lib.pfhe_engine_set_lanes(ctx._h, lanes))
+    o, oc = H.oracle(), ps.octx()
+    l, n = ps.limbs(), ps.n
+    elts = pf.get_elts_from_steps(steps, n)
+    glk_h = [H.switch_key(ps, 1000 * (i + 1)) for i in range(len(steps))]
+    glk = pf.PhantomGaloisKey(ctx, [list(k) for k in glk_h])
+    cts_h = [H.ciphertext(ps, 40 + i) for i in range(len(steps))]
+    want = []
+    for i, ct in enumerate(cts_h):
+        w = ct.copy()
+        o.orc_apply_galois(oc, l, P(w), elts[i], P(glk_h[i]))
+        want.append(w)
+    cts = [pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=(scheme != 2)) for ct in cts_h]
+    pf.rotate_batch(ctx, cts, steps, glk)
+    for i in range(len(steps)):
+        assert np.array_equal(cts[i].to_host(), want[i]), f"rotate batch item {i} (step {steps[i]})"
+    pf.rotate_batch(ctx, [], [], glk)
+    with pytest.raises(ValueError):   # the same buffer twice would race between lanes
+        pf.rotate_batch(ctx, [cts[0], cts[0]], [1, 2], glk)
+
+
 # ---------------------------------------------------------------------------------------------------------
 # BGV / BFV forms of the key switch and the modulus switch (rns_bconv.cu:583-606,636-652,790-827; rns.cu:1082-1235)
 # ---------------------------------------------------------------------------------------------------------

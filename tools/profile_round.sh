@@ -8,6 +8,7 @@ python tools/quick_bench.py primary > gpurun_out/${tag}_quick_primary.txt 2>&1
 python tools/quick_bench.py secondary > gpurun_out/${tag}_quick_secondary.txt 2>&1
 python tools/bfv_bench.py 100 > gpurun_out/${tag}_bfv.txt 2>&1
 python tools/two_lane.py 200 > gpurun_out/${tag}_lanes.txt 2>&1
+python tools/rotate32.py > gpurun_out/${tag}_rotate32.txt 2>&1
 ./tools/microbench > gpurun_out/${tag}_microbench.txt 2>&1
 ncu --metrics gpu__time_duration.sum,smsp__inst_executed.sum --clock-control none -c 400 --csv --log-file gpurun_out/${tag}_launches.csv \
     python bench.py --steps 8 --warmup 3 --no-cpu-baseline > gpurun_out/${tag}_ncu_bench.log 2>&1
