@@ -139,6 +139,9 @@ struct RoundMap {
     // a thread's G groups sit NTT_THREADS apart in the packed (hi, lo, batch) index, i.e. they differ in its
     // top bits; they use the same twiddles only when those bits belong to the low index
     static constexpr bool SHARE = !ROWS && S0 == 0 && LAM >= GB;
+    // row pass, one radix-2^R group per thread and 2^(P-R) = 32 threads per row: a warp owns a whole row of the tile in
+    // this round.  An exchange between two such rounds stays inside the warp (__syncwarp instead of a CTA barrier)
+    static constexpr bool WARP_ROW = ROWS && G == 1 && (P - R == 5) && (NTT_LOG_THREADS + NTT_LOG_EPT - P == 3);
     __device__ static __forceinline__ int mu(int tid, int g) { return (g << NTT_LOG_THREADS) | tid; }
 
     __device__ static __forceinline__ void decode(int mu, int &hi, int &lo, int &c) {
@@ -162,6 +165,13 @@ struct RoundMap {
     }
     __host__ __device__ static constexpr int kc(int k) { return skew(k << KSHIFT); }
 };
+
+// synchronisation of an exchange between round RA (writer side) and round RB (reader side) of a pass
+template<int P, int RA, int RB, bool ROWS>
+__device__ __forceinline__ void exchange_sync() {
+    if constexpr (RoundMap<P, RA, ROWS>::WARP_ROW && RoundMap<P, RB, ROWS>::WARP_ROW) __syncwarp();
+    else __syncthreads();
+}
 
 // ----------------------------------------------------------------------------------------------------
 // arithmetic policies.  Two exact implementations of the same modular butterflies:
@@ -598,7 +608,8 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
         // strided 64-byte segments of the tile, in a row pass a thread owns whole runs of 2^R consecutive coefficients
         // (LAM = 0) and a warp covers one contiguous stretch of a row, so no staging through shared memory is needed
         constexpr bool DIRECT_OUT = (RI == NR - 1);
-        if constexpr (!DIRECT_OUT && RI > 0) __syncthreads();   // all gathers of this round are done
+        // (no barrier before the scatter: a tile position depends on the element alone, not on the round, so a thread
+        // overwrites exactly the positions it gathered from)
         if constexpr (DIRECT_OUT) {
             size_t gi[NTT_EPT];
 #pragma unroll
@@ -612,7 +623,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
             for (int g = 0; g < M::G; g++)
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++) smem[s0[g] ^ M::kc(k)] = A::raw(x[(g << M::R) + k]);
-            __syncthreads();
+            exchange_sync<P, RI, RI + 1, ROWS>();
         }
         TL_MARK(5 + 2 * RI)
     };
@@ -668,7 +679,6 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
                     gi[(g << M::R) + k] = gl_index<P, ROWS, LOGN>(M::elem(hi[g], k, lo[g]), c[g], cx.tile);
             store.template scatter<1>(gi, x);
         } else {
-            if constexpr (!DIRECT_IN) __syncthreads();
 #pragma unroll
             for (int g = 0; g < M::G; g++)
 #pragma unroll
@@ -676,7 +686,7 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
                     const int e = M::elem(hi[g], k, lo[g]);
                     smem[s0[g] ^ M::kc(k)] = A::raw(x[(g << M::R) + k]);
                 }
-            __syncthreads();
+            exchange_sync<P, RI, RI - 1, ROWS>();
         }
     };
 
