@@ -130,6 +130,15 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
                             const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
                             void *stream);
+/* PhantomSecretKey::decrypt (src/secretkey.cu:533-723: ckks_decrypt / bgv_decrypt / bfv_decrypt) -- the step after the
+ * hot path.  encrypted = [size][l][n] at chain_index (CKKS / BGV: NTT form; BFV: coefficient form);
+ * secret_key_array = PhantomSecretKey::secret_key_array(): the powers s, s^2, .. s^(size-1) of the secret key in NTT form,
+ * [size-1][size_QP][n] at the key level (compute_secret_key_array, secretkey.cu:247-295).  destination: CKKS [l][n] in
+ * NTT form (the plaintext the decoder takes); BGV [n] = exact_convert_array to t (times correction_factor^-1); BFV [n] =
+ * behz_ / hps_decrypt_scale_and_round by the engine's mul_tech.  correction_factor: BGV only, 1 otherwise. */
+int pfhe_decrypt(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted, size_t size,
+                 const uint64_t *secret_key_array, uint64_t correction_factor, uint64_t *destination, void *stream);
+
 /* ---- BFV with mul_tech_type::hps_overq_leveled (pfhe_engine_set_mul_tech(e, 4)) ---------------------------------
  * The reference decides per operation how many levels to drop from the ciphertexts' noise-scale degree
  * (FindLevelsToDrop, evaluate.cu:550-643; the degree lives on PhantomCiphertext, ciphertext.h:21,97-131): the caller

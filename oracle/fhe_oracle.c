@@ -1446,6 +1446,181 @@ int orc_bfv_multiply_relin_hps(const orc_ctx *c, const u64 *ct1, const u64 *ct2,
 }
 
 /* ------------------------------------------------------------------------------------------------------
+ * decryption (PhantomSecretKey::ckks_decrypt / bgv_decrypt / bfv_decrypt, reference src/secretkey.cu:533-691).
+ * sk_pow = [size - 1][size_QP][n]: powers s, s^2, ... of the secret key in NTT form at the key level
+ * (secret_key_array(), secretkey.cu:247-295); limb i of the data level uses limb i of every power.
+ * ---------------------------------------------------------------------------------------------------- */
+static int bits_u64(u64 v) {
+    int b = 0;
+    while (v) b++, v >>= 1;
+    return b;
+}
+
+/* inner product c_0 + sum_i c_i s^i (CKKS/BGV: NTT form throughout; BFV: c_i to NTT form, sum back to coefficients, + c_0) */
+static void decrypt_inner(const orc_ctx *c, int l, const u64 *ct, int size, const u64 *sk_pow, u64 *acc, int bfv) {
+    size_t n = c->n, pl = (size_t)l * n, pk = (size_t)c->size_QP * n;
+    int idx[64];
+    for (int i = 0; i < l; i++) idx[i] = i;
+    u64 *tmp = (u64 *)malloc(pl * 8);
+    if (bfv) memset(acc, 0, pl * 8);
+    else memcpy(acc, ct, pl * 8);
+    for (int k = 1; k < size; k++) {
+        memcpy(tmp, ct + k * pl, pl * 8);
+        if (bfv) orc_ntt_forward(c, tmp, l, idx); /* secretkey.cu:603-606 */
+        const u64 *sk = sk_pow + (size_t)(k - 1) * pk;
+        for (int i = 0; i < l; i++) {
+            u64 q = c->primes[i];
+            for (size_t x = 0; x < n; x++) { /* multiply_and_add_rns_poly */
+                size_t j = (size_t)i * n + x;
+                acc[j] = addmod(orc_mulmod(tmp[j], sk[j], q), acc[j], q);
+            }
+        }
+    }
+    if (bfv) {
+        orc_ntt_inverse(c, acc, l, idx);
+        for (int i = 0; i < l; i++)
+            for (size_t x = 0; x < n; x++) acc[(size_t)i * n + x] = addmod(ct[(size_t)i * n + x], acc[(size_t)i * n + x], c->primes[i]);
+    }
+    free(tmp);
+}
+
+/* hps_decrypt_scale_and_round (rns.cu:1519-1692, tables :594-680): round(t/Q * x) mod t from the RNS residues, with the
+ * reference's four kernel variants selected by the bit budgets; every `sum += double(a) * c` is one fma, in index order */
+static void hps_decrypt_scale_round(const orc_ctx *c, int l, const u64 *x, u64 *out) {
+    const size_t n = c->n;
+    const u64 *Q = c->primes, t = c->t;
+    u64 qmax = 0;
+    for (int i = 0; i < c->size_Q; i++)
+        if (Q[i] > qmax) qmax = Q[i];
+    const int qMSB = bits_u64(qmax), sizeQMSB = bits_u64((u64)l), tMSB = bits_u64(t), hf = qMSB >> 1;
+    u64 mt[64], mtB[64];
+    double fr[64], frB[64];
+    for (int i = 0; i < l; i++) {
+        u64 qi = Q[i], hinv = orc_invmod(qhat_mod(Q, l, i, qi), qi);
+        u128 w = (u128)t * hinv;
+        mt[i] = (u64)((w / qi) % t);
+        fr[i] = (double)(u64)(w % qi) / (double)qi;
+        u64 hb = (u64)(((u128)hinv << hf) % qi);
+        w = (u128)t * hb;
+        mtB[i] = (u64)((w / qi) % t);
+        frB[i] = (double)(u64)(w % qi) / (double)qi;
+    }
+    const int large = qMSB + sizeQMSB >= 52;
+    const int lazy = large ? (hf + tMSB + sizeQMSB) < 52 : (qMSB + tMSB + sizeQMSB) < 52;
+    const double tInv = 1. / (double)t;
+#pragma omp parallel for num_threads(g_threads)
+    for (size_t k = 0; k < n; k++) {
+        double fs = 0.0;
+        u64 is = 0;
+        for (int i = 0; i < l; i++) {
+            u64 v = x[(size_t)i * n + k];
+            if (!large) {
+                fs = fma((double)v, fr[i], fs);
+                is += lazy ? v * mt[i] : orc_mulmod(v, mt[i], t);
+            } else {
+                u64 hi = v >> hf, lo = v & (((u64)1 << hf) - 1);
+                fs = fma((double)lo, fr[i], fs);
+                fs = fma((double)hi, frB[i], fs);
+                is += lazy ? lo * mt[i] : orc_mulmod(lo, mt[i], t);
+                is += lazy ? hi * mtB[i] : orc_mulmod(hi, mtB[i], t);
+            }
+        }
+        fs += (double)is;
+        u64 quot = sat_u64(fs * tInv);
+        fs -= (double)(t * quot);
+        out[k] = (u64)llround(fs);
+    }
+}
+
+/* behz_decrypt_scale_and_round (rns.cu:1008-1080, constants :331-390): gamma = the largest 61-bit NTT prime */
+static int behz_decrypt_scale_round(const orc_ctx *c, int l, const u64 *x, u64 *out) {
+    const size_t n = c->n;
+    const u64 *Q = c->primes, t = c->t;
+    u64 gamma;
+    {
+        int b61 = 61;
+        if (orc_create_primes(n, &b61, 1, &gamma)) return -1;
+    }
+    const u64 tg[2] = {t, gamma};
+    u64 *sc = (u64 *)malloc((size_t)l * n * 8), *o2 = (u64 *)malloc(2 * n * 8);
+    for (int i = 0; i < l; i++) {
+        u64 f = orc_mulmod(t % Q[i], gamma % Q[i], Q[i]);
+        for (size_t k = 0; k < n; k++) sc[(size_t)i * n + k] = orc_mulmod(x[(size_t)i * n + k], f, Q[i]);
+    }
+    const u64 *in[64];
+    u64 *op[2] = {o2, o2 + n};
+    for (int i = 0; i < l; i++) in[i] = sc + (size_t)i * n;
+    bconv(Q, l, tg, 2, in, op, n, 0); /* base_q_to_t_gamma_conv_.bConv_BEHZ */
+    u64 ninv[2];
+    for (int j = 0; j < 2; j++) {
+        u64 qm = prod_mod(Q, l, tg[j]);
+        ninv[j] = (tg[j] - orc_invmod(qm, tg[j])) % tg[j];
+    }
+    const u64 inv_gamma_t = orc_invmod(gamma % t, t), half = gamma >> 1;
+    for (size_t k = 0; k < n; k++) {
+        u64 a = orc_mulmod(o2[k], ninv[0], t), g = orc_mulmod(o2[n + k], ninv[1], gamma), tmp;
+        if (g > half) tmp = addmod(a, (gamma - g) % t, t); /* perform_final_multiplication, :984-1006 */
+        else tmp = submod(a, g % t, t);
+        out[k] = orc_mulmod(tmp, inv_gamma_t, t);
+    }
+    free(sc); free(o2);
+    return 0;
+}
+
+/* exact_convert_array Q_l -> t (rns_bconv.cu:374-430; bgv decrypt_mod_t, rns.cu:1237-1240): v accumulates IEEE
+ * quotients double(y_i) / double(q_i) in index order, rounded half away from zero */
+static void exact_convert_to_t(const orc_ctx *c, int l, const u64 *x, u64 *out) {
+    const size_t n = c->n;
+    const u64 *Q = c->primes, t = c->t;
+    u64 hinv[64], mat[64];
+    for (int i = 0; i < l; i++) hinv[i] = orc_invmod(qhat_mod(Q, l, i, Q[i]), Q[i]), mat[i] = qhat_mod(Q, l, i, t);
+    const u64 q_mod_t = prod_mod(Q, l, t);
+#pragma omp parallel for num_threads(g_threads)
+    for (size_t k = 0; k < n; k++) {
+        double v = 0.0;
+        u128 ip = 0;
+        for (int i = 0; i < l; i++) {
+            u64 y = orc_mulmod(x[(size_t)i * n + k], hinv[i], Q[i]);
+            ip = (ip + (u128)y * mat[i]) % t;
+            v += (double)y / (double)Q[i];
+        }
+        u64 rv = (u64)round(v);
+        out[k] = submod((u64)ip, orc_mulmod(rv % t, q_mod_t, t), t);
+    }
+}
+
+/* out: CKKS [l][n] (NTT form); BGV / BFV [n] residues mod t.  mul_tech as host/encryptionparams.h:25-35 (BFV only);
+ * correction_factor: BGV (ciphertext.h), 1 otherwise */
+int orc_decrypt(const orc_ctx *c, int l, const u64 *ct, int size, const u64 *sk_pow, int mul_tech, u64 correction_factor,
+                u64 *out) {
+    const size_t n = c->n;
+    if (size < 1 || l < 1 || l > 64) return -1;
+    if (c->scheme == ORC_SCHEME_CKKS) {
+        decrypt_inner(c, l, ct, size, sk_pow, out, 0);
+        return 0;
+    }
+    u64 *acc = (u64 *)malloc((size_t)l * n * 8);
+    int rc = 0;
+    if (c->scheme == ORC_SCHEME_BGV) {
+        int idx[64];
+        for (int i = 0; i < l; i++) idx[i] = i;
+        decrypt_inner(c, l, ct, size, sk_pow, acc, 0);
+        orc_ntt_inverse(c, acc, l, idx);
+        exact_convert_to_t(c, l, acc, out);
+        if (correction_factor != 1) { /* secretkey.cu:681-690 */
+            u64 fix = orc_invmod(correction_factor % c->t, c->t);
+            for (size_t k = 0; k < n; k++) out[k] = orc_mulmod(out[k], fix, c->t);
+        }
+    } else {
+        decrypt_inner(c, l, ct, size, sk_pow, acc, 1);
+        if (mul_tech == 1) rc = behz_decrypt_scale_round(c, l, acc, out);
+        else hps_decrypt_scale_round(c, l, acc, out);
+    }
+    free(acc);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------------
  * rescale / mod switch
  * ---------------------------------------------------------------------------------------------------- */
 void orc_rescale(const orc_ctx *c, int l, u64 *in, int size, u64 *out) {

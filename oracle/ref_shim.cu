@@ -14,6 +14,7 @@
 #include <chrono>
 #include <cstring>
 #include <memory>
+#include <sstream>
 #include <vector>
 
 #include "phantom.h"
@@ -326,6 +327,38 @@ int ref_multiply_deg(void *p, size_t chain_index, const uint64_t *ct1, const uin
         if (relin == 1) relinearize_inplace(*h->ctx, a, *h->rlk);
     }
     fetch_ct(a, out);
+    return 0;
+    SHIM_CATCH
+}
+
+/* the secret key (first power, NTT form, [size_QP][n]) through PhantomSecretKey::save (secretkey.h:346-364) */
+int ref_secret_key(void *p, uint64_t *host) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    if (!h->sk) throw std::invalid_argument("context was created without keys");
+    std::stringstream ss;
+    h->sk->save(ss);
+    const std::string blob = ss.str();
+    size_t hdr[3];
+    std::memcpy(hdr, blob.data(), sizeof(hdr));   /* sk_max_power, poly_modulus_degree, coeff_modulus_size */
+    std::memcpy(host, blob.data() + sizeof(hdr), hdr[1] * hdr[2] * sizeof(uint64_t));
+    return 0;
+    SHIM_CATCH
+}
+
+/* PhantomSecretKey::decrypt (secretkey.cu:693-723) of caller-supplied ciphertext words: out = [l][n] (CKKS) or [n] */
+int ref_decrypt(void *p, size_t chain_index, const uint64_t *ct, size_t size, uint64_t correction_factor, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    if (!h->sk) throw std::invalid_argument("context was created without keys");
+    bool ntt = h->scheme != scheme_type::bfv;
+    auto c = make_ct(h, chain_index, size, ct, ntt);
+    if (h->scheme == scheme_type::bgv) c.set_correction_factor(correction_factor);
+    PhantomPlaintext plain;
+    h->sk->decrypt(*h->ctx, c, plain);
+    cudaStreamSynchronize(cudaStreamPerThread);
+    size_t words = (h->scheme == scheme_type::ckks ? c.coeff_modulus_size() : 1) * h->n;   /* secretkey.cu:705-712 */
+    cudaMemcpy(out, plain.data(), words * sizeof(uint64_t), cudaMemcpyDeviceToHost);
     return 0;
     SHIM_CATCH
 }

@@ -184,6 +184,41 @@ class PhantomCiphertext:
         return c
 
 
+class PhantomSecretKey:
+    """The decrypting half of PhantomSecretKey (include/secretkey.h:226-338): the secret key's powers in NTT form at the
+    key level (secret_key_array()) and decrypt().  Key generation and encryption stay with the reference (SURVEY.md 8f);
+    the first power comes from there (PhantomSecretKey::save) or from the caller."""
+
+    def __init__(self, context, secret_key_ntt):
+        s1 = np.asarray(secret_key_ntt, dtype=np.uint64).reshape(1, context.size_QP, context.poly_degree)
+        self._pow = _to_dev(s1, context.device)   # [sk_max_power][size_QP][n]
+
+    def secret_key_array(self):
+        return self._pow
+
+    def _compute_secret_key_array(self, context, max_power):
+        """compute_secret_key_array (src/secretkey.cu:196-230): s^k = s^(k-1) * s, limb-wise, all key-level limbs."""
+        while self._pow.shape[0] < max_power:
+            nxt = torch.empty_like(self._pow[:1])
+            check(lib.pfhe_multiply_rns_poly(context._h, _ptr(self._pow[-1]), _ptr(self._pow[0]), _ptr(nxt),
+                                             context.size_QP, _stream()))
+            self._pow = torch.cat([self._pow, nxt])
+
+    def decrypt(self, context, cipher):
+        """PhantomSecretKey::decrypt (src/secretkey.cu:693-723): returns the plaintext words on the device -- CKKS:
+        [l][n] in NTT form (what the decoder takes); BFV / BGV: [n] residues mod t."""
+        _require_ntt(context, cipher)
+        size = cipher.size()
+        self._compute_secret_key_array(context, max(1, size - 1))
+        l, n = cipher.coeff_modulus_size(), context.poly_degree
+        shape = (l, n) if context.scheme == scheme_type.ckks else (n,)
+        out = torch.empty(shape, dtype=torch.int64, device=cipher.data.device)
+        cf = cipher.correction_factor if context.scheme == scheme_type.bgv else 1
+        check(lib.pfhe_decrypt(context._h, cipher.chain_index, _ptr(cipher.data), size, _ptr(self._pow), cf, _ptr(out),
+                               _stream()))
+        return out
+
+
 class PhantomRelinKey:
     """dnum device buffers [2][size_QP][N] in NTT form + a device array of their addresses
     (include/secretkey.h:102-127, public_keys_ptr())."""

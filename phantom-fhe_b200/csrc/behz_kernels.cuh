@@ -343,4 +343,136 @@ __global__ void __launch_bounds__(BEHZ_THREADS) k_expand_add(PolyView ct, PolyVi
             make_ulonglong2(add_mod(a.x, mul_shoup(b.x, f, q), q), add_mod(a.y, mul_shoup(b.y, f, q), q));
 }
 
+// ---------------------------------------------------------------------------------------------------
+// decryption tails (PhantomSecretKey::bfv_decrypt / bgv_decrypt, reference src/secretkey.cu:571-691): one thread per
+// coefficient turns the RNS residues of c_0 + c_1 s + ... into the plaintext residue mod t.
+// ---------------------------------------------------------------------------------------------------
+// c_0 + sum_k c_k s^k, limb-wise (multiply_and_add_rns_poly chain, secretkey.cu:553-562): ct = [size][l][n] (polys
+// 1.. already in NTT form; BFV passes its transformed copy and adds c_0 after the inverse transform), sk = powers of the
+// secret key, stride sk_stride words.  grid.y = limb, 2 coefficients per thread.
+__global__ void __launch_bounds__(BEHZ_THREADS) k_decrypt_inner(u64 *acc, const u64 *c0, const u64 *cts, size_t ct_stride,
+                                                               const u64 *sk, size_t sk_stride, int terms,
+                                                               const Modulus *mod, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int i = blockIdx.y;
+    const Modulus m = mod[i];
+    const size_t x = (size_t) i * n + ((size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x) * 2;
+    Acc128 a0{0, 0}, a1{0, 0};
+    if (c0) {
+        const ulonglong2 v = *reinterpret_cast<const ulonglong2 *>(c0 + x);
+        a0.lo = v.x, a1.lo = v.y;
+    }
+    for (int k = 0; k < terms; k++) {
+        const ulonglong2 c = *reinterpret_cast<const ulonglong2 *>(cts + (size_t) k * ct_stride + x);
+        const ulonglong2 s = *reinterpret_cast<const ulonglong2 *>(sk + (size_t) k * sk_stride + x);
+        a0.mac(c.x, s.x), a1.mac(c.y, s.y);
+    }
+    *reinterpret_cast<ulonglong2 *>(acc + x) = make_ulonglong2(barrett128(a0.lo, a0.hi, m), barrett128(a1.lo, a1.hi, m));
+}
+
+// hps_decrypt_scale_and_round (rns.cu:1519-1692): round(t/Q x) mod t.  `add` = c_0 (coefficient form) is added to the
+// inner product first (secretkey.cu:613-615).  large / lazy select the reference's four kernel variants; the FP sums
+// are one fma per term in index order, like the reference's compiled code.
+struct HpsDecryptArgs {
+    const u64 *x, *add;     // [l][n]
+    u64 *out;               // [n]
+    const u64 *mt, *mtB;    // [l]
+    const double *fr, *frB; // [l]
+    const Modulus *mod_q;
+    Modulus tm;
+    int l, large, lazy, hf;
+    size_t n;
+};
+__global__ void __launch_bounds__(BEHZ_THREADS) k_hps_decrypt(const HpsDecryptArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t k = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    const u64 t = a.tm.q;
+    double fs = 0.0;
+    u64 is = 0;
+    for (int i = 0; i < a.l; i++) {
+        const u64 v = add_mod(a.add[(size_t) i * a.n + k], a.x[(size_t) i * a.n + k], a.mod_q[i].q);
+        if (!a.large) {
+            fs = __fma_rn((double) v, a.fr[i], fs);
+            is += a.lazy ? v * a.mt[i] : mul_mod(v, a.mt[i], a.tm);
+        } else {
+            const u64 hi = v >> a.hf, lo = v & (((u64) 1 << a.hf) - 1);
+            fs = __fma_rn((double) lo, a.fr[i], fs);
+            fs = __fma_rn((double) hi, a.frB[i], fs);
+            is += a.lazy ? lo * a.mt[i] : mul_mod(lo, a.mt[i], a.tm);
+            is += a.lazy ? hi * a.mtB[i] : mul_mod(hi, a.mtB[i], a.tm);
+        }
+    }
+    fs = __dadd_rn(fs, (double) is);
+    const u64 quot = (u64) __dmul_rn(fs, 1. / (double) t);
+    fs = __dadd_rn(fs, -(double) (t * quot));
+    a.out[k] = (u64) llround(fs);
+}
+
+// behz_decrypt_scale_and_round (rns.cu:1008-1080): |gamma t|_q scaling, fast conversion to {t, gamma}, times
+// -Q^-1, centred correction through gamma, times gamma^-1 mod t
+struct BehzDecryptArgs {
+    const u64 *x, *add;
+    u64 *out;
+    const Tw *tg_mod_q;     // [l]   t * gamma mod q_i
+    const Tw *q_hinv;       // [l]   qhat_i^-1 mod q_i
+    const u64 *mat;         // [2][l] qhat_i mod t, mod gamma
+    const Modulus *mod_q;
+    Modulus tm, gm;
+    u64 ninv_t, ninv_g, inv_gamma_t;
+    int l;
+    size_t n;
+};
+__global__ void __launch_bounds__(BEHZ_THREADS) k_behz_decrypt(const BehzDecryptArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t k = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    Acc128 at{0, 0}, ag{0, 0};
+    for (int i = 0; i < a.l; i++) {
+        const u64 q = a.mod_q[i].q;
+        const u64 v = add_mod(a.add[(size_t) i * a.n + k], a.x[(size_t) i * a.n + k], q);
+        const u64 y = mul_shoup(mul_shoup(v, a.tg_mod_q[i], q), a.q_hinv[i], q);
+        at.mac(y, a.mat[i]);
+        ag.mac(y, a.mat[a.l + i]);
+    }
+    const u64 t = a.tm.q, g = a.gm.q;
+    const u64 rt = mul_mod(barrett128(at.lo, at.hi, a.tm), a.ninv_t, a.tm);
+    const u64 rg = mul_mod(barrett128(ag.lo, ag.hi, a.gm), a.ninv_g, a.gm);
+    u64 tmp;
+    if (rg > (g >> 1)) tmp = add_mod(rt, barrett128(g - rg, 0, a.tm), t);
+    else tmp = sub_mod(rt, barrett128(rg, 0, a.tm), t);
+    a.out[k] = mul_mod(tmp, a.inv_gamma_t, a.tm);
+}
+
+// exact_convert_array Q_l -> t (rns_bconv.cu:374-430; DRNSTool::decrypt_mod_t) and the BGV correction factor
+struct ExactConvertArgs {
+    const u64 *x;
+    u64 *out;
+    const Tw *q_hinv;       // [l]
+    const u64 *mat;         // [l] qhat_i mod t
+    const Modulus *mod_q;
+    Modulus tm;
+    u64 q_mod_t, fix;       // fix = correction_factor^-1 mod t (1: none)
+    int l;
+    size_t n;
+};
+__global__ void __launch_bounds__(BEHZ_THREADS) k_exact_convert_t(const ExactConvertArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t k = (size_t) blockIdx.x * BEHZ_THREADS + threadIdx.x;
+    double v = 0.0;
+    Acc128 ip{0, 0};
+    for (int i = 0; i < a.l; i++) {
+        const u64 q = a.mod_q[i].q;
+        const u64 y = mul_shoup(a.x[(size_t) i * a.n + k], a.q_hinv[i], q);
+        ip.mac(y, a.mat[i]);
+        v = __dadd_rn(v, __ddiv_rn((double) y, (double) q));   // IEEE quotient then sum, as the reference compiles it
+    }
+    const u64 rv = (u64) round(v);
+    u64 r = sub_mod(barrett128(ip.lo, ip.hi, a.tm), mul_mod(barrett128(rv, 0, a.tm), a.q_mod_t, a.tm), a.tm.q);
+    if (a.fix != 1) r = mul_mod(r, a.fix, a.tm);
+    a.out[k] = r;
+}
+
 } // namespace pfhe

@@ -265,6 +265,14 @@ int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const
     else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
     API_END
 }
+int pfhe_decrypt(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, const uint64_t *secret_key_array,
+                 uint64_t correction_factor, uint64_t *destination, void *stream) {
+    API_BEGIN
+    require(e && ct && destination && (size == 1 || secret_key_array), "null pointer");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.decrypt(l, U(ct), (int) size, U(secret_key_array), correction_factor, U(destination), S(stream));
+    API_END
+}
 int pfhe_find_levels_to_drop(pfhe_engine *e, size_t multiplicative_depth, int is_key_switch, int is_asymmetric,
                              int *levels) {
     API_BEGIN

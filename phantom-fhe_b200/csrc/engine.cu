@@ -1380,6 +1380,120 @@ void Engine::keyswitch_leveled(u64 *ct, const u64 *c2, const u64 *const *evk, in
     check_launch("k_expand_add");
 }
 
+const Decrypt &Engine::decrypt_tables(int l) {
+    if (l < 1 || l > size_Q_ || t_ <= 1) throw std::invalid_argument("decryption needs a plain modulus");
+    if ((int) dec_.size() <= size_Q_) dec_.resize(size_Q_ + 1);
+    if (dec_[l]) return *dec_[l];
+    auto d = std::make_unique<Decrypt>();
+    d->l = l;
+    const std::vector<u64> Q(primes_.begin(), primes_.begin() + l);
+    const u64 t = t_;
+    std::vector<Tw> q_hinv(l), tg(l);
+    std::vector<u64> q_to_t(l), mt(l), mtB(l), q_to_tg((size_t) 2 * l);
+    std::vector<double> fr(l), frB(l);
+    u64 qmax = 0;
+    for (int i = 0; i < size_Q_; i++) qmax = std::max(qmax, primes_[i]);
+    auto bits = [](u64 v) { return v ? 64 - __builtin_clzll(v) : 0; };
+    const int qMSB = bits(qmax), sizeQMSB = bits((u64) l), tMSB = bits(t);
+    d->hf = qMSB >> 1;
+    d->large = qMSB + sizeQMSB >= 52;
+    d->lazy = d->large ? (d->hf + tMSB + sizeQMSB) < 52 : (qMSB + tMSB + sizeQMSB) < 52;
+    if (scheme_ == Scheme::bfv) {
+        d->gamma = hm::create_primes(n_, std::vector<int>{61}).front();   // get_primes(n, 61, 1)[0] (rns.cu:333-334)
+        const u64 g = d->gamma;
+        d->ninv_t = (t - hm::invmod(hm::product_mod(Q, -1, t), t)) % t;
+        d->ninv_g = (g - hm::invmod(hm::product_mod(Q, -1, g), g)) % g;
+        d->inv_gamma_t = hm::invmod(g % t, t);
+    }
+    for (int i = 0; i < l; i++) {
+        const u64 qi = Q[i], hinv = hm::invmod(hm::product_mod(Q, i, qi), qi);
+        q_hinv[i] = make_tw(hinv, qi);
+        q_to_t[i] = hm::product_mod(Q, i, t);
+        unsigned __int128 w = (unsigned __int128) t * hinv;
+        mt[i] = (u64) ((w / qi) % t);
+        fr[i] = (double) (u64) (w % qi) / (double) qi;
+        const u64 hb = (u64) (((unsigned __int128) hinv << d->hf) % qi);
+        w = (unsigned __int128) t * hb;
+        mtB[i] = (u64) ((w / qi) % t);
+        frB[i] = (double) (u64) (w % qi) / (double) qi;
+        if (d->gamma) {
+            tg[i] = make_tw(hm::mulmod(t % qi, d->gamma % qi, qi), qi);
+            q_to_tg[i] = q_to_t[i];
+            q_to_tg[(size_t) l + i] = hm::product_mod(Q, i, d->gamma);
+        }
+    }
+    d->q_mod_t = hm::product_mod(Q, -1, t);
+    d->q_hinv.upload(q_hinv), d->q_to_t.upload(q_to_t);
+    d->mt.upload(mt), d->mtB.upload(mtB), d->fr.upload(fr), d->frB.upload(frB);
+    if (d->gamma) d->tg_mod_q.upload(tg), d->q_to_tg.upload(q_to_tg);
+    dec_[l] = std::move(d);
+    return *dec_[l];
+}
+
+static Modulus host_modulus(u64 q) {
+    const hm::BarrettRatio r = hm::barrett_ratio(q);
+    return Modulus{q, r.lo, r.hi};
+}
+
+// PhantomSecretKey::decrypt (reference src/secretkey.cu:533-691)
+void Engine::decrypt(int l, const u64 *ct, int size, const u64 *sk_pow, u64 correction_factor, u64 *out, cudaStream_t st) {
+    if (size < 1 || size > MXN_MAX + 1) throw std::invalid_argument("ciphertext size is not supported");
+    const size_t pl = (size_t) l * n_, pk = (size_t) size_QP_ * n_;
+    const dim3 gl((unsigned) (n_ / (2 * BEHZ_THREADS)), l), g1((unsigned) (n_ / BEHZ_THREADS));
+    if (scheme_ == Scheme::ckks) {   // c_0 + sum c_k s^k, NTT form (ckks_decrypt :533-569)
+        launch_pdl(k_decrypt_inner, gl, BEHZ_THREADS, 0, st, out, ct, ct + pl, pl, sk_pow, pk, size - 1,
+                   (const Modulus *) d_mod_.p, n_);
+        check_launch("k_decrypt_inner");
+        return;
+    }
+    const Decrypt &d = decrypt_tables(l);
+    const Modulus tm = host_modulus(t_);
+    u64 *acc = ws_.tmp.p;   // [l][n]
+    LimbVec v;
+    for (int i = 0; i < l; i++) v.push(i, i);
+    if (scheme_ == Scheme::bgv) {   // bgv_decrypt :638-691
+        launch_pdl(k_decrypt_inner, gl, BEHZ_THREADS, 0, st, acc, ct, ct + pl, pl, sk_pow, pk, size - 1,
+                   (const Modulus *) d_mod_.p, n_);
+        check_launch("k_decrypt_inner");
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_inv_list(acc, acc, ll, nullptr, 0, st); });
+        u64 fix = 1;
+        if (correction_factor != 1) {
+            if (std::gcd(correction_factor % t_, t_) != 1) throw std::logic_error("invalid correction factor");
+            fix = hm::invmod(correction_factor % t_, t_);
+        }
+        ExactConvertArgs a{acc, out, d.q_hinv.p, d.q_to_t.p, d_mod_.p, tm, d.q_mod_t, fix, l, n_};
+        launch_pdl(k_exact_convert_t, g1, BEHZ_THREADS, 0, st, a);
+        check_launch("k_exact_convert_t");
+        return;
+    }
+    // bfv_decrypt :571-636: c_k to NTT form, inner product with the key powers, back, + c_0, scale and round
+    u64 *cn = ws_.t_mod_up.p;   // [size-1][l][n] transformed copies
+    if (size > 1) {
+        if ((size_t) (size - 1) * pl > ws_.t_mod_up.count) throw std::invalid_argument("ciphertext size is not supported");
+        LimbVec vv;
+        for (int k = 0; k < size - 1; k++)
+            for (int i = 0; i < l; i++) vv.push(k * l + i, i);
+        run_chunks(vv, rowq_, [&](const LimbList &ll, size_t) { ntt_fwd_list(cn, ct + pl, ll, st); });
+        launch_pdl(k_decrypt_inner, gl, BEHZ_THREADS, 0, st, acc, (const u64 *) nullptr, (const u64 *) cn, pl, sk_pow, pk,
+                   size - 1, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_decrypt_inner");
+        run_chunks(v, rowq_, [&](const LimbList &ll, size_t) { ntt_inv_list(acc, acc, ll, nullptr, 0, st); });
+    } else {
+        PFHE_CUDA(cudaMemsetAsync(acc, 0, pl * 8, st));
+    }
+    if (mul_tech_ == 1) {
+        const Modulus gm = host_modulus(d.gamma);
+        BehzDecryptArgs a{acc, ct, out, d.tg_mod_q.p, d.q_hinv.p, d.q_to_tg.p, d_mod_.p, tm, gm,
+                          d.ninv_t, d.ninv_g, d.inv_gamma_t, l, n_};
+        launch_pdl(k_behz_decrypt, g1, BEHZ_THREADS, 0, st, a);
+        check_launch("k_behz_decrypt");
+    } else {
+        HpsDecryptArgs a{acc, ct, out, d.mt.p, d.mtB.p, d.fr.p, d.frB.p, d_mod_.p, tm, l, d.large, d.lazy, d.hf, n_};
+        launch_pdl(k_hps_decrypt, g1, BEHZ_THREADS, 0, st, a);
+        check_launch("k_hps_decrypt");
+    }
+}
+
 // FindLevelsToDrop (reference src/evaluate.cu:550-643), same double-precision formulas in the same order
 int Engine::find_levels_to_drop(size_t multiplicativeDepth, bool isKeySwitch, bool isAsymmetric) {
     if (scheme_ != Scheme::bfv || mul_tech_ != 4)

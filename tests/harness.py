@@ -60,6 +60,7 @@ def oracle():
         o.orc_multiply_relin.argtypes = [vp, ctypes.c_int, u64p, u64p, u64p, u64p]
         o.orc_hps_aux.argtypes = [vp, u64p, i32p]
         o.orc_bfv_multiply_hps.argtypes = [vp, u64p, u64p, u64p]
+        o.orc_decrypt.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.c_uint64, u64p]
         o.orc_bfv_multiply_hps_overq.argtypes = [vp, u64p, u64p, u64p, ctypes.c_int]
         o.orc_bfv_keyswitch_leveled.argtypes = [vp, u64p, u64p, u64p, ctypes.c_int, ctypes.c_int]
         o.orc_bfv_multiply_relin_hps_overq.argtypes = [vp, u64p, u64p, u64p, u64p, ctypes.c_int]
@@ -120,6 +121,9 @@ def reference():
         r.ref_ntt.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
         r.ref_multiply_relin.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
         r.ref_multiply.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
+        if hasattr(r, "ref_decrypt"):
+            r.ref_secret_key.argtypes = [vp, u64p]
+            r.ref_decrypt.argtypes = [vp, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.c_uint64, u64p]
         if hasattr(r, "ref_multiply_deg"):
             r.ref_multiply_deg.argtypes = [vp, ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int,
                                            u64p]

@@ -756,6 +756,92 @@ def test_bfv_multiply_against_unmodified_reference(mul_tech):
             r.ref_destroy(h)
 
 
+def _sk_powers(ps, s1, count):
+    """s, s^2, ... (NTT form, key level) from the first power, like compute_secret_key_array (secretkey.cu:196-230)"""
+    o = H.oracle()
+    kc = o.orc_create(ps.scheme, ps.n, P(ps.primes), ps.size_QP, 0, ps.t)   # every limb a data limb: poly_mul over all
+    pows = [s1.copy()]
+    for _ in range(count - 1):
+        nxt = np.zeros_like(s1)
+        o.orc_poly_mul(kc, P(pows[-1]), P(s1), P(nxt), ps.size_QP)
+        pows.append(nxt)
+    o.orc_destroy(kc)
+    return np.stack(pows)
+
+
+@pytest.mark.parametrize("scheme,mul_tech,cfg", [
+    (3, 0, dict(n=4096, l=4, alpha=2)), (1, 0, dict(n=4096, l=3, alpha=1)), (2, 1, dict(n=4096, l=3, alpha=1, qbits=36, pbits=42)),
+    (2, 2, dict(n=4096, l=3, alpha=1, qbits=36, pbits=42)), (2, 2, dict(n=8192, l=4, alpha=1, qbits=50, pbits=60)),
+    (2, 1, dict(n=8192, l=4, alpha=1, qbits=50, pbits=60)), (2, 3, dict(n=4096, l=5, alpha=2, qbits=44, pbits=60))])
+def test_decrypt(scheme, mul_tech, cfg):
+    """pfhe_decrypt (PhantomSecretKey::decrypt, secretkey.cu:533-723) vs the oracle: ciphertexts of size 2 and 3, the top
+    level and one level down, random words (decryption is defined on any words) and, for BGV, a correction factor."""
+    ps = H.params_small(scheme=scheme, t=65537 if scheme != 3 else 0, **cfg)
+    ctx = make_bfv_context(ps, mul_tech=pf.mul_tech_type(mul_tech)) if scheme == 2 else make_context(ps)
+    o, oc = H.oracle(), ps.octx()
+    n = ps.n
+    rng = np.random.default_rng(scheme * 7 + mul_tech)
+    s1 = np.stack([rng.integers(0, int(p), n, dtype=np.uint64) for p in ps.primes])
+    sk = _sk_powers(ps, s1, 2)
+    d_sk = dev(sk)
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    for chain_index in (1, 2):
+        l = ps.size_Q - (chain_index - 1)
+        for size, cf in ((2, 1), (3, 1), (1, 1)) + (((2, 5),) if scheme == 1 else ()):
+            ct = np.stack([np.stack([rng.integers(0, int(ps.primes[i]), n, dtype=np.uint64) for i in range(l)])
+                           for _ in range(size)])
+            shape = (l, n) if scheme == 3 else (n,)
+            want = np.zeros(shape, dtype=np.uint64)
+            assert o.orc_decrypt(oc, l, P(ct), size, P(sk), mul_tech, cf, P(want)) == 0
+            d_ct, d_out = dev(ct), torch.zeros(shape, dtype=torch.int64, device="cuda")
+            pf.check(pf.lib.pfhe_decrypt(ctx._h, chain_index, d_ct.data_ptr(), size, d_sk.data_ptr(), cf, d_out.data_ptr(), st))
+            assert np.array_equal(host(d_out), want), f"decrypt scheme {scheme} tech {mul_tech} level {chain_index} size {size}"
+
+
+@pytest.mark.parametrize("scheme,mul_tech", [(3, 0), (1, 0), (2, 1), (2, 2)])
+def test_decrypt_against_unmodified_reference(scheme, mul_tech):
+    """The reference's own secret key (exported through PhantomSecretKey::save) and its decrypt on caller-supplied
+    ciphertext words vs the engine and the oracle: N=2^14 BFV bench set / N=2^13 sets for CKKS and BGV."""
+    r = H.reference()
+    if r is None or not hasattr(r, "ref_decrypt"):
+        pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    if scheme == 2:
+        ps = H.params_bfv_bench(0)
+    else:
+        ps = H.params_small(8192, l=4, alpha=2, scheme=scheme, t=65537 if scheme == 1 else 0)
+    h = r.ref_create(scheme, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, mul_tech, None, 0, float(2 ** 30), 1)
+    assert h, r.ref_last_error()
+    try:
+        n = ps.n
+        s1 = np.zeros((ps.size_QP, n), dtype=np.uint64)
+        assert r.ref_secret_key(h, P(s1)) == 0, r.ref_last_error()
+        sk = _sk_powers(ps, s1, 2)
+        ctx = make_bfv_context(ps, mul_tech=pf.mul_tech_type(mul_tech)) if scheme == 2 else make_context(ps)
+        d_sk = dev(sk)
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        rng = np.random.default_rng(scheme)
+        l = ps.size_Q
+        for size, cf in ((2, 1), (3, 1)) + (((2, 3),) if scheme == 1 else ()):
+            ct = np.stack([np.stack([rng.integers(0, int(ps.primes[i]), n, dtype=np.uint64) for i in range(l)])
+                           for _ in range(size)])
+            shape = (l, n) if scheme == 3 else (n,)
+            want = np.zeros(shape, dtype=np.uint64)
+            assert r.ref_decrypt(h, 1, P(ct), size, cf, P(want)) == 0, r.ref_last_error()
+            mine = np.zeros(shape, dtype=np.uint64)
+            assert H.oracle().orc_decrypt(ps.octx(), l, P(ct), size, P(sk), mul_tech, cf, P(mine)) == 0
+            assert np.array_equal(mine, want), f"oracle decrypt vs reference, size {size}"
+            d_ct, d_out = dev(ct), torch.zeros(shape, dtype=torch.int64, device="cuda")
+            pf.check(pf.lib.pfhe_decrypt(ctx._h, 1, d_ct.data_ptr(), size, d_sk.data_ptr(), cf, d_out.data_ptr(), st))
+            assert np.array_equal(host(d_out), want), f"engine decrypt vs reference, size {size}"
+            # the host mirror: secret key object computing its own powers (compute_secret_key_array)
+            key = pf.PhantomSecretKey(ctx, s1)
+            c = pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=(scheme != 2))
+            c.correction_factor = cf
+            assert np.array_equal(host(key.decrypt(ctx, c)), want), "PhantomSecretKey.decrypt mirror"
+    finally:
+        r.ref_destroy(h)
+
+
 @pytest.mark.parametrize("scheme", [3, 1])
 def test_hoisting(scheme):
     ps = H.params_small(4096, l=5, alpha=2, scheme=scheme, t=65537 if scheme == 1 else 0)

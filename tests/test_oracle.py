@@ -341,3 +341,64 @@ def test_bfv_multiply_decrypts_to_the_plaintext_product(tech):
     assert nb.value in (lq + 1, lq + 2)
     assert int(bsk[nb.value - 1]) == max(int(v) for v in bsk[:nb.value])
     assert all(int(v) % (2 * n) == 1 and int(v).bit_length() == 61 for v in bsk[:nb.value])
+
+
+@pytest.mark.parametrize("scheme,mul_tech", [(3, 0), (1, 0), (2, 1), (2, 2)])
+def test_decrypt_recovers_the_message(scheme, mul_tech):
+    """orc_decrypt (secretkey.cu:533-691): symmetric encryptions (c0 = -(a s) + payload, c1 = a) built here with a ternary
+    secret decrypt to the message -- CKKS: the NTT-form plaintext itself; BGV: m from m + t e; BFV: m from Delta m + e
+    through the BEHZ and the HPS scale-and-round; a size-3 ciphertext uses s^2."""
+    o = H.oracle()
+    t = 65537 if scheme != 3 else 0
+    ps = H.ParamSet("dec", 4096, [40, 40, 40, 50], 1, scheme=scheme, t=t)
+    oc, n, l = ps.octx(), ps.n, ps.size_Q
+    rng = np.random.default_rng(scheme * 10 + mul_tech)
+    idx_all = (ctypes.c_int * ps.size_QP)(*range(ps.size_QP))
+    idx = (ctypes.c_int * l)(*range(l))
+    sec = rng.integers(-1, 2, n)
+    s1 = np.stack([np.array([(int(v)) % int(p) for v in sec], dtype=np.uint64) for p in ps.primes])   # key level
+    o.orc_ntt_forward(oc, P(s1), ps.size_QP, idx_all)
+    s2 = np.stack([np.array([(int(x) * int(x)) % int(p) for x in s1[i]], dtype=np.uint64) for i, p in enumerate(ps.primes)])
+    sk_pow = np.stack([s1, s2])
+    Q = 1
+    for p in ps.primes[:l]:
+        Q *= int(p)
+    m = rng.integers(0, t if t else 1 << 30, n)
+    e = rng.integers(-4, 5, n)
+    if scheme == 3:
+        payload = [int(v) for v in m]
+    elif scheme == 1:
+        payload = [int(v) + t * int(x) for v, x in zip(m, e)]
+    else:
+        payload = [(Q // t) * int(v) + int(x) for v, x in zip(m, e)]
+    pay = np.stack([np.array([v % int(p) for v in payload], dtype=np.uint64) for p in ps.primes[:l]])
+    a = np.stack([rng.integers(0, int(p), n, dtype=np.uint64) for p in ps.primes[:l]])   # NTT form
+    pay_ntt = pay.copy()
+    o.orc_ntt_forward(oc, P(pay_ntt), l, idx)
+    c0 = np.stack([np.array([(int(pv) - int(av) * int(sv)) % int(p) for pv, av, sv in zip(pay_ntt[i], a[i], s1[i])],
+                            dtype=np.uint64) for i, p in enumerate(ps.primes[:l])])
+    ct = np.stack([c0, a])
+    if scheme == 2:   # BFV ciphertexts live in coefficient form
+        for k in range(2):
+            o.orc_ntt_inverse(oc, P(ct[k]), l, idx)
+    out = np.zeros((l, n) if scheme == 3 else (n,), dtype=np.uint64)
+    assert o.orc_decrypt(oc, l, P(ct), 2, P(sk_pow), mul_tech, 1, P(out)) == 0
+    if scheme == 3:
+        assert np.array_equal(out, pay_ntt)
+    else:
+        assert [int(v) for v in out] == [int(v) for v in m]
+    # size 3: (c0 - b s^2, a, b) decrypts to the same message
+    b = np.stack([rng.integers(0, int(p), n, dtype=np.uint64) for p in ps.primes[:l]])
+    c0b = np.stack([np.array([(int(cv) - int(bv) * int(sv)) % int(p) for cv, bv, sv in zip(c0[i], b[i], s2[i])],
+                             dtype=np.uint64) for i, p in enumerate(ps.primes[:l])])
+    ct3 = np.stack([c0b, a, b])
+    if scheme == 2:
+        for k in range(3):
+            o.orc_ntt_inverse(oc, P(ct3[k]), l, idx)
+    out3 = np.zeros_like(out)
+    assert o.orc_decrypt(oc, l, P(ct3), 3, P(sk_pow), mul_tech, 1, P(out3)) == 0
+    assert np.array_equal(out3, out)
+    if scheme == 1:   # BGV correction factor: the decryption is multiplied by its inverse mod t
+        outc = np.zeros_like(out)
+        assert o.orc_decrypt(oc, l, P(ct), 2, P(sk_pow), 0, 3, P(outc)) == 0
+        assert [int(v) for v in outc] == [(int(v) * pow(3, -1, t)) % t for v in m]
