@@ -363,6 +363,52 @@ int ref_decrypt(void *p, size_t chain_index, const uint64_t *ct, size_t size, ui
     SHIM_CATCH
 }
 
+/* PhantomCiphertext::save of caller-supplied words and metadata; returns the stream length (or -1), bytes in out */
+long ref_save_ct(void *p, size_t chain_index, const uint64_t *ct, size_t size, double scale, size_t noise_deg,
+                 unsigned char *out, size_t cap) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto c = make_ct(h, chain_index, size, ct, h->scheme != scheme_type::bfv);
+    c.set_scale(scale);
+    c.SetNoiseScaleDeg(noise_deg);
+    std::stringstream ss;
+    c.save(ss);
+    const std::string blob = ss.str();
+    if (blob.size() > cap) throw std::invalid_argument("buffer too small");
+    std::memcpy(out, blob.data(), blob.size());
+    return (long) blob.size();
+    SHIM_CATCH
+}
+/* PhantomCiphertext::load of a caller-supplied stream: words to out, {chain_index, size, N, l, noise_deg, ntt} to meta */
+int ref_load_ct(const unsigned char *bytes, size_t len, uint64_t *out, size_t *meta, double *scale) {
+    SHIM_TRY
+    std::stringstream ss(std::string(reinterpret_cast<const char *>(bytes), len));
+    PhantomCiphertext c;
+    c.load(ss);
+    meta[0] = c.chain_index(), meta[1] = c.size(), meta[2] = c.poly_modulus_degree(), meta[3] = c.coeff_modulus_size();
+    meta[4] = c.GetNoiseScaleDeg(), meta[5] = c.is_ntt_form();
+    *scale = c.scale();
+    fetch_ct(c, out);
+    return 0;
+    SHIM_CATCH
+}
+/* save() of the context's own keys: which = 0 relin key, 1 Galois key, 2 secret key; returns the length */
+long ref_save_key(void *p, int which, unsigned char *out, size_t cap) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    std::stringstream ss;
+    if (which == 0) h->rlk->save(ss);
+    else if (which == 1) h->glk->save(ss);
+    else h->sk->save(ss);
+    const std::string blob = ss.str();
+    if (out) {
+        if (blob.size() > cap) throw std::invalid_argument("buffer too small");
+        std::memcpy(out, blob.data(), blob.size());
+    }
+    return (long) blob.size();
+    SHIM_CATCH
+}
+
 /* stage-wise key-switch taps (eval_key_switch.cu:95-182) for differential debugging */
 int ref_modup(void *p, size_t chain_index, const uint64_t *c2, uint64_t *t_mod_up) {
     SHIM_TRY

@@ -13,6 +13,7 @@ import enum
 import numpy as np
 import torch
 
+from . import serial
 from ._lib import lib, check, u64p, u32p, i32p
 
 
@@ -175,6 +176,21 @@ class PhantomCiphertext:
     def size(self):
         return 0 if self.data is None else self.data.shape[0]
 
+    def save(self, stream):
+        """PhantomCiphertext::save (include/ciphertext.h:173-190): byte-identical stream."""
+        serial.write_ciphertext(stream, self.to_host(), self.chain_index, self.scale, self.correction_factor,
+                                self.noise_scale_deg, self.is_ntt_form, self.is_asymmetric)
+
+    @classmethod
+    def load(cls, context, stream):
+        """PhantomCiphertext::load (include/ciphertext.h:192-213)."""
+        words, h = serial.read_ciphertext(stream)
+        if words.shape[2] != context.poly_degree or words.shape[1] != context.coeff_modulus_size(h["chain_index"]):
+            raise ValueError("ciphertext stream does not belong to this context")
+        c = cls(context, _to_dev(words, context.device), h["chain_index"], h["scale"], h["is_ntt_form"])
+        c.correction_factor, c.noise_scale_deg, c.is_asymmetric = h["correction_factor"], h["noise_scale_deg"], h["is_asymmetric"]
+        return c
+
     def coeff_modulus_size(self):
         return self.data.shape[1]
 
@@ -195,6 +211,20 @@ class PhantomSecretKey:
 
     def secret_key_array(self):
         return self._pow
+
+    def save(self, stream):
+        """PhantomSecretKey::save (include/secretkey.h:346-364): every power computed so far."""
+        torch.cuda.current_stream().synchronize()
+        serial.write_secret_key(stream, self._pow.cpu().numpy().view(np.uint64))
+
+    @classmethod
+    def load(cls, context, stream):
+        p = serial.read_secret_key(stream)
+        if p.shape[1] != context.size_QP or p.shape[2] != context.poly_degree:
+            raise ValueError("secret key stream does not belong to this context")
+        k = cls(context, p[0])
+        k._pow = _to_dev(p, context.device)
+        return k
 
     def _compute_secret_key_array(self, context, max_power):
         """compute_secret_key_array (src/secretkey.cu:196-230): s^k = s^(k-1) * s, limb-wise, all key-level limbs."""
@@ -232,6 +262,18 @@ class PhantomRelinKey:
     def public_keys_ptr(self):
         return _ptr(self._ptrs)
 
+    def _host_digits(self):
+        torch.cuda.current_stream().synchronize()
+        return [d.cpu().numpy().view(np.uint64) for d in self.digits]
+
+    def save(self, stream):
+        """PhantomRelinKey::save (include/secretkey.h:129-140)."""
+        serial.write_relin_key(stream, self._host_digits())
+
+    @classmethod
+    def load(cls, context, stream):
+        return cls(context, serial.read_relin_key(stream))
+
 
 class PhantomGaloisKey:
     """Relin keys indexed like the context's Galois elements (include/secretkey.h:168-192)."""
@@ -241,6 +283,14 @@ class PhantomGaloisKey:
 
     def get_relin_keys(self, index):
         return self.relin_keys[index]
+
+    def save(self, stream):
+        """PhantomGaloisKey::save (include/secretkey.h:194-205)."""
+        serial.write_galois_key(stream, [k._host_digits() for k in self.relin_keys])
+
+    @classmethod
+    def load(cls, context, stream):
+        return cls(context, serial.read_galois_key(stream))
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -121,6 +121,15 @@ def reference():
         r.ref_ntt.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
         r.ref_multiply_relin.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
         r.ref_multiply.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
+        if hasattr(r, "ref_save_ct"):
+            u8p = ctypes.POINTER(ctypes.c_ubyte)
+            r.ref_save_ct.restype = ctypes.c_long
+            r.ref_save_ct.argtypes = [vp, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.c_double, ctypes.c_size_t, u8p,
+                                      ctypes.c_size_t]
+            r.ref_load_ct.argtypes = [u8p, ctypes.c_size_t, u64p, ctypes.POINTER(ctypes.c_size_t),
+                                      ctypes.POINTER(ctypes.c_double)]
+            r.ref_save_key.restype = ctypes.c_long
+            r.ref_save_key.argtypes = [vp, ctypes.c_int, u8p, ctypes.c_size_t]
         if hasattr(r, "ref_decrypt"):
             r.ref_secret_key.argtypes = [vp, u64p]
             r.ref_decrypt.argtypes = [vp, ctypes.c_size_t, u64p, ctypes.c_size_t, ctypes.c_uint64, u64p]

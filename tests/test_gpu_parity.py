@@ -842,6 +842,70 @@ def test_decrypt_against_unmodified_reference(scheme, mul_tech):
         r.ref_destroy(h)
 
 
+def test_serialisation_against_unmodified_reference():
+    """Streams written by the reference's own save() (ciphertext, relinearisation key, Galois key, secret key) are read by
+    the host mirror and re-written byte for byte; a ciphertext stream written here is loaded by the reference."""
+    import io
+    r = H.reference()
+    if r is None or not hasattr(r, "ref_save_ct"):
+        pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    ps = H.params_small(4096, l=4, alpha=2)   # digits of equal size (the reference's kernels fault on l=3, alpha=2)
+    steps = (ctypes.c_int * 2)(1, -2)
+    h = r.ref_create(3, ps.n, P(ps.primes), ps.size_QP, ps.size_P, 0, 0, steps, 2, float(2 ** 30), 1)
+    assert h, r.ref_last_error()
+    try:
+        ctx = make_context(ps, [1, -2])
+        l, n = ps.limbs(), ps.n
+        ct = np.concatenate([H.ciphertext(ps, 5), H.ciphertext(ps, 6)[:1]])   # size 3
+        cap = 58 + ct.size * 8 + 64
+        buf = (ctypes.c_ubyte * cap)()
+        ln = r.ref_save_ct(h, 1, P(ct), 3, float(2 ** 37), 2, buf, cap)
+        assert ln == 58 + ct.size * 8, r.ref_last_error()
+        ref_bytes = bytes(buf[:ln])
+        c = pf.PhantomCiphertext.load(ctx, io.BytesIO(ref_bytes))
+        assert c.size() == 3 and c.chain_index == 1 and c.scale == float(2 ** 37) and c.noise_scale_deg == 2
+        assert np.array_equal(c.to_host(), ct)
+        out = io.BytesIO()
+        c.save(out)
+        assert out.getvalue() == ref_bytes, "ciphertext stream differs from the reference's"
+        # the reference loads what the mirror wrote
+        mine = pf.PhantomCiphertext.from_host(ctx, ct[:2], scale=3.5)
+        mine.noise_scale_deg = 4
+        out = io.BytesIO()
+        mine.save(out)
+        blob = out.getvalue()
+        words = np.zeros((2, l, n), dtype=np.uint64)
+        meta = (ctypes.c_size_t * 6)()
+        scale = ctypes.c_double()
+        arr = (ctypes.c_ubyte * len(blob)).from_buffer_copy(blob)
+        assert r.ref_load_ct(arr, len(blob), P(words), meta, ctypes.byref(scale)) == 0, r.ref_last_error()
+        assert list(meta) == [1, 2, n, l, 4, 1] and scale.value == 3.5 and np.array_equal(words, ct[:2])
+        # keys: relinearisation key, Galois key (two elements), secret key
+        for which, cls in ((0, pf.PhantomRelinKey), (1, pf.PhantomGaloisKey), (2, pf.PhantomSecretKey)):
+            ln = r.ref_save_key(h, which, None, 0)
+            assert ln > 0, r.ref_last_error()
+            kb = (ctypes.c_ubyte * ln)()
+            assert r.ref_save_key(h, which, kb, ln) == ln
+            ref_bytes = bytes(kb)
+            key = cls.load(ctx, io.BytesIO(ref_bytes))
+            out = io.BytesIO()
+            key.save(out)
+            assert out.getvalue() == ref_bytes, f"key stream {which} differs from the reference's"
+        # the loaded relinearisation key is the one the reference uses: same HMult+Relin words
+        ln = r.ref_save_key(h, 0, None, 0)
+        kb = (ctypes.c_ubyte * ln)()
+        r.ref_save_key(h, 0, kb, ln)
+        rlk = pf.PhantomRelinKey.load(ctx, io.BytesIO(bytes(kb)))
+        a, b = H.ciphertext(ps, 1), H.ciphertext(ps, 2)
+        want = np.zeros((2, l, n), dtype=np.uint64)
+        assert r.ref_multiply_relin(h, 1, P(a), P(b), P(want)) == 0, r.ref_last_error()
+        ca, cb = pf.PhantomCiphertext.from_host(ctx, a), pf.PhantomCiphertext.from_host(ctx, b)
+        pf.multiply_and_relin_inplace(ctx, ca, cb, rlk)
+        assert np.array_equal(ca.to_host(), want)
+    finally:
+        r.ref_destroy(h)
+
+
 @pytest.mark.parametrize("scheme", [3, 1])
 def test_hoisting(scheme):
     ps = H.params_small(4096, l=5, alpha=2, scheme=scheme, t=65537 if scheme == 1 else 0)

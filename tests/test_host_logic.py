@@ -4,6 +4,7 @@ import os
 import subprocess
 import sys
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -74,3 +75,40 @@ def test_two_rank_gloo_sharding(tmp_path):
     outs = [p.communicate(timeout=240)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+def test_serialisation_round_trip_and_layout():
+    """phantom-fhe_b200/serial.py: the reference's stream layouts (include/ciphertext.h:173-213, secretkey.h:129-219,346-390)
+    -- header bytes at their offsets, round trips of ciphertexts, relinearisation / Galois keys and secret keys, truncated
+    streams refused.  (Byte equality with streams written by the unmodified reference: tests/test_gpu_parity.py.)"""
+    import importlib.util
+    import io
+    import struct
+    spec = importlib.util.spec_from_file_location("pfhe_serial", os.path.join(ROOT, "phantom-fhe_b200", "serial.py"))
+    serial = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(serial)
+    rng = np.random.default_rng(0)
+    words = rng.integers(0, 1 << 60, (3, 2, 16), dtype=np.uint64)
+    buf = io.BytesIO()
+    serial.write_ciphertext(buf, words, 2, scale=2.0 ** 40, correction_factor=7, noise_scale_deg=3, is_ntt_form=True,
+                            is_asymmetric=True)
+    raw = buf.getvalue()
+    assert len(raw) == 58 + words.size * 8
+    assert struct.unpack_from("<QQQQ", raw, 0) == (2, 3, 16, 2)
+    assert struct.unpack_from("<d", raw, 32)[0] == 2.0 ** 40 and struct.unpack_from("<QQ", raw, 40) == (7, 3)
+    assert raw[56:58] == b"\x01\x01"
+    back, hdr = serial.read_ciphertext(io.BytesIO(raw))
+    assert np.array_equal(back, words) and hdr["chain_index"] == 2 and hdr["noise_scale_deg"] == 3 and hdr["is_asymmetric"]
+    with pytest.raises(ValueError):
+        serial.read_ciphertext(io.BytesIO(raw[:-8]))
+    keys = [[rng.integers(0, 1 << 50, (2, 3, 16), dtype=np.uint64) for _ in range(2)] for _ in range(3)]
+    buf = io.BytesIO()
+    serial.write_galois_key(buf, keys)
+    got = serial.read_galois_key(io.BytesIO(buf.getvalue()))
+    assert len(got) == 3 and all(np.array_equal(a, b) for ka, kb in zip(got, keys) for a, b in zip(ka, kb))
+    assert struct.unpack_from("<QQ", buf.getvalue(), 0) == (3, 2)   # key count, then dnum of the first key
+    pw = rng.integers(0, 1 << 50, (2, 3, 16), dtype=np.uint64)
+    buf = io.BytesIO()
+    serial.write_secret_key(buf, pw)
+    assert struct.unpack_from("<QQQ", buf.getvalue(), 0) == (2, 16, 3)
+    assert np.array_equal(serial.read_secret_key(io.BytesIO(buf.getvalue())), pw)
