@@ -308,7 +308,7 @@ def main():
         limbs_ntt = 64
         # 3 rotating buffers of 64 limbs (3 x 32 MiB, with the 20 MiB twiddle table > L2 in steady state)
         bufs = [torch.zeros(limbs_ntt * n, dtype=torch.int64, device="cuda") for _ in range(4)]
-        reps = 20
+        reps = 200
         turn = [0]
 
         def ntt_launch():
@@ -350,7 +350,7 @@ def main():
                 "peak_source": how, "traffic": traffic, "algorithmic_bytes": alg_bytes,
                 "launch_us": ntt_us, "limb_ntt_per_s": limbs_ntt / (ntt_us * 1e-6), "issue": issue,
                 "note": "not HBM-bound: 64-bit modular butterflies are bound by warp-instruction issue on sm_100a "
-                        "(FP64 and IMAD share the dispatch port, 2 clocks each; DESIGN.md 4.1, profiles/r1b_*)"}
+                        "(FP64 and IMAD share the dispatch port, 2 clocks each; DESIGN.md 4.1, profiles/r1c_*)"}
         if not args.no_cpu_baseline:
             cb = cpu_baseline(ps, a, b, rlk_h)
 
