@@ -130,6 +130,13 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
                             const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
                             void *stream);
+/* PhantomBatchEncoder::encode / decode for BFV / BGV (src/batchencoder.cu:62-118): `values` = count <= N slot values on
+ * the device (the reference copies its std::vector there first), `plain` = the [N] plaintext polynomial mod t,
+ * coefficient form.  Needs a batching plain modulus (prime, 1 mod 2N): the engine then keeps NTT tables for it
+ * (gpu_plain_tables).  Decode writes all N slots. */
+int pfhe_batch_encode(pfhe_engine *e, const uint64_t *values, size_t count, uint64_t *plain, void *stream);
+int pfhe_batch_decode(pfhe_engine *e, const uint64_t *plain, uint64_t *values, void *stream);
+
 /* PhantomSecretKey::decrypt (src/secretkey.cu:533-723: ckks_decrypt / bgv_decrypt / bfv_decrypt) -- the step after the
  * hot path.  encrypted = [size][l][n] at chain_index (CKKS / BGV: NTT form; BFV: coefficient form);
  * secret_key_array = PhantomSecretKey::secret_key_array(): the powers s, s^2, .. s^(size-1) of the secret key in NTT form,

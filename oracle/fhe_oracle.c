@@ -1621,6 +1621,51 @@ int orc_decrypt(const orc_ctx *c, int l, const u64 *ct, int size, const u64 *sk_
 }
 
 /* ------------------------------------------------------------------------------------------------------
+ * BFV / BGV batch encoder (PhantomBatchEncoder, reference src/batchencoder.cu): slot i lives at coefficient position
+ * index_map[i] of the NTT-form vector mod t (matrix representation: two rows of N/2 slots, generator 5), the plaintext
+ * is its inverse negacyclic NTT mod t.  t must be a prime = 1 mod 2N.
+ * ---------------------------------------------------------------------------------------------------- */
+static void batch_index_map(u64 n, u64 *map) { /* populate_matrix_reps_index_map, batchencoder.cu:26-49 */
+    int logn = 0;
+    while (((u64)1 << logn) < n) logn++;
+    u64 row = n >> 1, m = n << 1, pos = 1;
+    for (u64 i = 0; i < row; i++) {
+        map[i] = bitrev32((uint32_t)((pos - 1) >> 1), logn);
+        map[row | i] = bitrev32((uint32_t)((m - pos - 1) >> 1), logn);
+        pos = (pos * 5) & (m - 1);
+    }
+}
+int orc_batch_encode(u64 n, u64 t, const u64 *values, u64 count, u64 *plain) {
+    if (count > n) return -1;
+    orc_ctx *c = orc_create(ORC_SCHEME_CKKS, n, &t, 1, 0, 0); /* NTT tables mod t (gpu_plain_tables) */
+    if (!c) return -1;
+    u64 *map = (u64 *)malloc(n * 8);
+    batch_index_map(n, map);
+    for (u64 i = 0; i < n; i++) {
+        u64 v = i < count ? values[i] : 0;
+        plain[map[i]] = i < count ? v + (v >> 63) * t : 0; /* encode_gpu, batchencoder.cu:51-60 */
+    }
+    int zero = 0;
+    orc_ntt_inverse(c, plain, 1, &zero);
+    free(map);
+    orc_destroy(c);
+    return 0;
+}
+int orc_batch_decode(u64 n, u64 t, const u64 *plain, u64 *values) {
+    orc_ctx *c = orc_create(ORC_SCHEME_CKKS, n, &t, 1, 0, 0);
+    if (!c) return -1;
+    u64 *map = (u64 *)malloc(n * 8), *tmp = (u64 *)malloc(n * 8);
+    batch_index_map(n, map);
+    memcpy(tmp, plain, n * 8);
+    int zero = 0;
+    orc_ntt_forward(c, tmp, 1, &zero);
+    for (u64 i = 0; i < n; i++) values[i] = tmp[map[i]]; /* decode_gpu, batchencoder.cu:91-95 */
+    free(map); free(tmp);
+    orc_destroy(c);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------------
  * rescale / mod switch
  * ---------------------------------------------------------------------------------------------------- */
 void orc_rescale(const orc_ctx *c, int l, u64 *in, int size, u64 *out) {

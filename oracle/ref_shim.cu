@@ -409,6 +409,31 @@ long ref_save_key(void *p, int which, unsigned char *out, size_t cap) {
     SHIM_CATCH
 }
 
+/* PhantomBatchEncoder::encode / decode (batchencoder.cu:62-118): values[count] -> plain[n]; plain[n] -> values[n] */
+int ref_batch_encode(void *p, const uint64_t *values, size_t count, uint64_t *plain) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    PhantomBatchEncoder enc(*h->ctx);
+    std::vector<uint64_t> v(values, values + count);
+    PhantomPlaintext pt = enc.encode(*h->ctx, v);
+    cudaStreamSynchronize(cudaStreamPerThread);
+    cudaMemcpy(plain, pt.data(), h->n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    return 0;
+    SHIM_CATCH
+}
+int ref_batch_decode(void *p, const uint64_t *plain, uint64_t *values) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    PhantomBatchEncoder enc(*h->ctx);
+    std::vector<uint64_t> zeros(h->n, 0);
+    PhantomPlaintext pt = enc.encode(*h->ctx, zeros);   /* a plaintext object of the right shape */
+    cudaMemcpy(pt.data(), plain, h->n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    std::vector<uint64_t> out = enc.decode(*h->ctx, pt);
+    std::memcpy(values, out.data(), h->n * sizeof(uint64_t));
+    return 0;
+    SHIM_CATCH
+}
+
 /* stage-wise key-switch taps (eval_key_switch.cu:95-182) for differential debugging */
 int ref_modup(void *p, size_t chain_index, const uint64_t *c2, uint64_t *t_mod_up) {
     SHIM_TRY

@@ -200,6 +200,38 @@ class PhantomCiphertext:
         return c
 
 
+class PhantomBatchEncoder:
+    """PhantomBatchEncoder (include/batchencoder.h, src/batchencoder.cu): BFV / BGV slot packing over the plain modulus."""
+
+    def __init__(self, context):
+        if context.scheme not in (scheme_type.bfv, scheme_type.bgv):
+            raise ValueError("PhantomBatchEncoder only supports BFV/BGV scheme")
+        self._slots = context.poly_degree
+
+    def slot_count(self):
+        return self._slots
+
+    def encode(self, context, values_matrix):
+        """-> device plaintext [N] (coefficient form, residues mod t)"""
+        v = np.asarray(values_matrix)
+        if v.size > self._slots:
+            raise RuntimeError("values_matrix size is too large")
+        if v.dtype.kind == "i":
+            v = v.astype(np.int64).view(np.uint64)   # negative values go down as two's complement, like the reference's
+        v = np.ascontiguousarray(v, dtype=np.uint64)
+        d_in = _to_dev(v, context.device) if v.size else torch.zeros(1, dtype=torch.int64, device=context.device)
+        plain = torch.empty(self._slots, dtype=torch.int64, device=context.device)
+        check(lib.pfhe_batch_encode(context._h, _ptr(d_in), v.size, _ptr(plain), _stream()))
+        return plain
+
+    def decode(self, context, plain):
+        """-> numpy uint64 [N] slot values"""
+        out = torch.empty(self._slots, dtype=torch.int64, device=plain.device)
+        check(lib.pfhe_batch_decode(context._h, _ptr(plain), _ptr(out), _stream()))
+        torch.cuda.current_stream().synchronize()
+        return out.cpu().numpy().view(np.uint64)
+
+
 class PhantomSecretKey:
     """The decrypting half of PhantomSecretKey (include/secretkey.h:226-338): the secret key's powers in NTT form at the
     key level (secret_key_array()) and decrypt().  Key generation and encryption stay with the reference (SURVEY.md 8f);

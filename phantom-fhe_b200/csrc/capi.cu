@@ -265,6 +265,18 @@ int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const
     else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
     API_END
 }
+int pfhe_batch_encode(pfhe_engine *e, const uint64_t *values, size_t count, uint64_t *plain, void *stream) {
+    API_BEGIN
+    require(e && plain && (values || count == 0), "null pointer");
+    e->impl.batch_encode(U(values), count, U(plain), S(stream));
+    API_END
+}
+int pfhe_batch_decode(pfhe_engine *e, const uint64_t *plain, uint64_t *values, void *stream) {
+    API_BEGIN
+    require(e && plain && values, "null pointer");
+    e->impl.batch_decode(U(plain), U(values), S(stream));
+    API_END
+}
 int pfhe_decrypt(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, const uint64_t *secret_key_array,
                  uint64_t correction_factor, uint64_t *destination, void *stream) {
     API_BEGIN

@@ -221,6 +221,7 @@ void Engine::build_tables() {
     const bool allow_fp = !(env && env[0] == '0');
     rowq_ = primes_;
     if (t_ > 1) rowq_.push_back(t_);
+    batching_ = t_ > 1 && (t_ - 1) % (2 * n_) == 0 && (t_ >> 61) == 0 && hm::is_prime(t_);
     row_aux_ = (int) rowq_.size();
     if (scheme_ == Scheme::bfv && t_ > 1) {
         // BEHZ auxiliary base (rns.cu:400-420): 61-bit primes downwards from 2^61, the first is m_sk, the next
@@ -257,8 +258,9 @@ void Engine::build_tables() {
     is_fp_.assign(mod_rows_, 0);
     std::vector<double2> fpc(mod_rows_);
     for (int i = 0; i < mod_rows_; i++) {
-        // the plain modulus row has no NTT; BEHZ rows are 61-bit; Q, P and R rows below 2^46 run on the FP64 pipe
-        is_fp_[i] = !(t_ > 1 && i == size_QP_) && allow_fp && (rowq_[i] >> 46) == 0;
+        // BEHZ rows are 61-bit; Q, P and R rows below 2^46 run on the FP64 pipe; so does the plain-modulus row when it
+        // carries NTT tables (batching), because the NTT kernels pick the arithmetic from the modulus alone
+        is_fp_[i] = !(t_ > 1 && i == size_QP_ && !batching_) && allow_fp && (rowq_[i] >> 46) == 0;
         fpc[i] = make_double2((double) rowq_[i], 1.0 / (double) rowq_[i]);
     }
     for (int i = 0; i < size_QP_ && i < 128; i++)
@@ -274,7 +276,9 @@ void Engine::build_tables() {
         const u64 q = rowq_[i];
         const auto ratio = hm::barrett_ratio(q);
         mods[i] = Modulus{q, ratio.lo, ratio.hi};
-        if (t_ > 1 && i == size_QP_) continue;
+        // the row of the plain modulus gets NTT tables only when t supports batching (prime, 1 mod 2N): the BFV / BGV batch
+        // encoder transforms over it (gpu_plain_tables, reference src/context.cu); otherwise the row stays zero
+        if (t_ > 1 && i == size_QP_ && !batching_) continue;
         const u64 psi = hm::minimal_primitive_root(2 * n_, q);
         const u64 ipsi = hm::invmod(psi, q);
         Tw *f = tw.data() + (size_t) i * n_, *b = itw.data() + (size_t) i * n_;
@@ -1492,6 +1496,47 @@ void Engine::decrypt(int l, const u64 *ct, int size, const u64 *sk_pow, u64 corr
         launch_pdl(k_hps_decrypt, g1, BEHZ_THREADS, 0, st, a);
         check_launch("k_hps_decrypt");
     }
+}
+
+// PhantomBatchEncoder (reference src/batchencoder.cu): slots <-> plaintext polynomial mod t
+void Engine::batch_encode(const u64 *values, size_t count, u64 *plain, cudaStream_t st) {
+    if (scheme_ == Scheme::ckks) throw std::invalid_argument("PhantomBatchEncoder only supports BFV/BGV scheme");
+    if (!batching_) throw std::invalid_argument("the plain modulus does not support batching");
+    if (count > n_) throw std::logic_error("values_matrix size is too large");
+    ensure_batch_map();
+    launch_pdl(k_batch_encode, dim3((unsigned) (n_ / EW_THREADS)), EW_THREADS, 0, st, plain, values, count,
+               (const uint32_t *) d_batch_map_.p, t_);
+    check_launch("k_batch_encode");
+    LimbVec v;
+    v.push(0, size_QP_);   // the row of t
+    ntt_inv_list(plain, plain, single_list(v, rowq_), nullptr, 0, st);
+}
+
+void Engine::ensure_batch_map() {
+    if (!d_batch_map_.p) {
+        std::vector<uint32_t> map(n_);
+        const size_t row = n_ >> 1, m = n_ << 1;
+        u64 pos = 1;
+        for (size_t i = 0; i < row; i++) {   // populate_matrix_reps_index_map, batchencoder.cu:26-49
+            map[i] = hm::bit_reverse((uint32_t) ((pos - 1) >> 1), logn_);
+            map[row | i] = hm::bit_reverse((uint32_t) ((m - pos - 1) >> 1), logn_);
+            pos = (pos * 5) & (m - 1);
+        }
+        d_batch_map_.upload(map);
+    }
+}
+
+void Engine::batch_decode(const u64 *plain, u64 *values, cudaStream_t st) {
+    if (scheme_ == Scheme::ckks) throw std::invalid_argument("PhantomBatchEncoder only supports BFV/BGV scheme");
+    if (!batching_) throw std::invalid_argument("the plain modulus does not support batching");
+    ensure_batch_map();
+    u64 *tmp = ws_.tmp.p;
+    LimbVec v;
+    v.push(0, size_QP_);
+    ntt_fwd_list(tmp, plain, single_list(v, rowq_), st);
+    launch_pdl(k_batch_decode, dim3((unsigned) (n_ / EW_THREADS)), EW_THREADS, 0, st, values, (const u64 *) tmp,
+               (const uint32_t *) d_batch_map_.p);
+    check_launch("k_batch_decode");
 }
 
 // FindLevelsToDrop (reference src/evaluate.cu:550-643), same double-precision formulas in the same order

@@ -578,6 +578,25 @@ __global__ void __launch_bounds__(EW_THREADS) k_bgv_mod_t_divide(u64 *dst, const
     st2(dst + x, r[0], r[1]);
 }
 
+// PhantomBatchEncoder (reference src/batchencoder.cu:51-60,91-95): slot i <-> position map[i] of the NTT-form vector
+__global__ void __launch_bounds__(EW_THREADS) k_batch_encode(u64 *out, const u64 *in, size_t count, const uint32_t *map, u64 t) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t i = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
+    u64 v = 0;
+    if (i < count) {
+        v = in[i];
+        v += (v >> 63) * t;   // negative values arrive as two's complement
+    }
+    out[map[i]] = v;
+}
+__global__ void __launch_bounds__(EW_THREADS) k_batch_decode(u64 *out, const u64 *in, const uint32_t *map) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t i = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
+    out[i] = in[map[i]];
+}
+
 // dst[limb i] = src[perm...] helpers -------------------------------------------------------------------
 
 // apply_galois_ntt_permutation (reference src/galois.cu:11-18): dst[l][i] = src[l][perm[i]]

@@ -413,11 +413,11 @@ def test_multiply_3x3_against_unmodified_reference():
         r.ref_destroy(h)
 
 
-@pytest.mark.parametrize("lanes", [1, 2, 3])
-def test_multiply_relin_batch(lanes):
+@pytest.mark.parametrize("lanes,scheme", [(1, 3), (2, 3), (3, 3), (2, 1)])
+def test_multiply_relin_batch(lanes, scheme):
     """pfhe_multiply_and_relin_batch: independent pairs interleaved over the engine's lanes give, pair by pair, the
     words of the one-at-a-time op (and of the oracle); ragged counts, empty batch, mixed with single ops."""
-    ps = H.params_small(**KS_SETS[0])
+    ps = H.params_small(scheme=scheme, t=65537 if scheme == 1 else 0, **KS_SETS[0])
     ctx = make_context(ps)
     pf.check(pf.lib.pfhe_engine_set_lanes(ctx._h, lanes))
     assert pf.lib.pfhe_engine_lanes(ctx._h) == lanes
@@ -840,6 +840,51 @@ def test_decrypt_against_unmodified_reference(scheme, mul_tech):
             assert np.array_equal(host(key.decrypt(ctx, c)), want), "PhantomSecretKey.decrypt mirror"
     finally:
         r.ref_destroy(h)
+
+
+@pytest.mark.parametrize("scheme,n", [(2, 4096), (1, 8192), (2, 16384)])
+def test_batch_encoder(scheme, n):
+    """PhantomBatchEncoder mirror (pfhe_batch_encode / pfhe_batch_decode) vs the oracle and vs the reference's encoder:
+    full and short inputs, negative values, round trip; a plain modulus without batching support is refused."""
+    ps = H.params_small(n, l=3, alpha=1, scheme=scheme, t=65537 if n <= 16384 else 0)
+    ctx = make_bfv_context(ps) if scheme == 2 else make_context(ps)
+    o = H.oracle()
+    enc = pf.PhantomBatchEncoder(ctx)
+    rng = np.random.default_rng(n)
+    full = rng.integers(0, ps.t, n).astype(np.uint64)
+    short = np.array([7, -2, 0, 65536 - 1], dtype=np.int64)
+    r = H.reference()
+    h = None
+    if r is not None and hasattr(r, "ref_batch_encode"):
+        h = r.ref_create(scheme, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, 1, None, 0, 1.0, 0)
+        assert h, r.ref_last_error()
+    try:
+        for vals in (full, short):
+            u = np.ascontiguousarray(vals.astype(np.int64).view(np.uint64))
+            want = np.zeros(n, dtype=np.uint64)
+            assert o.orc_batch_encode(n, ps.t, P(u), u.size, P(want)) == 0
+            plain = enc.encode(ctx, vals)
+            assert np.array_equal(host(plain), want), "batch encode vs oracle"
+            slots = np.zeros(n, dtype=np.uint64)
+            assert o.orc_batch_decode(n, ps.t, P(want), P(slots)) == 0
+            got = enc.decode(ctx, plain)
+            assert np.array_equal(got, slots), "batch decode vs oracle"
+            assert np.array_equal(got[:u.size], np.array([int(v) % ps.t for v in vals.astype(np.int64)], dtype=np.uint64))
+            if h:
+                ref_plain, ref_slots = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+                assert r.ref_batch_encode(h, P(u), u.size, P(ref_plain)) == 0, r.ref_last_error()
+                assert np.array_equal(ref_plain, want), "oracle batch encode vs reference"
+                assert r.ref_batch_decode(h, P(want), P(ref_slots)) == 0, r.ref_last_error()
+                assert np.array_equal(ref_slots, slots), "oracle batch decode vs reference"
+    finally:
+        if h:
+            r.ref_destroy(h)
+    with pytest.raises(RuntimeError):
+        enc.encode(ctx, np.zeros(n + 1, dtype=np.uint64))
+    bad = H.params_small(n, l=3, alpha=1, scheme=scheme, t=65539)   # not 1 mod 2N
+    bctx = make_bfv_context(bad) if scheme == 2 else make_context(bad)
+    with pytest.raises(ValueError):
+        pf.PhantomBatchEncoder(bctx).encode(bctx, full)
 
 
 def test_serialisation_against_unmodified_reference():

@@ -402,3 +402,30 @@ def test_decrypt_recovers_the_message(scheme, mul_tech):
         outc = np.zeros_like(out)
         assert o.orc_decrypt(oc, l, P(ct), 2, P(sk_pow), 0, 3, P(outc)) == 0
         assert [int(v) for v in outc] == [(int(v) * pow(3, -1, t)) % t for v in m]
+
+
+def test_batch_encoder_is_slotwise():
+    """orc_batch_encode / decode (src/batchencoder.cu): decode(encode(v)) = v, and the product of two plaintext polynomials
+    mod (X^N + 1, t) decodes to the slot-wise product -- the property batching exists for."""
+    o = H.oracle()
+    n, t = 64, 65537 if False else 257   # 257 = 1 mod 128
+    rng = np.random.default_rng(3)
+    a, b = rng.integers(0, t, n).astype(np.uint64), rng.integers(0, t, n).astype(np.uint64)
+    pa, pb, back = np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64), np.zeros(n, dtype=np.uint64)
+    assert o.orc_batch_encode(n, t, P(a), n, P(pa)) == 0 and o.orc_batch_encode(n, t, P(b), n, P(pb)) == 0
+    assert o.orc_batch_decode(n, t, P(pa), P(back)) == 0 and np.array_equal(back, a)
+    prod = [0] * n
+    for i in range(n):
+        for j in range(n):
+            v = int(pa[i]) * int(pb[j])
+            if i + j >= n:
+                prod[i + j - n] -= v
+            else:
+                prod[i + j] += v
+    pp = np.array([v % t for v in prod], dtype=np.uint64)
+    assert o.orc_batch_decode(n, t, P(pp), P(back)) == 0
+    assert [int(v) for v in back] == [(int(x) * int(y)) % t for x, y in zip(a, b)]
+    # short input: the remaining slots are zero; negative values (two's complement) are lifted by t
+    short = np.array([5, (1 << 64) - 3], dtype=np.uint64)
+    assert o.orc_batch_encode(n, t, P(short), 2, P(pa)) == 0 and o.orc_batch_decode(n, t, P(pa), P(back)) == 0
+    assert int(back[0]) == 5 and int(back[1]) == t - 3 and not back[2:].any()
