@@ -887,6 +887,103 @@ def test_batch_encoder(scheme, n):
         pf.PhantomBatchEncoder(bctx).encode(bctx, full)
 
 
+@pytest.mark.parametrize("scheme,mul_tech", [(2, 2), (2, 1), (2, 3), (1, 0)])
+def test_end_to_end_semantics(scheme, mul_tech):
+    """decode(decrypt(evaluate(encrypt(encode(.))))) = the plaintext operation, every stage on the engine except the
+    randomised ones (key generation and encryption are written out here with numpy / the oracle's NTT): slot-wise product
+    through multiply + relinearize, slot rotation through rotate_inplace -- what the reference's examples check
+    (examples/3_bfv_basics etc.), here for BFV (HPS, BEHZ, HPS over Q) and BGV."""
+    n, t = 4096, 65537
+    # equal-size data primes: HPS over Q switches the second operand to a base R of primes just below min(q_i) and loses
+    # log2(Q / R) bits when one q_i is much larger than the others (the reference's algorithm, not an engine property)
+    ps = H.ParamSet("e2e", n, [44, 44, 44, 50], 1, scheme, t)
+    steps = [1]
+    ctx = make_bfv_context(ps, steps, mul_tech=pf.mul_tech_type(mul_tech)) if scheme == 2 else make_context(ps, steps)
+    o, oc = H.oracle(), ps.octx()
+    l, size_QP = ps.size_Q, ps.size_QP
+    primes = [int(p) for p in ps.primes]
+    rng = np.random.default_rng(100 * scheme + mul_tech)
+    idx_all = (ctypes.c_int * size_QP)(*range(size_QP))
+
+    def ntt(x):   # [size_QP][n] residues, coefficient -> NTT form
+        y = np.ascontiguousarray(x, dtype=np.uint64).copy()
+        o.orc_ntt_forward(oc, P(y), size_QP, idx_all)
+        return y
+
+    def small_poly(vals):   # small signed coefficients -> residues over all key primes
+        return np.stack([np.array([int(v) % p for v in vals], dtype=np.uint64) for p in primes])
+
+    def mul(a, b):   # limb-wise product of NTT-form residue matrices (object ints: exact)
+        return np.stack([(a[i].astype(object) * b[i].astype(object)) % primes[i] for i in range(a.shape[0])]).astype(np.uint64)
+
+    def add(a, b):
+        return np.stack([(a[i].astype(object) + b[i].astype(object)) % primes[i] for i in range(a.shape[0])]).astype(np.uint64)
+
+    def neg(a):
+        return np.stack([(primes[i] - a[i].astype(object)) % primes[i] for i in range(a.shape[0])]).astype(np.uint64)
+
+    s = ntt(small_poly(rng.integers(-1, 2, n)))
+    s2 = mul(s, s)
+    P_mod = [int(np.prod([primes[j] for j in range(l, size_QP)], dtype=object)) % primes[i] for i in range(size_QP)]
+    noise_scale = t if scheme == 1 else 1   # BGV keeps its noise a multiple of t
+
+    def switch_key(target):   # hybrid key for `target` (NTT form): digit d = limb d (alpha = 1), secretkey.cu:297-334
+        key = []
+        for d in range(l):
+            a = np.stack([rng.integers(0, p, n, dtype=np.uint64) for p in primes])
+            e = ntt(small_poly(noise_scale * rng.integers(-2, 3, n)))
+            b = add(neg(mul(a, s)), e)
+            b[d] = ((b[d].astype(object) + target[d].astype(object) * P_mod[d]) % primes[d]).astype(np.uint64)
+            key.append(np.stack([b, a]))
+        return key
+
+    rlk = pf.PhantomRelinKey(ctx, switch_key(s2))
+    elt = pf.get_elt_from_step(1, n)
+    tab = np.zeros(n, dtype=np.uint32)
+    o.orc_galois_table(n, elt, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    s_rot = np.stack([s[i][tab] for i in range(size_QP)])   # s(X^elt) in NTT form
+    glk = pf.PhantomGaloisKey(ctx, [switch_key(s_rot)])
+    enc = pf.PhantomBatchEncoder(ctx)
+    sk = pf.PhantomSecretKey(ctx, s)
+    Q = int(np.prod(primes[:l], dtype=object))
+
+    def encrypt(values):
+        m = host(enc.encode(ctx, values))   # [n] mod t, coefficient form
+        if scheme == 2:
+            payload = [(Q // t) * int(v) for v in m]
+            e = small_poly(rng.integers(-3, 4, n))
+        else:
+            payload = [int(v) for v in m]
+            e = small_poly(t * rng.integers(-3, 4, n))
+        pay = ntt(add(small_poly(payload), e))
+        a = np.stack([rng.integers(0, p, n, dtype=np.uint64) for p in primes])
+        ct = np.stack([add(pay, neg(mul(a, s)))[:l], a[:l]])   # NTT form
+        if scheme == 2:   # BFV ciphertexts live in coefficient form
+            idx = (ctypes.c_int * l)(*range(l))
+            for k in range(2):
+                o.orc_ntt_inverse(oc, P(ct[k]), l, idx)
+        return pf.PhantomCiphertext.from_host(ctx, ct, is_ntt_form=(scheme != 2))
+
+    v1, v2 = rng.integers(0, t, n), rng.integers(0, t, n)
+    c1, c2 = encrypt(v1), encrypt(v2)
+    assert [int(x) for x in enc.decode(ctx, sk.decrypt(ctx, c1))] == [int(x) for x in v1], "fresh ciphertext"
+    pf.multiply_inplace(ctx, c1, c2)
+    assert c1.size() == 3
+    assert [int(x) for x in enc.decode(ctx, sk.decrypt(ctx, c1))] == [(int(x) * int(y)) % t for x, y in zip(v1, v2)], \
+        "size-3 product decrypts with s^2"
+    pf.relinearize_inplace(ctx, c1, rlk)
+    want = [(int(x) * int(y)) % t for x, y in zip(v1, v2)]
+    assert [int(x) for x in enc.decode(ctx, sk.decrypt(ctx, c1))] == want, "multiply + relinearize"
+    c3 = encrypt(v1)
+    pf.multiply_and_relin_inplace(ctx, c3, c2, rlk)
+    assert [int(x) for x in enc.decode(ctx, sk.decrypt(ctx, c3))] == want, "multiply_and_relin_inplace"
+    # rotation by one step: each row of N/2 slots rotates left by one
+    pf.rotate_inplace(ctx, c3, 1, glk)
+    half = n // 2
+    rot = want[1:half] + want[:1] + want[half + 1:] + want[half:half + 1]
+    assert [int(x) for x in enc.decode(ctx, sk.decrypt(ctx, c3))] == rot, "rotate_inplace"
+
+
 def test_serialisation_against_unmodified_reference():
     """Streams written by the reference's own save() (ciphertext, relinearisation key, Galois key, secret key) are read by
     the host mirror and re-written byte for byte; a ciphertext stream written here is loaded by the reference."""
