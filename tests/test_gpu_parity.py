@@ -984,6 +984,111 @@ def test_end_to_end_semantics(scheme, mul_tech):
     assert [int(x) for x in enc.decode(ctx, sk.decrypt(ctx, c3))] == rot, "rotate_inplace"
 
 
+def test_ckks_end_to_end_semantics():
+    """CKKS at the ring level: Enc(m1) * Enc(m2), relinearised and rescaled on the engine, decrypts to m1 * m2 / q_last in
+    Z[X]/(X^N + 1) within the noise (relative error < 1e-3 of the scale, the reference examples' criterion); a rotation
+    decrypts to m(X^elt).  Key generation / encryption written out here; multiply, relinearize, rescale, rotate and
+    decrypt run on the engine."""
+    n = 4096
+    ps = H.ParamSet("ckks_e2e", n, [60, 40, 40, 40, 60], 1, 3, 0)
+    ctx = make_context(ps, [1])
+    o, oc = H.oracle(), ps.octx()
+    l, size_QP = ps.size_Q, ps.size_QP
+    primes = [int(p) for p in ps.primes]
+    rng = np.random.default_rng(2024)
+    idx_all = (ctypes.c_int * size_QP)(*range(size_QP))
+    scale = 2.0 ** 40
+
+    def ntt(x):
+        y = np.ascontiguousarray(x, dtype=np.uint64).copy()
+        o.orc_ntt_forward(oc, P(y), size_QP, idx_all)
+        return y
+
+    def residues(vals):
+        return np.stack([np.array([int(v) % p for v in vals], dtype=np.uint64) for p in primes])
+
+    def mul(a, b):
+        return np.stack([(a[i].astype(object) * b[i].astype(object)) % primes[i] for i in range(a.shape[0])]).astype(np.uint64)
+
+    def add(a, b):
+        return np.stack([(a[i].astype(object) + b[i].astype(object)) % primes[i] for i in range(a.shape[0])]).astype(np.uint64)
+
+    def neg(a):
+        return np.stack([(primes[i] - a[i].astype(object)) % primes[i] for i in range(a.shape[0])]).astype(np.uint64)
+
+    s = ntt(residues(rng.integers(-1, 2, n)))
+    P_mod = [primes[l] % primes[i] for i in range(size_QP)]
+
+    def switch_key(target):   # digit d = limb d (alpha = 1)
+        key = []
+        for d in range(l):
+            a = np.stack([rng.integers(0, p, n, dtype=np.uint64) for p in primes])
+            b = add(neg(mul(a, s)), ntt(residues(rng.integers(-2, 3, n))))
+            b[d] = ((b[d].astype(object) + target[d].astype(object) * P_mod[d]) % primes[d]).astype(np.uint64)
+            key.append(np.stack([b, a]))
+        return key
+
+    rlk = pf.PhantomRelinKey(ctx, switch_key(mul(s, s)))
+    elt = pf.get_elt_from_step(1, n)
+    tab = np.zeros(n, dtype=np.uint32)
+    o.orc_galois_table(n, elt, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    glk = pf.PhantomGaloisKey(ctx, [switch_key(np.stack([s[i][tab] for i in range(size_QP)]))])
+    sk = pf.PhantomSecretKey(ctx, s)
+
+    def encrypt(m):   # m: integer coefficients
+        pay = ntt(add(residues(m), residues(rng.integers(-3, 4, n))))
+        a = np.stack([rng.integers(0, p, n, dtype=np.uint64) for p in primes])
+        return pf.PhantomCiphertext.from_host(ctx, np.stack([add(pay, neg(mul(a, s)))[:l], a[:l]]), scale=scale)
+
+    def decrypt_coeffs(ct):   # engine decrypt (NTT form) -> centred integer coefficients
+        lv = ct.coeff_modulus_size()
+        w = host(sk.decrypt(ctx, ct)).copy()
+        o.orc_ntt_inverse(oc, P(w), lv, (ctypes.c_int * lv)(*range(lv)))
+        Ql = int(np.prod(primes[:lv], dtype=object))
+        out = []
+        for x in range(n):
+            v = 0
+            for i in range(lv):
+                qh = Ql // primes[i]
+                v += int(w[i, x]) * pow(qh, -1, primes[i]) % primes[i] * qh
+            v %= Ql
+            out.append(v - Ql if v > Ql // 2 else v)
+        return out
+
+    def negacyclic(a, b):   # exact product in Z[X]/(X^N + 1) through one big-prime-free route: numpy object convolution
+        full = np.convolve(np.array(a, dtype=object), np.array(b, dtype=object))
+        res = list(full[:n])
+        for k in range(n, len(full)):
+            res[k - n] -= full[k]
+        return res
+
+    m1 = [int(round(scale * v)) for v in rng.uniform(-1, 1, n)]
+    m2 = [int(round(scale * v)) for v in rng.uniform(-1, 1, n)]
+    c1, c2 = encrypt(m1), encrypt(m2)
+    fresh = decrypt_coeffs(c1)
+    assert max(abs(a - b) for a, b in zip(fresh, m1)) < 2 ** 12, "fresh ciphertext decrypts to m + small noise"
+    pf.multiply_and_relin_inplace(ctx, c1, c2, rlk)
+    rs = pf.rescale_to_next(ctx, c1)
+    assert rs.chain_index == 2 and rs.coeff_modulus_size() == l - 1
+    got = decrypt_coeffs(rs)
+    want = [v / primes[l - 1] for v in negacyclic(m1, m2)]
+    bound = 1e-3 * scale * scale / primes[l - 1] * n ** 0.5   # relative to the size of the product's coefficients
+    err = max(abs(a - b) for a, b in zip(got, want))
+    assert err < bound, (err, bound)
+    # rotation of a fresh ciphertext: m(X) -> m(X^elt)
+    c3 = encrypt(m1)
+    pf.rotate_inplace(ctx, c3, 1, glk)
+    rot = [0] * n
+    for j, v in enumerate(m1):
+        e = (j * elt) % (2 * n)
+        if e >= n:
+            rot[e - n] -= v
+        else:
+            rot[e] += v
+    got = decrypt_coeffs(c3)
+    assert max(abs(a - b) for a, b in zip(got, rot)) < 2 ** 24, "rotation decrypts to m(X^elt) within key-switch noise"
+
+
 def test_serialisation_against_unmodified_reference():
     """Streams written by the reference's own save() (ciphertext, relinearisation key, Galois key, secret key) are read by
     the host mirror and re-written byte for byte; a ciphertext stream written here is loaded by the reference."""
