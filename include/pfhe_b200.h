@@ -186,7 +186,7 @@ int pfhe_multiply_sizes(pfhe_engine *e, size_t chain_index, const uint64_t *encr
  * memory).  The reference runs independent ciphertexts on independent host threads / cudaStreamPerThread
  * (src/CMakeLists.txt:39, evaluate.cu:1079); here the ops go round-robin over pfhe_engine_lanes() internal streams,
  * each with its own workspace, forked from and joined back into `stream`.  destination[i] must not alias an operand.
- * CKKS / BGV. */
+ * All schemes (BFV: by the engine's mul_tech, 0 levels dropped for hps_overq_leveled). */
 int pfhe_multiply_and_relin_batch(pfhe_engine *e, size_t chain_index, const uint64_t *const *encrypted1,
                                   const uint64_t *const *encrypted2, uint64_t *const *destination, size_t count,
                                   const uint64_t *const *relin_keys, void *stream);

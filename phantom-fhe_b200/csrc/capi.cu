@@ -451,7 +451,6 @@ int pfhe_multiply_and_relin_batch(pfhe_engine *e, size_t chain_index, const uint
                                   const uint64_t *const *rlk, void *stream) {
     API_BEGIN
     require(ct1 && ct2 && dst, "null batch pointers");
-    require(e->impl.scheme() != Scheme::bfv, "batched multiply_and_relin covers CKKS / BGV");
     for (size_t i = 0; i < count; i++)
         require(dst[i] && ct1[i] && ct2[i] && dst[i] != ct1[i] && dst[i] != ct2[i], "destination aliases an operand");
     const int l = e->impl.limbs_at(chain_index);

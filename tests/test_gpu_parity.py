@@ -413,12 +413,12 @@ def test_multiply_3x3_against_unmodified_reference():
         r.ref_destroy(h)
 
 
-@pytest.mark.parametrize("lanes,scheme", [(1, 3), (2, 3), (3, 3), (2, 1)])
+@pytest.mark.parametrize("lanes,scheme", [(1, 3), (2, 3), (3, 3), (2, 1), (2, 2), (4, 2)])
 def test_multiply_relin_batch(lanes, scheme):
     """pfhe_multiply_and_relin_batch: independent pairs interleaved over the engine's lanes give, pair by pair, the
     words of the one-at-a-time op (and of the oracle); ragged counts, empty batch, mixed with single ops."""
-    ps = H.params_small(scheme=scheme, t=65537 if scheme == 1 else 0, **KS_SETS[0])
-    ctx = make_context(ps)
+    ps = H.params_small(scheme=scheme, t=65537 if scheme != 3 else 0, **KS_SETS[0])
+    ctx = make_bfv_context(ps, mul_tech=pf.mul_tech_type.hps) if scheme == 2 else make_context(ps)
     pf.check(pf.lib.pfhe_engine_set_lanes(ctx._h, lanes))
     assert pf.lib.pfhe_engine_lanes(ctx._h) == lanes
     o = H.oracle()
@@ -431,15 +431,18 @@ def test_multiply_relin_batch(lanes, scheme):
     want = []
     for x, y in zip(a, b):
         w = np.zeros((2, l, n), dtype=np.uint64)
-        o.orc_multiply_relin(ps.octx(), l, P(x), P(y), P(rlk_h), P(w))
+        if scheme == 2:
+            assert o.orc_bfv_multiply_relin_hps(ps.octx(), P(x), P(y), P(rlk_h), P(w)) == 0
+        else:
+            o.orc_multiply_relin(ps.octx(), l, P(x), P(y), P(rlk_h), P(w))
         want.append(w)
     pf.multiply_and_relin_batch(ctx, [], [], rlk)   # empty batch is a no-op
     for cnt in (1, 2, 5):
-        ca = [pf.PhantomCiphertext.from_host(ctx, x) for x in a[:cnt]]
-        cb = [pf.PhantomCiphertext.from_host(ctx, y) for y in b[:cnt]]
+        ca = [pf.PhantomCiphertext.from_host(ctx, x, is_ntt_form=(scheme != 2)) for x in a[:cnt]]
+        cb = [pf.PhantomCiphertext.from_host(ctx, y, is_ntt_form=(scheme != 2)) for y in b[:cnt]]
         pf.multiply_and_relin_batch(ctx, ca, cb, rlk)
         # a single op right behind the batch on the same stream (the batch has joined back into it)
-        single = pf.PhantomCiphertext.from_host(ctx, a[0])
+        single = pf.PhantomCiphertext.from_host(ctx, a[0], is_ntt_form=(scheme != 2))
         pf.multiply_and_relin_inplace(ctx, single, cb[0], rlk)
         for i in range(cnt):
             assert np.array_equal(ca[i].to_host(), want[i]), f"batch of {cnt}, pair {i}, lanes {lanes}"

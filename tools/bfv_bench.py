@@ -51,5 +51,23 @@ for which, tech in [(w, m) for m in (1, 2, 3) for w in (0, 1, 2)]:
         assert r.ref_time_op(h, 0, 1, P(a), P(b), 0, 0, 60, times.ctypes.data_as(ctypes.POINTER(ctypes.c_double))) == 0
         ref_us = float(np.median(times[10:]))
         r.ref_destroy(h)
-    print(f"bfv set {which} {pf.mul_tech_type(tech).name}: l={ps.limbs()} alpha={ps.size_P} engine {eng_us:.1f} us  reference {ref_us:.1f} us  "
+    # throughput of independent pairs through the batched entry point (lanes)
+    lane_txt = ""
+    if tech == 2:
+        cnt = 64
+        outs = [ca.data.clone() for _ in range(4)]
+        Arr = ctypes.c_void_p * cnt
+        aa, bb = Arr(*[ca.data.data_ptr()] * cnt), Arr(*[cb.data.data_ptr()] * cnt)
+        oo = Arr(*[outs[i % 4].data_ptr() for i in range(cnt)])
+        for lanes in (2, 4):
+            pf.check(pf.lib.pfhe_engine_set_lanes(ctx._h, lanes))
+            pf.check(pf.lib.pfhe_multiply_and_relin_batch(ctx._h, 1, aa, bb, oo, 8, rlk.public_keys_ptr(), st))
+            torch.cuda.synchronize()
+            e0.record()
+            pf.check(pf.lib.pfhe_multiply_and_relin_batch(ctx._h, 1, aa, bb, oo, cnt, rlk.public_keys_ptr(), st))
+            e1.record()
+            torch.cuda.synchronize()
+            lane_txt += f"  {lanes} lanes {e0.elapsed_time(e1) * 1000 / cnt:.1f} us/op"
+    print(f"bfv set {which} {pf.mul_tech_type(tech).name}:{lane_txt}  ", end="")
+    print(f" l={ps.limbs()} alpha={ps.size_P} engine {eng_us:.1f} us  reference {ref_us:.1f} us  "
           f"speedup {ref_us / eng_us:.2f}x", flush=True)
