@@ -130,6 +130,15 @@ int pfhe_multiply_and_relin_inplace(pfhe_engine *e, size_t chain_index, uint64_t
 int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted1,
                             const uint64_t *encrypted2, uint64_t *destination, const uint64_t *const *relin_keys,
                             void *stream);
+/* PhantomCKKSEncoder::encode_internal (src/ckks.cu:66-135; special inverse FFT src/fft.cu; decompose_array
+ * src/rns_base.cu:49-173): `values` = count <= N/2 complex numbers on the device (re, im interleaved, 16-byte aligned),
+ * `plain` = [l][N] residues in NTT form at chain_index with the given scale.  Same floating-point operations in the same
+ * order as the reference's kernels: the same words.  Synchronises `stream` once, like the reference (the magnitude of the
+ * encoded coefficients selects the decomposition and is validated against the modulus); coefficients above 128 bits
+ * (the reference's slow multi-word path) are refused.  Decoding (compose_array + forward FFT) is not built. */
+int pfhe_ckks_encode(pfhe_engine *e, size_t chain_index, const double *values, size_t count, double scale,
+                     uint64_t *plain, void *stream);
+
 /* PhantomBatchEncoder::encode / decode for BFV / BGV (src/batchencoder.cu:62-118): `values` = count <= N slot values on
  * the device (the reference copies its std::vector there first), `plain` = the [N] plaintext polynomial mod t,
  * coefficient form.  Needs a batching plain modulus (prime, 1 mod 2N): the engine then keeps NTT tables for it

@@ -1666,6 +1666,117 @@ int orc_batch_decode(u64 n, u64 t, const u64 *plain, u64 *values) {
 }
 
 /* ------------------------------------------------------------------------------------------------------
+ * CKKS encoder, encoding direction (PhantomCKKSEncoder::encode_internal, reference src/ckks.cu:66-135; special inverse
+ * FFT src/fft.cu:219-345,386-422; roots src/fft.cu:13-43; decompose_array src/rns_base.cu:49-103,155-173).
+ * Floating point: every operation below is the one the reference's compiled kernels execute, in the same order -- the
+ * Gentleman-Sande butterfly is (x0 + x1, (x0 - x1) * w) with the complex product contracted by nvcc to
+ * re = fma(d.x, w.x, -(d.y * w.y)) and one of two forms of im (see the loop; SASS of oracle/_ref), then * scalar, round().
+ * ---------------------------------------------------------------------------------------------------- */
+static void ckks_root(u64 m, u64 index, double *re, double *im) { /* ComplexRoots::get_root, 8-fold symmetry */
+    const double PI_ = 3.1415926535897932384626433832795028842;
+    index &= m - 1;
+    if (index <= m / 8) {
+        double th = 2 * PI_ * (double)index / (double)m;
+        *re = cos(th), *im = sin(th); /* std::polar(1.0, theta) */
+    } else if (index <= m / 4) {
+        double a, b;
+        ckks_root(m, m / 4 - index, &a, &b);
+        *re = b, *im = a;
+    } else if (index <= m / 2) {
+        double a, b;
+        ckks_root(m, m / 2 - index, &a, &b);
+        *re = 0.0 - a, *im = 0.0 - (-b); /* cuCsub({0,0}, cuConj(r)) */
+    } else if (index <= 3 * m / 4) {
+        double a, b;
+        ckks_root(m, index - m / 2, &a, &b);
+        *re = 0.0 - a, *im = 0.0 - b;
+    } else {
+        double a, b;
+        ckks_root(m, m - index, &a, &b);
+        *re = a, *im = -b;
+    }
+}
+
+/* values = count <= n/2 complex numbers (re, im interleaved); out = [l][n] residues in NTT form.
+ * Returns 0, -1 on bad arguments, -2 when the encoded values are too large (ckks.cu:122-124) or need the reference's slow
+ * multi-word path (more than 128 bits), which this restatement does not cover. */
+int orc_ckks_encode(const orc_ctx *c, int l, const double *values, u64 count, double scale, u64 *out) {
+    const u64 n = c->n, slots = n >> 1, m = n << 1;
+    if (count == 0 || count > slots || !(scale > 0)) return -1;
+    int logs = 0;
+    while (((u64)1 << logs) < slots) logs++;
+    double *xr = (double *)calloc(slots, sizeof(double)), *xi = (double *)calloc(slots, sizeof(double));
+    for (u64 i = 0; i < count; i++) { /* bit_reverse_kernel, ckks.cu:9-15 */
+        u64 r = logs ? bitrev32((uint32_t)i, logs) : 0;
+        xr[r] = values[2 * i], xi[r] = values[2 * i + 1];
+    }
+    u64 *group = (u64 *)malloc((slots / 2 + 1) * 8);
+    {
+        u64 pos = 1;
+        for (u64 i = 0; i < slots / 2; i++) group[i] = pos, pos = (pos * 5) & (m - 1);
+    }
+    const double fix = scale / (double)slots;
+    for (int iter = logs - 1; iter >= 0; iter--) { /* special_fft_backward */
+        const int logPairs = logs - iter - 1;
+        const u64 pairs = (u64)1 << logPairs;
+#pragma omp parallel for num_threads(g_threads)
+        for (u64 tid = 0; tid < slots / 2; tid++) {
+            u64 k = tid >> logPairs, j = tid & (pairs - 1), a = 2 * k * pairs + j, b = a + pairs;
+            uint32_t kk = (uint32_t)(k << logPairs);
+            u64 gi = (u64)(bitrev32(kk, 32) >> (33 - logs)); /* __brev(k << logPairs) >> (33 - logn) */
+            u64 psi = (group[gi] << logPairs) & (m - 1);
+            double wr, wi;
+            ckks_root(m, m - psi, &wr, &wi); /* twiddles[M - psiIdx], the table holds get_root(i) for i < M */
+            double sr = xr[a] + xr[b], si = xi[a] + xi[b], dr = xr[a] - xr[b], di = xi[a] - xi[b];
+            double t1 = di * wi;
+            xr[a] = sr, xi[a] = si;
+            xr[b] = fma(dr, wr, -t1);
+            /* the imaginary part was contracted differently in the reference's two kernels (SASS of oracle/_ref): the
+             * shared-memory kernel, which runs the stages with pairs <= SWITCH_POINT / 2 = 1024 (fft.cu:219-282,396-412),
+             * has fma(d.y, w.x, d.x * w.y); the one-stage kernel (fft.cu:296-345) fma(d.x, w.y, d.y * w.x) */
+            xi[b] = logPairs <= 10 ? fma(di, wr, dr * wi) : fma(dr, wi, di * wr);
+            if (iter == 0) {
+                xr[a] *= fix, xi[a] *= fix, xr[b] *= fix, xi[b] *= fix;
+            }
+        }
+    }
+    if (logs == 0) xr[0] *= fix, xi[0] *= fix; /* n = 2: no stage; not reachable for supported degrees */
+    double mx = 0;
+    for (u64 i = 0; i < slots; i++) mx = fmax(mx, fmax(fabs(xr[i]), fabs(xi[i])));
+    int bits = (int)ceil(log2(fmax(mx, 1.0))) + 1, qbits = 0;
+    {
+        big_t Qb = {{1}, 1};
+        for (int i = 0; i < l; i++) big_mul_word(&Qb, c->primes[i]);
+        qbits = 64 * (Qb.len - 1);
+        for (u64 v = Qb.w[Qb.len - 1]; v; v >>= 1) qbits++;
+    }
+    int rc = 0;
+    if (bits >= qbits || bits > 128) rc = -2;
+    for (int i = 0; i < l && !rc; i++) {
+        const u64 q = c->primes[i];
+        for (u64 x = 0; x < n; x++) {
+            double cd = round(x < slots ? xr[x] : xi[x - slots]);
+            int negv = signbit(cd) ? 1 : 0;
+            u64 r;
+            if (bits <= 64) r = sat_u64(fabs(cd)) % q;
+            else {
+                double ad = fabs(cd);
+                u128 v = ((u128)sat_u64(ad / 18446744073709551616.0) << 64) | sat_u64(fmod(ad, 18446744073709551616.0));
+                r = (u64)(v % q);
+            }
+            out[(size_t)i * n + x] = negv ? q - r : r; /* a negative zero gives q, as in the reference */
+        }
+    }
+    if (!rc) {
+        int idx[64];
+        for (int i = 0; i < l; i++) idx[i] = i;
+        orc_ntt_forward(c, out, l, idx);
+    }
+    free(group); free(xr); free(xi);
+    return rc;
+}
+
+/* ------------------------------------------------------------------------------------------------------
  * rescale / mod switch
  * ---------------------------------------------------------------------------------------------------- */
 void orc_rescale(const orc_ctx *c, int l, u64 *in, int size, u64 *out) {

@@ -409,6 +409,22 @@ long ref_save_key(void *p, int which, unsigned char *out, size_t cap) {
     SHIM_CATCH
 }
 
+/* PhantomCKKSEncoder::encode (ckks.cu:66-135): count complex values (re, im interleaved) -> [l][n] residues, NTT form */
+int ref_ckks_encode(void *p, const double *values, size_t count, size_t chain_index, double scale, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    PhantomCKKSEncoder enc(*h->ctx);
+    std::vector<cuDoubleComplex> v(count);
+    for (size_t i = 0; i < count; i++) v[i] = make_cuDoubleComplex(values[2 * i], values[2 * i + 1]);
+    PhantomPlaintext pt;
+    enc.encode(*h->ctx, v, scale, pt, chain_index);
+    cudaStreamSynchronize(cudaStreamPerThread);
+    size_t l = h->ctx->get_context_data(chain_index).parms().coeff_modulus().size();
+    cudaMemcpy(out, pt.data(), l * h->n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    return 0;
+    SHIM_CATCH
+}
+
 /* PhantomBatchEncoder::encode / decode (batchencoder.cu:62-118): values[count] -> plain[n]; plain[n] -> values[n] */
 int ref_batch_encode(void *p, const uint64_t *values, size_t count, uint64_t *plain) {
     SHIM_TRY

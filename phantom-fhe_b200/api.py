@@ -200,6 +200,31 @@ class PhantomCiphertext:
         return c
 
 
+class PhantomCKKSEncoder:
+    """Encoding half of PhantomCKKSEncoder (include/ckks.h, src/ckks.cu:66-135)."""
+
+    def __init__(self, context):
+        if context.scheme != scheme_type.ckks:
+            raise ValueError("unsupported scheme")
+        self._slots = context.poly_degree >> 1
+
+    def slot_count(self):
+        return self._slots
+
+    def encode(self, context, values, scale, chain_index=1):
+        """complex (or real) slot values -> device plaintext [l][N] in NTT form at chain_index"""
+        v = np.ascontiguousarray(np.asarray(values, dtype=np.complex128))
+        if v.size == 0:
+            raise ValueError("Input vector is empty")
+        if v.size > self._slots:
+            raise ValueError("Input vector exceeds max slots")
+        d_in = torch.from_numpy(v.view(np.float64).copy()).to(context.device)
+        l = context.coeff_modulus_size(chain_index)
+        plain = torch.empty((l, context.poly_degree), dtype=torch.int64, device=context.device)
+        check(lib.pfhe_ckks_encode(context._h, chain_index, _ptr(d_in), v.size, float(scale), _ptr(plain), _stream()))
+        return plain
+
+
 class PhantomBatchEncoder:
     """PhantomBatchEncoder (include/batchencoder.h, src/batchencoder.cu): BFV / BGV slot packing over the plain modulus."""
 

@@ -265,6 +265,14 @@ int pfhe_multiply(pfhe_engine *e, size_t chain_index, const uint64_t *ct1, const
     else e->impl.tensor_2x2(U(ct1), U(ct2), U(dst), l, S(stream));
     API_END
 }
+int pfhe_ckks_encode(pfhe_engine *e, size_t chain_index, const double *values, size_t count, double scale,
+                     uint64_t *plain, void *stream) {
+    API_BEGIN
+    require(e && values && plain, "null pointer");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.ckks_encode(l, reinterpret_cast<const double2 *>(values), count, scale, U(plain), S(stream));
+    API_END
+}
 int pfhe_batch_encode(pfhe_engine *e, const uint64_t *values, size_t count, uint64_t *plain, void *stream) {
     API_BEGIN
     require(e && plain && (values || count == 0), "null pointer");

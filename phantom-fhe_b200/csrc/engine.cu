@@ -1498,6 +1498,84 @@ void Engine::decrypt(int l, const u64 *ct, int size, const u64 *sk_pow, u64 corr
     }
 }
 
+// PhantomCKKSEncoder::encode_internal (reference src/ckks.cu:66-135)
+void Engine::ckks_encode(int l, const double2 *values, size_t count, double scale, u64 *out, cudaStream_t st) {
+    if (scheme_ != Scheme::ckks) throw std::invalid_argument("unsupported scheme");
+    const size_t slots = n_ >> 1;
+    const uint32_t M = (uint32_t) (n_ << 1);
+    const int logs = logn_ - 1;
+    if (count == 0) throw std::invalid_argument("Input vector is empty");
+    if (count > slots) throw std::invalid_argument("Input vector exceeds max slots");
+    std::vector<u64> ql(primes_.begin(), primes_.begin() + l);
+    const int qbits = hm::product_bits(ql);
+    if (scale <= 0 || (int) std::log2(scale) + 1 >= qbits) throw std::invalid_argument("scale out of bounds");
+    if (!d_ckks_roots_.p) {
+        // ComplexRoots (src/fft.cu:13-43): an eighth of the circle from polar(), the rest by symmetry
+        const double PI_ = 3.1415926535897932384626433832795028842;
+        std::vector<double2> eighth(M / 8 + 1), roots(M + 1);
+        for (size_t i = 0; i <= M / 8; i++) {
+            const double th = 2 * PI_ * (double) i / (double) M;
+            eighth[i] = make_double2(std::cos(th), std::sin(th));
+        }
+        std::function<double2(size_t)> root = [&](size_t i) -> double2 {
+            i &= M - 1;
+            if (i <= M / 8) return eighth[i];
+            if (i <= M / 4) {
+                const double2 r = eighth[M / 4 - i];
+                return make_double2(r.y, r.x);
+            }
+            if (i <= M / 2) {
+                const double2 r = root(M / 2 - i);
+                return make_double2(0.0 - r.x, 0.0 - (-r.y));
+            }
+            if (i <= 3 * (size_t) M / 4) {
+                const double2 r = root(i - M / 2);
+                return make_double2(0.0 - r.x, 0.0 - r.y);
+            }
+            const double2 r = root(M - i);
+            return make_double2(r.x, -r.y);
+        };
+        for (size_t i = 0; i <= M; i++) roots[i] = root(i);   // entry M = entry 0: the inverse reads tw[M - psi]
+        std::vector<uint32_t> group(std::max<size_t>(slots / 2, 1));
+        uint32_t pos = 1;
+        for (size_t i = 0; i < slots / 2; i++) group[i] = pos, pos = (pos * 5) & (M - 1);
+        d_ckks_roots_.upload(roots), d_ckks_group_.upload(group);
+        d_ckks_x_.alloc(slots), d_ckks_max_.alloc(1);
+    }
+    double2 *x = d_ckks_x_.p;
+    launch_pdl(k_ckks_place, dim3((unsigned) (slots / EW_THREADS)), EW_THREADS, 0, st, x, values, count, logs);
+    check_launch("k_ckks_place");
+    const double fix = scale / (double) slots;
+    // stages logs-1 .. iter_end inside blocks, the rest one launch each
+    const int blk_log = std::min(logs, CKKS_FFT_LOG_BLOCK);
+    const int iter_end = logs - blk_log;
+    const unsigned threads = 1u << (blk_log - 1);
+    launch_pdl(k_ckks_ifft_block, dim3((unsigned) (slots >> blk_log)), dim3(threads), ((size_t) 1 << blk_log) * sizeof(double2), st,
+               x, (const double2 *) d_ckks_roots_.p, (const uint32_t *) d_ckks_group_.p, logs, iter_end, M, fix);
+    check_launch("k_ckks_ifft_block");
+    for (int iter = iter_end - 1; iter >= 0; iter--) {
+        launch_pdl(k_ckks_ifft_stage, dim3((unsigned) (slots / 2 / EW_THREADS)), EW_THREADS, 0, st, x,
+                   (const double2 *) d_ckks_roots_.p, (const uint32_t *) d_ckks_group_.p, logs, iter, M, fix);
+        check_launch("k_ckks_ifft_stage");
+    }
+    // size of the encoded coefficients (the reference copies the vector to the host for this, ckks.cu:107-124)
+    PFHE_CUDA(cudaMemsetAsync(d_ckks_max_.p, 0, sizeof(unsigned long long), st));
+    launch_pdl(k_ckks_absmax, dim3((unsigned) (slots / EW_THREADS)), EW_THREADS, 0, st, (const double2 *) x, d_ckks_max_.p);
+    check_launch("k_ckks_absmax");
+    unsigned long long mb = 0;
+    PFHE_CUDA(cudaMemcpyAsync(&mb, d_ckks_max_.p, sizeof(mb), cudaMemcpyDeviceToHost, st));
+    PFHE_CUDA(cudaStreamSynchronize(st));
+    double max_coeff;
+    std::memcpy(&max_coeff, &mb, sizeof(double));
+    const int bits = (int) std::ceil(std::log2(std::max(max_coeff, 1.0))) + 1;
+    if (bits >= qbits) throw std::invalid_argument("encoded values are too large");
+    if (bits > 128) throw std::invalid_argument("encoded values need more than 128 bits: not supported");
+    launch_pdl(k_ckks_decompose, dim3((unsigned) (n_ / EW_THREADS), l), EW_THREADS, 0, st, out, (const double2 *) x,
+               (const Modulus *) d_mod_.p, n_, bits > 64 ? 1 : 0);
+    check_launch("k_ckks_decompose");
+    ntt_fwd_rows_range(out, l, 0, st);
+}
+
 // PhantomBatchEncoder (reference src/batchencoder.cu): slots <-> plaintext polynomial mod t
 void Engine::batch_encode(const u64 *values, size_t count, u64 *plain, cudaStream_t st) {
     if (scheme_ == Scheme::ckks) throw std::invalid_argument("PhantomBatchEncoder only supports BFV/BGV scheme");

@@ -578,6 +578,127 @@ __global__ void __launch_bounds__(EW_THREADS) k_bgv_mod_t_divide(u64 *dst, const
     st2(dst + x, r[0], r[1]);
 }
 
+// ---------------------------------------------------------------------------------------------------
+// CKKS encoder, encoding direction (PhantomCKKSEncoder::encode_internal, reference src/ckks.cu:66-135): bit-reversed
+// placement, special inverse FFT over the slots, rounding and RNS decomposition.  The floating-point operations are the
+// ones the reference's compiled kernels execute (Gentleman-Sande butterfly (x0 + x1, (x0 - x1) w) with
+// re = fma(d.x, w.x, -(d.y w.y)), im = fma(d.x, w.y, d.y w.x); then * scalar; then round()), so the residues are the same
+// words; only the schedule differs: the stages whose butterflies stay inside a block of CKKS_FFT_BLOCK slots run in one
+// shared-memory kernel, the rest one launch per stage.
+// ---------------------------------------------------------------------------------------------------
+constexpr int CKKS_FFT_LOG_BLOCK = 11;
+constexpr int CKKS_FFT_BLOCK = 1 << CKKS_FFT_LOG_BLOCK;
+
+__global__ void __launch_bounds__(EW_THREADS) k_ckks_place(double2 *x, const double2 *values, size_t count, int logs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t r = blockIdx.x * EW_THREADS + threadIdx.x;   // output position
+    const uint32_t i = logs ? (__brev(r) >> (32 - logs)) : 0;    // bit_reverse_kernel, ckks.cu:9-15
+    x[r] = i < count ? values[i] : make_double2(0.0, 0.0);
+}
+
+// one inverse butterfly on the pair (a, a + pairs).  nvcc contracted the imaginary part of the complex product
+// d.x w.y + d.y w.x differently in the reference's two kernels (SASS of oracle/_ref): the shared-memory kernel (stages
+// with pairs <= 1024) computes fma(d.y, w.x, d.x * w.y), the one-stage kernel fma(d.x, w.y, d.y * w.x); the two round
+// differently in about a quarter of the butterflies, which flips about one encoded coefficient in 10^4, so the form is
+// part of the result.  BLOCK_FORM selects the first.
+template<bool BLOCK_FORM>
+__device__ __forceinline__ void ckks_gs(double2 &x0, double2 &x1, const double2 w) {
+    const double sx = __dadd_rn(x0.x, x1.x), sy = __dadd_rn(x0.y, x1.y);
+    const double dx = __dadd_rn(x0.x, -x1.x), dy = __dadd_rn(x0.y, -x1.y);
+    const double t1 = __dmul_rn(dy, w.y);
+    const double re = __fma_rn(dx, w.x, -t1);
+    const double im = BLOCK_FORM ? __fma_rn(dy, w.x, __dmul_rn(dx, w.y)) : __fma_rn(dx, w.y, __dmul_rn(dy, w.x));
+    x0 = make_double2(sx, sy);
+    x1 = make_double2(re, im);
+}
+__device__ __forceinline__ double2 ckks_tw(const double2 *tw, const uint32_t *group, uint32_t k, int logPairs, int logs,
+                                           uint32_t M) {
+    // psiIdx = group[brev(k << logPairs) >> (33 - logs)] << logPairs mod M; inverse transform: twiddles[M - psiIdx]
+    uint32_t psi = group[__brev(k << logPairs) >> (33 - logs)];
+    psi = (psi << logPairs) & (M - 1);
+    return tw[M - psi];
+}
+
+// stages iter = logs-1 down to iter_end (pairs 1 .. BLOCK/2) inside blocks of CKKS_FFT_BLOCK (or all slots) elements
+__global__ void __launch_bounds__(CKKS_FFT_BLOCK / 2) k_ckks_ifft_block(double2 *x, const double2 *tw, const uint32_t *group,
+                                                                        int logs, int iter_end, uint32_t M, double scalar) {
+    extern __shared__ __align__(16) unsigned char ckks_smem[];
+    double2 *buf = reinterpret_cast<double2 *>(ckks_smem);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nb = blockDim.x * 2;                         // slots per block
+    const uint32_t base = blockIdx.x * nb, t = threadIdx.x;
+    buf[t] = x[base + t], buf[t + blockDim.x] = x[base + t + blockDim.x];
+    __syncthreads();
+    for (int iter = logs - 1; iter >= iter_end; iter--) {
+        const int logPairs = logs - iter - 1;
+        const uint32_t pairs = 1u << logPairs;
+        const uint32_t gt = blockIdx.x * blockDim.x + t;   // global butterfly index of this stage
+        const uint32_t k = gt >> logPairs, j = gt & (pairs - 1);
+        const uint32_t a = 2 * k * pairs + j - base;
+        double2 x0 = buf[a], x1 = buf[a + pairs];
+        ckks_gs<true>(x0, x1, ckks_tw(tw, group, k, logPairs, logs, M));
+        if (iter == 0 && scalar != 0.0) {
+            x0 = make_double2(__dmul_rn(x0.x, scalar), __dmul_rn(x0.y, scalar));
+            x1 = make_double2(__dmul_rn(x1.x, scalar), __dmul_rn(x1.y, scalar));
+        }
+        __syncthreads();
+        buf[a] = x0, buf[a + pairs] = x1;
+        __syncthreads();
+    }
+    x[base + t] = buf[t], x[base + t + blockDim.x] = buf[t + blockDim.x];
+}
+
+// one stage in global memory (pairs >= CKKS_FFT_BLOCK / 2)
+__global__ void __launch_bounds__(EW_THREADS) k_ckks_ifft_stage(double2 *x, const double2 *tw, const uint32_t *group, int logs,
+                                                               int iter, uint32_t M, double scalar) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t gt = blockIdx.x * EW_THREADS + threadIdx.x;
+    const int logPairs = logs - iter - 1;
+    const uint32_t pairs = 1u << logPairs;
+    const uint32_t k = gt >> logPairs, j = gt & (pairs - 1), a = 2 * k * pairs + j;
+    double2 x0 = x[a], x1 = x[a + pairs];
+    ckks_gs<false>(x0, x1, ckks_tw(tw, group, k, logPairs, logs, M));
+    if (iter == 0 && scalar != 0.0) {
+        x0 = make_double2(__dmul_rn(x0.x, scalar), __dmul_rn(x0.y, scalar));
+        x1 = make_double2(__dmul_rn(x1.x, scalar), __dmul_rn(x1.y, scalar));
+    }
+    x[a] = x0, x[a + pairs] = x1;
+}
+
+// max |component| over the slots as the bit pattern of a non-negative double (orders like the value)
+__global__ void __launch_bounds__(EW_THREADS) k_ckks_absmax(const double2 *x, unsigned long long *out) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const double2 v = x[blockIdx.x * EW_THREADS + threadIdx.x];
+    const double m = fmax(fabs(v.x), fabs(v.y));
+    unsigned long long b = (unsigned long long) __double_as_longlong(m);
+    for (int o = 16; o; o >>= 1) b = max(b, __shfl_xor_sync(0xffffffffu, b, o));
+    if ((threadIdx.x & 31) == 0) atomicMax(out, b);
+}
+
+// decompose_array (reference src/rns_base.cu:49-103): coefficient x of limb i from round(re) (x < n/2) or round(im);
+// wide = 0: values below 2^64, wide = 1: below 2^128.  grid.y = limb
+__global__ void __launch_bounds__(EW_THREADS) k_ckks_decompose(u64 *out, const double2 *x, const Modulus *mod, size_t n, int wide) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const Modulus m = mod[blockIdx.y];
+    const size_t c = (size_t) blockIdx.x * EW_THREADS + threadIdx.x, slots = n >> 1;
+    const double cd = round(c < slots ? x[c].x : x[c - slots].y);
+    const bool negative = signbit(cd);
+    const double ad = fabs(cd);
+    u64 r;
+    if (!wide) {
+        r = barrett64((u64) ad, m);
+    } else {
+        const u64 lo = (u64) fmod(ad, 18446744073709551616.0), hi = (u64) (ad / 18446744073709551616.0);
+        r = barrett128(lo, hi, m);
+    }
+    out[(size_t) blockIdx.y * n + c] = negative ? m.q - r : r;   // a negative zero yields q, like the reference
+}
+
 // PhantomBatchEncoder (reference src/batchencoder.cu:51-60,91-95): slot i <-> position map[i] of the NTT-form vector
 __global__ void __launch_bounds__(EW_THREADS) k_batch_encode(u64 *out, const u64 *in, size_t count, const uint32_t *map, u64 t) {
     pdl_launch_dependents();

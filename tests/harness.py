@@ -60,6 +60,7 @@ def oracle():
         o.orc_multiply_relin.argtypes = [vp, ctypes.c_int, u64p, u64p, u64p, u64p]
         o.orc_hps_aux.argtypes = [vp, u64p, i32p]
         o.orc_bfv_multiply_hps.argtypes = [vp, u64p, u64p, u64p]
+        o.orc_ckks_encode.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_uint64, ctypes.c_double, u64p]
         o.orc_batch_encode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, ctypes.c_uint64, u64p]
         o.orc_batch_decode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, u64p]
         o.orc_decrypt.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.c_uint64, u64p]
@@ -123,6 +124,9 @@ def reference():
         r.ref_ntt.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_size_t, ctypes.c_int]
         r.ref_multiply_relin.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
         r.ref_multiply.argtypes = [vp, ctypes.c_size_t, u64p, u64p, u64p]
+        if hasattr(r, "ref_ckks_encode"):
+            r.ref_ckks_encode.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t, ctypes.c_size_t,
+                                          ctypes.c_double, u64p]
         if hasattr(r, "ref_batch_encode"):
             r.ref_batch_encode.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
             r.ref_batch_decode.argtypes = [vp, u64p, u64p]

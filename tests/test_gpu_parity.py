@@ -987,6 +987,49 @@ def test_end_to_end_semantics(scheme, mul_tech):
     assert [int(x) for x in enc.decode(ctx, sk.decrypt(ctx, c3))] == rot, "rotate_inplace"
 
 
+@pytest.mark.parametrize("n,bits,scale_log,chain_index", [(4096, [50, 40, 40, 50], 40, 1), (8192, [60, 40, 40, 40, 60], 40, 2),
+                                                         (65536, [60] + [40] * 15 + [60] * 4, 40, 1),
+                                                         (4096, [50, 50, 50, 50], 80, 1)])
+def test_ckks_encode(n, bits, scale_log, chain_index):
+    """pfhe_ckks_encode (PhantomCKKSEncoder::encode, src/ckks.cu:66-135) vs the oracle and vs the reference's encoder: full
+    and short inputs, a lower level, a scale above 2^64 (the 128-bit decomposition), the N=2^16, L=16 set.  Same
+    floating-point operations in the same order: the words are equal, no tolerance."""
+    alpha = 4 if n == 65536 else 1
+    ps = H.ParamSet("ckks_enc", n, bits, alpha, 3, 0)
+    ctx = make_context(ps)
+    o, oc = H.oracle(), ps.octx()
+    l = ps.size_Q - (chain_index - 1)
+    slots = n // 2
+    enc = pf.PhantomCKKSEncoder(ctx)
+    rng = np.random.default_rng(n + scale_log)
+    scale = 2.0 ** scale_log
+    r = H.reference()
+    h = None
+    if r is not None and hasattr(r, "ref_ckks_encode"):
+        h = r.ref_create(3, ps.n, P(ps.primes), ps.size_QP, ps.size_P, 0, 0, None, 0, scale, 0)
+        assert h, r.ref_last_error()
+    try:
+        for count in (slots, 3, 1):
+            z = rng.uniform(-4, 4, count) + 1j * rng.uniform(-4, 4, count)
+            flat = np.ascontiguousarray(z.view(np.float64))
+            want = np.zeros((l, n), dtype=np.uint64)
+            assert o.orc_ckks_encode(oc, l, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), count, scale, P(want)) == 0
+            got = host(enc.encode(ctx, z, scale, chain_index))
+            assert np.array_equal(got, want), f"ckks encode vs oracle, {count} values"
+            if h:
+                ref = np.zeros((l, n), dtype=np.uint64)
+                assert r.ref_ckks_encode(h, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), count, chain_index, scale,
+                                         P(ref)) == 0, r.ref_last_error()
+                assert np.array_equal(ref, want), f"oracle ckks encode vs reference, {count} values"
+    finally:
+        if h:
+            r.ref_destroy(h)
+    with pytest.raises(ValueError):
+        enc.encode(ctx, np.zeros(slots + 1), scale, chain_index)
+    with pytest.raises(ValueError):   # scale out of bounds for the modulus
+        enc.encode(ctx, [1.0], 2.0 ** 400, chain_index)
+
+
 def test_ckks_end_to_end_semantics():
     """CKKS at the ring level: Enc(m1) * Enc(m2), relinearised and rescaled on the engine, decrypts to m1 * m2 / q_last in
     Z[X]/(X^N + 1) within the noise (relative error < 1e-3 of the scale, the reference examples' criterion); a rotation

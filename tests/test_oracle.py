@@ -429,3 +429,34 @@ def test_batch_encoder_is_slotwise():
     short = np.array([5, (1 << 64) - 3], dtype=np.uint64)
     assert o.orc_batch_encode(n, t, P(short), 2, P(pa)) == 0 and o.orc_batch_decode(n, t, P(pa), P(back)) == 0
     assert int(back[0]) == 5 and int(back[1]) == t - 3 and not back[2:].any()
+
+
+def test_ckks_encode_is_the_canonical_embedding():
+    """orc_ckks_encode (src/ckks.cu:66-135): the encoded polynomial evaluates to scale * z_j at the 2N-th roots zeta^(5^j),
+    every limb holds the same centred integer coefficients, short inputs leave the other slots at zero."""
+    o = H.oracle()
+    n = 4096
+    ps = H.ParamSet("enc", n, [50, 40, 40, 50], 1, 3, 0)
+    oc, l, slots = ps.octx(), ps.size_Q, n // 2
+    rng = np.random.default_rng(0)
+    z = rng.uniform(-1, 1, slots) + 1j * rng.uniform(-1, 1, slots)
+    z[5:] = 0
+    flat = np.ascontiguousarray(z[:5].view(np.float64))
+    out = np.zeros((l, n), dtype=np.uint64)
+    scale = 2.0 ** 40
+    assert o.orc_ckks_encode(oc, l, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 5, scale, P(out)) == 0
+    w = out.copy()
+    o.orc_ntt_inverse(oc, P(w), l, (ctypes.c_int * l)(*range(l)))
+    coef = None
+    for i in range(l):
+        q = int(ps.primes[i])
+        c = np.array([int(v) if int(v) < q // 2 else int(v) - q for v in w[i]], dtype=float)
+        assert coef is None or np.array_equal(c, coef)
+        coef = c
+    pos, m = 1, 2 * n
+    for j in range(8):
+        val = np.polyval(coef[::-1], np.exp(2j * np.pi * pos / m)) / scale
+        assert abs(val - z[j]) < 1e-9
+        pos = (pos * 5) % m
+    assert o.orc_ckks_encode(oc, l, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 0, scale, P(out)) == -1
+    assert o.orc_ckks_encode(oc, l, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 5, 2.0 ** 200, P(out)) == -2
