@@ -135,9 +135,14 @@ int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *
  * `plain` = [l][N] residues in NTT form at chain_index with the given scale.  Same floating-point operations in the same
  * order as the reference's kernels: the same words.  Synchronises `stream` once, like the reference (the magnitude of the
  * encoded coefficients selects the decomposition and is validated against the modulus); coefficients above 128 bits
- * (the reference's slow multi-word path) are refused.  Decoding (compose_array + forward FFT) is not built. */
+ * (the reference's slow multi-word path) are refused. */
 int pfhe_ckks_encode(pfhe_engine *e, size_t chain_index, const double *values, size_t count, double scale,
                      uint64_t *plain, void *stream);
+/* PhantomCKKSEncoder::decode_internal (src/ckks.cu:137-190; compose_array src/rns_base.cu:174-258; special forward FFT
+ * src/fft.cu:90-218,352-384): `plain` = [l][N] residues in NTT form with the given scale, `values` = N/2 complex numbers
+ * on the device.  Same operations in the same order as the reference's kernels; up to 32 limbs.  Does not synchronise. */
+int pfhe_ckks_decode(pfhe_engine *e, size_t chain_index, const uint64_t *plain, double scale, double *values,
+                     void *stream);
 
 /* PhantomBatchEncoder::encode / decode for BFV / BGV (src/batchencoder.cu:62-118): `values` = count <= N slot values on
  * the device (the reference copies its std::vector there first), `plain` = the [N] plaintext polynomial mod t,

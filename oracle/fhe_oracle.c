@@ -1776,6 +1776,145 @@ int orc_ckks_encode(const orc_ctx *c, int l, const double *values, u64 count, do
     return rc;
 }
 
+/* PhantomCKKSEncoder::decode_internal (src/ckks.cu:137-190): inverse NTT, CRT composition to multi-word integers
+ * (compose_array_kernel, src/rns_base.cu:174-244), centring against (Q + 1) / 2, conversion to double word by word
+ * (plain multiply then add: the ternary in the reference keeps nvcc from fusing them), forward special FFT
+ * (src/fft.cu:90-218,352-384; imaginary part of the product: fma(x1.y, w.x, x1.x * w.y) in the shared-memory kernel, i.e.
+ * for pairs <= 1024, fma(x1.x, w.y, x1.y * w.x) in the one-stage kernel), bit-reversed readout.
+ * plain = [l][n] in NTT form; out = n/2 complex values (re, im interleaved). */
+int orc_ckks_decode(const orc_ctx *c, int l, const u64 *plain, double scale, double *out) {
+    const u64 n = c->n, slots = n >> 1, m = n << 1;
+    if (!(scale > 0) || l < 1 || l > 64) return -1;
+    {   /* "scale out of bounds", ckks.cu:148-151 */
+        big_t Qb = {{1}, 1};
+        for (int i = 0; i < l; i++) big_mul_word(&Qb, c->primes[i]);
+        int qbits = 64 * (Qb.len - 1);
+        for (u64 v = Qb.w[Qb.len - 1]; v; v >>= 1) qbits++;
+        if ((int)log2(scale) >= qbits) return -2;
+    }
+    int logs = 0;
+    while (((u64)1 << logs) < slots) logs++;
+    const u64 *Q = c->primes;
+    u64 *w = (u64 *)malloc((size_t)l * n * 8);
+    memcpy(w, plain, (size_t)l * n * 8);
+    int idx[64];
+    for (int i = 0; i < l; i++) idx[i] = i;
+    orc_ntt_inverse(c, w, l, idx);
+    /* multi-word constants: Q, punctured products, threshold */
+    u64 Qw[64] = {0}, thr[64] = {0}, hat[64][64], hinv[64];
+    {
+        big_t b = {{1}, 1};
+        for (int i = 0; i < l; i++) big_mul_word(&b, Q[i]);
+        for (int k = 0; k < l; k++) Qw[k] = k < b.len ? b.w[k] : 0;
+        u64 carry = 1; /* (Q + 1) >> 1 */
+        u64 t[64];
+        for (int k = 0; k < l; k++) {
+            t[k] = Qw[k] + carry;
+            carry = (carry && t[k] == 0) ? 1 : 0;
+        }
+        for (int k = 0; k < l; k++) thr[k] = (t[k] >> 1) | (k + 1 < l ? t[k + 1] << 63 : 0);
+        for (int i = 0; i < l; i++) {
+            big_t h = {{1}, 1};
+            for (int j = 0; j < l; j++)
+                if (j != i) big_mul_word(&h, Q[j]);
+            for (int k = 0; k < l; k++) hat[i][k] = k < h.len ? h.w[k] : 0;
+            hinv[i] = orc_invmod(qhat_mod(Q, l, i, Q[i]), Q[i]);
+        }
+    }
+    double *xr = (double *)calloc(slots, sizeof(double)), *xi = (double *)calloc(slots, sizeof(double));
+    const double inv_scale = 1.0 / scale;
+#pragma omp parallel for num_threads(g_threads)
+    for (u64 x = 0; x < n; x++) {
+        u64 acc[64] = {0};
+        if (l > 1) {
+            for (int i = 0; i < l; i++) {
+                u64 prod = orc_mulmod(w[(size_t)i * n + x], hinv[i], Q[i]);
+                u64 tmp[65], carry = 0;
+                for (int k = 0; k < l; k++) { /* hat_i * prod, low l words (multiply_uint_uint64) */
+                    u128 t = (u128)hat[i][k] * prod + carry;
+                    tmp[k] = (u64)t, carry = (u64)(t >> 64);
+                }
+                /* acc = (acc + tmp) mod Q: both < Q (add_uint_uint_mod) */
+                u64 cy = 0, sum[64];
+                for (int k = 0; k < l; k++) {
+                    u128 t = (u128)acc[k] + tmp[k] + cy;
+                    sum[k] = (u64)t, cy = (u64)(t >> 64);
+                }
+                int ge = cy != 0;
+                if (!ge) {
+                    ge = 1;
+                    for (int k = l - 1; k >= 0; k--)
+                        if (sum[k] != Qw[k]) {
+                            ge = sum[k] > Qw[k];
+                            break;
+                        }
+                }
+                if (ge) {
+                    u64 bw = 0;
+                    for (int k = 0; k < l; k++) {
+                        u128 t = (u128)sum[k] - Qw[k] - bw;
+                        sum[k] = (u64)t, bw = (u64)(t >> 64) & 1;
+                    }
+                }
+                memcpy(acc, sum, l * 8);
+            }
+        } else acc[0] = w[x];
+        int upper = 1; /* acc >= threshold */
+        for (int k = l - 1; k >= 0; k--)
+            if (acc[k] != thr[k]) {
+                upper = acc[k] > thr[k];
+                break;
+            }
+        double res = 0.0, s2 = inv_scale;
+        for (int k = 0; k < l; k++, s2 *= 18446744073709551616.0) {
+            if (upper) {
+                if (acc[k] > Qw[k]) {
+                    u64 d = acc[k] - Qw[k];
+                    res += d ? (double)d * s2 : 0.0;
+                } else {
+                    u64 d = Qw[k] - acc[k];
+                    res -= d ? (double)d * s2 : 0.0;
+                }
+            } else {
+                u64 d = acc[k];
+                res += d ? (double)d * s2 : 0.0;
+            }
+        }
+        if (x < slots) xr[x] = res;
+        else xi[x - slots] = res;
+    }
+    u64 *group = (u64 *)malloc((slots / 2 + 1) * 8);
+    {
+        u64 pos = 1;
+        for (u64 i = 0; i < slots / 2; i++) group[i] = pos, pos = (pos * 5) & (m - 1);
+    }
+    for (int iter = 0; iter < logs; iter++) { /* special_fft_forward */
+        const int logPairs = logs - iter - 1;
+        const u64 pairs = (u64)1 << logPairs;
+#pragma omp parallel for num_threads(g_threads)
+        for (u64 tid = 0; tid < slots / 2; tid++) {
+            u64 k = tid >> logPairs, j = tid & (pairs - 1), a = 2 * k * pairs + j, b = a + pairs;
+            uint32_t kk = (uint32_t)(k << logPairs);
+            u64 gi = (u64)(bitrev32(kk, 32) >> (33 - logs));
+            u64 psi = (group[gi] << logPairs) & (m - 1);
+            double wr, wi;
+            ckks_root(m, psi, &wr, &wi);
+            double t1 = xi[b] * wi;
+            double re = fma(xr[b], wr, -t1);
+            double im = logPairs <= 10 ? fma(xi[b], wr, xr[b] * wi) : fma(xr[b], wi, xi[b] * wr);
+            double ar = xr[a], ai = xi[a];
+            xr[a] = ar + re, xi[a] = ai + im;
+            xr[b] = ar - re, xi[b] = ai - im;
+        }
+    }
+    for (u64 i = 0; i < slots; i++) { /* bit_reverse_kernel */
+        u64 r = logs ? bitrev32((uint32_t)i, logs) : 0;
+        out[2 * r] = xr[i], out[2 * r + 1] = xi[i];
+    }
+    free(group); free(xr); free(xi); free(w);
+    return 0;
+}
+
 /* ------------------------------------------------------------------------------------------------------
  * rescale / mod switch
  * ---------------------------------------------------------------------------------------------------- */

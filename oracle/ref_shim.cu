@@ -425,6 +425,41 @@ int ref_ckks_encode(void *p, const double *values, size_t count, size_t chain_in
     SHIM_CATCH
 }
 
+/* PhantomCKKSEncoder::decode (ckks.cu:137-190): [l][n] NTT-form residues at chain_index with the given scale -> n/2
+ * complex values (re, im interleaved) */
+int ref_ckks_decode(void *p, const uint64_t *plain, size_t chain_index, double scale, double *values) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    PhantomCKKSEncoder enc(*h->ctx);
+    std::vector<cuDoubleComplex> zero(1, make_cuDoubleComplex(0.0, 0.0));
+    PhantomPlaintext pt;
+    enc.encode(*h->ctx, zero, scale, pt, chain_index);   /* a plaintext object of the right shape, level and scale */
+    size_t l = h->ctx->get_context_data(chain_index).parms().coeff_modulus().size();
+    cudaStreamSynchronize(cudaStreamPerThread);
+    cudaMemcpy(pt.data(), plain, l * h->n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    std::vector<cuDoubleComplex> out;
+    enc.decode(*h->ctx, pt, out);
+    for (size_t i = 0; i < out.size(); i++) values[2 * i] = cuCreal(out[i]), values[2 * i + 1] = cuCimag(out[i]);
+    return 0;
+    SHIM_CATCH
+}
+
+/* encode then decode inside the reference, no host round trip of the plaintext */
+int ref_ckks_roundtrip(void *p, const double *values, size_t count, size_t chain_index, double scale, double *out_values) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    PhantomCKKSEncoder enc(*h->ctx);
+    std::vector<cuDoubleComplex> v(count);
+    for (size_t i = 0; i < count; i++) v[i] = make_cuDoubleComplex(values[2 * i], values[2 * i + 1]);
+    PhantomPlaintext pt;
+    enc.encode(*h->ctx, v, scale, pt, chain_index);
+    std::vector<cuDoubleComplex> out;
+    enc.decode(*h->ctx, pt, out);
+    for (size_t i = 0; i < out.size(); i++) out_values[2 * i] = cuCreal(out[i]), out_values[2 * i + 1] = cuCimag(out[i]);
+    return 0;
+    SHIM_CATCH
+}
+
 /* PhantomBatchEncoder::encode / decode (batchencoder.cu:62-118): values[count] -> plain[n]; plain[n] -> values[n] */
 int ref_batch_encode(void *p, const uint64_t *values, size_t count, uint64_t *plain) {
     SHIM_TRY

@@ -58,6 +58,7 @@ _sigs = {
     "pfhe_rescale_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_mod_switch_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_ckks_encode": (ctypes.c_int, [vp, sz, vp, sz, ctypes.c_double, vp, vp]),
+    "pfhe_ckks_decode": (ctypes.c_int, [vp, sz, vp, ctypes.c_double, vp, vp]),
     "pfhe_batch_encode": (ctypes.c_int, [vp, vp, sz, vp, vp]),
     "pfhe_batch_decode": (ctypes.c_int, [vp, vp, vp, vp]),
     "pfhe_decrypt": (ctypes.c_int, [vp, sz, vp, sz, vp, ctypes.c_uint64, vp, vp]),

@@ -201,7 +201,7 @@ class PhantomCiphertext:
 
 
 class PhantomCKKSEncoder:
-    """Encoding half of PhantomCKKSEncoder (include/ckks.h, src/ckks.cu:66-135)."""
+    """PhantomCKKSEncoder (include/ckks.h, src/ckks.cu:66-190): encode and decode."""
 
     def __init__(self, context):
         if context.scheme != scheme_type.ckks:
@@ -223,6 +223,20 @@ class PhantomCKKSEncoder:
         plain = torch.empty((l, context.poly_degree), dtype=torch.int64, device=context.device)
         check(lib.pfhe_ckks_encode(context._h, chain_index, _ptr(d_in), v.size, float(scale), _ptr(plain), _stream()))
         return plain
+
+    def decode(self, context, plain, scale, chain_index=None):
+        """device plaintext [l][N] in NTT form with the given scale -> numpy complex128 [N/2] (the reference reads
+        chain_index and scale off the PhantomPlaintext; here the level defaults to the one with l limbs)"""
+        if plain.dim() != 2 or plain.shape[1] != context.poly_degree:
+            raise ValueError("plaintext shape")
+        if chain_index is None:
+            chain_index = context.size_Q - plain.shape[0] + 1
+        if context.coeff_modulus_size(chain_index) != plain.shape[0]:
+            raise ValueError("plaintext does not match chain_index")
+        out = torch.empty(self._slots * 2, dtype=torch.float64, device=plain.device)
+        check(lib.pfhe_ckks_decode(context._h, chain_index, _ptr(plain.contiguous()), float(scale), _ptr(out), _stream()))
+        torch.cuda.current_stream().synchronize()
+        return out.cpu().numpy().view(np.complex128)
 
 
 class PhantomBatchEncoder:

@@ -273,6 +273,14 @@ int pfhe_ckks_encode(pfhe_engine *e, size_t chain_index, const double *values, s
     e->impl.ckks_encode(l, reinterpret_cast<const double2 *>(values), count, scale, U(plain), S(stream));
     API_END
 }
+int pfhe_ckks_decode(pfhe_engine *e, size_t chain_index, const uint64_t *plain, double scale, double *values,
+                     void *stream) {
+    API_BEGIN
+    require(e && values && plain, "null pointer");
+    const int l = e->impl.limbs_at(chain_index);
+    e->impl.ckks_decode(l, U(plain), scale, reinterpret_cast<double2 *>(values), S(stream));
+    API_END
+}
 int pfhe_batch_encode(pfhe_engine *e, const uint64_t *values, size_t count, uint64_t *plain, void *stream) {
     API_BEGIN
     require(e && plain && (values || count == 0), "null pointer");

@@ -1498,17 +1498,9 @@ void Engine::decrypt(int l, const u64 *ct, int size, const u64 *sk_pow, u64 corr
     }
 }
 
-// PhantomCKKSEncoder::encode_internal (reference src/ckks.cu:66-135)
-void Engine::ckks_encode(int l, const double2 *values, size_t count, double scale, u64 *out, cudaStream_t st) {
-    if (scheme_ != Scheme::ckks) throw std::invalid_argument("unsupported scheme");
+void Engine::ckks_tables() {
     const size_t slots = n_ >> 1;
     const uint32_t M = (uint32_t) (n_ << 1);
-    const int logs = logn_ - 1;
-    if (count == 0) throw std::invalid_argument("Input vector is empty");
-    if (count > slots) throw std::invalid_argument("Input vector exceeds max slots");
-    std::vector<u64> ql(primes_.begin(), primes_.begin() + l);
-    const int qbits = hm::product_bits(ql);
-    if (scale <= 0 || (int) std::log2(scale) + 1 >= qbits) throw std::invalid_argument("scale out of bounds");
     if (!d_ckks_roots_.p) {
         // ComplexRoots (src/fft.cu:13-43): an eighth of the circle from polar(), the rest by symmetry
         const double PI_ = 3.1415926535897932384626433832795028842;
@@ -1542,6 +1534,81 @@ void Engine::ckks_encode(int l, const double2 *values, size_t count, double scal
         d_ckks_roots_.upload(roots), d_ckks_group_.upload(group);
         d_ckks_x_.alloc(slots), d_ckks_max_.alloc(1);
     }
+}
+
+// PhantomCKKSEncoder::decode_internal (reference src/ckks.cu:137-190)
+void Engine::ckks_decode(int l, const u64 *plain, double scale, double2 *out, cudaStream_t st) {
+    if (scheme_ != Scheme::ckks) throw std::invalid_argument("unsupported scheme");
+    if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
+    if (l > CKKS_MAX_WORDS) throw std::invalid_argument("too many limbs for the CKKS decoder");
+    std::vector<u64> ql(primes_.begin(), primes_.begin() + l);
+    if (scale <= 0 || (int) std::log2(scale) >= hm::product_bits(ql)) throw std::invalid_argument("scale out of bounds");
+    ckks_tables();
+    if ((int) ckks_dec_.size() <= size_Q_) ckks_dec_.resize(size_Q_ + 1);
+    if (!ckks_dec_[l]) {
+        auto d = std::make_unique<CkksDec>();
+        auto words = [&](hm::BigUint b) {
+            b.w.resize(l, 0);
+            return b.w;
+        };
+        hm::BigUint Qb;
+        for (u64 q : ql) Qb.mul_word(q);
+        std::vector<u64> Qw = words(Qb), thr(l), hat((size_t) l * l);
+        std::vector<Tw> hinv(l);
+        {   // (Q + 1) >> 1
+            std::vector<u64> t(Qw);
+            for (int k = 0; k < l; k++)
+                if (++t[k] != 0) break;
+            for (int k = 0; k < l; k++) thr[k] = (t[k] >> 1) | (k + 1 < l ? t[k + 1] << 63 : 0);
+        }
+        for (int i = 0; i < l; i++) {
+            hm::BigUint h;
+            for (int j = 0; j < l; j++)
+                if (j != i) h.mul_word(ql[j]);
+            const std::vector<u64> hw = words(h);
+            std::copy(hw.begin(), hw.end(), hat.begin() + (size_t) i * l);
+            hinv[i] = make_tw(hm::invmod(hm::product_mod(ql, i, ql[i]), ql[i]), ql[i]);
+        }
+        d->hat.upload(hat), d->Qw.upload(Qw), d->thr.upload(thr), d->hinv.upload(hinv);
+        ckks_dec_[l] = std::move(d);
+    }
+    const CkksDec &d = *ckks_dec_[l];
+    const size_t slots = n_ >> 1;
+    const uint32_t M = (uint32_t) (n_ << 1);
+    const int logs = logn_ - 1;
+    u64 *w = ws_.tmp.p;
+    ntt_inv_rows_range(w, plain, l, 0, st);
+    double2 *x = d_ckks_x_.p;
+    CkksComposeArgs a{x, w, d.hat.p, d.Qw.p, d.thr.p, d.hinv.p, d_mod_.p, 1.0 / scale, l, n_};
+    launch_pdl(k_ckks_compose, dim3((unsigned) (n_ / EW_THREADS)), EW_THREADS, 0, st, a);
+    check_launch("k_ckks_compose");
+    const int blk_log = std::min(logs, CKKS_FFT_LOG_BLOCK);
+    const int iter_begin = logs - blk_log;
+    for (int iter = 0; iter < iter_begin; iter++) {
+        launch_pdl(k_ckks_fft_stage, dim3((unsigned) (slots / 2 / EW_THREADS)), EW_THREADS, 0, st, x,
+                   (const double2 *) d_ckks_roots_.p, (const uint32_t *) d_ckks_group_.p, logs, iter, M);
+        check_launch("k_ckks_fft_stage");
+    }
+    launch_pdl(k_ckks_fft_block, dim3((unsigned) (slots >> blk_log)), dim3(1u << (blk_log - 1)),
+               ((size_t) 1 << blk_log) * sizeof(double2), st, x, (const double2 *) d_ckks_roots_.p,
+               (const uint32_t *) d_ckks_group_.p, logs, iter_begin, M);
+    check_launch("k_ckks_fft_block");
+    launch_pdl(k_ckks_unplace, dim3((unsigned) (slots / EW_THREADS)), EW_THREADS, 0, st, out, (const double2 *) x, logs);
+    check_launch("k_ckks_unplace");
+}
+
+// PhantomCKKSEncoder::encode_internal (reference src/ckks.cu:66-135)
+void Engine::ckks_encode(int l, const double2 *values, size_t count, double scale, u64 *out, cudaStream_t st) {
+    if (scheme_ != Scheme::ckks) throw std::invalid_argument("unsupported scheme");
+    const size_t slots = n_ >> 1;
+    const uint32_t M = (uint32_t) (n_ << 1);
+    const int logs = logn_ - 1;
+    if (count == 0) throw std::invalid_argument("Input vector is empty");
+    if (count > slots) throw std::invalid_argument("Input vector exceeds max slots");
+    std::vector<u64> ql(primes_.begin(), primes_.begin() + l);
+    const int qbits = hm::product_bits(ql);
+    if (scale <= 0 || (int) std::log2(scale) + 1 >= qbits) throw std::invalid_argument("scale out of bounds");
+    ckks_tables();
     double2 *x = d_ckks_x_.p;
     launch_pdl(k_ckks_place, dim3((unsigned) (slots / EW_THREADS)), EW_THREADS, 0, st, x, values, count, logs);
     check_launch("k_ckks_place");

@@ -668,6 +668,145 @@ __global__ void __launch_bounds__(EW_THREADS) k_ckks_ifft_stage(double2 *x, cons
     x[a] = x0, x[a + pairs] = x1;
 }
 
+// ---- decoding direction (PhantomCKKSEncoder::decode_internal, src/ckks.cu:137-190) ---------------------------------
+// forward butterfly (x0 + x1 w, x0 - x1 w); imaginary part of the product in the reference's two contraction forms (see
+// ckks_gs): shared-memory kernel fma(x1.y, w.x, x1.x * w.y), one-stage kernel fma(x1.x, w.y, x1.y * w.x)
+template<bool BLOCK_FORM>
+__device__ __forceinline__ void ckks_ct(double2 &x0, double2 &x1, const double2 w) {
+    const double t1 = __dmul_rn(x1.y, w.y);
+    const double re = __fma_rn(x1.x, w.x, -t1);
+    const double im = BLOCK_FORM ? __fma_rn(x1.y, w.x, __dmul_rn(x1.x, w.y)) : __fma_rn(x1.x, w.y, __dmul_rn(x1.y, w.x));
+    const double2 a = x0;
+    x0 = make_double2(__dadd_rn(a.x, re), __dadd_rn(a.y, im));
+    x1 = make_double2(__dadd_rn(a.x, -re), __dadd_rn(a.y, -im));
+}
+__device__ __forceinline__ double2 ckks_tw_fwd(const double2 *tw, const uint32_t *group, uint32_t k, int logPairs, int logs,
+                                               uint32_t M) {
+    uint32_t psi = group[__brev(k << logPairs) >> (33 - logs)];
+    return tw[(psi << logPairs) & (M - 1)];
+}
+// stages iter_begin .. logs-1 (pairs <= CKKS_FFT_BLOCK / 2) inside blocks
+__global__ void __launch_bounds__(CKKS_FFT_BLOCK / 2) k_ckks_fft_block(double2 *x, const double2 *tw, const uint32_t *group,
+                                                                       int logs, int iter_begin, uint32_t M) {
+    extern __shared__ __align__(16) unsigned char ckks_smem[];
+    double2 *buf = reinterpret_cast<double2 *>(ckks_smem);
+    pdl_launch_dependents();
+    pdl_wait();
+    const int nb = blockDim.x * 2;
+    const uint32_t base = blockIdx.x * nb, t = threadIdx.x;
+    buf[t] = x[base + t], buf[t + blockDim.x] = x[base + t + blockDim.x];
+    __syncthreads();
+    for (int iter = iter_begin; iter < logs; iter++) {
+        const int logPairs = logs - iter - 1;
+        const uint32_t pairs = 1u << logPairs;
+        const uint32_t gt = blockIdx.x * blockDim.x + t;
+        const uint32_t k = gt >> logPairs, j = gt & (pairs - 1);
+        const uint32_t a = 2 * k * pairs + j - base;
+        double2 x0 = buf[a], x1 = buf[a + pairs];
+        ckks_ct<true>(x0, x1, ckks_tw_fwd(tw, group, k, logPairs, logs, M));
+        buf[a] = x0, buf[a + pairs] = x1;
+        __syncthreads();
+    }
+    x[base + t] = buf[t], x[base + t + blockDim.x] = buf[t + blockDim.x];
+}
+__global__ void __launch_bounds__(EW_THREADS) k_ckks_fft_stage(double2 *x, const double2 *tw, const uint32_t *group, int logs,
+                                                              int iter, uint32_t M) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t gt = blockIdx.x * EW_THREADS + threadIdx.x;
+    const int logPairs = logs - iter - 1;
+    const uint32_t pairs = 1u << logPairs;
+    const uint32_t k = gt >> logPairs, j = gt & (pairs - 1), a = 2 * k * pairs + j;
+    double2 x0 = x[a], x1 = x[a + pairs];
+    ckks_ct<false>(x0, x1, ckks_tw_fwd(tw, group, k, logPairs, logs, M));
+    x[a] = x0, x[a + pairs] = x1;
+}
+__global__ void __launch_bounds__(EW_THREADS) k_ckks_unplace(double2 *out, const double2 *x, int logs) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const uint32_t i = blockIdx.x * EW_THREADS + threadIdx.x;
+    out[logs ? (__brev(i) >> (32 - logs)) : 0] = x[i];   // bit_reverse_kernel, ckks.cu:9-15
+}
+
+// compose_array_kernel (reference src/rns_base.cu:174-244): CRT composition of one coefficient to a multi-word integer
+// mod Q, centring against (Q + 1) / 2, conversion to double word by word (multiply, then add: not fused in the
+// reference), times 1 / scale.  Coefficient x < n/2 becomes the real part of slot x, the others the imaginary parts.
+constexpr int CKKS_MAX_WORDS = 32;
+struct CkksComposeArgs {
+    double2 *x;
+    const u64 *w;        // [l][n] coefficient form
+    const u64 *hat;      // [l][l] punctured products, little-endian words
+    const u64 *Qw, *thr; // [l]
+    const Tw *hinv;      // [l]
+    const Modulus *mod;
+    double inv_scale;
+    int l;
+    size_t n;
+};
+__global__ void __launch_bounds__(EW_THREADS) k_ckks_compose(const CkksComposeArgs a) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t c = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
+    const int l = a.l;
+    u64 acc[CKKS_MAX_WORDS];
+    for (int k = 0; k < l; k++) acc[k] = 0;
+    if (l > 1) {
+        for (int i = 0; i < l; i++) {
+            const u64 prod = mul_shoup(a.w[(size_t) i * a.n + c], a.hinv[i], a.mod[i].q);
+            const u64 *h = a.hat + (size_t) i * l;
+            u64 carry = 0, cy = 0;
+            for (int k = 0; k < l; k++) {   // acc += hat_i * prod (low l words: the product is below Q)
+                const unsigned __int128 t = (unsigned __int128) h[k] * prod + carry;
+                carry = (u64) (t >> 64);
+                const unsigned __int128 s = (unsigned __int128) acc[k] + (u64) t + cy;
+                acc[k] = (u64) s, cy = (u64) (s >> 64);
+            }
+            bool ge = cy != 0;   // acc >= Q ?
+            if (!ge) {
+                ge = true;
+                for (int k = l - 1; k >= 0; k--)
+                    if (acc[k] != a.Qw[k]) {
+                        ge = acc[k] > a.Qw[k];
+                        break;
+                    }
+            }
+            if (ge) {
+                u64 bw = 0;
+                for (int k = 0; k < l; k++) {
+                    const unsigned __int128 t = (unsigned __int128) acc[k] - a.Qw[k] - bw;
+                    acc[k] = (u64) t, bw = (u64) (t >> 64) & 1;
+                }
+            }
+        }
+    } else {
+        acc[0] = a.w[c];
+    }
+    bool upper = true;   // acc >= (Q + 1) / 2 ?
+    for (int k = l - 1; k >= 0; k--)
+        if (acc[k] != a.thr[k]) {
+            upper = acc[k] > a.thr[k];
+            break;
+        }
+    double res = 0.0, s2 = a.inv_scale;
+    for (int k = 0; k < l; k++, s2 = __dmul_rn(s2, 18446744073709551616.0)) {
+        if (upper) {
+            if (acc[k] > a.Qw[k]) {
+                const u64 d = acc[k] - a.Qw[k];
+                res = __dadd_rn(res, d ? __dmul_rn((double) d, s2) : 0.0);
+            } else {
+                const u64 d = a.Qw[k] - acc[k];
+                res = __dadd_rn(res, -(d ? __dmul_rn((double) d, s2) : 0.0));
+            }
+        } else {
+            const u64 d = acc[k];
+            res = __dadd_rn(res, d ? __dmul_rn((double) d, s2) : 0.0);
+        }
+    }
+    const size_t slots = a.n >> 1;
+    if (c < slots) a.x[c].x = res;
+    else a.x[c - slots].y = res;
+}
+
 // max |component| over the slots as the bit pattern of a non-negative double (orders like the value)
 __global__ void __launch_bounds__(EW_THREADS) k_ckks_absmax(const double2 *x, unsigned long long *out) {
     pdl_launch_dependents();

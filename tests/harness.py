@@ -11,7 +11,7 @@ import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 ORACLE_DIR = os.path.join(ROOT, "oracle")
 ORACLE_SO = os.path.join(ORACLE_DIR, "liboracle.so")
-REF_SO = os.path.join(ORACLE_DIR, "_ref", "libphantom_ref.so")
+REF_SO = os.environ.get("PFHE_REF_SO", os.path.join(ORACLE_DIR, "_ref", "libphantom_ref.so"))
 
 u64p = ctypes.POINTER(ctypes.c_uint64)
 u32p = ctypes.POINTER(ctypes.c_uint32)
@@ -61,6 +61,7 @@ def oracle():
         o.orc_hps_aux.argtypes = [vp, u64p, i32p]
         o.orc_bfv_multiply_hps.argtypes = [vp, u64p, u64p, u64p]
         o.orc_ckks_encode.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_uint64, ctypes.c_double, u64p]
+        o.orc_ckks_decode.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
         o.orc_batch_encode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, ctypes.c_uint64, u64p]
         o.orc_batch_decode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, u64p]
         o.orc_decrypt.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.c_uint64, u64p]
@@ -127,6 +128,11 @@ def reference():
         if hasattr(r, "ref_ckks_encode"):
             r.ref_ckks_encode.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t, ctypes.c_size_t,
                                           ctypes.c_double, u64p]
+        if hasattr(r, "ref_ckks_decode"):
+            r.ref_ckks_decode.argtypes = [vp, u64p, ctypes.c_size_t, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+        if hasattr(r, "ref_ckks_roundtrip"):
+            r.ref_ckks_roundtrip.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t, ctypes.c_size_t,
+                                             ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
         if hasattr(r, "ref_batch_encode"):
             r.ref_batch_encode.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
             r.ref_batch_decode.argtypes = [vp, u64p, u64p]

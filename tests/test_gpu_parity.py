@@ -1030,6 +1030,57 @@ def test_ckks_encode(n, bits, scale_log, chain_index):
         enc.encode(ctx, [1.0], 2.0 ** 400, chain_index)
 
 
+@pytest.mark.parametrize("n,bits,scale_log,chain_index", [(4096, [50, 40, 40, 50], 40, 1), (8192, [60, 40, 40, 40, 60], 40, 2),
+                                                         (8192, [60, 40, 40, 40, 60], 30, 4),
+                                                         (65536, [60] + [40] * 15 + [60] * 4, 40, 1),
+                                                         (4096, [50, 50, 50, 50], 80, 1)])
+def test_ckks_decode(n, bits, scale_log, chain_index):
+    """pfhe_ckks_decode (PhantomCKKSEncoder::decode, src/ckks.cu:137-190) vs the oracle and vs the reference's decoder, on
+    encoded messages and on uniformly random residues (every word of the CRT composition in play): the doubles are equal
+    bit for bit, no tolerance.  One limb (the reference's l = 1 branch), a lower level, a scale above 2^64, N=2^16 L=16.
+    Then decode(encode(z)) returns z within the encoder's rounding (|error| * scale < N).  (The reference's rns_base.cu
+    is built unoptimised for this, see oracle/Makefile.ref: at -O3 its multi-word carry chain is miscompiled and the
+    reference does not decode its own encodings.)"""
+    alpha = 4 if n == 65536 else 1
+    ps = H.ParamSet("ckks_dec", n, bits, alpha, 3, 0)
+    ctx = make_context(ps)
+    o, oc = H.oracle(), ps.octx()
+    l = ps.size_Q - (chain_index - 1)
+    slots = n // 2
+    enc = pf.PhantomCKKSEncoder(ctx)
+    rng = np.random.default_rng(n + scale_log + chain_index)
+    scale = 2.0 ** scale_log
+    dp = ctypes.POINTER(ctypes.c_double)
+    r = H.reference()
+    h = None
+    if r is not None and hasattr(r, "ref_ckks_decode"):
+        h = r.ref_create(3, ps.n, P(ps.primes), ps.size_QP, ps.size_P, 0, 0, None, 0, scale, 0)
+        assert h, r.ref_last_error()
+    try:
+        z = rng.uniform(-4, 4, slots) + 1j * rng.uniform(-4, 4, slots)
+        encoded = host(enc.encode(ctx, z, scale, chain_index))
+        uniform = np.stack([rng.integers(0, q, n, dtype=np.uint64) for q in ps.primes[:l]])
+        for name, plain in (("encoded", encoded), ("uniform", uniform)):
+            plain = np.ascontiguousarray(plain)
+            want = np.zeros(2 * slots, dtype=np.float64)
+            assert o.orc_ckks_decode(oc, l, P(plain), scale, want.ctypes.data_as(dp)) == 0
+            got = enc.decode(ctx, dev(plain), scale, chain_index).view(np.float64)
+            assert np.array_equal(got.view(np.uint64), want.view(np.uint64)), f"ckks decode vs oracle, {name}"
+            if h:
+                ref = np.zeros(2 * slots, dtype=np.float64)
+                assert r.ref_ckks_decode(h, P(plain), chain_index, scale, ref.ctypes.data_as(dp)) == 0, r.ref_last_error()
+                assert np.array_equal(ref.view(np.uint64), want.view(np.uint64)), f"oracle ckks decode vs reference, {name}"
+        back = enc.decode(ctx, dev(encoded), scale)
+        assert np.max(np.abs(back - z)) * scale < n, "decode(encode(z)) != z"
+    finally:
+        if h:
+            r.ref_destroy(h)
+    with pytest.raises(ValueError):   # scale out of bounds for the modulus
+        enc.decode(ctx, dev(encoded), 2.0 ** 800, chain_index)
+    with pytest.raises(ValueError):
+        enc.decode(ctx, dev(encoded[:1]), scale, chain_index if l > 1 else 2)
+
+
 def test_ckks_end_to_end_semantics():
     """CKKS at the ring level: Enc(m1) * Enc(m2), relinearised and rescaled on the engine, decrypts to m1 * m2 / q_last in
     Z[X]/(X^N + 1) within the noise (relative error < 1e-3 of the scale, the reference examples' criterion); a rotation

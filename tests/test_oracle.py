@@ -431,6 +431,38 @@ def test_batch_encoder_is_slotwise():
     assert int(back[0]) == 5 and int(back[1]) == t - 3 and not back[2:].any()
 
 
+def test_ckks_decode_inverts_encode_and_composes_centred_integers():
+    """orc_ckks_decode (src/ckks.cu:137-190, compose_array src/rns_base.cu:174-258): decode(encode(z)) = z within the
+    encoder's rounding at full, lower and one-limb levels; a plaintext holding the constant integer c in every limb
+    (c positive, negative, above 2^64) decodes to c / scale in every slot: CRT composition, centring and the word-wise
+    conversion to double checked against Python integers."""
+    o = H.oracle()
+    dp = ctypes.POINTER(ctypes.c_double)
+    for n, bits in ((4096, [50, 40, 40, 50]), (8192, [60, 40, 40, 40, 60])):
+        ps = H.ParamSet("dec", n, bits, 1, 3, 0)
+        oc, slots = ps.octx(), n // 2
+        rng = np.random.default_rng(n)
+        z = rng.uniform(-3, 3, slots) + 1j * rng.uniform(-3, 3, slots)
+        flat = np.ascontiguousarray(z.view(np.float64))
+        for l, scale in ((ps.size_Q, 2.0 ** 40), (2, 2.0 ** 40), (1, 2.0 ** 30)):
+            plain = np.zeros((l, n), dtype=np.uint64)
+            assert o.orc_ckks_encode(oc, l, flat.ctypes.data_as(dp), slots, scale, P(plain)) == 0
+            back = np.zeros(2 * slots)
+            assert o.orc_ckks_decode(oc, l, P(plain), scale, back.ctypes.data_as(dp)) == 0
+            assert np.max(np.abs(back.view(np.complex128) - z)) * scale < n
+        l = ps.size_Q
+        for c in (12345, -987654321, (1 << 70) + 12345, -(1 << 90) + 7):
+            plain = np.zeros((l, n), dtype=np.uint64)   # NTT form of the constant polynomial c: c in every position
+            for i in range(l):
+                plain[i, :] = c % int(ps.primes[i])
+            back = np.zeros(2 * slots)
+            scale = 2.0 ** 20
+            assert o.orc_ckks_decode(oc, l, P(plain), scale, back.ctypes.data_as(dp)) == 0
+            v = back.view(np.complex128)
+            assert np.max(np.abs(v.real - c / scale)) <= abs(c / scale) * 1e-12 and np.max(np.abs(v.imag)) <= abs(c / scale) * 1e-12
+        assert o.orc_ckks_decode(oc, l, P(plain), 2.0 ** 400, back.ctypes.data_as(dp)) != 0
+
+
 def test_ckks_encode_is_the_canonical_embedding():
     """orc_ckks_encode (src/ckks.cu:66-135): the encoded polynomial evaluates to scale * z_j at the 2N-th roots zeta^(5^j),
     every limb holds the same centred integer coefficients, short inputs leave the other slots at zero."""
