@@ -1038,7 +1038,7 @@ def test_ckks_decode(n, bits, scale_log, chain_index):
     """pfhe_ckks_decode (PhantomCKKSEncoder::decode, src/ckks.cu:137-190) vs the oracle and vs the reference's decoder, on
     encoded messages and on uniformly random residues (every word of the CRT composition in play): the doubles are equal
     bit for bit, no tolerance.  One limb (the reference's l = 1 branch), a lower level, a scale above 2^64, N=2^16 L=16.
-    Then decode(encode(z)) returns z within the encoder's rounding (|error| * scale < N).  (The reference's rns_base.cu
+    Then decode(encode(z)) returns z within the encoder's rounding (|error| < N / scale, or double precision).  (The reference's rns_base.cu
     is built unoptimised for this, see oracle/Makefile.ref: at -O3 its multi-word carry chain is miscompiled and the
     reference does not decode its own encodings.)"""
     alpha = 4 if n == 65536 else 1
@@ -1071,7 +1071,7 @@ def test_ckks_decode(n, bits, scale_log, chain_index):
                 assert r.ref_ckks_decode(h, P(plain), chain_index, scale, ref.ctypes.data_as(dp)) == 0, r.ref_last_error()
                 assert np.array_equal(ref.view(np.uint64), want.view(np.uint64)), f"oracle ckks decode vs reference, {name}"
         back = enc.decode(ctx, dev(encoded), scale)
-        assert np.max(np.abs(back - z)) * scale < n, "decode(encode(z)) != z"
+        assert np.max(np.abs(back - z)) < max(n / scale, 1e-13), "decode(encode(z)) != z"   # rounding, or double precision
     finally:
         if h:
             r.ref_destroy(h)
@@ -1085,7 +1085,7 @@ def test_ckks_end_to_end_semantics():
     """CKKS at the ring level: Enc(m1) * Enc(m2), relinearised and rescaled on the engine, decrypts to m1 * m2 / q_last in
     Z[X]/(X^N + 1) within the noise (relative error < 1e-3 of the scale, the reference examples' criterion); a rotation
     decrypts to m(X^elt).  Key generation / encryption written out here; multiply, relinearize, rescale, rotate and
-    decrypt run on the engine."""
+    decrypt run on the engine.  Then the same at the slot level with the engine's CKKS encoder and decoder around it."""
     n = 4096
     ps = H.ParamSet("ckks_e2e", n, [60, 40, 40, 40, 60], 1, 3, 0)
     ctx = make_context(ps, [1])
@@ -1184,6 +1184,29 @@ def test_ckks_end_to_end_semantics():
             rot[e] += v
     got = decrypt_coeffs(c3)
     assert max(abs(a - b) for a, b in zip(got, rot)) < 2 ** 24, "rotation decrypts to m(X^elt) within key-switch noise"
+
+    # slot level, encoder and decoder on the engine too: decode(decrypt(Enc(encode(z1)) * Enc(encode(z2)))) = z1 * z2 slot by
+    # slot, and a rotation by one step moves slot i + 1 to slot i
+    cenc = pf.PhantomCKKSEncoder(ctx)
+    slots = n // 2
+    z1 = rng.uniform(-1, 1, slots) + 1j * rng.uniform(-1, 1, slots)
+    z2 = rng.uniform(-1, 1, slots) + 1j * rng.uniform(-1, 1, slots)
+
+    def encrypt_plain(pt):   # pt: [l][n] NTT form
+        e = ntt(residues(rng.integers(-3, 4, n)))[:l]
+        a = np.stack([rng.integers(0, p, n, dtype=np.uint64) for p in primes[:l]])
+        return pf.PhantomCiphertext.from_host(ctx, np.stack([add(add(pt, e), neg(mul(a, s[:l]))), a]), scale=scale)
+
+    d1, d2 = encrypt_plain(host(cenc.encode(ctx, z1, scale))), encrypt_plain(host(cenc.encode(ctx, z2, scale)))
+    assert np.max(np.abs(cenc.decode(ctx, sk.decrypt(ctx, d1), scale) - z1)) < 1e-6, "decode(decrypt(encrypt(encode(z)))) = z"
+    d3 = encrypt_plain(host(cenc.encode(ctx, z1, scale)))
+    pf.multiply_and_relin_inplace(ctx, d1, d2, rlk)
+    prod = pf.rescale_to_next(ctx, d1)
+    got = cenc.decode(ctx, sk.decrypt(ctx, prod), scale * scale / primes[l - 1])
+    assert np.max(np.abs(got - z1 * z2)) < 1e-5, "slot-wise product"
+    pf.rotate_inplace(ctx, d3, 1, glk)
+    got = cenc.decode(ctx, sk.decrypt(ctx, d3), scale)
+    assert np.max(np.abs(got - np.roll(z1, -1))) < 1e-4, "rotation by one slot"
 
 
 def test_serialisation_against_unmodified_reference():
