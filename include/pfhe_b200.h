@@ -138,6 +138,38 @@ int pfhe_multiply_and_relin(pfhe_engine *e, size_t chain_index, const uint64_t *
  * (the reference's slow multi-word path) are refused. */
 int pfhe_ckks_encode(pfhe_engine *e, size_t chain_index, const double *values, size_t count, double scale,
                      uint64_t *plain, void *stream);
+/* ---- samplers, key generation, encryption ------------------------------------------------
+ * The reference draws a fresh 64-byte seed from std::random_device for every random polynomial (random_bytes,
+ * include/prng.cuh:10-32) and expands it on the device with its Salsa20-core generator (src/prng.cu:17-133).  Here the
+ * caller supplies the seeds (`seed*` = 64 bytes on the host each); given the seed, every polynomial below is the one the
+ * reference's kernels produce.  All buffers are device memory; nothing synchronises unless stated.
+ *
+ * sample_ternary_poly / sample_error_poly / sample_uniform_poly (src/prng.cu:142-244): kind 0 / 1 / 2, out = [limbs][N]
+ * over the first `limbs` key primes. */
+int pfhe_sample_poly(pfhe_engine *e, int kind, size_t limbs, const uint8_t *seed, uint64_t *out, void *stream);
+/* PhantomSecretKey::gen_secretkey (src/secretkey.cu:345-378): secret_key = [size_QP][N], NTT form (secret_key_array()) */
+int pfhe_gen_secretkey(pfhe_engine *e, const uint8_t *seed, uint64_t *secret_key, void *stream);
+/* PhantomSecretKey::encrypt_zero_symmetric (src/secretkey.cu:232-295): ct = [2][l][N] = (-(a s + e), a) (e times t for BGV),
+ * NTT form (BFV at a data level: coefficient form).  chain_index 0 = the key level (l = size_QP): that is gen_publickey
+ * (src/secretkey.cu:380-392) and each digit of a key-switching key. */
+int pfhe_encrypt_zero_symmetric(pfhe_engine *e, size_t chain_index, const uint64_t *secret_key, const uint8_t *seed_a,
+                                const uint8_t *seed_e, uint64_t *ct, void *stream);
+/* PhantomPublicKey::encrypt_zero_asymmetric_internal (src/secretkey.cu:10-128): public_key = [2][size_QP][N] (key level, NTT
+ * form), ct = [2][size_Q][N]: (u pk + e) at the key level divided by P.  chain_index must be 1 (the reference's own
+ * mod-down step addresses the first data level only). */
+int pfhe_encrypt_zero_asymmetric(pfhe_engine *e, size_t chain_index, const uint64_t *public_key, const uint8_t *seed_u,
+                                 const uint8_t *seed_e, uint64_t *ct, void *stream);
+/* PhantomSecretKey::generate_one_kswitch_key (src/secretkey.cu:297-343): digits = HOST array of dnum = size_Q / size_P device
+ * buffers [2][size_QP][N]; new_key = [size_QP][N] NTT form (s^2 for gen_relinkey, the rotated key for a Galois key);
+ * seeds = dnum pairs (a, e) of 64 bytes.  Synchronises the stream once. */
+int pfhe_gen_kswitch_key(pfhe_engine *e, const uint64_t *new_key, const uint64_t *secret_key, const uint8_t *seeds,
+                         uint64_t *const *digits, void *stream);
+/* the secret key under a Galois automorphism (create_galois_keys, src/secretkey.cu:443-451): rotated = [size_QP][N] */
+int pfhe_galois_secret_key(pfhe_engine *e, const uint64_t *secret_key, uint32_t galois_elt, uint64_t *rotated, void *stream);
+/* the last step of encrypt_symmetric / encrypt_asymmetric (src/secretkey.cu:130-190, 463-530): ct[0] += plaintext.
+ * BFV: multiply_add_plain_with_scaling_variant (src/scalingvariant.cu:10-34), plain = [N] mod t; CKKS: plain = [l][N] NTT
+ * form; BGV: plain = [N] mod t, lifted to every limb and transformed. */
+int pfhe_encrypt_add_plain(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, void *stream);
 /* PhantomCKKSEncoder::decode_internal (src/ckks.cu:137-190; compose_array src/rns_base.cu:174-258; special forward FFT
  * src/fft.cu:90-218,352-384): `plain` = [l][N] residues in NTT form with the given scale, `values` = N/2 complex numbers
  * on the device.  Same operations in the same order as the reference's kernels; up to 32 limbs.  Does not synchronise. */

@@ -1996,3 +1996,221 @@ void orc_bgv_mod_switch(const orc_ctx *c, int l, u64 *in, int size, u64 *out) {
         orc_ntt_forward(c, co, nl, idx);
     }
 }
+
+/* =====================================================================================================
+ * Samplers, key generation, encryption (src/prng.cu, src/secretkey.cu, src/scalingvariant.cu)
+ * ===================================================================================================== */
+
+/* salsa20_gpu, src/prng.cu:17-133, for outlen = 64 (the only length the samplers ask for): the Salsa20 core, ten double
+ * rounds, over the state {key bytes 0..31 as 8 little-endian words, nonce low, nonce high, key bytes 32..55 as 6 words},
+ * input added back; the 64 output bytes are the 16 words in little-endian order. */
+void orc_prng_block(uint8_t out[64], const uint8_t *key, u64 nonce) {
+    static const unsigned char quarter[8][4] = {{0, 4, 8, 12}, {5, 9, 13, 1}, {10, 14, 2, 6}, {15, 3, 7, 11},
+                                                {0, 1, 2, 3},  {5, 6, 7, 4},  {10, 11, 8, 9}, {15, 12, 13, 14}};
+    static const int rot[4] = {7, 9, 13, 18};
+    uint32_t in[16], x[16];
+    for (int i = 0; i < 14; i++) {
+        const uint8_t *p = key + 4 * i;
+        uint32_t w = (uint32_t)p[0] | ((uint32_t)p[1] << 8) | ((uint32_t)p[2] << 16) | ((uint32_t)p[3] << 24);
+        in[i < 8 ? i : i + 2] = w;
+    }
+    in[8] = (uint32_t)nonce;
+    in[9] = (uint32_t)(nonce >> 32);
+    memcpy(x, in, sizeof(x));
+    for (int round = 0; round < 20; round += 2)
+        for (int qi = 0; qi < 8; qi++) {
+            const unsigned char *q = quarter[qi]; /* (a, b, c, d): b ^= (a+d)<<<7, c ^= (b+a)<<<9, d ^= (c+b)<<<13, a ^= (d+c)<<<18 */
+            int tgt[4] = {q[1], q[2], q[3], q[0]}, s0[4] = {q[0], q[1], q[2], q[3]}, s1[4] = {q[3], q[0], q[1], q[2]};
+            for (int k = 0; k < 4; k++) {
+                uint32_t v = x[s0[k]] + x[s1[k]];
+                x[tgt[k]] ^= (v << rot[k]) | (v >> (32 - rot[k]));
+            }
+        }
+    for (int i = 0; i < 16; i++) {
+        uint32_t w = x[i] + in[i];
+        out[4 * i] = (uint8_t)w, out[4 * i + 1] = (uint8_t)(w >> 8), out[4 * i + 2] = (uint8_t)(w >> 16), out[4 * i + 3] = (uint8_t)(w >> 24);
+    }
+}
+
+static int popcount8(unsigned v) { return __builtin_popcount(v & 0xFF); }
+
+/* sample_ternary_poly (:142-164), sample_error_poly (:222-244), sample_uniform_poly (:174-204); the loops run over the
+ * reference's thread index so that the nonces read as they do there.  out = [limbs][n] over primes 0 .. limbs-1 */
+int orc_sample_poly(const orc_ctx *c, int kind, int limbs, const uint8_t *seed, u64 *out) {
+    const u64 n = c->n;
+    if (limbs < 1 || limbs > c->size_QP) return -1;
+    uint8_t blk[64];
+    if (kind == 0 || kind == 1) {
+        for (u64 tid = 0; tid < n * (u64)limbs; tid++) {
+            const u64 q = c->primes[tid / n];
+            orc_prng_block(blk, seed, tid % n);
+            if (kind == 0) {
+                unsigned r = blk[0] % 3;
+                out[tid] = r == 0 ? q - 1 : r - 1;
+            } else {
+                int cbd = popcount8(blk[0]) + popcount8(blk[1]) + popcount8(blk[2] & 0x1F) - popcount8(blk[3]) - popcount8(blk[4]) -
+                          popcount8(blk[5] & 0x1F);
+                out[tid] = cbd < 0 ? q - (u64)(-cbd) : (u64)cbd;
+            }
+        }
+        return 0;
+    }
+    if (kind != 2) return -1;
+    const u64 groups = n >> 3;
+    for (u64 tid = 0; tid < groups * (u64)limbs; tid++) {
+        const u64 q = c->primes[tid / groups];
+        const u64 max_multiple = UINT64_MAX - (UINT64_MAX % q) - 1;
+        u64 tries = 0;
+        orc_prng_block(blk, seed, tid);
+        tries++;
+        for (int index = 0; index < 8; index++) {
+            u64 r;
+            for (;;) {
+                memcpy(&r, blk + 8 * index, 8); /* little-endian host, like the device */
+                if (r <= max_multiple) break;
+                orc_prng_block(blk, seed, tid + tries * n * (u64)limbs);
+                tries++;
+            }
+            out[tid * 8 + index] = r % q;
+        }
+    }
+    return 0;
+}
+
+/* gen_secretkey, secretkey.cu:345-378 */
+void orc_gen_secretkey(const orc_ctx *c, const uint8_t *seed, u64 *sk) {
+    int idx[64];
+    for (int i = 0; i < c->size_QP; i++) idx[i] = i;
+    orc_sample_poly(c, 0, c->size_QP, seed, sk);
+    orc_ntt_forward(c, sk, c->size_QP, idx);
+}
+
+/* encrypt_zero_symmetric, secretkey.cu:232-295.  chain_index 0: key level (size_QP limbs); data levels: BFV ciphertexts in
+ * coefficient form, the others in NTT form.  ct = [2][limbs][n] */
+int orc_encrypt_zero_symmetric(const orc_ctx *c, int chain_index, const u64 *sk, const uint8_t *seed_a, const uint8_t *seed_e,
+                               u64 *ct) {
+    if (chain_index < 0 || chain_index > c->size_Q) return -1;
+    const int limbs = chain_index == 0 ? c->size_QP : c->size_Q - (chain_index - 1);
+    const int ntt_form = chain_index == 0 || c->scheme != ORC_SCHEME_BFV;
+    const u64 n = c->n;
+    u64 *c0 = ct, *c1 = ct + (size_t)limbs * n;
+    u64 *e = (u64 *)malloc((size_t)limbs * n * 8);
+    int idx[64];
+    for (int i = 0; i < limbs; i++) idx[i] = i;
+    orc_sample_poly(c, 1, limbs, seed_e, e);
+    orc_sample_poly(c, 2, limbs, seed_a, c1);
+    if (ntt_form) {
+        if (c->scheme == ORC_SCHEME_BGV)
+            for (int i = 0; i < limbs; i++)
+                for (u64 x = 0; x < n; x++) e[i * n + x] = orc_mulmod(e[i * n + x], c->t % c->primes[i], c->primes[i]);
+        orc_ntt_forward(c, e, limbs, idx);
+        for (int i = 0; i < limbs; i++) {
+            const u64 q = c->primes[i];
+            for (u64 x = 0; x < n; x++) {
+                u64 v = addmod(orc_mulmod(c1[i * n + x], sk[i * n + x], q), e[i * n + x], q);
+                c0[i * n + x] = v ? q - v : 0;
+            }
+        }
+    } else {
+        for (int i = 0; i < limbs; i++)
+            for (u64 x = 0; x < n; x++) c0[i * n + x] = orc_mulmod(c1[i * n + x], sk[i * n + x], c->primes[i]);
+        orc_ntt_inverse(c, c0, limbs, idx);
+        for (int i = 0; i < limbs; i++) {
+            const u64 q = c->primes[i];
+            for (u64 x = 0; x < n; x++) {
+                u64 v = addmod(c0[i * n + x], e[i * n + x], q);
+                c0[i * n + x] = v ? q - v : 0;
+            }
+        }
+        orc_ntt_inverse(c, c1, limbs, idx);
+    }
+    free(e);
+    return 0;
+}
+
+/* encrypt_zero_asymmetric_internal at the first data level, secretkey.cu:10-128: (u pk_i + e) at the key level -- one error
+ * polynomial for both i, the seed is not renewed between them -- then DRNSTool::moddown (rns_bconv.cu:712-761).
+ * pk = [2][size_QP][n] NTT form, ct = [2][size_Q][n] */
+int orc_encrypt_zero_asymmetric(const orc_ctx *c, const u64 *pk, const uint8_t *seed_u, const uint8_t *seed_e, u64 *ct) {
+    const u64 n = c->n;
+    const int m = c->size_QP, l = c->size_Q;
+    if (c->size_P < 1) return -1;
+    int idx[64];
+    for (int i = 0; i < m; i++) idx[i] = i;
+    u64 *u = (u64 *)malloc((size_t)m * n * 8), *e = (u64 *)malloc((size_t)m * n * 8), *cx = (u64 *)malloc((size_t)m * n * 8);
+    orc_sample_poly(c, 0, m, seed_u, u);
+    orc_ntt_forward(c, u, m, idx);
+    for (int k = 0; k < 2; k++) {
+        const u64 *pki = pk + (size_t)k * m * n;
+        orc_sample_poly(c, 1, m, seed_e, e);
+        if (c->scheme == ORC_SCHEME_BFV) {
+            /* coefficient form: intt(pk u) + e, then the division by P without any transform (:76-92, rns_bconv.cu:744-757).
+             * orc_moddown_from_ntt starts from NTT form, so hand it ntt(intt(pk u) + e) = pk u + ntt(e): the same residues */
+            orc_ntt_forward(c, e, m, idx);
+        } else {
+            if (c->scheme == ORC_SCHEME_BGV)
+                for (int i = 0; i < m; i++)
+                    for (u64 x = 0; x < n; x++) e[i * n + x] = orc_mulmod(e[i * n + x], c->t % c->primes[i], c->primes[i]);
+            orc_ntt_forward(c, e, m, idx);
+        }
+        for (int i = 0; i < m; i++) {
+            const u64 q = c->primes[i];
+            for (u64 x = 0; x < n; x++) cx[i * n + x] = addmod(orc_mulmod(u[i * n + x], pki[i * n + x], q), e[i * n + x], q);
+        }
+        orc_moddown_from_ntt(c, l, cx, ct + (size_t)k * l * n);
+    }
+    free(u), free(e), free(cx);
+    return 0;
+}
+
+/* generate_one_kswitch_key, secretkey.cu:297-343 + multiply_temp_mod_and_add_rns_poly, polymath.cu:318-338.
+ * digits = [dnum][2][size_QP][n], dnum = size_Q / size_P; seeds = dnum pairs (a, e) of 64 bytes */
+int orc_gen_kswitch_key(const orc_ctx *c, const u64 *new_key, const u64 *sk, const uint8_t *seeds, u64 *digits) {
+    if (c->size_P < 1 || c->size_Q % c->size_P) return -1;
+    const u64 n = c->n;
+    const int dnum = c->size_Q / c->size_P, alpha = c->size_P;
+    const size_t digit_words = (size_t)2 * c->size_QP * n;
+    for (int d = 0; d < dnum; d++)
+        orc_encrypt_zero_symmetric(c, 0, sk, seeds + 128 * d, seeds + 128 * d + 64, digits + d * digit_words);
+    for (int j = 0; j < dnum * alpha; j++) {
+        const u64 q = c->primes[j], P = bigP_mod(c, q);
+        u64 *key = digits + (size_t)(j / alpha) * digit_words + (size_t)j * n;
+        for (u64 x = 0; x < n; x++) key[x] = addmod(key[x], orc_mulmod(new_key[(size_t)j * n + x], P, q), q);
+    }
+    return 0;
+}
+
+/* c0 += plaintext: bfv_add_timesQ_overt_kernel (polymath.cu:413-436) for BFV, add_rns_poly for CKKS (plain = [l][n]), lift +
+ * transform + add for BGV (secretkey.cu:170-185, 506-525) */
+int orc_encrypt_add_plain(const orc_ctx *c, int l, u64 *ct0, const u64 *plain) {
+    const u64 n = c->n;
+    if (l < 1 || l > c->size_Q) return -1;
+    if (c->scheme == ORC_SCHEME_CKKS) {
+        for (int i = 0; i < l; i++)
+            for (u64 x = 0; x < n; x++) ct0[i * n + x] = addmod(ct0[i * n + x], plain[i * n + x], c->primes[i]);
+        return 0;
+    }
+    const u64 t = c->t;
+    if (c->scheme == ORC_SCHEME_BFV) {
+        u64 q_mod_t = 1 % t;
+        for (int i = 0; i < l; i++) q_mod_t = orc_mulmod(q_mod_t, c->primes[i] % t, t);
+        const u64 neg = (t - q_mod_t) % t;
+        for (int i = 0; i < l; i++) {
+            const u64 q = c->primes[i], tinv = orc_invmod(t % q, q);
+            for (u64 x = 0; x < n; x++)
+                ct0[i * n + x] = addmod(ct0[i * n + x], orc_mulmod(orc_mulmod(plain[x], neg, t), tinv, q), q);
+        }
+        return 0;
+    }
+    u64 *lift = (u64 *)malloc((size_t)l * n * 8);
+    int idx[64];
+    for (int i = 0; i < l; i++) {
+        idx[i] = i;
+        for (u64 x = 0; x < n; x++) lift[i * n + x] = plain[x] % c->primes[i];
+    }
+    orc_ntt_forward(c, lift, l, idx);
+    for (int i = 0; i < l; i++)
+        for (u64 x = 0; x < n; x++) ct0[i * n + x] = addmod(ct0[i * n + x], lift[i * n + x], c->primes[i]);
+    free(lift);
+    return 0;
+}

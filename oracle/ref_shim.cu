@@ -460,6 +460,58 @@ int ref_ckks_roundtrip(void *p, const double *values, size_t count, size_t chain
     SHIM_CATCH
 }
 
+/* the reference's sampler kernels (prng.cu:142-244) with a caller-supplied 64-byte seed, launched the way secretkey.cu
+ * launches them: kind 0 ternary, 1 error, 2 uniform; out = [limbs][n] */
+int ref_sample_poly(void *p, int kind, const uint8_t *seed, size_t limbs, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto d_seed = phantom::util::make_cuda_auto_ptr<uint8_t>(phantom::util::global_variables::prng_seed_byte_count, s);
+    auto d_out = phantom::util::make_cuda_auto_ptr<uint64_t>(limbs * h->n, s);
+    cudaMemcpyAsync(d_seed.get(), seed, phantom::util::global_variables::prng_seed_byte_count, cudaMemcpyHostToDevice, s);
+    auto base_rns = h->ctx->gpu_rns_tables().modulus();
+    uint64_t grid = h->n * limbs / blockDimGlb.x;
+    if (kind == 0) sample_ternary_poly<<<grid, blockDimGlb, 0, s>>>(d_out.get(), d_seed.get(), base_rns, h->n, limbs);
+    else if (kind == 1) sample_error_poly<<<grid, blockDimGlb, 0, s>>>(d_out.get(), d_seed.get(), base_rns, h->n, limbs);
+    else if (kind == 2) sample_uniform_poly<<<grid, blockDimGlb, 0, s>>>(d_out.get(), d_seed.get(), base_rns, h->n, limbs);
+    else throw std::invalid_argument("unknown sampler");
+    cudaStreamSynchronize(s);
+    cudaMemcpy(out, d_out.get(), limbs * h->n * sizeof(uint64_t), cudaMemcpyDeviceToHost);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+/* PhantomSecretKey::encrypt_symmetric / PhantomPublicKey::encrypt_asymmetric (secretkey.cu:130-190, 463-530) of a
+ * caller-supplied plaintext with the context's own keys: plain = [n] mod t (BFV, BGV) or [l][n] NTT form (CKKS) */
+int ref_encrypt(void *p, int asymmetric, size_t chain_index, const uint64_t *plain, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    if (!h->sk) throw std::invalid_argument("context was created without keys");
+    const auto &s = cudaStreamPerThread;
+    PhantomPlaintext pt;
+    size_t l = 1;
+    if (h->scheme == scheme_type::ckks) {   /* a plaintext object of the right level and scale, then the caller's words */
+        PhantomCKKSEncoder enc(*h->ctx);
+        std::vector<cuDoubleComplex> zero(1, make_cuDoubleComplex(0.0, 0.0));
+        enc.encode(*h->ctx, zero, h->scale, pt, chain_index);
+        l = h->ctx->get_context_data(chain_index).parms().coeff_modulus().size();
+    } else {
+        pt.resize(1, h->n, s);
+    }
+    cudaStreamSynchronize(s);
+    cudaMemcpy(pt.data(), plain, l * h->n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    PhantomCiphertext ct;
+    if (asymmetric) {
+        PhantomPublicKey pk = h->sk->gen_publickey(*h->ctx);
+        pk.encrypt_asymmetric(*h->ctx, pt, ct);
+    } else {
+        h->sk->encrypt_symmetric(*h->ctx, pt, ct);
+    }
+    fetch_ct(ct, out);
+    return 0;
+    SHIM_CATCH
+}
+
 /* PhantomBatchEncoder::encode / decode (batchencoder.cu:62-118): values[count] -> plain[n]; plain[n] -> values[n] */
 int ref_batch_encode(void *p, const uint64_t *values, size_t count, uint64_t *plain) {
     SHIM_TRY

@@ -59,6 +59,13 @@ _sigs = {
     "pfhe_mod_switch_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_ckks_encode": (ctypes.c_int, [vp, sz, vp, sz, ctypes.c_double, vp, vp]),
     "pfhe_ckks_decode": (ctypes.c_int, [vp, sz, vp, ctypes.c_double, vp, vp]),
+    "pfhe_sample_poly": (ctypes.c_int, [vp, ctypes.c_int, sz, ctypes.c_char_p, vp, vp]),
+    "pfhe_gen_secretkey": (ctypes.c_int, [vp, ctypes.c_char_p, vp, vp]),
+    "pfhe_encrypt_zero_symmetric": (ctypes.c_int, [vp, sz, vp, ctypes.c_char_p, ctypes.c_char_p, vp, vp]),
+    "pfhe_encrypt_zero_asymmetric": (ctypes.c_int, [vp, sz, vp, ctypes.c_char_p, ctypes.c_char_p, vp, vp]),
+    "pfhe_gen_kswitch_key": (ctypes.c_int, [vp, vp, vp, ctypes.c_char_p, vp, vp]),
+    "pfhe_galois_secret_key": (ctypes.c_int, [vp, vp, ctypes.c_uint32, vp, vp]),
+    "pfhe_encrypt_add_plain": (ctypes.c_int, [vp, sz, vp, vp, vp]),
     "pfhe_batch_encode": (ctypes.c_int, [vp, vp, sz, vp, vp]),
     "pfhe_batch_decode": (ctypes.c_int, [vp, vp, vp, vp]),
     "pfhe_decrypt": (ctypes.c_int, [vp, sz, vp, sz, vp, ctypes.c_uint64, vp, vp]),

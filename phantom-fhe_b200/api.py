@@ -9,6 +9,7 @@ std::logic_error -> RuntimeError.  All arithmetic happens in libpfhe_b200.so on 
 """
 import ctypes
 import enum
+import os
 
 import numpy as np
 import torch
@@ -271,14 +272,122 @@ class PhantomBatchEncoder:
         return out.cpu().numpy().view(np.uint64)
 
 
-class PhantomSecretKey:
-    """The decrypting half of PhantomSecretKey (include/secretkey.h:226-338): the secret key's powers in NTT form at the
-    key level (secret_key_array()) and decrypt().  Key generation and encryption stay with the reference (SURVEY.md 8f);
-    the first power comes from there (PhantomSecretKey::save) or from the caller."""
+def random_bytes(count=64):
+    """random_bytes (include/prng.cuh:10-32): the seeds of the device generator.  The reference draws them from
+    std::random_device; os.urandom is the same kind of source."""
+    return os.urandom(count)
 
-    def __init__(self, context, secret_key_ntt):
+
+def _seed(seed):
+    seed = random_bytes() if seed is None else bytes(seed)
+    if len(seed) != 64:
+        raise ValueError("a seed is 64 bytes (prng_seed_byte_count)")
+    return seed
+
+
+def _first_plain_level(context, plain):
+    if context.scheme == scheme_type.ckks:
+        if plain.dim() != 2 or plain.shape[1] != context.poly_degree:
+            raise ValueError("CKKS plaintext is [l][N] in NTT form")
+        return context.size_Q - plain.shape[0] + 1
+    if plain.dim() != 1 or plain.shape[0] != context.poly_degree:
+        raise ValueError("BFV / BGV plaintext is [N] residues mod t")
+    return context.get_first_index()
+
+
+class PhantomPublicKey:
+    """PhantomPublicKey (include/secretkey.h:25-100): an encryption of zero at the key level, [2][size_QP][N] in NTT form,
+    and encrypt_asymmetric (src/secretkey.cu:130-190)."""
+
+    def __init__(self, context, pk):
+        self.pk = pk   # device [2][size_QP][N]
+
+    def encrypt_asymmetric(self, context, plain, scale=1.0, seeds=None):
+        """plain: device plaintext (BFV / BGV: [N] mod t, first data level; CKKS: [l][N] NTT form, l = size_Q: the
+        reference's mod-down step serves the first data level only).  seeds = (seed_u, seed_e) or None for fresh ones."""
+        chain_index = _first_plain_level(context, plain)
+        su, se = (None, None) if seeds is None else seeds
+        l, n = context.coeff_modulus_size(chain_index), context.poly_degree
+        data = torch.empty((2, l, n), dtype=torch.int64, device=context.device)
+        check(lib.pfhe_encrypt_zero_asymmetric(context._h, chain_index, _ptr(self.pk), _seed(su), _seed(se), _ptr(data),
+                                               _stream()))
+        check(lib.pfhe_encrypt_add_plain(context._h, chain_index, _ptr(data), _ptr(plain.contiguous()), _stream()))
+        ct = PhantomCiphertext(context, data, chain_index, scale if context.scheme == scheme_type.ckks else 1.0,
+                               context.scheme != scheme_type.bfv)
+        ct.is_asymmetric = True
+        return ct
+
+
+class PhantomSecretKey:
+    """PhantomSecretKey (include/secretkey.h:226-338, src/secretkey.cu:196-723): the secret key's powers in NTT form at the
+    key level (secret_key_array()), key generation, symmetric encryption and decrypt().  PhantomSecretKey(context) draws a
+    new key like the reference's constructor; PhantomSecretKey(context, s) wraps an existing first power (from
+    PhantomSecretKey::save of a stock build, or from the caller)."""
+
+    def __init__(self, context, secret_key_ntt=None, seed=None):
+        if secret_key_ntt is None:
+            self._pow = torch.empty((1, context.size_QP, context.poly_degree), dtype=torch.int64, device=context.device)
+            check(lib.pfhe_gen_secretkey(context._h, _seed(seed), _ptr(self._pow), _stream()))   # gen_secretkey :345-378
+            return
         s1 = np.asarray(secret_key_ntt, dtype=np.uint64).reshape(1, context.size_QP, context.poly_degree)
         self._pow = _to_dev(s1, context.device)   # [sk_max_power][size_QP][n]
+
+    def _encrypt_zero_symmetric(self, context, chain_index, seed_a, seed_e):
+        limbs = context.size_QP if chain_index == 0 else context.coeff_modulus_size(chain_index)
+        ct = torch.empty((2, limbs, context.poly_degree), dtype=torch.int64, device=context.device)
+        check(lib.pfhe_encrypt_zero_symmetric(context._h, chain_index, _ptr(self._pow), _seed(seed_a), _seed(seed_e), _ptr(ct),
+                                              _stream()))
+        return ct
+
+    def gen_publickey(self, context, seeds=None):
+        """gen_publickey (src/secretkey.cu:380-392): encrypt_zero_symmetric at the key level.  seeds = (seed_a, seed_e)"""
+        sa, se = (None, None) if seeds is None else seeds
+        return PhantomPublicKey(context, self._encrypt_zero_symmetric(context, 0, sa, se))
+
+    def _kswitch_key(self, context, new_key, seeds):
+        """generate_one_kswitch_key (src/secretkey.cu:297-343) -> PhantomRelinKey"""
+        if context.size_P < 1 or context.size_Q % context.size_P:
+            raise ValueError("size_Q must be a multiple of size_P")
+        dnum = context.size_Q // context.size_P
+        if seeds is None:
+            seeds = b"".join(random_bytes() for _ in range(2 * dnum))
+        if len(seeds) != 128 * dnum:
+            raise ValueError("a key-switching key takes dnum pairs of 64-byte seeds")
+        digits = [torch.empty((2, context.size_QP, context.poly_degree), dtype=torch.int64, device=context.device)
+                  for _ in range(dnum)]
+        ptrs = (ctypes.c_void_p * dnum)(*[d.data_ptr() for d in digits])
+        check(lib.pfhe_gen_kswitch_key(context._h, _ptr(new_key), _ptr(self._pow), bytes(seeds), ptrs, _stream()))
+        return PhantomRelinKey.from_device(context, digits)
+
+    def gen_relinkey(self, context, seeds=None):
+        """gen_relinkey (src/secretkey.cu:394-418): key-switching key for s^2"""
+        self._compute_secret_key_array(context, 2)
+        return self._kswitch_key(context, self._pow[1], seeds)
+
+    def create_galois_keys(self, context, seeds=None):
+        """create_galois_keys (src/secretkey.cu:420-461): one key-switching key per Galois element of the context, for the
+        secret key under that automorphism.  seeds: one bytes object of dnum seed pairs per element, or None"""
+        keys = []
+        rotated = torch.empty_like(self._pow[0])
+        for i, elt in enumerate(context.parms.galois_elts):
+            check(lib.pfhe_galois_secret_key(context._h, _ptr(self._pow), int(elt), _ptr(rotated), _stream()))
+            keys.append(self._kswitch_key(context, rotated, None if seeds is None else seeds[i]))
+        gk = PhantomGaloisKey.__new__(PhantomGaloisKey)
+        gk.relin_keys = keys
+        return gk
+
+    def encrypt_symmetric(self, context, plain, scale=1.0, seeds=None):
+        """encrypt_symmetric (src/secretkey.cu:463-530).  plain as in PhantomPublicKey.encrypt_asymmetric, CKKS at any level.
+        seeds = (seed_a, seed_e); the ciphertext keeps seed_a like the reference's seed_ptr()"""
+        chain_index = _first_plain_level(context, plain)
+        sa, se = (None, None) if seeds is None else seeds
+        sa = _seed(sa)
+        data = self._encrypt_zero_symmetric(context, chain_index, sa, se)
+        check(lib.pfhe_encrypt_add_plain(context._h, chain_index, _ptr(data), _ptr(plain.contiguous()), _stream()))
+        ct = PhantomCiphertext(context, data, chain_index, scale if context.scheme == scheme_type.ckks else 1.0,
+                               context.scheme != scheme_type.bfv)
+        ct.seed = sa
+        return ct
 
     def secret_key_array(self):
         return self._pow
@@ -329,6 +438,14 @@ class PhantomRelinKey:
                                context.device) for d in digits_host]
         ptrs = np.array([d.data_ptr() for d in self.digits], dtype=np.uint64)
         self._ptrs = _to_dev(ptrs, context.device)
+
+    @classmethod
+    def from_device(cls, context, digits):
+        """wrap digits already on the device (key generation)"""
+        k = cls.__new__(cls)
+        k.digits = list(digits)
+        k._ptrs = _to_dev(np.array([d.data_ptr() for d in k.digits], dtype=np.uint64), context.device)
+        return k
 
     def public_keys_ptr(self):
         return _ptr(self._ptrs)

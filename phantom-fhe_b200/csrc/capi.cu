@@ -281,6 +281,65 @@ int pfhe_ckks_decode(pfhe_engine *e, size_t chain_index, const uint64_t *plain, 
     e->impl.ckks_decode(l, U(plain), scale, reinterpret_cast<double2 *>(values), S(stream));
     API_END
 }
+static pfhe::Seed seed_of(const uint8_t *bytes) {
+    pfhe::Seed s;
+    for (int i = 0; i < 16; i++)
+        s.w[i] = (uint32_t) bytes[4 * i] | ((uint32_t) bytes[4 * i + 1] << 8) | ((uint32_t) bytes[4 * i + 2] << 16) |
+                 ((uint32_t) bytes[4 * i + 3] << 24);
+    return s;
+}
+int pfhe_sample_poly(pfhe_engine *e, int kind, size_t limbs, const uint8_t *seed, uint64_t *out, void *stream) {
+    API_BEGIN
+    require(e && seed && out, "null pointer");
+    e->impl.sample_poly(kind, (int) limbs, seed_of(seed), U(out), S(stream));
+    API_END
+}
+int pfhe_gen_secretkey(pfhe_engine *e, const uint8_t *seed, uint64_t *secret_key, void *stream) {
+    API_BEGIN
+    require(e && seed && secret_key, "null pointer");
+    e->impl.gen_secret_key(seed_of(seed), U(secret_key), S(stream));
+    API_END
+}
+int pfhe_encrypt_zero_symmetric(pfhe_engine *e, size_t chain_index, const uint64_t *secret_key, const uint8_t *seed_a,
+                                const uint8_t *seed_e, uint64_t *ct, void *stream) {
+    API_BEGIN
+    require(e && secret_key && seed_a && seed_e && ct, "null pointer");
+    const int limbs = chain_index == 0 ? e->impl.size_QP() : e->impl.limbs_at(chain_index);
+    const bool ntt_form = chain_index == 0 || e->impl.scheme() != pfhe::Scheme::bfv;
+    e->impl.encrypt_zero_symmetric(limbs, ntt_form, U(secret_key), seed_of(seed_a), seed_of(seed_e), U(ct), S(stream));
+    API_END
+}
+int pfhe_encrypt_zero_asymmetric(pfhe_engine *e, size_t chain_index, const uint64_t *public_key, const uint8_t *seed_u,
+                                 const uint8_t *seed_e, uint64_t *ct, void *stream) {
+    API_BEGIN
+    require(e && public_key && seed_u && seed_e && ct, "null pointer");
+    require(chain_index == 1, "asymmetric encryption is built for the first data level");
+    e->impl.encrypt_zero_asymmetric(U(public_key), seed_of(seed_u), seed_of(seed_e), U(ct), S(stream));
+    API_END
+}
+int pfhe_gen_kswitch_key(pfhe_engine *e, const uint64_t *new_key, const uint64_t *secret_key, const uint8_t *seeds,
+                         uint64_t *const *digits, void *stream) {
+    API_BEGIN
+    require(e && new_key && secret_key && seeds && digits, "null pointer");
+    require(e->impl.size_P() > 0 && e->impl.size_Q() % e->impl.size_P() == 0, "size_Q must be a multiple of size_P");
+    const int dnum = e->impl.size_Q() / e->impl.size_P();
+    std::vector<pfhe::Seed> sd(2 * (size_t) dnum);
+    for (int i = 0; i < 2 * dnum; i++) sd[i] = seed_of(seeds + 64 * (size_t) i);
+    e->impl.kswitch_key(U(new_key), U(secret_key), sd.data(), reinterpret_cast<pfhe::u64 *const *>(digits), S(stream));
+    API_END
+}
+int pfhe_galois_secret_key(pfhe_engine *e, const uint64_t *secret_key, uint32_t galois_elt, uint64_t *rotated, void *stream) {
+    API_BEGIN
+    require(e && secret_key && rotated, "null pointer");
+    e->impl.galois_secret_key(U(secret_key), galois_elt, U(rotated), S(stream));
+    API_END
+}
+int pfhe_encrypt_add_plain(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, void *stream) {
+    API_BEGIN
+    require(e && ct && plain, "null pointer");
+    e->impl.encrypt_add_plain(e->impl.limbs_at(chain_index), U(ct), U(plain), S(stream));
+    API_END
+}
 int pfhe_batch_encode(pfhe_engine *e, const uint64_t *values, size_t count, uint64_t *plain, void *stream) {
     API_BEGIN
     require(e && plain && (values || count == 0), "null pointer");

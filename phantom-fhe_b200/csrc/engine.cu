@@ -12,6 +12,7 @@
 #include "launch.hpp"
 #include "poly_kernels.cuh"
 #include "behz_kernels.cuh"
+#include "sampler_kernels.cuh"
 
 namespace pfhe {
 
@@ -1904,6 +1905,160 @@ void Engine::mod_switch_drop(int l, u64 *out, const u64 *in, int size, cudaStrea
     for (int s = 0; s < size; s++)
         PFHE_CUDA(cudaMemcpyAsync(out + (size_t) s * (l - 1) * n_, in + (size_t) s * l * n_, (size_t) (l - 1) * n_ * 8,
                                   cudaMemcpyDeviceToDevice, st));
+}
+
+// ---- samplers, key generation, encryption ----------------------------------------------------
+
+// sample_ternary_poly / sample_error_poly / sample_uniform_poly (reference src/prng.cu:142-244): out = [limbs][n] over the
+// modulus rows 0 .. limbs-1 (limbs = size_QP at the key level, l at a data level)
+void Engine::sample_poly(int kind, int limbs, const Seed &seed, u64 *out, cudaStream_t st) const {
+    if (limbs < 1 || limbs > size_QP_) throw std::invalid_argument("limb count out of range");
+    const dim3 per_coeff((unsigned) (n_ / EW_THREADS));
+    switch (kind) {
+        case SAMPLE_TERNARY:
+            launch_pdl(k_sample_small<SAMPLE_TERNARY>, per_coeff, EW_THREADS, 0, st, out, seed, (const Modulus *) d_mod_.p, n_, limbs);
+            break;
+        case SAMPLE_ERROR:
+            launch_pdl(k_sample_small<SAMPLE_ERROR>, per_coeff, EW_THREADS, 0, st, out, seed, (const Modulus *) d_mod_.p, n_, limbs);
+            break;
+        case SAMPLE_UNIFORM:
+            launch_pdl(k_sample_uniform, dim3((unsigned) ((n_ / 8 + EW_THREADS - 1) / EW_THREADS), limbs), EW_THREADS, 0, st, out,
+                       seed, (const Modulus *) d_mod_.p, n_, limbs);
+            break;
+        default: throw std::invalid_argument("unknown sampler");
+    }
+    check_launch("k_sample");
+}
+
+// PhantomSecretKey::gen_secretkey (secretkey.cu:345-378): ternary secret over every key prime, NTT form, [size_QP][n]
+void Engine::gen_secret_key(const Seed &seed, u64 *sk, cudaStream_t st) const {
+    sample_poly(SAMPLE_TERNARY, size_QP_, seed, sk, st);
+    ntt_fwd_rows_range(sk, size_QP_, 0, st);
+}
+
+// PhantomSecretKey::encrypt_zero_symmetric (secretkey.cu:232-295): out = [2][limbs][n] = (-(a s + e), a), e scaled by t
+// for BGV; NTT form, or (BFV) coefficient form.  sk = first power of the key, NTT form, key-level layout
+void Engine::encrypt_zero_symmetric(int limbs, bool ntt_form, const u64 *sk, const Seed &seed_a, const Seed &seed_e, u64 *out,
+                                    cudaStream_t st) {
+    if (limbs < 1 || limbs > size_QP_) throw std::invalid_argument("limb count out of range");
+    u64 *c0 = out, *c1 = out + (size_t) limbs * n_, *e = ws_.cx.p;
+    const dim3 grid((unsigned) (n_ / EW_THREADS), limbs);
+    sample_poly(SAMPLE_ERROR, limbs, seed_e, e, st);
+    sample_poly(SAMPLE_UNIFORM, limbs, seed_a, c1, st);
+    if (ntt_form) {
+        if (scheme_ == Scheme::bgv) {
+            launch_pdl(k_scale_by, grid, EW_THREADS, 0, st, e, t_, (const Modulus *) d_mod_.p, n_);
+            check_launch("k_scale_by");
+        }
+        ntt_fwd_rows_range(e, limbs, 0, st);
+        launch_pdl(k_enc_fma<true>, grid, EW_THREADS, 0, st, c0, (const u64 *) c1, sk, (const u64 *) e, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_enc_fma");
+    } else {
+        // the uniform sample is read as the NTT form of a: c0 = -(intt(a s) + e), c1 = intt(a).  In NTT form first
+        // (-(a s + ntt(e))), then both polynomials back: the same residues, one batched inverse transform
+        ntt_fwd_rows_range(e, limbs, 0, st);
+        launch_pdl(k_enc_fma<true>, grid, EW_THREADS, 0, st, c0, (const u64 *) c1, sk, (const u64 *) e, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_enc_fma");
+        ntt_batch(out, 2, limbs, 0, true, st);
+    }
+}
+
+// PhantomPublicKey::encrypt_zero_asymmetric_internal (secretkey.cu:10-128) at the first data level: an encryption of zero
+// under the public key at the key level, (u pk_i + e) with e scaled by t for BGV, brought down to Q by dividing by P
+// (DRNSTool::moddown, rns_bconv.cu:712-761).  out = [2][size_Q][n], NTT form (CKKS, BGV) or coefficient form (BFV).
+// Like the reference, both polynomials get the same error polynomial (one seed, nonces restart at zero).
+void Engine::encrypt_zero_asymmetric(const u64 *pk, const Seed &seed_u, const Seed &seed_e, u64 *out, cudaStream_t st) {
+    if (size_P_ < 1) throw std::invalid_argument("asymmetric encryption needs a special modulus");
+    if (3 * size_Q_ < size_QP_) throw std::invalid_argument("special modulus larger than the workspace allows");
+    const int m = size_QP_, l = size_Q_;
+    u64 *u = ws_.t_mod_up.p, *e = ws_.tmp.p, *cx = ws_.cx.p;
+    const dim3 grid((unsigned) (n_ / EW_THREADS), m);
+    sample_poly(SAMPLE_TERNARY, m, seed_u, u, st);
+    ntt_fwd_rows_range(u, m, 0, st);
+    sample_poly(SAMPLE_ERROR, m, seed_e, e, st);
+    if (scheme_ == Scheme::bgv) {
+        launch_pdl(k_scale_by, grid, EW_THREADS, 0, st, e, t_, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_scale_by");
+    }
+    ntt_fwd_rows_range(e, m, 0, st);
+    for (int i = 0; i < 2; i++) {
+        launch_pdl(k_enc_fma<false>, grid, EW_THREADS, 0, st, cx + (size_t) i * m * n_, (const u64 *) u, pk + (size_t) i * m * n_,
+                   (const u64 *) e, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_enc_fma");
+    }
+    // BFV: the reference goes to coefficient form before the division; dividing from NTT form gives the same residues
+    if (scheme_ == Scheme::ckks) moddown(l, out, cx, ws_.delta.p, 2, nullptr, 0, st);
+    else moddown_generic(l, out, cx, 2, nullptr, 0, st);
+}
+
+// PhantomSecretKey::generate_one_kswitch_key (secretkey.cu:297-343): digit d = encryption of zero at the key level with
+// P * new_key added to the limbs of digit d of its first polynomial.  digits = host array of dnum device buffers
+// [2][size_QP][n]; seeds = dnum pairs (a, e).  Like the reference dnum = size_Q / size_P: size_Q must be a multiple of it.
+void Engine::kswitch_key(const u64 *new_key, const u64 *sk, const Seed *seeds, u64 *const *digits, cudaStream_t st) {
+    if (size_P_ < 1 || size_Q_ % size_P_) throw std::invalid_argument("size_Q must be a multiple of size_P");
+    const int dnum = size_Q_ / size_P_;
+    if (!d_p_mod_q_.p) {
+        std::vector<u64> v(size_Q_);
+        for (int j = 0; j < size_Q_; j++) {
+            u64 r = 1;
+            for (int i = 0; i < size_P_; i++) r = hm::mulmod(r, primes_[size_Q_ + i] % primes_[j], primes_[j]);
+            v[j] = r;
+        }
+        d_p_mod_q_.upload(v);
+    }
+    for (int d = 0; d < dnum; d++) encrypt_zero_symmetric(size_QP_, true, sk, seeds[2 * d], seeds[2 * d + 1], digits[d], st);
+    DevBuf<u64 *> &ptrs = d_digit_ptrs_;
+    if (ptrs.count < (size_t) dnum) ptrs.alloc(dnum);
+    PFHE_CUDA(cudaMemcpyAsync(ptrs.p, digits, sizeof(u64 *) * dnum, cudaMemcpyHostToDevice, st));
+    PFHE_CUDA(cudaStreamSynchronize(st));   // `digits` is the caller's (pageable) array
+    launch_pdl(k_kswitch_target, dim3((unsigned) (n_ / EW_THREADS), size_Q_), EW_THREADS, 0, st, (u64 *const *) ptrs.p, new_key,
+               (const u64 *) d_p_mod_q_.p, (const Modulus *) d_mod_.p, n_, size_P_);
+    check_launch("k_kswitch_target");
+}
+
+// multiply_add_plain_with_scaling_variant (scalingvariant.cu:10-34): c0 += round-free scaling of the plaintext,
+// [m * (-Q_l mod t)]_t * t^-1 mod q_i; ct0 = [l][n] coefficient form, plain = [n] residues mod t
+void Engine::bfv_add_plain(int l, u64 *ct0, const u64 *plain, cudaStream_t st) {
+    if (scheme_ != Scheme::bfv) throw std::invalid_argument("unsupported scheme");
+    if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
+    if (!d_tinv_mod_q_.p) {
+        std::vector<u64> v(size_Q_);
+        for (int j = 0; j < size_Q_; j++) v[j] = hm::invmod(t_ % primes_[j], primes_[j]);
+        d_tinv_mod_q_.upload(v);
+    }
+    u64 q_mod_t = 1 % t_;
+    for (int j = 0; j < l; j++) q_mod_t = hm::mulmod(q_mod_t, primes_[j] % t_, t_);
+    const u64 neg = (t_ - q_mod_t) % t_;
+    launch_pdl(k_bfv_add_plain, dim3((unsigned) (n_ / EW_THREADS), l), EW_THREADS, 0, st, ct0, plain, neg, t_,
+               (const u64 *) d_tinv_mod_q_.p, (const Modulus *) d_mod_.p, n_);
+    check_launch("k_bfv_add_plain");
+}
+
+// the key-switching target of a Galois key: the secret key under the automorphism, over every key prime
+// (create_galois_keys, secretkey.cu:443-451: key_galois_tool->apply_galois_ntt)
+void Engine::galois_secret_key(const u64 *sk, uint32_t galois_elt, u64 *rotated, cudaStream_t st) const {
+    const int gi = galois_index(galois_elt);
+    launch_pdl(k_galois_ntt, dim3((unsigned) (n_ / (2 * EW_THREADS)), size_QP_), EW_THREADS, 0, st, rotated, sk,
+               (const uint32_t *) d_perm_[gi].p, n_);
+    check_launch("k_galois_ntt");
+}
+
+// c0 += plaintext, the last step of encrypt_symmetric / encrypt_asymmetric (secretkey.cu:130-190, 463-530).
+// BFV: scaled by Q_l / t (bfv_add_plain); CKKS: plain = [l][n] in NTT form; BGV: plain = [n] residues mod t, lifted to every
+// limb and transformed
+void Engine::encrypt_add_plain(int l, u64 *ct0, const u64 *plain, cudaStream_t st) {
+    if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
+    if (scheme_ == Scheme::bfv) return bfv_add_plain(l, ct0, plain, st);
+    const dim3 grid((unsigned) (n_ / EW_THREADS), l);
+    if (scheme_ == Scheme::ckks) {
+        elementwise(EW_ADD, ct0, plain, ct0, l, st);
+        return;
+    }
+    u64 *lifted = ws_.tmp.p;
+    launch_pdl(k_lift_plain, grid, EW_THREADS, 0, st, lifted, plain, (const Modulus *) d_mod_.p, n_);
+    check_launch("k_lift_plain");
+    ntt_fwd_rows_range(lifted, l, 0, st);
+    elementwise(EW_ADD, ct0, lifted, ct0, l, st);
 }
 
 } // namespace pfhe

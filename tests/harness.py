@@ -62,6 +62,15 @@ def oracle():
         o.orc_bfv_multiply_hps.argtypes = [vp, u64p, u64p, u64p]
         o.orc_ckks_encode.argtypes = [vp, ctypes.c_int, ctypes.POINTER(ctypes.c_double), ctypes.c_uint64, ctypes.c_double, u64p]
         o.orc_ckks_decode.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+        o.orc_prng_block.argtypes = [vp, ctypes.c_char_p, ctypes.c_uint64]
+        o.orc_prng_block.restype = None
+        o.orc_sample_poly.argtypes = [vp, ctypes.c_int, ctypes.c_int, ctypes.c_char_p, u64p]
+        o.orc_gen_secretkey.argtypes = [vp, ctypes.c_char_p, u64p]
+        o.orc_gen_secretkey.restype = None
+        o.orc_encrypt_zero_symmetric.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_char_p, ctypes.c_char_p, u64p]
+        o.orc_encrypt_zero_asymmetric.argtypes = [vp, u64p, ctypes.c_char_p, ctypes.c_char_p, u64p]
+        o.orc_gen_kswitch_key.argtypes = [vp, u64p, u64p, ctypes.c_char_p, u64p]
+        o.orc_encrypt_add_plain.argtypes = [vp, ctypes.c_int, u64p, u64p]
         o.orc_batch_encode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, ctypes.c_uint64, u64p]
         o.orc_batch_decode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, u64p]
         o.orc_decrypt.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.c_uint64, u64p]
@@ -133,6 +142,9 @@ def reference():
         if hasattr(r, "ref_ckks_roundtrip"):
             r.ref_ckks_roundtrip.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.c_size_t, ctypes.c_size_t,
                                              ctypes.c_double, ctypes.POINTER(ctypes.c_double)]
+        if hasattr(r, "ref_sample_poly"):
+            r.ref_sample_poly.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, u64p]
+            r.ref_encrypt.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
         if hasattr(r, "ref_batch_encode"):
             r.ref_batch_encode.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
             r.ref_batch_decode.argtypes = [vp, u64p, u64p]

@@ -1,0 +1,246 @@
+"""GPU parity tests of the rows either side of the hot path that need randomness: the
+samplers, key generation and encryption of src/prng.cu and src/secretkey.cu.  With caller-supplied seeds every polynomial
+is bit-exact against the oracle; the sampler kernels are compared with the reference's own kernels on the same seed; and
+keys / ciphertexts made here are used by the unmodified reference (its evaluator and its decrypt) and the other way round."""
+import ctypes
+
+import numpy as np
+import pytest
+import torch
+
+import harness as H
+from harness import P
+
+pytestmark = pytest.mark.gpu
+
+pf = None
+
+
+def setup_module(module):
+    global pf
+    import phantom_fhe_b200 as m
+    pf = m
+
+
+def make_context(ps, steps=(), mul_tech=2):
+    parms = pf.EncryptionParameters(pf.scheme_type(ps.scheme))
+    parms.set_poly_modulus_degree(ps.n)
+    parms.set_coeff_modulus([int(p) for p in ps.primes])
+    parms.set_special_modulus_size(ps.size_P)
+    if ps.t:
+        parms.set_plain_modulus(ps.t)
+    if ps.scheme == 2:
+        parms.set_mul_tech(mul_tech)
+    if steps:
+        parms.set_galois_elts(pf.get_elts_from_steps(list(steps), ps.n))
+    return pf.PhantomContext(parms)
+
+
+def dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int64)).cuda()
+
+
+def host(t):
+    torch.cuda.synchronize()
+    return t.cpu().numpy().view(np.uint64)
+
+
+def seeds_of(rng, count):
+    return [bytes(rng.integers(0, 256, 64, dtype=np.uint8)) for _ in range(count)]
+
+
+def stream():
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def param_set(scheme, n=4096):
+    if scheme == 2:
+        return H.params_small(n, l=3, alpha=1, qbits=36, pbits=42, scheme=2, t=65537)
+    return H.params_small(n, l=4, alpha=2, scheme=scheme, t=65537 if scheme == 1 else 0)
+
+
+@pytest.mark.parametrize("n,bits,alpha", [(4096, [60, 40, 60], 1), (8192, [60, 60, 50, 40, 60, 60], 2), (65536, [60, 40, 40, 60], 1)])
+def test_samplers_against_reference_kernels(n, bits, alpha):
+    """pfhe_sample_poly vs the oracle vs the reference's sample_ternary_poly / sample_error_poly / sample_uniform_poly
+    (src/prng.cu:142-244) on the same seeds, at the key level and at a lower limb count; 60-bit primes reject one uniform
+    word in sixteen, so the re-draw path is in every comparison."""
+    ps = H.ParamSet("smp", n, bits, alpha, 3, 0)
+    ctx = make_context(ps)
+    o, oc = H.oracle(), ps.octx()
+    rng = np.random.default_rng(n)
+    r = H.reference()
+    h = None
+    if r is not None and hasattr(r, "ref_sample_poly"):
+        h = r.ref_create(3, ps.n, P(ps.primes), ps.size_QP, ps.size_P, 0, 0, None, 0, 1.0, 0)
+        assert h, r.ref_last_error()
+    try:
+        for limbs in (ps.size_QP, 2):
+            for kind in (0, 1, 2):
+                for seed in seeds_of(rng, 2) + [bytes(64), bytes([255] * 64)]:
+                    want = np.zeros((limbs, n), dtype=np.uint64)
+                    assert o.orc_sample_poly(oc, kind, limbs, seed, P(want)) == 0
+                    d = torch.zeros((limbs, n), dtype=torch.int64, device="cuda")
+                    pf.check(pf.lib.pfhe_sample_poly(ctx._h, kind, limbs, seed, d.data_ptr(), stream()))
+                    assert np.array_equal(host(d), want), f"sampler {kind}, {limbs} limbs vs oracle"
+                    if h:
+                        ref = np.zeros((limbs, n), dtype=np.uint64)
+                        assert r.ref_sample_poly(h, kind, seed, limbs, P(ref)) == 0, r.ref_last_error()
+                        assert np.array_equal(ref, want), f"oracle sampler {kind}, {limbs} limbs vs reference kernel"
+    finally:
+        if h:
+            r.ref_destroy(h)
+    with pytest.raises(ValueError):   # std::invalid_argument
+        pf.check(pf.lib.pfhe_sample_poly(ctx._h, 3, 1, bytes(64), d.data_ptr(), stream()))
+
+
+@pytest.mark.parametrize("scheme", [3, 1, 2])
+def test_keygen_and_encryption_against_oracle(scheme):
+    """Secret key, public key, relinearisation key, Galois key, symmetric and public-key ciphertexts from fixed seeds:
+    engine (through the host mirror) == oracle, word for word (src/secretkey.cu:10-530)."""
+    ps = param_set(scheme)
+    ctx = make_context(ps, steps=[1])
+    o, oc = H.oracle(), ps.octx()
+    n, l, m = ps.n, ps.size_Q, ps.size_QP
+    dnum = l // ps.size_P
+    rng = np.random.default_rng(100 + scheme)
+    sd = seeds_of(rng, 12)
+    sk = pf.PhantomSecretKey(ctx, seed=sd[0])
+    want_sk = np.zeros((m, n), dtype=np.uint64)
+    o.orc_gen_secretkey(oc, sd[0], P(want_sk))
+    assert np.array_equal(host(sk.secret_key_array())[0], want_sk), "gen_secretkey"
+    pk = sk.gen_publickey(ctx, seeds=(sd[1], sd[2]))
+    want_pk = np.zeros((2, m, n), dtype=np.uint64)
+    assert o.orc_encrypt_zero_symmetric(oc, 0, P(want_sk), sd[1], sd[2], P(want_pk)) == 0
+    assert np.array_equal(host(pk.pk), want_pk), "gen_publickey"
+    # relinearisation key
+    kseeds = b"".join(seeds_of(rng, 2 * dnum))
+    rlk = sk.gen_relinkey(ctx, seeds=kseeds)
+    kc = o.orc_create(ps.scheme, ps.n, P(ps.primes), m, 0, ps.t)
+    sk2 = np.zeros_like(want_sk)
+    o.orc_poly_mul(kc, P(want_sk), P(want_sk), P(sk2), m)
+    o.orc_destroy(kc)
+    want_rlk = np.zeros((dnum, 2, m, n), dtype=np.uint64)
+    assert o.orc_gen_kswitch_key(oc, P(sk2), P(want_sk), kseeds, P(want_rlk)) == 0
+    for d in range(dnum):
+        assert np.array_equal(host(rlk.digits[d]), want_rlk[d]), f"gen_relinkey digit {d}"
+    # Galois key of step 1
+    gseeds = b"".join(seeds_of(rng, 2 * dnum))
+    glk = sk.create_galois_keys(ctx, seeds=[gseeds])
+    elt = pf.get_elt_from_step(1, n)
+    tab = np.zeros(n, dtype=np.uint32)
+    o.orc_galois_table(n, elt, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+    rotated = np.ascontiguousarray(np.stack([want_sk[i][tab] for i in range(m)]))
+    want_glk = np.zeros((dnum, 2, m, n), dtype=np.uint64)
+    assert o.orc_gen_kswitch_key(oc, P(rotated), P(want_sk), gseeds, P(want_glk)) == 0
+    for d in range(dnum):
+        assert np.array_equal(host(glk.get_relin_keys(0).digits[d]), want_glk[d]), f"create_galois_keys digit {d}"
+    # ciphertexts
+    if scheme == 3:
+        plain = np.stack([rng.integers(0, int(ps.primes[i]), n, dtype=np.uint64) for i in range(l)])
+    else:
+        plain = rng.integers(0, ps.t, n).astype(np.uint64)
+    ct = sk.encrypt_symmetric(ctx, dev(plain), seeds=(sd[3], sd[4]))
+    want = np.zeros((2, l, n), dtype=np.uint64)
+    assert o.orc_encrypt_zero_symmetric(oc, 1, P(want_sk), sd[3], sd[4], P(want)) == 0
+    assert o.orc_encrypt_add_plain(oc, l, P(want), P(plain)) == 0
+    assert np.array_equal(host(ct.data), want), "encrypt_symmetric"
+    assert ct.is_ntt_form == (scheme != 2) and ct.chain_index == 1
+    ct = pk.encrypt_asymmetric(ctx, dev(plain), seeds=(sd[5], sd[6]))
+    assert o.orc_encrypt_zero_asymmetric(oc, P(want_pk), sd[5], sd[6], P(want)) == 0
+    assert o.orc_encrypt_add_plain(oc, l, P(want), P(plain)) == 0
+    assert np.array_equal(host(ct.data), want), "encrypt_asymmetric"
+    assert ct.is_asymmetric
+    if scheme == 3:   # CKKS symmetric encryption at a lower level (plain.chain_index(), secretkey.cu:484-500)
+        low = np.ascontiguousarray(plain[:l - 1])
+        ct = sk.encrypt_symmetric(ctx, dev(low), scale=2.0 ** 30, seeds=(sd[7], sd[8]))
+        want = np.zeros((2, l - 1, n), dtype=np.uint64)
+        assert o.orc_encrypt_zero_symmetric(oc, 2, P(want_sk), sd[7], sd[8], P(want)) == 0
+        assert o.orc_encrypt_add_plain(oc, l - 1, P(want), P(low)) == 0
+        assert np.array_equal(host(ct.data), want) and ct.chain_index == 2 and ct.scale == 2.0 ** 30
+    # fresh seeds: two encryptions of the same plaintext differ, both decrypt
+    c1, c2 = sk.encrypt_symmetric(ctx, dev(plain)), sk.encrypt_symmetric(ctx, dev(plain))
+    assert not np.array_equal(host(c1.data), host(c2.data))
+    if scheme != 3:
+        assert np.array_equal(host(sk.decrypt(ctx, c1)) % ps.t, plain) and np.array_equal(host(sk.decrypt(ctx, c2)) % ps.t, plain)
+    with pytest.raises(ValueError):
+        sk.encrypt_symmetric(ctx, dev(plain), seeds=(b"short", sd[0]))
+
+
+@pytest.mark.parametrize("scheme", [2, 1, 3])
+def test_keys_and_ciphertexts_interoperate_with_the_reference(scheme):
+    """Both directions with the unmodified reference, sharing only the secret key (exported through its save()):
+    - ciphertexts encrypted here (symmetric, and public-key under a public key generated here) are decrypted by the
+      reference's decrypt;
+    - ciphertexts encrypted by the reference (encrypt_symmetric, encrypt_asymmetric) are decrypted here;
+    - a relinearisation key generated here is loaded into the reference's key object and its own multiply + relinearize +
+      decrypt return the product (BFV / BGV: exact)."""
+    r = H.reference()
+    if r is None or not hasattr(r, "ref_encrypt"):
+        pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    ps = param_set(scheme, 8192)
+    n, l, m, t = ps.n, ps.size_Q, ps.size_QP, ps.t
+    scale = float(2 ** 30)
+    h = r.ref_create(scheme, n, P(ps.primes), m, ps.size_P, t, 2, None, 0, scale, 1)
+    assert h, r.ref_last_error()
+    try:
+        ctx = make_context(ps)
+        o, oc = H.oracle(), ps.octx()
+        s1 = np.zeros((m, n), dtype=np.uint64)
+        assert r.ref_secret_key(h, P(s1)) == 0, r.ref_last_error()
+        sk = pf.PhantomSecretKey(ctx, s1)
+        pk = sk.gen_publickey(ctx)
+        rng = np.random.default_rng(scheme)
+        rows = (ctypes.c_int * l)(*range(l))
+        q0 = int(ps.primes[0])
+
+        def plaintext():
+            if scheme == 3:
+                coef = rng.integers(-1000, 1000, n) * (1 << 20)
+                pl = np.stack([np.array([int(v) % int(ps.primes[i]) for v in coef], dtype=np.uint64) for i in range(l)])
+                o.orc_ntt_forward(oc, P(pl), l, rows)
+                return pl, coef
+            pl = rng.integers(0, t, n).astype(np.uint64)
+            return pl, pl
+
+        def same(dec, want, what):
+            if scheme != 3:
+                assert np.array_equal(dec % t, want), what
+                return
+            w = np.ascontiguousarray(dec).copy()
+            o.orc_ntt_inverse(oc, P(w), l, rows)
+            got = np.array([int(v) - q0 if int(v) > q0 // 2 else int(v) for v in w[0]])
+            assert np.max(np.abs(got - want)) < 1 << 14, what
+
+        shape = (l, n) if scheme == 3 else (n,)
+        pl, want = plaintext()
+        for name, ct in (("symmetric", sk.encrypt_symmetric(ctx, dev(pl), scale)),
+                         ("public-key", pk.encrypt_asymmetric(ctx, dev(pl), scale))):
+            dec = np.zeros(shape, dtype=np.uint64)
+            assert r.ref_decrypt(h, 1, P(host(ct.data)), 2, 1, P(dec)) == 0, r.ref_last_error()
+            same(dec, want, f"reference decrypts the engine's {name} ciphertext")
+        for asym in (0, 1):
+            words = np.zeros((2, l, n), dtype=np.uint64)
+            assert r.ref_encrypt(h, asym, 1, P(pl), P(words)) == 0, r.ref_last_error()
+            ct = pf.PhantomCiphertext.from_host(ctx, words, scale=scale, is_ntt_form=(scheme != 2))
+            same(host(sk.decrypt(ctx, ct)), want, f"engine decrypts the reference's ciphertext (asymmetric={asym})")
+        if scheme == 3:
+            return
+        # the engine's relinearisation key inside the reference's evaluator
+        rlk = sk.gen_relinkey(ctx)
+        for d, digit in enumerate(rlk.digits):
+            assert r.ref_key_set(h, -1, d, P(host(digit))) == 0, r.ref_last_error()
+        a = np.zeros(n, dtype=np.uint64)
+        a[0], a[1] = 3, 5
+        b = np.zeros(n, dtype=np.uint64)
+        b[0], b[n - 1] = 7, 2
+        ca, cb = np.zeros((2, l, n), dtype=np.uint64), np.zeros((2, l, n), dtype=np.uint64)
+        assert r.ref_encrypt(h, 0, 1, P(a), P(ca)) == 0 and r.ref_encrypt(h, 1, 1, P(b), P(cb)) == 0, r.ref_last_error()
+        prod = np.zeros((2, l, n), dtype=np.uint64)
+        assert r.ref_multiply_relin(h, 1, P(ca), P(cb), P(prod)) == 0, r.ref_last_error()
+        dec = np.zeros(n, dtype=np.uint64)
+        assert r.ref_decrypt(h, 1, P(prod), 2, 1, P(dec)) == 0, r.ref_last_error()
+        want = np.zeros(n, dtype=np.uint64)
+        want[0], want[1], want[n - 1] = 11, 35, 6   # (3 + 5x)(7 + 2x^(n-1)) mod x^n + 1
+        assert np.array_equal(dec % t, want), "reference multiply + relinearize with the engine's key"
+    finally:
+        r.ref_destroy(h)

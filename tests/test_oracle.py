@@ -492,3 +492,141 @@ def test_ckks_encode_is_the_canonical_embedding():
         pos = (pos * 5) % m
     assert o.orc_ckks_encode(oc, l, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 0, scale, P(out)) == -1
     assert o.orc_ckks_encode(oc, l, flat.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), 5, 2.0 ** 200, P(out)) == -2
+
+
+# ---------------------------------------------------------------------------------------------------------
+# samplers, key generation, encryption (src/prng.cu, src/secretkey.cu)
+# ---------------------------------------------------------------------------------------------------------
+def test_prng_core_is_the_salsa20_core():
+    """salsa20_gpu (src/prng.cu:17-133) is the Salsa20 core over {key[0:32], nonce, key[32:56]}: the core's published
+    known-answer vector (Salsa20 specification, section 8, second example), laid out that way."""
+    o = H.oracle()
+    inp = [211, 159, 13, 115, 76, 55, 82, 183, 3, 117, 222, 37, 191, 187, 234, 136, 49, 237, 179, 48, 1, 106, 178, 219, 175,
+           199, 166, 48, 86, 16, 179, 207, 31, 240, 32, 63, 15, 83, 93, 161, 116, 147, 48, 113, 238, 55, 204, 36, 79, 201,
+           235, 79, 3, 81, 156, 47, 203, 26, 244, 243, 88, 118, 104, 54]
+    want = [109, 42, 178, 168, 156, 240, 248, 238, 168, 196, 190, 203, 26, 110, 170, 154, 29, 29, 150, 26, 150, 30, 235,
+            249, 190, 163, 251, 48, 69, 144, 51, 57, 118, 40, 152, 157, 180, 57, 27, 94, 107, 42, 236, 35, 27, 111, 114,
+            114, 219, 236, 232, 135, 111, 155, 110, 18, 24, 232, 95, 158, 179, 19, 48, 202]
+    key = bytes(inp[0:32] + inp[40:64] + [0] * 8)
+    out = (ctypes.c_uint8 * 64)()
+    o.orc_prng_block(out, key, int.from_bytes(bytes(inp[32:40]), "little"))
+    assert list(out) == want
+
+
+def test_samplers_shape_of_the_distributions():
+    """orc_sample_poly (src/prng.cu:142-244): ternary and error polynomials are the same small integers in every limb,
+    with the expected spread; uniform residues are below q and spread over the range; a different seed gives a different
+    polynomial, the same seed the same one."""
+    o = H.oracle()
+    n = 4096
+    ps = H.ParamSet("smp", n, [60, 40, 60], 1, 3, 0)
+    oc, m = ps.octx(), ps.size_QP
+    seed, other = bytes(range(64)), bytes(range(1, 65))
+    out = np.zeros((m, n), dtype=np.uint64)
+
+    def centred(row, q):
+        return np.where(row > q // 2, row.astype(np.int64) - np.int64(q), row.astype(np.int64))
+
+    assert o.orc_sample_poly(oc, 0, m, seed, P(out)) == 0
+    tern = centred(out[0], int(ps.primes[0]))
+    assert set(np.unique(tern)) == {-1, 0, 1} and all(np.array_equal(centred(out[i], int(ps.primes[i])), tern) for i in range(m))
+    assert abs(np.mean(tern == 0) - 85 / 256) < 0.03   # byte mod 3: 86 zeros -> -1, 85 -> 0, 85 -> 1
+    assert o.orc_sample_poly(oc, 1, m, seed, P(out)) == 0
+    err = centred(out[0], int(ps.primes[0]))
+    assert np.max(np.abs(err)) <= 21 and all(np.array_equal(centred(out[i], int(ps.primes[i])), err) for i in range(m))
+    assert abs(np.var(err) - 10.5) < 1.0 and abs(np.mean(err)) < 0.2   # centred binomial, 21 against 21 bits
+    assert o.orc_sample_poly(oc, 2, m, seed, P(out)) == 0
+    for i in range(m):
+        q = int(ps.primes[i])
+        assert int(out[i].max()) < q and abs(float(np.mean(out[i].astype(np.float64))) / q - 0.5) < 0.02
+    again, diff = np.zeros_like(out), np.zeros_like(out)
+    o.orc_sample_poly(oc, 2, m, seed, P(again))
+    o.orc_sample_poly(oc, 2, m, other, P(diff))
+    assert np.array_equal(again, out) and not np.array_equal(diff, out)
+
+
+@pytest.mark.parametrize("scheme", [2, 1, 3])
+def test_keygen_and_encryption_semantics(scheme):
+    """Keys and ciphertexts made by the oracle's restatement of src/secretkey.cu decrypt (orc_decrypt) to what went in:
+    symmetric and public-key encryption, and a relinearisation key from orc_gen_kswitch_key carries a product through
+    orc_multiply_relin.  BFV / BGV: exact plaintexts; CKKS: within the noise."""
+    o = H.oracle()
+    n, t = 4096, 65537
+    if scheme == 2:
+        ps = H.params_small(n, l=3, alpha=1, qbits=36, pbits=42, scheme=2, t=t)
+    else:
+        ps = H.params_small(n, l=4, alpha=2, scheme=scheme, t=t if scheme == 1 else 0)
+    oc, l, m = ps.octx(), ps.size_Q, ps.size_QP
+    rng = np.random.default_rng(scheme)
+    seeds = [bytes(rng.integers(0, 256, 64, dtype=np.uint8)) for _ in range(16)]
+    sk = np.zeros((m, n), dtype=np.uint64)
+    o.orc_gen_secretkey(oc, seeds[0], P(sk))
+    kc = o.orc_create(ps.scheme, ps.n, P(ps.primes), m, 0, ps.t)
+    sk2 = np.zeros_like(sk)
+    o.orc_poly_mul(kc, P(sk), P(sk), P(sk2), m)
+    o.orc_destroy(kc)
+    pows = np.stack([sk, sk2])
+    pk = np.zeros((2, m, n), dtype=np.uint64)
+    assert o.orc_encrypt_zero_symmetric(oc, 0, P(sk), seeds[1], seeds[2], P(pk)) == 0
+    mul_tech = 2 if scheme == 2 else 0
+
+    def plaintext():
+        if scheme == 3:   # small integer coefficients times 2^20, NTT form
+            coef = rng.integers(-1000, 1000, n) * (1 << 20)
+            pl = np.stack([np.array([int(v) % int(ps.primes[i]) for v in coef], dtype=np.uint64) for i in range(l)])
+            o.orc_ntt_forward(oc, P(pl), l, (ctypes.c_int * l)(*range(l)))
+            return pl, coef
+        pl = rng.integers(0, t, n).astype(np.uint64)
+        return pl, pl
+
+    def decrypted(ct, size=2):
+        out = np.zeros((l, n) if scheme == 3 else (n,), dtype=np.uint64)
+        assert o.orc_decrypt(oc, l, P(ct), size, P(pows), mul_tech, 1, P(out)) == 0
+        if scheme != 3:
+            return out
+        o.orc_ntt_inverse(oc, P(out), l, (ctypes.c_int * l)(*range(l)))
+        q0 = int(ps.primes[0])
+        return np.array([int(v) - q0 if int(v) > q0 // 2 else int(v) for v in out[0]])
+
+    def check(ct, want, what):
+        got = decrypted(ct)
+        if scheme == 3:
+            assert np.max(np.abs(got - want)) < 1 << 12, what
+        else:
+            assert np.array_equal(got, want), what
+
+    pl, want = plaintext()
+    ct = np.zeros((2, l, n), dtype=np.uint64)
+    assert o.orc_encrypt_zero_symmetric(oc, 1, P(sk), seeds[3], seeds[4], P(ct)) == 0
+    assert o.orc_encrypt_add_plain(oc, l, P(ct), P(pl)) == 0
+    check(ct, want, "symmetric encryption")
+    ct2 = np.zeros((2, l, n), dtype=np.uint64)
+    assert o.orc_encrypt_zero_asymmetric(oc, P(pk), seeds[5], seeds[6], P(ct2)) == 0
+    assert o.orc_encrypt_add_plain(oc, l, P(ct2), P(pl)) == 0
+    check(ct2, want, "public-key encryption")
+    if scheme == 3:
+        return
+    # relinearisation key: Enc(a) * Enc(b) relinearised decrypts to the negacyclic product a * b mod t
+    dnum = ps.size_Q // ps.size_P
+    rlk = np.zeros((dnum, 2, m, n), dtype=np.uint64)
+    kseeds = b"".join(seeds[7:7 + 2 * dnum])
+    assert o.orc_gen_kswitch_key(oc, P(sk2), P(sk), kseeds, P(rlk)) == 0
+    a = np.zeros(n, dtype=np.uint64)
+    a[0], a[1] = 3, 5
+    b = np.zeros(n, dtype=np.uint64)
+    b[0], b[n - 1] = 7, 2
+    cts = []
+    for k, p_ in enumerate((a, b)):
+        c_ = np.zeros((2, l, n), dtype=np.uint64)
+        assert o.orc_encrypt_zero_symmetric(oc, 1, P(sk), seeds[12 + k], seeds[14 + k], P(c_)) == 0
+        assert o.orc_encrypt_add_plain(oc, l, P(c_), P(p_)) == 0
+        cts.append(c_)
+    out = np.zeros((2, l, n), dtype=np.uint64)
+    if scheme == 2:
+        assert o.orc_bfv_multiply_relin_hps(oc, P(cts[0]), P(cts[1]), P(rlk), P(out)) == 0
+    else:
+        o.orc_multiply_relin(oc, l, P(cts[0]), P(cts[1]), P(rlk), P(out))
+    want = np.zeros(n, dtype=np.int64)   # (3 + 5x)(7 + 2x^(n-1)) = 21 + 35x + 6x^(n-1) - 10
+    want[0], want[1], want[n - 1] = 11, 35, 6
+    got = decrypted(out).astype(np.int64) % t   # the reference's HPS rounding returns t itself for some zero coefficients
+    assert np.array_equal(got, want), ("product through the generated relinearisation key", np.nonzero(got != want)[0][:8], got[got != want][:8])
