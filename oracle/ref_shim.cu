@@ -512,6 +512,49 @@ int ref_encrypt(void *p, int asymmetric, size_t chain_index, const uint64_t *pla
     SHIM_CATCH
 }
 
+/* encrypt_symmetric with the context's key, then PhantomCiphertext::save_symmetric (ciphertext.h:216-245): the stream to
+ * `bytes` (returns its length), the full ciphertext words to `words` */
+long ref_encrypt_save_symmetric(void *p, size_t chain_index, const uint64_t *plain, unsigned char *bytes, size_t cap,
+                                uint64_t *words) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    if (!h->sk) throw std::invalid_argument("context was created without keys");
+    const auto &s = cudaStreamPerThread;
+    PhantomPlaintext pt;
+    size_t l = 1;
+    if (h->scheme == scheme_type::ckks) {
+        PhantomCKKSEncoder enc(*h->ctx);
+        std::vector<cuDoubleComplex> zero(1, make_cuDoubleComplex(0.0, 0.0));
+        enc.encode(*h->ctx, zero, h->scale, pt, chain_index);
+        l = h->ctx->get_context_data(chain_index).parms().coeff_modulus().size();
+    } else {
+        pt.resize(1, h->n, s);
+    }
+    cudaStreamSynchronize(s);
+    cudaMemcpy(pt.data(), plain, l * h->n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    PhantomCiphertext ct;
+    h->sk->encrypt_symmetric(*h->ctx, pt, ct);
+    fetch_ct(ct, words);
+    std::stringstream ss;
+    ct.save_symmetric(ss);
+    const std::string blob = ss.str();
+    if (blob.size() > cap) throw std::invalid_argument("buffer too small");
+    std::memcpy(bytes, blob.data(), blob.size());
+    return (long) blob.size();
+    SHIM_CATCH
+}
+/* PhantomCiphertext::load_symmetric (ciphertext.h:247-307) of a caller-supplied stream: the rebuilt words to `words` */
+int ref_load_symmetric(void *p, const unsigned char *bytes, size_t len, uint64_t *words) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    std::stringstream ss(std::string(reinterpret_cast<const char *>(bytes), len));
+    PhantomCiphertext ct;
+    ct.load_symmetric(*h->ctx, ss);
+    fetch_ct(ct, words);
+    return 0;
+    SHIM_CATCH
+}
+
 /* PhantomBatchEncoder::encode / decode (batchencoder.cu:62-118): values[count] -> plain[n]; plain[n] -> values[n] */
 int ref_batch_encode(void *p, const uint64_t *values, size_t count, uint64_t *plain) {
     SHIM_TRY

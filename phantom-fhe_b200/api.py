@@ -163,6 +163,7 @@ class PhantomCiphertext:
         self.correction_factor = 1
         self.noise_scale_deg = 1     # noiseScaleDeg_ (include/ciphertext.h:21): read by mul_tech hps_overq_leveled
         self.is_asymmetric = False   # is_asymmetric_ (:23)
+        self.seed = None             # seed_ of c1 (symmetric encryption; save_symmetric writes it instead of c1)
 
     @classmethod
     def from_host(cls, context, words, chain_index=1, scale=1.0, is_ntt_form=True):
@@ -190,6 +191,32 @@ class PhantomCiphertext:
             raise ValueError("ciphertext stream does not belong to this context")
         c = cls(context, _to_dev(words, context.device), h["chain_index"], h["scale"], h["is_ntt_form"])
         c.correction_factor, c.noise_scale_deg, c.is_asymmetric = h["correction_factor"], h["noise_scale_deg"], h["is_asymmetric"]
+        return c
+
+    def save_symmetric(self, stream):
+        """PhantomCiphertext::save_symmetric (include/ciphertext.h:216-245): c0 and the seed of c1, half the bytes."""
+        if self.is_asymmetric or getattr(self, "seed", None) is None:
+            raise RuntimeError("Asymmetric ciphertext does not have seed.")
+        if self.size() != 2:
+            raise RuntimeError("This method is only for 2-polynomial ciphertext.")
+        serial.write_ciphertext_symmetric(stream, self.to_host()[0], self.seed, self.chain_index, self.scale,
+                                          self.correction_factor, self.noise_scale_deg, self.is_ntt_form)
+
+    @classmethod
+    def load_symmetric(cls, context, stream):
+        """PhantomCiphertext::load_symmetric (include/ciphertext.h:247-307): c1 is drawn again from the seed on the device
+        (sample_uniform_poly), and brought to coefficient form for BFV.  First data level only, like the reference."""
+        c0, seed, h = serial.read_ciphertext_symmetric(stream)
+        l, n = c0.shape
+        if n != context.poly_degree or l != context.coeff_modulus_size(context.get_first_index()):
+            raise RuntimeError("Only support ciphertext without modulus switching.")
+        data = torch.empty((2, l, n), dtype=torch.int64, device=context.device)
+        data[0].copy_(_to_dev(c0, context.device))
+        check(lib.pfhe_sample_poly(context._h, 2, l, seed, _ptr(data[1]), _stream()))
+        if not h["is_ntt_form"]:
+            check(lib.pfhe_ntt_backward_inplace(context._h, _ptr(data[1]), l, 0, _stream()))
+        c = cls(context, data, h["chain_index"], h["scale"], h["is_ntt_form"])
+        c.correction_factor, c.noise_scale_deg, c.seed = h["correction_factor"], h["noise_scale_deg"], seed
         return c
 
     def coeff_modulus_size(self):

@@ -43,6 +43,40 @@ def read_ciphertext(stream):
                        is_asymmetric=asym)
 
 
+def write_ciphertext_symmetric(stream, c0, seed, chain_index, scale=1.0, correction_factor=1, noise_scale_deg=1,
+                               is_ntt_form=True):
+    """PhantomCiphertext::save_symmetric (include/ciphertext.h:216-245): the header of save(), c0 only, then the 64-byte
+    seed the second polynomial was drawn from."""
+    w = np.ascontiguousarray(c0, dtype=np.uint64)
+    if w.ndim != 2:
+        raise ValueError("c0 must be [coeff_modulus_size][N]")
+    if len(seed) != 64:
+        raise ValueError("a seed is 64 bytes")
+    l, n = w.shape
+    stream.write(_HDR.pack(chain_index, 2, n, l, float(scale), int(correction_factor), int(noise_scale_deg), bool(is_ntt_form),
+                           False))
+    stream.write(w.tobytes())
+    stream.write(bytes(seed))
+
+
+def read_ciphertext_symmetric(stream):
+    """-> (c0 [l][N], seed, dict of the header fields)   (load_symmetric, include/ciphertext.h:247-307)"""
+    raw = stream.read(_HDR.size)
+    if len(raw) != _HDR.size:
+        raise ValueError("truncated ciphertext stream")
+    ci, size, n, l, scale, cf, deg, ntt, asym = _HDR.unpack(raw)
+    if asym:
+        raise RuntimeError("Asymmetric ciphertext does not have seed.")
+    if size != 2:
+        raise RuntimeError("This method is only for 2-polynomial ciphertext.")
+    body = stream.read(l * n * 8)
+    seed = stream.read(64)
+    if len(body) != l * n * 8 or len(seed) != 64:
+        raise ValueError("truncated ciphertext stream")
+    return np.frombuffer(body, dtype=np.uint64).reshape(l, n).copy(), seed, dict(
+        chain_index=ci, scale=scale, correction_factor=cf, noise_scale_deg=deg, is_ntt_form=ntt, is_asymmetric=False)
+
+
 def write_relin_key(stream, digits):
     """digits: dnum arrays [2][size_QP][N] (NTT form).  Header fields as generate_one_kswitch_key leaves them:
     chain_index 0, scale 1, NTT form (secretkey.cu:297-334)."""

@@ -145,6 +145,10 @@ def reference():
         if hasattr(r, "ref_sample_poly"):
             r.ref_sample_poly.argtypes = [vp, ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t, u64p]
             r.ref_encrypt.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, u64p, u64p]
+        if hasattr(r, "ref_load_symmetric"):
+            r.ref_encrypt_save_symmetric.argtypes = [vp, ctypes.c_size_t, u64p, ctypes.c_char_p, ctypes.c_size_t, u64p]
+            r.ref_encrypt_save_symmetric.restype = ctypes.c_long
+            r.ref_load_symmetric.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, u64p]
         if hasattr(r, "ref_batch_encode"):
             r.ref_batch_encode.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
             r.ref_batch_decode.argtypes = [vp, u64p, u64p]

@@ -112,3 +112,20 @@ def test_serialisation_round_trip_and_layout():
     serial.write_secret_key(buf, pw)
     assert struct.unpack_from("<QQQ", buf.getvalue(), 0) == (2, 16, 3)
     assert np.array_equal(serial.read_secret_key(io.BytesIO(buf.getvalue())), pw)
+    # seed-compressed symmetric form (save_symmetric / load_symmetric, ciphertext.h:216-307): header, c0, 64-byte seed
+    c0, seed = words[0], bytes(range(64))
+    buf = io.BytesIO()
+    serial.write_ciphertext_symmetric(buf, c0, seed, 1, scale=2.0 ** 30, is_ntt_form=False)
+    raw = buf.getvalue()
+    assert len(raw) == 58 + c0.size * 8 + 64 and raw[-64:] == seed and raw[56:58] == b"\x00\x00"
+    assert struct.unpack_from("<QQQQ", raw, 0) == (1, 2, 16, 2)
+    back, sd, hdr = serial.read_ciphertext_symmetric(io.BytesIO(raw))
+    assert np.array_equal(back, c0) and sd == seed and hdr["scale"] == 2.0 ** 30 and not hdr["is_ntt_form"]
+    with pytest.raises(ValueError):
+        serial.read_ciphertext_symmetric(io.BytesIO(raw[:-1]))
+    with pytest.raises(ValueError):
+        serial.write_ciphertext_symmetric(io.BytesIO(), c0, b"short", 1)
+    full = io.BytesIO()
+    serial.write_ciphertext(full, words, 1, is_asymmetric=True)
+    with pytest.raises(RuntimeError):   # "Asymmetric ciphertext does not have seed."
+        serial.read_ciphertext_symmetric(io.BytesIO(full.getvalue()))

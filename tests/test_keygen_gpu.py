@@ -244,3 +244,53 @@ def test_keys_and_ciphertexts_interoperate_with_the_reference(scheme):
         assert np.array_equal(dec % t, want), "reference multiply + relinearize with the engine's key"
     finally:
         r.ref_destroy(h)
+
+
+@pytest.mark.parametrize("scheme", [2, 1, 3])
+def test_seed_compressed_ciphertexts_against_the_reference(scheme):
+    """PhantomCiphertext::save_symmetric / load_symmetric (include/ciphertext.h:216-307): c0 plus the 64-byte seed of c1.
+    A stream written by the reference (after its own encrypt_symmetric) is expanded here to the reference's full
+    ciphertext and re-written byte for byte; a stream written here is expanded by the reference to this ciphertext."""
+    import io
+    r = H.reference()
+    if r is None or not hasattr(r, "ref_load_symmetric"):
+        pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    ps = param_set(scheme)
+    n, l, m, t = ps.n, ps.size_Q, ps.size_QP, ps.t
+    scale = float(2 ** 30)
+    h = r.ref_create(scheme, n, P(ps.primes), m, ps.size_P, t, 2, None, 0, scale, 1)
+    assert h, r.ref_last_error()
+    try:
+        ctx = make_context(ps)
+        rng = np.random.default_rng(7 + scheme)
+        if scheme == 3:
+            plain = np.stack([rng.integers(0, int(ps.primes[i]), n, dtype=np.uint64) for i in range(l)])
+        else:
+            plain = rng.integers(0, t, n).astype(np.uint64)
+        cap = 64 + l * n * 8 + 256
+        buf = ctypes.create_string_buffer(cap)
+        words = np.zeros((2, l, n), dtype=np.uint64)
+        length = r.ref_encrypt_save_symmetric(h, 1, P(plain), buf, cap, P(words))
+        assert length > 0, r.ref_last_error()
+        blob = buf.raw[:length]
+        ct = pf.PhantomCiphertext.load_symmetric(ctx, io.BytesIO(blob))
+        assert np.array_equal(host(ct.data), words), "load_symmetric of the reference's stream"
+        assert ct.is_ntt_form == (scheme != 2) and not ct.is_asymmetric
+        out = io.BytesIO()
+        ct.save_symmetric(out)
+        assert out.getvalue() == blob, "save_symmetric re-writes the reference's stream"
+        # the other direction
+        s1 = np.zeros((m, n), dtype=np.uint64)
+        assert r.ref_secret_key(h, P(s1)) == 0
+        mine = pf.PhantomSecretKey(ctx, s1).encrypt_symmetric(ctx, dev(plain), scale)
+        out = io.BytesIO()
+        mine.save_symmetric(out)
+        assert len(out.getvalue()) == length
+        back = np.zeros((2, l, n), dtype=np.uint64)
+        assert r.ref_load_symmetric(h, out.getvalue(), len(out.getvalue()), P(back)) == 0, r.ref_last_error()
+        assert np.array_equal(back, host(mine.data)), "the reference's load_symmetric of a stream written here"
+        asym = pf.PhantomSecretKey(ctx, s1).gen_publickey(ctx).encrypt_asymmetric(ctx, dev(plain), scale)
+        with pytest.raises(RuntimeError):
+            asym.save_symmetric(io.BytesIO())
+    finally:
+        r.ref_destroy(h)
