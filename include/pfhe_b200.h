@@ -170,6 +170,20 @@ int pfhe_galois_secret_key(pfhe_engine *e, const uint64_t *secret_key, uint32_t 
  * BFV: multiply_add_plain_with_scaling_variant (src/scalingvariant.cu:10-34), plain = [N] mod t; CKKS: plain = [l][N] NTT
  * form; BGV: plain = [N] mod t, lifted to every limb and transformed. */
 int pfhe_encrypt_add_plain(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, void *stream);
+/* add_plain_inplace / sub_plain_inplace (src/evaluate.cu:1106-1224): ct[0] +-= plaintext, plaintext shapes as above; BGV
+ * multiplies the lifted plaintext by the ciphertext's correction factor (multiply_scalar_and_add / _sub_rns_poly). */
+int pfhe_add_plain_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, uint64_t correction_factor,
+                           void *stream);
+int pfhe_sub_plain_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, uint64_t correction_factor,
+                           void *stream);
+/* multiply_plain_inplace (src/evaluate.cu:1226-1340): every polynomial of ct = [size][l][N] times the plaintext (BFV:
+ * multiply_plain_normal through NTT form and back; CKKS: multiply_plain_ntt; BGV: lifted plaintext). */
+int pfhe_multiply_plain_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, size_t size, const uint64_t *plain,
+                                void *stream);
+/* multiply_scalar_rns_poly (src/polymath.cu:210-228) on `size` polynomials of coeff_mod_size limbs: the correction-factor
+ * balancing of BGV add / sub (src/evaluate.cu:148-165). */
+int pfhe_multiply_scalar_rns_poly(pfhe_engine *e, uint64_t *inout, size_t size, uint64_t scalar, size_t coeff_mod_size,
+                                  void *stream);
 /* PhantomCKKSEncoder::decode_internal (src/ckks.cu:137-190; compose_array src/rns_base.cu:174-258; special forward FFT
  * src/fft.cu:90-218,352-384): `plain` = [l][N] residues in NTT form with the given scale, `values` = N/2 complex numbers
  * on the device.  Same operations in the same order as the reference's kernels; up to 32 limbs.  Does not synchronise. */

@@ -2180,14 +2180,18 @@ int orc_gen_kswitch_key(const orc_ctx *c, const u64 *new_key, const u64 *sk, con
     return 0;
 }
 
-/* c0 += plaintext: bfv_add_timesQ_overt_kernel (polymath.cu:413-436) for BFV, add_rns_poly for CKKS (plain = [l][n]), lift +
- * transform + add for BGV (secretkey.cu:170-185, 506-525) */
-int orc_encrypt_add_plain(const orc_ctx *c, int l, u64 *ct0, const u64 *plain) {
+/* add_plain_inplace / sub_plain_inplace (evaluate.cu:1106-1224): c0 +-= plaintext.  BFV: bfv_add / bfv_sub_timesQ_overt_kernel
+ * (polymath.cu:413-461), plain = [n] mod t; CKKS: add / sub_rns_poly, plain = [l][n] NTT form; BGV: plain reduced under every
+ * limb, transformed, times the correction factor (multiply_scalar_and_add / _sub_rns_poly, polymath.cu:246-285) */
+int orc_plain_add(const orc_ctx *c, int l, u64 *ct0, const u64 *plain, int sub, u64 correction_factor) {
     const u64 n = c->n;
     if (l < 1 || l > c->size_Q) return -1;
     if (c->scheme == ORC_SCHEME_CKKS) {
         for (int i = 0; i < l; i++)
-            for (u64 x = 0; x < n; x++) ct0[i * n + x] = addmod(ct0[i * n + x], plain[i * n + x], c->primes[i]);
+            for (u64 x = 0; x < n; x++) {
+                const u64 q = c->primes[i], a = ct0[i * n + x], b = plain[i * n + x];
+                ct0[i * n + x] = sub ? submod(a, b, q) : addmod(a, b, q);
+            }
         return 0;
     }
     const u64 t = c->t;
@@ -2197,8 +2201,10 @@ int orc_encrypt_add_plain(const orc_ctx *c, int l, u64 *ct0, const u64 *plain) {
         const u64 neg = (t - q_mod_t) % t;
         for (int i = 0; i < l; i++) {
             const u64 q = c->primes[i], tinv = orc_invmod(t % q, q);
-            for (u64 x = 0; x < n; x++)
-                ct0[i * n + x] = addmod(ct0[i * n + x], orc_mulmod(orc_mulmod(plain[x], neg, t), tinv, q), q);
+            for (u64 x = 0; x < n; x++) {
+                const u64 v = orc_mulmod(orc_mulmod(plain[x], neg, t), tinv, q);
+                ct0[i * n + x] = sub ? submod(ct0[i * n + x], v, q) : addmod(ct0[i * n + x], v, q);
+            }
         }
         return 0;
     }
@@ -2209,8 +2215,49 @@ int orc_encrypt_add_plain(const orc_ctx *c, int l, u64 *ct0, const u64 *plain) {
         for (u64 x = 0; x < n; x++) lift[i * n + x] = plain[x] % c->primes[i];
     }
     orc_ntt_forward(c, lift, l, idx);
-    for (int i = 0; i < l; i++)
-        for (u64 x = 0; x < n; x++) ct0[i * n + x] = addmod(ct0[i * n + x], lift[i * n + x], c->primes[i]);
+    for (int i = 0; i < l; i++) {
+        const u64 q = c->primes[i];
+        for (u64 x = 0; x < n; x++) {
+            const u64 v = orc_mulmod(lift[i * n + x], correction_factor % q, q);
+            ct0[i * n + x] = sub ? submod(ct0[i * n + x], v, q) : addmod(ct0[i * n + x], v, q);
+        }
+    }
+    free(lift);
+    return 0;
+}
+
+/* the last step of encrypt_symmetric / encrypt_asymmetric (secretkey.cu:130-190, 463-530) */
+int orc_encrypt_add_plain(const orc_ctx *c, int l, u64 *ct0, const u64 *plain) { return orc_plain_add(c, l, ct0, plain, 0, 1); }
+
+/* multiply_plain_inplace (evaluate.cu:1226-1340): ct = [size][l][n].  BFV: multiply_plain_normal with abs_plain_rns_poly
+ * (polymath.cu:645-664); CKKS: multiply_plain_ntt; BGV: lifted plaintext */
+int orc_plain_multiply(const orc_ctx *c, int l, u64 *ct, int size, const u64 *plain) {
+    const u64 n = c->n;
+    if (l < 1 || l > c->size_Q || size < 1) return -1;
+    int idx[64];
+    for (int i = 0; i < l; i++) idx[i] = i;
+    u64 *lift = NULL;
+    const u64 *factor = plain;
+    if (c->scheme != ORC_SCHEME_CKKS) {
+        const u64 t = c->t;
+        lift = (u64 *)malloc((size_t)l * n * 8);
+        for (int i = 0; i < l; i++)
+            for (u64 x = 0; x < n; x++) {
+                u64 v = plain[x];
+                if (c->scheme == ORC_SCHEME_BFV) v = v >= ((t + 1) >> 1) ? v + (c->primes[i] - t) : v;
+                else v %= c->primes[i];
+                lift[i * n + x] = v;
+            }
+        orc_ntt_forward(c, lift, l, idx);
+        factor = lift;
+    }
+    for (int k = 0; k < size; k++) {
+        u64 *ck = ct + (size_t)k * l * n;
+        if (c->scheme == ORC_SCHEME_BFV) orc_ntt_forward(c, ck, l, idx);
+        for (int i = 0; i < l; i++)
+            for (u64 x = 0; x < n; x++) ck[i * n + x] = orc_mulmod(ck[i * n + x], factor[i * n + x], c->primes[i]);
+        if (c->scheme == ORC_SCHEME_BFV) orc_ntt_inverse(c, ck, l, idx);
+    }
     free(lift);
     return 0;
 }

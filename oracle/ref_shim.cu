@@ -555,6 +555,66 @@ int ref_load_symmetric(void *p, const unsigned char *bytes, size_t len, uint64_t
     SHIM_CATCH
 }
 
+/* a PhantomPlaintext holding caller-supplied words: [n] mod t (BFV, BGV) or [l][n] NTT form at chain_index with the
+ * context's scale (CKKS; built by encoding zero, then overwritten: the class has no public setters for level and scale) */
+static PhantomPlaintext make_plain(RefCtx *h, size_t chain_index, const uint64_t *plain) {
+    const auto &s = cudaStreamPerThread;
+    PhantomPlaintext pt;
+    size_t l = 1;
+    if (h->scheme == scheme_type::ckks) {
+        PhantomCKKSEncoder enc(*h->ctx);
+        std::vector<cuDoubleComplex> zero(1, make_cuDoubleComplex(0.0, 0.0));
+        enc.encode(*h->ctx, zero, h->scale, pt, chain_index);
+        l = h->ctx->get_context_data(chain_index).parms().coeff_modulus().size();
+    } else {
+        pt.resize(1, h->n, s);
+    }
+    cudaStreamSynchronize(s);
+    cudaMemcpy(pt.data(), plain, l * h->n * sizeof(uint64_t), cudaMemcpyHostToDevice);
+    return pt;
+}
+
+/* add_plain_inplace / sub_plain_inplace / multiply_plain_inplace (evaluate.cu:1106-1340) on caller-supplied words:
+ * op 0 / 1 / 2 */
+int ref_plain_op(void *p, int op, size_t chain_index, const uint64_t *ct, size_t size, const uint64_t *plain,
+                 uint64_t correction_factor, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto c = make_ct(h, chain_index, size, ct, h->scheme != scheme_type::bfv);
+    if (h->scheme == scheme_type::bgv) c.set_correction_factor(correction_factor);
+    PhantomPlaintext pt = make_plain(h, chain_index, plain);
+    if (op == 0) add_plain_inplace(*h->ctx, c, pt);
+    else if (op == 1) sub_plain_inplace(*h->ctx, c, pt);
+    else if (op == 2) multiply_plain_inplace(*h->ctx, c, pt);
+    else throw std::invalid_argument("unknown op");
+    fetch_ct(c, out);
+    return 0;
+    SHIM_CATCH
+}
+
+/* add_inplace / sub_inplace / sub_inplace(negate) / negate_inplace (evaluate.cu:106-338): op 0 / 1 / 2 / 3; the BGV
+ * correction factors go in, the balanced one comes back */
+int ref_add_sub(void *p, int op, size_t chain_index, const uint64_t *ct1, const uint64_t *ct2, size_t size, uint64_t cf1,
+                uint64_t cf2, uint64_t *out, uint64_t *cf_out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    bool ntt = h->scheme != scheme_type::bfv;
+    auto a = make_ct(h, chain_index, size, ct1, ntt);
+    if (h->scheme == scheme_type::bgv) a.set_correction_factor(cf1);
+    if (op == 3) {
+        negate_inplace(*h->ctx, a);
+    } else {
+        auto b = make_ct(h, chain_index, size, ct2, ntt);
+        if (h->scheme == scheme_type::bgv) b.set_correction_factor(cf2);
+        if (op == 0) add_inplace(*h->ctx, a, b);
+        else sub_inplace(*h->ctx, a, b, op == 2);
+    }
+    fetch_ct(a, out);
+    *cf_out = a.correction_factor();
+    return 0;
+    SHIM_CATCH
+}
+
 /* PhantomBatchEncoder::encode / decode (batchencoder.cu:62-118): values[count] -> plain[n]; plain[n] -> values[n] */
 int ref_batch_encode(void *p, const uint64_t *values, size_t count, uint64_t *plain) {
     SHIM_TRY

@@ -66,6 +66,10 @@ _sigs = {
     "pfhe_gen_kswitch_key": (ctypes.c_int, [vp, vp, vp, ctypes.c_char_p, vp, vp]),
     "pfhe_galois_secret_key": (ctypes.c_int, [vp, vp, ctypes.c_uint32, vp, vp]),
     "pfhe_encrypt_add_plain": (ctypes.c_int, [vp, sz, vp, vp, vp]),
+    "pfhe_add_plain_inplace": (ctypes.c_int, [vp, sz, vp, vp, ctypes.c_uint64, vp]),
+    "pfhe_sub_plain_inplace": (ctypes.c_int, [vp, sz, vp, vp, ctypes.c_uint64, vp]),
+    "pfhe_multiply_plain_inplace": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_multiply_scalar_rns_poly": (ctypes.c_int, [vp, vp, sz, ctypes.c_uint64, sz, vp]),
     "pfhe_batch_encode": (ctypes.c_int, [vp, vp, sz, vp, vp]),
     "pfhe_batch_decode": (ctypes.c_int, [vp, vp, vp, vp]),
     "pfhe_decrypt": (ctypes.c_int, [vp, sz, vp, sz, vp, ctypes.c_uint64, vp, vp]),

@@ -9,6 +9,7 @@ std::logic_error -> RuntimeError.  All arithmetic happens in libpfhe_b200.so on 
 """
 import ctypes
 import enum
+import math
 import os
 
 import numpy as np
@@ -729,7 +730,186 @@ def mod_switch_to_next(context, encrypted):
     dst = torch.empty((size, l - 1, n), dtype=torch.int64, device=encrypted.data.device)
     check(lib.pfhe_mod_switch_to_next(context._h, encrypted.chain_index, _ptr(encrypted.data), size, _ptr(dst),
                                       _stream()))
-    return PhantomCiphertext(None, dst, encrypted.chain_index + 1, encrypted.scale, encrypted.is_ntt_form)
+    out = PhantomCiphertext(None, dst, encrypted.chain_index + 1, encrypted.scale, encrypted.is_ntt_form)
+    out.noise_scale_deg, out.is_asymmetric = encrypted.noise_scale_deg, encrypted.is_asymmetric
+    if context.scheme == scheme_type.bgv:   # correction factor times q_last^-1 mod t (evaluate.cu:1420-1425)
+        t = context.parms.plain_modulus
+        q_last = context.parms.coeff_modulus[l - 1]
+        out.correction_factor = encrypted.correction_factor * pow(q_last % t, -1, t) % t
+    return out
+
+
+def mod_switch_to_inplace(context, encrypted, chain_index):
+    """mod_switch_to_inplace (include/evaluate.cuh:169-177)"""
+    if encrypted.chain_index > chain_index:
+        raise ValueError("cannot switch to higher level modulus")
+    while encrypted.chain_index != chain_index:
+        nxt = mod_switch_to_next(context, encrypted)
+        encrypted.__dict__.update(nxt.__dict__)
+
+
+def mod_switch_to(context, encrypted, chain_index):
+    out = encrypted.clone()
+    mod_switch_to_inplace(context, out, chain_index)
+    return out
+
+
+# ---- linear operations and plaintext operands (src/evaluate.cu:14-338, 1106-1340) ------------------------------------------
+def _are_close(a, b):
+    """are_close<double> (include/host/common.h:342-345)"""
+    return abs(a - b) < np.finfo(np.float64).eps * max(abs(a), abs(b), 1.0)
+
+
+def balance_correction_factors(factor1, factor2, t):
+    """balance_correction_factors (src/evaluate.cu:14-72): (f, e1, e2) with e1 * factor1 = e2 * factor2 = f mod t and
+    |e1| + |e2| minimal over the remainders of the extended Euclidean algorithm on (t, factor2 / factor1)."""
+    half = t // 2
+
+    def bal(x):
+        return x - t if x > half else x
+
+    try:
+        ratio = pow(factor1, -1, t) * factor2 % t
+    except ValueError:
+        raise RuntimeError("invalid correction factor1")
+    e1, e2 = ratio, 1
+    best = abs(bal(e1)) + abs(bal(e2))
+    prev_a, prev_b, a, b = t, 0, ratio, 1
+    while a != 0:
+        q = prev_a // a
+        prev_a, a = a, prev_a % a
+        prev_b, b = b, prev_b - b * q
+        a_mod, b_mod = a % t, b % t
+        if a_mod != 0 and math.gcd(a_mod, t) == 1:
+            cand = abs(bal(a_mod)) + abs(bal(b_mod))
+            if cand < best:
+                best, e1, e2 = cand, a_mod, b_mod
+    return e1 * factor1 % t, e1, e2
+
+
+def _check_pair(a, b):
+    if a.chain_index != b.chain_index:
+        raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+    if a.is_ntt_form != b.is_ntt_form:
+        raise ValueError("NTT form mismatch")
+    if not _are_close(a.scale, b.scale):
+        raise ValueError("scale mismatch")
+    if a.size() != b.size():
+        raise ValueError("poly number mismatch")
+
+
+def negate_inplace(context, encrypted):
+    """negate_inplace (src/evaluate.cu:83-108)"""
+    l = encrypted.coeff_modulus_size()
+    for k in range(encrypted.size()):
+        check(lib.pfhe_negate_rns_poly(context._h, _ptr(encrypted.data[k]), _ptr(encrypted.data[k]), l, _stream()))
+
+
+def _add_sub(context, encrypted1, encrypted2, sub, negate):
+    _check_pair(encrypted1, encrypted2)
+    l = encrypted1.coeff_modulus_size()
+    other = encrypted2.data
+    if encrypted1.correction_factor != encrypted2.correction_factor:   # BGV: balance the factors first (:148-165)
+        f, e1, e2 = balance_correction_factors(encrypted1.correction_factor, encrypted2.correction_factor,
+                                               context.parms.plain_modulus)
+        other = encrypted2.data.clone()
+        check(lib.pfhe_multiply_scalar_rns_poly(context._h, _ptr(encrypted1.data), encrypted1.size(), e1, l, _stream()))
+        check(lib.pfhe_multiply_scalar_rns_poly(context._h, _ptr(other), encrypted2.size(), e2, l, _stream()))
+        encrypted1.correction_factor = f
+    fn = lib.pfhe_sub_rns_poly if sub else lib.pfhe_add_rns_poly
+    for k in range(encrypted1.size()):
+        a, b = encrypted1.data[k], other[k]
+        if negate:
+            a, b = b, a
+        check(fn(context._h, _ptr(a), _ptr(b), _ptr(encrypted1.data[k]), l, _stream()))
+
+
+def add_inplace(context, encrypted1, encrypted2):
+    """add_inplace (src/evaluate.cu:115-197)"""
+    _add_sub(context, encrypted1, encrypted2, False, False)
+
+
+def sub_inplace(context, encrypted1, encrypted2, negate=False):
+    """sub_inplace (src/evaluate.cu:263-338): encrypted1 - encrypted2, or encrypted2 - encrypted1 with negate"""
+    _add_sub(context, encrypted1, encrypted2, True, negate)
+
+
+def add_many(context, encrypteds):
+    """add_many (src/evaluate.cu:200-261) -> the sum as a new ciphertext"""
+    if not encrypteds:
+        raise ValueError("encrypteds cannot be empty")
+    for c in encrypteds[1:]:
+        try:
+            _check_pair(encrypteds[0], c)
+        except ValueError as e:
+            raise ValueError(str(e).replace("encrypted1 and encrypted2", "encrypteds"))
+    out = encrypteds[0].clone()
+    for c in encrypteds[1:]:
+        add_inplace(context, out, c)
+    return out
+
+
+def _plain_operand(context, encrypted, plain, plain_scale):
+    _require_ntt(context, encrypted)
+    n, l = context.poly_degree, encrypted.coeff_modulus_size()
+    if context.scheme == scheme_type.ckks:
+        if tuple(plain.shape) != (l, n):
+            raise ValueError("encrypted and plain parameter mismatch")
+    elif tuple(plain.shape) != (n,):
+        raise ValueError("BFV / BGV plaintext is [N] residues mod t")
+    return plain.contiguous(), (encrypted.scale if plain_scale is None else plain_scale)
+
+
+def add_plain_inplace(context, encrypted, plain, plain_scale=None):
+    """add_plain_inplace (src/evaluate.cu:1106-1164).  plain: device words (BFV / BGV [N] mod t, CKKS [l][N] NTT form);
+    plain_scale: the plaintext's scale (the reference reads it off the PhantomPlaintext), default the ciphertext's"""
+    p, ps = _plain_operand(context, encrypted, plain, plain_scale)
+    if not _are_close(encrypted.scale, ps):
+        raise ValueError("scale mismatch")
+    check(lib.pfhe_add_plain_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data), _ptr(p),
+                                     encrypted.correction_factor, _stream()))
+
+
+def sub_plain_inplace(context, encrypted, plain, plain_scale=None):
+    """sub_plain_inplace (src/evaluate.cu:1166-1224)"""
+    p, ps = _plain_operand(context, encrypted, plain, plain_scale)
+    if not _are_close(encrypted.scale, ps):
+        raise ValueError("scale mismatch")
+    check(lib.pfhe_sub_plain_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data), _ptr(p),
+                                     encrypted.correction_factor, _stream()))
+
+
+def multiply_plain_inplace(context, encrypted, plain, plain_scale=1.0):
+    """multiply_plain_inplace (src/evaluate.cu:1226-1340); the scale becomes encrypted.scale * plain_scale"""
+    p, ps = _plain_operand(context, encrypted, plain, plain_scale)
+    check(lib.pfhe_multiply_plain_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data), encrypted.size(), _ptr(p),
+                                          _stream()))
+    encrypted.scale = encrypted.scale * ps
+
+
+# the copying forms the reference's Python binding exposes (python/src/binding.cu:125-165, include/evaluate.cuh)
+def _copying(fn):
+    def wrapped(context, encrypted, *args, **kwargs):
+        out = encrypted.clone()
+        fn(context, out, *args, **kwargs)
+        return out
+    wrapped.__name__ = fn.__name__.replace("_inplace", "")
+    wrapped.__doc__ = f"copying form of {fn.__name__}"
+    return wrapped
+
+
+negate = _copying(negate_inplace)
+add = _copying(add_inplace)
+sub = _copying(sub_inplace)
+add_plain = _copying(add_plain_inplace)
+sub_plain = _copying(sub_plain_inplace)
+multiply_plain = _copying(multiply_plain_inplace)
+multiply = _copying(multiply_inplace)
+multiply_and_relin = _copying(multiply_and_relin_inplace)
+relinearize = _copying(relinearize_inplace)
+apply_galois = _copying(apply_galois_inplace)
+rotate = _copying(rotate_inplace)
+hoisting = _copying(hoisting_inplace)
 
 
 def nwt_2d_radix8_forward_inplace(inout, context, coeff_modulus_size, start_modulus_idx):

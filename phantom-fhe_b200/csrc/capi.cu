@@ -337,7 +337,35 @@ int pfhe_galois_secret_key(pfhe_engine *e, const uint64_t *secret_key, uint32_t 
 int pfhe_encrypt_add_plain(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, void *stream) {
     API_BEGIN
     require(e && ct && plain, "null pointer");
-    e->impl.encrypt_add_plain(e->impl.limbs_at(chain_index), U(ct), U(plain), S(stream));
+    e->impl.plain_add(e->impl.limbs_at(chain_index), U(ct), U(plain), false, 1, S(stream));
+    API_END
+}
+int pfhe_add_plain_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, uint64_t correction_factor,
+                           void *stream) {
+    API_BEGIN
+    require(e && ct && plain, "null pointer");
+    e->impl.plain_add(e->impl.limbs_at(chain_index), U(ct), U(plain), false, correction_factor, S(stream));
+    API_END
+}
+int pfhe_sub_plain_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, uint64_t correction_factor,
+                           void *stream) {
+    API_BEGIN
+    require(e && ct && plain, "null pointer");
+    e->impl.plain_add(e->impl.limbs_at(chain_index), U(ct), U(plain), true, correction_factor, S(stream));
+    API_END
+}
+int pfhe_multiply_plain_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, size_t size, const uint64_t *plain,
+                                void *stream) {
+    API_BEGIN
+    require(e && ct && plain, "null pointer");
+    e->impl.plain_multiply(e->impl.limbs_at(chain_index), U(ct), (int) size, U(plain), S(stream));
+    API_END
+}
+int pfhe_multiply_scalar_rns_poly(pfhe_engine *e, uint64_t *inout, size_t size, uint64_t scalar, size_t coeff_mod_size,
+                                  void *stream) {
+    API_BEGIN
+    require(e && inout, "null pointer");
+    e->impl.multiply_scalar((int) coeff_mod_size, U(inout), (int) size, scalar, S(stream));
     API_END
 }
 int pfhe_batch_encode(pfhe_engine *e, const uint64_t *values, size_t count, uint64_t *plain, void *stream) {

@@ -2016,24 +2016,6 @@ void Engine::kswitch_key(const u64 *new_key, const u64 *sk, const Seed *seeds, u
     check_launch("k_kswitch_target");
 }
 
-// multiply_add_plain_with_scaling_variant (scalingvariant.cu:10-34): c0 += round-free scaling of the plaintext,
-// [m * (-Q_l mod t)]_t * t^-1 mod q_i; ct0 = [l][n] coefficient form, plain = [n] residues mod t
-void Engine::bfv_add_plain(int l, u64 *ct0, const u64 *plain, cudaStream_t st) {
-    if (scheme_ != Scheme::bfv) throw std::invalid_argument("unsupported scheme");
-    if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
-    if (!d_tinv_mod_q_.p) {
-        std::vector<u64> v(size_Q_);
-        for (int j = 0; j < size_Q_; j++) v[j] = hm::invmod(t_ % primes_[j], primes_[j]);
-        d_tinv_mod_q_.upload(v);
-    }
-    u64 q_mod_t = 1 % t_;
-    for (int j = 0; j < l; j++) q_mod_t = hm::mulmod(q_mod_t, primes_[j] % t_, t_);
-    const u64 neg = (t_ - q_mod_t) % t_;
-    launch_pdl(k_bfv_add_plain, dim3((unsigned) (n_ / EW_THREADS), l), EW_THREADS, 0, st, ct0, plain, neg, t_,
-               (const u64 *) d_tinv_mod_q_.p, (const Modulus *) d_mod_.p, n_);
-    check_launch("k_bfv_add_plain");
-}
-
 // the key-switching target of a Galois key: the secret key under the automorphism, over every key prime
 // (create_galois_keys, secretkey.cu:443-451: key_galois_tool->apply_galois_ntt)
 void Engine::galois_secret_key(const u64 *sk, uint32_t galois_elt, u64 *rotated, cudaStream_t st) const {
@@ -2043,22 +2025,72 @@ void Engine::galois_secret_key(const u64 *sk, uint32_t galois_elt, u64 *rotated,
     check_launch("k_galois_ntt");
 }
 
-// c0 += plaintext, the last step of encrypt_symmetric / encrypt_asymmetric (secretkey.cu:130-190, 463-530).
-// BFV: scaled by Q_l / t (bfv_add_plain); CKKS: plain = [l][n] in NTT form; BGV: plain = [n] residues mod t, lifted to every
-// limb and transformed
-void Engine::encrypt_add_plain(int l, u64 *ct0, const u64 *plain, cudaStream_t st) {
+// add_plain_inplace / sub_plain_inplace (evaluate.cu:1106-1224) and the last step of encrypt_symmetric / encrypt_asymmetric
+// (secretkey.cu:130-190, 463-530): c0 +-= plaintext.
+//   BFV   multiply_add / multiply_sub_plain_with_scaling_variant (scalingvariant.cu:10-60): plain = [n] mod t, scaled by Q_l / t
+//   CKKS  plain = [l][n] in NTT form
+//   BGV   plain = [n] mod t, lifted to every limb, transformed, times the ciphertext's correction factor
+void Engine::plain_add(int l, u64 *ct0, const u64 *plain, bool sub, u64 correction_factor, cudaStream_t st) {
     if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
-    if (scheme_ == Scheme::bfv) return bfv_add_plain(l, ct0, plain, st);
     const dim3 grid((unsigned) (n_ / EW_THREADS), l);
     if (scheme_ == Scheme::ckks) {
-        elementwise(EW_ADD, ct0, plain, ct0, l, st);
+        elementwise(sub ? EW_SUB : EW_ADD, ct0, plain, ct0, l, st);
+        return;
+    }
+    if (scheme_ == Scheme::bfv) {
+        if (!d_tinv_mod_q_.p) {
+            std::vector<u64> v(size_Q_);
+            for (int j = 0; j < size_Q_; j++) v[j] = hm::invmod(t_ % primes_[j], primes_[j]);
+            d_tinv_mod_q_.upload(v);
+        }
+        u64 q_mod_t = 1 % t_;
+        for (int j = 0; j < l; j++) q_mod_t = hm::mulmod(q_mod_t, primes_[j] % t_, t_);
+        const u64 neg = (t_ - q_mod_t) % t_;
+        if (sub) launch_pdl(k_bfv_add_plain<true>, grid, EW_THREADS, 0, st, ct0, plain, neg, t_, (const u64 *) d_tinv_mod_q_.p, (const Modulus *) d_mod_.p, n_);
+        else launch_pdl(k_bfv_add_plain<false>, grid, EW_THREADS, 0, st, ct0, plain, neg, t_, (const u64 *) d_tinv_mod_q_.p, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_bfv_add_plain");
         return;
     }
     u64 *lifted = ws_.tmp.p;
-    launch_pdl(k_lift_plain, grid, EW_THREADS, 0, st, lifted, plain, (const Modulus *) d_mod_.p, n_);
+    launch_pdl(k_lift_plain<false>, grid, EW_THREADS, 0, st, lifted, plain, (const Modulus *) d_mod_.p, n_, t_);
     check_launch("k_lift_plain");
     ntt_fwd_rows_range(lifted, l, 0, st);
-    elementwise(EW_ADD, ct0, lifted, ct0, l, st);
+    if (sub) launch_pdl(k_axpy<true>, grid, EW_THREADS, 0, st, ct0, (const u64 *) ct0, (const u64 *) lifted, correction_factor, (const Modulus *) d_mod_.p, n_);
+    else launch_pdl(k_axpy<false>, grid, EW_THREADS, 0, st, ct0, (const u64 *) ct0, (const u64 *) lifted, correction_factor, (const Modulus *) d_mod_.p, n_);
+    check_launch("k_axpy");
+}
+
+// multiply_plain_inplace (evaluate.cu:1226-1340): every polynomial of ct times the plaintext.  CKKS: plain = [l][n] NTT form;
+// BGV: plain lifted and transformed; BFV (multiply_plain_normal): plain lifted with the upper half moved to negative
+// residues, ciphertext to NTT form and back.  ct = [size][l][n]
+void Engine::plain_multiply(int l, u64 *ct, int size, const u64 *plain, cudaStream_t st) {
+    if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
+    if (size < 1) throw std::invalid_argument("ciphertext is empty");
+    const dim3 grid((unsigned) (n_ / EW_THREADS), l);
+    const u64 *factor = plain;
+    if (scheme_ != Scheme::ckks) {
+        u64 *lifted = ws_.tmp.p;
+        if (scheme_ == Scheme::bfv) launch_pdl(k_lift_plain<true>, grid, EW_THREADS, 0, st, lifted, plain, (const Modulus *) d_mod_.p, n_, t_);
+        else launch_pdl(k_lift_plain<false>, grid, EW_THREADS, 0, st, lifted, plain, (const Modulus *) d_mod_.p, n_, t_);
+        check_launch("k_lift_plain");
+        ntt_fwd_rows_range(lifted, l, 0, st);
+        factor = lifted;
+    }
+    if (scheme_ == Scheme::bfv) ntt_batch(ct, size, l, 0, false, st);
+    for (int k = 0; k < size; k++) elementwise(EW_MUL, ct + (size_t) k * l * n_, factor, ct + (size_t) k * l * n_, l, st);
+    if (scheme_ == Scheme::bfv) ntt_batch(ct, size, l, 0, true, st);
+}
+
+// multiply_scalar_rns_poly (polymath.cu:210-228) over `count` limbs starting at modulus row 0 of each polynomial:
+// the BGV correction-factor balancing of add / sub (evaluate.cu:148-165)
+void Engine::multiply_scalar(int l, u64 *inout, int size, u64 scalar, cudaStream_t st) const {
+    if (l < 1 || l > size_QP_) throw std::invalid_argument("limb count out of range");
+    for (int k = 0; k < size; k++) {
+        u64 *pk = inout + (size_t) k * l * n_;
+        launch_pdl(k_axpy<false>, dim3((unsigned) (n_ / EW_THREADS), l), EW_THREADS, 0, st, pk, (const u64 *) nullptr, (const u64 *) pk, scalar,
+                   (const Modulus *) d_mod_.p, n_);
+        check_launch("k_axpy");
+    }
 }
 
 } // namespace pfhe

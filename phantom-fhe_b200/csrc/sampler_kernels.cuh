@@ -131,10 +131,13 @@ __global__ void __launch_bounds__(EW_THREADS) k_kswitch_target(u64 *const *digit
     key[o] = add_mod(key[o], mul_mod(new_key[o], p_mod_q[j], m), m.q);
 }
 
-// bfv_add_timesQ_overt_kernel (polymath.cu:413-436): c0 += [m * (-Q_l mod t)]_t * t^-1 mod q_i
+// ---- plaintext operands (add_plain / sub_plain / multiply_plain, evaluate.cu:1106-1340, and the last step of encryption) --
+
+// bfv_add_timesQ_overt_kernel / bfv_sub_timesQ_overt_kernel (polymath.cu:413-461): c0 +-= [m * (-Q_l mod t)]_t * t^-1 mod q_i
+// (t may be any modulus here, not only a table row: plain 128-bit remainder)
+template<bool SUB>
 __global__ void __launch_bounds__(EW_THREADS) k_bfv_add_plain(u64 *ct0, const u64 *plain, u64 neg_q_mod_t, u64 t,
                                                               const u64 *tinv_mod_q, const Modulus *mod, size_t n) {
-    // (t may be any modulus here, not only a table row: plain 128-bit remainder, once per coefficient and limb)
     pdl_launch_dependents();
     pdl_wait();
     const size_t c = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
@@ -142,16 +145,37 @@ __global__ void __launch_bounds__(EW_THREADS) k_bfv_add_plain(u64 *ct0, const u6
     const Modulus m = mod[i];
     const u64 scaled = (u64) (((unsigned __int128) plain[c] * neg_q_mod_t) % t);
     const size_t o = (size_t) i * n + c;
-    ct0[o] = add_mod(ct0[o], mul_mod(scaled, tinv_mod_q[i], m), m.q);
+    const u64 v = mul_mod(scaled, tinv_mod_q[i], m);
+    ct0[o] = SUB ? sub_mod(ct0[o], v, m.q) : add_mod(ct0[o], v, m.q);
 }
 
-// BGV plaintext [n] (residues mod t) copied under every limb (encrypt_symmetric, secretkey.cu:513-518; the asymmetric path
-// reduces mod q_i on the way, nwt_2d_radix8_forward_modup_fuse -- the same thing whenever t < q_i)
-__global__ void __launch_bounds__(EW_THREADS) k_lift_plain(u64 *out, const u64 *plain, const Modulus *mod, size_t n) {
+// a plaintext [n] (residues mod t) under every limb.  ABS = false: reduced mod q_i (nwt_2d_radix8_forward_modup_fuse's
+// load; encrypt_symmetric copies it unreduced, the same thing whenever t < q_i).  ABS = true: abs_plain_rns_poly
+// (polymath.cu:645-664), values from (t + 1) / 2 up stand for negative numbers and move to q_i - (t - value)
+template<bool ABS>
+__global__ void __launch_bounds__(EW_THREADS) k_lift_plain(u64 *out, const u64 *plain, const Modulus *mod, size_t n, u64 t) {
     pdl_launch_dependents();
     pdl_wait();
     const size_t c = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
-    out[(size_t) blockIdx.y * n + c] = barrett64(plain[c], mod[blockIdx.y]);
+    const Modulus m = mod[blockIdx.y];
+    u64 v = plain[c];
+    if (ABS) v = v >= ((t + 1) >> 1) ? v + (m.q - t) : v;
+    else v = barrett64(v, m);
+    out[(size_t) blockIdx.y * n + c] = v;
+}
+
+// multiply_scalar_and_add_rns_poly / multiply_scalar_and_sub_rns_poly / multiply_scalar_rns_poly (polymath.cu:210-285):
+// out = a +- scalar * b, or scalar * b alone when a is null
+template<bool SUB>
+__global__ void __launch_bounds__(EW_THREADS) k_axpy(u64 *out, const u64 *a, const u64 *b, u64 scalar, const Modulus *mod,
+                                                     size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t c = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
+    const Modulus m = mod[blockIdx.y];
+    const size_t o = (size_t) blockIdx.y * n + c;
+    const u64 v = mul_mod(b[o], barrett64(scalar, m), m);
+    out[o] = !a ? v : SUB ? sub_mod(a[o], v, m.q) : add_mod(a[o], v, m.q);
 }
 
 }   // namespace pfhe

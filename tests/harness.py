@@ -71,6 +71,8 @@ def oracle():
         o.orc_encrypt_zero_asymmetric.argtypes = [vp, u64p, ctypes.c_char_p, ctypes.c_char_p, u64p]
         o.orc_gen_kswitch_key.argtypes = [vp, u64p, u64p, ctypes.c_char_p, u64p]
         o.orc_encrypt_add_plain.argtypes = [vp, ctypes.c_int, u64p, u64p]
+        o.orc_plain_add.argtypes = [vp, ctypes.c_int, u64p, u64p, ctypes.c_int, ctypes.c_uint64]
+        o.orc_plain_multiply.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p]
         o.orc_batch_encode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, ctypes.c_uint64, u64p]
         o.orc_batch_decode.argtypes = [ctypes.c_uint64, ctypes.c_uint64, u64p, u64p]
         o.orc_decrypt.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p, ctypes.c_int, ctypes.c_uint64, u64p]
@@ -149,6 +151,10 @@ def reference():
             r.ref_encrypt_save_symmetric.argtypes = [vp, ctypes.c_size_t, u64p, ctypes.c_char_p, ctypes.c_size_t, u64p]
             r.ref_encrypt_save_symmetric.restype = ctypes.c_long
             r.ref_load_symmetric.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t, u64p]
+        if hasattr(r, "ref_plain_op"):
+            r.ref_plain_op.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p, ctypes.c_uint64, u64p]
+            r.ref_add_sub.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_uint64,
+                                      ctypes.c_uint64, u64p, u64p]
         if hasattr(r, "ref_batch_encode"):
             r.ref_batch_encode.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
             r.ref_batch_decode.argtypes = [vp, u64p, u64p]

@@ -129,3 +129,33 @@ def test_serialisation_round_trip_and_layout():
     serial.write_ciphertext(full, words, 1, is_asymmetric=True)
     with pytest.raises(RuntimeError):   # "Asymmetric ciphertext does not have seed."
         serial.read_ciphertext_symmetric(io.BytesIO(full.getvalue()))
+
+
+def test_balance_correction_factors():
+    """balance_correction_factors (src/evaluate.cu:14-72) in the host mirror: e1 * f1 = e2 * f2 = f mod t with e1, e2
+    invertible, never worse than the trivial pair (f2 / f1, 1), and the small cases worked by hand."""
+    import importlib.util
+    import math
+    import types
+    import sys
+    src = open(os.path.join(ROOT, "phantom-fhe_b200", "api.py")).read()
+    start = src.index("def balance_correction_factors")
+    end = src.index("def _check_pair")
+    ns = {"math": math}
+    exec(src[start:end], ns)   # the function is pure Python; api.py itself needs the CUDA library to import
+    bal = ns["balance_correction_factors"]
+    t = 65537
+    assert bal(3, 5, t) == (15, 5, 3)
+    assert bal(1, 1, t) == (1, 1, 1)
+    rng = np.random.default_rng(0)
+    for _ in range(200):
+        f1, f2 = int(rng.integers(1, t)), int(rng.integers(1, t))
+        f, e1, e2 = bal(f1, f2, t)
+        assert e1 * f1 % t == f and e2 * f2 % t == f and math.gcd(e1, t) == 1 and math.gcd(e2, t) == 1
+
+        def mag(x):
+            return min(x, t - x)
+        ratio = pow(f1, -1, t) * f2 % t
+        assert mag(e1) + mag(e2) <= mag(ratio) + 1
+    with pytest.raises(RuntimeError):
+        bal(0, 5, t)
