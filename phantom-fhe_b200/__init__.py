@@ -8,7 +8,7 @@ torch.distributed only.  There is no CPU fallback: a missing library or a missin
 """
 from ._lib import lib, LIB_PATH, PfheError, check  # noqa: F401
 from .api import (  # noqa: F401
-    EncryptionParameters, PhantomContext, PhantomCiphertext, PhantomRelinKey, PhantomGaloisKey, PhantomSecretKey, PhantomPublicKey, random_bytes, PhantomBatchEncoder, PhantomCKKSEncoder, CoeffModulus,
+    EncryptionParameters, PhantomContext, PhantomCiphertext, PhantomRelinKey, PhantomGaloisKey, PhantomSecretKey, PhantomPublicKey, random_bytes, save_plaintext, load_plaintext, PhantomBatchEncoder, PhantomCKKSEncoder, CoeffModulus, PlainModulus, create_coeff_modulus, create_plain_modulus,
     scheme_type, mul_tech_type, multiply_inplace, relinearize_inplace, multiply_and_relin_inplace, multiply_and_relin_batch, rotate_inplace, rotate_batch,
     apply_galois_inplace, hoisting_inplace, rescale_to_next, mod_switch_to_next, get_elt_from_step, get_elts_from_steps,
     nwt_2d_radix8_forward_inplace, nwt_2d_radix8_backward_inplace,

@@ -52,6 +52,18 @@ class CoeffModulus:
         return [int(v) for v in out]
 
 
+class PlainModulus:
+    @staticmethod
+    def Batching(poly_modulus_degree, bit_size):
+        """PlainModulus::Batching (include/host/modulus.h:317-319): the first prime of that size that is 1 mod 2N"""
+        return CoeffModulus.Create(poly_modulus_degree, [bit_size])[0]
+
+
+# names of the reference's Python binding (python/src/binding.cu:41-43)
+create_coeff_modulus = CoeffModulus.Create
+create_plain_modulus = PlainModulus.Batching
+
+
 def get_elt_from_step(step, coeff_count):
     """include/galois.cuh:16-49"""
     elt = ctypes.c_uint32()
@@ -267,6 +279,42 @@ class PhantomCKKSEncoder:
         torch.cuda.current_stream().synchronize()
         return out.cpu().numpy().view(np.complex128)
 
+    # names of the reference's Python binding (python/src/binding.cu:98-117)
+    def encode_complex_vector(self, context, values, scale, chain_index=1):
+        return self.encode(context, values, scale, chain_index)
+
+    def encode_double_vector(self, context, values, scale, chain_index=1):
+        return self.encode(context, np.asarray(values, dtype=np.float64), scale, chain_index)
+
+    def decode_complex_vector(self, context, plain, scale, chain_index=None):
+        return self.decode(context, plain, scale, chain_index)
+
+    def decode_double_vector(self, context, plain, scale, chain_index=None):
+        """the real parts (decode_internal's std::vector<double> form, include/ckks.h:46-55)"""
+        return np.ascontiguousarray(self.decode(context, plain, scale, chain_index).real)
+
+
+def save_plaintext(stream, plain, chain_index=0, scale=1.0):
+    """PhantomPlaintext::save (include/plaintext.h:69-81) of a device plaintext: CKKS [l][N] with its level and scale,
+    BFV / BGV [N] (chain_index 0, scale 1 as the batch encoder leaves them)."""
+    torch.cuda.current_stream().synchronize()
+    serial.write_plaintext(stream, plain.cpu().numpy().view(np.uint64), chain_index, scale)
+
+
+def load_plaintext(context, stream):
+    """PhantomPlaintext::load (include/plaintext.h:83-97) -> (device words, chain_index, scale).  The reference's CKKS
+    encoder sizes every plaintext for the full chain and fills the first l limbs (include/ckks.h:78-80), so a stream written
+    by a stock build may carry more limbs than the level has: the limbs of the level are kept."""
+    words, chain_index, scale = serial.read_plaintext(stream)
+    if words.shape[1] != context.poly_degree:
+        raise ValueError("plaintext stream does not belong to this context")
+    if context.scheme == scheme_type.ckks:
+        l = context.coeff_modulus_size(chain_index)
+        if words.shape[0] < l:
+            raise ValueError("plaintext stream does not belong to this context")
+        return _to_dev(words[:l], context.device), chain_index, scale
+    return _to_dev(words[0], context.device), chain_index, scale
+
 
 class PhantomBatchEncoder:
     """PhantomBatchEncoder (include/batchencoder.h, src/batchencoder.cu): BFV / BGV slot packing over the plain modulus."""
@@ -329,6 +377,18 @@ class PhantomPublicKey:
 
     def __init__(self, context, pk):
         self.pk = pk   # device [2][size_QP][N]
+
+    def save(self, stream):
+        """PhantomPublicKey::save (include/secretkey.h:85-90)"""
+        torch.cuda.current_stream().synchronize()
+        serial.write_public_key(stream, self.pk.cpu().numpy().view(np.uint64))
+
+    @classmethod
+    def load(cls, context, stream):
+        words = serial.read_public_key(stream)
+        if words.shape[1] != context.size_QP or words.shape[2] != context.poly_degree:
+            raise ValueError("public key stream does not belong to this context")
+        return cls(context, _to_dev(words, context.device))
 
     def encrypt_asymmetric(self, context, plain, scale=1.0, seeds=None):
         """plain: device plaintext (BFV / BGV: [N] mod t, first data level; CKKS: [l][N] NTT form, l = size_Q: the

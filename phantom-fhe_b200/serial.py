@@ -90,6 +90,42 @@ def read_relin_key(stream):
     return [read_ciphertext(stream)[0] for _ in range(dnum)]
 
 
+def write_public_key(stream, pk):
+    """PhantomPublicKey::save (include/secretkey.h:85-90): the ciphertext stream of pk_ -- [2][size_QP][N], chain_index 0,
+    NTT form, as encrypt_zero_symmetric leaves it (secretkey.cu:380-392)."""
+    write_ciphertext(stream, pk, 0, 1.0, 1, 1, True, False)
+
+
+def read_public_key(stream):
+    words, hdr = read_ciphertext(stream)
+    if words.shape[0] != 2 or hdr["chain_index"] != 0:
+        raise ValueError("not a public key stream")
+    return words
+
+
+def write_plaintext(stream, words, chain_index, scale=1.0):
+    """PhantomPlaintext::save (include/plaintext.h:69-81): chain_index, N, coeff_modulus_size, scale, words."""
+    w = np.ascontiguousarray(words, dtype=np.uint64)
+    if w.ndim == 1:
+        w = w.reshape(1, -1)
+    if w.ndim != 2:
+        raise ValueError("plaintext words must be [coeff_modulus_size][N]")
+    stream.write(struct.pack("<QQQd", chain_index, w.shape[1], w.shape[0], float(scale)))
+    stream.write(w.tobytes())
+
+
+def read_plaintext(stream):
+    """-> (words [coeff_modulus_size][N], chain_index, scale)   (PhantomPlaintext::load, include/plaintext.h:83-97)"""
+    raw = stream.read(32)
+    if len(raw) != 32:
+        raise ValueError("truncated plaintext stream")
+    ci, n, l, scale = struct.unpack("<QQQd", raw)
+    body = stream.read(l * n * 8)
+    if len(body) != l * n * 8:
+        raise ValueError("truncated plaintext stream")
+    return np.frombuffer(body, dtype=np.uint64).reshape(l, n).copy(), ci, scale
+
+
 def write_galois_key(stream, keys):
     stream.write(struct.pack("<Q", len(keys)))
     for k in keys:

@@ -159,3 +159,37 @@ def test_balance_correction_factors():
         assert mag(e1) + mag(e2) <= mag(ratio) + 1
     with pytest.raises(RuntimeError):
         bal(0, 5, t)
+
+
+def test_plaintext_and_public_key_streams():
+    """PhantomPlaintext::save / load (include/plaintext.h:69-97) and PhantomPublicKey::save / load (include/secretkey.h:85-96):
+    field order and sizes, round trips, truncation refused."""
+    import importlib.util
+    import io
+    import struct
+    spec = importlib.util.spec_from_file_location("pfhe_serial2", os.path.join(ROOT, "phantom-fhe_b200", "serial.py"))
+    serial = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(serial)
+    rng = np.random.default_rng(1)
+    words = rng.integers(0, 1 << 50, (3, 16), dtype=np.uint64)
+    buf = io.BytesIO()
+    serial.write_plaintext(buf, words, 2, scale=2.0 ** 40)
+    raw = buf.getvalue()
+    assert len(raw) == 32 + words.size * 8 and struct.unpack_from("<QQQd", raw, 0) == (2, 16, 3, 2.0 ** 40)
+    back, ci, scale = serial.read_plaintext(io.BytesIO(raw))
+    assert np.array_equal(back, words) and ci == 2 and scale == 2.0 ** 40
+    buf = io.BytesIO()
+    serial.write_plaintext(buf, words[0], 0)   # BFV / BGV: one row of residues mod t
+    assert struct.unpack_from("<QQQd", buf.getvalue(), 0) == (0, 16, 1, 1.0)
+    with pytest.raises(ValueError):
+        serial.read_plaintext(io.BytesIO(raw[:-1]))
+    pk = rng.integers(0, 1 << 50, (2, 4, 16), dtype=np.uint64)
+    buf = io.BytesIO()
+    serial.write_public_key(buf, pk)
+    raw = buf.getvalue()
+    assert struct.unpack_from("<QQQQ", raw, 0) == (0, 2, 16, 4) and raw[56:58] == b"\x01\x00"
+    assert np.array_equal(serial.read_public_key(io.BytesIO(raw)), pk)
+    one = io.BytesIO()
+    serial.write_ciphertext(one, pk, 1)
+    with pytest.raises(ValueError):
+        serial.read_public_key(io.BytesIO(one.getvalue()))
