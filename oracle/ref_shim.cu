@@ -615,6 +615,22 @@ int ref_add_sub(void *p, int op, size_t chain_index, const uint64_t *ct1, const 
     SHIM_CATCH
 }
 
+/* gen_publickey with the context's secret key, then PhantomPublicKey::save (secretkey.h:85-90): returns the stream length */
+long ref_public_key_stream(void *p, unsigned char *out, size_t cap) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    if (!h->sk) throw std::invalid_argument("context was created without keys");
+    PhantomPublicKey pk = h->sk->gen_publickey(*h->ctx);
+    cudaStreamSynchronize(cudaStreamPerThread);
+    std::stringstream ss;
+    pk.save(ss);
+    const std::string blob = ss.str();
+    if (blob.size() > cap) throw std::invalid_argument("buffer too small");
+    std::memcpy(out, blob.data(), blob.size());
+    return (long) blob.size();
+    SHIM_CATCH
+}
+
 /* PhantomBatchEncoder::encode / decode (batchencoder.cu:62-118): values[count] -> plain[n]; plain[n] -> values[n] */
 int ref_batch_encode(void *p, const uint64_t *values, size_t count, uint64_t *plain) {
     SHIM_TRY

@@ -155,6 +155,9 @@ def reference():
             r.ref_plain_op.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, u64p, ctypes.c_size_t, u64p, ctypes.c_uint64, u64p]
             r.ref_add_sub.argtypes = [vp, ctypes.c_int, ctypes.c_size_t, u64p, u64p, ctypes.c_size_t, ctypes.c_uint64,
                                       ctypes.c_uint64, u64p, u64p]
+        if hasattr(r, "ref_public_key_stream"):
+            r.ref_public_key_stream.argtypes = [vp, ctypes.c_char_p, ctypes.c_size_t]
+            r.ref_public_key_stream.restype = ctypes.c_long
         if hasattr(r, "ref_batch_encode"):
             r.ref_batch_encode.argtypes = [vp, u64p, ctypes.c_size_t, u64p]
             r.ref_batch_decode.argtypes = [vp, u64p, u64p]
