@@ -62,3 +62,37 @@ def test_product_does_not_touch_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".hpp", ".h")) or f == "Makefile":
                 text = open(os.path.join(dirpath, f), errors="ignore").read()
                 assert "liboracle" not in text and "fhe_oracle" not in text and "harness" not in text, f
+
+
+def test_header_is_plain_c_and_links_from_c(tmp_path):
+    """include/pfhe_b200.h is a C header (no C++ or torch types in any signature): a C99 translation unit that includes it
+    compiles with -Wall -Werror -pedantic, links against the library without any other dependency named on the command
+    line, and calls a host-only entry point the way a cgo / JNI / ctypes binding would."""
+    import shutil
+    import subprocess
+    import phantom_fhe_b200 as pf
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("no C compiler")
+    src = tmp_path / "demo.c"
+    src.write_text(
+        '#include <stdio.h>\n#include "pfhe_b200.h"\n'
+        "int main(void) {\n"
+        "    int bits[2] = {50, 40};\n    uint64_t primes[2];\n"
+        "    int rc = pfhe_create_primes(4096, bits, 2, primes);\n"
+        "    if (rc != 0) { printf(\"error %d: %s\\n\", rc, pfhe_last_error()); return 1; }\n"
+        "    printf(\"%llu %llu\\n\", (unsigned long long) primes[0], (unsigned long long) primes[1]);\n"
+        "    pfhe_engine *e = 0;\n"
+        "    rc = pfhe_engine_create(&e, 3, 4096, primes, 2, 1, 0, 0, 0);   /* no device here: must fail, not fall back */\n"
+        "    printf(\"%d\\n\", rc);\n    return 0;\n}\n")
+    exe = tmp_path / "demo"
+    lib_dir = os.path.dirname(pf.LIB_PATH)
+    subprocess.check_call([gcc, "-std=c99", "-Wall", "-Werror", "-pedantic", "-I", os.path.join(ROOT, "include"), str(src), "-o",
+                           str(exe), "-L", lib_dir, "-lpfhe_b200", f"-Wl,-rpath,{lib_dir}"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stdout + out.stderr
+    lines = out.stdout.split()
+    assert [int(lines[0]), int(lines[1])] == pf.CoeffModulus.Create(4096, [50, 40])
+    import torch
+    if not torch.cuda.is_available():
+        assert int(lines[2]) == 3   # PFHE_ERR_CUDA
