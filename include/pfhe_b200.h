@@ -166,6 +166,13 @@ int pfhe_gen_kswitch_key(pfhe_engine *e, const uint64_t *new_key, const uint64_t
                          uint64_t *const *digits, void *stream);
 /* the secret key under a Galois automorphism (create_galois_keys, src/secretkey.cu:443-451): rotated = [size_QP][N] */
 int pfhe_galois_secret_key(pfhe_engine *e, const uint64_t *secret_key, uint32_t galois_elt, uint64_t *rotated, void *stream);
+/* PhantomGaloisTool::apply_galois_ntt (src/galois.cu:86-102, NTT form: an index permutation, the element must be one of the
+ * context's) and apply_galois (src/galois.cu:20-39,104-120, coefficient form: x^i -> +-x^(i elt mod 2N), any odd element):
+ * result[limb] = automorphism of operand[limb] over the first coeff_mod_size key primes; not in place. */
+int pfhe_apply_galois_ntt(pfhe_engine *e, const uint64_t *operand, size_t coeff_mod_size, uint32_t galois_elt, uint64_t *result,
+                          void *stream);
+int pfhe_apply_galois(pfhe_engine *e, const uint64_t *operand, size_t coeff_mod_size, uint32_t galois_elt, uint64_t *result,
+                      void *stream);
 /* the last step of encrypt_symmetric / encrypt_asymmetric (src/secretkey.cu:130-190, 463-530): ct[0] += plaintext.
  * BFV: multiply_add_plain_with_scaling_variant (src/scalingvariant.cu:10-34), plain = [N] mod t; CKKS: plain = [l][N] NTT
  * form; BGV: plain = [N] mod t, lifted to every limb and transformed. */

@@ -65,6 +65,8 @@ _sigs = {
     "pfhe_encrypt_zero_asymmetric": (ctypes.c_int, [vp, sz, vp, ctypes.c_char_p, ctypes.c_char_p, vp, vp]),
     "pfhe_gen_kswitch_key": (ctypes.c_int, [vp, vp, vp, ctypes.c_char_p, vp, vp]),
     "pfhe_galois_secret_key": (ctypes.c_int, [vp, vp, ctypes.c_uint32, vp, vp]),
+    "pfhe_apply_galois_ntt": (ctypes.c_int, [vp, vp, sz, ctypes.c_uint32, vp, vp]),
+    "pfhe_apply_galois": (ctypes.c_int, [vp, vp, sz, ctypes.c_uint32, vp, vp]),
     "pfhe_encrypt_add_plain": (ctypes.c_int, [vp, sz, vp, vp, vp]),
     "pfhe_add_plain_inplace": (ctypes.c_int, [vp, sz, vp, vp, ctypes.c_uint64, vp]),
     "pfhe_sub_plain_inplace": (ctypes.c_int, [vp, sz, vp, vp, ctypes.c_uint64, vp]),

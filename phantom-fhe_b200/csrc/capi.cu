@@ -331,7 +331,23 @@ int pfhe_gen_kswitch_key(pfhe_engine *e, const uint64_t *new_key, const uint64_t
 int pfhe_galois_secret_key(pfhe_engine *e, const uint64_t *secret_key, uint32_t galois_elt, uint64_t *rotated, void *stream) {
     API_BEGIN
     require(e && secret_key && rotated, "null pointer");
-    e->impl.galois_secret_key(U(secret_key), galois_elt, U(rotated), S(stream));
+    e->impl.galois_ntt(U(secret_key), e->impl.size_QP(), galois_elt, U(rotated), S(stream));
+    API_END
+}
+int pfhe_apply_galois_ntt(pfhe_engine *e, const uint64_t *operand, size_t coeff_mod_size, uint32_t galois_elt, uint64_t *result,
+                          void *stream) {
+    API_BEGIN
+    require(e && operand && result, "null pointer");
+    e->impl.galois_ntt(U(operand), (int) coeff_mod_size, galois_elt, U(result), S(stream));
+    API_END
+}
+int pfhe_apply_galois(pfhe_engine *e, const uint64_t *operand, size_t coeff_mod_size, uint32_t galois_elt, uint64_t *result,
+                      void *stream) {
+    API_BEGIN
+    require(e && operand && result && operand != result, "null pointer or in-place call");
+    require(coeff_mod_size >= 1 && coeff_mod_size <= (size_t) e->impl.size_QP(), "limb count out of range");
+    require((galois_elt & 1) && galois_elt < 2 * e->impl.n(), "Galois element is not valid");
+    e->impl.galois_coeff(U(result), U(operand), galois_elt, (int) coeff_mod_size, 1, S(stream));
     API_END
 }
 int pfhe_encrypt_add_plain(pfhe_engine *e, size_t chain_index, uint64_t *ct, const uint64_t *plain, void *stream) {

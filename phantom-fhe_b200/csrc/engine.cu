@@ -2016,11 +2016,14 @@ void Engine::kswitch_key(const u64 *new_key, const u64 *sk, const Seed *seeds, u
     check_launch("k_kswitch_target");
 }
 
-// the key-switching target of a Galois key: the secret key under the automorphism, over every key prime
-// (create_galois_keys, secretkey.cu:443-451: key_galois_tool->apply_galois_ntt)
-void Engine::galois_secret_key(const u64 *sk, uint32_t galois_elt, u64 *rotated, cudaStream_t st) const {
+// PhantomGaloisTool::apply_galois_ntt (galois.cu:86-102): result[limb][i] = operand[limb][perm[i]] over `limbs` limbs; the
+// index permutation is the same for every modulus.  With limbs = size_QP on the secret key this is the key-switching
+// target of a Galois key (create_galois_keys, secretkey.cu:443-451)
+void Engine::galois_ntt(const u64 *operand, int limbs, uint32_t galois_elt, u64 *result, cudaStream_t st) const {
+    if (limbs < 1) throw std::invalid_argument("limb count out of range");
+    if (operand == result) throw std::invalid_argument("the permutation does not work in place");
     const int gi = galois_index(galois_elt);
-    launch_pdl(k_galois_ntt, dim3((unsigned) (n_ / (2 * EW_THREADS)), size_QP_), EW_THREADS, 0, st, rotated, sk,
+    launch_pdl(k_galois_ntt, dim3((unsigned) (n_ / (2 * EW_THREADS)), limbs), EW_THREADS, 0, st, result, operand,
                (const uint32_t *) d_perm_[gi].p, n_);
     check_launch("k_galois_ntt");
 }

@@ -87,6 +87,10 @@ def oracle():
         o.orc_galois_elt_from_step.restype = ctypes.c_uint32
         o.orc_galois_elt_from_step.argtypes = [ctypes.c_int, ctypes.c_uint64]
         o.orc_apply_galois.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_uint32, u64p]
+        o.orc_apply_galois_ntt.argtypes = [vp, u64p, u64p, ctypes.c_int, u32p]
+        o.orc_apply_galois_ntt.restype = None
+        o.orc_apply_galois_coeff.argtypes = [vp, u64p, u64p, ctypes.c_int, ctypes.c_uint32]
+        o.orc_apply_galois_coeff.restype = None
         o.orc_hoisting.argtypes = [vp, ctypes.c_int, u64p, u32p, ctypes.c_int, ctypes.POINTER(u64p)]
         o.orc_rescale.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p]
         o.orc_divide_round_q_last.argtypes = [vp, ctypes.c_int, u64p, ctypes.c_int, u64p]

@@ -80,3 +80,43 @@ def test_public_key_and_plaintext_streams(scheme):
         assert np.array_equal(dec % t, host(plain)), "reference decrypts a ciphertext made under its own public key"
     finally:
         r.ref_destroy(h)
+
+
+def test_standalone_galois_permutations():
+    """pfhe_apply_galois_ntt (PhantomGaloisTool::apply_galois_ntt, src/galois.cu:86-102) and pfhe_apply_galois (coefficient
+    form, src/galois.cu:20-39) on their own, against the oracle: every key limb, several elements; in-place calls and
+    elements the context does not hold are refused."""
+    ps = H.params_small(4096, l=3, alpha=1, scheme=3)
+    parms = pf.EncryptionParameters(pf.scheme_type.ckks)
+    parms.set_poly_modulus_degree(ps.n)
+    parms.set_coeff_modulus([int(p) for p in ps.primes])
+    parms.set_special_modulus_size(ps.size_P)
+    steps = [1, -3, 0]
+    parms.set_galois_elts(pf.get_elts_from_steps(steps, ps.n))
+    ctx = pf.PhantomContext(parms)
+    o, oc = H.oracle(), ps.octx()
+    n, m = ps.n, ps.size_QP
+    st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+    x = H.uniform_limbs(ps, list(range(m)), 5)[0]
+    d_x = torch.from_numpy(x.view(np.int64)).cuda()
+    d_y = torch.zeros_like(d_x)
+    for elt in pf.get_elts_from_steps(steps, n):
+        tab = np.zeros(n, dtype=np.uint32)
+        o.orc_galois_table(n, elt, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+        want = np.zeros_like(x)
+        o.orc_apply_galois_ntt(oc, P(x), P(want), m, tab.ctypes.data_as(ctypes.POINTER(ctypes.c_uint32)))
+        pf.check(pf.lib.pfhe_apply_galois_ntt(ctx._h, d_x.data_ptr(), m, elt, d_y.data_ptr(), st))
+        assert np.array_equal(host(d_y), want), f"NTT-form automorphism, element {elt}"
+        o.orc_apply_galois_coeff(oc, P(x), P(want), m, elt)
+        pf.check(pf.lib.pfhe_apply_galois(ctx._h, d_x.data_ptr(), m, elt, d_y.data_ptr(), st))
+        assert np.array_equal(host(d_y), want), f"coefficient-form automorphism, element {elt}"
+    want = np.zeros_like(x)
+    o.orc_apply_galois_coeff(oc, P(x), P(want), 2, 3)   # any odd element in coefficient form, fewer limbs
+    pf.check(pf.lib.pfhe_apply_galois(ctx._h, d_x.data_ptr(), 2, 3, d_y.data_ptr(), st))
+    assert np.array_equal(host(d_y)[:2], want[:2])
+    with pytest.raises(ValueError):
+        pf.check(pf.lib.pfhe_apply_galois_ntt(ctx._h, d_x.data_ptr(), m, 3, d_y.data_ptr(), st))   # not a context element
+    with pytest.raises(ValueError):
+        pf.check(pf.lib.pfhe_apply_galois_ntt(ctx._h, d_x.data_ptr(), m, 5, d_x.data_ptr(), st))   # in place
+    with pytest.raises(ValueError):
+        pf.check(pf.lib.pfhe_apply_galois(ctx._h, d_x.data_ptr(), m, 4, d_y.data_ptr(), st))       # even element
