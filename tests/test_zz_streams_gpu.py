@@ -1,6 +1,7 @@
-"""GPU tests of the remaining stream formats of the host mirror: public keys (include/secretkey.h:85-96) and plaintexts
-(include/plaintext.h:69-97).  A public key written by the unmodified reference is loaded here and used to encrypt; the
-reference decrypts the result."""
+"""GPU tests of the outer layers of the host mirror: the remaining stream formats -- public keys (include/secretkey.h:85-96)
+and plaintexts (include/plaintext.h:69-97); a public key written by the unmodified reference is loaded here and used to
+encrypt, the reference decrypts the result -- the Galois permutations on their own, and scripts written against the names
+of the reference's Python binding (`import pyPhantom as phantom`, python/src/binding.cu)."""
 import ctypes
 import io
 
@@ -120,3 +121,89 @@ def test_standalone_galois_permutations():
         pf.check(pf.lib.pfhe_apply_galois_ntt(ctx._h, d_x.data_ptr(), m, 5, d_x.data_ptr(), st))   # in place
     with pytest.raises(ValueError):
         pf.check(pf.lib.pfhe_apply_galois(ctx._h, d_x.data_ptr(), m, 4, d_y.data_ptr(), st))       # even element
+
+
+def test_pyphantom_surface_ckks():
+    """A script in the shape of the reference's python/examples/ckks.py, written against `import pyPhantom as phantom`:
+    keys, encode, public-key encryption, multiply_and_relin, rescale, hoisting over seven steps, add, decrypt, decode."""
+    import pyPhantom as phantom
+    n, scale = 8192, 2.0 ** 40
+    steps = [1, 2, 3, 4, 5, 6, 7]
+    parms = phantom.params(phantom.scheme_type.ckks)
+    parms.set_poly_modulus_degree(n)
+    parms.set_coeff_modulus(phantom.create_coeff_modulus(n, [60, 40, 40, 60]))
+    parms.set_special_modulus_size(1)
+    parms.set_galois_elts(phantom.get_elts_from_steps(steps, n))
+    ctx = phantom.context(parms)
+    sk = phantom.secret_key(ctx)
+    pk, rlk, glk = sk.gen_publickey(ctx), sk.gen_relinkey(ctx), sk.create_galois_keys(ctx)
+    enc = phantom.ckks_encoder(ctx)
+    slots = enc.slot_count()
+    msg = np.zeros(slots)
+    msg[:8] = [1.0, 2.0, 3.0, 4.0, 5.0, 6.0, 7.0, 8.0]
+    pt = enc.encode_double_vector(ctx, list(msg), scale, chain_index=1)
+    ct = pk.encrypt_asymmetric(ctx, pt)
+    ct = phantom.multiply_and_relin(ctx, ct, ct, rlk)
+    ct = phantom.rescale_to_next(ctx, ct)
+    ct2 = phantom.hoisting(ctx, ct, glk, steps)
+    ct = phantom.add(ctx, ct, ct2)
+    got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, ct)))
+    sq = msg * msg
+    want = sq + sum(np.roll(sq, -k) for k in steps)
+    assert np.max(np.abs(got - want)) < 1e-3, np.max(np.abs(got - want))
+    # plaintext operands and level switching through the binding's names
+    half = enc.encode_double_vector(ctx, [0.5] * slots, scale, chain_index=1)
+    c2 = phantom.multiply_plain(ctx, pk.encrypt_asymmetric(ctx, pt), half)
+    c2 = phantom.rescale_to_next(ctx, c2)
+    got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, c2)))
+    assert np.max(np.abs(got - 0.5 * msg)) < 1e-4
+    low = phantom.mod_switch_to_next(ctx, pt)
+    assert low.chain_index() == 2 and low.data.shape[0] == 2
+    c3 = phantom.add_plain(ctx, phantom.mod_switch_to(ctx, sk.encrypt_symmetric(ctx, pt), 2), low)
+    got = np.array(enc.decode_double_vector(ctx, sk.decrypt(ctx, c3)))
+    assert np.max(np.abs(got - 2 * msg)) < 1e-4
+    with pytest.raises(ValueError):
+        phantom.add_plain(ctx, c3, pt)   # plaintext at another level
+
+
+@pytest.mark.parametrize("scheme", ["bfv", "bgv"])
+def test_pyphantom_surface_integer_schemes(scheme):
+    """The shape of python/examples/bfv.py / bgv.py: batch encoding, public-key encryption, multiply_and_relin (BFV with
+    mul_tech hps_overq_leveled), a rotation by one step, decrypt, decode."""
+    import pyPhantom as phantom
+    n = 8192
+    parms = phantom.params(getattr(phantom.scheme_type, scheme))
+    parms.set_poly_modulus_degree(n)
+    parms.set_coeff_modulus(phantom.create_coeff_modulus(n, [50, 50, 50, 50, 60, 60]))
+    parms.set_plain_modulus(phantom.create_plain_modulus(n, 20))
+    parms.set_special_modulus_size(2)
+    parms.set_galois_elts(phantom.get_elts_from_steps([1], n))
+    if scheme == "bfv":
+        parms.set_mul_tech(phantom.mul_tech_type.hps_overq_leveled)
+    ctx = phantom.context(parms)
+    t = parms.plain_modulus
+    sk = phantom.secret_key(ctx)
+    pk, rlk, glk = sk.gen_publickey(ctx), sk.gen_relinkey(ctx), sk.create_galois_keys(ctx)
+    enc = phantom.batch_encoder(ctx)
+    assert enc.slot_count() == n
+    rng = np.random.default_rng(3)
+    msg = [int(v) for v in rng.integers(0, 1000, n)]
+    pt = enc.encode(ctx, msg)
+    ct = pk.encrypt_asymmetric(ctx, pt)
+    assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, ct))] == msg
+    ct = phantom.multiply_and_relin(ctx, ct, ct, rlk)
+    sq = [v * v % t for v in msg]
+    assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, ct))] == sq
+    ct = phantom.rotate(ctx, ct, 1, glk)
+    half = n // 2
+    rot = [sq[(i + 1) % half] for i in range(half)] + [sq[half + (i + 1) % half] for i in range(half)]
+    assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, ct))] == rot
+    # linear surface
+    two = phantom.add(ctx, sk.encrypt_symmetric(ctx, pt), pk.encrypt_asymmetric(ctx, pt))
+    assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, two))] == [2 * v % t for v in msg]
+    three = phantom.add_plain(ctx, two, pt)
+    assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, three))] == [3 * v % t for v in msg]
+    prod = phantom.multiply_plain(ctx, sk.encrypt_symmetric(ctx, pt), pt)
+    assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, prod))] == sq
+    zero = phantom.sub(ctx, two, phantom.add_many(ctx, [sk.encrypt_symmetric(ctx, pt), sk.encrypt_symmetric(ctx, pt)]))
+    assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, zero))] == [0] * n
