@@ -689,6 +689,20 @@ def apply_galois_inplace(context, encrypted, galois_elt, galois_keys):
     if galois_elt not in elts:
         raise ValueError("Galois elt not present")
     key = galois_keys.get_relin_keys(elts.index(galois_elt))
+    if _leveled(context) and encrypted.chain_index == 1:
+        # keyswitch_inplace with is_relin = false under mul_tech hps_overq_leveled (eval_key_switch.cu:111-123, 141-146,
+        # 168-174): the switched polynomial is scaled down by the levels FindLevelsToDrop allows, switched there, expanded
+        drop = _levels_to_drop(context, encrypted.noise_scale_deg - 1, True, encrypted.is_asymmetric)
+        if drop:
+            l = encrypted.coeff_modulus_size()
+            moved = torch.empty_like(encrypted.data)
+            for k in range(2):
+                check(lib.pfhe_apply_galois(context._h, _ptr(encrypted.data[k]), l, galois_elt, _ptr(moved[k]), _stream()))
+            encrypted.data[0].copy_(moved[0])
+            encrypted.data[1].zero_()
+            check(lib.pfhe_keyswitch_leveled_inplace(context._h, _ptr(encrypted.data), _ptr(moved[1]), key.public_keys_ptr(),
+                                                     drop, _stream()))
+            return
     check(lib.pfhe_apply_galois_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data), galois_elt,
                                         key.public_keys_ptr(), _stream()))
 

@@ -207,3 +207,39 @@ def test_pyphantom_surface_integer_schemes(scheme):
     assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, prod))] == sq
     zero = phantom.sub(ctx, two, phantom.add_many(ctx, [sk.encrypt_symmetric(ctx, pt), sk.encrypt_symmetric(ctx, pt)]))
     assert [v % t for v in enc.decode(ctx, sk.decrypt(ctx, zero))] == [0] * n
+
+
+def test_rotate_under_leveled_mul_tech_against_reference():
+    """rotate_inplace for BFV with mul_tech hps_overq_leveled: the reference's key switch drops levels for rotations too
+    (keyswitch_inplace with is_relin = false, eval_key_switch.cu:111-174).  Same words as the unmodified reference, with the
+    reference's own Galois key."""
+    r = H.reference()
+    if r is None:
+        pytest.skip("oracle/_ref/libphantom_ref.so was not built")
+    ps = H.params_bfv_bench(0)
+    steps = (ctypes.c_int * 1)(1)
+    h = r.ref_create(2, ps.n, P(ps.primes), ps.size_QP, ps.size_P, ps.t, 4, steps, 1, 1.0, 1)
+    assert h, r.ref_last_error()
+    try:
+        n, l, m = ps.n, ps.size_Q, ps.size_QP
+        dnum = r.ref_dnum(h)
+        glk_h = np.zeros((dnum, 2, m, n), dtype=np.uint64)
+        for d in range(dnum):
+            assert r.ref_key_get(h, 0, d, P(glk_h[d])) == 0
+        parms = pf.EncryptionParameters(pf.scheme_type.bfv)
+        parms.set_poly_modulus_degree(n)
+        parms.set_coeff_modulus([int(p) for p in ps.primes])
+        parms.set_special_modulus_size(ps.size_P)
+        parms.set_plain_modulus(ps.t)
+        parms.set_mul_tech(pf.mul_tech_type.hps_overq_leveled)
+        parms.set_galois_elts(pf.get_elts_from_steps([1], n))
+        ctx = pf.PhantomContext(parms)
+        glk = pf.PhantomGaloisKey(ctx, [list(glk_h)])
+        a = H.ciphertext(ps, 21)
+        want = np.zeros((2, l, n), dtype=np.uint64)
+        assert r.ref_rotate(h, 1, P(a), 1, P(want)) == 0, r.ref_last_error()
+        c = pf.PhantomCiphertext.from_host(ctx, a, is_ntt_form=False)
+        pf.rotate_inplace(ctx, c, 1, glk)
+        assert np.array_equal(c.to_host(), want), "rotate under hps_overq_leveled vs reference"
+    finally:
+        r.ref_destroy(h)
