@@ -630,3 +630,20 @@ def test_keygen_and_encryption_semantics(scheme):
     want[0], want[1], want[n - 1] = 11, 35, 6
     got = decrypted(out).astype(np.int64) % t   # the reference's HPS rounding returns t itself for some zero coefficients
     assert np.array_equal(got, want), ("product through the generated relinearisation key", np.nonzero(got != want)[0][:8], got[got != want][:8])
+
+
+def test_samplers_known_answers():
+    """tests/golden/sampler_kat.json (see make_sampler_kat.py: oracle output that the GPU tests show equal to the reference's
+    sample_*_poly kernels): heads and SHA-256 of whole polynomials for three seeds and the three samplers."""
+    import hashlib
+    import json
+    kat = json.load(open(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "sampler_kat.json")))
+    ps = H.ParamSet("kat", kat["n"], kat["bits"], 1, 3, 0)
+    assert [int(p) for p in ps.primes] == kat["primes"]
+    o, oc, m = H.oracle(), ps.octx(), ps.size_QP
+    seeds = dict(counting=bytes(range(64)), zeros=bytes(64), ones=bytes([255] * 64))
+    for case in kat["cases"]:
+        out = np.zeros((m, kat["n"]), dtype=np.uint64)
+        assert o.orc_sample_poly(oc, case["kind"], m, seeds[case["seed"]], P(out)) == 0
+        assert [[int(v) for v in out[i, :8]] for i in range(m)] == case["head"]
+        assert hashlib.sha256(out.tobytes()).hexdigest() == case["sha256"]
