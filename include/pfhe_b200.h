@@ -56,8 +56,8 @@ int pfhe_engine_create(pfhe_engine **out, int scheme, uint64_t n, const uint64_t
                        uint64_t plain_modulus, const uint32_t *galois_elts, int n_galois);
 void pfhe_engine_destroy(pfhe_engine *e);
 /* EncryptionParameters::set_mul_tech (include/host/encryptionparams.h:25-35,57-69): 1 = behz, 2 = hps (the default
- * of a BFV engine, like the reference), 3 = hps_overq, 4 = hps_overq_leveled (accepted, but multiplication then
- * returns PFHE_ERR_INVALID_ARGUMENT "unsupported scheme": not built).  BFV engines only. */
+ * of a BFV engine, like the reference), 3 = hps_overq, 4 = hps_overq_leveled (the level-dropping forms take the number of
+ * levels from the caller: pfhe_find_levels_to_drop, pfhe_multiply_leveled, ... below).  BFV engines only. */
 int pfhe_engine_set_mul_tech(pfhe_engine *e, int mul_tech);
 uint64_t pfhe_poly_degree(const pfhe_engine *e);
 int pfhe_size_QP(const pfhe_engine *e);

@@ -616,8 +616,15 @@ def multiply_inplace(context, encrypted1, encrypted2):
     else:   # tensor_prod_mxn_rns_poly branch of bgv_ckks_multiply (evaluate.cu:382-386)
         check(lib.pfhe_multiply_sizes(context._h, encrypted1.chain_index, _ptr(a), s1, _ptr(b), s2, _ptr(dst), _stream()))
     encrypted1.data = dst
+    _after_product(context, encrypted1, encrypted2)
+
+
+def _after_product(context, encrypted1, encrypted2):
+    """bookkeeping of bgv_ckks_multiply (src/evaluate.cu:388-396): CKKS scales multiply, BGV correction factors multiply mod t"""
     if context.scheme == scheme_type.ckks:
         encrypted1.scale = encrypted1.scale * encrypted2.scale
+    elif context.scheme == scheme_type.bgv:
+        encrypted1.correction_factor = encrypted1.correction_factor * encrypted2.correction_factor % context.parms.plain_modulus
 
 
 def relinearize_inplace(context, encrypted, relin_keys):
@@ -641,6 +648,12 @@ def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
     _require_ntt(context, encrypted2)
     if encrypted1.chain_index != encrypted2.chain_index:
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+    if encrypted1.is_ntt_form != encrypted2.is_ntt_form:
+        raise ValueError("NTT form mismatch")
+    if not _are_close(encrypted1.scale, encrypted2.scale):
+        raise ValueError("scale mismatch")
+    if encrypted1.size() != encrypted2.size():
+        raise ValueError("poly number mismatch")
     dst = torch.empty_like(encrypted1.data)
     if _leveled(context):   # bfv_mul_relin_hps, leveled branch (evaluate.cu:845-856, 962-964)
         deg = max(encrypted1.noise_scale_deg, encrypted2.noise_scale_deg)
@@ -652,8 +665,7 @@ def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
         check(lib.pfhe_multiply_and_relin(context._h, encrypted1.chain_index, _ptr(encrypted1.data),
                                           _ptr(encrypted2.data), _ptr(dst), relin_keys.public_keys_ptr(), _stream()))
     encrypted1.data = dst   # like the reference's resize: the ciphertext now owns a new buffer
-    if context.scheme == scheme_type.ckks:
-        encrypted1.scale = encrypted1.scale * encrypted2.scale
+    _after_product(context, encrypted1, encrypted2)
 
 
 def multiply_and_relin_batch(context, encrypted1, encrypted2, relin_keys):
@@ -677,8 +689,7 @@ def multiply_and_relin_batch(context, encrypted1, encrypted2, relin_keys):
                                             relin_keys.public_keys_ptr(), _stream()))
     for a, b, d in zip(encrypted1, encrypted2, dst):
         a.data = d
-        if context.scheme == scheme_type.ckks:
-            a.scale = a.scale * b.scale
+        _after_product(context, a, b)
 
 
 def apply_galois_inplace(context, encrypted, galois_elt, galois_keys):

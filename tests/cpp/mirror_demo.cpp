@@ -1,0 +1,151 @@
+// An application written against the reference's class and function names (phantom.h), running on the C++ mirror
+// include/phantom_b200.hpp: key generation, encoding, public-key and symmetric encryption, multiply + relinearize (fused
+// and in two steps), rotation, addition, level switching, rescaling, decryption, decoding -- BFV (mul_tech
+// hps_overq_leveled), BGV and CKKS.  Prints OK and exits 0 when every decrypted result is the expected one.
+#include <cstdio>
+#include <string>
+#include <vector>
+
+#include "phantom_b200.hpp"
+
+using namespace phantom_b200;
+
+static int failures = 0;
+static void expect(bool ok, const std::string &what) {
+    std::printf("%s %s\n", ok ? "ok  " : "FAIL", what.c_str());
+    if (!ok) failures++;
+}
+
+static void integer_scheme(scheme_type scheme) {
+    const size_t n = 8192;
+    const std::string name = scheme == scheme_type::bfv ? "bfv" : "bgv";
+    EncryptionParameters parms(scheme);
+    parms.set_poly_modulus_degree(n);
+    parms.set_coeff_modulus(CoeffModulus::Create(n, {50, 50, 50, 50, 60, 60}));
+    parms.set_special_modulus_size(2);
+    parms.set_plain_modulus(PlainModulus::Batching(n, 20));
+    parms.set_galois_elts(get_elts_from_steps({1}, n));
+    if (scheme == scheme_type::bfv) parms.set_mul_tech(mul_tech_type::hps_overq_leveled);
+    PhantomContext context(parms);
+    const uint64_t t = parms.plain_modulus();
+
+    PhantomSecretKey secret_key(context);
+    PhantomPublicKey public_key = secret_key.gen_publickey(context);
+    PhantomRelinKey relin_keys = secret_key.gen_relinkey(context);
+    PhantomGaloisKey galois_keys = secret_key.create_galois_keys(context);
+    PhantomBatchEncoder encoder(context);
+
+    std::vector<uint64_t> msg(n), sq(n), rot(n);
+    for (size_t i = 0; i < n; i++) msg[i] = (i * 7 + 3) % 1000, sq[i] = msg[i] * msg[i] % t;
+    const size_t half = n / 2;
+    for (size_t i = 0; i < half; i++) rot[i] = sq[(i + 1) % half], rot[half + i] = sq[half + (i + 1) % half];
+
+    auto decrypted = [&](const PhantomCiphertext &ct) {
+        PhantomPlaintext pt;
+        secret_key.decrypt(context, ct, pt);
+        auto v = encoder.decode(context, pt);
+        for (auto &x : v) x %= t;
+        return v;
+    };
+
+    PhantomPlaintext plain;
+    encoder.encode(context, msg, plain);
+    PhantomCiphertext asym, sym;
+    public_key.encrypt_asymmetric(context, plain, asym);
+    secret_key.encrypt_symmetric(context, plain, sym);
+    expect(decrypted(asym) == msg, name + ": public-key encryption round trip");
+    expect(decrypted(sym) == msg, name + ": symmetric encryption round trip");
+
+    PhantomCiphertext fused = asym;
+    multiply_and_relin_inplace(context, fused, asym, relin_keys);
+    expect(fused.size() == 2 && decrypted(fused) == sq, name + ": multiply_and_relin_inplace");
+    PhantomCiphertext two_step = sym;
+    multiply_inplace(context, two_step, sym);
+    expect(two_step.size() == 3 && decrypted(two_step) == sq, name + ": multiply_inplace (three polynomials)");
+    relinearize_inplace(context, two_step, relin_keys);
+    expect(two_step.size() == 2 && decrypted(two_step) == sq, name + ": relinearize_inplace");
+
+    rotate_inplace(context, fused, 1, galois_keys);
+    expect(decrypted(fused) == rot, name + ": rotate_inplace by one step");
+
+    PhantomCiphertext sum = sym;
+    add_inplace(context, sum, asym);
+    std::vector<uint64_t> twice(n);
+    for (size_t i = 0; i < n; i++) twice[i] = 2 * msg[i] % t;
+    expect(decrypted(sum) == twice, name + ": add_inplace");
+    add_plain_inplace(context, sum, plain);
+    sub_inplace(context, sum, asym);
+    expect(decrypted(sum) == twice, name + ": add_plain_inplace, sub_inplace");
+    multiply_plain_inplace(context, sym, plain);
+    expect(decrypted(sym) == sq, name + ": multiply_plain_inplace");
+    PhantomCiphertext lower = mod_switch_to_next(context, two_step);
+    expect(lower.chain_index() == 2 && lower.coeff_modulus_size() == 3 && decrypted(lower) == sq, name + ": mod_switch_to_next");
+    bool threw = false;
+    try {
+        add_inplace(context, lower, two_step);
+    } catch (const std::invalid_argument &) { threw = true; }
+    expect(threw, name + ": level mismatch is refused");
+}
+
+static void ckks() {
+    const size_t n = 8192;
+    const double scale = 1099511627776.0;   // 2^40
+    EncryptionParameters parms(scheme_type::ckks);
+    parms.set_poly_modulus_degree(n);
+    parms.set_coeff_modulus(CoeffModulus::Create(n, {60, 40, 40, 60}));
+    parms.set_special_modulus_size(1);
+    parms.set_galois_elts(get_elts_from_steps({1, 2}, n));
+    PhantomContext context(parms);
+    PhantomSecretKey secret_key(context);
+    PhantomPublicKey public_key = secret_key.gen_publickey(context);
+    PhantomRelinKey relin_keys = secret_key.gen_relinkey(context);
+    PhantomGaloisKey galois_keys = secret_key.create_galois_keys(context);
+    PhantomCKKSEncoder encoder(context);
+    const size_t slots = encoder.slot_count();
+    std::vector<double> msg(slots);
+    for (size_t i = 0; i < slots; i++) msg[i] = 0.001 * (double) (i % 1000) - 0.3;
+
+    auto max_error = [&](const PhantomCiphertext &ct, const std::vector<double> &want) {
+        PhantomPlaintext pt;
+        secret_key.decrypt(context, ct, pt);
+        std::vector<double> got;
+        encoder.decode(context, pt, got);
+        double worst = 0;
+        for (size_t i = 0; i < slots; i++) worst = std::max(worst, std::fabs(got[i] - want[i]));
+        return worst;
+    };
+
+    PhantomPlaintext plain;
+    encoder.encode(context, msg, scale, plain);
+    PhantomCiphertext ct;
+    public_key.encrypt_asymmetric(context, plain, ct);
+    expect(max_error(ct, msg) < 1e-6, "ckks: encode, encrypt, decrypt, decode");
+    PhantomCiphertext prod = ct;
+    multiply_and_relin_inplace(context, prod, ct, relin_keys);
+    PhantomCiphertext rescaled = rescale_to_next(context, prod);
+    std::vector<double> sq(slots), rot(slots);
+    for (size_t i = 0; i < slots; i++) sq[i] = msg[i] * msg[i];
+    for (size_t i = 0; i < slots; i++) rot[i] = sq[(i + 2) % slots];
+    expect(rescaled.chain_index() == 2 && max_error(rescaled, sq) < 1e-5, "ckks: multiply_and_relin_inplace, rescale_to_next");
+    rotate_inplace(context, rescaled, 2, galois_keys);
+    expect(max_error(rescaled, rot) < 1e-5, "ckks: rotate_inplace by two steps");
+    PhantomCiphertext sym;
+    secret_key.encrypt_symmetric(context, plain, sym);
+    add_inplace(context, sym, ct);
+    std::vector<double> twice(slots);
+    for (size_t i = 0; i < slots; i++) twice[i] = 2 * msg[i];
+    expect(max_error(sym, twice) < 1e-6, "ckks: encrypt_symmetric, add_inplace");
+}
+
+int main() {
+    try {
+        integer_scheme(scheme_type::bfv);
+        integer_scheme(scheme_type::bgv);
+        ckks();
+    } catch (const std::exception &e) {
+        std::printf("FAIL exception: %s\n", e.what());
+        return 2;
+    }
+    std::printf(failures ? "FAILED %d\n" : "OK\n", failures);
+    return failures ? 1 : 0;
+}

@@ -96,3 +96,21 @@ def test_header_is_plain_c_and_links_from_c(tmp_path):
     import torch
     if not torch.cuda.is_available():
         assert int(lines[2]) == 3   # PFHE_ERR_CUDA
+
+
+def test_cpp_mirror_header_compiles():
+    """include/phantom_b200.hpp (the reference's C++ class and function names over the C-ABI) and the demo application
+    written against it compile as C++17 with warnings as errors; without a device the application fails loudly."""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no C++ compiler or CUDA headers")
+    subprocess.check_call([gxx, "-std=c++17", "-Wall", "-Wextra", "-Werror", "-fsyntax-only", "-I", os.path.join(ROOT, "include"),
+                           "-I", cuda_inc, os.path.join(ROOT, "tests", "cpp", "mirror_demo.cpp")])
+    exe = os.path.join(ROOT, "tests", "cpp", "mirror_demo")
+    import torch
+    if os.path.exists(exe) and not torch.cuda.is_available():
+        out = subprocess.run([exe], capture_output=True, text=True, timeout=120)
+        assert out.returncode == 2 and "no CPU path" in out.stdout

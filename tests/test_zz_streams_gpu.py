@@ -243,3 +243,23 @@ def test_rotate_under_leveled_mul_tech_against_reference():
         assert np.array_equal(c.to_host(), want), "rotate under hps_overq_leveled vs reference"
     finally:
         r.ref_destroy(h)
+
+
+def test_cpp_mirror_application():
+    """tests/cpp/mirror_demo.cpp: an application written against the reference's C++ names (PhantomContext,
+    PhantomSecretKey, multiply_and_relin_inplace, rotate_inplace, rescale_to_next, ...) on include/phantom_b200.hpp --
+    BFV (hps_overq_leveled), BGV and CKKS flows; every decrypted result must be the expected one."""
+    import os
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "tests", "cpp", "mirror_demo")
+    if not os.path.exists(exe):
+        if shutil.which("nvcc") is None:
+            pytest.skip("mirror_demo was not built and there is no nvcc")
+        lib_dir = os.path.join(root, "phantom-fhe_b200")
+        subprocess.check_call(["nvcc", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
+                               os.path.join(root, "tests", "cpp", "mirror_demo.cpp"), "-o", exe, "-L", lib_dir, "-lpfhe_b200",
+                               "-Xlinker", "-rpath", "-Xlinker", lib_dir, "-Wno-deprecated-gpu-targets"])
+    out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
