@@ -595,10 +595,14 @@ def multiply_inplace(context, encrypted1, encrypted2):
     """multiply_inplace (src/evaluate.cu:1029-1057 -> bgv_ckks_multiply :345-397, bfv_multiply_behz :451-548)."""
     _require_ntt(context, encrypted1)
     _require_ntt(context, encrypted2)
-    if encrypted1.chain_index != encrypted2.chain_index:
+    if encrypted1.chain_index != encrypted2.chain_index:   # the reference's checks, in its order (evaluate.cu:1033-1040)
         raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+    if encrypted1.is_ntt_form != encrypted2.is_ntt_form:
+        raise ValueError("NTT form mismatch")
+    if not _are_close(encrypted1.scale, encrypted2.scale):
+        raise ValueError("scale mismatch")
     if encrypted1.size() != encrypted2.size():
-        raise ValueError("poly number mismatch")   # evaluate.cu:1039-1040
+        raise ValueError("poly number mismatch")
     l, n = encrypted1.coeff_modulus_size(), context.poly_degree
     s1, s2 = encrypted1.size(), encrypted2.size()
     dst = torch.empty((s1 + s2 - 1, l, n), dtype=torch.int64, device=encrypted1.data.device)
