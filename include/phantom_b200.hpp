@@ -607,7 +607,8 @@ inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &enc
 inline PhantomCiphertext rescale_to_next(const PhantomContext &context, const PhantomCiphertext &encrypted) {
     if (context.parms().scheme() != scheme_type::ckks) throw std::invalid_argument("unsupported scheme");
     if (encrypted.chain_index() == context.size_Q()) throw std::invalid_argument("end of modulus switching chain reached");
-    PhantomCiphertext dst = encrypted.attributes_only();
+    PhantomCiphertext dst;   // a fresh object, like the reference's `destination`: only scale and form are set below
+    dst.set_ntt_form(encrypted.is_ntt_form());
     dst.resize(context, encrypted.chain_index() + 1, encrypted.size());
     rethrow(pfhe_rescale_to_next(context.engine(), encrypted.chain_index(), encrypted.data(), encrypted.size(), dst.data(), context.stream()));
     dst.set_scale(encrypted.scale() / (double) context.parms().coeff_modulus()[encrypted.coeff_modulus_size() - 1]);
@@ -617,7 +618,9 @@ inline PhantomCiphertext rescale_to_next(const PhantomContext &context, const Ph
 inline PhantomCiphertext mod_switch_to_next(const PhantomContext &context, const PhantomCiphertext &encrypted) {
     if (encrypted.chain_index() == context.size_Q()) throw std::invalid_argument("end of modulus switching chain reached");
     detail::require_form(context, encrypted);
-    PhantomCiphertext dst = encrypted.attributes_only();
+    PhantomCiphertext dst;   // fresh: noiseScaleDeg and is_asymmetric restart at their defaults (evaluate.cu:1527-1541)
+    dst.set_ntt_form(encrypted.is_ntt_form());
+    dst.set_scale(encrypted.scale());
     dst.resize(context, encrypted.chain_index() + 1, encrypted.size());
     rethrow(pfhe_mod_switch_to_next(context.engine(), encrypted.chain_index(), encrypted.data(), encrypted.size(), dst.data(), context.stream()));
     if (context.parms().scheme() == scheme_type::bgv) {   // correction factor times q_last^-1 mod t (evaluate.cu:1420-1425)

@@ -820,7 +820,7 @@ def mod_switch_to_next(context, encrypted):
     check(lib.pfhe_mod_switch_to_next(context._h, encrypted.chain_index, _ptr(encrypted.data), size, _ptr(dst),
                                       _stream()))
     out = PhantomCiphertext(None, dst, encrypted.chain_index + 1, encrypted.scale, encrypted.is_ntt_form)
-    out.noise_scale_deg, out.is_asymmetric = encrypted.noise_scale_deg, encrypted.is_asymmetric
+    # (the reference builds the result in a fresh PhantomCiphertext: noiseScaleDeg_ and is_asymmetric_ restart at their defaults)
     if context.scheme == scheme_type.bgv:   # correction factor times q_last^-1 mod t (evaluate.cu:1420-1425)
         t = context.parms.plain_modulus
         q_last = context.parms.coeff_modulus[l - 1]
