@@ -261,5 +261,7 @@ def test_cpp_mirror_application():
         subprocess.check_call(["nvcc", "-std=c++17", "-O2", "-I", os.path.join(root, "include"),
                                os.path.join(root, "tests", "cpp", "mirror_demo.cpp"), "-o", exe, "-L", lib_dir, "-lpfhe_b200",
                                "-Xlinker", "-rpath", "-Xlinker", lib_dir, "-Wno-deprecated-gpu-targets"])
+    if not os.access(exe, os.X_OK):
+        os.chmod(exe, 0o755)
     out = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
