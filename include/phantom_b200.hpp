@@ -484,26 +484,80 @@ inline void check_pair(const PhantomCiphertext &a, const PhantomCiphertext &b) {
     if (a.size() != b.size()) throw std::invalid_argument("poly number mismatch");
 }
 }   // namespace detail
-// add_inplace / sub_inplace (evaluate.cu:115-338).  BGV operands with different correction factors are refused here: the
-// balancing of the factors (balance_correction_factors) lives in the Python mirror only
+namespace detail {
+// balance_correction_factors (evaluate.cu:14-72): (f, e1, e2) with e1 * factor1 = e2 * factor2 = f mod t, e1 and e2
+// invertible, |e1| + |e2| minimal over the remainders of the extended Euclidean algorithm on (t, factor2 / factor1)
+struct Balanced {
+    uint64_t f, e1, e2;
+};
+inline Balanced balance_correction_factors(uint64_t factor1, uint64_t factor2, uint64_t t) {
+    using i128 = __int128;
+    auto gcd = [](uint64_t a, uint64_t b) {
+        while (b) {
+            const uint64_t r = a % b;
+            a = b, b = r;
+        }
+        return a;
+    };
+    auto mag = [&](uint64_t x) { return (i128) (x > t / 2 ? t - x : x); };
+    uint64_t inv1;
+    {   // factor1^-1 mod t
+        i128 r0 = t, r1 = factor1 % t, s0 = 0, s1 = 1;
+        while (r1) {
+            const i128 k = r0 / r1, r2 = r0 - k * r1, s2 = s0 - k * s1;
+            r0 = r1, r1 = r2, s0 = s1, s1 = s2;
+        }
+        if (r0 != 1) throw std::logic_error("invalid correction factor1");
+        inv1 = (uint64_t) (s0 < 0 ? s0 + (i128) t : s0);
+    }
+    const uint64_t ratio = (uint64_t) ((unsigned __int128) inv1 * (factor2 % t) % t);
+    uint64_t e1 = ratio, e2 = 1;
+    i128 best = mag(e1) + mag(e2);
+    i128 prev_a = t, prev_b = 0, a = ratio, b = 1;
+    while (a != 0) {
+        const i128 q = prev_a / a, rem = prev_a % a;
+        prev_a = a, a = rem;
+        const i128 nb = prev_b - b * q;
+        prev_b = b, b = nb;
+        const uint64_t a_mod = (uint64_t) (((a % (i128) t) + (i128) t) % (i128) t), b_mod = (uint64_t) (((b % (i128) t) + (i128) t) % (i128) t);
+        if (a_mod != 0 && gcd(a_mod, t) == 1) {
+            const i128 cand = mag(a_mod) + mag(b_mod);
+            if (cand < best) best = cand, e1 = a_mod, e2 = b_mod;
+        }
+    }
+    return Balanced{(uint64_t) ((unsigned __int128) e1 * (factor1 % t) % t), e1, e2};
+}
+// add_inplace / sub_inplace (evaluate.cu:115-338): BGV operands with different correction factors are scaled to a common
+// one first (multiply_scalar_rns_poly, :148-165)
+inline void add_sub(const PhantomContext &context, PhantomCiphertext &encrypted1, const PhantomCiphertext &encrypted2, bool sub, bool negate) {
+    check_pair(encrypted1, encrypted2);
+    const size_t l = encrypted1.coeff_modulus_size(), words = l * encrypted1.poly_modulus_degree();
+    const uint64_t *other = encrypted2.data();
+    DeviceWords scaled;
+    if (encrypted1.correction_factor() != encrypted2.correction_factor()) {
+        const Balanced bal = balance_correction_factors(encrypted1.correction_factor(), encrypted2.correction_factor(),
+                                                        context.parms().plain_modulus());
+        scaled.resize(encrypted2.size() * words);
+        cuda_check(cudaMemcpyAsync(scaled.get(), encrypted2.data(), encrypted2.size() * words * 8, cudaMemcpyDeviceToDevice, context.stream()));
+        rethrow(pfhe_multiply_scalar_rns_poly(context.engine(), encrypted1.data(), encrypted1.size(), bal.e1, l, context.stream()));
+        rethrow(pfhe_multiply_scalar_rns_poly(context.engine(), scaled.get(), encrypted2.size(), bal.e2, l, context.stream()));
+        encrypted1.set_correction_factor(bal.f);
+        other = scaled.get();
+    }
+    for (size_t k = 0; k < encrypted1.size(); k++) {
+        const uint64_t *a = encrypted1.data() + k * words, *b = other + k * words;
+        if (sub) rethrow(pfhe_sub_rns_poly(context.engine(), negate ? b : a, negate ? a : b, encrypted1.data() + k * words, l, context.stream()));
+        else rethrow(pfhe_add_rns_poly(context.engine(), a, b, encrypted1.data() + k * words, l, context.stream()));
+    }
+    if (scaled.size()) cuda_check(cudaStreamSynchronize(context.stream()));   // the scaled copy is freed on return
+}
+}   // namespace detail
 inline void add_inplace(const PhantomContext &context, PhantomCiphertext &encrypted1, const PhantomCiphertext &encrypted2) {
-    detail::check_pair(encrypted1, encrypted2);
-    if (encrypted1.correction_factor() != encrypted2.correction_factor()) throw std::logic_error("correction factors differ");
-    const size_t words = encrypted1.coeff_modulus_size() * encrypted1.poly_modulus_degree();
-    for (size_t k = 0; k < encrypted1.size(); k++)
-        rethrow(pfhe_add_rns_poly(context.engine(), encrypted1.data() + k * words, encrypted2.data() + k * words,
-                                  encrypted1.data() + k * words, encrypted1.coeff_modulus_size(), context.stream()));
+    detail::add_sub(context, encrypted1, encrypted2, false, false);
 }
 inline void sub_inplace(const PhantomContext &context, PhantomCiphertext &encrypted1, const PhantomCiphertext &encrypted2,
                         bool negate = false) {
-    detail::check_pair(encrypted1, encrypted2);
-    if (encrypted1.correction_factor() != encrypted2.correction_factor()) throw std::logic_error("correction factors differ");
-    const size_t words = encrypted1.coeff_modulus_size() * encrypted1.poly_modulus_degree();
-    for (size_t k = 0; k < encrypted1.size(); k++) {
-        const uint64_t *a = encrypted1.data() + k * words, *b = encrypted2.data() + k * words;
-        rethrow(pfhe_sub_rns_poly(context.engine(), negate ? b : a, negate ? a : b, encrypted1.data() + k * words,
-                                  encrypted1.coeff_modulus_size(), context.stream()));
-    }
+    detail::add_sub(context, encrypted1, encrypted2, true, negate);
 }
 inline void add_plain_inplace(const PhantomContext &context, PhantomCiphertext &encrypted, const PhantomPlaintext &plain) {   // :1106-1164
     detail::require_form(context, encrypted);
@@ -590,18 +644,40 @@ inline void multiply_and_relin_inplace(const PhantomContext &context, PhantomCip
     cuda_check(cudaStreamSynchronize(context.stream()));
     encrypted1 = std::move(dst);
 }
-// rotate_inplace (evaluate.cu:1633-1668) for a step whose Galois element the context holds (the reference additionally
-// composes missing steps out of powers of two: that recursion is in the Python mirror)
-inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &encrypted, int step, const PhantomGaloisKey &galois_key) {
+// apply_galois_inplace (evaluate.cu:1567-1630)
+inline void apply_galois_inplace(const PhantomContext &context, PhantomCiphertext &encrypted, uint32_t galois_elt,
+                                 const PhantomGaloisKey &galois_keys) {
     if (encrypted.size() > 2) throw std::invalid_argument("encrypted size must be 2");
-    if (step == 0) return;
     const auto &elts = context.parms().galois_elts();
-    const uint32_t elt = get_elt_from_step(step, context.poly_degree());
-    size_t idx = 0;
-    while (idx < elts.size() && elts[idx] != elt) idx++;
-    if (idx == elts.size()) throw std::invalid_argument("Galois key not present");
-    rethrow(pfhe_apply_galois_inplace(context.engine(), encrypted.chain_index(), encrypted.data(), elt,
-                                      galois_key.get_relin_keys(idx).public_keys_ptr(), context.stream()));
+    const auto it = std::find(elts.begin(), elts.end(), galois_elt);
+    if (it == elts.end()) throw std::invalid_argument("Galois elt not present");
+    rethrow(pfhe_apply_galois_inplace(context.engine(), encrypted.chain_index(), encrypted.data(), galois_elt,
+                                      galois_keys.get_relin_keys((size_t) (it - elts.begin())).public_keys_ptr(), context.stream()));
+}
+// rotate_inplace / rotate_internal (evaluate.cu:1633-1668): a step whose element the context holds is one automorphism;
+// any other step is composed from the powers of two of its non-adjacent form (include/host/numth.h:17-34)
+inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &encrypted, int step, const PhantomGaloisKey &galois_key) {
+    const size_t n = context.poly_degree();
+    const uint32_t elt = get_elt_from_step(step, n);
+    const auto &elts = context.parms().galois_elts();
+    if (std::find(elts.begin(), elts.end(), elt) != elts.end()) {
+        apply_galois_inplace(context, encrypted, elt, galois_key);
+        return;
+    }
+    std::vector<int> naf;
+    {
+        const bool negative = step < 0;
+        unsigned long long value = (unsigned long long) (negative ? -(long long) step : (long long) step);
+        for (int i = 0; value; i++) {
+            int zi = 0;
+            if (value & 1) zi = 2 - (int) (value & 3);
+            value = (value - zi) >> 1;
+            if (zi) naf.push_back((negative ? -1 : 1) * zi * (1 << i));
+        }
+    }
+    if (naf.size() == 1) throw std::invalid_argument("Galois key not present");
+    for (int s : naf)
+        if ((size_t) std::abs(s) != (n >> 1)) rotate_inplace(context, encrypted, s, galois_key);
 }
 // rescale_to_next (evaluate.cu:1545-1565)
 inline PhantomCiphertext rescale_to_next(const PhantomContext &context, const PhantomCiphertext &encrypted) {

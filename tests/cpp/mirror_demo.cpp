@@ -94,7 +94,7 @@ static void ckks() {
     parms.set_poly_modulus_degree(n);
     parms.set_coeff_modulus(CoeffModulus::Create(n, {60, 40, 40, 60}));
     parms.set_special_modulus_size(1);
-    parms.set_galois_elts(get_elts_from_steps({1, 2}, n));
+    parms.set_galois_elts(get_elts_from_steps({1, 2, 4, -1}, n));
     PhantomContext context(parms);
     PhantomSecretKey secret_key(context);
     PhantomPublicKey public_key = secret_key.gen_publickey(context);
@@ -127,6 +127,11 @@ static void ckks() {
     for (size_t i = 0; i < slots; i++) sq[i] = msg[i] * msg[i];
     for (size_t i = 0; i < slots; i++) rot[i] = sq[(i + 2) % slots];
     expect(rescaled.chain_index() == 2 && max_error(rescaled, sq) < 1e-5, "ckks: multiply_and_relin_inplace, rescale_to_next");
+    PhantomCiphertext by_three = rescaled;   // no key for step 3: composed from its non-adjacent form, -1 then +4
+    rotate_inplace(context, by_three, 3, galois_keys);
+    std::vector<double> rot3(slots);
+    for (size_t i = 0; i < slots; i++) rot3[i] = sq[(i + 3) % slots];
+    expect(max_error(by_three, rot3) < 1e-5, "ckks: rotate_inplace by three steps through the NAF recursion");
     rotate_inplace(context, rescaled, 2, galois_keys);
     expect(max_error(rescaled, rot) < 1e-5, "ckks: rotate_inplace by two steps");
     PhantomCiphertext sym;

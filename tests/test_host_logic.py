@@ -193,3 +193,41 @@ def test_plaintext_and_public_key_streams():
     serial.write_ciphertext(one, pk, 1)
     with pytest.raises(ValueError):
         serial.read_public_key(io.BytesIO(one.getvalue()))
+
+
+def test_cpp_mirror_balances_like_the_python_mirror(tmp_path):
+    """include/phantom_b200.hpp's balance_correction_factors against the Python mirror's (both restate
+    src/evaluate.cu:14-72) on a few hundred factor pairs, several plain moduli."""
+    import math
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no C++ compiler or CUDA headers")
+    src = tmp_path / "bal.cpp"
+    src.write_text(
+        '#include <cstdio>\n#include <cstdlib>\n#include "phantom_b200.hpp"\n'
+        "int main(int argc, char **argv) {\n"
+        "    for (int i = 1; i + 2 < argc; i += 3) {\n"
+        "        auto b = phantom_b200::detail::balance_correction_factors(strtoull(argv[i], 0, 10), strtoull(argv[i + 1], 0, 10),\n"
+        "                                                                  strtoull(argv[i + 2], 0, 10));\n"
+        '        std::printf("%llu %llu %llu\\n", (unsigned long long) b.f, (unsigned long long) b.e1, (unsigned long long) b.e2);\n'
+        "    }\n    return 0;\n}\n")
+    exe = tmp_path / "bal"
+    subprocess.check_call([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, str(src), "-o", str(exe)])
+    api_src = open(os.path.join(ROOT, "phantom-fhe_b200", "api.py")).read()
+    ns = {"math": math}
+    exec(api_src[api_src.index("def balance_correction_factors"):api_src.index("def _check_pair")], ns)
+    rng = np.random.default_rng(5)
+    cases = []
+    for t in (65537, 1032193, 786433, (1 << 20) + 7):
+        for _ in range(60):
+            f1, f2 = int(rng.integers(1, t)), int(rng.integers(1, t))
+            if math.gcd(f1, t) == 1:
+                cases.append((f1, f2, t))
+    args = [str(v) for c in cases for v in c]
+    out = subprocess.run([str(exe)] + args, capture_output=True, text=True, timeout=120)
+    assert out.returncode == 0, out.stderr
+    got = [tuple(int(v) for v in line.split()) for line in out.stdout.strip().splitlines()]
+    assert got == [ns["balance_correction_factors"](*c) for c in cases]
