@@ -644,6 +644,21 @@ inline void multiply_and_relin_inplace(const PhantomContext &context, PhantomCip
     cuda_check(cudaStreamSynchronize(context.stream()));
     encrypted1 = std::move(dst);
 }
+namespace detail {
+// non-adjacent form of a step as signed powers of two, lowest first (naf, include/host/numth.h:17-34)
+inline std::vector<int> naf(int step) {
+    std::vector<int> out;
+    const bool negative = step < 0;
+    long long value = negative ? -(long long) step : (long long) step;
+    for (int i = 0; value; i++) {
+        int zi = 0;
+        if (value & 1) zi = 2 - (int) (value & 3);
+        value = (value - zi) >> 1;
+        if (zi) out.push_back((negative ? -1 : 1) * zi * (1 << i));
+    }
+    return out;
+}
+}   // namespace detail
 // apply_galois_inplace (evaluate.cu:1567-1630)
 inline void apply_galois_inplace(const PhantomContext &context, PhantomCiphertext &encrypted, uint32_t galois_elt,
                                  const PhantomGaloisKey &galois_keys) {
@@ -664,17 +679,7 @@ inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &enc
         apply_galois_inplace(context, encrypted, elt, galois_key);
         return;
     }
-    std::vector<int> naf;
-    {
-        const bool negative = step < 0;
-        unsigned long long value = (unsigned long long) (negative ? -(long long) step : (long long) step);
-        for (int i = 0; value; i++) {
-            int zi = 0;
-            if (value & 1) zi = 2 - (int) (value & 3);
-            value = (value - zi) >> 1;
-            if (zi) naf.push_back((negative ? -1 : 1) * zi * (1 << i));
-        }
-    }
+    const std::vector<int> naf = detail::naf(step);
     if (naf.size() == 1) throw std::invalid_argument("Galois key not present");
     for (int s : naf)
         if ((size_t) std::abs(s) != (n >> 1)) rotate_inplace(context, encrypted, s, galois_key);

@@ -197,7 +197,8 @@ def test_plaintext_and_public_key_streams():
 
 def test_cpp_mirror_balances_like_the_python_mirror(tmp_path):
     """include/phantom_b200.hpp's balance_correction_factors against the Python mirror's (both restate
-    src/evaluate.cu:14-72) on a few hundred factor pairs, several plain moduli."""
+    src/evaluate.cu:14-72) on a few hundred factor pairs, several plain moduli; and its non-adjacent form of rotation steps
+    against the Python mirror's."""
     import math
     import shutil
     import subprocess
@@ -213,6 +214,11 @@ def test_cpp_mirror_balances_like_the_python_mirror(tmp_path):
         "        auto b = phantom_b200::detail::balance_correction_factors(strtoull(argv[i], 0, 10), strtoull(argv[i + 1], 0, 10),\n"
         "                                                                  strtoull(argv[i + 2], 0, 10));\n"
         '        std::printf("%llu %llu %llu\\n", (unsigned long long) b.f, (unsigned long long) b.e1, (unsigned long long) b.e2);\n'
+        "    }\n"
+        "    for (int step = -70; step <= 70; step++) {\n"
+        '        std::printf("naf %d:", step);\n'
+        '        for (int p : phantom_b200::detail::naf(step)) std::printf(" %d", p);\n'
+        '        std::printf("\\n");\n'
         "    }\n    return 0;\n}\n")
     exe = tmp_path / "bal"
     subprocess.check_call([gxx, "-std=c++17", "-O1", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc, str(src), "-o", str(exe)])
@@ -229,5 +235,9 @@ def test_cpp_mirror_balances_like_the_python_mirror(tmp_path):
     args = [str(v) for c in cases for v in c]
     out = subprocess.run([str(exe)] + args, capture_output=True, text=True, timeout=120)
     assert out.returncode == 0, out.stderr
-    got = [tuple(int(v) for v in line.split()) for line in out.stdout.strip().splitlines()]
+    lines = out.stdout.strip().splitlines()
+    got = [tuple(int(v) for v in line.split()) for line in lines if not line.startswith("naf")]
     assert got == [ns["balance_correction_factors"](*c) for c in cases]
+    exec(api_src[api_src.index("def _naf"):api_src.index("def rotate_inplace")], ns)
+    nafs = {int(line.split(":")[0].split()[1]): [int(v) for v in line.split(":")[1].split()] for line in lines if line.startswith("naf")}
+    assert len(nafs) == 141 and all(nafs[step] == ns["_naf"](step) for step in range(-70, 71))
