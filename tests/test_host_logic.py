@@ -241,3 +241,30 @@ def test_cpp_mirror_balances_like_the_python_mirror(tmp_path):
     exec(api_src[api_src.index("def _naf"):api_src.index("def rotate_inplace")], ns)
     nafs = {int(line.split(":")[0].split()[1]): [int(v) for v in line.split(":")[1].split()] for line in lines if line.startswith("naf")}
     assert len(nafs) == 141 and all(nafs[step] == ns["_naf"](step) for step in range(-70, 71))
+
+
+def test_pyphantom_module_has_the_binding_surface():
+    """`import pyPhantom` offers every class, enum and function name the reference's pybind module defines
+    (python/src/binding.cu:13-166) and the methods the binding attaches to them."""
+    import pyPhantom as phantom
+    for name in ("scheme_type", "mul_tech_type", "sec_level_type", "modulus", "create_coeff_modulus", "create_plain_modulus",
+                 "params", "cuda_stream", "context", "secret_key", "public_key", "relin_key", "galois_key", "get_elt_from_step",
+                 "get_elts_from_steps", "batch_encoder", "ckks_encoder", "plaintext", "ciphertext", "negate", "add", "add_plain",
+                 "add_many", "sub", "sub_plain", "multiply", "multiply_and_relin", "multiply_plain", "relinearize",
+                 "rescale_to_next", "mod_switch_to_next", "mod_switch_to", "apply_galois", "rotate", "hoisting"):
+        assert hasattr(phantom, name), name
+    for cls, methods in ((phantom.params, ("set_mul_tech", "set_poly_modulus_degree", "set_special_modulus_size", "set_galois_elts",
+                                           "set_coeff_modulus", "set_plain_modulus")),
+                         (phantom.secret_key, ("gen_publickey", "gen_relinkey", "create_galois_keys", "encrypt_symmetric", "decrypt")),
+                         (phantom.public_key, ("encrypt_asymmetric",)),
+                         (phantom.batch_encoder, ("slot_count", "encode", "decode")),
+                         (phantom.ckks_encoder, ("slot_count", "encode_complex_vector", "encode_double_vector",
+                                                 "decode_complex_vector", "decode_double_vector")),
+                         (phantom.ciphertext, ("set_scale",))):
+        for m in methods:
+            assert callable(getattr(cls, m, None)), f"{cls.__name__}.{m}"
+    assert [int(v) for v in (phantom.scheme_type.bgv, phantom.scheme_type.bfv, phantom.scheme_type.ckks)] == [1, 2, 3]
+    assert int(phantom.mul_tech_type.hps_overq_leveled) == 4
+    assert phantom.create_plain_modulus(8192, 20) % 16384 == 1
+    p = phantom.plaintext()
+    assert p.chain_index() == 0 and p.scale() == 1.0 and phantom.ciphertext().size() == 0
