@@ -268,3 +268,133 @@ def test_pyphantom_module_has_the_binding_surface():
     assert phantom.create_plain_modulus(8192, 20) % 16384 == 1
     p = phantom.plaintext()
     assert p.chain_index() == 0 and p.scale() == 1.0 and phantom.ciphertext().size() == 0
+
+
+class _StubLib:
+    """stands in for libpfhe_b200 in host-logic tests: every entry point succeeds and records its name"""
+
+    def __init__(self):
+        self.calls = []
+
+    def __getattr__(self, name):
+        def call(*args):
+            self.calls.append(name)
+            if name == "pfhe_find_levels_to_drop":
+                args[-1]._obj.value = 1
+            return 0
+        return call
+
+
+def test_evaluator_bookkeeping_with_a_stub_library(monkeypatch):
+    """The host side of the mirror's evaluator without a device: which C-ABI entry point each call reaches, and the
+    bookkeeping the reference does around them -- CKKS scales multiply, BGV correction factors multiply (products) or are
+    balanced (sums) or pick up q_last^-1 (mod switch), hps_overq_leveled raises the noise degree, the reference's operand
+    checks fire with its messages (src/evaluate.cu:115-197, 345-397, 1029-1104, 1376-1427, 1505-1543)."""
+    import torch
+    import phantom_fhe_b200.api as api
+    stub = _StubLib()
+    monkeypatch.setattr(api, "lib", stub)
+    monkeypatch.setattr(api, "_stream", lambda: None)
+
+    class Ctx:
+        def __init__(self, scheme, mul_tech=api.mul_tech_type.hps, t=65537):
+            self.scheme, self._h, self.poly_degree, self.size_Q, self.size_QP, self.size_P = scheme, None, 8, 3, 4, 1
+            self.parms = types.SimpleNamespace(mul_tech=mul_tech, plain_modulus=t, coeff_modulus=[97, 193, 257, 769], galois_elts=[])
+            self.device = torch.device("cpu")
+
+        def coeff_modulus_size(self, chain_index):
+            return self.size_Q - (chain_index - 1)
+
+    import types
+
+    def ct(ctx, size=2, chain_index=1, scale=1.0, cf=1):
+        c = api.PhantomCiphertext(None, torch.zeros((size, ctx.coeff_modulus_size(chain_index), 8), dtype=torch.int64), chain_index,
+                                  scale, ctx.scheme != api.scheme_type.bfv)
+        c.correction_factor = cf
+        return c
+
+    ckks = Ctx(api.scheme_type.ckks)
+    a, b = ct(ckks, scale=2.0 ** 20), ct(ckks, scale=2.0 ** 20)
+    api.multiply_inplace(ckks, a, b)
+    assert stub.calls[-1] == "pfhe_multiply" and a.size() == 3 and a.scale == 2.0 ** 40
+    api.relinearize_inplace(ckks, a, types.SimpleNamespace(public_keys_ptr=lambda: None))
+    assert stub.calls[-1] == "pfhe_relinearize_inplace" and a.size() == 2
+    with pytest.raises(ValueError, match="scale mismatch"):
+        api.multiply_inplace(ckks, a, b)
+    with pytest.raises(ValueError, match="parameter mismatch"):
+        api.multiply_and_relin_inplace(ckks, ct(ckks), ct(ckks, chain_index=2), None)
+    nxt = api.rescale_to_next(ckks, b)
+    assert nxt.chain_index == 2 and nxt.scale == 2.0 ** 20 / 257 and nxt.coeff_modulus_size() == 2
+
+    bgv = Ctx(api.scheme_type.bgv)
+    a, b = ct(bgv, cf=3), ct(bgv, cf=5)
+    api.multiply_and_relin_inplace(bgv, a, b, types.SimpleNamespace(public_keys_ptr=lambda: None))
+    assert stub.calls[-1] == "pfhe_multiply_and_relin" and a.correction_factor == 15
+    low = api.mod_switch_to_next(bgv, a)
+    assert low.chain_index == 2 and low.correction_factor == 15 * pow(257, -1, 65537) % 65537
+    a, b = ct(bgv, cf=3), ct(bgv, cf=5)
+    api.add_inplace(bgv, a, b)
+    assert stub.calls.count("pfhe_multiply_scalar_rns_poly") == 2 and a.correction_factor == api.balance_correction_factors(3, 5, 65537)[0]
+    assert b.correction_factor == 5
+    api.sub_inplace(bgv, a, ct(bgv, cf=a.correction_factor), negate=True)
+    assert stub.calls[-1] == "pfhe_sub_rns_poly"
+    api.add_plain_inplace(bgv, a, torch.zeros(8, dtype=torch.int64))
+    assert stub.calls[-1] == "pfhe_add_plain_inplace"
+    with pytest.raises(ValueError, match="poly number mismatch"):
+        api.add_inplace(bgv, a, ct(bgv, size=3))
+
+    lev = Ctx(api.scheme_type.bfv, api.mul_tech_type.hps_overq_leveled)
+    a, b = ct(lev), ct(lev)
+    a.is_asymmetric = True
+    api.multiply_and_relin_inplace(lev, a, b, types.SimpleNamespace(public_keys_ptr=lambda: None))
+    assert stub.calls[-1] == "pfhe_multiply_and_relin_leveled" and a.noise_scale_deg == 2
+    api.multiply_inplace(lev, a, b)
+    assert stub.calls[-1] == "pfhe_multiply_leveled" and a.noise_scale_deg == 3 and a.size() == 3
+    low = api.mod_switch_to_next(lev, b)
+    assert low.noise_scale_deg == 1 and not low.is_asymmetric and not low.is_ntt_form
+    with pytest.raises(ValueError, match="BFV encrypted cannot be in NTT form"):
+        wrong = ct(lev)
+        wrong.is_ntt_form = True
+        api.multiply_plain_inplace(lev, wrong, torch.zeros(8, dtype=torch.int64))
+    total = api.add_many(lev, [ct(lev), ct(lev), ct(lev)])
+    assert total.size() == 2 and stub.calls[-1] == "pfhe_add_rns_poly"
+
+
+def test_pyphantom_wrappers_with_a_stub_library(monkeypatch):
+    """The binding-shaped layer (phantom-fhe_b200/pyphantom.py) without a device: results come back as `ciphertext`
+    objects, operands are left alone, plaintext levels are checked and switched like the reference's overloads
+    (include/evaluate.cuh:150-207)."""
+    import types
+    import torch
+    import phantom_fhe_b200.api as api
+    import pyPhantom as phantom
+    stub = _StubLib()
+    monkeypatch.setattr(api, "lib", stub)
+    monkeypatch.setattr(api, "_stream", lambda: None)
+    ctx = types.SimpleNamespace(scheme=api.scheme_type.ckks, _h=None, poly_degree=8, size_Q=3, size_QP=4, size_P=1,
+                                device=torch.device("cpu"), coeff_modulus_size=lambda ci: 3 - (ci - 1),
+                                parms=types.SimpleNamespace(mul_tech=api.mul_tech_type.none, plain_modulus=0,
+                                                            coeff_modulus=[97, 193, 257, 769], galois_elts=[]))
+    a = phantom.ciphertext(None, torch.zeros((2, 3, 8), dtype=torch.int64), 1, 2.0 ** 20, True)
+    b = phantom.ciphertext(None, torch.ones((2, 3, 8), dtype=torch.int64), 1, 2.0 ** 20, True)
+    keys = types.SimpleNamespace(public_keys_ptr=lambda: None)
+    prod = phantom.multiply_and_relin(ctx, a, b, keys)
+    assert isinstance(prod, phantom.ciphertext) and prod.scale == 2.0 ** 40 and a.scale == 2.0 ** 20 and prod is not a
+    total = phantom.add(ctx, a, b)
+    assert isinstance(total, phantom.ciphertext) and stub.calls[-1] == "pfhe_add_rns_poly"
+    dest = phantom.ciphertext()
+    assert phantom.add_many(ctx, [a, b], dest) is dest and dest.size() == 2
+    pt = phantom.plaintext(torch.zeros((3, 8), dtype=torch.int64), 1, 2.0 ** 20)
+    assert phantom.add_plain(ctx, a, pt).chain_index == 1
+    low = phantom.mod_switch_to(ctx, pt, 3)
+    assert low.chain_index() == 3 and low.data.shape[0] == 1 and pt.chain_index() == 1
+    with pytest.raises(ValueError, match="parameter mismatch"):
+        phantom.add_plain(ctx, a, low)
+    with pytest.raises(ValueError, match="higher level"):
+        phantom.mod_switch_to(ctx, low, 1)
+    with pytest.raises(ValueError, match="end of modulus switching chain"):
+        phantom.mod_switch_to_next(ctx, low)
+    down = phantom.mod_switch_to(ctx, a, 2)
+    assert isinstance(down, phantom.ciphertext) and down.chain_index == 2 and a.chain_index == 1
+    scaled = phantom.multiply_plain(ctx, a, pt)
+    assert scaled.scale == 2.0 ** 40
