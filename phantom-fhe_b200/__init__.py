@@ -12,6 +12,6 @@ from .api import (  # noqa: F401
     scheme_type, mul_tech_type, multiply_inplace, relinearize_inplace, multiply_and_relin_inplace, multiply_and_relin_batch, rotate_inplace, rotate_batch,
     apply_galois_inplace, hoisting_inplace, rescale_to_next, mod_switch_to_next, get_elt_from_step, get_elts_from_steps,
     nwt_2d_radix8_forward_inplace, nwt_2d_radix8_backward_inplace,
-    negate_inplace, add_inplace, sub_inplace, add_many, add_plain_inplace, sub_plain_inplace, multiply_plain_inplace, mod_switch_to_inplace, mod_switch_to,
+    negate_inplace, add_inplace, sub_inplace, add_many, add_plain_inplace, sub_plain_inplace, multiply_plain_inplace, mod_switch_to_inplace, mod_switch_to, mod_switch_to_next_inplace, rescale_to_next_inplace, keyswitch_inplace,
     negate, add, sub, add_plain, sub_plain, multiply_plain, multiply, multiply_and_relin, relinearize, apply_galois, rotate, hoisting, balance_correction_factors,
 )

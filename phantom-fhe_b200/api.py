@@ -828,6 +828,32 @@ def mod_switch_to_next(context, encrypted):
     return out
 
 
+def mod_switch_to_next_inplace(context, encrypted):
+    """mod_switch_to_next_inplace (include/evaluate.cuh:148-151)"""
+    encrypted.__dict__.update(mod_switch_to_next(context, encrypted).__dict__)
+
+
+def rescale_to_next_inplace(context, encrypted):
+    """rescale_to_next_inplace (include/evaluate.cuh:221-224)"""
+    encrypted.__dict__.update(rescale_to_next(context, encrypted).__dict__)
+
+
+def keyswitch_inplace(context, encrypted, c2, relin_keys, is_relin=True):
+    """keyswitch_inplace (src/eval_key_switch.cu:95-182): encrypted[0..1] += key switch of the device polynomial c2 ([l][N],
+    NTT form for CKKS / BGV, coefficient form for BFV) under relin_keys; is_relin only matters to hps_overq_leveled, where
+    it selects the level-dropping rule"""
+    _require_ntt(context, encrypted)
+    if encrypted.size() < 2:
+        raise ValueError("encrypted size must be at least 2")
+    if _leveled(context) and encrypted.chain_index == 1:
+        drop = _levels_to_drop(context, encrypted.noise_scale_deg - 1, not is_relin, encrypted.is_asymmetric)
+        check(lib.pfhe_keyswitch_leveled_inplace(context._h, _ptr(encrypted.data), _ptr(c2), relin_keys.public_keys_ptr(), drop,
+                                                 _stream()))
+        return
+    check(lib.pfhe_keyswitch_inplace(context._h, encrypted.chain_index, _ptr(encrypted.data), _ptr(c2),
+                                     relin_keys.public_keys_ptr(), _stream()))
+
+
 def mod_switch_to_inplace(context, encrypted, chain_index):
     """mod_switch_to_inplace (include/evaluate.cuh:169-177)"""
     if encrypted.chain_index > chain_index:

@@ -325,6 +325,12 @@ def test_evaluator_bookkeeping_with_a_stub_library(monkeypatch):
         api.multiply_and_relin_inplace(ckks, ct(ckks), ct(ckks, chain_index=2), None)
     nxt = api.rescale_to_next(ckks, b)
     assert nxt.chain_index == 2 and nxt.scale == 2.0 ** 20 / 257 and nxt.coeff_modulus_size() == 2
+    api.rescale_to_next_inplace(ckks, b)
+    assert b.chain_index == 2 and b.coeff_modulus_size() == 2
+    api.mod_switch_to_next_inplace(ckks, b)
+    assert b.chain_index == 3 and stub.calls[-1] == "pfhe_mod_switch_to_next"
+    api.keyswitch_inplace(ckks, b, torch.zeros((1, 8), dtype=torch.int64), types.SimpleNamespace(public_keys_ptr=lambda: None))
+    assert stub.calls[-1] == "pfhe_keyswitch_inplace"
 
     bgv = Ctx(api.scheme_type.bgv)
     a, b = ct(bgv, cf=3), ct(bgv, cf=5)
@@ -352,6 +358,8 @@ def test_evaluator_bookkeeping_with_a_stub_library(monkeypatch):
     assert stub.calls[-1] == "pfhe_multiply_leveled" and a.noise_scale_deg == 3 and a.size() == 3
     low = api.mod_switch_to_next(lev, b)
     assert low.noise_scale_deg == 1 and not low.is_asymmetric and not low.is_ntt_form
+    api.keyswitch_inplace(lev, ct(lev), torch.zeros((3, 8), dtype=torch.int64), types.SimpleNamespace(public_keys_ptr=lambda: None), False)
+    assert stub.calls[-1] == "pfhe_keyswitch_leveled_inplace"
     with pytest.raises(ValueError, match="BFV encrypted cannot be in NTT form"):
         wrong = ct(lev)
         wrong.is_ntt_form = True
