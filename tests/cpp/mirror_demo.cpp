@@ -3,6 +3,7 @@
 // and in two steps), rotation, addition, level switching, rescaling, decryption, decoding -- BFV (mul_tech
 // hps_overq_leveled), BGV and CKKS.  Prints OK and exits 0 when every decrypted result is the expected one.
 #include <cstdio>
+#include <cstdlib>
 #include <string>
 #include <vector>
 
@@ -11,13 +12,18 @@
 using namespace phantom_b200;
 
 static int failures = 0;
+// ring degree: 2^13 unless PFHE_DEMO_LOGN says otherwise (the CPU run against the oracle uses a smaller ring)
+static size_t ring_degree() {
+    const char *v = std::getenv("PFHE_DEMO_LOGN");
+    return (size_t) 1 << (v ? std::atoi(v) : 13);
+}
 static void expect(bool ok, const std::string &what) {
     std::printf("%s %s\n", ok ? "ok  " : "FAIL", what.c_str());
     if (!ok) failures++;
 }
 
 static void integer_scheme(scheme_type scheme) {
-    const size_t n = 8192;
+    const size_t n = ring_degree();
     const std::string name = scheme == scheme_type::bfv ? "bfv" : "bgv";
     EncryptionParameters parms(scheme);
     parms.set_poly_modulus_degree(n);
@@ -88,7 +94,7 @@ static void integer_scheme(scheme_type scheme) {
 }
 
 static void ckks() {
-    const size_t n = 8192;
+    const size_t n = ring_degree();
     const double scale = 1099511627776.0;   // 2^40
     EncryptionParameters parms(scheme_type::ckks);
     parms.set_poly_modulus_degree(n);

@@ -406,3 +406,26 @@ def test_pyphantom_wrappers_with_a_stub_library(monkeypatch):
     assert isinstance(down, phantom.ciphertext) and down.chain_index == 2 and a.chain_index == 1
     scaled = phantom.multiply_plain(ctx, a, pt)
     assert scaled.scale == 2.0 ** 40
+
+
+def test_cpp_mirror_application_on_the_oracle(tmp_path):
+    """tests/cpp/mirror_demo.cpp (an application written against the reference's C++ names, include/phantom_b200.hpp) linked
+    against tests/cpp/mock_pfhe_oracle.cpp -- host memory for device memory, the CPU oracle behind every C-ABI entry point
+    the mirror calls -- instead of the real library: the mirror's call sequences, buffer sizes and bookkeeping carry BFV
+    (hps_overq_leveled), BGV and CKKS flows from key generation to decoded results.  (The GPU suite runs the same
+    application on the real library.)"""
+    import shutil
+    import subprocess
+    gxx = shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no C++ compiler or CUDA headers")
+    oracle_dir = os.path.join(ROOT, "oracle")
+    exe = tmp_path / "mirror_demo_cpu"
+    subprocess.check_call([gxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+                           os.path.join(ROOT, "tests", "cpp", "mirror_demo.cpp"), os.path.join(ROOT, "tests", "cpp", "mock_pfhe_oracle.cpp"),
+                           "-o", str(exe), "-L", oracle_dir, "-loracle", f"-Wl,-rpath,{oracle_dir}"])
+    for logn in ("12", "13"):
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600, env=dict(os.environ, PFHE_DEMO_LOGN=logn))
+        assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
+        assert out.stdout.count("ok  ") == 27 and "FAIL" not in out.stdout
