@@ -86,6 +86,24 @@ static void integer_scheme(scheme_type scheme) {
     expect(decrypted(sym) == sq, name + ": multiply_plain_inplace");
     PhantomCiphertext lower = mod_switch_to_next(context, two_step);
     expect(lower.chain_index() == 2 && lower.coeff_modulus_size() == 3 && decrypted(lower) == sq, name + ": mod_switch_to_next");
+    if (scheme == scheme_type::bgv) {
+        // operands whose correction factors differ: x^2 one level down carries q_last^-2, `lower` carries q_last^-1; the
+        // sum balances them (balance_correction_factors) and still decrypts to the sum of the two messages
+        PhantomCiphertext fresh;
+        secret_key.encrypt_symmetric(context, plain, fresh);
+        PhantomCiphertext x = mod_switch_to_next(context, fresh);
+        PhantomCiphertext xx = x;
+        multiply_and_relin_inplace(context, xx, x, relin_keys);
+        expect(xx.correction_factor() != lower.correction_factor() && decrypted(xx) == sq, name + ": product one level down");
+        add_inplace(context, xx, lower);
+        std::vector<uint64_t> twice_sq(n);
+        for (size_t i = 0; i < n; i++) twice_sq[i] = 2 * sq[i] % t;
+        expect(decrypted(xx) == twice_sq, name + ": add_inplace balances different correction factors");
+        sub_inplace(context, xx, lower, true);   // lower - xx = -sq
+        std::vector<uint64_t> minus_sq(n);
+        for (size_t i = 0; i < n; i++) minus_sq[i] = (t - sq[i]) % t;
+        expect(decrypted(xx) == minus_sq, name + ": sub_inplace with negate after balancing");
+    }
     bool threw = false;
     try {
         add_inplace(context, lower, two_step);
