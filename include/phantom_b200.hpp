@@ -684,6 +684,19 @@ inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &enc
     for (int s : naf)
         if ((size_t) std::abs(s) != (n >> 1)) rotate_inplace(context, encrypted, s, galois_key);
 }
+// hoisting_inplace (evaluate.cu:1670-1865): ct <- sum over the steps of rotate(ct, step), one shared mod-up and mod-down
+inline void hoisting_inplace(const PhantomContext &context, PhantomCiphertext &ct, const PhantomGaloisKey &glk, const std::vector<int> &steps) {
+    if (ct.size() > 2) throw std::invalid_argument("ciphertext size must be 2");
+    const auto &elts = context.parms().galois_elts();
+    std::vector<const uint64_t *const *> keys;
+    for (int step : steps) {
+        const uint32_t elt = get_elt_from_step(step, context.poly_degree());
+        const auto it = std::find(elts.begin(), elts.end(), elt);
+        if (it == elts.end()) throw std::logic_error("Galois key not present in hoisting");
+        keys.push_back(glk.get_relin_keys((size_t) (it - elts.begin())).public_keys_ptr());
+    }
+    rethrow(pfhe_hoisting_inplace(context.engine(), ct.chain_index(), ct.data(), steps.data(), steps.size(), keys.data(), context.stream()));
+}
 // rescale_to_next (evaluate.cu:1545-1565)
 inline PhantomCiphertext rescale_to_next(const PhantomContext &context, const PhantomCiphertext &encrypted) {
     if (context.parms().scheme() != scheme_type::ckks) throw std::invalid_argument("unsupported scheme");

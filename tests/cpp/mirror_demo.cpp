@@ -156,6 +156,11 @@ static void ckks() {
     std::vector<double> rot3(slots);
     for (size_t i = 0; i < slots; i++) rot3[i] = sq[(i + 3) % slots];
     expect(max_error(by_three, rot3) < 1e-5, "ckks: rotate_inplace by three steps through the NAF recursion");
+    PhantomCiphertext hoisted = rescaled;   // the rotations by 1, 2 and 4 summed with one shared mod-up
+    hoisting_inplace(context, hoisted, galois_keys, {1, 2, 4});
+    std::vector<double> rot_sum(slots);
+    for (size_t i = 0; i < slots; i++) rot_sum[i] = sq[(i + 1) % slots] + sq[(i + 2) % slots] + sq[(i + 4) % slots];
+    expect(max_error(hoisted, rot_sum) < 1e-4, "ckks: hoisting_inplace over three steps");
     rotate_inplace(context, rescaled, 2, galois_keys);
     expect(max_error(rescaled, rot) < 1e-5, "ckks: rotate_inplace by two steps");
     PhantomCiphertext sym;

@@ -428,4 +428,4 @@ def test_cpp_mirror_application_on_the_oracle(tmp_path):
     for logn in ("12", "13"):
         out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600, env=dict(os.environ, PFHE_DEMO_LOGN=logn))
         assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
-        assert out.stdout.count("ok  ") == 30 and "FAIL" not in out.stdout
+        assert out.stdout.count("ok  ") == 31 and "FAIL" not in out.stdout
