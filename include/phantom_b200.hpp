@@ -17,6 +17,8 @@
 #include <limits>
 #include <string>
 #include <cstdint>
+#include <istream>
+#include <ostream>
 #include <random>
 #include <stdexcept>
 #include <utility>
@@ -148,6 +150,48 @@ private:
     size_t words_ = 0;
 };
 
+namespace detail {
+// the reference's streams are raw struct members, little-endian (include/ciphertext.h:173-213, include/plaintext.h:69-97)
+template<class T>
+inline void put(std::ostream &s, const T &v) {
+    s.write(reinterpret_cast<const char *>(&v), sizeof(T));
+}
+template<class T>
+inline T get(std::istream &s) {
+    T v{};
+    s.read(reinterpret_cast<char *>(&v), sizeof(T));
+    if (!s) throw std::invalid_argument("truncated stream");
+    return v;
+}
+inline void put_words(std::ostream &s, const DeviceWords &d, size_t first, size_t words) {
+    const std::vector<uint64_t> host = d.download();
+    s.write(reinterpret_cast<const char *>(host.data() + first), (std::streamsize) (words * 8));
+}
+inline void get_words(std::istream &s, DeviceWords &d, size_t words) {
+    std::vector<uint64_t> host(words);
+    s.read(reinterpret_cast<char *>(host.data()), (std::streamsize) (words * 8));
+    if (!s) throw std::invalid_argument("truncated stream");
+    d.upload(host.data(), words);
+}
+struct CipherHeader {   // 58 bytes on the wire
+    uint64_t chain_index, size, n, l;
+    double scale;
+    uint64_t correction_factor, noise_scale_deg;
+    bool is_ntt_form, is_asymmetric;
+    void write(std::ostream &s) const {
+        put(s, chain_index), put(s, size), put(s, n), put(s, l), put(s, scale), put(s, correction_factor), put(s, noise_scale_deg);
+        put(s, is_ntt_form), put(s, is_asymmetric);
+    }
+    static CipherHeader read(std::istream &s) {
+        CipherHeader h;
+        h.chain_index = get<uint64_t>(s), h.size = get<uint64_t>(s), h.n = get<uint64_t>(s), h.l = get<uint64_t>(s);
+        h.scale = get<double>(s), h.correction_factor = get<uint64_t>(s), h.noise_scale_deg = get<uint64_t>(s);
+        h.is_ntt_form = get<bool>(s), h.is_asymmetric = get<bool>(s);
+        return h;
+    }
+};
+}   // namespace detail
+
 class PhantomContext {   // include/context.cuh:118-214 as far as this path reads it
 public:
     explicit PhantomContext(const EncryptionParameters &parms, cudaStream_t stream = cudaStreamPerThread)
@@ -190,11 +234,25 @@ private:
 class PhantomPlaintext {   // include/plaintext.h: BFV / BGV [N] mod t (chain_index 0), CKKS [l][N] NTT form + scale
 public:
     DeviceWords data_;
-    size_t chain_index_ = 0;
+    size_t chain_index_ = 0, poly_modulus_degree_ = 0;
     double scale_ = 1.0;
     uint64_t *data() const { return data_.get(); }
     size_t chain_index() const { return chain_index_; }
     double scale() const { return scale_; }
+    void save(std::ostream &stream) const {   // plaintext.h:69-81
+        if (!poly_modulus_degree_) throw std::invalid_argument("empty plaintext");
+        const uint64_t l = data_.size() / poly_modulus_degree_;
+        detail::put<uint64_t>(stream, chain_index_), detail::put<uint64_t>(stream, poly_modulus_degree_), detail::put<uint64_t>(stream, l);
+        detail::put(stream, scale_);
+        detail::put_words(stream, data_, 0, data_.size());
+    }
+    void load(std::istream &stream) {   // plaintext.h:83-97
+        chain_index_ = detail::get<uint64_t>(stream);
+        const uint64_t n = detail::get<uint64_t>(stream), l = detail::get<uint64_t>(stream);
+        scale_ = detail::get<double>(stream);
+        poly_modulus_degree_ = n;
+        detail::get_words(stream, data_, n * l);
+    }
 };
 
 class PhantomCiphertext {   // include/ciphertext.h:10-170
@@ -221,6 +279,24 @@ public:
     bool is_asymmetric() const { return is_asymmetric_; }
     void set_asymmetric(bool a) { is_asymmetric_ = a; }
     DeviceWords &words() { return data_; }
+    std::vector<uint8_t> &seed_ptr() { return seed_; }   // seed of c1 after symmetric encryption (ciphertext.h:16,163-170)
+    const std::vector<uint8_t> &seed_ptr() const { return seed_; }
+    void save(std::ostream &stream) const {   // ciphertext.h:173-190
+        header().write(stream);
+        detail::put_words(stream, data_, 0, data_.size());
+    }
+    void load(std::istream &stream) {   // ciphertext.h:192-213
+        adopt(detail::CipherHeader::read(stream));
+        detail::get_words(stream, data_, size_ * coeff_modulus_size_ * poly_modulus_degree_);
+    }
+    void save_symmetric(std::ostream &stream) const {   // ciphertext.h:216-245: c0 and the seed of c1
+        if (is_asymmetric_ || seed_.size() != 64) throw std::runtime_error("Asymmetric ciphertext does not have seed.");
+        if (size_ != 2) throw std::runtime_error("This method is only for 2-polynomial ciphertext.");
+        header().write(stream);
+        detail::put_words(stream, data_, 0, coeff_modulus_size_ * poly_modulus_degree_);
+        stream.write(reinterpret_cast<const char *>(seed_.data()), 64);
+    }
+    inline void load_symmetric(const class PhantomContext &context, std::istream &stream);   // ciphertext.h:247-307, below
     // a ciphertext with this one's attributes and no words yet (what the reference's resize leaves of the old object)
     PhantomCiphertext attributes_only() const {
         PhantomCiphertext c;
@@ -230,18 +306,45 @@ public:
     }
 
 private:
+    detail::CipherHeader header() const {
+        return detail::CipherHeader{chain_index_, size_, poly_modulus_degree_, coeff_modulus_size_, scale_, correction_factor_, noiseScaleDeg_,
+                                    is_ntt_form_, is_asymmetric_};
+    }
+    void adopt(const detail::CipherHeader &h) {
+        chain_index_ = h.chain_index, size_ = h.size, poly_modulus_degree_ = h.n, coeff_modulus_size_ = h.l, scale_ = h.scale;
+        correction_factor_ = h.correction_factor, noiseScaleDeg_ = h.noise_scale_deg, is_ntt_form_ = h.is_ntt_form, is_asymmetric_ = h.is_asymmetric;
+    }
     DeviceWords data_;
     size_t size_ = 0, chain_index_ = 0, coeff_modulus_size_ = 0, poly_modulus_degree_ = 0;
     double scale_ = 1.0;
     uint64_t correction_factor_ = 1;
     size_t noiseScaleDeg_ = 1;
     bool is_ntt_form_ = true, is_asymmetric_ = false;
+    std::vector<uint8_t> seed_;
 };
+inline void PhantomCiphertext::load_symmetric(const PhantomContext &context, std::istream &stream) {
+    const auto h = detail::CipherHeader::read(stream);
+    if (h.is_asymmetric) throw std::runtime_error("Asymmetric ciphertext does not have seed.");
+    if (h.size != 2) throw std::runtime_error("This method is only for 2-polynomial ciphertext.");
+    if (h.l != context.coeff_modulus_size(context.get_first_index())) throw std::runtime_error("Only support ciphertext without modulus switching.");
+    adopt(h);
+    const size_t words = h.l * h.n;
+    std::vector<uint64_t> c0(words);
+    stream.read(reinterpret_cast<char *>(c0.data()), (std::streamsize) (words * 8));
+    seed_.resize(64);
+    stream.read(reinterpret_cast<char *>(seed_.data()), 64);
+    if (!stream) throw std::invalid_argument("truncated stream");
+    data_.resize(2 * words);
+    cuda_check(cudaMemcpy(data_.get(), c0.data(), words * 8, cudaMemcpyHostToDevice));
+    rethrow(pfhe_sample_poly(context.engine(), 2, h.l, seed_.data(), data_.get() + words, context.stream()));   // c1 from its seed
+    if (!h.is_ntt_form) rethrow(pfhe_ntt_backward_inplace(context.engine(), data_.get() + words, h.l, 0, context.stream()));
+}
 
 class PhantomRelinKey {   // include/secretkey.h:102-166: dnum buffers [2][size_QP][N] + a device array of their addresses
 public:
     PhantomRelinKey() = default;
-    void adopt(std::vector<DeviceWords> &&digits) {
+    void adopt(std::vector<DeviceWords> &&digits, size_t poly_modulus_degree, size_t size_QP) {
+        n_ = poly_modulus_degree, size_QP_ = size_QP;
         digits_ = std::move(digits);
         std::vector<uint64_t> addr;
         for (auto &d : digits_) addr.push_back(reinterpret_cast<uint64_t>(d.get()));
@@ -249,16 +352,45 @@ public:
     }
     const uint64_t *const *public_keys_ptr() const { return reinterpret_cast<const uint64_t *const *>(ptrs_.get()); }
     size_t dnum() const { return digits_.size(); }
+    // secretkey.h:129-162: dnum, then every digit as the ciphertext stream of a public key (chain_index 0, NTT form)
+    void save(std::ostream &stream) const {
+        detail::put<uint64_t>(stream, digits_.size());
+        for (const auto &d : digits_) {
+            detail::CipherHeader{0, 2, n_, size_QP_, 1.0, 1, 1, true, false}.write(stream);
+            detail::put_words(stream, d, 0, d.size());
+        }
+    }
+    void load(std::istream &stream) {
+        const uint64_t dnum = detail::get<uint64_t>(stream);
+        std::vector<DeviceWords> digits(dnum);
+        size_t n = 0, size_QP = 0;
+        for (auto &d : digits) {
+            const auto h = detail::CipherHeader::read(stream);
+            n = h.n, size_QP = h.l;
+            detail::get_words(stream, d, h.size * h.l * h.n);
+        }
+        adopt(std::move(digits), n, size_QP);
+    }
 
 private:
     std::vector<DeviceWords> digits_;
     DeviceWords ptrs_;
+    size_t n_ = 0, size_QP_ = 0;
 };
 
 class PhantomGaloisKey {   // include/secretkey.h:168-224
 public:
     std::vector<PhantomRelinKey> relin_keys_;
     const PhantomRelinKey &get_relin_keys(size_t index) const { return relin_keys_.at(index); }
+    void save(std::ostream &stream) const {   // secretkey.h:194-205
+        detail::put<uint64_t>(stream, relin_keys_.size());
+        for (const auto &k : relin_keys_) k.save(stream);
+    }
+    void load(std::istream &stream) {   // secretkey.h:207-219
+        relin_keys_.clear();
+        relin_keys_.resize(detail::get<uint64_t>(stream));
+        for (auto &k : relin_keys_) k.load(stream);
+    }
 };
 
 namespace detail {
@@ -293,6 +425,17 @@ inline int levels_to_drop(const PhantomContext &context, size_t depth, bool is_k
 class PhantomPublicKey {   // include/secretkey.h:25-100
 public:
     DeviceWords pk_;   // [2][size_QP][N], NTT form
+    size_t n_ = 0, size_QP_ = 0;
+    void save(std::ostream &stream) const {   // secretkey.h:85-90
+        if (!pk_.size()) throw std::invalid_argument("PhantomPublicKey has not been generated");
+        detail::CipherHeader{0, 2, n_, size_QP_, 1.0, 1, 1, true, false}.write(stream);
+        detail::put_words(stream, pk_, 0, pk_.size());
+    }
+    void load(std::istream &stream) {   // secretkey.h:92-96
+        const auto h = detail::CipherHeader::read(stream);
+        n_ = h.n, size_QP_ = h.l;
+        detail::get_words(stream, pk_, h.size * h.l * h.n);
+    }
     // encrypt_asymmetric (src/secretkey.cu:130-190); first data level (see pfhe_encrypt_zero_asymmetric)
     void encrypt_asymmetric(const PhantomContext &context, const PhantomPlaintext &plain, PhantomCiphertext &cipher) const {
         const auto scheme = context.parms().scheme();
@@ -310,16 +453,28 @@ public:
 class PhantomSecretKey {   // include/secretkey.h:226-338
 public:
     explicit PhantomSecretKey(const PhantomContext &context) {   // gen_secretkey, src/secretkey.cu:345-378
+        n_ = context.poly_degree(), size_QP_ = context.size_QP();
         pow_.resize(context.size_QP() * context.poly_degree());
         const auto seed = detail::random_seed();
         rethrow(pfhe_gen_secretkey(context.engine(), seed.bytes, pow_.get(), context.stream()));
         powers_ = 1;
     }
+    PhantomSecretKey() = default;   // to be filled by load()
     const uint64_t *secret_key_array() const { return pow_.get(); }
+    void save(std::ostream &stream) const {   // secretkey.h:346-364: every power computed so far
+        detail::put<uint64_t>(stream, powers_), detail::put<uint64_t>(stream, n_), detail::put<uint64_t>(stream, size_QP_);
+        detail::put_words(stream, pow_, 0, pow_.size());
+    }
+    void load(std::istream &stream) {   // secretkey.h:366-390
+        powers_ = detail::get<uint64_t>(stream);
+        n_ = detail::get<uint64_t>(stream), size_QP_ = detail::get<uint64_t>(stream);
+        detail::get_words(stream, pow_, powers_ * n_ * size_QP_);
+    }
 
     PhantomPublicKey gen_publickey(const PhantomContext &context) const {   // :380-392
         PhantomPublicKey pk;
         pk.pk_.resize(2 * context.size_QP() * context.poly_degree());
+        pk.n_ = context.poly_degree(), pk.size_QP_ = context.size_QP();
         const auto sa = detail::random_seed(), se = detail::random_seed();
         rethrow(pfhe_encrypt_zero_symmetric(context.engine(), 0, pow_.get(), sa.bytes, se.bytes, pk.pk_.get(), context.stream()));
         return pk;
@@ -347,6 +502,7 @@ public:
         cipher.set_ntt_form(scheme != scheme_type::bfv);
         cipher.set_scale(scheme == scheme_type::ckks ? plain.scale() : 1.0);
         cipher.set_correction_factor(1), cipher.SetNoiseScaleDeg(1), cipher.set_asymmetric(false);
+        cipher.seed_ptr().assign(sa.bytes, sa.bytes + 64);   // kept for save_symmetric, like the reference's seed_ptr()
     }
     void decrypt(const PhantomContext &context, const PhantomCiphertext &cipher, PhantomPlaintext &plain) {   // :693-723
         detail::require_form(context, cipher);
@@ -357,6 +513,7 @@ public:
                              context.parms().scheme() == scheme_type::bgv ? cipher.correction_factor() : 1, plain.data(), context.stream()));
         plain.chain_index_ = ckks ? cipher.chain_index() : 0;
         plain.scale_ = ckks ? cipher.scale() : 1.0;
+        plain.poly_modulus_degree_ = context.poly_degree();
     }
 
 private:
@@ -388,11 +545,11 @@ private:
         }
         rethrow(pfhe_gen_kswitch_key(context.engine(), new_key, pow_.get(), seeds.data(), ptrs.data(), context.stream()));
         PhantomRelinKey key;
-        key.adopt(std::move(digits));
+        key.adopt(std::move(digits), context.poly_degree(), context.size_QP());
         return key;
     }
     DeviceWords pow_;   // [sk_max_power][size_QP][N], NTT form
-    size_t powers_ = 0;
+    size_t powers_ = 0, n_ = 0, size_QP_ = 0;
 };
 
 class PhantomBatchEncoder {   // include/batchencoder.h, src/batchencoder.cu
@@ -409,7 +566,7 @@ public:
         plain.data_.resize(slots_);
         rethrow(pfhe_batch_encode(context.engine(), in.get(), values.size(), plain.data(), context.stream()));
         cuda_check(cudaStreamSynchronize(context.stream()));   // `in` is freed on return
-        plain.chain_index_ = 0, plain.scale_ = 1.0;
+        plain.chain_index_ = 0, plain.scale_ = 1.0, plain.poly_modulus_degree_ = slots_;
     }
     std::vector<uint64_t> decode(const PhantomContext &context, const PhantomPlaintext &plain) const {
         DeviceWords out(slots_);
@@ -439,7 +596,7 @@ public:
         cudaStreamSynchronize(context.stream());
         cudaFree(d_in);
         rethrow(rc);
-        plain.chain_index_ = chain_index, plain.scale_ = scale;
+        plain.chain_index_ = chain_index, plain.scale_ = scale, plain.poly_modulus_degree_ = context.poly_degree();
     }
     void encode(const PhantomContext &context, const std::vector<double> &values, double scale, PhantomPlaintext &plain,
                 size_t chain_index = 1) const {

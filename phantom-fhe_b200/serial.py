@@ -1,7 +1,8 @@
 """Byte-compatible save / load of ciphertexts and keys (reference include/ciphertext.h:173-213, include/secretkey.h:
 84-96,129-162,194-219,346-390): the streams stock Phantom writes can be read here and vice versa, so fixtures and
 batches can be exchanged with an unmodified build.  Host-side only; the seed-compressed symmetric
-form (save_symmetric / load_symmetric) needs the reference's PRNG sampler and is not built.
+form (save_symmetric / load_symmetric, include/ciphertext.h:216-307) is c0 plus the 64-byte seed of c1, which the loader
+expands on the device.  include/phantom_b200.hpp writes the same streams from C++.
 
 Layout of a ciphertext stream (little-endian, the reference writes raw struct members):
   size_t chain_index, size, poly_modulus_degree, coeff_modulus_size; double scale; uint64 correction_factor;

@@ -4,6 +4,8 @@
 // hps_overq_leveled), BGV and CKKS.  Prints OK and exits 0 when every decrypted result is the expected one.
 #include <cstdio>
 #include <cstdlib>
+#include <fstream>
+#include <sstream>
 #include <string>
 #include <vector>
 
@@ -20,6 +22,31 @@ static size_t ring_degree() {
 static void expect(bool ok, const std::string &what) {
     std::printf("%s %s\n", ok ? "ok  " : "FAIL", what.c_str());
     if (!ok) failures++;
+}
+
+// every object through its stream and back (the reference's save / load); with PFHE_DEMO_DUMP=<dir> the streams are also
+// written to files there (tests/test_host_logic.py reads them with the Python mirror's serial.py)
+template<class T>
+static std::string saved(const T &object) {
+    std::ostringstream out;
+    object.save(out);
+    return out.str();
+}
+static void dump(const std::string &name, const std::string &bytes) {
+    if (const char *dir = std::getenv("PFHE_DEMO_DUMP")) {
+        std::ofstream f(std::string(dir) + "/" + name, std::ios::binary);
+        f.write(bytes.data(), (std::streamsize) bytes.size());
+    }
+}
+template<class T>
+static void reload(T &object, const std::string &name) {
+    const std::string bytes = saved(object);
+    dump(name, bytes);
+    std::istringstream in(bytes);
+    T fresh;
+    fresh.load(in);
+    expect(saved(fresh) == bytes, name + ": save, load, save gives the same stream");
+    object = std::move(fresh);
 }
 
 static void integer_scheme(scheme_type scheme) {
@@ -40,6 +67,10 @@ static void integer_scheme(scheme_type scheme) {
     PhantomRelinKey relin_keys = secret_key.gen_relinkey(context);
     PhantomGaloisKey galois_keys = secret_key.create_galois_keys(context);
     PhantomBatchEncoder encoder(context);
+    reload(secret_key, name + "_secret_key.bin");   // from here on everything runs on keys that went through their streams
+    reload(public_key, name + "_public_key.bin");
+    reload(relin_keys, name + "_relin_key.bin");
+    reload(galois_keys, name + "_galois_key.bin");
 
     std::vector<uint64_t> msg(n), sq(n), rot(n);
     for (size_t i = 0; i < n; i++) msg[i] = (i * 7 + 3) % 1000, sq[i] = msg[i] * msg[i] % t;
@@ -61,6 +92,24 @@ static void integer_scheme(scheme_type scheme) {
     secret_key.encrypt_symmetric(context, plain, sym);
     expect(decrypted(asym) == msg, name + ": public-key encryption round trip");
     expect(decrypted(sym) == msg, name + ": symmetric encryption round trip");
+    reload(plain, name + "_plaintext.bin");
+    reload(asym, name + "_ciphertext.bin");
+    {   // seed-compressed form: c0 and the seed of c1; the loader draws c1 again
+        std::ostringstream out;
+        sym.save_symmetric(out);
+        dump(name + "_ciphertext_symmetric.bin", out.str());
+        std::istringstream in(out.str());
+        PhantomCiphertext expanded;
+        expanded.load_symmetric(context, in);
+        expect(out.str().size() == 58 + sym.coeff_modulus_size() * n * 8 + 64 && saved(expanded) == saved(sym),
+               name + ": save_symmetric / load_symmetric rebuild the ciphertext");
+        bool refused = false;
+        try {
+            std::ostringstream no;
+            asym.save_symmetric(no);
+        } catch (const std::runtime_error &) { refused = true; }
+        expect(refused, name + ": a public-key ciphertext has no seed to save");
+    }
 
     PhantomCiphertext fused = asym;
     multiply_and_relin_inplace(context, fused, asym, relin_keys);
@@ -144,6 +193,10 @@ static void ckks() {
     PhantomCiphertext ct;
     public_key.encrypt_asymmetric(context, plain, ct);
     expect(max_error(ct, msg) < 1e-6, "ckks: encode, encrypt, decrypt, decode");
+    reload(plain, "ckks_plaintext.bin");
+    reload(ct, "ckks_ciphertext.bin");
+    reload(relin_keys, "ckks_relin_key.bin");
+    expect(plain.scale() == scale && plain.chain_index() == 1 && ct.scale() == scale, "ckks: level and scale survive the streams");
     PhantomCiphertext prod = ct;
     multiply_and_relin_inplace(context, prod, ct, relin_keys);
     PhantomCiphertext rescaled = rescale_to_next(context, prod);

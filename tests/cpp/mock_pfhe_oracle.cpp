@@ -122,6 +122,16 @@ int pfhe_multiply_scalar_rns_poly(pfhe_engine *e, uint64_t *inout, size_t size, 
     return PFHE_OK;
 }
 
+int pfhe_sample_poly(pfhe_engine *e, int kind, size_t limbs, const uint8_t *seed, uint64_t *out, void *) {
+    return orc_sample_poly(e->c, kind, (int) limbs, seed, out) == 0 ? PFHE_OK : fail(PFHE_ERR_INVALID_ARGUMENT, "unknown sampler");
+}
+int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t limbs, size_t start, void *) {
+    std::vector<int> rows(limbs);
+    for (size_t i = 0; i < limbs; i++) rows[i] = (int) (start + i);
+    orc_ntt_inverse(e->c, inout, (int) limbs, rows.data());
+    return PFHE_OK;
+}
+
 // ---- keys, encryption, decryption ----------------------------------------------------------------------------------------
 int pfhe_gen_secretkey(pfhe_engine *e, const uint8_t *seed, uint64_t *sk, void *) {
     orc_gen_secretkey(e->c, seed, sk);

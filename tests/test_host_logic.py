@@ -425,7 +425,44 @@ def test_cpp_mirror_application_on_the_oracle(tmp_path):
     subprocess.check_call([gxx, "-std=c++17", "-O2", "-Wall", "-Wextra", "-Werror", "-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
                            os.path.join(ROOT, "tests", "cpp", "mirror_demo.cpp"), os.path.join(ROOT, "tests", "cpp", "mock_pfhe_oracle.cpp"),
                            "-o", str(exe), "-L", oracle_dir, "-loracle", f"-Wl,-rpath,{oracle_dir}"])
+    dump = tmp_path / "streams"
+    dump.mkdir()
     for logn in ("12", "13"):
-        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600, env=dict(os.environ, PFHE_DEMO_LOGN=logn))
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600,
+                             env=dict(os.environ, PFHE_DEMO_LOGN=logn, PFHE_DEMO_DUMP=str(dump)))
         assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
-        assert out.stdout.count("ok  ") == 31 and "FAIL" not in out.stdout
+        assert out.stdout.count("ok  ") == 51 and "FAIL" not in out.stdout
+    # the streams the C++ mirror wrote are the Python mirror's (and so the reference's) formats: read and re-written byte for byte
+    import importlib.util
+    import io
+    spec = importlib.util.spec_from_file_location("pfhe_serial3", os.path.join(ROOT, "phantom-fhe_b200", "serial.py"))
+    serial = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(serial)
+    n = 8192
+    for scheme in ("bfv", "bgv"):
+        def raw(kind):
+            return open(dump / f"{scheme}_{kind}.bin", "rb").read()
+
+        def rewritten(write, *args, **kw):
+            buf = io.BytesIO()
+            write(buf, *args, **kw)
+            return buf.getvalue()
+        words, hdr = serial.read_ciphertext(io.BytesIO(raw("ciphertext")))
+        assert words.shape == (2, 4, n) and hdr["is_asymmetric"] and hdr["is_ntt_form"] == (scheme == "bgv")
+        assert rewritten(serial.write_ciphertext, words, hdr["chain_index"], hdr["scale"], hdr["correction_factor"],
+                         hdr["noise_scale_deg"], hdr["is_ntt_form"], hdr["is_asymmetric"]) == raw("ciphertext")
+        c0, seed, hdr = serial.read_ciphertext_symmetric(io.BytesIO(raw("ciphertext_symmetric")))
+        assert rewritten(serial.write_ciphertext_symmetric, c0, seed, hdr["chain_index"], hdr["scale"], hdr["correction_factor"],
+                         hdr["noise_scale_deg"], hdr["is_ntt_form"]) == raw("ciphertext_symmetric")
+        pk = serial.read_public_key(io.BytesIO(raw("public_key")))
+        assert pk.shape == (2, 6, n) and rewritten(serial.write_public_key, pk) == raw("public_key")
+        digits = serial.read_relin_key(io.BytesIO(raw("relin_key")))
+        assert len(digits) == 2 and rewritten(serial.write_relin_key, digits) == raw("relin_key")
+        keys = serial.read_galois_key(io.BytesIO(raw("galois_key")))
+        assert len(keys) == 1 and rewritten(serial.write_galois_key, keys) == raw("galois_key")
+        powers = serial.read_secret_key(io.BytesIO(raw("secret_key")))
+        assert powers.shape == (2, 6, n) and rewritten(serial.write_secret_key, powers) == raw("secret_key")
+        plain, ci, scale = serial.read_plaintext(io.BytesIO(raw("plaintext")))
+        assert plain.shape == (1, n) and ci == 0 and rewritten(serial.write_plaintext, plain, ci, scale) == raw("plaintext")
+    plain, ci, scale = serial.read_plaintext(io.BytesIO(open(dump / "ckks_plaintext.bin", "rb").read()))
+    assert plain.shape == (3, n) and ci == 1 and scale == 2.0 ** 40
