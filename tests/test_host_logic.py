@@ -466,3 +466,30 @@ def test_cpp_mirror_application_on_the_oracle(tmp_path):
         assert plain.shape == (1, n) and ci == 0 and rewritten(serial.write_plaintext, plain, ci, scale) == raw("plaintext")
     plain, ci, scale = serial.read_plaintext(io.BytesIO(open(dump / "ckks_plaintext.bin", "rb").read()))
     assert plain.shape == (3, n) and ci == 1 and scale == 2.0 ** 40
+
+
+def test_cpp_mirror_application_under_sanitizers(tmp_path):
+    """The same application, stand-in and the oracle's C source compiled with AddressSanitizer + UndefinedBehaviorSanitizer:
+    "device" buffers are heap blocks here, so a ciphertext, key or plaintext buffer sized wrongly by the mirror (or overrun
+    by the oracle) is an error, and so is any leak of the RAII wrappers."""
+    import shutil
+    import subprocess
+    gcc, gxx = shutil.which("gcc"), shutil.which("g++")
+    cuda_inc = "/usr/local/cuda/include"
+    if gcc is None or gxx is None or not os.path.exists(os.path.join(cuda_inc, "cuda_runtime.h")):
+        pytest.skip("no C/C++ compiler or CUDA headers")
+    flags = ["-O1", "-g", "-fsanitize=address,undefined", "-fno-omit-frame-pointer"]
+    probe = subprocess.run([gxx, "-fsanitize=address,undefined", "-x", "c++", "-", "-o", str(tmp_path / "probe")],
+                           input="int main(){return 0;}", capture_output=True, text=True)
+    if probe.returncode != 0:
+        pytest.skip("sanitizer runtimes are not installed")
+    obj = tmp_path / "oracle_asan.o"
+    subprocess.check_call([gcc] + flags + ["-w", "-c", os.path.join(ROOT, "oracle", "fhe_oracle.c"), "-I", os.path.join(ROOT, "oracle"),
+                                           "-o", str(obj)])
+    exe = tmp_path / "mirror_demo_asan"
+    subprocess.check_call([gxx, "-std=c++17"] + flags + ["-I", os.path.join(ROOT, "include"), "-I", cuda_inc,
+                                                       os.path.join(ROOT, "tests", "cpp", "mirror_demo.cpp"),
+                                                       os.path.join(ROOT, "tests", "cpp", "mock_pfhe_oracle.cpp"), str(obj), "-o", str(exe), "-lm"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=900,
+                         env=dict(os.environ, PFHE_DEMO_LOGN="12", ASAN_OPTIONS="detect_leaks=1", UBSAN_OPTIONS="halt_on_error=1"))
+    assert out.returncode == 0 and out.stdout.strip().endswith("OK") and "runtime error" not in out.stderr, out.stdout[-2000:] + out.stderr[-4000:]
