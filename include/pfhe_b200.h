@@ -279,7 +279,8 @@ int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted,
                         const uint64_t *const *galois_key, void *stream);
 /* hoisting_inplace (src/evaluate.cu:1670-1865): encrypted <- sum_i rotate(encrypted, steps[i]) with one shared mod-up
  * and one mod-down; galois_keys[i] = PhantomGaloisKey::get_relin_keys(index of steps[i]).public_keys_ptr() (host
- * array of n_steps device pointer arrays) */
+ * array of n_steps device pointer arrays).  CKKS and BGV engines; a BFV engine answers PFHE_ERR_INVALID_ARGUMENT
+ * "unsupported scheme" (the host mirrors compose the sum from pfhe_apply_galois_inplace and pfhe_add_rns_poly there). */
 int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, const int *steps, size_t n_steps,
                           const uint64_t *const *const *galois_keys, void *stream);
 /* rescale_to_next (src/evaluate.cu:1545-1565): destination = [size][l-1][n] */

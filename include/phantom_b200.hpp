@@ -844,6 +844,22 @@ inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &enc
 // hoisting_inplace (evaluate.cu:1670-1865): ct <- sum over the steps of rotate(ct, step), one shared mod-up and mod-down
 inline void hoisting_inplace(const PhantomContext &context, PhantomCiphertext &ct, const PhantomGaloisKey &glk, const std::vector<int> &steps) {
     if (ct.size() > 2) throw std::invalid_argument("ciphertext size must be 2");
+    if (context.parms().scheme() == scheme_type::bfv) {
+        // the engine's hoisted form is built for the NTT-form schemes; for BFV the sum is composed from the rotations
+        // themselves: the same plaintext as the reference's hoisted result, not the same words (no shared mod-up)
+        PhantomCiphertext total;
+        for (size_t i = 0; i < steps.size(); i++) {
+            PhantomCiphertext term = ct;
+            rotate_inplace(context, term, steps[i], glk);
+            if (i == 0) total = std::move(term);
+            else add_inplace(context, total, term);
+        }
+        if (!steps.empty()) {
+            cuda_check(cudaStreamSynchronize(context.stream()));
+            ct = std::move(total);
+        }
+        return;
+    }
     const auto &elts = context.parms().galois_elts();
     std::vector<const uint64_t *const *> keys;
     for (int step : steps) {

@@ -783,6 +783,20 @@ def hoisting_inplace(context, ct, glk, steps):
     """hoisting_inplace (src/evaluate.cu:1670-1865)."""
     if ct.size() > 2:
         raise ValueError("ciphertext size must be 2")
+    if context.scheme == scheme_type.bfv:
+        # the engine's hoisted form is built for the NTT-form schemes; for BFV the sum is composed from the rotations
+        # themselves: the same plaintext as the reference's hoisted result, not the same words (no shared mod-up)
+        total = None
+        for s in steps:
+            term = ct.clone()
+            rotate_inplace(context, term, s, glk)
+            if total is None:
+                total = term
+            else:
+                add_inplace(context, total, term)
+        if total is not None:
+            ct.data = total.data
+        return
     elts = context.parms.galois_elts
     ptrs = []
     for s in steps:

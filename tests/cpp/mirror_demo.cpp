@@ -120,6 +120,13 @@ static void integer_scheme(scheme_type scheme) {
     relinearize_inplace(context, two_step, relin_keys);
     expect(two_step.size() == 2 && decrypted(two_step) == sq, name + ": relinearize_inplace");
 
+    {   // hoisting over {1, 1}: twice the rotation by one step (BGV: the hoisted form; BFV: composed from rotations)
+        PhantomCiphertext hoisted = fused;
+        hoisting_inplace(context, hoisted, galois_keys, {1, 1});
+        std::vector<uint64_t> twice_rot(n);
+        for (size_t i = 0; i < n; i++) twice_rot[i] = 2 * rot[i] % t;
+        expect(decrypted(hoisted) == twice_rot, name + ": hoisting_inplace");
+    }
     rotate_inplace(context, fused, 1, galois_keys);
     expect(decrypted(fused) == rot, name + ": rotate_inplace by one step");
 

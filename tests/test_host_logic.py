@@ -366,6 +366,15 @@ def test_evaluator_bookkeeping_with_a_stub_library(monkeypatch):
         api.multiply_plain_inplace(lev, wrong, torch.zeros(8, dtype=torch.int64))
     total = api.add_many(lev, [ct(lev), ct(lev), ct(lev)])
     assert total.size() == 2 and stub.calls[-1] == "pfhe_add_rns_poly"
+    # BFV hoisting is composed from rotations (leveled key switch under hps_overq_leveled) and additions
+    lev.parms.galois_elts = [0]   # the stub's get_elt_from_step answers 0 for every step
+    glk = types.SimpleNamespace(get_relin_keys=lambda idx: types.SimpleNamespace(public_keys_ptr=lambda: None))
+    c = ct(lev)
+    before = len(stub.calls)
+    api.hoisting_inplace(lev, c, glk, [1, 2])
+    made = stub.calls[before:]
+    assert made.count("pfhe_keyswitch_leveled_inplace") == 2 and made.count("pfhe_apply_galois") == 4 and made[-1] == "pfhe_add_rns_poly"
+    assert "pfhe_hoisting_inplace" not in made and c.size() == 2
 
 
 def test_pyphantom_wrappers_with_a_stub_library(monkeypatch):
@@ -431,7 +440,7 @@ def test_cpp_mirror_application_on_the_oracle(tmp_path):
         out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600,
                              env=dict(os.environ, PFHE_DEMO_LOGN=logn, PFHE_DEMO_DUMP=str(dump)))
         assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
-        assert out.stdout.count("ok  ") == 51 and "FAIL" not in out.stdout
+        assert out.stdout.count("ok  ") == 53 and "FAIL" not in out.stdout
     # the streams the C++ mirror wrote are the Python mirror's (and so the reference's) formats: read and re-written byte for byte
     import importlib.util
     import io
