@@ -823,8 +823,26 @@ inline void apply_galois_inplace(const PhantomContext &context, PhantomCiphertex
     const auto &elts = context.parms().galois_elts();
     const auto it = std::find(elts.begin(), elts.end(), galois_elt);
     if (it == elts.end()) throw std::invalid_argument("Galois elt not present");
-    rethrow(pfhe_apply_galois_inplace(context.engine(), encrypted.chain_index(), encrypted.data(), galois_elt,
-                                      galois_keys.get_relin_keys((size_t) (it - elts.begin())).public_keys_ptr(), context.stream()));
+    const PhantomRelinKey &key = galois_keys.get_relin_keys((size_t) (it - elts.begin()));
+    if (context.leveled() && encrypted.chain_index() == 1) {
+        // keyswitch_inplace with is_relin = false under mul_tech hps_overq_leveled (eval_key_switch.cu:111-123, 141-146,
+        // 168-174): the switched polynomial is scaled down by the levels FindLevelsToDrop allows, switched there, expanded
+        const int drop = detail::levels_to_drop(context, encrypted.GetNoiseScaleDeg() - 1, true, encrypted.is_asymmetric());
+        if (drop) {
+            const size_t l = encrypted.coeff_modulus_size(), words = l * encrypted.poly_modulus_degree();
+            DeviceWords moved(2 * words);
+            for (size_t k = 0; k < 2; k++)
+                rethrow(pfhe_apply_galois(context.engine(), encrypted.data() + k * words, l, galois_elt, moved.get() + k * words, context.stream()));
+            cuda_check(cudaMemcpyAsync(encrypted.data(), moved.get(), words * 8, cudaMemcpyDeviceToDevice, context.stream()));
+            cuda_check(cudaMemsetAsync(encrypted.data() + words, 0, words * 8, context.stream()));
+            rethrow(pfhe_keyswitch_leveled_inplace(context.engine(), encrypted.data(), moved.get() + words, key.public_keys_ptr(), drop,
+                                                   context.stream()));
+            cuda_check(cudaStreamSynchronize(context.stream()));   // `moved` is freed on return
+            return;
+        }
+    }
+    rethrow(pfhe_apply_galois_inplace(context.engine(), encrypted.chain_index(), encrypted.data(), galois_elt, key.public_keys_ptr(),
+                                      context.stream()));
 }
 // rotate_inplace / rotate_internal (evaluate.cu:1633-1668): a step whose element the context holds is one automorphism;
 // any other step is composed from the powers of two of its non-adjacent form (include/host/numth.h:17-34)

@@ -93,7 +93,18 @@ int pfhe_engine_set_mul_tech(pfhe_engine *e, int m) {
     return PFHE_OK;
 }
 int pfhe_find_levels_to_drop(pfhe_engine *, size_t, int, int, int *levels) {
-    *levels = 0;   // dropping no level is always admissible; the rule itself is the engine's (and is tested there)
+    // the rule itself is the engine's (and is tested there); here: no level, or PFHE_MOCK_DROP levels so that the
+    // level-dropping branches of the mirror run too
+    const char *v = std::getenv("PFHE_MOCK_DROP");
+    *levels = v ? std::atoi(v) : 0;
+    return PFHE_OK;
+}
+cudaError_t cudaMemsetAsync(void *p, int value, size_t bytes, cudaStream_t) {
+    std::memset(p, value, bytes);
+    return cudaSuccess;
+}
+int pfhe_apply_galois(pfhe_engine *e, const uint64_t *operand, size_t l, uint32_t elt, uint64_t *result, void *) {
+    orc_apply_galois_coeff(e->flat, operand, result, (int) l, elt);
     return PFHE_OK;
 }
 

@@ -441,6 +441,10 @@ def test_cpp_mirror_application_on_the_oracle(tmp_path):
                              env=dict(os.environ, PFHE_DEMO_LOGN=logn, PFHE_DEMO_DUMP=str(dump)))
         assert out.returncode == 0 and out.stdout.strip().endswith("OK"), out.stdout + out.stderr
         assert out.stdout.count("ok  ") == 53 and "FAIL" not in out.stdout
+    for drop in ("1", "2"):   # the level-dropping branches of hps_overq_leveled: products, relinearisation, rotations, hoisting
+        out = subprocess.run([str(exe)], capture_output=True, text=True, timeout=600,
+                             env=dict(os.environ, PFHE_DEMO_LOGN="12", PFHE_MOCK_DROP=drop))
+        assert out.returncode == 0 and out.stdout.count("ok  ") == 53 and "FAIL" not in out.stdout, out.stdout + out.stderr
     # the streams the C++ mirror wrote are the Python mirror's (and so the reference's) formats: read and re-written byte for byte
     import importlib.util
     import io
