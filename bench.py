@@ -1,26 +1,35 @@
 #!/usr/bin/env python
-"""bench.py -- CKKS HMult+Relin at N=2^16, L=16 (BASELINE.json configs[1]) on N GPUs of one node.
+"""bench.py -- CKKS HMult+Relin at N=2^16, L=16 over a batch of independent ciphertext pairs, sharded over the GPUs of
+one node (BASELINE.json configs[1] is the op, configs[4] the batch of 1024 sharded over 1/2/4/8 GPUs).
 
-A "step" is one multiply_inplace + relinearize_inplace on one size-2 ciphertext pair at the top data level
-(primes CoeffModulus::Create(65536, {60, 40x15, 60x4}), special_modulus_size 4, dnum 4) with synthetic uniform
-residues and a synthetic relinearisation key.  Inputs rotate over 8 distinct ciphertext pairs (256 MiB per GPU,
-larger than the 126 MB L2) so a step never finds its operands in L2.
+A "step" is one pass of the hot path over the batch: `--batch` (default 1024) multiply_inplace + relinearize_inplace
+ops on size-2 ciphertexts at the top data level (primes CoeffModulus::Create(65536, {60, 40x15, 60x4}),
+special_modulus_size 4, dnum 4; synthetic uniform residues, synthetic relinearisation key shared by all ranks).  The
+batch is partitioned over the ranks in contiguous blocks (phantom-fhe_b200/shard.py); one GPU holds the whole batch at
+--gpus 1 (32 GiB of operands + 16 GiB of results, far beyond the 126 MB L2).
 
-  value      whole-job HE-ops/s with operands resident in HBM (CUDA events, max over ranks)
-  e2e        the same metric through the C-ABI call that takes HOST buffers
-             (pfhe_multiply_and_relin_host_batch: H2D of both operands and D2H of the result inside the timed region)
-  roofline   dominant kernel = the forward NTT pair (k_fwd_cols + k_fwd_rows) at the mod-up shape (64 limbs),
-             algorithmic bytes 16*N per limb-NTT, timed live with CUDA events
-  cpu_baseline  the oracle's C restatement (oracle/liboracle.so, OpenMP over limbs) on the host cores, bounded sample
+  value          whole-job HE-ops/s with every rank's block resident in its own HBM (CUDA events, max over ranks)
+  scatter_gather the same pass when the batch does NOT live where it is computed, NCCL send/recv over NVLink inside the
+                 timed region, double-buffered against the arithmetic:
+                   rooted  the whole batch lives in rank 0's HBM (scatter operands, gather results; bound by rank 0's
+                           NVLink egress of 32 MiB per remote op)
+                   spread  the batch lives evenly on all ranks in the producer's partition, every rank computes a 1/G
+                           sub-slice of every other rank's slice (all-to-all repartition and back)
+  e2e            the same metric through the C-ABI call that takes HOST buffers (pfhe_multiply_and_relin_host_batch:
+                 H2D of both operands and D2H of the result inside the timed region, per rank from its own pinned buffers)
+  single_op_ms   latency of one op issued alone (BASELINE.json configs[1], the figure the reference's bench quotes)
+  roofline       dominant kernel = the forward NTT pair at the mod-up shape (64 limb-NTTs), algorithmic bytes 16*N per
+                 limb-NTT, timed live with CUDA events; roofline_inner_prod: the key inner product alone
+  cpu_baseline   the oracle's C restatement (oracle/liboracle.so, OpenMP over limbs) on the host cores, bounded sample
+  extra          BASELINE.json configs[2] (BFV HMult+Relin, N=2^14, t=65537) and configs[3] (32 CKKS rotations) on rank 0
 
 --impl reference times the UNMODIFIED reference (oracle/_ref/libphantom_ref.so, built from /root/reference by
-oracle/Makefile.ref) on the same GPU through its own public API (multiply_inplace + relinearize_inplace, timed the
-way benchmark/ckks_bench.cu does); if that library is absent it times the oracle port on the host cores.
-Multi-GPU: independent ciphertexts shard across ranks with no data-path collective (weak scaling); NCCL is used
-only for the barrier and the max-over-ranks of the device time.
+oracle/Makefile.ref) on GPU 0 through its own public API, one op at a time the way benchmark/ckks_bench.cu does, over the
+same batch size per step; if that library is absent it times the oracle port on the host cores.
 """
 import argparse
 import ctypes
+import hashlib
 import json
 import os
 import subprocess
@@ -28,13 +37,15 @@ import sys
 import threading
 import time
 
-import numpy as np
-
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-sys.path.insert(0, os.path.join(ROOT, "tests"))
 
-N_PAIRS = 8  # distinct resident input pairs (8 x 32 MiB > L2)
+LOGN, N = 16, 65536
+BITS = [60] + [40] * 15 + [60] * 4
+SIZE_P = 4
+N_REF_PAIRS = 8     # reference arm / cpu baseline: distinct host-generated pairs
+E2E_PAIRS = 16      # pinned host pairs per rank the e2e leg cycles over (768 MiB pinned)
+KERNEL_SOURCES = ("ntt.cuh", "ntt_kernels.cu", "modarith.cuh", "poly_kernels.cuh")
 
 
 def measured_peaks():
@@ -43,6 +54,14 @@ def measured_peaks():
         with open(path) as f:
             return json.load(f).get("hbm_gbs", 6650.0), "measured"
     return 6650.0, "fallback"
+
+
+def kernel_source_sha():
+    h = hashlib.sha256()
+    for name in KERNEL_SOURCES:
+        with open(os.path.join(ROOT, "phantom-fhe_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
 
 
 class ClockSampler:
@@ -88,15 +107,33 @@ class ClockSampler:
                 if val.lower().startswith("active"):
                     reasons.add(name)
         sm.sort()
-        # median of the samples taken under load (upper half)
-        load = sm[len(sm) // 2:] if sm else []
+        load = sm[len(sm) // 2:] if sm else []   # median of the samples taken under load (upper half)
         med = load[len(load) // 2] if load else None
         return {"sm_mhz": med, "sm_max_mhz": mx, "reasons": sorted(reasons)}
 
 
-def cpu_baseline(ps, a, b, rlk_h, ops=None, budget_s=12.0):
+def workload_name(batch):
+    return (f"CKKS HMult+Relin, N=2^16, L=16, alpha=4, dnum=4; step = batch of {batch} independent ciphertext pairs "
+            "sharded over the ranks in contiguous blocks")
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# host-side baselines (the only legs that touch oracle/ -- through tests/harness.py)
+# ---------------------------------------------------------------------------------------------------------------
+def _harness():
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
     import harness as H
+    return H
+
+
+def cpu_baseline(ops=None, budget_s=12.0):
+    H = _harness()
     from harness import P
+    import numpy as np
+    ps = H.params_primary()
+    a = [H.ciphertext(ps, 10 + 2 * i) for i in range(2)]
+    b = [H.ciphertext(ps, 11 + 2 * i) for i in range(2)]
+    rlk_h = H.switch_key(ps, 100)
     o = H.oracle()
     cores = min(os.cpu_count() or 1, 64)
     o.orc_set_threads(cores)
@@ -115,53 +152,80 @@ def cpu_baseline(ps, a, b, rlk_h, ops=None, budget_s=12.0):
             "sample": f"{ops} HMult+Relin ops at N=2^16, L=16 through oracle/liboracle.so (OpenMP over limbs)"}
 
 
-def run_reference(args, ps, a, b, rank, world):
-    """--impl reference: the unmodified reference on this GPU, or the oracle port on the host cores."""
-    import harness as H
-    from harness import P
+def run_reference(args, rank):
+    """--impl reference: the unmodified reference on GPU 0 (rank 0 only), or the oracle port on the host cores."""
     if rank != 0:
         return None
-    r = H.reference()
-    line = {"impl": "reference", "metric": "CKKS HMult+Relin ops/s (N=2^16, L=16)", "unit": "HE-ops/s",
-            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "weak",
-            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "CKKS HMult+Relin, N=2^16, L=16, alpha=4, dnum=4, batch=1 ciphertext pair per step"}}
+    H = _harness()
+    from harness import P
     import torch
+    ps = H.params_primary()
+    line = {"impl": "reference", "metric": "CKKS HMult+Relin ops/s (N=2^16, L=16)", "unit": "HE-ops/s",
+            "n_gpus": 1, "steps": args.steps, "warmup": args.warmup, "higher_is_better": True, "scaling": "strong",
+            "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(args.batch),
+                       "issue": "one op at a time through multiply_inplace + relinearize_inplace on a fresh copy, "
+                                "cudaEvent pair per op (benchmark/ckks_bench.cu:167-176); the reference is single-device"}}
+    r = H.reference()
     if r is not None and torch.cuda.is_available():
+        a = [H.ciphertext(ps, 10 + 2 * i) for i in range(N_REF_PAIRS)]
+        b = [H.ciphertext(ps, 11 + 2 * i) for i in range(N_REF_PAIRS)]
         steps_arr = (ctypes.c_int * 1)(1)
         h = r.ref_create(3, ps.n, P(ps.primes), ps.size_QP, ps.size_P, 0, 0, steps_arr, 1, float(2 ** 40), 1)
         if not h:
             raise RuntimeError(r.ref_last_error().decode())
-        trials = args.warmup + args.steps
-        times = (ctypes.c_double * trials)()
-        assert r.ref_time_op(h, 0, 1, P(a[0]), P(b[0]), 0, 0, trials, times) == 0, r.ref_last_error()
-        dev = sum(times[args.warmup:]) / args.steps
-        e2e_trials = min(trials, args.warmup + 10)
-        assert r.ref_time_op(h, 0, 1, P(a[0]), P(b[0]), 0, 1, e2e_trials, times) == 0, r.ref_last_error()
-        e2e = sum(times[args.warmup:e2e_trials]) / (e2e_trials - args.warmup)
+        per_pair = -(-args.batch // N_REF_PAIRS)
+
+        def run(mode, steps):
+            """`steps` passes over the batch: every resident pair takes batch / N_REF_PAIRS consecutive trials"""
+            total_us = 0.0
+            times = (ctypes.c_double * per_pair)()
+            for _ in range(steps):
+                left = args.batch
+                for k in range(N_REF_PAIRS):
+                    cnt = min(per_pair, left)
+                    if cnt <= 0:
+                        break
+                    assert r.ref_time_op(h, 0, 1, P(a[k]), P(b[k]), 0, mode, cnt, times) == 0, r.ref_last_error()
+                    total_us += sum(times[:cnt])
+                    left -= cnt
+            return total_us
+
+        run(0, min(args.warmup, 1))
+        dev_us = run(0, args.steps)
+        e2e_steps = max(1, min(args.steps, 2))
+        e2e_us = run(1, e2e_steps)
         r.ref_destroy(h)
         words = 2 * ps.limbs() * ps.n
-        line.update({"value": 1e6 / dev, "ms_per_step": dev / 1e3,
-                     "cpu_baseline": {"value": 1e6 / dev, "unit": "HE-ops/s", "cores": 0, "kind": "reference",
+        value = args.steps * args.batch / (dev_us * 1e-6)
+        line.update({"value": value, "ms_per_step": dev_us / 1e3 / args.steps,
+                     "single_op_ms": dev_us / 1e3 / (args.steps * args.batch),
+                     "cpu_baseline": {"value": value, "unit": "HE-ops/s", "cores": 0, "kind": "reference",
                                       "sample": "unmodified phantom-fhe kernels rebuilt for sm_100a on this GPU "
-                                                "(multiply_inplace + relinearize_inplace, cudaEvent per trial)"},
-                     "e2e": {"value": 1e6 / e2e, "unit": "HE-ops/s", "h2d_bytes_per_step": 2 * words * 8,
-                             "d2h_bytes_per_step": words * 8}})
+                                                "(multiply_inplace + relinearize_inplace, cudaEvent per op)"},
+                     "e2e": {"value": e2e_steps * args.batch / (e2e_us * 1e-6), "unit": "HE-ops/s",
+                             "h2d_bytes_per_step": args.batch * 2 * words * 8, "d2h_bytes_per_step": args.batch * words * 8,
+                             "steps": e2e_steps}})
     else:
-        cb = cpu_baseline(ps, a, b, H.switch_key(ps, 100), ops=max(1, min(args.steps, 3)))
-        line.update({"value": cb["value"], "ms_per_step": 1e3 / cb["value"], "cpu_baseline": cb,
+        cb = cpu_baseline(ops=max(1, min(args.steps, 3)))
+        line.update({"value": cb["value"], "ms_per_step": 1e3 * args.batch / cb["value"], "cpu_baseline": cb,
                      "e2e": {"value": cb["value"], "unit": "HE-ops/s", "h2d_bytes_per_step": 0,
                              "d2h_bytes_per_step": 0}})
     return line
 
 
+# ---------------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=400)
-    ap.add_argument("--warmup", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine", choices=["engine", "reference"])
+    ap.add_argument("--batch", type=int, default=1024, help="ciphertext pairs per step (whole job)")
+    ap.add_argument("--chunk", type=int, default=8, help="pairs per pipeline tick of the scatter/gather")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[3] lines")
+    ap.add_argument("--no-exchange", action="store_true", help="skip the scatter/gather legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -169,68 +233,67 @@ def main():
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
 
-    import harness as H
-    ps = H.params_primary()
-    # every rank owns different ciphertexts (seeds offset by rank), the key is shared
-    a = [H.ciphertext(ps, 10 + 2 * (rank * N_PAIRS + i)) for i in range(N_PAIRS)]
-    b = [H.ciphertext(ps, 11 + 2 * (rank * N_PAIRS + i)) for i in range(N_PAIRS)]
-
     if args.impl == "reference":
-        line = run_reference(args, ps, a, b, rank, world)
+        line = run_reference(args, rank)
         if line is not None:
             print(json.dumps(line), flush=True)
         return
 
+    import numpy as np
     import torch
     import torch.distributed as dist
     import phantom_fhe_b200 as pf
     from phantom_fhe_b200 import lib, check
+    from phantom_fhe_b200.shard import ExchangePlan, Exchange, shard_range
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py needs a CUDA device: phantom-fhe_b200 has no CPU path")
     torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
     if world > 1:
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist.init_process_group("nccl", device_id=dev)
 
+    primes = pf.CoeffModulus.Create(N, BITS)
     parms = pf.EncryptionParameters(pf.scheme_type.ckks)
-    parms.set_poly_modulus_degree(ps.n)
-    parms.set_coeff_modulus([int(p) for p in ps.primes])
-    parms.set_special_modulus_size(ps.size_P)
+    parms.set_poly_modulus_degree(N)
+    parms.set_coeff_modulus(primes)
+    parms.set_special_modulus_size(SIZE_P)
     ctx = pf.PhantomContext(parms)
-    l, n = ps.limbs(), ps.n
-    words = 2 * l * n
-    rlk_h = H.switch_key(ps, 100)
-    rlk = pf.PhantomRelinKey(ctx, list(rlk_h))
+    size_QP = len(primes)
+    l = size_QP - SIZE_P
+    n = N
+    words = 2 * l * n                 # one ciphertext
+    in_words, out_words = 2 * words, words
     st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
 
-    def to_dev(x):
-        return torch.from_numpy(x.view(np.int64)).cuda()
+    def fill_uniform(view, moduli, gen, block=64):
+        """view: [..., len(moduli), n] int64; limb j gets uniform residues below moduli[j] (device generator)"""
+        flat = view.reshape(-1, len(moduli), n)
+        for b0 in range(0, flat.shape[0], block):
+            sl = flat[b0:b0 + block]
+            for j, q in enumerate(moduli):
+                sl[:, j, :] = torch.randint(0, int(q), (sl.shape[0], n), generator=gen, device=dev, dtype=torch.int64)
 
-    da = [to_dev(x) for x in a]
-    db = [to_dev(x) for x in b]
-    work = [torch.empty_like(da[0]) for _ in range(N_PAIRS)]
+    # relinearisation key: dnum digits [2][size_QP][n], the same words on every rank (same seed)
+    gen = torch.Generator(device=dev)
+    gen.manual_seed(100)
+    dnum = ctx.dnum(1)
+    digits = [torch.empty((2, size_QP, n), dtype=torch.int64, device=dev) for _ in range(dnum)]
+    for d in digits:
+        fill_uniform(d, primes, gen)
+    rlk = pf.PhantomRelinKey.from_device(ctx, digits)
 
-    def device_step(i):
-        k = i % N_PAIRS
-        # multiply + relinearize of pair k; the result goes to its own buffer (the reference's in-place form
-        # reallocates the ciphertext, include/ciphertext.h:44-72), operands stay intact
-        check(lib.pfhe_multiply_and_relin(ctx._h, 1, da[k].data_ptr(), db[k].data_ptr(), work[k].data_ptr(),
-                                          rlk.public_keys_ptr(), st))
-
-    CHUNK = 8 * N_PAIRS
-    PtrC = ctypes.c_void_p * CHUNK
-    arr_a = PtrC(*[da[i % N_PAIRS].data_ptr() for i in range(CHUNK)])
-    arr_b = PtrC(*[db[i % N_PAIRS].data_ptr() for i in range(CHUNK)])
-    arr_o = PtrC(*[work[i % N_PAIRS].data_ptr() for i in range(CHUNK)])
-
-    def device_steps(count):
-        # `count` <= CHUNK steps = `count` independent HMult+Relin ops through the batched C-ABI entry point, one op per
-        # step, interleaved over the engine's lanes (independent ciphertexts are the path's sharding unit); operands
-        # rotate over the N_PAIRS resident pairs, op i and op i + N_PAIRS share an output buffer and a lane (ordered)
-        check(lib.pfhe_multiply_and_relin_batch(ctx._h, 1, arr_a, arr_b, arr_o, count, rlk.public_keys_ptr(), st))
-
-    def refill():
-        pass
+    # the batch.  Rank 0 allocates all of it (home of the rooted plan); its own block is a slice of that.  The other
+    # ranks hold only their block.  Distinct words per unit (seeded by rank).
+    B = args.batch
+    lo, hi = shard_range(B, rank, world)
+    n_home = B if rank == 0 else hi - lo
+    store_in = torch.empty((n_home, in_words), dtype=torch.int64, device=dev)
+    store_out = torch.empty((n_home, out_words), dtype=torch.int64, device=dev)
+    gen.manual_seed(1000 + rank)
+    fill_uniform(store_in.view(n_home, 4, l, n), primes[:l], gen)
+    own_in = store_in[lo:hi] if rank == 0 else store_in
+    own_out = store_out[lo:hi] if rank == 0 else store_out
 
     def barrier():
         torch.cuda.synchronize()
@@ -241,139 +304,243 @@ def main():
     def max_over_ranks(ms):
         if world == 1:
             return ms
-        t = torch.tensor([ms], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    # ---- device-resident throughput ---------------------------------------------------------------------
-    refill()
-    for i in range(args.warmup):
-        device_step(i)
-    device_steps(N_PAIRS)
-    barrier()
+    ptr_cache = {}
+
+    def compute_fn(tag):
+        def compute(t, views):
+            key = (tag, t)
+            if key not in ptr_cache:
+                pa, pb, po = [], [], []
+                for vin, vout in views:
+                    for j in range(vin.shape[0]):
+                        base = vin.data_ptr() + j * in_words * 8
+                        pa.append(base)
+                        pb.append(base + words * 8)
+                        po.append(vout.data_ptr() + j * out_words * 8)
+                Arr = ctypes.c_void_p * len(pa)
+                ptr_cache[key] = (Arr(*pa), Arr(*pb), Arr(*po), len(pa))
+            a, b, o, cnt = ptr_cache[key]
+            if cnt:
+                check(lib.pfhe_multiply_and_relin_batch(ctx._h, 1, a, b, o, cnt, rlk.public_keys_ptr(), st))
+        return compute
+
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    timed_launches = [0]
+
+    def timed_passes(ex, tag, warm, steps):
+        fn = compute_fn(tag)
+        for _ in range(warm):
+            ex.run(fn)
+        barrier()
+        before = ctx.launch_count()
+        e0.record()
+        for _ in range(steps):
+            ex.run(fn)
+        e1.record()
+        barrier()
+        timed_launches[0] = ctx.launch_count() - before
+        return max_over_ranks(e0.elapsed_time(e1))
+
+    # ---- value: every rank's block resident in its own HBM ---------------------------------------------------
+    plan_local = ExchangePlan.local(B, world, args.chunk)
+    ex_local = Exchange(plan_local, rank, own_in, own_out, dist if world > 1 else None)
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
-    launches0 = ctx.launch_count()
-    total_ms = 0.0
-    done = 0
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    while done < args.steps:
-        chunk = min(CHUNK, args.steps - done)
-        refill()  # untimed: restore the in-place operands
-        barrier()
-        e0.record()
-        device_steps(chunk)
-        e1.record()
-        barrier()
-        total_ms += e0.elapsed_time(e1)
-        done += chunk
-    launches = ctx.launch_count() - launches0
-    dev_ms = max_over_ranks(total_ms)
-    # latency of one op issued alone (one lane, nothing else on the GPU): the figure the reference's own bench quotes
-    lat_steps = min(args.steps, 64)
+    dev_ms = timed_passes(ex_local, "local", args.warmup, args.steps)
+    launches = timed_launches[0]   # this rank's kernels inside the timed region
+
+    # ---- latency of one op issued alone (BASELINE configs[1]) --------------------------------------------------
+    lat_ops = min(hi - lo, 64)
     barrier()
     e0.record()
-    for i in range(lat_steps):
-        device_step(i)
+    for i in range(lat_ops):
+        base = own_in.data_ptr() + i * in_words * 8
+        check(lib.pfhe_multiply_and_relin(ctx._h, 1, base, base + words * 8, own_out.data_ptr() + i * out_words * 8,
+                                          rlk.public_keys_ptr(), st))
     e1.record()
     barrier()
-    lat_ms = max_over_ranks(e0.elapsed_time(e1)) / lat_steps
+    lat_ms = max_over_ranks(e0.elapsed_time(e1)) / max(lat_ops, 1)
 
-    # ---- end to end from pinned host memory ---------------------------------------------------------------
-    pin_a = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in a]
-    pin_b = [torch.from_numpy(x.view(np.int64)).pin_memory() for x in b]
-    pin_o = [torch.empty((2, l, n), dtype=torch.int64).pin_memory() for _ in range(N_PAIRS)]
-    e2e_steps = min(args.steps, 100)
-    PtrArr = ctypes.c_void_p * e2e_steps
-    pa = PtrArr(*[pin_a[i % N_PAIRS].data_ptr() for i in range(e2e_steps)])
-    pb = PtrArr(*[pin_b[i % N_PAIRS].data_ptr() for i in range(e2e_steps)])
-    po = PtrArr(*[pin_o[i % N_PAIRS].data_ptr() for i in range(e2e_steps)])
-    check(lib.pfhe_multiply_and_relin_host_batch(ctx._h, 1, pa, pb, po, min(args.warmup, e2e_steps),
-                                                 rlk.public_keys_ptr(), st))
+    # ---- scatter / gather over NVLink inside the timed region -------------------------------------------------
+    sg = None
+    if world > 1 and not args.no_exchange:
+        sg = {}
+        sg_steps = args.steps
+        for kind in ("rooted", "spread"):
+            if kind == "rooted":
+                plan = ExchangePlan.rooted(B, world, args.chunk, 0)
+                ex = Exchange(plan, rank, store_in if rank == 0 else store_in[:0], store_out if rank == 0 else store_out[:0], dist)
+            else:
+                plan = ExchangePlan.spread(B, world, args.chunk)
+                ex = Exchange(plan, rank, own_in, own_out, dist)
+            ms = timed_passes(ex, kind, 2, sg_steps)
+            sent, recv = plan.bytes_moved(0, in_words * 8, out_words * 8)
+            sg[kind] = {"value": sg_steps * B / (ms * 1e-3), "unit": "HE-ops/s", "ms_per_step": ms / sg_steps,
+                        "steps": sg_steps, "rank0_sent_bytes_per_step": sent, "rank0_recv_bytes_per_step": recv,
+                        "rank0_egress_gbs": sent * sg_steps / (ms * 1e-3) / 1e9,
+                        "vs_compute_only": (sg_steps / ms) / (args.steps / dev_ms)}
+            del ex
+        sg["transport"] = "torch.distributed batch_isend_irecv (ncclSend/ncclRecv groups), one group per tick of " \
+                          f"{args.chunk} pairs, double-buffered staging, overlapped with the arithmetic"
+        sg["nvlink_peak_gbs_per_direction"] = 900.0
+
+    # ---- end to end from pinned host memory ----------------------------------------------------------------
+    shard = hi - lo
+    e2e_pairs = min(E2E_PAIRS, max(shard, 1))
+    pin_in = torch.empty((e2e_pairs, in_words), dtype=torch.int64).pin_memory()
+    pin_out = torch.empty((e2e_pairs, out_words), dtype=torch.int64).pin_memory()
+    pin_in.copy_(own_in[:e2e_pairs])
+    PtrArr = ctypes.c_void_p * shard
+    pa = PtrArr(*[pin_in.data_ptr() + (i % e2e_pairs) * in_words * 8 for i in range(shard)])
+    pb = PtrArr(*[pin_in.data_ptr() + (i % e2e_pairs) * in_words * 8 + words * 8 for i in range(shard)])
+    po = PtrArr(*[pin_out.data_ptr() + (i % e2e_pairs) * out_words * 8 for i in range(shard)])
+    e2e_steps = max(1, min(args.steps, 3))
+    check(lib.pfhe_multiply_and_relin_host_batch(ctx._h, 1, pa, pb, po, min(shard, 2 * e2e_pairs), rlk.public_keys_ptr(), st))
     barrier()
     t0 = time.perf_counter()
     e0.record()
-    check(lib.pfhe_multiply_and_relin_host_batch(ctx._h, 1, pa, pb, po, e2e_steps, rlk.public_keys_ptr(), st))
+    for _ in range(e2e_steps):
+        check(lib.pfhe_multiply_and_relin_host_batch(ctx._h, 1, pa, pb, po, shard, rlk.public_keys_ptr(), st))
     e1.record()
     barrier()
     e2e_ms = max_over_ranks(e0.elapsed_time(e1))
     wall_ms = (time.perf_counter() - t0) * 1e3
+    # the same copies with no arithmetic between them: what the host <-> device links give this rank layout
+    s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
+    copy_ops = min(shard, 4 * e2e_pairs)
+    dst_in = store_in[:2]
+    barrier()
+    e0.record()
+    s_h2d.wait_stream(torch.cuda.current_stream())
+    s_d2h.wait_stream(torch.cuda.current_stream())
+    for i in range(copy_ops):
+        with torch.cuda.stream(s_h2d):
+            dst_in[i % 2].copy_(pin_in[i % e2e_pairs], non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            pin_out[i % e2e_pairs].copy_(store_out[i % 2], non_blocking=True)
+    torch.cuda.current_stream().wait_stream(s_h2d)
+    torch.cuda.current_stream().wait_stream(s_d2h)
+    e1.record()
+    barrier()
+    copy_ms = max_over_ranks(e0.elapsed_time(e1))
     clocks = sampler.stop() if rank == 0 else None
 
-    # ---- roofline of the dominant kernel: forward NTT at the mod-up shape (64 limb-NTTs per launch pair) -------
-    roof = None
-    cb = None
+    # ---- rooflines, baselines, extra configs: rank 0 ---------------------------------------------------------
+    roof = roof_ip = cb = extra = None
     if rank == 0:
+        peak, how = measured_peaks()
+        # forward NTT at the mod-up shape: 4 polynomials x 16 limbs per launch pair, 4 rotating 32 MiB buffers
         limbs_ntt = 64
-        # 3 rotating buffers of 64 limbs (3 x 32 MiB, with the 20 MiB twiddle table > L2 in steady state)
-        bufs = [torch.zeros(limbs_ntt * n, dtype=torch.int64, device="cuda") for _ in range(4)]
+        bufs = store_in.view(-1)[:4 * limbs_ntt * n].view(4, limbs_ntt * n)
         reps = 200
-        turn = [0]
-
-        def ntt_launch():
-            # 4 polynomials x 16 limbs in one launch pair: the shape of the mod-up NTT (beta = 4, l = 16)
-            buf = bufs[turn[0] % len(bufs)]
-            turn[0] += 1
-            check(lib.pfhe_ntt_forward_inplace_batch(ctx._h, buf.data_ptr(), 4, 16, 0, st))
-
-        for _ in range(3):
-            ntt_launch()
+        for i in range(3):
+            check(lib.pfhe_ntt_forward_inplace_batch(ctx._h, bufs[i % 4].data_ptr(), 4, 16, 0, st))
         torch.cuda.synchronize()
         e0.record()
-        for _ in range(reps):
-            ntt_launch()
+        for i in range(reps):
+            check(lib.pfhe_ntt_forward_inplace_batch(ctx._h, bufs[i % 4].data_ptr(), 4, 16, 0, st))
         e1.record()
         torch.cuda.synchronize()
         ntt_us = e0.elapsed_time(e1) * 1e3 / reps
         alg_bytes = limbs_ntt * 16 * n
-        peak, how = measured_peaks()
         achieved = alg_bytes / (ntt_us * 1e-6) / 1e9
-        traffic, issue = None, None
+        traffic, issue, prof_src = None, None, None
         tpath = os.path.join(ROOT, "profiles", "ntt_traffic.json")
         if os.path.exists(tpath):
             with open(tpath) as f:
                 prof = json.load(f)
-            traffic = prof.get("dram_bytes_total")
-            if prof.get("warp_instructions"):
-                # what the kernel pair is actually bound by: warp-instruction issue.  Peak = one warp
-                # instruction per scheduler per clock = SMs x 4 x SM clock; FP64 / IMAD instructions hold the dispatch port
-                # for two clocks, so a mix dominated by them tops out near half of that.
-                prop = torch.cuda.get_device_properties(local_rank)
-                peak_inst = prop.multi_processor_count * 4 * (clocks["sm_mhz"] or 1965.0) * 1e6 if clocks else None
-                ach_inst = prof["warp_instructions"] / (ntt_us * 1e-6)
-                issue = {"warp_inst_per_launch": prof["warp_instructions"], "achieved_ginst_s": ach_inst / 1e9,
-                         "peak_ginst_s": peak_inst / 1e9 if peak_inst else None,
-                         "frac": ach_inst / peak_inst if peak_inst else None}
-        roof = {"kernel": "forward negacyclic NTT (k_fwd_cols + k_fwd_rows), 64 limb-NTTs of N=2^16",
+            # ncu figures come from a committed capture: valid only for the kernel sources they were taken from
+            if prof.get("kernel_source_sha") == kernel_source_sha():
+                prof_src = {"source": "profile", "file": "profiles/ntt_traffic.json", "git": prof.get("git"),
+                            "kernel_source_sha": prof.get("kernel_source_sha")}
+                traffic = prof.get("dram_bytes_total")
+                if prof.get("warp_instructions"):
+                    prop = torch.cuda.get_device_properties(local_rank)
+                    peak_inst = prop.multi_processor_count * 4 * ((clocks or {}).get("sm_mhz") or 1965.0) * 1e6
+                    ach_inst = prof["warp_instructions"] / (ntt_us * 1e-6)
+                    issue = {"warp_inst_per_launch": prof["warp_instructions"], "achieved_ginst_s": ach_inst / 1e9,
+                             "peak_ginst_s": peak_inst / 1e9, "frac": ach_inst / peak_inst}
+            else:
+                prof_src = {"source": "profile", "stale": True,
+                            "note": "profiles/ntt_traffic.json was captured from other kernel sources; traffic withheld"}
+        roof = {"kernel": "forward negacyclic NTT (column pass + row pass), 64 limb-NTTs of N=2^16",
                 "bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "peak_source": how, "traffic": traffic, "algorithmic_bytes": alg_bytes,
-                "launch_us": ntt_us, "limb_ntt_per_s": limbs_ntt / (ntt_us * 1e-6), "issue": issue,
-                "note": "not HBM-bound: 64-bit modular butterflies are bound by warp-instruction issue on sm_100a "
-                        "(FP64 and IMAD share the dispatch port, 2 clocks each; DESIGN.md 4.1, profiles/r1c_*)"}
+                "peak_source": how, "traffic": traffic, "traffic_source": prof_src, "algorithmic_bytes": alg_bytes,
+                "launch_us": ntt_us, "limb_ntt_per_s": limbs_ntt / (ntt_us * 1e-6), "issue": issue}
+        # key inner product alone on a full grid: reads beta*m digit limbs + 2*beta*m key limbs, writes 2*m limbs
+        beta, m = dnum, l + SIZE_P
+        t_mod_up = torch.empty((2, beta, m, n), dtype=torch.int64, device=dev)
+        fill_uniform(t_mod_up, primes, gen)
+        t_mod_up = t_mod_up.view(2, beta * m * n)
+        cxb = torch.empty((2, 2 * m * n), dtype=torch.int64, device=dev)
+        for i in range(3):
+            check(lib.pfhe_key_switch_inner_prod(ctx._h, 1, cxb[i % 2].data_ptr(), t_mod_up[i % 2].data_ptr(),
+                                                 rlk.public_keys_ptr(), st))
+        torch.cuda.synchronize()
+        e0.record()
+        for i in range(reps):
+            check(lib.pfhe_key_switch_inner_prod(ctx._h, 1, cxb[i % 2].data_ptr(), t_mod_up[i % 2].data_ptr(),
+                                                 rlk.public_keys_ptr(), st))
+        e1.record()
+        torch.cuda.synchronize()
+        ip_us = e0.elapsed_time(e1) * 1e3 / reps
+        ip_bytes = (3 * beta * m + 2 * m) * 8 * n
+        ip_ach = ip_bytes / (ip_us * 1e-6) / 1e9
+        roof_ip = {"kernel": "key-switch inner product (k_inner_prod<4>), beta=4, m=20, alone on a full grid",
+                   "bound": "hbm", "achieved": ip_ach, "peak": peak, "unit": "GB/s", "frac": ip_ach / peak,
+                   "peak_source": how, "traffic": None, "algorithmic_bytes": ip_bytes, "launch_us": ip_us}
+        if not args.no_extra:
+            extra = extra_configs(pf, lib, check, torch, dev)
         if not args.no_cpu_baseline:
-            cb = cpu_baseline(ps, a, b, rlk_h)
+            cb = cpu_baseline()
 
     if rank == 0:
-        total_steps = args.steps * world
-        value = total_steps / (dev_ms * 1e-3)
+        value = args.steps * B / (dev_ms * 1e-3)
         line = {
             "metric": "CKKS HMult+Relin ops/s (N=2^16, L=16)", "value": value, "unit": "HE-ops/s", "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": dev_ms / args.steps, "higher_is_better": True,
-            "scaling": "weak", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
-            "config": {"workload": "CKKS HMult+Relin, N=2^16, L=16, alpha=4, dnum=4, batch=1 ciphertext pair per step",
-                       "issue": f"steps go through pfhe_multiply_and_relin_batch, {lib.pfhe_engine_lanes(ctx._h)} "
-                                "independent ops in flight (lanes); single_op_ms = one op at a time",
-                       "l2": f"inputs rotate over {N_PAIRS} resident pairs (256 MiB per GPU) > 126 MB L2",
-                       "sharding": "independent ciphertexts per rank, shared key, no data-path collective"},
-            "e2e": {"value": e2e_steps * world / (e2e_ms * 1e-3), "unit": "HE-ops/s",
-                    "h2d_bytes_per_step": 2 * words * 8, "d2h_bytes_per_step": words * 8,
-                    "wall_ms": wall_ms},
-            "single_op_ms": lat_ms, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof, "cpu_baseline": cb,
+            "scaling": "strong", "vs_baseline": None, "dtype": "u64", "data": "synthetic",
+            "config": {"workload": workload_name(B),
+                       "batch": B, "pairs_per_rank": hi - lo,
+                       "issue": f"each rank issues its block through pfhe_multiply_and_relin_batch in calls of {args.chunk} "
+                                f"ops, {lib.pfhe_engine_lanes(ctx._h)} independent ops in flight (lanes); "
+                                "single_op_ms = one op at a time (BASELINE configs[1])",
+                       "l2": f"every pair is distinct: {(hi - lo) * 48} MiB of operands + results per rank per step, far "
+                             "beyond the 126 MB L2",
+                       "sharding": "value: every rank's block resident in its own HBM, no data-path collective; "
+                                   "scatter_gather: the batch is moved with NCCL send/recv inside the timed region",
+                       "e2e": f"every rank streams its block from / to its own pinned host buffers, cycling {e2e_pairs} "
+                              f"pinned pairs ({e2e_pairs * 48} MiB), {e2e_steps} steps"},
+            "e2e": {"value": e2e_steps * B / (e2e_ms * 1e-3), "unit": "HE-ops/s",
+                    "h2d_bytes_per_step": B * in_words * 8, "d2h_bytes_per_step": B * out_words * 8,
+                    "steps": e2e_steps, "wall_ms": wall_ms,
+                    "copy_only_ops_per_s": copy_ops * world / (copy_ms * 1e-3),
+                    "copy_only_gbs": copy_ops * world * (in_words + out_words) * 8 / (copy_ms * 1e-3) / 1e9},
+            "scatter_gather": sg,
+            "single_op_ms": lat_ms, "gpu_launches": int(launches), "clocks": clocks, "roofline": roof,
+            "roofline_inner_prod": roof_ip, "cpu_baseline": cb, "extra": extra,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def extra_configs(pf, lib, check, torch, dev):
+    """BASELINE.json configs[2] and configs[3] on one GPU, device resident, CUDA events (not the headline metric)."""
+    out = {}
+    try:
+        sys.path.insert(0, os.path.join(ROOT, "tools"))
+        import extra_bench
+        out = extra_bench.run(pf, lib, check, torch, dev)
+    except Exception as e:   # the headline line must not die on an extra
+        out = {"error": f"{type(e).__name__}: {e}"}
+    return out
 
 
 if __name__ == "__main__":
