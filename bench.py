@@ -226,6 +226,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[3] lines")
     ap.add_argument("--no-exchange", action="store_true", help="skip the scatter/gather legs")
+    ap.add_argument("--peer", action="store_true", help="also run the zero-copy leg (kernels address rank 0's HBM)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -370,24 +371,68 @@ def main():
     # ---- scatter / gather over NVLink inside the timed region -------------------------------------------------
     sg = None
     if world > 1 and not args.no_exchange:
+        from phantom_fhe_b200.shard import PullExchange, peer_view
         sg = {}
         sg_steps = args.steps
-        for kind in ("rooted", "spread"):
-            if kind == "rooted":
-                plan = ExchangePlan.rooted(B, world, args.chunk, 0)
-                ex = Exchange(plan, rank, store_in if rank == 0 else store_in[:0], store_out if rank == 0 else store_out[:0], dist)
-            else:
-                plan = ExchangePlan.spread(B, world, args.chunk)
-                ex = Exchange(plan, rank, own_in, own_out, dist)
-            ms = timed_passes(ex, kind, 2, sg_steps)
+        empty_in, empty_out = store_in[:0], store_out[:0]
+
+        def record(name, plan, ms, extra=None):
             sent, recv = plan.bytes_moved(0, in_words * 8, out_words * 8)
-            sg[kind] = {"value": sg_steps * B / (ms * 1e-3), "unit": "HE-ops/s", "ms_per_step": ms / sg_steps,
+            sg[name] = {"value": sg_steps * B / (ms * 1e-3), "unit": "HE-ops/s", "ms_per_step": ms / sg_steps,
                         "steps": sg_steps, "rank0_sent_bytes_per_step": sent, "rank0_recv_bytes_per_step": recv,
                         "rank0_egress_gbs": sent * sg_steps / (ms * 1e-3) / 1e9,
                         "vs_compute_only": (sg_steps / ms) / (args.steps / dev_ms)}
+            sg[name].update(extra or {})
+
+        plans = {"rooted": ExchangePlan.rooted(B, world, args.chunk, 0), "spread": ExchangePlan.spread(B, world, args.chunk)}
+        # (1) NCCL: grouped ncclSend / ncclRecv per tick, two-sided
+        for kind, plan in plans.items():
+            if kind == "rooted":
+                ex = Exchange(plan, rank, store_in if rank == 0 else empty_in, store_out if rank == 0 else empty_out, dist)
+            else:
+                ex = Exchange(plan, rank, own_in, own_out, dist)
+            record(f"{kind}_nccl", plan, timed_passes(ex, kind + "_nccl", 2, sg_steps))
             del ex
-        sg["transport"] = "torch.distributed batch_isend_irecv (ncclSend/ncclRecv groups), one group per tick of " \
-                          f"{args.chunk} pairs, double-buffered staging, overlapped with the arithmetic"
+        # (2) one-sided over CUDA IPC mappings of the home storage: pulls / pushes by the copy engines
+        maps = []
+        try:
+            root_in, m = peer_view(store_in if rank == 0 else None, 0, rank, dist, dev)
+            maps.append(m)
+            root_out, m = peer_view(store_out if rank == 0 else None, 0, rank, dist, dev)
+            maps.append(m)
+            homes_in, homes_out = [None] * world, [None] * world
+            for r in range(world):
+                homes_in[r], m = peer_view(own_in if rank == r else None, r, rank, dist, dev)
+                maps.append(m)
+                homes_out[r], m = peer_view(own_out if rank == r else None, r, rank, dist, dev)
+                maps.append(m)
+            r_in = [root_in if r == 0 else (empty_in if r == rank else None) for r in range(world)]
+            r_out = [root_out if r == 0 else (empty_out if r == rank else None) for r in range(world)]
+            record("rooted_pull", plans["rooted"], timed_passes(PullExchange(plans["rooted"], rank, r_in, r_out), "rooted_pull", 2, sg_steps))
+            record("spread_pull", plans["spread"], timed_passes(PullExchange(plans["spread"], rank, homes_in, homes_out), "spread_pull", 2, sg_steps))
+            if args.peer:
+                # (3) zero-copy: the kernels themselves address rank 0's HBM (no staging at all)
+                ex = Exchange(ExchangePlan.local(B, world, args.chunk), rank, root_in[lo:hi], root_out[lo:hi], dist)
+                ms = timed_passes(ex, "peer", 2, sg_steps)
+                remote = B - (shard_range(B, 0, world)[1] - shard_range(B, 0, world)[0])
+                sg["rooted_zero_copy"] = {
+                    "value": sg_steps * B / (ms * 1e-3), "unit": "HE-ops/s", "ms_per_step": ms / sg_steps, "steps": sg_steps,
+                    "vs_compute_only": (sg_steps / ms) / (args.steps / dev_ms),
+                    "rank0_egress_gbs": remote * 3 * words * 8 * sg_steps / (ms * 1e-3) / 1e9,
+                    "note": "kernels load operands from / store results to rank 0's HBM: a1, b1 are read by the first inverse "
+                            "pass and all four polynomials by the last epilogue (48 MiB over NVLink per remote op)"}
+                del ex
+            del root_in, root_out, homes_in, homes_out, r_in, r_out
+        except Exception as e:   # IPC mapping unavailable: the NCCL legs stand
+            sg["pull_error"] = f"{type(e).__name__}: {e}"
+        for mp in maps:
+            if mp is not None:
+                mp.close()
+        sg["transport"] = {
+            "nccl": "torch.distributed batch_isend_irecv (ncclSend/ncclRecv groups), one group per tick of "
+                    f"{args.chunk} pairs, double-buffered staging, overlapped with the arithmetic",
+            "pull": "home storage of every rank mapped into the others (CUDA IPC over NVLink); the computing rank pulls "
+                    "operands / pushes results with cudaMemcpyAsync on side streams (copy engines), double-buffered"}
         sg["nvlink_peak_gbs_per_direction"] = 900.0
 
     # ---- end to end from pinned host memory ----------------------------------------------------------------

@@ -306,6 +306,20 @@ int pfhe_rescale_host(pfhe_engine *e, size_t chain_index, const uint64_t *h_encr
 int pfhe_ntt_forward_host(pfhe_engine *e, const uint64_t *h_in, uint64_t *h_out, size_t coeff_modulus_size,
                           size_t start_modulus_idx, void *stream);
 
+/* Multi-GPU batches (the reference is single-device): lets the kernels of the calling thread's current
+ * device dereference memory of `peer_device` over NVLink (cudaDeviceEnablePeerAccess; already enabled is not an error),
+ * so that operand / destination pointers of the entry points above may point into another GPU's HBM of the same node
+ * (CUDA IPC mappings of another rank's buffers included).  PFHE_ERR_UNSUPPORTED if the devices are not peers. */
+int pfhe_enable_peer_access(int peer_device);
+/* Zero-copy batches across the ranks of one node (one process per GPU): the owner of a device buffer exports it
+ * (cudaIpcGetMemHandle of the allocation that contains `device_ptr`; `handle_out` = 64 opaque bytes, `offset_out` =
+ * byte offset of device_ptr inside that allocation), another process maps it with its OWN device current
+ * (cudaIpcOpenMemHandle with lazy peer access: the mapping is addressable by that device's kernels over NVLink) and
+ * receives the address that corresponds to the exported pointer.  pfhe_ipc_close takes the address pfhe_ipc_open gave. */
+int pfhe_ipc_export(const void *device_ptr, unsigned char handle_out[64], uint64_t *offset_out);
+int pfhe_ipc_open(const unsigned char handle[64], uint64_t offset, void **mapped_out);
+int pfhe_ipc_close(void *mapped, uint64_t offset);
+
 /* number of kernel launches issued by this engine since creation (bench.py's gpu_launches) */
 uint64_t pfhe_launch_count(const pfhe_engine *e);
 

@@ -91,6 +91,10 @@ _sigs = {
     "pfhe_rescale_host": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_ntt_forward_host": (ctypes.c_int, [vp, vp, vp, sz, sz, vp]),
     "pfhe_launch_count": (ctypes.c_uint64, [vp]),
+    "pfhe_enable_peer_access": (ctypes.c_int, [ctypes.c_int]),
+    "pfhe_ipc_export": (ctypes.c_int, [vp, ctypes.c_char_p, u64p]),
+    "pfhe_ipc_open": (ctypes.c_int, [ctypes.c_char_p, ctypes.c_uint64, ctypes.POINTER(vp)]),
+    "pfhe_ipc_close": (ctypes.c_int, [vp, ctypes.c_uint64]),
 }
 for _name, (_res, _args) in _sigs.items():
     _f = getattr(lib, _name)   # AttributeError if the library does not export a declared symbol

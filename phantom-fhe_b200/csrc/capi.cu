@@ -94,6 +94,60 @@ int pfhe_dnum(const pfhe_engine *e, size_t chain_index) {
 }
 uint64_t pfhe_launch_count(const pfhe_engine *) { return g_launches.load(); }
 
+int pfhe_ipc_export(const void *device_ptr, unsigned char handle_out[64], uint64_t *offset_out) {
+    API_BEGIN
+    require(device_ptr && handle_out && offset_out, "null argument");
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "handle size");
+    // base of the allocation: the handle names the whole allocation, the mapping starts at its base
+    using RangeFn = int (*)(unsigned long long *, size_t *, unsigned long long);
+    void *fn = nullptr;
+    cudaDriverEntryPointQueryResult qr;
+    PFHE_CUDA(cudaGetDriverEntryPoint("cuMemGetAddressRange", &fn, cudaEnableDefault, &qr));
+    if (!fn || qr != cudaDriverEntryPointSuccess) throw std::logic_error("cuMemGetAddressRange is unavailable");
+    unsigned long long base = 0;
+    size_t size = 0;
+    if (reinterpret_cast<RangeFn>(fn)(&base, &size, (unsigned long long) (uintptr_t) device_ptr) != 0)
+        throw std::invalid_argument("not a device allocation");
+    cudaIpcMemHandle_t h;
+    PFHE_CUDA(cudaIpcGetMemHandle(&h, reinterpret_cast<void *>((uintptr_t) base)));
+    std::memcpy(handle_out, &h, 64);
+    *offset_out = (uint64_t) ((uintptr_t) device_ptr - (uintptr_t) base);
+    API_END
+}
+
+int pfhe_ipc_open(const unsigned char handle[64], uint64_t offset, void **mapped_out) {
+    API_BEGIN
+    require(handle && mapped_out, "null argument");
+    cudaIpcMemHandle_t h;
+    std::memcpy(&h, handle, 64);
+    void *base = nullptr;
+    PFHE_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+    *mapped_out = static_cast<unsigned char *>(base) + offset;
+    API_END
+}
+
+int pfhe_ipc_close(void *mapped, uint64_t offset) {
+    API_BEGIN
+    if (mapped) PFHE_CUDA(cudaIpcCloseMemHandle(static_cast<unsigned char *>(mapped) - offset));
+    API_END
+}
+
+int pfhe_enable_peer_access(int peer_device) {
+    API_BEGIN
+    int dev = 0, can = 0;
+    PFHE_CUDA(cudaGetDevice(&dev));
+    if (peer_device == dev) return PFHE_OK;
+    PFHE_CUDA(cudaDeviceCanAccessPeer(&can, dev, peer_device));
+    if (!can) {
+        g_error = "devices are not peers";
+        return PFHE_ERR_UNSUPPORTED;
+    }
+    const cudaError_t ce = cudaDeviceEnablePeerAccess(peer_device, 0);
+    if (ce == cudaErrorPeerAccessAlreadyEnabled) cudaGetLastError();   // clear the sticky-less error
+    else if (ce != cudaSuccess) throw CudaError(ce, "cudaDeviceEnablePeerAccess");
+    API_END
+}
+
 int pfhe_galois_elt_from_step(int step, uint64_t n, uint32_t *elt_out) {
     API_BEGIN
     // get_elt_from_step, include/galois.cuh:16-49

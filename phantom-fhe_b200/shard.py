@@ -40,6 +40,50 @@ def max_over_ranks(value, dist=None, device=None):
     return float(t.item())
 
 
+class _Mapped:
+    """device memory of another rank mapped into this process (pfhe_ipc_open); exposes __cuda_array_interface__"""
+
+    def __init__(self, ptr, offset, shape):
+        self.ptr, self.offset = ptr, offset
+        self.__cuda_array_interface__ = {"shape": tuple(shape), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+    def close(self):
+        from ._lib import lib
+        if self.ptr:
+            lib.pfhe_ipc_close(self.ptr, self.offset)
+            self.ptr = 0
+
+
+def peer_view(tensor, src, rank, dist, device):
+    """A tensor on every rank that aliases rank `src`'s contiguous int64 `tensor` (CUDA IPC mapping of the allocation,
+    opened with the importing rank's own device current so that its kernels address the owner's HBM over NVLink):
+    kernels of the other ranks read their operands from, and write their results to, the owner's memory directly --
+    no staging copy, no communication kernel.  `tensor` is only looked at on `src`.  Returns (view, mapping); keep the
+    mapping alive while the view is in use and close() it afterwards.  The caller orders accesses across ranks
+    (barrier + synchronize around a pass)."""
+    import ctypes
+    import torch
+    from ._lib import lib, check
+    box = [None]
+    if rank == src:
+        if tensor.dtype != torch.int64 or not tensor.is_contiguous():
+            raise ValueError("peer_view exports contiguous int64 tensors")
+        handle = ctypes.create_string_buffer(64)
+        offset = ctypes.c_uint64()
+        check(lib.pfhe_ipc_export(ctypes.c_void_p(tensor.data_ptr()), handle, ctypes.byref(offset)))
+        box[0] = (handle.raw, int(offset.value), tuple(tensor.shape))
+    dist.broadcast_object_list(box, src)
+    if rank == src:
+        return tensor, None
+    raw, offset, shape = box[0]
+    mapped = ctypes.c_void_p()
+    with torch.cuda.device(device):
+        check(lib.pfhe_ipc_open(raw, offset, ctypes.byref(mapped)))
+        m = _Mapped(mapped.value, offset, shape)
+        view = torch.as_tensor(m, device=device)
+    return view, m
+
+
 @dataclass
 class Piece:
     """a run of consecutive units [lo, hi) (global ids) that live on rank `home` and are computed by one rank in one tick"""
@@ -250,3 +294,78 @@ class Exchange:
         for works in pending.values():
             for w in works:
                 w.wait()
+
+
+class PullExchange(Exchange):
+    """One-sided form of the same pipeline for ranks that can address each other's home storage (peer_view mappings of
+    one NVLink node): the computing rank PULLS the operands of tick t+1 into its staging slot and PUSHES the results of
+    tick t-1 back with plain asynchronous copies (copy engines: no communication kernel competes with the arithmetic
+    for SMs, no rendezvous with the owner) while it computes tick t.  homes_in / homes_out: per rank, that rank's home
+    storage as addressable from here (own tensors for `rank`, mappings for the others; entries of ranks this rank never
+    touches may be None).  The caller brackets a pass with a barrier on both sides (operands must be final before, results
+    are visible to their owners after)."""
+
+    def __init__(self, plan, rank, homes_in, homes_out):
+        super().__init__(plan, rank, homes_in[rank], homes_out[rank], dist=_NoDist if plan.world > 1 else None)
+        self.homes_in, self.homes_out = homes_in, homes_out
+        t = self.torch
+        self.cuda = homes_in[rank].is_cuda
+        if self.cuda and self.stage_in:
+            self.s_in, self.s_out = t.cuda.Stream(), t.cuda.Stream()
+            self.ev_in = [t.cuda.Event() for _ in range(2)]
+            self.ev_comp = [t.cuda.Event() for _ in range(2)]
+            self.ev_out = [t.cuda.Event() for _ in range(2)]
+
+    def run(self, compute):
+        t = self.torch
+        plan, me = self.plan, self.rank
+        mine = plan.ticks[me]
+        staged = self.cuda and bool(self.stage_in)
+        if staged:
+            cur = t.cuda.current_stream()
+            self.s_in.wait_stream(cur)
+            self.s_out.wait_stream(cur)
+        used = set()
+        for u, tick in enumerate(mine):
+            slot = u % 2
+            remote = [p for p in tick if p.home != me]
+            if remote:
+                if staged:
+                    if u >= 2 and slot in used:
+                        self.s_in.wait_event(self.ev_comp[slot])      # compute(u - 2) has read this slot
+                    with t.cuda.stream(self.s_in):
+                        for p in remote:
+                            lo = plan.home[p.home][0]
+                            self.stage_in[slot][p.off:p.off + len(p)].copy_(self.homes_in[p.home][p.lo - lo:p.hi - lo],
+                                                                          non_blocking=True)
+                        self.ev_in[slot].record(self.s_in)
+                    cur.wait_event(self.ev_in[slot])
+                    if slot in used:
+                        cur.wait_event(self.ev_out[slot])             # results of tick u - 2 have left this slot
+                else:
+                    for p in remote:
+                        lo = plan.home[p.home][0]
+                        self.stage_in[slot][p.off:p.off + len(p)].copy_(self.homes_in[p.home][p.lo - lo:p.hi - lo])
+            compute(u, self.tick_views(u))
+            if remote:
+                if staged:
+                    self.ev_comp[slot].record(cur)
+                    self.s_out.wait_event(self.ev_comp[slot])
+                    with t.cuda.stream(self.s_out):
+                        for p in remote:
+                            lo = plan.home[p.home][0]
+                            self.homes_out[p.home][p.lo - lo:p.hi - lo].copy_(self.stage_out[slot][p.off:p.off + len(p)],
+                                                                              non_blocking=True)
+                        self.ev_out[slot].record(self.s_out)
+                    used.add(slot)
+                else:
+                    for p in remote:
+                        lo = plan.home[p.home][0]
+                        self.homes_out[p.home][p.lo - lo:p.hi - lo].copy_(self.stage_out[slot][p.off:p.off + len(p)])
+        if staged:
+            cur.wait_stream(self.s_out)
+            cur.wait_stream(self.s_in)
+
+
+class _NoDist:
+    """placeholder: PullExchange never posts a message"""

@@ -122,3 +122,36 @@ def test_exchange_over_gloo(tmp_path, world):
     outs = [p.communicate(timeout=300)[0] for p in procs]
     for p, o in zip(procs, outs):
         assert p.returncode == 0, o
+
+
+@pytest.mark.parametrize("world", [1, 2, 3, 8])
+def test_pull_exchange_single_process(world):
+    """the one-sided pipeline (PullExchange): ranks run one after another against shared home storage"""
+    import torch
+    from phantom_fhe_b200.shard import ExchangePlan, PullExchange
+    iw, ow = 10, 5
+
+    def unit_in(i):
+        return torch.arange(iw, dtype=torch.int64) + 1000 * i
+
+    def compute(t, views):
+        for vin, vout in views:
+            vout.copy_(vin[:, :ow] * 7 + vin[:, ow:] + 1)
+
+    for total in (0, 3, 16, 37):
+        for chunk in (1, 4, 6):
+            for kind in ("rooted", "spread", "local"):
+                plan = getattr(ExchangePlan, kind)(total, world, chunk)
+                homes_in, homes_out = [], []
+                for r in range(world):
+                    lo, hi = plan.home[r]
+                    homes_in.append(torch.stack([unit_in(i) for i in range(lo, hi)]) if hi > lo
+                                    else torch.zeros((0, iw), dtype=torch.int64))
+                    homes_out.append(torch.full((hi - lo, ow), -1, dtype=torch.int64))
+                for r in range(world):
+                    PullExchange(plan, r, homes_in, homes_out).run(compute)
+                for r in range(world):
+                    lo, hi = plan.home[r]
+                    for i in range(lo, hi):
+                        v = unit_in(i)
+                        assert torch.equal(homes_out[r][i - lo], v[:ow] * 7 + v[ow:] + 1), (kind, total, chunk, i)
