@@ -63,6 +63,10 @@ uint64_t pfhe_poly_degree(const pfhe_engine *e);
 int pfhe_size_QP(const pfhe_engine *e);
 int pfhe_size_P(const pfhe_engine *e);
 int pfhe_dnum(const pfhe_engine *e, size_t chain_index); /* beta at that level, src/rns.cu:152 */
+/* The engine's Galois elements in key order (PhantomGaloisTool::galois_elts(), include/galois.cuh:140): the list given to
+ * pfhe_engine_create, or -- when that list was empty -- the reference's default get_elts_all() (src/galois.cu:41-65:
+ * 2N-1, then 5^(2^i) and 5^-(2^i) for i < log2(N)-1).  Writes at most `capacity` entries, returns the count (-1: no engine). */
+int pfhe_galois_elts(const pfhe_engine *e, uint32_t *elts_out, int capacity);
 /* get_elt_from_step (include/galois.cuh:16-49) */
 int pfhe_galois_elt_from_step(int step, uint64_t n, uint32_t *elt_out);
 

@@ -202,6 +202,10 @@ public:
                                    (int) parms.special_modulus_size(), parms.plain_modulus(), elts.empty() ? nullptr : elts.data(),
                                    (int) elts.size()));
         if (parms.scheme() == scheme_type::bfv) rethrow(pfhe_engine_set_mul_tech(engine_, (int) parms.mul_tech()));
+        // key order of the context: the given elements or the reference's default set (include/galois.cuh:84-89)
+        std::vector<uint32_t> effective((size_t) std::max(0, pfhe_galois_elts(engine_, nullptr, 0)));
+        pfhe_galois_elts(engine_, effective.data(), (int) effective.size());
+        parms_.set_galois_elts(effective);
     }
     PhantomContext(const PhantomContext &) = delete;
     PhantomContext &operator=(const PhantomContext &) = delete;
@@ -210,6 +214,14 @@ public:
     }
     pfhe_engine *engine() const { return engine_; }
     cudaStream_t stream() const { return stream_; }
+    // a ciphertext handed to the engine must have the shape its chain_index implies: the engine derives limb counts
+    // from the level, not from the buffer
+    template<class Ct>
+    void check(const Ct &ct) const {
+        if (ct.poly_modulus_degree() != poly_degree() || ct.chain_index() < 1 || ct.chain_index() > size_Q() ||
+            ct.coeff_modulus_size() != coeff_modulus_size(ct.chain_index()))
+            throw std::invalid_argument("ciphertext does not belong to this context");
+    }
     const EncryptionParameters &parms() const { return parms_; }
     size_t poly_degree() const { return parms_.poly_modulus_degree(); }
     size_t size_QP() const { return parms_.coeff_modulus().size(); }
@@ -286,9 +298,15 @@ public:
         detail::put_words(stream, data_, 0, data_.size());
     }
     void load(std::istream &stream) {   // ciphertext.h:192-213
-        adopt(detail::CipherHeader::read(stream));
+        const auto h = detail::CipherHeader::read(stream);
+        // refuse headers that cannot describe a ciphertext before sizing a device buffer from them
+        if (h.size > 64 || h.l > 16384 || h.n > (size_t(1) << 17) || (h.n & (h.n - 1)) != 0)
+            throw std::invalid_argument("ciphertext stream is not valid");
+        adopt(h);
         detail::get_words(stream, data_, size_ * coeff_modulus_size_ * poly_modulus_degree_);
     }
+    // the same, checked against the context the ciphertext is going to be used with: degree and limb count of its level
+    inline void load(const class PhantomContext &context, std::istream &stream);
     void save_symmetric(std::ostream &stream) const {   // ciphertext.h:216-245: c0 and the seed of c1
         if (is_asymmetric_ || seed_.size() != 64) throw std::runtime_error("Asymmetric ciphertext does not have seed.");
         if (size_ != 2) throw std::runtime_error("This method is only for 2-polynomial ciphertext.");
@@ -322,11 +340,18 @@ private:
     bool is_ntt_form_ = true, is_asymmetric_ = false;
     std::vector<uint8_t> seed_;
 };
+inline void PhantomCiphertext::load(const PhantomContext &context, std::istream &stream) {
+    load(stream);
+    context.check(*this);
+}
 inline void PhantomCiphertext::load_symmetric(const PhantomContext &context, std::istream &stream) {
     const auto h = detail::CipherHeader::read(stream);
     if (h.is_asymmetric) throw std::runtime_error("Asymmetric ciphertext does not have seed.");
     if (h.size != 2) throw std::runtime_error("This method is only for 2-polynomial ciphertext.");
-    if (h.l != context.coeff_modulus_size(context.get_first_index())) throw std::runtime_error("Only support ciphertext without modulus switching.");
+    if (h.l != context.coeff_modulus_size(context.get_first_index()) || h.chain_index != context.get_first_index())
+        throw std::runtime_error("Only support ciphertext without modulus switching.");
+    // the sampler below writes h.l limbs of the CONTEXT's degree: a stream of another degree must not size the buffer
+    if (h.n != context.poly_degree()) throw std::invalid_argument("ciphertext stream does not belong to this context");
     adopt(h);
     const size_t words = h.l * h.n;
     std::vector<uint64_t> c0(words);
@@ -370,6 +395,13 @@ public:
             detail::get_words(stream, d, h.size * h.l * h.n);
         }
         adopt(std::move(digits), n, size_QP);
+    }
+    // checked against the context: the key inner product walks dnum digit pointers of [2][size_QP][N] words each
+    template<class Ctx>
+    void load(const Ctx &context, std::istream &stream) {
+        load(stream);
+        if (digits_.size() != (size_t) pfhe_dnum(context.engine(), 1) || n_ != context.poly_degree() || size_QP_ != context.size_QP())
+            throw std::invalid_argument("relinearisation key stream does not belong to this context");
     }
 
 private:
@@ -735,6 +767,8 @@ inline void multiply_plain_inplace(const PhantomContext &context, PhantomCiphert
 
 // multiply_inplace (evaluate.cu:1029-1057): two-polynomial operands -> three polynomials
 inline void multiply_inplace(const PhantomContext &context, PhantomCiphertext &encrypted1, const PhantomCiphertext &encrypted2) {
+    context.check(encrypted1);
+    context.check(encrypted2);
     detail::require_form(context, encrypted1);
     detail::require_form(context, encrypted2);
     if (encrypted1.chain_index() != encrypted2.chain_index()) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
@@ -760,6 +794,7 @@ inline void multiply_inplace(const PhantomContext &context, PhantomCiphertext &e
 }
 // relinearize_inplace (evaluate.cu:1342-1374)
 inline void relinearize_inplace(const PhantomContext &context, PhantomCiphertext &encrypted, const PhantomRelinKey &relin_keys) {
+    context.check(encrypted);
     if (encrypted.size() != 3) throw std::invalid_argument("destination_size must be 3");
     detail::require_form(context, encrypted);
     const size_t words = encrypted.coeff_modulus_size() * encrypted.poly_modulus_degree();
@@ -780,6 +815,8 @@ inline void relinearize_inplace(const PhantomContext &context, PhantomCiphertext
 // multiply_and_relin_inplace (evaluate.cu:1061-1104): the fused tensor + key switch of the engine
 inline void multiply_and_relin_inplace(const PhantomContext &context, PhantomCiphertext &encrypted1, const PhantomCiphertext &encrypted2,
                                        const PhantomRelinKey &relin_keys) {
+    context.check(encrypted1);
+    context.check(encrypted2);
     detail::require_form(context, encrypted1);
     detail::require_form(context, encrypted2);
     if (encrypted1.chain_index() != encrypted2.chain_index()) throw std::invalid_argument("encrypted1 and encrypted2 parameter mismatch");
@@ -819,6 +856,7 @@ inline std::vector<int> naf(int step) {
 // apply_galois_inplace (evaluate.cu:1567-1630)
 inline void apply_galois_inplace(const PhantomContext &context, PhantomCiphertext &encrypted, uint32_t galois_elt,
                                  const PhantomGaloisKey &galois_keys) {
+    context.check(encrypted);
     if (encrypted.size() > 2) throw std::invalid_argument("encrypted size must be 2");
     const auto &elts = context.parms().galois_elts();
     const auto it = std::find(elts.begin(), elts.end(), galois_elt);
@@ -861,6 +899,7 @@ inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &enc
 }
 // hoisting_inplace (evaluate.cu:1670-1865): ct <- sum over the steps of rotate(ct, step), one shared mod-up and mod-down
 inline void hoisting_inplace(const PhantomContext &context, PhantomCiphertext &ct, const PhantomGaloisKey &glk, const std::vector<int> &steps) {
+    context.check(ct);
     if (ct.size() > 2) throw std::invalid_argument("ciphertext size must be 2");
     if (context.parms().scheme() == scheme_type::bfv) {
         // the engine's hoisted form is built for the NTT-form schemes; for BFV the sum is composed from the rotations
@@ -890,6 +929,7 @@ inline void hoisting_inplace(const PhantomContext &context, PhantomCiphertext &c
 }
 // rescale_to_next (evaluate.cu:1545-1565)
 inline PhantomCiphertext rescale_to_next(const PhantomContext &context, const PhantomCiphertext &encrypted) {
+    context.check(encrypted);
     if (context.parms().scheme() != scheme_type::ckks) throw std::invalid_argument("unsupported scheme");
     if (encrypted.chain_index() == context.size_Q()) throw std::invalid_argument("end of modulus switching chain reached");
     PhantomCiphertext dst;   // a fresh object, like the reference's `destination`: only scale and form are set below
@@ -901,6 +941,7 @@ inline PhantomCiphertext rescale_to_next(const PhantomContext &context, const Ph
 }
 // mod_switch_to_next (evaluate.cu:1505-1543)
 inline PhantomCiphertext mod_switch_to_next(const PhantomContext &context, const PhantomCiphertext &encrypted) {
+    context.check(encrypted);
     if (encrypted.chain_index() == context.size_Q()) throw std::invalid_argument("end of modulus switching chain reached");
     detail::require_form(context, encrypted);
     PhantomCiphertext dst;   // fresh: noiseScaleDeg and is_asymmetric restart at their defaults (evaluate.cu:1527-1541)

@@ -29,6 +29,7 @@ _sigs = {
     "pfhe_size_QP": (ctypes.c_int, [vp]),
     "pfhe_size_P": (ctypes.c_int, [vp]),
     "pfhe_dnum": (ctypes.c_int, [vp, sz]),
+    "pfhe_galois_elts": (ctypes.c_int, [vp, u32p, ctypes.c_int]),
     "pfhe_galois_elt_from_step": (ctypes.c_int, [ctypes.c_int, ctypes.c_uint64, u32p]),
     "pfhe_ntt_forward_inplace": (ctypes.c_int, [vp, vp, sz, sz, vp]),
     "pfhe_ntt_backward_inplace": (ctypes.c_int, [vp, vp, sz, sz, vp]),

@@ -7,6 +7,7 @@ PhantomGaloisKey (include/secretkey.h:99-219) and the evaluator free functions (
 Where the reference throws std::invalid_argument this raises ValueError with the same message;
 std::logic_error -> RuntimeError.  All arithmetic happens in libpfhe_b200.so on the current CUDA stream.
 """
+import copy
 import ctypes
 import enum
 import math
@@ -135,6 +136,13 @@ class PhantomContext:
         check(lib.pfhe_engine_create(ctypes.byref(handle), int(params.scheme), self.poly_degree, primes, self.size_QP,
                                      self.size_P, params.plain_modulus, elts, len(params.galois_elts)))
         self._h = handle
+        # the key order of the context: the given elements, or the reference's default set when none were given
+        # (PhantomGaloisTool, include/galois.cuh:84-89); the mirror's key generation and lookups index this list
+        cnt = lib.pfhe_galois_elts(handle, None, 0)
+        buf = (ctypes.c_uint32 * max(1, cnt))()
+        lib.pfhe_galois_elts(handle, buf, cnt)
+        self.parms = copy.copy(params)
+        self.parms.galois_elts = [int(buf[i]) for i in range(cnt)]
         if self.scheme == scheme_type.bfv:
             check(lib.pfhe_engine_set_mul_tech(handle, int(params.mul_tech)))
         self.device = torch.device("cuda", torch.cuda.current_device())
@@ -221,7 +229,8 @@ class PhantomCiphertext:
         (sample_uniform_poly), and brought to coefficient form for BFV.  First data level only, like the reference."""
         c0, seed, h = serial.read_ciphertext_symmetric(stream)
         l, n = c0.shape
-        if n != context.poly_degree or l != context.coeff_modulus_size(context.get_first_index()):
+        if (n != context.poly_degree or l != context.coeff_modulus_size(context.get_first_index())
+                or h["chain_index"] != context.get_first_index()):
             raise RuntimeError("Only support ciphertext without modulus switching.")
         data = torch.empty((2, l, n), dtype=torch.int64, device=context.device)
         data[0].copy_(_to_dev(c0, context.device))
@@ -548,7 +557,10 @@ class PhantomRelinKey:
 
     @classmethod
     def load(cls, context, stream):
-        return cls(context, serial.read_relin_key(stream))
+        digits = serial.read_relin_key(stream)
+        if len(digits) != context.dnum(1):   # the inner product walks dnum digit pointers
+            raise ValueError("relinearisation key stream does not belong to this context")
+        return cls(context, digits)
 
 
 class PhantomGaloisKey:
@@ -607,7 +619,7 @@ def multiply_inplace(context, encrypted1, encrypted2):
     s1, s2 = encrypted1.size(), encrypted2.size()
     dst = torch.empty((s1 + s2 - 1, l, n), dtype=torch.int64, device=encrypted1.data.device)
     a, b = encrypted1.data, encrypted2.data
-    if _leveled(context):   # bfv_multiply_hps, leveled branch (evaluate.cu:680-690, 798-800)
+    if _leveled(context) and encrypted1.chain_index == 1:   # bfv_multiply_hps, leveled branch (evaluate.cu:680-690, 798-800)
         if s1 != 2 or s2 != 2:
             raise RuntimeError("dest_size must be 3 when computing BFV multiplication using HPS")
         deg = max(encrypted1.noise_scale_deg, encrypted2.noise_scale_deg)
@@ -636,7 +648,7 @@ def relinearize_inplace(context, encrypted, relin_keys):
     if encrypted.size() != 3:
         raise ValueError("destination_size must be 3")
     _require_ntt(context, encrypted)
-    if _leveled(context):   # keyswitch_inplace, leveled branch (eval_key_switch.cu:113-123): is_relin -> not a key switch
+    if _leveled(context) and encrypted.chain_index == 1:   # keyswitch_inplace, leveled branch (eval_key_switch.cu:113-123)
         drop = _levels_to_drop(context, encrypted.noise_scale_deg - 1, False, encrypted.is_asymmetric)
         check(lib.pfhe_keyswitch_leveled_inplace(context._h, _ptr(encrypted.data), _ptr(encrypted.data[2]),
                                                  relin_keys.public_keys_ptr(), drop, _stream()))
@@ -658,8 +670,11 @@ def multiply_and_relin_inplace(context, encrypted1, encrypted2, relin_keys):
         raise ValueError("scale mismatch")
     if encrypted1.size() != encrypted2.size():
         raise ValueError("poly number mismatch")
-    dst = torch.empty_like(encrypted1.data)
-    if _leveled(context):   # bfv_mul_relin_hps, leveled branch (evaluate.cu:845-856, 962-964)
+    if encrypted1.size() != 2:   # the reference's relinearisation step refuses anything but a 3-polynomial product
+        raise ValueError("destination_size must be 3")
+    l, n = encrypted1.coeff_modulus_size(), context.poly_degree
+    dst = torch.empty((2, l, n), dtype=torch.int64, device=encrypted1.data.device)
+    if _leveled(context) and encrypted1.chain_index == 1:   # bfv_mul_relin_hps, leveled branch (evaluate.cu:845-856, 962-964)
         deg = max(encrypted1.noise_scale_deg, encrypted2.noise_scale_deg)
         drop = _levels_to_drop(context, deg - 1, False, encrypted1.is_asymmetric)
         check(lib.pfhe_multiply_and_relin_leveled(context._h, _ptr(encrypted1.data), _ptr(encrypted2.data), _ptr(dst),
@@ -685,6 +700,12 @@ def multiply_and_relin_batch(context, encrypted1, encrypted2, relin_keys):
         _require_ntt(context, b)
         if a.chain_index != ci or b.chain_index != ci:
             raise ValueError("encrypted1 and encrypted2 parameter mismatch")
+        if a.is_ntt_form != b.is_ntt_form:
+            raise ValueError("NTT form mismatch")
+        if not _are_close(a.scale, b.scale):
+            raise ValueError("scale mismatch")
+        if a.size() != 2 or b.size() != 2:
+            raise ValueError("destination_size must be 3")
     dst = [torch.empty_like(a.data) for a in encrypted1]
     n = len(dst)
     arr = ctypes.c_void_p * n

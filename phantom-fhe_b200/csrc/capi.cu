@@ -94,6 +94,14 @@ int pfhe_dnum(const pfhe_engine *e, size_t chain_index) {
 }
 uint64_t pfhe_launch_count(const pfhe_engine *) { return g_launches.load(); }
 
+int pfhe_galois_elts(const pfhe_engine *e, uint32_t *elts_out, int capacity) {
+    if (!e) return -1;
+    const auto &g = e->impl.galois_elts();
+    if (elts_out)
+        for (int i = 0; i < capacity && i < (int) g.size(); i++) elts_out[i] = g[i];
+    return (int) g.size();
+}
+
 int pfhe_ipc_export(const void *device_ptr, unsigned char handle_out[64], uint64_t *offset_out) {
     API_BEGIN
     require(device_ptr && handle_out && offset_out, "null argument");
@@ -266,7 +274,7 @@ int pfhe_negate_rns_poly(pfhe_engine *e, const uint64_t *a, uint64_t *r, size_t 
 int pfhe_modup(pfhe_engine *e, size_t chain_index, uint64_t *dst, const uint64_t *cks, void *stream) {
     API_BEGIN
     const int l = e->impl.limbs_at(chain_index);
-    e->impl.modup(l, U(dst), U(cks), e->impl.ws().t_cks.p, S(stream));
+    e->impl.modup(l, U(dst), U(cks), e->impl.ws(S(stream)).t_cks.p, S(stream));
     API_END
 }
 int pfhe_key_switch_inner_prod(pfhe_engine *e, size_t chain_index, uint64_t *p_cx, const uint64_t *p_t_mod_up,
@@ -279,7 +287,7 @@ int pfhe_key_switch_inner_prod(pfhe_engine *e, size_t chain_index, uint64_t *p_c
 int pfhe_moddown_from_ntt(pfhe_engine *e, size_t chain_index, uint64_t *ct_i, uint64_t *cx_i, void *stream) {
     API_BEGIN
     const int l = e->impl.limbs_at(chain_index);
-    if (e->impl.scheme() == Scheme::ckks) e->impl.moddown(l, U(ct_i), U(cx_i), e->impl.ws().delta.p, 1, nullptr, 0u, S(stream));
+    if (e->impl.scheme() == Scheme::ckks) e->impl.moddown(l, U(ct_i), U(cx_i), e->impl.ws(S(stream)).delta.p, 1, nullptr, 0u, S(stream));
     else e->impl.moddown_generic(l, U(ct_i), U(cx_i), 1, nullptr, 0u, S(stream));
     API_END
 }
@@ -601,7 +609,7 @@ int pfhe_multiply_and_relin_host(pfhe_engine *e, size_t chain_index, const uint6
     API_BEGIN
     const int l = e->impl.limbs_at(chain_index);
     const size_t words = (size_t) 2 * l * e->impl.n();
-    auto &io = e->impl.host_io(2 * words);
+    auto &io = e->impl.host_io(2 * words, S(stream));
     PFHE_CUDA(cudaMemcpyAsync(io.p, h1, words * 8, cudaMemcpyHostToDevice, S(stream)));
     PFHE_CUDA(cudaMemcpyAsync(io.p + words, h2, words * 8, cudaMemcpyHostToDevice, S(stream)));
     e->impl.multiply_relin(l, io.p, io.p, io.p + words, K(rlk), S(stream));
@@ -644,7 +652,7 @@ int pfhe_rotate_host(pfhe_engine *e, size_t chain_index, const uint64_t *h, int 
     const size_t words = (size_t) 2 * l * e->impl.n();
     uint32_t elt = 0;
     if (pfhe_galois_elt_from_step(step, e->impl.n(), &elt) != PFHE_OK) throw std::invalid_argument(g_error);
-    auto &io = e->impl.host_io(words);
+    auto &io = e->impl.host_io(words, S(stream));
     PFHE_CUDA(cudaMemcpyAsync(io.p, h, words * 8, cudaMemcpyHostToDevice, S(stream)));
     e->impl.apply_galois(l, io.p, elt, K(glk), S(stream));
     PFHE_CUDA(cudaMemcpyAsync(hout, io.p, words * 8, cudaMemcpyDeviceToHost, S(stream)));
@@ -656,7 +664,7 @@ int pfhe_rescale_host(pfhe_engine *e, size_t chain_index, const uint64_t *h, siz
     require(e->impl.scheme() == Scheme::ckks, "unsupported scheme");
     const int l = e->impl.limbs_at(chain_index);
     const size_t in_words = size * l * e->impl.n(), out_words = size * (l - 1) * e->impl.n();
-    auto &io = e->impl.host_io(in_words + out_words);
+    auto &io = e->impl.host_io(in_words + out_words, S(stream));
     PFHE_CUDA(cudaMemcpyAsync(io.p, h, in_words * 8, cudaMemcpyHostToDevice, S(stream)));
     e->impl.rescale(l, io.p + in_words, io.p, (int) size, S(stream));
     PFHE_CUDA(cudaMemcpyAsync(hout, io.p + in_words, out_words * 8, cudaMemcpyDeviceToHost, S(stream)));
@@ -667,7 +675,7 @@ int pfhe_ntt_forward_host(pfhe_engine *e, const uint64_t *hin, uint64_t *hout, s
     API_BEGIN
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
     const size_t words = count * e->impl.n();
-    auto &io = e->impl.host_io(words);
+    auto &io = e->impl.host_io(words, S(stream));
     PFHE_CUDA(cudaMemcpyAsync(io.p, hin, words * 8, cudaMemcpyHostToDevice, S(stream)));
     e->impl.ntt_fwd_rows_range(io.p, (int) count, (int) start, S(stream));
     PFHE_CUDA(cudaMemcpyAsync(hout, io.p, words * 8, cudaMemcpyDeviceToHost, S(stream)));

@@ -95,9 +95,23 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
     const size_t alpha = std::max(size_P_, 1);
     const size_t beta_max = (size_Q_ + alpha - 1) / alpha;
     (void) beta_max;
-    alloc_workspace(ws_);
     if (const char *e = std::getenv("PFHE_LANES")) set_lanes(std::atoi(e));
 
+    // no Galois elements given: all power-of-two steps in both directions plus the conjugation element, which is what
+    // the NAF decomposition of rotate_inplace needs (PhantomGaloisTool::get_elts_all, reference src/galois.cu:41-65,
+    // substituted in include/galois.cuh:84-89)
+    if (galois_elts_.empty()) {
+        const uint32_t m = (uint32_t) (2 * n_);
+        galois_elts_.push_back(m - 1);
+        uint64_t pos = 5, neg = 1;
+        while ((neg * 5) % m != 1) neg += 2;   // 5^-1 mod 2N
+        for (int i = 0; i < logn_ - 1; i++) {
+            galois_elts_.push_back((uint32_t) pos);
+            pos = (pos * pos) & (m - 1);
+            galois_elts_.push_back((uint32_t) neg);
+            neg = (neg * neg) & (m - 1);
+        }
+    }
     // Galois permutation tables (reference include/galois.cuh:98-113)
     d_perm_.resize(galois_elts_.size());
     std::vector<uint32_t> table(n_);
@@ -128,49 +142,63 @@ void Engine::set_lanes(int k) {
     n_lanes_ = k;
 }
 
-// exchange the engine's active workspace / fork-join objects with those of lane k (k = 0: nothing to do)
-void Engine::swap_lane(int k) {
-    if (k == 0) return;
-    Lane &L = lane_[k];
-    std::swap(ws_, L.ws);
-    std::swap(s_side_, L.s_side);
-    std::swap(ev_fork_, L.ev_fork);
-    std::swap(ev_join_, L.ev_join);
+static std::pair<uintptr_t, std::thread::id> stream_key(cudaStream_t st) {
+    // the legacy / per-thread handles name a different stream in every thread
+    const bool implicit = st == nullptr || st == cudaStreamLegacy || st == cudaStreamPerThread;
+    return {reinterpret_cast<uintptr_t>(st), implicit ? std::this_thread::get_id() : std::thread::id()};
 }
 
-// independent ops round-robin over the lanes: lane 0 is the caller's stream, lane k > 0 an internal stream with its own
-// workspace; forks from and joins back into `st`
+StreamCtx &Engine::sctx(cudaStream_t st) {
+    std::lock_guard<std::mutex> g(sctx_mu_);
+    auto &slot = sctx_[stream_key(st)];
+    if (!slot) {
+        slot = std::make_unique<StreamCtx>();
+        alloc_workspace(slot->ws);
+    }
+    return *slot;
+}
+
+StreamCtx::~StreamCtx() {
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (s_side) cudaStreamDestroy(s_side);
+    for (int i = 0; i < 2; i++) {
+        if (ev_in[i]) cudaEventDestroy(ev_in[i]);
+        if (ev_comp[i]) cudaEventDestroy(ev_comp[i]);
+        if (ev_out[i]) cudaEventDestroy(ev_out[i]);
+    }
+    if (s_in) cudaStreamDestroy(s_in);
+    if (s_out) cudaStreamDestroy(s_out);
+}
+
+// independent ops round-robin over the lanes: lane 0 is the caller's stream, lane k > 0 an internal stream (which gets
+// its own workspace like any other stream); forks from and joins back into `st`
 void Engine::run_lanes(size_t count, cudaStream_t st, const std::function<void(size_t, cudaStream_t)> &op) {
     const int L = (int) std::min<size_t>((size_t) n_lanes_, count);
     if (L <= 1) {
         for (size_t i = 0; i < count; i++) op(i, st);
         return;
     }
-    if (!lane_[0].ev_done) PFHE_CUDA(cudaEventCreateWithFlags(&lane_[0].ev_done, cudaEventDisableTiming));
-    for (int k = 1; k < L; k++) {
-        Lane &ln = lane_[k];
-        if (!ln.stream) {
-            PFHE_CUDA(cudaStreamCreateWithFlags(&ln.stream, cudaStreamNonBlocking));
-            PFHE_CUDA(cudaEventCreateWithFlags(&ln.ev_done, cudaEventDisableTiming));
-            alloc_workspace(ln.ws);
-        }
+    Lanes *ln;
+    {
+        std::lock_guard<std::mutex> g(sctx_mu_);
+        ln = &lanes_[stream_key(st)];
     }
-    PFHE_CUDA(cudaEventRecord(lane_[0].ev_done, st));
-    for (int k = 1; k < L; k++) PFHE_CUDA(cudaStreamWaitEvent(lane_[k].stream, lane_[0].ev_done, 0));
+    if (!ln->ev_done[0]) PFHE_CUDA(cudaEventCreateWithFlags(&ln->ev_done[0], cudaEventDisableTiming));
+    for (int k = 1; k < L; k++)
+        if (!ln->stream[k]) {
+            PFHE_CUDA(cudaStreamCreateWithFlags(&ln->stream[k], cudaStreamNonBlocking));
+            PFHE_CUDA(cudaEventCreateWithFlags(&ln->ev_done[k], cudaEventDisableTiming));
+        }
+    PFHE_CUDA(cudaEventRecord(ln->ev_done[0], st));
+    for (int k = 1; k < L; k++) PFHE_CUDA(cudaStreamWaitEvent(ln->stream[k], ln->ev_done[0], 0));
     for (size_t i = 0; i < count; i++) {
         const int k = (int) (i % (size_t) L);
-        swap_lane(k);
-        try {
-            op(i, k == 0 ? st : lane_[k].stream);
-        } catch (...) {
-            swap_lane(k);
-            throw;
-        }
-        swap_lane(k);
+        op(i, k == 0 ? st : ln->stream[k]);
     }
     for (int k = 1; k < L; k++) {
-        PFHE_CUDA(cudaEventRecord(lane_[k].ev_done, lane_[k].stream));
-        PFHE_CUDA(cudaStreamWaitEvent(st, lane_[k].ev_done, 0));
+        PFHE_CUDA(cudaEventRecord(ln->ev_done[k], ln->stream[k]));
+        PFHE_CUDA(cudaStreamWaitEvent(st, ln->ev_done[k], 0));
     }
 }
 
@@ -185,23 +213,13 @@ void Engine::apply_galois_batch(int l, u64 *const *ct, const uint32_t *elts, con
 }
 
 Engine::~Engine() {
-    for (Lane &ln : lane_) {
-        if (ln.ev_fork) cudaEventDestroy(ln.ev_fork);
-        if (ln.ev_join) cudaEventDestroy(ln.ev_join);
-        if (ln.ev_done) cudaEventDestroy(ln.ev_done);
-        if (ln.s_side) cudaStreamDestroy(ln.s_side);
-        if (ln.stream) cudaStreamDestroy(ln.stream);
-    }
-    if (ev_fork_) cudaEventDestroy(ev_fork_);
-    if (ev_join_) cudaEventDestroy(ev_join_);
-    if (s_side_) cudaStreamDestroy(s_side_);
-    for (int i = 0; i < 2; i++) {
-        if (ev_in_[i]) cudaEventDestroy(ev_in_[i]);
-        if (ev_comp_[i]) cudaEventDestroy(ev_comp_[i]);
-        if (ev_out_[i]) cudaEventDestroy(ev_out_[i]);
-    }
-    if (s_in_) cudaStreamDestroy(s_in_);
-    if (s_out_) cudaStreamDestroy(s_out_);
+    cudaDeviceSynchronize();
+    sctx_.clear();
+    for (auto &kv : lanes_)
+        for (int k = 0; k < 4; k++) {
+            if (kv.second.ev_done[k]) cudaEventDestroy(kv.second.ev_done[k]);
+            if (kv.second.stream[k]) cudaStreamDestroy(kv.second.stream[k]);
+        }
 }
 
 Tw Engine::make_tw_row(int row, u64 w) const {
@@ -344,6 +362,7 @@ int Engine::galois_index(uint32_t elt) const {
 
 const Level &Engine::level(int l) const {
     if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     auto &slot = const_cast<Engine *>(this)->levels_[l];
     if (!slot) const_cast<Engine *>(this)->build_level(l);
     return *slot;
@@ -733,6 +752,7 @@ void Engine::moddown(int l, u64 *out, u64 *cx, u64 *delta, int npoly, const u64 
 //   ->  [bconv | forward NTT | (cx - delta) P^-1 + addend]          9 kernels, no copies, no t_cks->t_mod_up pass
 void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts, const u64 *const *evk,
                              const u64 *addend, unsigned add_mask, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     const Level &lv = level(l);
     const int alpha = lv.alpha, m = lv.m;
     if (alpha == 0) throw std::logic_error("key switching needs special primes");
@@ -806,18 +826,21 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
     //    before the epilogue.
     const bool fork = overlap_;
     cudaStream_t sc = st;   // stream of the P-limb chain
+    cudaEvent_t ev_join = nullptr;
     inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, l, alpha, 0, lazy_t_);
     if (fork) {
-        if (!s_side_) {
+        StreamCtx &fj = sctx(st);
+        if (!fj.s_side) {
             int least = 0, greatest = 0;
             PFHE_CUDA(cudaDeviceGetStreamPriorityRange(&least, &greatest));
-            PFHE_CUDA(cudaStreamCreateWithPriority(&s_side_, cudaStreamNonBlocking, greatest));
-            PFHE_CUDA(cudaEventCreateWithFlags(&ev_fork_, cudaEventDisableTiming));
-            PFHE_CUDA(cudaEventCreateWithFlags(&ev_join_, cudaEventDisableTiming));
+            PFHE_CUDA(cudaStreamCreateWithPriority(&fj.s_side, cudaStreamNonBlocking, greatest));
+            PFHE_CUDA(cudaEventCreateWithFlags(&fj.ev_fork, cudaEventDisableTiming));
+            PFHE_CUDA(cudaEventCreateWithFlags(&fj.ev_join, cudaEventDisableTiming));
         }
-        PFHE_CUDA(cudaEventRecord(ev_fork_, st));
-        PFHE_CUDA(cudaStreamWaitEvent(s_side_, ev_fork_, 0));
-        sc = s_side_;
+        ev_join = fj.ev_join;
+        PFHE_CUDA(cudaEventRecord(fj.ev_fork, st));
+        PFHE_CUDA(cudaStreamWaitEvent(fj.s_side, fj.ev_fork, 0));
+        sc = fj.s_side;
     } else {
         inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l, 0, lazy_t_);
     }
@@ -858,9 +881,9 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
             PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), st));
         } else {
             PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), sc, 1));   // 5a: column pass
-            PFHE_CUDA(cudaEventRecord(ev_join_, sc));
+            PFHE_CUDA(cudaEventRecord(ev_join, sc));
             inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l, side_ctas_, lazy_t_);   // Q limbs
-            PFHE_CUDA(cudaStreamWaitEvent(st, ev_join_, 0));
+            PFHE_CUDA(cudaStreamWaitEvent(st, ev_join, 0));
             PFHE_CUDA(ntt_forward_bconv(plan_, delta, ll, bl, &ea, ts, bar(2, 0), st, 2));   // 5b: row pass + epilogue
         }
     }
@@ -868,6 +891,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
 
 // keyswitch_inplace (reference src/eval_key_switch.cu:95-182): out[2][l][n] = addend + moddown(<modup(c2), evk>)
 void Engine::keyswitch(int l, u64 *out, const u64 *c2, const u64 *const *evk, const u64 *addend, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (scheme_ == Scheme::ckks) {
         keyswitch_fused(l, out, c2, nullptr, evk, addend, addend ? 3u : 0u, st);
         return;
@@ -880,6 +904,7 @@ void Engine::keyswitch(int l, u64 *out, const u64 *c2, const u64 *const *evk, co
 
 void Engine::moddown_generic(int l, u64 *out, u64 *cx, int npoly, const u64 *addend, unsigned add_mask,
                              cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     const Level &lv = level(l);
     const int alpha = lv.alpha, m = lv.m;
     const bool bgv = scheme_ == Scheme::bgv;
@@ -935,6 +960,7 @@ void Engine::moddown_generic(int l, u64 *out, u64 *cx, int npoly, const u64 *add
 }
 
 void Engine::mod_switch_scale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (l < 2) throw std::invalid_argument("end of modulus switching chain reached");
     const Level &lv = level(l);
     const int nl = l - 1;
@@ -967,6 +993,7 @@ void Engine::galois_coeff(u64 *dst, const u64 *src, uint32_t elt, int l, int npo
 // BFV multiplication, BEHZ variant
 // ---------------------------------------------------------------------------------------------------
 const Behz &Engine::behz(int l) {
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     if (scheme_ != Scheme::bfv || naux_ == 0) throw std::invalid_argument("unsupported scheme");
     if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
     if (behz_[l]) return *behz_[l];
@@ -1029,6 +1056,7 @@ const Behz &Engine::behz(int l) {
 }
 
 void Engine::bfv_multiply_behz(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     const Behz &b = behz(l);
     const int nbsk = b.nbsk;
     const size_t need = (size_t) 7 * (l + nbsk) * n_;
@@ -1096,6 +1124,7 @@ void Engine::set_mul_tech(int m) {
 }
 
 const Hps &Engine::hps() {
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     if (scheme_ != Scheme::bfv || nR_ == 0) throw std::invalid_argument("unsupported scheme");
     if (hps_) return *hps_;
     auto h = std::make_unique<Hps>();
@@ -1142,6 +1171,7 @@ const Hps &Engine::hps() {
 }
 
 void Engine::bfv_multiply_hps(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     // the reference always takes the constants of the first data level here (evaluate.cu:672-696)
     if (l != size_Q_) throw std::invalid_argument("HPS multiplication is defined at the first data level only");
     const Hps &h = hps();
@@ -1196,6 +1226,7 @@ void Engine::bfv_multiply_hps(int l, u64 *out3, const u64 *ct1, const u64 *ct2, 
 
 // constants of HPS over Q with `drop` dropped levels (reference rns.cu:794-975; host/rns.cu:470-495 for the var1 form)
 const HpsQ &Engine::hpsq(int drop) {
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     if (scheme_ != Scheme::bfv || nR_ == 0) throw std::invalid_argument("unsupported scheme");
     if (drop < 0 || drop >= size_Q_) throw std::invalid_argument("levels dropped out of range");
     if ((int) hpsq_.size() <= drop) hpsq_.resize(drop + 1);
@@ -1278,6 +1309,7 @@ const HpsQ &Engine::hpsq(int drop) {
 // comes back to Ql from there; tensor product over Ql u Rl; t/Rl scale-and-round straight to Ql; expansion back to Q.
 void Engine::bfv_multiply_hps_overq(int l, u64 *out3, const u64 *ct1, const u64 *ct2, int drop, cudaStream_t st,
                                     bool keep_c2_low) {
+    Workspace &ws_ = ws(st);
     if (l != size_Q_) throw std::invalid_argument("HPS multiplication is defined at the first data level only");
     const HpsQ &h = hpsq(drop);
     const int lq = size_Q_, ll = h.ll;
@@ -1358,6 +1390,7 @@ void Engine::bfv_multiply_hps_overq(int l, u64 *out3, const u64 *ct1, const u64 
 }
 
 void Engine::keyswitch_leveled(u64 *ct, const u64 *c2, const u64 *const *evk, int drop, bool c2_low, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (scheme_ != Scheme::bfv) throw std::invalid_argument("unsupported scheme");
     const int lq = size_Q_;
     if (drop == 0) {
@@ -1386,6 +1419,7 @@ void Engine::keyswitch_leveled(u64 *ct, const u64 *c2, const u64 *const *evk, in
 }
 
 const Decrypt &Engine::decrypt_tables(int l) {
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     if (l < 1 || l > size_Q_ || t_ <= 1) throw std::invalid_argument("decryption needs a plain modulus");
     if ((int) dec_.size() <= size_Q_) dec_.resize(size_Q_ + 1);
     if (dec_[l]) return *dec_[l];
@@ -1442,6 +1476,7 @@ static Modulus host_modulus(u64 q) {
 
 // PhantomSecretKey::decrypt (reference src/secretkey.cu:533-691)
 void Engine::decrypt(int l, const u64 *ct, int size, const u64 *sk_pow, u64 correction_factor, u64 *out, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (size < 1 || size > MXN_MAX + 1) throw std::invalid_argument("ciphertext size is not supported");
     const size_t pl = (size_t) l * n_, pk = (size_t) size_QP_ * n_;
     const dim3 gl((unsigned) (n_ / (2 * BEHZ_THREADS)), l), g1((unsigned) (n_ / BEHZ_THREADS));
@@ -1500,6 +1535,7 @@ void Engine::decrypt(int l, const u64 *ct, int size, const u64 *sk_pow, u64 corr
 }
 
 void Engine::ckks_tables() {
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     const size_t slots = n_ >> 1;
     const uint32_t M = (uint32_t) (n_ << 1);
     if (!d_ckks_roots_.p) {
@@ -1539,12 +1575,14 @@ void Engine::ckks_tables() {
 
 // PhantomCKKSEncoder::decode_internal (reference src/ckks.cu:137-190)
 void Engine::ckks_decode(int l, const u64 *plain, double scale, double2 *out, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (scheme_ != Scheme::ckks) throw std::invalid_argument("unsupported scheme");
     if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
     if (l > CKKS_MAX_WORDS) throw std::invalid_argument("too many limbs for the CKKS decoder");
     std::vector<u64> ql(primes_.begin(), primes_.begin() + l);
     if (scale <= 0 || (int) std::log2(scale) >= hm::product_bits(ql)) throw std::invalid_argument("scale out of bounds");
     ckks_tables();
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     if ((int) ckks_dec_.size() <= size_Q_) ckks_dec_.resize(size_Q_ + 1);
     if (!ckks_dec_[l]) {
         auto d = std::make_unique<CkksDec>();
@@ -1659,6 +1697,7 @@ void Engine::batch_encode(const u64 *values, size_t count, u64 *plain, cudaStrea
 }
 
 void Engine::ensure_batch_map() {
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
     if (!d_batch_map_.p) {
         std::vector<uint32_t> map(n_);
         const size_t row = n_ >> 1, m = n_ << 1;
@@ -1673,6 +1712,7 @@ void Engine::ensure_batch_map() {
 }
 
 void Engine::batch_decode(const u64 *plain, u64 *values, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (scheme_ == Scheme::ckks) throw std::invalid_argument("PhantomBatchEncoder only supports BFV/BGV scheme");
     if (!batching_) throw std::invalid_argument("the plain modulus does not support batching");
     ensure_batch_map();
@@ -1736,10 +1776,12 @@ void Engine::bfv_multiply(int l, u64 *out3, const u64 *ct1, const u64 *ct2, cuda
 }
 
 // multiply_inplace + relinearize_inplace (reference src/evaluate.cu:345-397,451-548,819-1026,1342-1374)
-void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st) {
+void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, const u64 *const *rlk, cudaStream_t st,
+                            int leveled_drop) {
+    Workspace &ws_ = ws(st);
     if (scheme_ == Scheme::bfv) {
         u64 *d = ws_.tmp.p;
-        const int drop = mul_tech_ == 4 ? leveled_drop_ : 0;   // hps_overq_leveled: set by multiply_relin_leveled
+        const int drop = mul_tech_ == 4 ? leveled_drop : 0;   // hps_overq_leveled: the caller supplies the levels
         if (drop) {   // bfv_mul_relin_hps with levels dropped (evaluate.cu:819-1026): c2 stays at Ql and is switched there
             bfv_multiply_hps_overq(l, d, ct1, ct2, drop, st, true);
             keyswitch_leveled(d, d + (size_t) 2 * l * n_, rlk, drop, true, st);
@@ -1779,42 +1821,44 @@ void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, con
 void Engine::multiply_relin_host_batch(int l, const u64 *const *h1, const u64 *const *h2, u64 *const *hout,
                                        size_t count, const u64 *const *rlk, cudaStream_t st) {
     const size_t words = (size_t) 2 * l * n_;
-    if (!s_in_) {
-        PFHE_CUDA(cudaStreamCreateWithFlags(&s_in_, cudaStreamNonBlocking));
-        PFHE_CUDA(cudaStreamCreateWithFlags(&s_out_, cudaStreamNonBlocking));
+    StreamCtx &c = sctx(st);
+    if (!c.s_in) {
+        PFHE_CUDA(cudaStreamCreateWithFlags(&c.s_in, cudaStreamNonBlocking));
+        PFHE_CUDA(cudaStreamCreateWithFlags(&c.s_out, cudaStreamNonBlocking));
         for (int i = 0; i < 2; i++) {
-            PFHE_CUDA(cudaEventCreateWithFlags(&ev_in_[i], cudaEventDisableTiming));
-            PFHE_CUDA(cudaEventCreateWithFlags(&ev_comp_[i], cudaEventDisableTiming));
-            PFHE_CUDA(cudaEventCreateWithFlags(&ev_out_[i], cudaEventDisableTiming));
+            PFHE_CUDA(cudaEventCreateWithFlags(&c.ev_in[i], cudaEventDisableTiming));
+            PFHE_CUDA(cudaEventCreateWithFlags(&c.ev_comp[i], cudaEventDisableTiming));
+            PFHE_CUDA(cudaEventCreateWithFlags(&c.ev_out[i], cudaEventDisableTiming));
         }
     }
     for (int i = 0; i < 2; i++) {
-        if (pipe_in_[i].count < 2 * words) pipe_in_[i].alloc(2 * words);
-        if (pipe_out_[i].count < words) pipe_out_[i].alloc(words);
+        if (c.pipe_in[i].count < 2 * words) c.pipe_in[i].alloc(2 * words);
+        if (c.pipe_out[i].count < words) c.pipe_out[i].alloc(words);
     }
     // side streams start after whatever the caller already queued on `st`
-    PFHE_CUDA(cudaEventRecord(ev_comp_[0], st));
-    PFHE_CUDA(cudaStreamWaitEvent(s_in_, ev_comp_[0], 0));
-    PFHE_CUDA(cudaStreamWaitEvent(s_out_, ev_comp_[0], 0));
+    PFHE_CUDA(cudaEventRecord(c.ev_comp[0], st));
+    PFHE_CUDA(cudaStreamWaitEvent(c.s_in, c.ev_comp[0], 0));
+    PFHE_CUDA(cudaStreamWaitEvent(c.s_out, c.ev_comp[0], 0));
     for (size_t i = 0; i < count; i++) {
         const int b = (int) (i & 1);
-        if (i >= 2) PFHE_CUDA(cudaStreamWaitEvent(s_in_, ev_comp_[b], 0));   // input buffer b consumed
-        PFHE_CUDA(cudaMemcpyAsync(pipe_in_[b].p, h1[i], words * 8, cudaMemcpyHostToDevice, s_in_));
-        PFHE_CUDA(cudaMemcpyAsync(pipe_in_[b].p + words, h2[i], words * 8, cudaMemcpyHostToDevice, s_in_));
-        PFHE_CUDA(cudaEventRecord(ev_in_[b], s_in_));
-        PFHE_CUDA(cudaStreamWaitEvent(st, ev_in_[b], 0));
-        if (i >= 2) PFHE_CUDA(cudaStreamWaitEvent(st, ev_out_[b], 0));       // output buffer b drained
-        multiply_relin(l, pipe_out_[b].p, pipe_in_[b].p, pipe_in_[b].p + words, rlk, st);
-        PFHE_CUDA(cudaEventRecord(ev_comp_[b], st));
-        PFHE_CUDA(cudaStreamWaitEvent(s_out_, ev_comp_[b], 0));
-        PFHE_CUDA(cudaMemcpyAsync(hout[i], pipe_out_[b].p, words * 8, cudaMemcpyDeviceToHost, s_out_));
-        PFHE_CUDA(cudaEventRecord(ev_out_[b], s_out_));
+        if (i >= 2) PFHE_CUDA(cudaStreamWaitEvent(c.s_in, c.ev_comp[b], 0));   // input buffer b consumed
+        PFHE_CUDA(cudaMemcpyAsync(c.pipe_in[b].p, h1[i], words * 8, cudaMemcpyHostToDevice, c.s_in));
+        PFHE_CUDA(cudaMemcpyAsync(c.pipe_in[b].p + words, h2[i], words * 8, cudaMemcpyHostToDevice, c.s_in));
+        PFHE_CUDA(cudaEventRecord(c.ev_in[b], c.s_in));
+        PFHE_CUDA(cudaStreamWaitEvent(st, c.ev_in[b], 0));
+        if (i >= 2) PFHE_CUDA(cudaStreamWaitEvent(st, c.ev_out[b], 0));       // output buffer b drained
+        multiply_relin(l, c.pipe_out[b].p, c.pipe_in[b].p, c.pipe_in[b].p + words, rlk, st);
+        PFHE_CUDA(cudaEventRecord(c.ev_comp[b], st));
+        PFHE_CUDA(cudaStreamWaitEvent(c.s_out, c.ev_comp[b], 0));
+        PFHE_CUDA(cudaMemcpyAsync(hout[i], c.pipe_out[b].p, words * 8, cudaMemcpyDeviceToHost, c.s_out));
+        PFHE_CUDA(cudaEventRecord(c.ev_out[b], c.s_out));
     }
-    for (int b = 0; b < 2 && (size_t) b < count; b++) PFHE_CUDA(cudaStreamWaitEvent(st, ev_out_[b], 0));
+    for (int b = 0; b < 2 && (size_t) b < count; b++) PFHE_CUDA(cudaStreamWaitEvent(st, c.ev_out[b], 0));
 }
 
 // apply_galois_inplace for CKKS/BGV (reference src/evaluate.cu:1567-1630)
 void Engine::apply_galois(int l, u64 *ct, uint32_t galois_elt, const u64 *const *glk, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     const int gi = galois_index(galois_elt);
     u64 *tmp = ws_.tmp.p;   // [2][l][n]: permuted c0, c1
     if (scheme_ == Scheme::bfv) {
@@ -1840,6 +1884,7 @@ void Engine::apply_galois(int l, u64 *ct, uint32_t galois_elt, const u64 *const 
 // hoisting_inplace (reference src/evaluate.cu:1670-1865), CKKS/BGV
 void Engine::hoisting(int l, u64 *ct, const std::vector<uint32_t> &elts, const std::vector<const u64 *const *> &keys,
                       cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (scheme_ == Scheme::bfv) throw std::invalid_argument("unsupported scheme");
     if (elts.empty() || elts.size() != keys.size()) throw std::invalid_argument("steps / keys mismatch");
     const Level &lv = level(l);
@@ -1868,6 +1913,7 @@ void Engine::hoisting(int l, u64 *ct, const std::vector<uint32_t> &elts, const s
 
 // rescale_to_next for CKKS (reference src/evaluate.cu:1376-1427 + divide_and_round_q_last_ntt rns.cu:1160-1184)
 void Engine::rescale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (l < 2) throw std::invalid_argument("end of modulus switching chain reached");
     const Level &lv = level(l);
     const int nl = l - 1;
@@ -1940,6 +1986,7 @@ void Engine::gen_secret_key(const Seed &seed, u64 *sk, cudaStream_t st) const {
 // for BGV; NTT form, or (BFV) coefficient form.  sk = first power of the key, NTT form, key-level layout
 void Engine::encrypt_zero_symmetric(int limbs, bool ntt_form, const u64 *sk, const Seed &seed_a, const Seed &seed_e, u64 *out,
                                     cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (limbs < 1 || limbs > size_QP_) throw std::invalid_argument("limb count out of range");
     u64 *c0 = out, *c1 = out + (size_t) limbs * n_, *e = ws_.cx.p;
     const dim3 grid((unsigned) (n_ / EW_THREADS), limbs);
@@ -1968,6 +2015,7 @@ void Engine::encrypt_zero_symmetric(int limbs, bool ntt_form, const u64 *sk, con
 // (DRNSTool::moddown, rns_bconv.cu:712-761).  out = [2][size_Q][n], NTT form (CKKS, BGV) or coefficient form (BFV).
 // Like the reference, both polynomials get the same error polynomial (one seed, nonces restart at zero).
 void Engine::encrypt_zero_asymmetric(const u64 *pk, const Seed &seed_u, const Seed &seed_e, u64 *out, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (size_P_ < 1) throw std::invalid_argument("asymmetric encryption needs a special modulus");
     if (3 * size_Q_ < size_QP_) throw std::invalid_argument("special modulus larger than the workspace allows");
     const int m = size_QP_, l = size_Q_;
@@ -2034,6 +2082,7 @@ void Engine::galois_ntt(const u64 *operand, int limbs, uint32_t galois_elt, u64 
 //   CKKS  plain = [l][n] in NTT form
 //   BGV   plain = [n] mod t, lifted to every limb, transformed, times the ciphertext's correction factor
 void Engine::plain_add(int l, u64 *ct0, const u64 *plain, bool sub, u64 correction_factor, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
     const dim3 grid((unsigned) (n_ / EW_THREADS), l);
     if (scheme_ == Scheme::ckks) {
@@ -2067,6 +2116,7 @@ void Engine::plain_add(int l, u64 *ct0, const u64 *plain, bool sub, u64 correcti
 // BGV: plain lifted and transformed; BFV (multiply_plain_normal): plain lifted with the upper half moved to negative
 // residues, ciphertext to NTT form and back.  ct = [size][l][n]
 void Engine::plain_multiply(int l, u64 *ct, int size, const u64 *plain, cudaStream_t st) {
+    Workspace &ws_ = ws(st);
     if (l < 1 || l > size_Q_) throw std::invalid_argument("index is invalid!");
     if (size < 1) throw std::invalid_argument("ciphertext is empty");
     const dim3 grid((unsigned) (n_ / EW_THREADS), l);

@@ -79,9 +79,26 @@ int pfhe_engine_create(pfhe_engine **out, int scheme, uint64_t n, const uint64_t
         return fail(PFHE_ERR_INVALID_ARGUMENT, "invalid parameters");
     }
     e->scheme = scheme, e->n = n, e->t = t, e->size_QP = size_QP, e->size_P = size_P, e->size_Q = size_QP - size_P;
-    e->elts.assign(elts, elts + n_elts);
+    if (elts && n_elts > 0) e->elts.assign(elts, elts + n_elts);
+    if (e->elts.empty()) {   // get_elts_all (reference src/galois.cu:41-65)
+        const uint32_t m = (uint32_t) (2 * n);
+        int logn = 0;
+        while (((uint64_t) 1 << logn) < n) logn++;
+        e->elts.push_back(m - 1);
+        uint64_t pos = 5, neg = 1;
+        while ((neg * 5) % m != 1) neg += 2;
+        for (int i = 0; i < logn - 1; i++) {
+            e->elts.push_back((uint32_t) pos), pos = (pos * pos) & (m - 1);
+            e->elts.push_back((uint32_t) neg), neg = (neg * neg) & (m - 1);
+        }
+    }
     *out = e;
     return PFHE_OK;
+}
+int pfhe_galois_elts(const pfhe_engine *e, uint32_t *out, int cap) {
+    if (out)
+        for (int i = 0; i < cap && i < (int) e->elts.size(); i++) out[i] = e->elts[i];
+    return (int) e->elts.size();
 }
 void pfhe_engine_destroy(pfhe_engine *e) {
     if (!e) return;
