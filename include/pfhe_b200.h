@@ -71,7 +71,10 @@ int pfhe_galois_elts(const pfhe_engine *e, uint32_t *elts_out, int capacity);
 int pfhe_galois_elt_from_step(int step, uint64_t n, uint32_t *elt_out);
 
 /* ---- NTT (replaces include/ntt.cuh:172-226) --------------------------------------------------------- */
-/* nwt_2d_radix8_forward_inplace (src/ntt/fntt_2d.cu:620-653) */
+/* Addressing of every launcher in this section is the reference's: `inout` / `in` / `out` point at limb 0 of a buffer
+ * [..][N]; the call works on limbs [start_modulus_idx, start_modulus_idx + coeff_modulus_size) of it, limb i with the
+ * constants of table entry i (fntt_2d.cu:35-40: data_ptr = inout + twr_idx * n, twr_idx = i + start_mod_idx).
+ * nwt_2d_radix8_forward_inplace (src/ntt/fntt_2d.cu:620-653) */
 int pfhe_ntt_forward_inplace(pfhe_engine *e, uint64_t *inout, size_t coeff_modulus_size, size_t start_modulus_idx,
                              void *stream);
 /* nwt_2d_radix8_backward_inplace (src/ntt/intt_2d.cu:724-757) */
@@ -94,6 +97,82 @@ int pfhe_ntt_forward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout
 int pfhe_ntt_backward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t coeff_modulus_size,
                                                   size_t start_modulus_idx, size_t size_QP, size_t size_P,
                                                   void *stream);
+
+
+/* ---- the remaining launchers of include/ntt.cuh:172-226, same addressing ----------------------------------------
+ * `table` names the DNTTTable the reference passes: PFHE_TABLE_RNS = context.gpu_rns_tables() (key-level primes),
+ * PFHE_TABLE_BSK = rns_tool.gpu_Bsk_tables() (B_0.., m_sk; BFV), PFHE_TABLE_QLRL = gpu_QlRl_tables() (Q then R; BFV HPS),
+ * PFHE_TABLE_PLAIN = gpu_plain_tables() (the batching plain modulus).  The Bsk and QlRl tables belong to a level's DRNSTool:
+ * pass family | chain_index << 8 for a level other than the first data level. */
+enum { PFHE_TABLE_RNS = 0, PFHE_TABLE_BSK = 1, PFHE_TABLE_QLRL = 2, PFHE_TABLE_PLAIN = 3 };
+int pfhe_table_size(const pfhe_engine *e, int table);
+/* modulus of entry idx of that table (0 if out of range) */
+uint64_t pfhe_table_modulus(const pfhe_engine *e, int table, size_t idx);
+/* nwt_2d_radix8_forward_inplace / _backward_inplace / _backward on any table (fntt_2d.cu:620-653, intt_2d.cu:724-757,
+ * ntt_modup.cu:320-354) */
+int pfhe_nwt_2d_radix8_forward_inplace(pfhe_engine *e, int table, uint64_t *inout, size_t coeff_modulus_size,
+                                       size_t start_modulus_idx, void *stream);
+int pfhe_nwt_2d_radix8_backward_inplace(pfhe_engine *e, int table, uint64_t *inout, size_t coeff_modulus_size,
+                                        size_t start_modulus_idx, void *stream);
+int pfhe_nwt_2d_radix8_backward(pfhe_engine *e, int table, uint64_t *out, const uint64_t *in, size_t coeff_modulus_size,
+                                size_t start_modulus_idx, void *stream);
+/* nwt_2d_radix8_forward_inplace_fuse_moddown (ntt_moddown.cu:222-261): ct[i] = (cx[i] - NTT(delta[i])) * bigPInv_mod_q[i];
+ * delta is clobbered */
+int pfhe_nwt_2d_radix8_forward_inplace_fuse_moddown(pfhe_engine *e, uint64_t *ct, const uint64_t *cx,
+                                                    const uint64_t *bigPInv_mod_q, const uint64_t *bigPInv_mod_q_shoup,
+                                                    uint64_t *delta, size_t coeff_modulus_size, size_t start_modulus_idx,
+                                                    void *stream);
+/* nwt_2d_radix8_forward_inplace_include_temp_mod (fntt_2d.cu:655-692): limb coeff_modulus_size - 1 uses table entry
+ * total_modulus_size - 1 */
+int pfhe_nwt_2d_radix8_forward_inplace_include_temp_mod(pfhe_engine *e, int table, uint64_t *inout,
+                                                        size_t coeff_modulus_size, size_t start_modulus_idx,
+                                                        size_t total_modulus_size, void *stream);
+/* nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range (ntt_modup.cu:610-657) */
+int pfhe_nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range(pfhe_engine *e, uint64_t *inout,
+                                                                         size_t coeff_modulus_size, size_t start_modulus_idx,
+                                                                         size_t size_QP, size_t size_P,
+                                                                         size_t excluded_range_start,
+                                                                         size_t excluded_range_end, void *stream);
+/* nwt_2d_radix8_forward_modup_fuse (ntt_keyswitch_old.cu:225-265): out[i] = NTT of in[i] with the constants of table entry
+ * modulus_index for every limb of the window (inputs below that modulus, e.g. a plaintext modulo t lifted under q_i) */
+int pfhe_nwt_2d_radix8_forward_modup_fuse(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t modulus_index,
+                                          size_t coeff_modulus_size, size_t start_modulus_idx, void *stream);
+/* nwt_2d_radix8_backward_scale / _backward_inplace_scale (ntt_modup.cu:356-393, intt_2d.cu:759-794): inverse transform
+ * times scale[i]; scale / scale_shoup are device arrays indexed by limb */
+int pfhe_nwt_2d_radix8_backward_scale(pfhe_engine *e, int table, uint64_t *out, const uint64_t *in,
+                                      size_t coeff_modulus_size, size_t start_modulus_idx, const uint64_t *scale,
+                                      const uint64_t *scale_shoup, void *stream);
+int pfhe_nwt_2d_radix8_backward_inplace_scale(pfhe_engine *e, int table, uint64_t *inout, size_t coeff_modulus_size,
+                                              size_t start_modulus_idx, const uint64_t *scale, const uint64_t *scale_shoup,
+                                              void *stream);
+/* nwt_2d_radix8_backward_inplace_include_temp_mod_scale (intt_2d.cu:835-873): scale indexed by table entry */
+int pfhe_nwt_2d_radix8_backward_inplace_include_temp_mod_scale(pfhe_engine *e, int table, uint64_t *inout,
+                                                               size_t coeff_modulus_size, size_t start_modulus_idx,
+                                                               size_t total_modulus_size, const uint64_t *scale,
+                                                               const uint64_t *scale_shoup, void *stream);
+
+/* ---- DBaseConverter::bConv_BEHZ / bConv_BEHZ_var1 / bConv_HPS (include/rns_bconv.cuh:62-68, src/rns_bconv.cu:212-246,
+ * 354-372).  The converter is named by its bases: ibase / obase are (table, entry) pairs flattened as table * 65536 + entry.
+ * src = [ni][N], dst = [no][N] (coefficient form).  BEHZ: y_i = x_i qhat_i^-1, dst_j = sum y_i (qhat_i mod p_j);
+ * var1: y_i = x_i (-P qhat_i^-1), dst_j = sum y_i (q_i^-1 mod p_j); HPS: BEHZ minus round(sum y_i / q_i) * Q mod p_j with
+ * the reference's FP64 accumulation order. */
+enum { PFHE_BCONV_BEHZ = 0, PFHE_BCONV_BEHZ_VAR1 = 1, PFHE_BCONV_HPS = 2 };
+int pfhe_bconv(pfhe_engine *e, int mode, const uint32_t *ibase, int ni, const uint32_t *obase, int no, uint64_t *dst,
+               const uint64_t *src, void *stream);
+/* DRNSTool::moddown (src/rns_bconv.cu:712-761): ct_i[l][N] = moddown of cx_i[l + size_P][N]; CKKS / BGV input in NTT form,
+ * BFV input in coefficient form.  cx_i is clobbered. */
+int pfhe_moddown(pfhe_engine *e, size_t chain_index, uint64_t *ct_i, uint64_t *cx_i, void *stream);
+/* DRNSTool::divide_and_round_q_last (src/rns.cu:1082-1126, coefficient form), divide_and_round_q_last_ntt (:1160-1184,
+ * NTT form) and mod_t_and_divide_q_last_ntt (:1186-1235, NTT form with the plain-modulus correction): src = [size][l][N] at
+ * chain_index, dst = [size][l-1][N].  Unlike the reference, src is left intact. */
+int pfhe_divide_and_round_q_last(pfhe_engine *e, size_t chain_index, const uint64_t *src, size_t cipher_size,
+                                 uint64_t *dst, void *stream);
+int pfhe_divide_and_round_q_last_ntt(pfhe_engine *e, size_t chain_index, const uint64_t *src, size_t cipher_size,
+                                     uint64_t *dst, void *stream);
+int pfhe_mod_t_and_divide_q_last_ntt(pfhe_engine *e, size_t chain_index, const uint64_t *src, size_t cipher_size,
+                                     uint64_t *dst, void *stream);
+/* add_to_ct_kernel (src/rns_bconv.cu:763-769): ct[l][N] += cx[l][N] */
+int pfhe_add_to_ct(pfhe_engine *e, uint64_t *ct, const uint64_t *cx, size_t size_Ql, void *stream);
 
 /* ---- dyadic kernels (replace the __global__ symbols evaluate.cu launches, include/polymath.cuh) ------ */
 /* tensor_prod_2x2_rns_poly (src/polymath.cu:463-498); result = [3][l][n], may alias operand1 */
@@ -283,10 +362,14 @@ int pfhe_rotate_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted,
                         const uint64_t *const *galois_key, void *stream);
 /* hoisting_inplace (src/evaluate.cu:1670-1865): encrypted <- sum_i rotate(encrypted, steps[i]) with one shared mod-up
  * and one mod-down; galois_keys[i] = PhantomGaloisKey::get_relin_keys(index of steps[i]).public_keys_ptr() (host
- * array of n_steps device pointer arrays).  CKKS and BGV engines; a BFV engine answers PFHE_ERR_INVALID_ARGUMENT
- * "unsupported scheme" (the host mirrors compose the sum from pfhe_apply_galois_inplace and pfhe_add_rns_poly there). */
+ * array of n_steps device pointer arrays).  All three schemes; BFV ciphertexts are in coefficient form (apply_galois on c0,
+ * mod-up from and mod-down to coefficient form, evaluate.cu:1745-1747) and, like the reference's, at the first data level. */
 int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *encrypted, const int *steps, size_t n_steps,
                           const uint64_t *const *const *galois_keys, void *stream);
+/* the same under mul_tech hps_overq_leveled with `levels_dropped` levels dropped (pfhe_find_levels_to_drop with
+ * is_key_switch = 1; evaluate.cu:1690-1701): encrypted = [2][size_Q][n] is scaled to Ql, rotated and summed there, expanded back */
+int pfhe_hoisting_leveled_inplace(pfhe_engine *e, uint64_t *encrypted, const int *steps, size_t n_steps,
+                                  const uint64_t *const *const *galois_keys, int levels_dropped, void *stream);
 /* rescale_to_next (src/evaluate.cu:1545-1565): destination = [size][l-1][n] */
 int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *encrypted, size_t size,
                          uint64_t *destination, void *stream);

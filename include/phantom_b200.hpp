@@ -901,22 +901,8 @@ inline void rotate_inplace(const PhantomContext &context, PhantomCiphertext &enc
 inline void hoisting_inplace(const PhantomContext &context, PhantomCiphertext &ct, const PhantomGaloisKey &glk, const std::vector<int> &steps) {
     context.check(ct);
     if (ct.size() > 2) throw std::invalid_argument("ciphertext size must be 2");
-    if (context.parms().scheme() == scheme_type::bfv) {
-        // the engine's hoisted form is built for the NTT-form schemes; for BFV the sum is composed from the rotations
-        // themselves: the same plaintext as the reference's hoisted result, not the same words (no shared mod-up)
-        PhantomCiphertext total;
-        for (size_t i = 0; i < steps.size(); i++) {
-            PhantomCiphertext term = ct;
-            rotate_inplace(context, term, steps[i], glk);
-            if (i == 0) total = std::move(term);
-            else add_inplace(context, total, term);
-        }
-        if (!steps.empty()) {
-            cuda_check(cudaStreamSynchronize(context.stream()));
-            ct = std::move(total);
-        }
-        return;
-    }
+    if (context.parms().scheme() == scheme_type::bfv && ct.chain_index() != 1)
+        throw std::invalid_argument("BFV hoisting is built for the first data level");   // evaluate.cu:1688-1708
     const auto &elts = context.parms().galois_elts();
     std::vector<const uint64_t *const *> keys;
     for (int step : steps) {
@@ -924,6 +910,11 @@ inline void hoisting_inplace(const PhantomContext &context, PhantomCiphertext &c
         const auto it = std::find(elts.begin(), elts.end(), elt);
         if (it == elts.end()) throw std::logic_error("Galois key not present in hoisting");
         keys.push_back(glk.get_relin_keys((size_t) (it - elts.begin())).public_keys_ptr());
+    }
+    if (context.leveled()) {   // hps_overq_leveled: a key switch at the depth of the ciphertext (evaluate.cu:1690-1701)
+        const int drop = detail::levels_to_drop(context, ct.GetNoiseScaleDeg() - 1, true, ct.is_asymmetric());
+        rethrow(pfhe_hoisting_leveled_inplace(context.engine(), ct.data(), steps.data(), steps.size(), keys.data(), drop, context.stream()));
+        return;
     }
     rethrow(pfhe_hoisting_inplace(context.engine(), ct.chain_index(), ct.data(), steps.data(), steps.size(), keys.data(), context.stream()));
 }

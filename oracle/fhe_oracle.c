@@ -817,8 +817,10 @@ void orc_apply_galois(const orc_ctx *c, int l, u64 *ct, uint32_t elt, const u64 
     free(tmp);
 }
 
-/* hoisting_inplace (CKKS/BGV), evaluate.cu:1670-1865: sum over elts of the rotated ciphertext with one shared
- * mod-up and one mod-down.  glk[i] = switching key of elts[i] ([dnum][2][size_QP][n]) */
+/* hoisting_inplace, evaluate.cu:1670-1865: sum over elts of the rotated ciphertext with one shared mod-up and one
+ * mod-down.  glk[i] = switching key of elts[i] ([dnum][2][size_QP][n]).  BFV (:1745-1747, 1808-1810): c0 takes the
+ * coefficient-form automorphism, mod-up starts from and mod-down ends in coefficient form (orc_modup /
+ * orc_moddown_from_ntt branch on the scheme). */
 void orc_hoisting(const orc_ctx *c, int l, u64 *ct, const uint32_t *elts, int n_elts, const u64 *const *glk) {
     size_t n = c->n, poly = (size_t)l * n;
     int m = l + c->size_P, beta = orc_beta(c, l);
@@ -831,7 +833,8 @@ void orc_hoisting(const orc_ctx *c, int l, u64 *ct, const uint32_t *elts, int n_
     orc_modup(c, l, ct + poly, up);
     for (int e = 0; e < n_elts; e++) {
         orc_galois_table(n, elts[e], table);
-        orc_apply_galois_ntt(c, ct, tmp, l, table);
+        if (c->scheme == ORC_SCHEME_BFV) orc_apply_galois_coeff(c, ct, tmp, l, elts[e]);
+        else orc_apply_galois_ntt(c, ct, tmp, l, table);
         orc_poly_add(c, acc_c0, tmp, acc_c0, l);
         /* the same index permutation on every limb of every digit (:1775-1778); moduli do not matter here */
         for (int b = 0; b < beta * m; b++)
@@ -1402,6 +1405,37 @@ int orc_bfv_keyswitch_leveled(const orc_ctx *c, u64 *ct, const u64 *c2, const u6
             }
         }
     free(ks); free(low);
+    return 0;
+}
+
+/* hoisting_inplace under mul_tech hps_overq_leveled with `drop` levels dropped (evaluate.cu:1690-1701, 1731-1733,
+ * 1761-1763, 1847-1862): both polynomials are scaled from Q to Ql (scaleAndRound_HPS_Q_Ql), hoisted there, and the
+ * result expanded back to Q (ExpandCRTBasis_Ql_Q: times QlDrop mod q_i, dropped limbs zero).  ct = [2][size_Q][n] */
+int orc_bfv_hoisting_leveled(const orc_ctx *c, u64 *ct, const uint32_t *elts, int n_elts, const u64 *const *glk, int drop) {
+    const size_t n = c->n;
+    const int lq = c->size_Q, ll = lq - drop;
+    const u64 *Q = c->primes;
+    if (drop < 0 || ll < 1) return -1;
+    if (drop == 0) {
+        orc_hoisting(c, lq, ct, elts, n_elts, glk);
+        return 0;
+    }
+    const size_t pl = (size_t)ll * n, pq = (size_t)lq * n;
+    u64 *low = (u64 *)malloc(2 * pl * 8);
+    u64 *tab = (u64 *)malloc((size_t)ll * (drop + 1) * 8);
+    double *frac = (double *)malloc(drop * sizeof(double));
+    scale_round_tables(Q, ll, Q + ll, drop, 1, tab, frac);
+    for (int k = 0; k < 2; k++) scale_round_to_a(Q, ll, drop, tab, frac, ct + k * pq, ct + k * pq + pl, low + k * pl, n);
+    free(tab); free(frac);
+    orc_hoisting(c, ll, low, elts, n_elts, glk);
+    memset(ct, 0, 2 * pq * 8);
+    for (int k = 0; k < 2; k++)
+        for (int i = 0; i < ll; i++) {
+            u64 f = prod_mod(Q + ll, drop, Q[i]);
+            for (size_t x = 0; x < n; x++)
+                ct[k * pq + (size_t)i * n + x] = orc_mulmod(low[k * pl + (size_t)i * n + x], f, Q[i]);
+        }
+    free(low);
     return 0;
 }
 

@@ -144,7 +144,7 @@ void *ref_create(int scheme, size_t n, const uint64_t *primes, int size_QP, int 
         if (gen_keys) {
             h->sk = std::make_unique<PhantomSecretKey>(*h->ctx);
             h->rlk = std::make_unique<PhantomRelinKey>(h->sk->gen_relinkey(*h->ctx));
-            if (n_steps > 0) h->glk = std::make_unique<PhantomGaloisKey>(h->sk->create_galois_keys(*h->ctx));
+            if (n_steps > 0 || gen_keys == 2) h->glk = std::make_unique<PhantomGaloisKey>(h->sk->create_galois_keys(*h->ctx));   // gen_keys 2: keys of the default elements
         }
         cudaStreamSynchronize(cudaStreamPerThread);
         return h;
@@ -843,6 +843,193 @@ int ref_time_op(void *p, int op, size_t chain_index, const uint64_t *ct1, const 
     cudaEventDestroy(e0);
     cudaEventDestroy(e1);
     return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+/* ---------------------------------------------------------------------------------------------------
+ * kernel-level launchers of include/ntt.cuh:172-226 on caller-supplied words.  buf = [total_limbs][n] host words
+ * (in place); aux = second host buffer where the launcher has one (input of the out-of-place forms, cx of
+ * fuse_moddown).  variant: 0 forward_inplace, 1 backward_inplace, 2 backward (out of place: aux -> buf),
+ * 3 forward_inplace_fuse_moddown (buf = delta on entry, ct on return; aux = cx; scale = bigPInv_mod_q),
+ * 4 forward_inplace_include_temp_mod (prm[0] = total), 5 forward_inplace_include_special_mod (prm = size_QP, size_P),
+ * 6 ..._include_special_mod_exclude_range (prm = size_QP, size_P, excl_start, excl_end),
+ * 7 forward_modup_fuse (aux -> buf, prm[0] = modulus_index), 8 backward_scale (aux -> buf), 9 backward_inplace_scale,
+ * 10 backward_inplace_include_special_mod (prm = size_QP, size_P), 11 backward_inplace_include_temp_mod_scale (prm[0] = total).
+ * table: 0 gpu_rns_tables, 1 gpu_Bsk_tables, 2 gpu_QlRl_tables.  scale: host values, Shoup companions made here
+ * with the table's own modulus (compute_shoup).
+ * ------------------------------------------------------------------------------------------------- */
+int ref_nwt(void *p, int variant, int table, uint64_t *buf, const uint64_t *aux, size_t total_limbs, size_t count,
+            size_t start, const size_t *prm, const uint64_t *scale, size_t n_scale, const uint64_t *scale_mod) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto &tool = h->ctx->get_context_data(1).gpu_rns_tool();
+    const DNTTTable &tab = table == 0 ? h->ctx->gpu_rns_tables() : table == 1 ? tool.gpu_Bsk_tables() : tool.gpu_QlRl_tables();
+    size_t words = total_limbs * h->n;
+    auto d = make_cuda_auto_ptr<uint64_t>(words, s);
+    auto d2 = make_cuda_auto_ptr<uint64_t>(words, s);
+    cudaMemcpyAsync(d.get(), buf, words * 8, cudaMemcpyHostToDevice, s);
+    if (aux) cudaMemcpyAsync(d2.get(), aux, words * 8, cudaMemcpyHostToDevice, s);
+    auto sc = make_cuda_auto_ptr<uint64_t>(n_scale + 1, s);
+    auto scs = make_cuda_auto_ptr<uint64_t>(n_scale + 1, s);
+    if (scale) {
+        std::vector<uint64_t> sh(n_scale);
+        for (size_t i = 0; i < n_scale; i++) sh[i] = compute_shoup(scale[i], scale_mod[i]);
+        cudaMemcpyAsync(sc.get(), scale, n_scale * 8, cudaMemcpyHostToDevice, s);
+        cudaMemcpyAsync(scs.get(), sh.data(), n_scale * 8, cudaMemcpyHostToDevice, s);
+        cudaStreamSynchronize(s);
+    }
+    switch (variant) {
+        case 0: nwt_2d_radix8_forward_inplace(d.get(), tab, count, start, s); break;
+        case 1: nwt_2d_radix8_backward_inplace(d.get(), tab, count, start, s); break;
+        case 2: nwt_2d_radix8_backward(d.get(), d2.get(), tab, count, start, s); break;
+        case 3: {
+            auto ct = make_cuda_auto_ptr<uint64_t>(words, s);
+            cudaMemsetAsync(ct.get(), 0, words * 8, s);
+            nwt_2d_radix8_forward_inplace_fuse_moddown(ct.get(), d2.get(), sc.get(), scs.get(), d.get(), tab, count, start, s);
+            cudaMemcpyAsync(d.get(), ct.get(), words * 8, cudaMemcpyDeviceToDevice, s);
+            cudaStreamSynchronize(s);
+            break;
+        }
+        case 4: nwt_2d_radix8_forward_inplace_include_temp_mod(d.get(), tab, count, start, prm[0], s); break;
+        case 5: nwt_2d_radix8_forward_inplace_include_special_mod(d.get(), tab, count, start, prm[0], prm[1], s); break;
+        case 6:
+            nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range(d.get(), tab, count, start, prm[0], prm[1], prm[2],
+                                                                            prm[3], s);
+            break;
+        case 7: nwt_2d_radix8_forward_modup_fuse(d.get(), d2.get(), prm[0], tab, count, start, s); break;
+        case 8: nwt_2d_radix8_backward_scale(d.get(), d2.get(), tab, count, start, sc.get(), scs.get(), s); break;
+        case 9: nwt_2d_radix8_backward_inplace_scale(d.get(), tab, count, start, sc.get(), scs.get(), s); break;
+        case 10: nwt_2d_radix8_backward_inplace_include_special_mod(d.get(), tab, count, start, prm[0], prm[1], s); break;
+        case 11:
+            nwt_2d_radix8_backward_inplace_include_temp_mod_scale(d.get(), tab, count, start, prm[0], sc.get(), scs.get(), s);
+            break;
+        default: throw std::invalid_argument("unknown launcher");
+    }
+    cudaMemcpyAsync(buf, d.get(), words * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+/* moduli of a table family (for building test inputs): 1 Bsk, 2 QlRl */
+int ref_table_moduli(void *p, int table, uint64_t *out, int cap) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto &tool = h->ctx->get_context_data(1).gpu_rns_tool();
+    const DNTTTable &tab = table == 0 ? h->ctx->gpu_rns_tables() : table == 1 ? tool.gpu_Bsk_tables() : tool.gpu_QlRl_tables();
+    int cnt = (int) tab.size();
+    std::vector<DModulus> m(cnt);
+    cudaMemcpy(m.data(), tab.modulus(), cnt * sizeof(DModulus), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < cnt && i < cap; i++) out[i] = m[i].value();
+    return cnt;
+    SHIM_CATCH
+}
+
+/* DBaseConverter::bConv_* of the converters a level owns.  which: 0 base_P_to_Ql_conv (key switch), 1 digit d's
+ * part_Ql -> compl_part_QlP converter (aux = d), 2 base_Ql_to_Rl_conv, 3 base_Rl_to_Ql_conv (BFV HPS).
+ * mode: 0 bConv_BEHZ, 1 bConv_BEHZ_var1, 2 bConv_HPS.  src = [ni][n], dst = [no][n] host words; returns no. */
+int ref_bconv(void *p, size_t chain_index, int which, int aux, int mode, const uint64_t *src, size_t ni, uint64_t *dst,
+              size_t no) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto &tool = h->ctx->get_context_data(chain_index).gpu_rns_tool();
+    const DBaseConverter &cv = which == 0 ? tool.base_P_to_Ql_conv()
+                             : which == 1 ? tool.base_part_Ql_to_compl_part_QlP_conv(aux)
+                             : which == 2 ? tool.base_Ql_to_Rl_conv() : tool.base_Rl_to_Ql_conv();
+    if (cv.ibase().size() != ni || cv.obase().size() != no) throw std::invalid_argument("base sizes differ");
+    auto in = make_cuda_auto_ptr<uint64_t>(ni * h->n, s);
+    auto out = make_cuda_auto_ptr<uint64_t>(no * h->n, s);
+    cudaMemcpyAsync(in.get(), src, ni * h->n * 8, cudaMemcpyHostToDevice, s);
+    if (mode == 0) cv.bConv_BEHZ(out.get(), in.get(), h->n, s);
+    else if (mode == 1) cv.bConv_BEHZ_var1(out.get(), in.get(), h->n, s);
+    else cv.bConv_HPS(out.get(), in.get(), h->n, s);
+    cudaMemcpyAsync(dst, out.get(), no * h->n * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+/* moduli of a converter's bases: out = ibase then obase; returns ni * 65536 + no */
+int ref_bconv_bases(void *p, size_t chain_index, int which, int aux, uint64_t *out, int cap) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto &tool = h->ctx->get_context_data(chain_index).gpu_rns_tool();
+    const DBaseConverter &cv = which == 0 ? tool.base_P_to_Ql_conv()
+                             : which == 1 ? tool.base_part_Ql_to_compl_part_QlP_conv(aux)
+                             : which == 2 ? tool.base_Ql_to_Rl_conv() : tool.base_Rl_to_Ql_conv();
+    int ni = (int) cv.ibase().size(), no = (int) cv.obase().size();
+    std::vector<DModulus> m(ni + no);
+    cudaMemcpy(m.data(), cv.ibase().base(), ni * sizeof(DModulus), cudaMemcpyDeviceToHost);
+    cudaMemcpy(m.data() + ni, cv.obase().base(), no * sizeof(DModulus), cudaMemcpyDeviceToHost);
+    for (int i = 0; i < ni + no && i < cap; i++) out[i] = m[i].value();
+    return ni * 65536 + no;
+    SHIM_CATCH
+}
+
+/* DRNSTool::moddown (rns_bconv.cu:712-761): cx_i = [l + size_P][n] -> out [l][n] */
+int ref_moddown_plain(void *p, size_t chain_index, const uint64_t *cx_i, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto &tool = h->ctx->get_context_data(chain_index).gpu_rns_tool();
+    size_t l = tool.base_Ql().size(), m = l + h->size_P;
+    auto buf = make_cuda_auto_ptr<uint64_t>(m * h->n, s);
+    auto ct = make_cuda_auto_ptr<uint64_t>(l * h->n, s);
+    cudaMemcpyAsync(buf.get(), cx_i, m * h->n * 8, cudaMemcpyHostToDevice, s);
+    tool.moddown(ct.get(), buf.get(), h->ctx->gpu_rns_tables(), h->scheme, s);
+    cudaMemcpyAsync(out, ct.get(), l * h->n * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+/* DRNSTool::divide_and_round_q_last (variant 1), divide_and_round_q_last_ntt (0), mod_t_and_divide_q_last_ntt (2):
+ * src = [size][l][n] -> dst = [size][l-1][n] */
+int ref_divide_round(void *p, int variant, size_t chain_index, const uint64_t *src, size_t size, uint64_t *dst) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto &tool = h->ctx->get_context_data(chain_index).gpu_rns_tool();
+    size_t l = tool.base_Ql().size();
+    auto in = make_cuda_auto_ptr<uint64_t>(size * l * h->n, s);
+    auto out = make_cuda_auto_ptr<uint64_t>(size * (l - 1) * h->n, s);
+    cudaMemcpyAsync(in.get(), src, size * l * h->n * 8, cudaMemcpyHostToDevice, s);
+    if (variant == 0) tool.divide_and_round_q_last_ntt(in.get(), size, h->ctx->gpu_rns_tables(), out.get(), s);
+    else if (variant == 1) tool.divide_and_round_q_last(in.get(), size, out.get(), s);
+    else tool.mod_t_and_divide_q_last_ntt(in.get(), size, h->ctx->gpu_rns_tables(), out.get(), s);
+    cudaMemcpyAsync(dst, out.get(), size * (l - 1) * h->n * 8, cudaMemcpyDeviceToHost, s);
+    cudaStreamSynchronize(s);
+    return cudaGetLastError() == cudaSuccess ? 0 : -1;
+    SHIM_CATCH
+}
+
+/* hoisting_inplace (evaluate.cu:1670-1865) over `n_steps` steps; noise_deg = noiseScaleDeg of the input (BFV leveled) */
+int ref_hoisting(void *p, size_t chain_index, const uint64_t *ct, const int *steps, int n_steps, size_t noise_deg,
+                 uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    auto a = make_ct(h, chain_index, 2, ct, h->scheme != scheme_type::bfv);
+    a.SetNoiseScaleDeg(noise_deg);
+    hoisting_inplace(*h->ctx, a, *h->glk, std::vector<int>(steps, steps + n_steps));
+    fetch_ct(a, out);
+    return 0;
+    SHIM_CATCH
+}
+
+/* keyswitch_inplace (eval_key_switch.cu:95-182) with the relin key: ct = [2][l][n] += keyswitch(c2 [l][n]) */
+int ref_keyswitch(void *p, size_t chain_index, const uint64_t *ct, const uint64_t *c2, uint64_t *out) {
+    SHIM_TRY
+    auto h = static_cast<RefCtx *>(p);
+    const auto &s = cudaStreamPerThread;
+    auto a = make_ct(h, chain_index, 2, ct, h->scheme != scheme_type::bfv);
+    size_t words = a.coeff_modulus_size() * h->n;
+    auto d = make_cuda_auto_ptr<uint64_t>(words, s);
+    cudaMemcpyAsync(d.get(), c2, words * 8, cudaMemcpyHostToDevice, s);
+    keyswitch_inplace(*h->ctx, a, d.get(), *h->rlk, true, s);
+    fetch_ct(a, out);
+    return 0;
     SHIM_CATCH
 }
 

@@ -38,6 +38,24 @@ _sigs = {
     "pfhe_ntt_backward": (ctypes.c_int, [vp, vp, vp, sz, sz, vp]),
     "pfhe_ntt_forward_inplace_include_special_mod": (ctypes.c_int, [vp, vp, sz, sz, sz, sz, vp]),
     "pfhe_ntt_backward_inplace_include_special_mod": (ctypes.c_int, [vp, vp, sz, sz, sz, sz, vp]),
+    "pfhe_table_size": (ctypes.c_int, [vp, ctypes.c_int]),
+    "pfhe_table_modulus": (ctypes.c_uint64, [vp, ctypes.c_int, sz]),
+    "pfhe_nwt_2d_radix8_forward_inplace": (ctypes.c_int, [vp, ctypes.c_int, vp, sz, sz, vp]),
+    "pfhe_nwt_2d_radix8_backward_inplace": (ctypes.c_int, [vp, ctypes.c_int, vp, sz, sz, vp]),
+    "pfhe_nwt_2d_radix8_backward": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, sz, sz, vp]),
+    "pfhe_nwt_2d_radix8_forward_inplace_fuse_moddown": (ctypes.c_int, [vp, vp, vp, vp, vp, vp, sz, sz, vp]),
+    "pfhe_nwt_2d_radix8_forward_inplace_include_temp_mod": (ctypes.c_int, [vp, ctypes.c_int, vp, sz, sz, sz, vp]),
+    "pfhe_nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range": (ctypes.c_int, [vp, vp, sz, sz, sz, sz, sz, sz, vp]),
+    "pfhe_nwt_2d_radix8_forward_modup_fuse": (ctypes.c_int, [vp, vp, vp, sz, sz, sz, vp]),
+    "pfhe_nwt_2d_radix8_backward_scale": (ctypes.c_int, [vp, ctypes.c_int, vp, vp, sz, sz, vp, vp, vp]),
+    "pfhe_nwt_2d_radix8_backward_inplace_scale": (ctypes.c_int, [vp, ctypes.c_int, vp, sz, sz, vp, vp, vp]),
+    "pfhe_nwt_2d_radix8_backward_inplace_include_temp_mod_scale": (ctypes.c_int, [vp, ctypes.c_int, vp, sz, sz, sz, vp, vp, vp]),
+    "pfhe_bconv": (ctypes.c_int, [vp, ctypes.c_int, u32p, ctypes.c_int, u32p, ctypes.c_int, vp, vp, vp]),
+    "pfhe_moddown": (ctypes.c_int, [vp, sz, vp, vp, vp]),
+    "pfhe_divide_and_round_q_last": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_divide_and_round_q_last_ntt": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_mod_t_and_divide_q_last_ntt": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
+    "pfhe_add_to_ct": (ctypes.c_int, [vp, vp, vp, sz, vp]),
     "pfhe_tensor_prod_2x2": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
     "pfhe_tensor_square_2x2": (ctypes.c_int, [vp, vp, vp, sz, vp]),
     "pfhe_add_rns_poly": (ctypes.c_int, [vp, vp, vp, vp, sz, vp]),
@@ -56,6 +74,7 @@ _sigs = {
     "pfhe_rotate_batch": (ctypes.c_int, [vp, sz, vp, i32p, vp, sz, vp]),
     "pfhe_rotate_inplace": (ctypes.c_int, [vp, sz, vp, ctypes.c_int, vp, vp]),
     "pfhe_hoisting_inplace": (ctypes.c_int, [vp, sz, vp, i32p, sz, vp, vp]),
+    "pfhe_hoisting_leveled_inplace": (ctypes.c_int, [vp, vp, i32p, sz, vp, ctypes.c_int, vp]),
     "pfhe_rescale_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_mod_switch_to_next": (ctypes.c_int, [vp, sz, vp, sz, vp, vp]),
     "pfhe_ckks_encode": (ctypes.c_int, [vp, sz, vp, sz, ctypes.c_double, vp, vp]),

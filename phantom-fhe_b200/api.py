@@ -804,20 +804,9 @@ def hoisting_inplace(context, ct, glk, steps):
     """hoisting_inplace (src/evaluate.cu:1670-1865)."""
     if ct.size() > 2:
         raise ValueError("ciphertext size must be 2")
-    if context.scheme == scheme_type.bfv:
-        # the engine's hoisted form is built for the NTT-form schemes; for BFV the sum is composed from the rotations
-        # themselves: the same plaintext as the reference's hoisted result, not the same words (no shared mod-up)
-        total = None
-        for s in steps:
-            term = ct.clone()
-            rotate_inplace(context, term, s, glk)
-            if total is None:
-                total = term
-            else:
-                add_inplace(context, total, term)
-        if total is not None:
-            ct.data = total.data
-        return
+    if context.scheme == scheme_type.bfv and ct.chain_index != 1:
+        # the reference takes the first level's tool whatever the ciphertext's level (evaluate.cu:1688-1708)
+        raise ValueError("BFV hoisting is built for the first data level")
     elts = context.parms.galois_elts
     ptrs = []
     for s in steps:
@@ -827,6 +816,10 @@ def hoisting_inplace(context, ct, glk, steps):
         ptrs.append(glk.get_relin_keys(elts.index(e)).public_keys_ptr().value)
     arr = (ctypes.c_void_p * len(ptrs))(*ptrs)
     st = (ctypes.c_int * len(steps))(*steps)
+    if _leveled(context):   # hps_overq_leveled: a key switch at the depth of the ciphertext (evaluate.cu:1690-1701)
+        drop = _levels_to_drop(context, ct.noise_scale_deg - 1, True, ct.is_asymmetric)
+        check(lib.pfhe_hoisting_leveled_inplace(context._h, _ptr(ct.data), st, len(steps), arr, drop, _stream()))
+        return
     check(lib.pfhe_hoisting_inplace(context._h, ct.chain_index, _ptr(ct.data), st, len(steps), arr, _stream()))
 
 

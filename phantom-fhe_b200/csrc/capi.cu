@@ -179,15 +179,16 @@ int pfhe_galois_elt_from_step(int step, uint64_t n, uint32_t *elt_out) {
 int pfhe_ntt_forward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, void *stream) {
     API_BEGIN
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
-    // reference semantics: limb i of the buffer (0-based from `inout`) uses table row start+i
-    e->impl.ntt_fwd_rows_range(U(inout), (int) count, (int) start, S(stream));
+    // reference addressing: limbs [start, start + count) of the buffer, limb i with table row i (fntt_2d.cu:35-40)
+    e->impl.ntt_fwd_rows_range(U(inout) + start * e->impl.n(), (int) count, (int) start, S(stream));
     API_END
 }
 
 int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, void *stream) {
     API_BEGIN
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
-    e->impl.ntt_inv_rows_range(U(inout), U(inout), (int) count, (int) start, S(stream));
+    u64 *p = U(inout) + start * e->impl.n();
+    e->impl.ntt_inv_rows_range(p, p, (int) count, (int) start, S(stream));
     API_END
 }
 
@@ -210,7 +211,7 @@ int pfhe_ntt_backward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_po
 int pfhe_ntt_backward(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t count, size_t start, void *stream) {
     API_BEGIN
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
-    e->impl.ntt_inv_rows_range(U(out), U(in), (int) count, (int) start, S(stream));
+    e->impl.ntt_inv_rows_range(U(out) + start * e->impl.n(), U(in) + start * e->impl.n(), (int) count, (int) start, S(stream));
     API_END
 }
 
@@ -237,6 +238,137 @@ int pfhe_ntt_backward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inou
                                                   size_t size_QP, size_t size_P, void *stream) {
     API_BEGIN
     special_mod(e, inout, count, start, size_QP, size_P, true, stream);
+    API_END
+}
+
+
+// ---- the remaining launchers of include/ntt.cuh:172-226 and the DRNSTool / DBaseConverter members -------------------
+int pfhe_table_size(const pfhe_engine *e, int table) {
+    try {
+        return e ? e->impl.table_size(table) : 0;
+    } catch (...) { return 0; }
+}
+uint64_t pfhe_table_modulus(const pfhe_engine *e, int table, size_t idx) {
+    try {
+        return e ? e->impl.row_modulus(e->impl.table_row(table, idx)) : 0;
+    } catch (...) { return 0; }
+}
+static Engine::NttCall ntt_call(bool inverse, int table, size_t count, size_t start) {
+    Engine::NttCall c;
+    c.inverse = inverse, c.table = table, c.count = count, c.start = start;
+    return c;
+}
+int pfhe_nwt_2d_radix8_forward_inplace(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start, void *stream) {
+    API_BEGIN
+    e->impl.ntt_call(U(inout), U(inout), ntt_call(false, table, count, start), nullptr, nullptr, S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_backward_inplace(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start, void *stream) {
+    API_BEGIN
+    e->impl.ntt_call(U(inout), U(inout), ntt_call(true, table, count, start), nullptr, nullptr, S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_backward(pfhe_engine *e, int table, uint64_t *out, const uint64_t *in, size_t count, size_t start,
+                                void *stream) {
+    API_BEGIN
+    e->impl.ntt_call(U(out), U(in), ntt_call(true, table, count, start), nullptr, nullptr, S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_forward_inplace_fuse_moddown(pfhe_engine *e, uint64_t *ct, const uint64_t *cx, const uint64_t *pinv,
+                                                    const uint64_t *pinv_shoup, uint64_t *delta, size_t count, size_t start,
+                                                    void *stream) {
+    API_BEGIN
+    require(ct && cx && pinv && pinv_shoup && delta, "null argument");
+    e->impl.ntt_fuse_moddown(U(ct), U(cx), U(pinv), U(pinv_shoup), U(delta), count, start, S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_forward_inplace_include_temp_mod(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start,
+                                                        size_t total, void *stream) {
+    API_BEGIN
+    auto c = ntt_call(false, table, count, start);
+    c.remap = 2, c.a = total;
+    e->impl.ntt_call(U(inout), U(inout), c, nullptr, nullptr, S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range(pfhe_engine *e, uint64_t *inout, size_t count,
+                                                                         size_t start, size_t size_QP, size_t size_P,
+                                                                         size_t excl_lo, size_t excl_hi, void *stream) {
+    API_BEGIN
+    require((int) size_QP == e->impl.size_QP() && (int) size_P == e->impl.size_P(), "size_QP/size_P mismatch");
+    auto c = ntt_call(false, Engine::TABLE_RNS, count, start);
+    c.remap = 1, c.a = size_QP, c.b = size_P, c.excl_lo = excl_lo, c.excl_hi = excl_hi;
+    e->impl.ntt_call(U(inout), U(inout), c, nullptr, nullptr, S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_forward_modup_fuse(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t modulus_index, size_t count,
+                                          size_t start, void *stream) {
+    API_BEGIN
+    auto c = ntt_call(false, Engine::TABLE_RNS, count, start);
+    c.fixed_entry = (long) modulus_index;
+    e->impl.ntt_call(U(out), U(in), c, nullptr, nullptr, S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_backward_scale(pfhe_engine *e, int table, uint64_t *out, const uint64_t *in, size_t count, size_t start,
+                                      const uint64_t *scale, const uint64_t *scale_shoup, void *stream) {
+    API_BEGIN
+    require(scale && scale_shoup, "null argument");
+    e->impl.ntt_call(U(out), U(in), ntt_call(true, table, count, start), U(scale), U(scale_shoup), S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_backward_inplace_scale(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start,
+                                              const uint64_t *scale, const uint64_t *scale_shoup, void *stream) {
+    API_BEGIN
+    require(scale && scale_shoup, "null argument");
+    e->impl.ntt_call(U(inout), U(inout), ntt_call(true, table, count, start), U(scale), U(scale_shoup), S(stream));
+    API_END
+}
+int pfhe_nwt_2d_radix8_backward_inplace_include_temp_mod_scale(pfhe_engine *e, int table, uint64_t *inout, size_t count,
+                                                               size_t start, size_t total, const uint64_t *scale,
+                                                               const uint64_t *scale_shoup, void *stream) {
+    API_BEGIN
+    require(scale && scale_shoup, "null argument");
+    auto c = ntt_call(true, table, count, start);
+    c.remap = 2, c.a = total;
+    e->impl.ntt_call(U(inout), U(inout), c, U(scale), U(scale_shoup), S(stream));
+    API_END
+}
+int pfhe_bconv(pfhe_engine *e, int mode, const uint32_t *ibase, int ni, const uint32_t *obase, int no, uint64_t *dst,
+               const uint64_t *src, void *stream) {
+    API_BEGIN
+    require(ibase && obase && ni > 0 && no > 0 && dst && src, "base is invalid");
+    std::vector<int> in_rows, out_rows;
+    for (int i = 0; i < ni; i++) in_rows.push_back(e->impl.table_row((int) (ibase[i] >> 16), ibase[i] & 0xffffu));
+    for (int j = 0; j < no; j++) out_rows.push_back(e->impl.table_row((int) (obase[j] >> 16), obase[j] & 0xffffu));
+    e->impl.bconv(mode, e->impl.converter(in_rows, out_rows), U(dst), U(src), S(stream));
+    API_END
+}
+int pfhe_moddown(pfhe_engine *e, size_t chain_index, uint64_t *ct_i, uint64_t *cx_i, void *stream) {
+    API_BEGIN
+    e->impl.moddown_plain(e->impl.limbs_at(chain_index), U(ct_i), U(cx_i), S(stream));
+    API_END
+}
+int pfhe_divide_and_round_q_last(pfhe_engine *e, size_t chain_index, const uint64_t *src, size_t size, uint64_t *dst,
+                                 void *stream) {
+    API_BEGIN
+    e->impl.divide_round_q_last(e->impl.limbs_at(chain_index), U(dst), U(src), (int) size, 1, S(stream));
+    API_END
+}
+int pfhe_divide_and_round_q_last_ntt(pfhe_engine *e, size_t chain_index, const uint64_t *src, size_t size, uint64_t *dst,
+                                     void *stream) {
+    API_BEGIN
+    e->impl.rescale(e->impl.limbs_at(chain_index), U(dst), U(src), (int) size, S(stream));
+    API_END
+}
+int pfhe_mod_t_and_divide_q_last_ntt(pfhe_engine *e, size_t chain_index, const uint64_t *src, size_t size, uint64_t *dst,
+                                     void *stream) {
+    API_BEGIN
+    e->impl.divide_round_q_last(e->impl.limbs_at(chain_index), U(dst), U(src), (int) size, 2, S(stream));
+    API_END
+}
+int pfhe_add_to_ct(pfhe_engine *e, uint64_t *ct, const uint64_t *cx, size_t size_Ql, void *stream) {
+    API_BEGIN
+    require(size_Ql >= 1 && size_Ql <= (size_t) e->impl.size_QP(), "coeff_mod_size is invalid");
+    e->impl.elementwise(EW_ADD, U(ct), U(cx), U(ct), (int) size_Ql, S(stream));
     API_END
 }
 
@@ -582,6 +714,19 @@ int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, cons
         keys[i] = K(galois_keys[i]);
     }
     e->impl.hoisting(l, U(ct), elts, keys, S(stream));
+    API_END
+}
+int pfhe_hoisting_leveled_inplace(pfhe_engine *e, uint64_t *ct, const int *steps, size_t n_steps,
+                                  const uint64_t *const *const *galois_keys, int levels_dropped, void *stream) {
+    API_BEGIN
+    require(steps && galois_keys && n_steps > 0, "steps is empty");
+    std::vector<uint32_t> elts(n_steps);
+    std::vector<const u64 *const *> keys(n_steps);
+    for (size_t i = 0; i < n_steps; i++) {
+        if (pfhe_galois_elt_from_step(steps[i], e->impl.n(), &elts[i]) != PFHE_OK) throw std::invalid_argument(g_error);
+        keys[i] = K(galois_keys[i]);
+    }
+    e->impl.hoisting(e->impl.size_Q(), U(ct), elts, keys, S(stream), levels_dropped);
     API_END
 }
 int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *dst,

@@ -323,6 +323,12 @@ void Engine::build_tables() {
     d_tw_.upload(tw);
     d_itw_.upload(itw);
     d_inv_fin_.upload(fin);
+    {
+        std::vector<u64> fi((size_t) 2 * mod_rows_);
+        for (int i = 0; i < mod_rows_; i++)
+            fi[2 * i] = h_ninv_[i], fi[2 * i + 1] = h_ninv_[i] ? hm::mulmod(h_itw1_[i], h_ninv_[i], rowq_[i]) : 0;
+        d_fin_int_.upload(fi);
+    }
     d_mod_.upload(mods);
     // single-word Barrett constants: growth class g covers values < 2^(2k+g), k = bit length of q
     std::vector<BarG> bars((size_t) 64 * mod_rows_);
@@ -959,8 +965,9 @@ void Engine::moddown_generic(int l, u64 *out, u64 *cx, int npoly, const u64 *add
     }
 }
 
-void Engine::mod_switch_scale(int l, u64 *out, const u64 *in, int size, cudaStream_t st) {
+void Engine::divide_round_q_last(int l, u64 *out, const u64 *in, int size, int mode, cudaStream_t st) {
     Workspace &ws_ = ws(st);
+    if (mode != 1 && mode != 2) throw std::invalid_argument("unsupported scheme");
     if (l < 2) throw std::invalid_argument("end of modulus switching chain reached");
     const Level &lv = level(l);
     const int nl = l - 1;
@@ -968,7 +975,7 @@ void Engine::mod_switch_scale(int l, u64 *out, const u64 *in, int size, cudaStre
     for (int s = 0; s < size; s++) {
         const u64 *ci = in + (size_t) s * l * n_;
         u64 *co = out + (size_t) s * nl * n_;
-        if (scheme_ == Scheme::bfv) {
+        if (mode == 1) {
             launch_pdl(k_divide_round_last, grid, EW_THREADS, 0, st, co, ci, lv.qlast_inv_slots.p, d_mod_.p, n_, nl);
             check_launch("k_divide_round_last");
         } else {   // BGV
@@ -1881,34 +1888,67 @@ void Engine::apply_galois(int l, u64 *ct, uint32_t galois_elt, const u64 *const 
     keyswitch_fused(l, ct, tmp + (size_t) l * n_, nullptr, glk, tmp, 1u, st);
 }
 
-// hoisting_inplace (reference src/evaluate.cu:1670-1865), CKKS/BGV
+// hoisting_inplace (reference src/evaluate.cu:1670-1865): one mod-up of c1 shared by all rotations, the automorphism of the
+// digits folded into the inner product, one mod-down.  BFV: coefficient-form ends (apply_galois on c0, mod-up from and
+// mod-down to coefficient form); under hps_overq_leveled with `drop` levels dropped the ciphertext is first scaled from Q
+// to Ql (scaleAndRound_HPS_Q_Ql, :1731-1733,1761-1763) and the result expanded back (ExpandCRTBasis_Ql_Q, :1847-1862).
 void Engine::hoisting(int l, u64 *ct, const std::vector<uint32_t> &elts, const std::vector<const u64 *const *> &keys,
-                      cudaStream_t st) {
+                      cudaStream_t st, int drop) {
     Workspace &ws_ = ws(st);
-    if (scheme_ == Scheme::bfv) throw std::invalid_argument("unsupported scheme");
     if (elts.empty() || elts.size() != keys.size()) throw std::invalid_argument("steps / keys mismatch");
-    const Level &lv = level(l);
-    const size_t poly = (size_t) l * n_;
-    u64 *acc_c0 = ws_.tmp.p;                 // [l][n]
+    const bool bfv = scheme_ == Scheme::bfv;
+    if (drop && (!bfv || mul_tech_ != 4 || l != size_Q_)) throw std::invalid_argument("levels can be dropped under hps_overq_leveled only");
+    if (drop < 0 || drop >= l) throw std::invalid_argument("levels dropped is out of range");
+    const int ll = l - drop;
+    const Level &lv = level(ll);
+    (void) lv;
+    const size_t poly = (size_t) ll * n_, pq = (size_t) l * n_;
+    u64 *acc_c0 = ws_.tmp.p;                 // [ll][n]
     u64 *c0 = ws_.tmp.p + poly, *c1 = ws_.tmp.p + 2 * poly;   // private copies: ct is overwritten at the end
-    PFHE_CUDA(cudaMemcpyAsync(c0, ct, 2 * poly * 8, cudaMemcpyDeviceToDevice, st));
-    // one mod-up of c1 for all rotations (:1761)
-    modup(l, ws_.t_mod_up.p, c1, ws_.t_cks.p, st);
-    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+    if (drop) {
+        const HpsQ &h = hpsq(drop);
+        ScaleRoundArgs a{PolyView{ct, pq}, PolyView{ct + poly, pq}, PolyView{c0, poly}, h.dr_tab.p, h.dr_frac.p, nullptr, d_mod_.p,
+                         ll, drop, 0, n_};
+        launch_pdl(k_scale_round, dim3((unsigned) (n_ / BEHZ_THREADS), 2), BEHZ_THREADS, 0, st, a);
+        check_launch("k_scale_round");
+    } else {
+        PFHE_CUDA(cudaMemcpyAsync(c0, ct, 2 * poly * 8, cudaMemcpyDeviceToDevice, st));
+    }
+    // one mod-up of c1 for all rotations (:1769)
+    modup(ll, ws_.t_mod_up.p, c1, ws_.t_cks.p, st);
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), ll);
     for (size_t i = 0; i < elts.size(); i++) {
         int gi;
         try {
             gi = galois_index(elts[i]);
         } catch (const std::invalid_argument &) { throw std::logic_error("Galois key not present in hoisting"); }
-        if (i == 0) launch_pdl(k_galois_ntt, grid, EW_THREADS, 0, st, acc_c0, c0, d_perm_[gi].p, n_);
-        else launch_pdl(k_galois_ntt_acc, grid, EW_THREADS, 0, st, acc_c0, c0, d_perm_[gi].p, d_mod_.p, n_);
-        check_launch("k_galois_ntt");
+        if (bfv) {   // apply_galois on the coefficient form (:1745-1747, 1808-1810)
+            if (i == 0) {
+                galois_coeff(acc_c0, c0, elts[i], ll, 1, st);
+            } else {
+                u64 *t = ws_.delta.p;
+                galois_coeff(t, c0, elts[i], ll, 1, st);
+                elementwise(EW_ADD, acc_c0, t, acc_c0, ll, st);
+            }
+        } else {
+            if (i == 0) launch_pdl(k_galois_ntt, grid, EW_THREADS, 0, st, acc_c0, c0, d_perm_[gi].p, n_);
+            else launch_pdl(k_galois_ntt_acc, grid, EW_THREADS, 0, st, acc_c0, c0, d_perm_[gi].p, d_mod_.p, n_);
+            check_launch("k_galois_ntt");
+        }
         // automorphism of the digits + inner product + accumulation in one kernel
-        inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, keys[i], st, nullptr, nullptr, d_perm_[gi].p, i > 0);
+        inner_prod(ll, ws_.cx.p, ws_.t_mod_up.p, keys[i], st, nullptr, nullptr, d_perm_[gi].p, i > 0);
     }
     // one mod-down per polynomial; new c0 = acc_c0 + moddown(cx0), new c1 = moddown(cx1)
-    if (scheme_ == Scheme::ckks) moddown(l, ct, ws_.cx.p, ws_.delta.p, 2, acc_c0, 1u, st);
-    else moddown_generic(l, ct, ws_.cx.p, 2, acc_c0, 1u, st);
+    u64 *out = drop ? c0 : ct;
+    if (scheme_ == Scheme::ckks) moddown(ll, out, ws_.cx.p, ws_.delta.p, 2, acc_c0, 1u, st);
+    else moddown_generic(ll, out, ws_.cx.p, 2, acc_c0, 1u, st);
+    if (drop) {
+        const HpsQ &h = hpsq(drop);
+        PFHE_CUDA(cudaMemsetAsync(ct, 0, 2 * pq * 8, st));
+        launch_pdl(k_expand_add, dim3((unsigned) (n_ / (2 * BEHZ_THREADS)), 2 * ll), BEHZ_THREADS, 0, st, PolyView{ct, pq},
+                   PolyView{c0, poly}, (const Tw *) h.expand.p, (const Modulus *) d_mod_.p, ll, n_);
+        check_launch("k_expand_add");
+    }
 }
 
 // rescale_to_next for CKKS (reference src/evaluate.cu:1376-1427 + divide_and_round_q_last_ntt rns.cu:1160-1184)
@@ -2144,6 +2184,197 @@ void Engine::multiply_scalar(int l, u64 *inout, int size, u64 scalar, cudaStream
                    (const Modulus *) d_mod_.p, n_);
         check_launch("k_axpy");
     }
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// The reference's kernel-level launchers with the reference's own addressing (cut line 2): thin forms over
+// the LimbList machinery above, for a maintainer who keeps evaluate.cu / rns.cu untouched and swaps the launchers only.
+// ---------------------------------------------------------------------------------------------------------------------
+// `table` = family | chain_index << 8 (chain_index 0 = the first data level): the Bsk and QlRl tables belong to a level's
+// DRNSTool in the reference (rns.cu:435-448, 700-714)
+int Engine::table_size(int table) const {
+    const int fam = table & 0xff, ci = table >> 8;
+    const int l = limbs_at(ci ? (size_t) ci : 1);
+    switch (fam) {
+        case TABLE_RNS: return size_QP_;
+        case TABLE_BSK: {
+            if (!naux_) return 0;
+            std::vector<u64> ql(primes_.begin(), primes_.begin() + l);
+            const int tb = 64 - __builtin_clzll(t_);
+            return l + ((32 + tb + hm::product_bits(ql) >= 61 * l + 61) ? 1 : 0) + 1;   // base_B_size + m_sk (rns.cu:400-406)
+        }
+        case TABLE_QLRL: return nR_ ? l + std::min(nR_, l + 1) : 0;
+        case TABLE_PLAIN: return (t_ > 1 && batching_) ? 1 : 0;
+        default: throw std::invalid_argument("unknown table family");
+    }
+}
+
+int Engine::table_row(int table, size_t idx) const {
+    const int size = table_size(table);
+    if ((long) idx >= (long) size) throw std::invalid_argument("modulus index out of range");
+    const int fam = table & 0xff, ci = table >> 8;
+    const int l = limbs_at(ci ? (size_t) ci : 1);
+    switch (fam) {
+        case TABLE_RNS: return (int) idx;
+        // gpu_Bsk_tables: B_0 .. B_{nB-1}, then m_sk; stored here as [m_sk, B...]
+        case TABLE_BSK: return (int) idx == size - 1 ? row_aux_ : row_aux_ + 1 + (int) idx;
+        // gpu_QlRl_tables: the level's Q rows, then R rows
+        case TABLE_QLRL: return (int) idx < l ? (int) idx : row_R_ + ((int) idx - l);
+        default: return size_QP_;   // the plain modulus
+    }
+}
+
+void Engine::ntt_call(u64 *out, const u64 *in, const NttCall &c, const u64 *scale, const u64 *scale_shoup, cudaStream_t st) {
+    if (c.count == 0) return;
+    if ((scale == nullptr) != (scale_shoup == nullptr)) throw std::invalid_argument("scale and scale_shoup go together");
+    if (scale && !c.inverse) throw std::invalid_argument("only the inverse transforms take a scale");
+    LimbVec v;
+    std::vector<int> sidx;   // index into scale[] per slot
+    for (size_t i = 0; i < c.count; i++) {
+        const size_t idx = c.start + i;
+        if (idx >= c.excl_lo && idx < c.excl_hi) continue;
+        size_t entry = idx;
+        if (c.fixed_entry >= 0) entry = (size_t) c.fixed_entry;
+        else if (c.remap == 1) {   // fntt_2d.cu:433-436
+            if (c.b > c.count || c.start + c.count > c.a + c.count) throw std::invalid_argument("modulus index out of range");
+            if (idx >= c.start + c.count - c.b) entry = c.a - (c.start + c.count - idx);
+        } else if (c.remap == 2) {   // fntt_2d.cu:225-226: the last limb of the window uses the last table entry
+            if (idx == c.count - 1) entry = c.a - 1;
+        }
+        if (idx > 32000) throw std::invalid_argument("modulus index out of range");
+        v.push((int) idx, table_row(c.table, entry));
+        sidx.push_back((int) (c.remap == 2 ? entry : idx));
+    }
+    for (size_t b = 0; b < v.size();) {
+        size_t taken;
+        const LimbList ll = v.chunk(b, taken, rowq_);
+        if (!c.inverse) {
+            ntt_fwd_list(out, in, ll, st);
+        } else if (!scale) {
+            ntt_inv_list(out, in, ll, nullptr, 0, st);
+        } else {
+            // constants of the last inverse stage from the caller's device arrays: {n^-1 s, itw[1] n^-1 s} per slot
+            Workspace &w = ws(st);
+            if (w.fin.count < 2 * NTT_MAX_LIMBS) w.fin.alloc(2 * NTT_MAX_LIMBS);
+            FinList fl{};
+            fl.count = ll.count;
+            for (int k = 0; k < ll.count; k++) fl.row[k] = ll.row[k], fl.idx[k] = (short) sidx[b + k];
+            launch_pdl(k_make_fin, dim3(1), dim3(NTT_MAX_LIMBS), 0, st, w.fin.p, scale, fl, (const u64 *) d_fin_int_.p,
+                       (const Modulus *) d_mod_.p, (const unsigned char *) d_is_fp_.p, plan_.fp_enabled);
+            check_launch("k_make_fin");
+            ntt_inv_list(out, in, ll, w.fin.p, 1, st);
+        }
+        b += taken;
+    }
+}
+
+void Engine::ntt_fuse_moddown(u64 *ct, const u64 *cx, const u64 *pinv, const u64 *pinv_shoup, u64 *delta, size_t count,
+                              size_t start, cudaStream_t st) {
+    if (count == 0) return;
+    if (start + count > (size_t) size_QP_) throw std::invalid_argument("modulus index out of range");
+    LimbVec v;
+    for (size_t i = 0; i < count; i++) v.push((int) (start + i), (int) (start + i));
+    Workspace &w = ws(st);
+    if (w.fin.count < 2 * NTT_MAX_LIMBS) w.fin.alloc(2 * NTT_MAX_LIMBS);
+    for (size_t b = 0; b < v.size();) {
+        size_t taken;
+        const LimbList ll = v.chunk(b, taken, rowq_);
+        FinList fl{};
+        fl.count = ll.count;
+        for (int k = 0; k < ll.count; k++) fl.row[k] = ll.row[k], fl.idx[k] = ll.data[k];
+        launch_pdl(k_zip_tw, dim3(1), dim3(NTT_MAX_LIMBS), 0, st, w.fin.p, pinv, pinv_shoup, fl);
+        check_launch("k_zip_tw");
+        EpiArgs ea{};
+        ea.sub_base = cx, ea.out_base = ct, ea.add_base = nullptr, ea.mulc = w.fin.p;
+        for (int k = 0; k < ll.count; k++) ea.sub[k] = ea.out[k] = ll.data[k], ea.add[k] = -1;
+        g_launches.fetch_add(2, std::memory_order_relaxed);
+        PFHE_CUDA(ntt_forward_epilogue(plan_, delta, ll, ea, st));
+        b += taken;
+    }
+}
+
+const Engine::Converter &Engine::converter(const std::vector<int> &in_rows, const std::vector<int> &out_rows) {
+    std::lock_guard<std::recursive_mutex> g(table_mu_);
+    auto &slot = converters_[{in_rows, out_rows}];
+    if (slot) return *slot;
+    const int ni = (int) in_rows.size(), no = (int) out_rows.size();
+    if (ni < 1 || no < 1 || ni > BEHZ_MAX_LIMBS || no > BEHZ_MAX_LIMBS) throw std::invalid_argument("base size is not supported");
+    std::vector<u64> ib, ob;
+    for (int r : in_rows) {
+        if (r < 0 || r >= mod_rows_) throw std::invalid_argument("modulus index out of range");
+        ib.push_back(rowq_[r]);
+    }
+    for (int r : out_rows) {
+        if (r < 0 || r >= mod_rows_) throw std::invalid_argument("modulus index out of range");
+        ob.push_back(rowq_[r]);
+    }
+    auto cv = std::make_unique<Converter>();
+    cv->in_rows = in_rows, cv->out_rows = out_rows;
+    std::vector<Modulus> mi, mo;
+    for (u64 q : ib) mi.push_back(host_modulus(q));
+    for (u64 q : ob) mo.push_back(host_modulus(q));
+    std::vector<Tw> hinv(ni), v1c(ni);
+    std::vector<double> inv(ni);
+    std::vector<u64> mat((size_t) no * ni), Imod(no), v1m((size_t) no * ni);
+    for (int i = 0; i < ni; i++) {
+        const u64 q = ib[i];
+        const u64 hat_inv = hm::invmod(hm::product_mod(ib, i, q), q);
+        hinv[i] = make_tw(hat_inv, q);
+        inv[i] = 1.0 / (double) q;
+        // negPQHatInvModq (host/rns.cu:478-483): -(O mod q_i) * ihat_i^-1 mod q_i, stored unreduced as q - x (may equal q)
+        const u64 PQ = hm::mulmod(hm::product_mod(ob, -1, q), hat_inv, q);
+        v1c[i] = make_ulonglong2(q - PQ, 0);
+    }
+    for (int j = 0; j < no; j++) {
+        const u64 p = ob[j];
+        Imod[j] = hm::product_mod(ib, -1, p);
+        for (int i = 0; i < ni; i++) {
+            mat[(size_t) j * ni + i] = hm::product_mod(ib, i, p);
+            v1m[(size_t) j * ni + i] = (ib[i] % p) ? hm::invmod(ib[i] % p, p) : 0;
+        }
+    }
+    cv->mod_in.upload(mi), cv->mod_out.upload(mo), cv->hinv.upload(hinv), cv->inv.upload(inv), cv->mat.upload(mat);
+    cv->Imod.upload(Imod), cv->v1_c.upload(v1c), cv->v1_mat.upload(v1m);
+    slot = std::move(cv);
+    return *slot;
+}
+
+void Engine::bconv(int mode, const Converter &cv, u64 *dst, const u64 *src, cudaStream_t st) {
+    const int ni = (int) cv.in_rows.size(), no = (int) cv.out_rows.size();
+    const dim3 grid((unsigned) (n_ / BEHZ_THREADS), 1);
+    const PolyView in{const_cast<u64 *>(src), 0}, out{dst, 0};
+    if (mode == 0) {          // bConv_BEHZ: y_i = x_i ihat_i^-1, out_j = sum y_i (ihat_i mod o_j)
+        BconvVar1Args a{in, out, cv.hinv.p, cv.mat.p, cv.mod_in.p, cv.mod_out.p, ni, no, n_};
+        launch_pdl(k_bconv_var1, grid, BEHZ_THREADS, 0, st, a);
+    } else if (mode == 1) {   // bConv_BEHZ_var1
+        BconvVar1Args a{in, out, cv.v1_c.p, cv.v1_mat.p, cv.mod_in.p, cv.mod_out.p, ni, no, n_};
+        launch_pdl(k_bconv_var1, grid, BEHZ_THREADS, 0, st, a);
+    } else if (mode == 2) {   // bConv_HPS
+        BconvHpsArgs a{in, out, cv.hinv.p, cv.inv.p, cv.mat.p, cv.Imod.p, cv.mod_in.p, cv.mod_out.p, ni, no, n_};
+        launch_pdl(k_bconv_hps, grid, BEHZ_THREADS, 0, st, a);
+    } else {
+        throw std::invalid_argument("unknown base conversion");
+    }
+    check_launch("k_bconv (boundary)");
+}
+
+void Engine::moddown_plain(int l, u64 *ct_i, u64 *cx_i, cudaStream_t st) {
+    if (scheme_ != Scheme::bfv) {   // CKKS / BGV: the same result as moddown_from_NTT (rns_bconv.cu:720-753)
+        if (scheme_ == Scheme::ckks) moddown(l, ct_i, cx_i, ws(st).delta.p, 1, nullptr, 0u, st);
+        else moddown_generic(l, ct_i, cx_i, 1, nullptr, 0u, st);
+        return;
+    }
+    const Level &lv = level(l);
+    if (lv.alpha == 0) throw std::logic_error("key switching needs special primes");
+    std::vector<int> pr, qr;
+    for (int i = 0; i < lv.alpha; i++) pr.push_back(size_Q_ + i);
+    for (int j = 0; j < l; j++) qr.push_back(j);
+    u64 *delta = ws(st).delta.p;
+    bconv(0, converter(pr, qr), delta, cx_i + (size_t) l * n_, st);
+    dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+    launch_pdl(k_moddown_coeff, grid, EW_THREADS, 0, st, ct_i, (const u64 *) cx_i, (const u64 *) delta, (const Tw *) lv.pinv_slots.p,
+               (const u64 *) nullptr, (const Modulus *) d_mod_.p, n_);
+    check_launch("k_moddown_coeff");
 }
 
 } // namespace pfhe

@@ -908,4 +908,46 @@ __global__ void __launch_bounds__(EW_THREADS) k_reduce_last(u64 *dst, const u64 
     st2(dst + (size_t) j * n + x, barrett64(v.x, m), barrett64(v.y, m));
 }
 
+
+// ---------------------------------------------------------------------------------------------------
+// per-call constants of the kernel-level launchers that take device arrays from the caller (nwt_2d_radix8_*_scale,
+// ..._fuse_moddown): one thread per limb slot
+// ---------------------------------------------------------------------------------------------------
+struct FinList {
+    int count;
+    short row[NTT_MAX_LIMBS];   // table row of the slot
+    short idx[NTT_MAX_LIMBS];   // index into the caller's array
+};
+
+__device__ __forceinline__ Tw tw_of_row(u64 w, u64 q, bool fp) {
+    if (fp) {
+        const double dw = (double) w, wi = dw / (double) q;
+        return make_ulonglong2((u64) __double_as_longlong(dw), (u64) __double_as_longlong(wi));
+    }
+    return make_ulonglong2(w, (u64) ((((unsigned __int128) w) << 64) / q));
+}
+
+// fin[2 s] = tw(n^-1 scale), fin[2 s + 1] = tw(itw[1] n^-1 scale) in the representation of the slot's row
+__global__ void k_make_fin(Tw *fin, const u64 *scale, FinList fl, const u64 *fin_int, const Modulus *mod,
+                           const unsigned char *is_fp, int fp_enabled) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int s = threadIdx.x;
+    if (s >= fl.count) return;
+    const int row = fl.row[s];
+    const u64 q = mod[row].q;
+    const u64 c = scale[fl.idx[s]] % q;
+    const bool fp = fp_enabled && is_fp[row];
+    fin[2 * s] = tw_of_row((u64) ((unsigned __int128) fin_int[2 * row] * c % q), q, fp);
+    fin[2 * s + 1] = tw_of_row((u64) ((unsigned __int128) fin_int[2 * row + 1] * c % q), q, fp);
+}
+
+// epilogue constants {c, floor(c 2^64 / q)} from the caller's two arrays
+__global__ void k_zip_tw(Tw *out, const u64 *c, const u64 *c_shoup, FinList fl) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int s = threadIdx.x;
+    if (s < fl.count) out[s] = make_ulonglong2(c[fl.idx[s]], c_shoup[fl.idx[s]]);
+}
+
 } // namespace pfhe

@@ -120,7 +120,7 @@ static void integer_scheme(scheme_type scheme) {
     relinearize_inplace(context, two_step, relin_keys);
     expect(two_step.size() == 2 && decrypted(two_step) == sq, name + ": relinearize_inplace");
 
-    {   // hoisting over {1, 1}: twice the rotation by one step (BGV: the hoisted form; BFV: composed from rotations)
+    {   // hoisting over {1, 1}: twice the rotation by one step (one shared mod-up; BFV with the coefficient-form ends)
         PhantomCiphertext hoisted = fused;
         hoisting_inplace(context, hoisted, galois_keys, {1, 1});
         std::vector<uint64_t> twice_rot(n);

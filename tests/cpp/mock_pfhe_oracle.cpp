@@ -281,6 +281,19 @@ int pfhe_hoisting_inplace(pfhe_engine *e, size_t chain_index, uint64_t *ct, cons
     orc_hoisting(e->c, limbs_at(e, chain_index), ct, elts.data(), (int) n_steps, key_ptrs.data());
     return PFHE_OK;
 }
+int pfhe_hoisting_leveled_inplace(pfhe_engine *e, uint64_t *ct, const int *steps, size_t n_steps,
+                                  const uint64_t *const *const *keys, int drop, void *) {
+    std::vector<std::vector<uint64_t>> gathered;
+    std::vector<const uint64_t *> key_ptrs;
+    std::vector<uint32_t> elts;
+    for (size_t i = 0; i < n_steps; i++) {
+        gathered.push_back(gather_key(e, keys[i]));
+        elts.push_back(orc_galois_elt_from_step(steps[i], e->n));
+    }
+    for (auto &g : gathered) key_ptrs.push_back(g.data());
+    return orc_bfv_hoisting_leveled(e->c, ct, elts.data(), (int) n_steps, key_ptrs.data(), drop) == 0
+                   ? PFHE_OK : fail(PFHE_ERR_INVALID_ARGUMENT, "hoisting failed");
+}
 int pfhe_rescale_to_next(pfhe_engine *e, size_t chain_index, const uint64_t *ct, size_t size, uint64_t *dst, void *) {
     const int l = limbs_at(e, chain_index);
     std::vector<uint64_t> copy(ct, ct + size * l * e->n);   // the oracle uses its input as scratch

@@ -187,19 +187,20 @@ def test_ntt_config1_known_answer():
 
 
 def test_ntt_start_index_and_linearity():
+    """reference addressing (fntt_2d.cu:35-40): limbs [start, start + count) of the buffer, limb i with table row i"""
     ps = H.params_small(4096, l=4, alpha=2)
     ctx = make_context(ps)
     o = H.oracle()
     rows = [2, 3, 4]
-    x = H.uniform_limbs(ps, rows, 3)[0]
-    y = H.uniform_limbs(ps, rows, 4)[0]
+    x = H.uniform_limbs(ps, list(range(5)), 3)[0]
+    y = H.uniform_limbs(ps, list(range(5)), 4)[0]
     want = x.copy()
-    o.orc_ntt_forward(ps.octx(), P(want), 3, idx_arr(rows))
+    o.orc_ntt_forward(ps.octx(), P(want[2:]), 3, idx_arr(rows))   # limbs 0 and 1 stay as they are
     dx, dy = dev(x), dev(y)
     pf.nwt_2d_radix8_forward_inplace(dx, ctx, 3, 2)
     assert np.array_equal(host(dx), want)
     # linearity: NTT(x + y) = NTT(x) + NTT(y) limb-wise
-    q = ps.primes[rows].reshape(-1, 1)
+    q = ps.primes[:5].reshape(-1, 1)
     s = ((x.astype(object) + y.astype(object)) % q.astype(object)).astype(np.uint64)
     ds = dev(s)
     pf.nwt_2d_radix8_forward_inplace(ds, ctx, 3, 2)

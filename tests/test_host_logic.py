@@ -1,5 +1,6 @@
 """Host-side logic of the mirror interface that needs no GPU: NAF rotation decomposition, parameter plumbing,
 batch sharding (incl. a world_size-2 gloo run)."""
+import ctypes
 import os
 import subprocess
 import sys
@@ -366,15 +367,19 @@ def test_evaluator_bookkeeping_with_a_stub_library(monkeypatch):
         api.multiply_plain_inplace(lev, wrong, torch.zeros(8, dtype=torch.int64))
     total = api.add_many(lev, [ct(lev), ct(lev), ct(lev)])
     assert total.size() == 2 and stub.calls[-1] == "pfhe_add_rns_poly"
-    # BFV hoisting is composed from rotations (leveled key switch under hps_overq_leveled) and additions
+    # BFV hoisting under hps_overq_leveled: one call of the leveled entry point with the levels of a key switch
     lev.parms.galois_elts = [0]   # the stub's get_elt_from_step answers 0 for every step
-    glk = types.SimpleNamespace(get_relin_keys=lambda idx: types.SimpleNamespace(public_keys_ptr=lambda: None))
+    glk = types.SimpleNamespace(get_relin_keys=lambda idx: types.SimpleNamespace(public_keys_ptr=lambda: ctypes.c_void_p(0)))
     c = ct(lev)
     before = len(stub.calls)
     api.hoisting_inplace(lev, c, glk, [1, 2])
     made = stub.calls[before:]
-    assert made.count("pfhe_keyswitch_leveled_inplace") == 2 and made.count("pfhe_apply_galois") == 4 and made[-1] == "pfhe_add_rns_poly"
+    assert made[-1] == "pfhe_hoisting_leveled_inplace" and "pfhe_find_levels_to_drop" in made
     assert "pfhe_hoisting_inplace" not in made and c.size() == 2
+    low2 = ct(lev)
+    low2.chain_index = 2
+    with pytest.raises(ValueError, match="first data level"):
+        api.hoisting_inplace(lev, low2, glk, [1])
 
 
 def test_pyphantom_wrappers_with_a_stub_library(monkeypatch):
