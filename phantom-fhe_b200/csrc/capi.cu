@@ -221,10 +221,11 @@ int pfhe_ntt_backward(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t 
 // row size_QP - size_QlP + t otherwise, where size_QlP = start + count at every reference call site.
 static void special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, size_t size_QP, size_t size_P,
                         bool inverse, void *stream) {
-    require((int) size_QP == e->impl.size_QP() && (int) size_P == e->impl.size_P(), "size_QP/size_P mismatch");
-    const size_t size_QlP = start + count;
-    require(size_QlP >= size_P && size_QlP <= size_QP, "modulus index out of range");
-    e->impl.ntt_special_range(U(inout), (int) count, (int) start, (int) (size_QlP - size_P), inverse, S(stream));
+    require(size_QP <= (size_t) e->impl.size_QP() && size_P <= count, "modulus index out of range");
+    Engine::NttCall c;
+    c.inverse = inverse, c.table = Engine::TABLE_RNS, c.count = count, c.start = start;
+    c.remap = 1, c.a = size_QP, c.b = size_P;
+    e->impl.ntt_call(U(inout), U(inout), c, nullptr, nullptr, S(stream));
 }
 
 int pfhe_ntt_forward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t start,
@@ -294,7 +295,7 @@ int pfhe_nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range(pfhe_en
                                                                          size_t start, size_t size_QP, size_t size_P,
                                                                          size_t excl_lo, size_t excl_hi, void *stream) {
     API_BEGIN
-    require((int) size_QP == e->impl.size_QP() && (int) size_P == e->impl.size_P(), "size_QP/size_P mismatch");
+    require(size_QP <= (size_t) e->impl.size_QP() && size_P <= count, "modulus index out of range");
     auto c = ntt_call(false, Engine::TABLE_RNS, count, start);
     c.remap = 1, c.a = size_QP, c.b = size_P, c.excl_lo = excl_lo, c.excl_hi = excl_hi;
     e->impl.ntt_call(U(inout), U(inout), c, nullptr, nullptr, S(stream));
