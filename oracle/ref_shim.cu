@@ -174,6 +174,7 @@ uint32_t ref_galois_elt_at(void *p, int idx) {
 
 /* key digit d = [2][size_QP][n] words.  which < 0: relin key; which >= 0: galois key index. dir 0 = get. */
 static int key_xfer(RefCtx *h, int which, int d, uint64_t *host, int dir) {
+    cudaGetLastError();   /* a launch the reference left unchecked must not fail the transfer */
     uint64_t *const *dev_ptrs =
             which < 0 ? h->rlk->public_keys_ptr() : h->glk->get_relin_keys(which).public_keys_ptr();
     uint64_t *ptr = nullptr;
