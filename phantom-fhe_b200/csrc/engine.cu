@@ -148,7 +148,7 @@ static std::pair<uintptr_t, std::thread::id> stream_key(cudaStream_t st) {
     return {reinterpret_cast<uintptr_t>(st), implicit ? std::this_thread::get_id() : std::thread::id()};
 }
 
-StreamCtx &Engine::sctx(cudaStream_t st) {
+StreamCtx &Engine::sctx(cudaStream_t st) const {
     std::lock_guard<std::mutex> g(sctx_mu_);
     auto &slot = sctx_[stream_key(st)];
     if (!slot) {
@@ -529,8 +529,13 @@ static void check_launch(const char *what) {
 }
 
 void Engine::ntt_fwd_list(u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) const {
-    g_launches.fetch_add(2, std::memory_order_relaxed);
-    PFHE_CUDA(ntt_forward(plan_, dst, src, ll, st));
+    Workspace &w = ws(st);
+    if (!w.sync.p) {
+        w.sync.alloc(1);
+        PFHE_CUDA(cudaMemset(w.sync.p, 0, sizeof(FusedSync)));
+    }
+    g_launches.fetch_add(2, std::memory_order_relaxed);   // (one launch under PFHE_NTT_FUSED=1: counted as the pair it replaces)
+    PFHE_CUDA(ntt_forward(plan_, dst, src, ll, st, w.sync.p));
 }
 void Engine::ntt_inv_list(u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
                           cudaStream_t st) const {

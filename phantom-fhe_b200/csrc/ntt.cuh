@@ -326,6 +326,7 @@ struct PassCtx {
     typename A::Consts c;
     int tile;                   // tile index inside the limb (column block resp. row block)
     Tw fin_x, fin_y;            // constants of the last inverse stage
+    uint32_t parity = 0;        // phase of `bar` this pass waits for (a persistent CTA reuses the barrier tile after tile)
 };
 
 // one forward round on the registers of a thread: x[g * 2^R + k]
@@ -597,7 +598,7 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++) x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
         }
-        if constexpr (RI == 0 && !ROWS) mbar_wait(cx.bar, 0);   // staged twiddles landed (overlapped the gather)
+        if constexpr (RI == 0 && !ROWS) mbar_wait(cx.bar, cx.parity);   // staged twiddles landed (overlapped the gather)
         fwd_round<A, M, ROWS, LOGN, SBASE>(x, cx.tw, hi, c, cx.tile, cx.c);
 #ifdef PFHE_TIMELINE
 #pragma unroll
@@ -667,7 +668,7 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
 #pragma unroll
                 for (int k = 0; k < (1 << M::R); k++) x[(g << M::R) + k] = A::from_raw(smem[s0[g] ^ M::kc(k)]);
         }
-        if constexpr (RI == NR - 1 && !ROWS) mbar_wait(cx.bar, 0);
+        if constexpr (RI == NR - 1 && !ROWS) mbar_wait(cx.bar, cx.parity);
         inv_round<A, M, ROWS, LOGN, FINAL && RI == 0>(x, cx.tw, hi, c, cx.tile, cx.c, cx.fin_x, cx.fin_y);
         if constexpr (RI == 0) {
             // first round in index order = last in time: values leave the pass

@@ -16,9 +16,20 @@ struct NttPlan {
     int fp_enabled;               // 0: integer butterflies everywhere (PFHE_FP64_NTT=0)
 };
 
+// per-stream state of the single-launch transform (k_fwd_fused): work-item ticket, per-slot counts of finished column
+// tiles, exit count.  Zero-initialised once; every launch leaves it zeroed.
+struct FusedSync {
+    unsigned ticket, done;
+    unsigned ready[NTT_MAX_LIMBS];
+};
+
 // forward negacyclic NTT of the limbs in `ll` (replaces nwt_2d_radix8_forward_inplace and its
-// include_special_mod / include_temp_mod / exclude_range variants, reference include/ntt.cuh:172-201)
-cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st);
+// include_special_mod / include_temp_mod / exclude_range variants, reference include/ntt.cuh:172-201).
+// With `sync` (and enough limbs to fill the GPU) both passes run in ONE persistent launch: CTAs draw (limb, pass, tile)
+// work items from a ticket counter, a row tile starts as soon as the column tiles of ITS limb are done (per-limb
+// counters, release / acquire through L2) instead of waiting for the whole column-pass grid.
+cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st,
+                        FusedSync *sync = nullptr);
 
 // forward NTT of `data` (in place, ll.src must equal ll.data) whose row pass ends in the EpiArgs epilogue
 cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st);

@@ -1,4 +1,7 @@
 // ntt_kernels.cu -- kernels and launchers built on the pass drivers of ntt.cuh.
+#include <algorithm>
+#include <cstdlib>
+
 #include "ntt_api.cuh"
 #include "launch.hpp"
 
@@ -116,6 +119,140 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows(u64 *d
                     else return A::canon_fwd(v, c);
                 }));
     })
+}
+
+// ---- both passes in one persistent launch -------------------------------------------------------------------------
+// Work items in ticket order: column tiles of slot k, then row tiles of slot k - delay (so that by the time a row tile is
+// drawn the column tiles it depends on were drawn ~delay limbs earlier and are normally finished).  A row tile waits on
+// ready[slot] == tiles-per-pass; it can only wait for lower tickets, which running CTAs hold: no deadlock whatever the
+// residency.  The intermediate goes through L2: column tiles publish with fence + atomic, row tiles read with ld.cg (the
+// transform is in place: the SM's L1 may still hold the pre-transform words of the same addresses).
+__device__ __forceinline__ unsigned ld_acquire_u32(const unsigned *p) {
+    unsigned v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+
+__device__ __forceinline__ void publish_tile(unsigned *ready, int slot) {   // thread 0, after a CTA barrier
+    __threadfence();   // release: cumulative over the stores the barrier made visible to this thread
+    atomicAdd(ready + slot, 1u);
+}
+
+// stores of a column tile; just before them thread 0 publishes the PREVIOUS column tile of this CTA: by now those stores
+// have long been acknowledged, so the fence costs nothing -- publishing right after a tile's own stores would stall the
+// whole CTA for the store round trip, which a non-persistent CTA never waits for
+template<class A>
+struct ColStorePublish {
+    u64 *d;
+    unsigned *ready;
+    int pending;
+    template<int RUN>
+    __device__ __forceinline__ void scatter(const size_t (&idx)[NTT_EPT], const typename A::T (&x)[NTT_EPT]) const {
+        if (threadIdx.x == 0 && pending >= 0) publish_tile(ready, pending);
+#pragma unroll
+        for (int k = 0; k < NTT_EPT; k++) d[idx[k]] = A::raw(x[k]);
+    }
+};
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_fused(u64 *dst, const u64 *src, LimbList ll, NttPlan p,
+                                                                           FusedSync *sy, int delay) {
+    extern __shared__ __align__(128) unsigned char dyn_smem[];
+    u64 *smem = reinterpret_cast<u64 *>(dyn_smem);
+    Tw *stw = reinterpret_cast<Tw *>(smem + NTT_TILE);
+    uint64_t *bar = reinterpret_cast<uint64_t *>(stw + NTT_STW_ENTRIES);
+    __shared__ unsigned s_item;
+    constexpr unsigned T = 1u << (LOGN - NTT_LOG_TILE);
+    const unsigned count = (unsigned) ll.count, D = min((unsigned) delay, count);
+    const unsigned total = count * 2 * T, head = D * T, mid = (count - D) * 2 * T;
+    if (threadIdx.x == 0) mbar_init(bar, 1);
+    __syncthreads();
+    pdl_launch_dependents();
+    pdl_wait();
+    uint32_t parity = 0;
+    // thread 0 draws the NEXT ticket while the current tile is being worked on: the atomic's round trip is off the path
+    unsigned next = 0;
+    int pending = -1;   // slot of this CTA's last column tile, not yet counted in ready[]
+    if (threadIdx.x == 0) next = atomicAdd(&sy->ticket, 1u);
+    for (;;) {
+        if (threadIdx.x == 0) s_item = next;
+        __syncthreads();
+        const unsigned w = s_item;
+        if (w >= total) break;
+        if (threadIdx.x == 0) next = atomicAdd(&sy->ticket, 1u);
+        unsigned slot, tile;
+        bool rows;
+        if (w < head) {
+            rows = false, slot = w / T, tile = w % T;
+        } else if (w < head + mid) {
+            const unsigned v = w - head, k = D + v / (2 * T), r = v % (2 * T);
+            rows = r >= T, slot = rows ? k - D : k, tile = rows ? r - T : r;
+        } else {
+            const unsigned v = w - head - mid;
+            rows = true, slot = count - D + v / T, tile = v % T;
+        }
+        const int row = ll.row[slot];
+        const u64 q = ll.q[slot];
+        const bool fp = p.fp_enabled && (q >> fp::MAX_BITS) == 0;
+        u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
+        if (!rows) {
+            if (threadIdx.x == 0) stage_twiddles<ntt_p1(LOGN)>(stw, p.tw + ((size_t) row << LOGN), bar);
+            const u64 *sp = src + ((size_t) ll.src[slot] << LOGN);
+            if (fp) {
+                using A = FpArith;
+                const A::Consts c = A::consts(q);
+                PassCtx<A> cx{stw, bar, c, (int) tile, {}, {}, parity};
+                forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
+                        smem, cx, per_elem_load<A::T>([&](size_t i) { return A::load(sp[i], c); }),
+                        ColStorePublish<A>{d, sy->ready, pending});
+            } else {
+                using A = IntArith;
+                const A::Consts c = A::consts(q);
+                PassCtx<A> cx{stw, bar, c, (int) tile, {}, {}, parity};
+                forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
+                        smem, cx, per_elem_load<A::T>([&](size_t i) { return A::load(sp[i], c); }),
+                        ColStorePublish<A>{d, sy->ready, pending});
+            }
+            parity ^= 1u;
+            pending = (int) slot;
+            __syncthreads();   // every thread's stores are ordered before whatever thread 0 publishes later
+        } else {
+            if (threadIdx.x == 0) {
+                if (pending >= 0) publish_tile(sy->ready, pending);   // never wait on a count this CTA still holds back
+                while (ld_acquire_u32(&sy->ready[slot]) < T) __nanosleep(64);
+            }
+            pending = -1;
+            __syncthreads();
+            const Tw *tw = p.tw + ((size_t) row << LOGN);
+            if (fp) {
+                using A = FpArith;
+                const A::Consts c = A::consts(q);
+                PassCtx<A> cx{tw, nullptr, c, (int) tile, {}, {}};
+                forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+                        smem, cx, per_elem_load<A::T>([&](size_t i) { return A::from_raw(__ldcg(d + i)); }),
+                        vec_store<A::T>(d, [&](A::T v) { return A::canon_fwd(v, c); }));
+            } else {
+                using A = IntArith;
+                const A::Consts c = A::consts(q);
+                PassCtx<A> cx{tw, nullptr, c, (int) tile, {}, {}};
+                forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+                        smem, cx, per_elem_load<A::T>([&](size_t i) { return A::from_raw(__ldcg(d + i)); }),
+                        vec_store<A::T>(d, [&](A::T v) { return A::canon_fwd(v, c); }));
+            }
+            __syncthreads();   // the exchange tile and s_item are free again
+        }
+    }
+    // the last CTA to leave restores the counters for the next launch on this stream
+    if (threadIdx.x == 0) {
+        if (pending >= 0) publish_tile(sy->ready, pending);
+        __threadfence();
+        if (atomicAdd(&sy->done, 1u) == gridDim.x - 1) {
+            for (unsigned i = 0; i < count; i++) sy->ready[i] = 0;
+            sy->ticket = 0;
+            sy->done = 0;
+            __threadfence();
+        }
+    }
 }
 
 template<int LOGN>
@@ -529,6 +666,7 @@ static void opt_in_all() {
     opt_in_smem(k_inv_rows_mul<LOGN>);
     opt_in_smem(k_fwd_cols_bconv<LOGN>);
     opt_in_smem(k_fwd_rows_epi_tensor<LOGN>);
+    opt_in_smem(k_fwd_fused<LOGN>);
     done = true;
 }
 
@@ -538,6 +676,46 @@ static void fwd_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList 
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
     launch_pdl(k_fwd_cols<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, src, ll, p);
     launch_pdl(k_fwd_rows<LOGN, false>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
+}
+
+// persistent single-launch form: as many CTAs as the device holds at once (a smaller grid only lowers the parallelism,
+// a larger one is harmless: tickets decide who works)
+static int fused_grid_limit() {
+    static int limit = 0;
+    if (!limit) {
+        int dev = 0, sms = 148;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        limit = sms * NTT_MIN_BLOCKS;
+    }
+    return limit;
+}
+static int fused_delay() {
+    static int d = -1;
+    if (d < 0) {
+        const char *e = std::getenv("PFHE_NTT_FUSED_DELAY");
+        d = e ? std::atoi(e) : NTT_MAX_LIMBS;   // all column tiles first: a row tile then never finds its limb unfinished
+    }
+    return d;
+}
+static bool fused_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        // opt-in: measured slower than the launch pair on B200 (37.4 vs 33.2 us for 64 limbs of N = 2^16, DESIGN.md 4.1:
+        // +7 % instructions and 3x the barrier stalls of the persistent loop outweigh the filled tail, which programmatic
+        // dependent launch already half-hides for the pair).  Kept for the record and for A/B runs.
+        const char *e = std::getenv("PFHE_NTT_FUSED");
+        on = e && e[0] == '1';
+    }
+    return on;
+}
+
+template<int LOGN>
+static void fwd_fused_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st, FusedSync *sync) {
+    opt_in_all<LOGN>();
+    const int total = ll.count * 2 * (1 << (LOGN - NTT_LOG_TILE));
+    dim3 grid((unsigned) std::min(total, fused_grid_limit()));
+    launch_pdl(k_fwd_fused<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, src, ll, p, sync, fused_delay());
 }
 
 template<int LOGN>
@@ -575,9 +753,14 @@ static bool aligned32(Ptr... p) {
     return ((... | reinterpret_cast<uintptr_t>(p)) & 31u) == 0;
 }
 
-cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st) {
+cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st, FusedSync *sync) {
     if (ll.count == 0) return cudaSuccess;
     if (!aligned32(dst, src)) return cudaErrorMisalignedAddress;
+    // one persistent launch when the tiles of one pass fill the device at least once, else the launch pair
+    if (sync && fused_enabled() && (ll.count << (p.logn - NTT_LOG_TILE)) >= fused_grid_limit()) {
+        PFHE_DISPATCH_LOGN(fwd_fused_impl, p, dst, src, ll, st, sync)
+        return cudaGetLastError();
+    }
     PFHE_DISPATCH_LOGN(fwd_impl, p, dst, src, ll, st)
     return cudaGetLastError();
 }
