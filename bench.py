@@ -227,6 +227,8 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[3] lines")
     ap.add_argument("--no-exchange", action="store_true", help="skip the scatter/gather legs")
     ap.add_argument("--peer", action="store_true", help="also run the zero-copy leg (kernels address rank 0's HBM)")
+    ap.add_argument("--depth", type=int, default=3, help="staging slots of the one-sided scatter/gather pipeline")
+    ap.add_argument("--sg-only", action="store_true", help="stop after the scatter/gather legs (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
 
@@ -408,8 +410,8 @@ def main():
                 maps.append(m)
             r_in = [root_in if r == 0 else (empty_in if r == rank else None) for r in range(world)]
             r_out = [root_out if r == 0 else (empty_out if r == rank else None) for r in range(world)]
-            record("rooted_pull", plans["rooted"], timed_passes(PullExchange(plans["rooted"], rank, r_in, r_out), "rooted_pull", 2, sg_steps))
-            record("spread_pull", plans["spread"], timed_passes(PullExchange(plans["spread"], rank, homes_in, homes_out), "spread_pull", 2, sg_steps))
+            record("rooted_pull", plans["rooted"], timed_passes(PullExchange(plans["rooted"], rank, r_in, r_out, args.depth), "rooted_pull", 2, sg_steps))
+            record("spread_pull", plans["spread"], timed_passes(PullExchange(plans["spread"], rank, homes_in, homes_out, args.depth), "spread_pull", 2, sg_steps))
             if args.peer:
                 # (3) zero-copy: the kernels themselves address rank 0's HBM (no staging at all)
                 ex = Exchange(ExchangePlan.local(B, world, args.chunk), rank, root_in[lo:hi], root_out[lo:hi], dist)
@@ -435,6 +437,14 @@ def main():
                     "operands / pushes results with cudaMemcpyAsync on side streams (copy engines), double-buffered"}
         sg["nvlink_peak_gbs_per_direction"] = 900.0
 
+    if args.sg_only:
+        if rank == 0:
+            print(json.dumps({"value": args.steps * B / (dev_ms * 1e-3), "n_gpus": world, "chunk": args.chunk, "depth": args.depth,
+                              "scatter_gather": sg}), flush=True)
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
     # ---- end to end from pinned host memory ----------------------------------------------------------------
     shard = hi - lo
     e2e_pairs = min(E2E_PAIRS, max(shard, 1))
@@ -458,19 +468,25 @@ def main():
     wall_ms = (time.perf_counter() - t0) * 1e3
     # the same copies with no arithmetic between them: what the host <-> device links give this rank layout
     s_h2d, s_d2h = torch.cuda.Stream(), torch.cuda.Stream()
-    copy_ops = min(shard, 4 * e2e_pairs)
+    copy_ops = shard
     dst_in = store_in[:2]
+
+    def copy_pass(count):
+        s_h2d.wait_stream(torch.cuda.current_stream())
+        s_d2h.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s_h2d):
+            for i in range(count):
+                dst_in[i % 2].copy_(pin_in[i % e2e_pairs], non_blocking=True)
+        with torch.cuda.stream(s_d2h):
+            for i in range(count):
+                pin_out[i % e2e_pairs].copy_(store_out[i % 2], non_blocking=True)
+        torch.cuda.current_stream().wait_stream(s_h2d)
+        torch.cuda.current_stream().wait_stream(s_d2h)
+
+    copy_pass(min(shard, 2 * e2e_pairs))
     barrier()
     e0.record()
-    s_h2d.wait_stream(torch.cuda.current_stream())
-    s_d2h.wait_stream(torch.cuda.current_stream())
-    for i in range(copy_ops):
-        with torch.cuda.stream(s_h2d):
-            dst_in[i % 2].copy_(pin_in[i % e2e_pairs], non_blocking=True)
-        with torch.cuda.stream(s_d2h):
-            pin_out[i % e2e_pairs].copy_(store_out[i % 2], non_blocking=True)
-    torch.cuda.current_stream().wait_stream(s_h2d)
-    torch.cuda.current_stream().wait_stream(s_d2h)
+    copy_pass(copy_ops)
     e1.record()
     barrier()
     copy_ms = max_over_ranks(e0.elapsed_time(e1))

@@ -201,7 +201,7 @@ class Exchange:
     """Runs an ExchangePlan.  `store_in` / `store_out`: this rank's home storage, tensors [n_home, in_words] and
     [n_home, out_words] (n_home = hi - lo of plan.home[rank]; may be empty).  Staging for remote units is allocated here."""
 
-    def __init__(self, plan, rank, store_in, store_out, dist=None, group=None):
+    def __init__(self, plan, rank, store_in, store_out, dist=None, group=None, depth=2):
         import torch
         self.torch = torch
         self.plan, self.rank, self.dist, self.group = plan, rank, dist, group
@@ -211,7 +211,8 @@ class Exchange:
             raise ValueError("home storage does not match the plan")
         self.in_words, self.out_words = store_in.shape[1], store_out.shape[1]
         remote = any(p.home != rank for tick in plan.ticks[rank] for p in tick)
-        slots = 2 if remote else 0
+        self.depth = depth
+        slots = depth if remote else 0
         self.stage_in = [store_in.new_empty((plan.slot, self.in_words)) for _ in range(slots)]
         self.stage_out = [store_out.new_empty((plan.slot, self.out_words)) for _ in range(slots)]
         if plan.world > 1 and dist is None:
@@ -231,7 +232,7 @@ class Exchange:
                 if p.home == self.rank:
                     views.append((self.store_in[p.lo - lo:p.hi - lo], self.store_out[p.lo - lo:p.hi - lo]))
                 else:
-                    views.append((self.stage_in[t % 2][p.off:p.off + len(p)], self.stage_out[t % 2][p.off:p.off + len(p)]))
+                    views.append((self.stage_in[t % self.depth][p.off:p.off + len(p)], self.stage_out[t % self.depth][p.off:p.off + len(p)]))
         self._views[t] = views
         return views
 
@@ -305,16 +306,16 @@ class PullExchange(Exchange):
     touches may be None).  The caller brackets a pass with a barrier on both sides (operands must be final before, results
     are visible to their owners after)."""
 
-    def __init__(self, plan, rank, homes_in, homes_out):
-        super().__init__(plan, rank, homes_in[rank], homes_out[rank], dist=_NoDist if plan.world > 1 else None)
+    def __init__(self, plan, rank, homes_in, homes_out, depth=3):
+        super().__init__(plan, rank, homes_in[rank], homes_out[rank], dist=_NoDist if plan.world > 1 else None, depth=depth)
         self.homes_in, self.homes_out = homes_in, homes_out
         t = self.torch
         self.cuda = homes_in[rank].is_cuda
         if self.cuda and self.stage_in:
             self.s_in, self.s_out = t.cuda.Stream(), t.cuda.Stream()
-            self.ev_in = [t.cuda.Event() for _ in range(2)]
-            self.ev_comp = [t.cuda.Event() for _ in range(2)]
-            self.ev_out = [t.cuda.Event() for _ in range(2)]
+            self.ev_in = [t.cuda.Event() for _ in range(depth)]
+            self.ev_comp = [t.cuda.Event() for _ in range(depth)]
+            self.ev_out = [t.cuda.Event() for _ in range(depth)]
 
     def run(self, compute):
         t = self.torch
@@ -327,11 +328,11 @@ class PullExchange(Exchange):
             self.s_out.wait_stream(cur)
         used = set()
         for u, tick in enumerate(mine):
-            slot = u % 2
+            slot = u % self.depth
             remote = [p for p in tick if p.home != me]
             if remote:
                 if staged:
-                    if u >= 2 and slot in used:
+                    if slot in used:
                         self.s_in.wait_event(self.ev_comp[slot])      # compute(u - 2) has read this slot
                     with t.cuda.stream(self.s_in):
                         for p in remote:
