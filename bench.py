@@ -227,7 +227,7 @@ def main():
     ap.add_argument("--no-extra", action="store_true", help="skip the configs[2] / configs[3] lines")
     ap.add_argument("--no-exchange", action="store_true", help="skip the scatter/gather legs")
     ap.add_argument("--peer", action="store_true", help="also run the zero-copy leg (kernels address rank 0's HBM)")
-    ap.add_argument("--depth", type=int, default=3, help="staging slots of the one-sided scatter/gather pipeline")
+    ap.add_argument("--depth", type=int, default=2, help="staging slots of the one-sided scatter/gather pipeline")
     ap.add_argument("--sg-only", action="store_true", help="stop after the scatter/gather legs (tuning runs)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -383,7 +383,9 @@ def main():
             sg[name] = {"value": sg_steps * B / (ms * 1e-3), "unit": "HE-ops/s", "ms_per_step": ms / sg_steps,
                         "steps": sg_steps, "rank0_sent_bytes_per_step": sent, "rank0_recv_bytes_per_step": recv,
                         "rank0_egress_gbs": sent * sg_steps / (ms * 1e-3) / 1e9,
-                        "vs_compute_only": (sg_steps / ms) / (args.steps / dev_ms)}
+                        "vs_compute_only": (sg_steps / ms) / (args.steps / dev_ms),
+                        # what rank 0's NVLink port allows at its nominal 900 GB/s per direction, whatever the pipeline
+                        "rank0_link_bound_ops_per_s": B / (max(sent, recv) / 900e9) if max(sent, recv) else None}
             sg[name].update(extra or {})
 
         plans = {"rooted": ExchangePlan.rooted(B, world, args.chunk, 0), "spread": ExchangePlan.spread(B, world, args.chunk)}

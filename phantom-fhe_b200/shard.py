@@ -306,7 +306,7 @@ class PullExchange(Exchange):
     touches may be None).  The caller brackets a pass with a barrier on both sides (operands must be final before, results
     are visible to their owners after)."""
 
-    def __init__(self, plan, rank, homes_in, homes_out, depth=3):
+    def __init__(self, plan, rank, homes_in, homes_out, depth=2):
         super().__init__(plan, rank, homes_in[rank], homes_out[rank], dist=_NoDist if plan.world > 1 else None, depth=depth)
         self.homes_in, self.homes_out = homes_in, homes_out
         t = self.torch
