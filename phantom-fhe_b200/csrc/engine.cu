@@ -767,7 +767,7 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
     const Level &lv = level(l);
     const int alpha = lv.alpha, m = lv.m;
     if (alpha == 0) throw std::logic_error("key switching needs special primes");
-    if (alpha > FUSE_MAX_IN || (size_t) lv.beta * m > NTT_MAX_LIMBS || 2 * l > NTT_MAX_LIMBS) {
+    if (alpha > FUSE_MAX_IN || m > NTT_MAX_LIMBS || 2 * l > NTT_MAX_LIMBS || lv.beta * m > 32767) {
         // shapes outside the fused kernels' limits take the modular path
         const u64 *src = c2;
         if (ts) {
@@ -790,11 +790,14 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         if (ts) PFHE_CUDA(ntt_inverse_mul(plan_, t_cks, *ts, bar(1, 0), ll, lv.modup_fin.p, 1, st));
         else PFHE_CUDA(ntt_inverse(plan_, t_cks, c2, ll, lv.modup_fin.p, 1, st));
     }
-    // 2. mod-up: convert + forward NTT, one launch pair per group of digits of equal size
+    // 2. mod-up: convert + forward NTT, one launch pair per group of digits of equal size (and of at most NTT_MAX_LIMBS
+    //    converted limbs: larger parameter sets, e.g. the 36..43-prime sets of benchmark/ckks_bench.cu, take several)
     for (int d0 = 0; d0 < lv.beta;) {
         const int ni = lv.digit_size[d0];
+        const int per_digit = m - ni;
         int d1 = d0;
-        while (d1 < lv.beta && lv.digit_size[d1] == ni) d1++;
+        while (d1 < lv.beta && lv.digit_size[d1] == ni && (d1 - d0 + 1) * per_digit <= NTT_MAX_LIMBS) d1++;
+        if (d1 == d0) throw std::logic_error("digit wider than a launch");   // excluded by the shape test above
         LimbList ll{};
         BconvLoad bl{};
         size_t moff = 0;

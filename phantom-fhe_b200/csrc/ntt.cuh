@@ -98,7 +98,10 @@ __host__ __device__ constexpr int skew(int i) { return i ^ skew_bits(i); }
 // Base conversion folded into the load of the forward column pass: slot s converts the `ni` coefficient-form
 // limbs starting at limb in_limb[s] of in_base with matrix row mat_row[s] (bconv_matmul_*, reference
 // src/rns_bconv.cu:109-210,455-485), so the converted polynomial never goes through memory before its NTT.
-constexpr int FUSE_MAX_IN = 4;
+#ifndef PFHE_FUSE_MAX_IN
+#define PFHE_FUSE_MAX_IN 6
+#endif
+constexpr int FUSE_MAX_IN = PFHE_FUSE_MAX_IN;   // special primes per digit the fused conversions take (benchmark/ckks_bench.cu goes up to 6)
 struct BconvLoad {
     const u64 *in_base;
     const u64 *mat;          // [rows][ni] qhat_i mod p_j

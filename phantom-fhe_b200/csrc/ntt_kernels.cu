@@ -395,7 +395,7 @@ struct Lo64 {   // low 64 bits of a sum of products; the cross terms go straight
     __device__ __forceinline__ u64 value() const { return ((u64) hi << 32) | lo; }
 };
 
-template<int LOGN>
+template<int LOGN, int MAXIN>
 struct BconvGatherFp {
     const u64 *in;
     const double2 *mf;   // [ni][2], global memory: read where used (CTA-uniform, L1 broadcast) to keep registers free
@@ -417,7 +417,7 @@ struct BconvGatherFp {
 #pragma unroll
             for (int k = 0; k < HB; k++) s[k] = 0.0, r[k].lo = 0u, r[k].hi = h0;
 #pragma unroll
-            for (int i = 0; i < FUSE_MAX_IN; i++) {
+            for (int i = 0; i < MAXIN; i++) {
                 if (i < ni) {
                     u64 y[HB];
 #pragma unroll
@@ -456,7 +456,7 @@ struct BconvGatherFp {
 #pragma unroll
         for (int k = 0; k < NTT_EPT; k++) x[k] = 0.0;
 #pragma unroll
-        for (int i = 0; i < FUSE_MAX_IN; i++) {
+        for (int i = 0; i < MAXIN; i++) {
             if (i < ni) {
                 u64 y[NTT_EPT];
 #pragma unroll
@@ -478,10 +478,10 @@ struct BconvGatherFp {
 #endif
     }
 };
-template<int LOGN>
+template<int LOGN, int MAXIN>
 struct BconvGatherInt {
     const u64 *in;
-    const u64 *mi;       // [ni]
+    const u64 *mi;       // [ni] (<= MAXIN)
     int ni;
     BarG bg;
     Modulus m;
@@ -491,7 +491,7 @@ struct BconvGatherInt {
 #pragma unroll
         for (int k = 0; k < NTT_EPT; k++) acc[k] = Acc128{0, 0};
 #pragma unroll
-        for (int i = 0; i < FUSE_MAX_IN; i++) {
+        for (int i = 0; i < MAXIN; i++) {
             if (i < ni) {
                 u64 y[NTT_EPT];
 #pragma unroll
@@ -506,7 +506,7 @@ struct BconvGatherInt {
 };
 
 // forward column pass whose input is produced by the fast base conversion of `ni` coefficient-form limbs
-template<class A, int LOGN>
+template<class A, int LOGN, int MAXIN>
 __device__ __forceinline__ void fwd_cols_bconv_body(u64 *smem, const Tw *stw, uint64_t *bar, u64 q, int row, int slot,
                                                     const u64 *in, u64 *d, const BconvLoad &bl, const Modulus *mod) {
     const typename A::Consts c = A::consts(q);
@@ -516,23 +516,24 @@ __device__ __forceinline__ void fwd_cols_bconv_body(u64 *smem, const Tw *stw, ui
     if constexpr (std::is_same<A, FpArith>::value) {
         const double2 *mf = bl.matf + 2 * ((size_t) bl.mat_row[slot] * ni);
         forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
-                smem, cx, BconvGatherFp<LOGN>{in, mf, ni, big, c.q},
+                smem, cx, BconvGatherFp<LOGN, MAXIN>{in, mf, ni, big, c.q},
                 per_elem_store<double>([&](size_t i, double v) { d[i] = A::raw(v); }));
     } else {
-        u64 mi[FUSE_MAX_IN];
+        u64 mi[MAXIN];
 #pragma unroll
-        for (int i = 0; i < FUSE_MAX_IN; i++)
+        for (int i = 0; i < MAXIN; i++)
             if (i < ni) mi[i] = bl.mat[(size_t) bl.mat_row[slot] * ni + i];
         const int cls = max(0, bl.xbits - (64 - __clzll((long long) q)));
         const BarG bg = bl.bar[(size_t) min(cls, 63) * bl.size_QP + row];
         const Modulus m = mod[row];
         forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
-                smem, cx, BconvGatherInt<LOGN>{in, mi, ni, bg, m},
+                smem, cx, BconvGatherInt<LOGN, MAXIN>{in, mi, ni, bg, m},
                 per_elem_store<u64>([&](size_t i, u64 v) { d[i] = v; }));
     }
 }
 
-template<int LOGN>
+// MAXIN: unroll bound of the conversion's input loop (4 covers the common digit widths without register spills, 6 the rest)
+template<int LOGN, int MAXIN>
 __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_cols_bconv(u64 *dst, LimbList ll, NttPlan p, BconvLoad bl) {
     const int slot = blockIdx.y;
     const int row = ll.row[slot];
@@ -541,8 +542,8 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_cols_bconv(
     const u64 *in = bl.in_base + ((size_t) bl.in_limb[slot] << LOGN);
     const u64 q = ll.q[slot];
     if (p.fp_enabled && (q >> fp::MAX_BITS) == 0)
-        fwd_cols_bconv_body<FpArith, LOGN>(smem, stw, bar, q, row, slot, in, d, bl, p.mod);
-    else fwd_cols_bconv_body<IntArith, LOGN>(smem, stw, bar, q, row, slot, in, d, bl, p.mod);
+        fwd_cols_bconv_body<FpArith, LOGN, MAXIN>(smem, stw, bar, q, row, slot, in, d, bl, p.mod);
+    else fwd_cols_bconv_body<IntArith, LOGN, MAXIN>(smem, stw, bar, q, row, slot, in, d, bl, p.mod);
 }
 
 // last forward pass of HMult+Relin: out = (cx - NTT(delta)) * P^-1 + d_k with d_0 = a0 b0, d_1 = a0 b1 + a1 b0
@@ -664,7 +665,8 @@ static void opt_in_all() {
     opt_in_smem(k_inv_rows<LOGN>);
     opt_in_smem(k_inv_cols<LOGN>);
     opt_in_smem(k_inv_rows_mul<LOGN>);
-    opt_in_smem(k_fwd_cols_bconv<LOGN>);
+    opt_in_smem(k_fwd_cols_bconv<LOGN, 4>);
+    opt_in_smem(k_fwd_cols_bconv<LOGN, FUSE_MAX_IN>);
     opt_in_smem(k_fwd_rows_epi_tensor<LOGN>);
     opt_in_smem(k_fwd_fused<LOGN>);
     done = true;
@@ -786,7 +788,10 @@ static void fwd_bconv_impl(const NttPlan &p, u64 *dst, const LimbList &ll, const
                            const TensorSrc *ts, const BarG *bar1, cudaStream_t st, int phase) {
     opt_in_all<LOGN>();
     dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
-    if (phase != 2) launch_pdl(k_fwd_cols_bconv<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, bl);
+    if (phase != 2) {
+        if (bl.ni <= 4) launch_pdl(k_fwd_cols_bconv<LOGN, 4>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, bl);
+        else launch_pdl(k_fwd_cols_bconv<LOGN, FUSE_MAX_IN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, ll, p, bl);
+    }
     if (phase == 1) return;
     if (!ea && phase == 3) launch_pdl(k_fwd_rows<LOGN, true>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
     else if (!ea) launch_pdl(k_fwd_rows<LOGN, false>, grid, NTT_THREADS, NTT_SMEM_ROWS, st, dst, ll, p);
