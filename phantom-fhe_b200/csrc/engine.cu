@@ -34,6 +34,10 @@ static void push_matf(std::vector<double2> &v, u64 M, u64 p) {
 }
 
 static Tw make_tw(u64 w, u64 q) { return make_ulonglong2(w, hm::shoup(w, q)); }
+static Modulus host_modulus(u64 q) {
+    const hm::BarrettRatio r = hm::barrett_ratio(q);
+    return Modulus{q, r.lo, r.hi};
+}
 
 // launch helper: NTT lists longer than NTT_MAX_LIMBS are cut into chunks
 struct LimbVec {
@@ -130,7 +134,7 @@ Engine::Engine(Scheme scheme, size_t n, const std::vector<u64> &primes, int size
 void Engine::alloc_workspace(Workspace &w) const {
     const size_t alpha = std::max(size_P_, 1);
     const size_t beta_max = (size_Q_ + alpha - 1) / alpha;
-    w.t_cks.alloc((size_t) size_Q_ * n_);
+    w.t_cks.alloc((size_t) std::max(size_Q_, 2 * (size_P_ + 1)) * n_);   // also the compact [2][alpha + 1] buffer of the BGV mod-down
     w.t_mod_up.alloc(beta_max * size_QP_ * n_);
     w.cx.alloc((size_t) 2 * size_QP_ * n_);
     w.delta.alloc((size_t) 2 * (size_Q_ + 1) * n_);
@@ -493,6 +497,24 @@ void Engine::build_level(int l) {
             }
             lv->moddown_mat_t.upload(tm);
             lv->moddown_matf_t.upload(tmf);
+            {   // fused BGV mod-down: the plain-modulus correction enters the conversion as one more input limb c < t with
+                // matrix entry -P mod q_j (bgv_moddown_kernel, rns_bconv.cu:636-652: delta' = delta - c * (P mod q_j))
+                std::vector<u64> bm;
+                std::vector<double2> bmf;
+                for (int j = 0; j < l; j++) {
+                    const u64 q = rowq_[j];
+                    for (int i = 0; i < alpha; i++) {
+                        bm.push_back(hm::product_mod(pbase, i, q));
+                        push_matf(bmf, bm.back(), q);
+                    }
+                    const u64 pm = hm::product_mod(pbase, -1, q);
+                    bm.push_back(pm ? q - pm : 0);
+                    push_matf(bmf, bm.back(), q);
+                }
+                lv->moddown_mat_bgv.upload(bm);
+                lv->moddown_matf_bgv.upload(bmf);
+                lv->moddown_big_bgv = lv->moddown_big | ((t_ >> fp::MAX_BITS) ? 1u << alpha : 0u);
+            }
             lv->moddown_omod_t.upload(tomod);
             lv->moddown_olimb_t.upload(tolimb);
             const u64 Pt = hm::product_mod(pbase, -1, t_);
@@ -767,7 +789,9 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
     const Level &lv = level(l);
     const int alpha = lv.alpha, m = lv.m;
     if (alpha == 0) throw std::logic_error("key switching needs special primes");
-    if (alpha > FUSE_MAX_IN || m > NTT_MAX_LIMBS || 2 * l > NTT_MAX_LIMBS || lv.beta * m > 32767) {
+    const bool bgv = scheme_ == Scheme::bgv;
+    if (bgv && (t_ <= 1 || lv.pinv_t.x == 0)) throw std::logic_error("invalid rns bases when computing pjInv_mod_t");
+    if (alpha + (bgv ? 1 : 0) > FUSE_MAX_IN || m > NTT_MAX_LIMBS || 2 * l > NTT_MAX_LIMBS || lv.beta * m > 32767) {
         // shapes outside the fused kernels' limits take the modular path
         const u64 *src = c2;
         if (ts) {
@@ -777,7 +801,8 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         }
         modup(l, ws_.t_mod_up.p, src, ws_.t_cks.p, st);
         inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
-        moddown(l, out, ws_.cx.p, ws_.delta.p, 2, addend, add_mask, st);
+        if (bgv) moddown_generic(l, out, ws_.cx.p, 2, addend, add_mask, st);
+        else moddown(l, out, ws_.cx.p, ws_.delta.p, 2, addend, add_mask, st);
         return;
     }
     u64 *t_cks = ws_.t_cks.p, *t_mod_up = ws_.t_mod_up.p, *cx = ws_.cx.p, *delta = ws_.delta.p;
@@ -858,12 +883,23 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
     } else {
         inner_prod(l, cx, t_mod_up, evk, st, ts ? nullptr : c2, ts, nullptr, false, 0, l, 0, lazy_t_);
     }
-    // 4. inverse NTT of the P limbs fused with n^-1 * phat_i^-1
+    // 4. inverse NTT of the P limbs fused with n^-1 * phat_i^-1.  BGV: out of place into a compact [2][alpha + 1][n] buffer
+    //    whose last limb receives the plain-modulus correction c = [(sum_k y_k (phat_k mod t)) P^-1]_t
+    const int nin = alpha + (bgv ? 1 : 0);
+    u64 *pin = bgv ? t_cks : cx;   // where the conversion of step 5 finds its inputs
     {
         LimbVec v;
         for (int k = 0; k < 2; k++)
-            for (int i = 0; i < alpha; i++) v.push(k * m + l + i, size_Q_ + i);
-        ntt_inv_list(cx, cx, single_list(v, rowq_), lv.moddown_fin.p, 1, sc);
+            for (int i = 0; i < alpha; i++) {
+                if (bgv) v.push(k * nin + i, size_Q_ + i, k * m + l + i);
+                else v.push(k * m + l + i, size_Q_ + i);
+            }
+        ntt_inv_list(pin, cx, single_list(v, rowq_), lv.moddown_fin.p, 1, sc);
+        if (bgv) {
+            launch_pdl(k_bgv_corr, dim3((unsigned) (n_ / EW_THREADS), 2), EW_THREADS, 0, sc, pin, (const u64 *) (lv.moddown_mat_t.p + (size_t) l * alpha),
+                       alpha, lv.pinv_t, host_modulus(t_), n_);
+            check_launch("k_bgv_corr");
+        }
     }
     // 5. mod-down: convert P -> q_j, forward NTT, (cx - delta) * P^-1 + addend
     {
@@ -872,8 +908,10 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         EpiArgs ea{};
         int pbits = 0;
         for (int i = 0; i < alpha; i++) pbits = std::max(pbits, 64 - __builtin_clzll(rowq_[size_Q_ + i]));
-        bl.in_base = cx, bl.mat = lv.moddown_mat.p, bl.matf = lv.moddown_matf.p, bl.bar = d_bar_.p;
-        bl.size_QP = mod_rows_, bl.ni = alpha, bl.xbits = pbits + ceil_log2(alpha);
+        if (bgv) pbits = std::max(pbits, 64 - __builtin_clzll(t_));
+        bl.in_base = pin, bl.bar = d_bar_.p;
+        bl.mat = bgv ? lv.moddown_mat_bgv.p : lv.moddown_mat.p, bl.matf = bgv ? lv.moddown_matf_bgv.p : lv.moddown_matf.p;
+        bl.size_QP = mod_rows_, bl.ni = nin, bl.xbits = pbits + ceil_log2(nin);
         ea.sub_base = cx, ea.out_base = out, ea.add_base = addend, ea.mulc = lv.pinv_slots.p;
         int cnt = 0;
         for (int k = 0; k < 2; k++)   // natural slot order: mulc (P^-1 per slot) is indexed by k * l + j
@@ -881,9 +919,9 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
                 ll.data[cnt] = ll.src[cnt] = (short) (k * l + j);
                 ll.row[cnt] = (short) j;
                 ll.q[cnt] = rowq_[j];
-                bl.in_limb[cnt] = (short) (k * m + l);
+                bl.in_limb[cnt] = (short) (bgv ? k * nin : k * m + l);
                 bl.mat_row[cnt] = (short) j;
-                bl.in_big[cnt] = (unsigned char) lv.moddown_big;
+                bl.in_big[cnt] = (unsigned char) (bgv ? lv.moddown_big_bgv : lv.moddown_big);
                 ea.sub[cnt] = (short) (k * m + j);
                 ea.out[cnt] = (short) (k * l + j);
                 ea.add[cnt] = ts ? (short) k : (short) ((addend && ((add_mask >> k) & 1)) ? k * l + j : -1);
@@ -906,11 +944,11 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
 // keyswitch_inplace (reference src/eval_key_switch.cu:95-182): out[2][l][n] = addend + moddown(<modup(c2), evk>)
 void Engine::keyswitch(int l, u64 *out, const u64 *c2, const u64 *const *evk, const u64 *addend, cudaStream_t st) {
     Workspace &ws_ = ws(st);
-    if (scheme_ == Scheme::ckks) {
+    if (scheme_ != Scheme::bfv) {   // CKKS, and BGV with the plain-modulus correction folded into the mod-down conversion
         keyswitch_fused(l, out, c2, nullptr, evk, addend, addend ? 3u : 0u, st);
         return;
     }
-    // BGV (NTT-form input, plain-modulus correction) and BFV (coefficient-form input and output)
+    // BFV (coefficient-form input and output)
     modup(l, ws_.t_mod_up.p, c2, ws_.t_cks.p, st);
     inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
     moddown_generic(l, out, ws_.cx.p, 2, addend, addend ? 3u : 0u, st);
@@ -1484,10 +1522,6 @@ const Decrypt &Engine::decrypt_tables(int l) {
     return *dec_[l];
 }
 
-static Modulus host_modulus(u64 q) {
-    const hm::BarrettRatio r = hm::barrett_ratio(q);
-    return Modulus{q, r.lo, r.hi};
-}
 
 // PhantomSecretKey::decrypt (reference src/secretkey.cu:533-691)
 void Engine::decrypt(int l, const u64 *ct, int size, const u64 *sk_pow, u64 correction_factor, u64 *out, cudaStream_t st) {
@@ -1804,13 +1838,6 @@ void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, con
             bfv_multiply(l, d, ct1, ct2, st);
             keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
         }
-        PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
-        return;
-    }
-    if (scheme_ == Scheme::bgv) {
-        u64 *d = ws_.tmp.p;
-        tensor_2x2(ct1, ct2, d, l, st);
-        keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
         PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
         return;
     }

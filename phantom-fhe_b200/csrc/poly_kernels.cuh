@@ -539,6 +539,20 @@ __global__ void __launch_bounds__(EW_THREADS) k_bgv_moddown(u64 *dst, const u64 
     st2(dst + x, r[0], r[1]);
 }
 
+// plain-modulus correction of the BGV mod-down (bgv_moddown_kernel, src/rns_bconv.cu:636-652, with base_P_to_t_conv):
+// buf = [npoly][alpha + 1][n]; limb alpha <- ((sum_k buf[k] * (phat_k mod t)) mod t) * P^-1 mod t.  The inputs already
+// carry the phat_k^-1 scaling (folded into the inverse transform).  grid = (n / EW_THREADS, npoly)
+__global__ void __launch_bounds__(EW_THREADS) k_bgv_corr(u64 *buf, const u64 *mat_t, int alpha, Tw pinv_t, Modulus mt, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const size_t x = (size_t) blockIdx.x * EW_THREADS + threadIdx.x;
+    u64 *b = buf + (size_t) blockIdx.y * (alpha + 1) * n + x;
+    Acc128 acc{0, 0};
+    for (int k = 0; k < alpha; k++) acc.mac(b[(size_t) k * n], mat_t[k]);
+    const u64 dt = barrett128(acc.lo, acc.hi, mt);
+    b[(size_t) alpha * n] = mul_shoup(dt, pinv_t, mt.q);
+}
+
 // divide_and_round_q_last_kernel (src/rns.cu:1082-1108), BFV modulus switch in the coefficient domain:
 // dst[j] = (src[j] - (src[last] mod q_j)) * q_last^-1 mod q_j
 __global__ void __launch_bounds__(EW_THREADS) k_divide_round_last(u64 *dst, const u64 *src, const Tw *qlast_inv,
