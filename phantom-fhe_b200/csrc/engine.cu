@@ -349,7 +349,8 @@ void Engine::build_tables() {
             bars[(size_t) g * mod_rows_ + i] = b;
         }
     d_bar_.upload(bars);
-    plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p, d_is_fp_.p, d_fpc_.p, allow_fp ? 1 : 0};
+    const char *pfe = std::getenv("PFHE_EPI_PREFETCH");
+    plan_ = NttPlan{logn_, d_tw_.p, d_itw_.p, d_mod_.p, d_inv_fin_.p, d_is_fp_.p, d_fpc_.p, allow_fp ? 1 : 0, (pfe && pfe[0] == '1') ? 1 : 0};
 }
 
 const BarG *Engine::bar(int terms, int extra_bits) const {

@@ -14,6 +14,7 @@ struct NttPlan {
     const unsigned char *is_fp;   // [size_QP]
     const double2 *fpc;           // [size_QP] {double(q), 1/double(q)}
     int fp_enabled;               // 0: integer butterflies everywhere (PFHE_FP64_NTT=0)
+    int epi_prefetch;             // fused epilogues prefetch their operands into L2 at tile start (PFHE_EPI_PREFETCH=1; measured +1.3 % time on B200, off by default)
 };
 
 // per-stream state of the single-launch transform (k_fwd_fused): work-item ticket, per-slot counts of finished column

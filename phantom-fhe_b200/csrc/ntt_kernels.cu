@@ -645,6 +645,17 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_rows_epi_te
     e.k = ea.mulc[slot];
     e.bg = bar1[row];   // growth class 1: sum of two products
     e.m = p.mod[row];
+    if (p.epi_prefetch && threadIdx.x < NTT_TILE * 8 / 128) {
+        // the epilogue's operands were last touched a whole key switch ago: start them on their way from HBM to L2 now,
+        // the transform hides the latency (one 128-byte line per thread and operand; the tile is 16 KiB of each)
+        const size_t o = ((size_t) blockIdx.x << NTT_LOG_TILE) + (size_t) threadIdx.x * 16;
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(e.a0 + o));
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(e.b0 + o));
+        if (e.kpoly != 0) {
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e.a1 + o));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(e.b1 + o));
+        }
+    }
     const u64 q = ll.q[slot];
     if (p.fp_enabled && (q >> fp::MAX_BITS) == 0) fwd_rows_epi_tensor_body<FpArith, LOGN>(smem, stw, bar, q, e);
     else fwd_rows_epi_tensor_body<IntArith, LOGN>(smem, stw, bar, q, e);
