@@ -33,6 +33,13 @@ def launches(path, out):
         f.write("## share by kernel\n\n| kernel | total us | share |\n|---|---|---|\n")
         for k, t in sorted(agg.items(), key=lambda x: -x[1]):
             f.write(f"| `{k}` | {t:.1f} | {100 * t / total:.1f}% |\n")
+        own = {k: t for k, t in agg.items() if not k.startswith("at::")}
+        if len(own) != len(agg):   # torch kernels = the untimed synthetic-data set-up of bench.py (device-side generator)
+            tot = sum(own.values())
+            f.write("\n## share by kernel, engine kernels only (the `at::` launches above are bench.py's untimed "
+                    "synthetic-data set-up)\n\n| kernel | total us | share |\n|---|---|---|\n")
+            for k, t in sorted(own.items(), key=lambda x: -x[1]):
+                f.write(f"| `{k}` | {t:.1f} | {100 * t / tot:.1f}% |\n")
         f.write(f"\ntotal {total:.1f} us over {len(d)} launches\n\n## launches\n\n" + "\n".join(lines) + "\n")
 
 
