@@ -154,11 +154,18 @@ static std::pair<uintptr_t, std::thread::id> stream_key(cudaStream_t st) {
 
 StreamCtx &Engine::sctx(cudaStream_t st) const {
     std::lock_guard<std::mutex> g(sctx_mu_);
-    auto &slot = sctx_[stream_key(st)];
-    if (!slot) {
-        slot = std::make_unique<StreamCtx>();
-        alloc_workspace(slot->ws);
+    const auto key = stream_key(st);
+    auto it = sctx_.find(key);
+    if (it != sctx_.end()) return *it->second;
+    if (sctx_.size() >= 32) {
+        // streams and threads come and go (a context is ~110 MiB at the primary set): when many have piled up, wait for
+        // the device and drop them all; live streams get a fresh context on their next call
+        cudaDeviceSynchronize();
+        sctx_.clear();
     }
+    auto &slot = sctx_[key];
+    slot = std::make_unique<StreamCtx>();
+    alloc_workspace(slot->ws);
     return *slot;
 }
 
