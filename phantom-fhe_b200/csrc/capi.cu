@@ -178,6 +178,7 @@ int pfhe_galois_elt_from_step(int step, uint64_t n, uint32_t *elt_out) {
 // ---- NTT --------------------------------------------------------------------------------------------
 int pfhe_ntt_forward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
     // reference addressing: limbs [start, start + count) of the buffer, limb i with table row i (fntt_2d.cu:35-40)
     e->impl.ntt_fwd_rows_range(U(inout) + start * e->impl.n(), (int) count, (int) start, S(stream));
@@ -186,6 +187,7 @@ int pfhe_ntt_forward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, size
 
 int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, size_t start, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
     u64 *p = U(inout) + start * e->impl.n();
     e->impl.ntt_inv_rows_range(p, p, (int) count, (int) start, S(stream));
@@ -195,6 +197,7 @@ int pfhe_ntt_backward_inplace(pfhe_engine *e, uint64_t *inout, size_t count, siz
 int pfhe_ntt_forward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_poly, size_t count, size_t start,
                                    void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(start + count <= (size_t) e->impl.size_QP() && n_poly * count < 32768, "modulus index out of range");
     e->impl.ntt_batch(U(inout), (int) n_poly, (int) count, (int) start, false, S(stream));
     API_END
@@ -203,6 +206,7 @@ int pfhe_ntt_forward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_pol
 int pfhe_ntt_backward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_poly, size_t count, size_t start,
                                     void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(start + count <= (size_t) e->impl.size_QP() && n_poly * count < 32768, "modulus index out of range");
     e->impl.ntt_batch(U(inout), (int) n_poly, (int) count, (int) start, true, S(stream));
     API_END
@@ -210,6 +214,7 @@ int pfhe_ntt_backward_inplace_batch(pfhe_engine *e, uint64_t *inout, size_t n_po
 
 int pfhe_ntt_backward(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t count, size_t start, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(start + count <= (size_t) e->impl.size_QP(), "modulus index out of range");
     e->impl.ntt_inv_rows_range(U(out) + start * e->impl.n(), U(in) + start * e->impl.n(), (int) count, (int) start, S(stream));
     API_END
@@ -231,6 +236,7 @@ static void special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t st
 int pfhe_ntt_forward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t start,
                                                  size_t size_QP, size_t size_P, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     special_mod(e, inout, count, start, size_QP, size_P, false, stream);
     API_END
 }
@@ -238,6 +244,7 @@ int pfhe_ntt_forward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout
 int pfhe_ntt_backward_inplace_include_special_mod(pfhe_engine *e, uint64_t *inout, size_t count, size_t start,
                                                   size_t size_QP, size_t size_P, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     special_mod(e, inout, count, start, size_QP, size_P, true, stream);
     API_END
 }
@@ -261,17 +268,20 @@ static Engine::NttCall ntt_call(bool inverse, int table, size_t count, size_t st
 }
 int pfhe_nwt_2d_radix8_forward_inplace(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     e->impl.ntt_call(U(inout), U(inout), ntt_call(false, table, count, start), nullptr, nullptr, S(stream));
     API_END
 }
 int pfhe_nwt_2d_radix8_backward_inplace(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     e->impl.ntt_call(U(inout), U(inout), ntt_call(true, table, count, start), nullptr, nullptr, S(stream));
     API_END
 }
 int pfhe_nwt_2d_radix8_backward(pfhe_engine *e, int table, uint64_t *out, const uint64_t *in, size_t count, size_t start,
                                 void *stream) {
     API_BEGIN
+    SmallNttScope small;
     e->impl.ntt_call(U(out), U(in), ntt_call(true, table, count, start), nullptr, nullptr, S(stream));
     API_END
 }
@@ -286,6 +296,7 @@ int pfhe_nwt_2d_radix8_forward_inplace_fuse_moddown(pfhe_engine *e, uint64_t *ct
 int pfhe_nwt_2d_radix8_forward_inplace_include_temp_mod(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start,
                                                         size_t total, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     auto c = ntt_call(false, table, count, start);
     c.remap = 2, c.a = total;
     e->impl.ntt_call(U(inout), U(inout), c, nullptr, nullptr, S(stream));
@@ -295,6 +306,7 @@ int pfhe_nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range(pfhe_en
                                                                          size_t start, size_t size_QP, size_t size_P,
                                                                          size_t excl_lo, size_t excl_hi, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(size_QP <= (size_t) e->impl.size_QP() && size_P <= count, "modulus index out of range");
     auto c = ntt_call(false, Engine::TABLE_RNS, count, start);
     c.remap = 1, c.a = size_QP, c.b = size_P, c.excl_lo = excl_lo, c.excl_hi = excl_hi;
@@ -304,6 +316,7 @@ int pfhe_nwt_2d_radix8_forward_inplace_include_special_mod_exclude_range(pfhe_en
 int pfhe_nwt_2d_radix8_forward_modup_fuse(pfhe_engine *e, uint64_t *out, const uint64_t *in, size_t modulus_index, size_t count,
                                           size_t start, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     auto c = ntt_call(false, Engine::TABLE_RNS, count, start);
     c.fixed_entry = (long) modulus_index;
     e->impl.ntt_call(U(out), U(in), c, nullptr, nullptr, S(stream));
@@ -312,6 +325,7 @@ int pfhe_nwt_2d_radix8_forward_modup_fuse(pfhe_engine *e, uint64_t *out, const u
 int pfhe_nwt_2d_radix8_backward_scale(pfhe_engine *e, int table, uint64_t *out, const uint64_t *in, size_t count, size_t start,
                                       const uint64_t *scale, const uint64_t *scale_shoup, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(scale && scale_shoup, "null argument");
     e->impl.ntt_call(U(out), U(in), ntt_call(true, table, count, start), U(scale), U(scale_shoup), S(stream));
     API_END
@@ -319,6 +333,7 @@ int pfhe_nwt_2d_radix8_backward_scale(pfhe_engine *e, int table, uint64_t *out, 
 int pfhe_nwt_2d_radix8_backward_inplace_scale(pfhe_engine *e, int table, uint64_t *inout, size_t count, size_t start,
                                               const uint64_t *scale, const uint64_t *scale_shoup, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(scale && scale_shoup, "null argument");
     e->impl.ntt_call(U(inout), U(inout), ntt_call(true, table, count, start), U(scale), U(scale_shoup), S(stream));
     API_END
@@ -327,6 +342,7 @@ int pfhe_nwt_2d_radix8_backward_inplace_include_temp_mod_scale(pfhe_engine *e, i
                                                                size_t start, size_t total, const uint64_t *scale,
                                                                const uint64_t *scale_shoup, void *stream) {
     API_BEGIN
+    SmallNttScope small;
     require(scale && scale_shoup, "null argument");
     auto c = ntt_call(true, table, count, start);
     c.remap = 2, c.a = total;

@@ -37,7 +37,7 @@ cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll
 
 // inverse NTT whose input is the limb-wise product a1 * b1 (HMult fused into the key switch)
 cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, const BarG *bar0, const LimbList &ll,
-                            const Tw *fin, int by_slot, cudaStream_t st);
+                            const Tw *fin, int by_slot, cudaStream_t st, FusedSync *sync = nullptr);
 
 // forward NTT of base-converted inputs (BconvLoad) written to `dst`; optional epilogue (ea) and tensor addend (ts)
 // phase: 0 = column pass (with the conversion) then row pass; 1 = column pass only; 2 = row pass only (the two
@@ -47,8 +47,9 @@ cudaError_t ntt_forward_bconv(const NttPlan &p, u64 *dst, const LimbList &ll, co
 
 // inverse NTT incl. n^-1; `fin` (optional) = per-slot or per-row {c, itw1*c} pairs with c = n^-1 * scalar
 // (replaces nwt_2d_radix8_backward[_inplace][_scale] and variants, include/ntt.cuh:206-226)
+// (with `sync` and few enough limbs for all CTAs to be resident: one cooperative launch for both passes, as ntt_forward)
 cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
-                        cudaStream_t st);
+                        cudaStream_t st, FusedSync *sync = nullptr);
 
 // single-CTA transforms for dim <= 2048 on caller-supplied reference-order tables (fnwt_1d / inwt_1d,
 // reference include/ntt.cuh:157-170); limb i of the call is absolute index start + i in every array

@@ -364,6 +364,91 @@ __global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_rows_mul(u6
     else inv_rows_mul_body<IntArith, LOGN>(smem, stw, bar, q, a1, b1, d, bg);
 }
 
+// ---- few limbs: both passes of a transform in ONE launch of limbs x tiles CTAs ---------------------------------------------
+// A transform of a few limbs is two single-wave launches: its time is the latency chain of one tile twice plus the gap
+// between the launches.  Here CTA (tile t, slot s) runs its first-pass tile, counts itself into ready[s], waits until the
+// N / 2048 tiles of ITS limb are in, and runs second-pass tile t -- no launch boundary, no grid-wide barrier.  The CTAs wait
+// for each other, so the launch is cooperative (the runtime guarantees that all of them are resident, also next to another
+// such launch of a different lane).  The last CTA to leave restores the counters.
+__device__ __forceinline__ void small_sync(FusedSync *sy, int slot, unsigned tiles) {
+    __syncthreads();   // every thread's first-pass stores are ordered before thread 0's release
+    if (threadIdx.x == 0) {
+        publish_tile(sy->ready, slot);
+        while (ld_acquire_u32(&sy->ready[slot]) < tiles) __nanosleep(32);
+    }
+    __syncthreads();
+}
+__device__ __forceinline__ void small_exit(FusedSync *sy, unsigned count) {
+    if (threadIdx.x == 0) {
+        __threadfence();
+        if (atomicAdd(&sy->done, 1u) == gridDim.x * gridDim.y - 1) {
+            for (unsigned i = 0; i < count; i++) sy->ready[i] = 0;
+            sy->done = 0;
+            __threadfence();
+        }
+    }
+}
+
+template<int LOGN>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_fwd_small(u64 *dst, const u64 *src, LimbList ll, NttPlan p,
+                                                                           FusedSync *sy) {
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    PFHE_NTT_SMEM_COLS(ntt_p1(LOGN), p.tw)
+    const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
+    u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
+    const Tw *tw = p.tw + ((size_t) row << LOGN);
+    PFHE_ARITH_DISPATCH(row, {
+        const typename A::Consts c = A::consts(q);
+        PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, {}, {}};
+        forward_pass<A, ntt_p1(LOGN), false, LOGN, 0>(
+                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::load(s[i], c); }),
+                per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::raw(v); }));
+        small_sync(sy, slot, gridDim.x);
+        PassCtx<A> cr{tw, nullptr, c, (int) blockIdx.x, {}, {}};
+        forward_pass<A, ntt_p2(LOGN), true, LOGN, ntt_p1(LOGN)>(
+                smem, cr, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(__ldcg(d + i)); }),
+                vec_store<typename A::T>(d, [&](typename A::T v) { return A::canon_fwd(v, c); }));
+    })
+    small_exit(sy, gridDim.y);
+}
+
+// inverse: row pass (optionally of the product a1 * b1, MUL) then column pass with the folded constants of the last stage
+template<int LOGN, bool MUL>
+__global__ void __launch_bounds__(NTT_THREADS, NTT_MIN_BLOCKS) k_inv_small(u64 *dst, const u64 *src, TensorSrc ts, const BarG *bar0,
+                                                                           LimbList ll, NttPlan p, const Tw *fin, int fin_by_slot,
+                                                                           FusedSync *sy) {
+    const int slot = blockIdx.y;
+    const int row = ll.row[slot];
+    PFHE_NTT_SMEM_COLS(ntt_p1(LOGN), p.itw)
+    u64 *d = dst + ((size_t) ll.data[slot] << LOGN);
+    const Tw *tw = p.itw + ((size_t) row << LOGN);
+    const int f = fin_by_slot ? slot : row;
+    PFHE_ARITH_DISPATCH(row, {
+        const typename A::Consts c = A::consts(q);
+        PassCtx<A> cr{tw, nullptr, c, (int) blockIdx.x, {}, {}};
+        if constexpr (MUL) {
+            const size_t poly = (size_t) ts.l << LOGN;
+            const u64 *a1 = ts.a + poly + ((size_t) ll.src[slot] << LOGN);
+            const u64 *b1 = ts.b + poly + ((size_t) ll.src[slot] << LOGN);
+            inverse_pass<A, ntt_p2(LOGN), true, LOGN, false>(
+                    smem, cr, MulLoad<A>{a1, b1, c, bar0[row], q},
+                    per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::raw(v); }));
+        } else {
+            const u64 *s = src + ((size_t) ll.src[slot] << LOGN);
+            inverse_pass<A, ntt_p2(LOGN), true, LOGN, false>(
+                    smem, cr, vec_load<typename A::T>(s, [&](u64 v) { return A::load(v, c); }),
+                    per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::raw(v); }));
+        }
+        small_sync(sy, slot, gridDim.x);
+        PassCtx<A> cx{stw, bar, c, (int) blockIdx.x, fin[2 * f], fin[2 * f + 1]};
+        inverse_pass<A, ntt_p1(LOGN), false, LOGN, true>(
+                smem, cx, per_elem_load<typename A::T>([&](size_t i) { return A::from_raw(__ldcg(d + i)); }),
+                per_elem_store<typename A::T>([&](size_t i, typename A::T v) { d[i] = A::canon_inv(v, c); }));
+    })
+    small_exit(sy, gridDim.y);
+}
+
 // base conversion as the gather of a column pass: inputs outer, elements inner, so the eight loads of one input
 // limb are in flight together and the uniform "split this input" branch sits outside the element loop.
 //
@@ -680,6 +765,9 @@ static void opt_in_all() {
     opt_in_smem(k_fwd_cols_bconv<LOGN, FUSE_MAX_IN>);
     opt_in_smem(k_fwd_rows_epi_tensor<LOGN>);
     opt_in_smem(k_fwd_fused<LOGN>);
+    opt_in_smem(k_fwd_small<LOGN>);
+    opt_in_smem(k_inv_small<LOGN, false>);
+    opt_in_smem(k_inv_small<LOGN, true>);
     done = true;
 }
 
@@ -722,6 +810,45 @@ static bool fused_enabled() {
     }
     return on;
 }
+
+// single launch for few limbs: every CTA must be resident at once (cooperative launch; on refusal the caller falls back)
+static bool small_enabled() {
+    static int on = -1;
+    if (on < 0) {
+        const char *e = std::getenv("PFHE_NTT_SMALL");
+        on = !(e && e[0] == '0');
+    }
+    return on;
+}
+static bool small_fits(const NttPlan &p, const LimbList &ll, const FusedSync *sync) {
+    return sync && small_enabled() && (ll.count << (p.logn - NTT_LOG_TILE)) <= fused_grid_limit();
+}
+template<int LOGN>
+static cudaError_t fwd_small_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st, FusedSync *sync) {
+    opt_in_all<LOGN>();
+    dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
+    return launch_coop_pdl(k_fwd_small<LOGN>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, src, ll, p, sync);
+}
+template<int LOGN>
+static cudaError_t inv_small_impl(const NttPlan &p, u64 *dst, const u64 *src, const TensorSrc *ts, const BarG *bar0,
+                                  const LimbList &ll, const Tw *fin, int by_slot, cudaStream_t st, FusedSync *sync) {
+    opt_in_all<LOGN>();
+    dim3 grid(1 << (LOGN - NTT_LOG_TILE), ll.count);
+    const Tw *f = fin ? fin : p.inv_fin;
+    const int bs = fin ? by_slot : 0;
+    if (ts) return launch_coop_pdl(k_inv_small<LOGN, true>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, src, *ts, bar0, ll, p, f, bs, sync);
+    return launch_coop_pdl(k_inv_small<LOGN, false>, grid, NTT_THREADS, NTT_SMEM_COLS, st, dst, src, TensorSrc{}, bar0, ll, p, f, bs, sync);
+}
+#define PFHE_DISPATCH_LOGN_RC(RC, FN, ...)                                                                \
+    switch (p.logn) {                                                                                     \
+        case 12: RC = FN<12>(__VA_ARGS__); break;                                                         \
+        case 13: RC = FN<13>(__VA_ARGS__); break;                                                         \
+        case 14: RC = FN<14>(__VA_ARGS__); break;                                                         \
+        case 15: RC = FN<15>(__VA_ARGS__); break;                                                         \
+        case 16: RC = FN<16>(__VA_ARGS__); break;                                                         \
+        case 17: RC = FN<17>(__VA_ARGS__); break;                                                         \
+        default: return cudaErrorInvalidValue;                                                            \
+    }
 
 template<int LOGN>
 static void fwd_fused_impl(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st, FusedSync *sync) {
@@ -769,6 +896,12 @@ static bool aligned32(Ptr... p) {
 cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st, FusedSync *sync) {
     if (ll.count == 0) return cudaSuccess;
     if (!aligned32(dst, src)) return cudaErrorMisalignedAddress;
+    if (small_fits(p, ll, sync)) {   // few limbs: one cooperative launch for both passes
+        cudaError_t rc = cudaSuccess;
+        PFHE_DISPATCH_LOGN_RC(rc, fwd_small_impl, p, dst, src, ll, st, sync)
+        if (rc == cudaSuccess) return cudaGetLastError();
+        cudaGetLastError();   // refused (does not fit next to what is running, or not supported): the launch pair
+    }
     // one persistent launch when the tiles of one pass fill the device at least once, else the launch pair
     if (sync && fused_enabled() && (ll.count << (p.logn - NTT_LOG_TILE)) >= fused_grid_limit()) {
         PFHE_DISPATCH_LOGN(fwd_fused_impl, p, dst, src, ll, st, sync)
@@ -811,9 +944,15 @@ static void fwd_bconv_impl(const NttPlan &p, u64 *dst, const LimbList &ll, const
 }
 
 cudaError_t ntt_inverse_mul(const NttPlan &p, u64 *dst, const TensorSrc &ts, const BarG *bar0, const LimbList &ll,
-                            const Tw *fin, int by_slot, cudaStream_t st) {
+                            const Tw *fin, int by_slot, cudaStream_t st, FusedSync *sync) {
     if (ll.count == 0) return cudaSuccess;
     if (!aligned32(dst, ts.a, ts.b)) return cudaErrorMisalignedAddress;
+    if (small_fits(p, ll, sync)) {
+        cudaError_t rc = cudaSuccess;
+        PFHE_DISPATCH_LOGN_RC(rc, inv_small_impl, p, dst, nullptr, &ts, bar0, ll, fin, by_slot, st, sync)
+        if (rc == cudaSuccess) return cudaGetLastError();
+        cudaGetLastError();
+    }
     PFHE_DISPATCH_LOGN(inv_mul_impl, p, dst, ts, bar0, ll, fin, by_slot, st)
     return cudaGetLastError();
 }
@@ -903,9 +1042,15 @@ cudaError_t ntt_1d(bool inverse, u64 *inout, const u64 *tw, const u64 *tws, cons
 }
 
 cudaError_t ntt_inverse(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,
-                        cudaStream_t st) {
+                        cudaStream_t st, FusedSync *sync) {
     if (ll.count == 0) return cudaSuccess;
     if (!aligned32(dst, src)) return cudaErrorMisalignedAddress;
+    if (small_fits(p, ll, sync)) {
+        cudaError_t rc = cudaSuccess;
+        PFHE_DISPATCH_LOGN_RC(rc, inv_small_impl, p, dst, src, nullptr, nullptr, ll, fin, by_slot, st, sync)
+        if (rc == cudaSuccess) return cudaGetLastError();
+        cudaGetLastError();
+    }
     PFHE_DISPATCH_LOGN(inv_impl, p, dst, src, ll, fin, by_slot, st)
     return cudaGetLastError();
 }

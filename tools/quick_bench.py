@@ -103,7 +103,7 @@ def main():
         trials = 50
         times = (ctypes.c_double * trials)()
         for op, name, aux in ((3, f"fwd NTT x{ps.size_QP}", ps.size_QP), (4, f"inv NTT x{ps.size_QP}", ps.size_QP),
-                              (3, "fwd NTT x1", 1), (0, "HMult+Relin", 0), (1, "rotate", 1), (2, "rescale", 0)):
+                              (3, "fwd NTT x1", 1), (3, "fwd NTT x4", 4), (4, "inv NTT x1", 1), (0, "HMult+Relin", 0), (1, "rotate", 1), (2, "rescale", 0)):
             assert r.ref_time_op(h, op, 1, P(a), P(b), aux, 0, trials, times) == 0, r.ref_last_error()
             ts = sorted(times)
             print(f"reference {name}: median {ts[trials // 2]:.1f} us best {ts[0]:.1f} us")
