@@ -157,12 +157,8 @@ StreamCtx &Engine::sctx(cudaStream_t st) const {
     const auto key = stream_key(st);
     auto it = sctx_.find(key);
     if (it != sctx_.end()) return *it->second;
-    if (sctx_.size() >= 32) {
-        // streams and threads come and go (a context is ~110 MiB at the primary set): when many have piled up, wait for
-        // the device and drop them all; live streams get a fresh context on their next call
-        cudaDeviceSynchronize();
-        sctx_.clear();
-    }
+    // contexts live as long as the engine: other threads may be inside a call that holds a reference to theirs (a context
+    // is ~110 MiB at the primary set; applications that churn through streams or threads should reuse them)
     auto &slot = sctx_[key];
     slot = std::make_unique<StreamCtx>();
     alloc_workspace(slot->ws);
