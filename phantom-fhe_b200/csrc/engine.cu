@@ -823,13 +823,24 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
         }
         modup(l, ws_.t_mod_up.p, src, ws_.t_cks.p, st);
         inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
-        if (bgv) moddown_generic(l, out, ws_.cx.p, 2, addend, add_mask, st);
+        if (scheme_ != Scheme::ckks) moddown_generic(l, out, ws_.cx.p, 2, addend, add_mask, st);
         else moddown(l, out, ws_.cx.p, ws_.delta.p, 2, addend, add_mask, st);
         return;
     }
     u64 *t_cks = ws_.t_cks.p, *t_mod_up = ws_.t_mod_up.p, *cx = ws_.cx.p, *delta = ws_.delta.p;
-    // 1. inverse NTT fused with n^-1 * qhat_i^-1 (and with the a1*b1 product for HMult)
-    {
+    // 1. inverse NTT fused with n^-1 * qhat_i^-1 (and with the a1*b1 product for HMult).  BFV: c2 is already in coefficient
+    //    form -- only the qhat_i^-1 scaling (bconv_mult_kernel, rns_bconv.cu:598), and the digits' own limbs, which the inner
+    //    product takes in NTT form, are transformed once into `delta` (free until the mod-down)
+    const bool bfv = scheme_ == Scheme::bfv;
+    if (bfv) {
+        if (ts) throw std::logic_error("the BFV product is not a limb-wise tensor product");
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l);
+        launch_pdl(k_scale_limbs, grid, EW_THREADS, 0, st, t_cks, c2, (const Tw *) lv.modup_fin_coeff.p, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_scale_limbs");
+        LimbVec v;
+        for (int i = 0; i < l; i++) v.push(i, i);
+        ntt_fwd_list(delta, c2, single_list(v, rowq_), st);
+    } else {
         LimbVec v;
         for (int i = 0; i < l; i++) v.push(i, i);
         const LimbList ll = single_list(v, rowq_);
@@ -885,6 +896,11 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
     //    fork -- the latency-bound chain 4 -> 5a goes to a high-priority side stream, the bandwidth-bound Q-limb half of
     //    the inner product stays on the caller's stream and fills the SMs the small launches leave idle -- and join
     //    before the epilogue.
+    if (bfv) {   // coefficient-domain mod-down (moddown_from_NTT, BFV branch): every limb of cx goes back, no epilogue to fuse
+        inner_prod(l, cx, t_mod_up, evk, st, delta, nullptr, nullptr, false, 0, -1, 0, lazy_t_);
+        moddown_generic(l, out, cx, 2, addend, add_mask, st);
+        return;
+    }
     const bool fork = overlap_;
     cudaStream_t sc = st;   // stream of the P-limb chain
     cudaEvent_t ev_join = nullptr;
@@ -966,14 +982,10 @@ void Engine::keyswitch_fused(int l, u64 *out, const u64 *c2, const TensorSrc *ts
 // keyswitch_inplace (reference src/eval_key_switch.cu:95-182): out[2][l][n] = addend + moddown(<modup(c2), evk>)
 void Engine::keyswitch(int l, u64 *out, const u64 *c2, const u64 *const *evk, const u64 *addend, cudaStream_t st) {
     Workspace &ws_ = ws(st);
-    if (scheme_ != Scheme::bfv) {   // CKKS, and BGV with the plain-modulus correction folded into the mod-down conversion
-        keyswitch_fused(l, out, c2, nullptr, evk, addend, addend ? 3u : 0u, st);
-        return;
-    }
-    // BFV (coefficient-form input and output)
-    modup(l, ws_.t_mod_up.p, c2, ws_.t_cks.p, st);
-    inner_prod(l, ws_.cx.p, ws_.t_mod_up.p, evk, st);
-    moddown_generic(l, out, ws_.cx.p, 2, addend, addend ? 3u : 0u, st);
+    // CKKS; BGV with the plain-modulus correction folded into the mod-down conversion; BFV with the fused mod-up and the
+    // coefficient-domain mod-down
+    (void) ws_;
+    keyswitch_fused(l, out, c2, nullptr, evk, addend, addend ? 3u : 0u, st);
 }
 
 void Engine::moddown_generic(int l, u64 *out, u64 *cx, int npoly, const u64 *addend, unsigned add_mask,
