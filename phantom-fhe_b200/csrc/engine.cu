@@ -1002,6 +1002,18 @@ void Engine::moddown_generic(int l, u64 *out, u64 *cx, int npoly, const u64 *add
             for (int j = 0; j < m; j++) v.push(k * m + j, j < l ? j : size_Q_ + (j - l));
         run_chunks(v, rowq_, [&](const LimbList &ll, size_t b) { ntt_inv_list(cx, cx, ll, lv.moddown_fin_all.p + 2 * b, 1, st); });
     }
+    static const bool one_pass = [] {
+        const char *e = std::getenv("PFHE_BFV_MODDOWN_FUSED");
+        return !(e && e[0] == '0');
+    }();
+    if (!bgv && one_pass) {
+        // BFV: conversion, (cx - delta) * P^-1 and the addition in one pass; the result stays in the coefficient domain
+        dim3 grid((unsigned) (n_ / (2 * EW_THREADS)), l, npoly);
+        launch_pdl(k_moddown_coeff_conv, grid, EW_THREADS, 0, st, out, (const u64 *) cx, (const u64 *) lv.moddown_mat.p, alpha, m,
+                   (const Tw *) lv.pinv_slots.p, addend, add_mask, (const Modulus *) d_mod_.p, n_);
+        check_launch("k_moddown_coeff_conv");
+        return;
+    }
     // 2. P -> Ql (and, BGV, P -> t) conversion
     u64 *delta = ws_.delta.p;
     const int no = bgv ? l + 1 : l;
@@ -1868,11 +1880,11 @@ void Engine::multiply_relin(int l, u64 *out, const u64 *ct1, const u64 *ct2, con
         if (drop) {   // bfv_mul_relin_hps with levels dropped (evaluate.cu:819-1026): c2 stays at Ql and is switched there
             bfv_multiply_hps_overq(l, d, ct1, ct2, drop, st, true);
             keyswitch_leveled(d, d + (size_t) 2 * l * n_, rlk, drop, true, st);
+            PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
         } else {
             bfv_multiply(l, d, ct1, ct2, st);
-            keyswitch(l, d, d + (size_t) 2 * l * n_, rlk, d, st);
+            keyswitch(l, out, d + (size_t) 2 * l * n_, rlk, d, st);   // out = (d0, d1) + keyswitch(d2): no copy
         }
-        PFHE_CUDA(cudaMemcpyAsync(out, d, (size_t) 2 * l * n_ * 8, cudaMemcpyDeviceToDevice, st));
         return;
     }
     if (out == ct1 || out == ct2) {

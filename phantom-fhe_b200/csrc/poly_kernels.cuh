@@ -539,6 +539,36 @@ __global__ void __launch_bounds__(EW_THREADS) k_bgv_moddown(u64 *dst, const u64 
     st2(dst + x, r[0], r[1]);
 }
 
+// BFV mod-down in one pass over the output limbs (bConv_BEHZ matmul of the P limbs, rns_bconv.cu:143-168 / :691-707, +
+// moddown_kernel :680-689 + add_to_ct :763-769): out[k][j] = (cx[k][j] - sum_i cx[k][l + i] * (phat_i mod q_j)) * P^-1 (+ add).
+// cx = [npoly][m][n] in coefficient form, its P limbs already scaled by phat_i^-1.  grid = (n / (2 EW_THREADS), l, npoly)
+__global__ void __launch_bounds__(EW_THREADS) k_moddown_coeff_conv(u64 *out, const u64 *cx, const u64 *mat, int alpha, int m,
+                                                                    const Tw *pinv, const u64 *add, unsigned add_mask,
+                                                                    const Modulus *mod, size_t n) {
+    pdl_launch_dependents();
+    pdl_wait();
+    const int j = blockIdx.y, k = blockIdx.z, l = gridDim.y;
+    const Modulus mj = mod[j];
+    const size_t xo = ((size_t) blockIdx.x * EW_THREADS + threadIdx.x) * 2;
+    const u64 *c = cx + (size_t) k * m * n;
+    Acc128 a0{0, 0}, a1{0, 0};
+    for (int i = 0; i < alpha; i++) {
+        const ulonglong2 y = ld2(c + (size_t) (l + i) * n + xo);
+        const u64 M = mat[(size_t) j * alpha + i];
+        a0.mac(y.x, M), a1.mac(y.y, M);
+    }
+    const u64 d0 = barrett128(a0.lo, a0.hi, mj), d1 = barrett128(a1.lo, a1.hi, mj);
+    const ulonglong2 v = ld2(c + (size_t) j * n + xo);
+    const Tw pi = pinv[j];
+    u64 r0 = mul_shoup(sub_mod(v.x, d0, mj.q), pi, mj.q), r1 = mul_shoup(sub_mod(v.y, d1, mj.q), pi, mj.q);
+    const size_t o = ((size_t) k * l + j) * n + xo;
+    if (add && ((add_mask >> k) & 1)) {
+        const ulonglong2 a = ld2(add + o);
+        r0 = add_mod(r0, a.x, mj.q), r1 = add_mod(r1, a.y, mj.q);
+    }
+    st2(out + o, r0, r1);
+}
+
 // plain-modulus correction of the BGV mod-down (bgv_moddown_kernel, src/rns_bconv.cu:636-652, with base_P_to_t_conv):
 // buf = [npoly][alpha + 1][n]; limb alpha <- ((sum_k buf[k] * (phat_k mod t)) mod t) * P^-1 mod t.  The inputs already
 // carry the phat_k^-1 scaling (folded into the inverse transform).  grid = (n / EW_THREADS, npoly)
