@@ -558,9 +558,9 @@ def main():
         roof_ip = {"kernel": "key-switch inner product (k_inner_prod<4>), beta=4, m=20, alone on a full grid",
                    "bound": "hbm", "achieved": ip_ach, "peak": peak, "unit": "GB/s", "frac": ip_ach / peak,
                    "peak_source": how, "traffic": None, "algorithmic_bytes": ip_bytes, "launch_us": ip_us}
-        if not args.no_extra:
+        if not args.no_extra and world == 1:
             extra = extra_configs(pf, lib, check, torch, dev)
-        if not args.no_cpu_baseline:
+        if not args.no_cpu_baseline and world == 1:   # reported baselines: rank 0 at N = 1 only
             cb = cpu_baseline()
 
     if rank == 0:
