@@ -743,11 +743,14 @@ void Engine::inner_prod(int l, u64 *cx, const u64 *t_mod_up, const u64 *const *e
     const InnerProdArgs A{cx, t_mod_up, evk, d_mod_.p, bar(lv.beta), bar(1, 0),
                           RowArith{d_is_fp_.p, d_fpc_.p, fp_mask_[0], fp_mask_[1], size_QP_ <= 128}, os, perm,
                           accumulate ? 1 : 0, t_lazy ? 1 : 0, n_, l, lv.m, size_Q_, size_QP_, lv.beta, j_begin, j_count};
-    const unsigned tiles = (unsigned) (n_ / IP_TILE) * (unsigned) j_count;
+    // few limbs (the P limbs on the critical path of the fused key switch): one coefficient pair per thread
+    const bool thin = persist_ctas == 0 && lv.beta == 4 && !perm && !accumulate && (size_t) j_count * n_ / IP_TILE <= 296;
+    const unsigned tiles = (unsigned) (n_ / (thin ? IP_TILE / IP_PAIRS : IP_TILE)) * (unsigned) j_count;
     const dim3 grid(persist_ctas > 0 ? std::min((unsigned) persist_ctas, tiles) : tiles);
     const bool plain = !perm && !accumulate;
     auto go = [&](auto kern) { launch_pdl(kern, grid, EW_THREADS, 0, st, A); };
     if (!plain) go(k_inner_prod<0, false>);
+    else if (thin) go(k_inner_prod<4, true, 1>);
     else if (lv.beta == 1) go(k_inner_prod<1, true>);
     else if (lv.beta == 2) go(k_inner_prod<2, true>);
     else if (lv.beta == 3) go(k_inner_prod<3, true>);

@@ -336,7 +336,7 @@ struct InnerProdArgs {
 constexpr int IP_PAIRS = 2;
 constexpr int IP_TILE = IP_PAIRS * 2 * EW_THREADS;
 
-template<int BETA, bool PLAIN>
+template<int BETA, bool PLAIN, int PAIRS>
 __device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const int j, const unsigned bx) {
     const int beta = BETA > 0 ? BETA : A.beta;
     const size_t n = A.n;
@@ -359,7 +359,7 @@ __device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const in
 #pragma unroll
         for (int d = 0; d < BETA; d++) kp[d] = A.evk[d] + (size_t) row * n;
     }
-    const size_t x_base = ((size_t) bx * IP_PAIRS * EW_THREADS + threadIdx.x) * 2;
+    const size_t x_base = ((size_t) bx * PAIRS * EW_THREADS + threadIdx.x) * 2;
     const bool is_fp = A.ra.fp(row);   // CTA-uniform
     double q = 0, qi = 0;
     Modulus md{};
@@ -368,7 +368,7 @@ __device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const in
     else md = A.mod[row], bg = A.bar[row], b0 = A.bar0[row];
 
 #pragma unroll 1
-    for (int ip = 0; ip < IP_PAIRS; ip++) {
+    for (int ip = 0; ip < PAIRS; ip++) {
         const size_t x = x_base + (size_t) ip * 2 * EW_THREADS;
         size_t px0 = x, px1 = x + 1;
         if (perm) {   // hoisting (reference src/evaluate.cu:1775-1835): digits are read through the Galois permutation
@@ -471,15 +471,17 @@ __device__ __forceinline__ void inner_prod_tile(const InnerProdArgs &A, const in
 
 // grid-stride over the tiles (limb-major); a grid of all tiles runs the loop once, a smaller grid ("persist": leaves
 // room on every SM for the higher-priority mod-down chain of the fused key switch) walks them
-template<int BETA, bool PLAIN>
+// PAIRS: coefficient pairs per thread.  2 for the streaming launches; 1 for the few-limb launch on the critical path of the
+// key switch (the P limbs: twice the CTAs, half the serial work per thread)
+template<int BETA, bool PLAIN, int PAIRS = IP_PAIRS>
 __global__ void __launch_bounds__(EW_THREADS, 4) k_inner_prod(const InnerProdArgs A) {
     pdl_launch_dependents();
     pdl_wait();
-    const unsigned nbx = (unsigned) (A.n / IP_TILE);   // power of two
+    const unsigned nbx = (unsigned) (A.n / (PAIRS * 2 * EW_THREADS));   // power of two
     const unsigned sh = 31u - (unsigned) __clz(nbx);
     const unsigned total = nbx * (unsigned) A.j_count;
     for (unsigned tile = blockIdx.x; tile < total; tile += gridDim.x)
-        inner_prod_tile<BETA, PLAIN>(A, A.j0 + (int) (tile >> sh), tile & (nbx - 1));
+        inner_prod_tile<BETA, PLAIN, PAIRS>(A, A.j0 + (int) (tile >> sh), tile & (nbx - 1));
 }
 
 // ---------------------------------------------------------------------------------------------------
