@@ -611,8 +611,11 @@ void Engine::ntt_inv_rows_range(u64 *dst, const u64 *src, int count, int start_r
 
 void Engine::ntt_batch(u64 *inout, int n_poly, int count, int start_row, bool inverse, cudaStream_t st) const {
     LimbVec v;
-    for (int p = 0; p < n_poly; p++)
-        for (int i = 0; i < count; i++) v.push(p * count + i, start_row + i);
+    // limbs on the (slower) integer butterflies first: their tiles start in the first wave instead of stretching the last
+    for (int pass = 0; pass < 2; pass++)
+        for (int p = 0; p < n_poly; p++)
+            for (int i = 0; i < count; i++)
+                if ((!is_fp_[start_row + i]) == (pass == 0)) v.push(p * count + i, start_row + i);
     run_chunks(v, rowq_, [&](const LimbList &ll, size_t) {
         if (inverse) ntt_inv_list(inout, inout, ll, nullptr, 0, st);
         else ntt_fwd_list(inout, inout, ll, st);
