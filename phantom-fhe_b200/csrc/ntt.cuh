@@ -23,9 +23,15 @@
 
 namespace pfhe {
 
-constexpr int NTT_LOG_THREADS = 8;
+#ifndef PFHE_NTT_LOG_THREADS
+#define PFHE_NTT_LOG_THREADS 8
+#endif
+#ifndef PFHE_NTT_LOG_EPT
+#define PFHE_NTT_LOG_EPT 3
+#endif
+constexpr int NTT_LOG_THREADS = PFHE_NTT_LOG_THREADS;
 constexpr int NTT_THREADS = 1 << NTT_LOG_THREADS;
-constexpr int NTT_LOG_EPT = 3;                       // elements per thread = one radix-8 group
+constexpr int NTT_LOG_EPT = PFHE_NTT_LOG_EPT;         // elements per thread = one radix-8 group (A/B builds: 2 = radix-4, 512 threads)
 constexpr int NTT_EPT = 1 << NTT_LOG_EPT;
 constexpr int NTT_LOG_TILE = NTT_LOG_THREADS + NTT_LOG_EPT;
 constexpr int NTT_TILE = 1 << NTT_LOG_TILE;
@@ -636,6 +642,8 @@ __device__ __forceinline__ void forward_pass(u64 *smem, const PassCtx<A> &cx, Lo
     if constexpr (NR > 1) run_round(std::integral_constant<int, 1>{});
     if constexpr (NR > 2) run_round(std::integral_constant<int, 2>{});
     if constexpr (NR > 3) run_round(std::integral_constant<int, 3>{});
+    if constexpr (NR > 4) run_round(std::integral_constant<int, 4>{});
+    static_assert(NR <= 5, "round schedule too long");
 
     TL_MARK(12)
 }
@@ -694,6 +702,8 @@ __device__ __forceinline__ void inverse_pass(u64 *smem, const PassCtx<A> &cx, Lo
         }
     };
 
+    static_assert(NR <= 5, "round schedule too long");
+    if constexpr (NR > 4) run_round(std::integral_constant<int, 4>{});
     if constexpr (NR > 3) run_round(std::integral_constant<int, 3>{});
     if constexpr (NR > 2) run_round(std::integral_constant<int, 2>{});
     if constexpr (NR > 1) run_round(std::integral_constant<int, 1>{});
