@@ -55,7 +55,11 @@ def stream():
 
 def param_set(scheme, n=4096):
     if scheme == 2:
-        return H.params_small(n, l=3, alpha=1, qbits=36, pbits=42, scheme=2, t=65537)
+        # equal-size data primes: the reference's HPS multiplication takes its auxiliary base R as size_Q + 1 primes below
+        # min(q_i) (rns.cu:687-694) and needs R > Q t N; with a first prime 10 bits above the others (params_small) R falls
+        # ~4 bits short at N = 8192 and about one product in seven decrypts wrongly -- in the reference and, word for word,
+        # here (tools/dbg_interop2.py)
+        return H.ParamSet(f"bfv_keygen{n}", n, [40, 40, 40, 50], 1, scheme=2, t=65537)
     return H.params_small(n, l=4, alpha=2, scheme=scheme, t=65537 if scheme == 1 else 0)
 
 
