@@ -579,6 +579,10 @@ void Engine::ntt_fwd_list(u64 *dst, const u64 *src, const LimbList &ll, cudaStre
     if (!g_small_ntt && !fused_env) sy = nullptr;   // inside a pipeline: the launch pair
     g_launches.fetch_add(2, std::memory_order_relaxed);   // (one launch under PFHE_NTT_FUSED=1: counted as the pair it replaces)
     (void) w;
+    if (plan_.logn == 16 && ntt_cluster_mode()) {   // opt-in experiment: cluster per limb, intermediate in distributed shared memory
+        PFHE_CUDA(ntt_forward_cluster(plan_, dst, src, ll, st));
+        return;
+    }
     PFHE_CUDA(ntt_forward(plan_, dst, src, ll, st, sy));
 }
 void Engine::ntt_inv_list(u64 *dst, const u64 *src, const LimbList &ll, const Tw *fin, int by_slot,

@@ -32,6 +32,11 @@ struct FusedSync {
 cudaError_t ntt_forward(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st,
                         FusedSync *sync = nullptr);
 
+// experiment (ntt_cluster.cu, PFHE_NTT_CLUSTER=8 | 16, N = 2^16 only): one launch, a thread-block cluster per limb, the
+// intermediate in distributed shared memory.  ntt_cluster_mode() = 0 unless the variable asks for it.
+int ntt_cluster_mode();
+cudaError_t ntt_forward_cluster(const NttPlan &p, u64 *dst, const u64 *src, const LimbList &ll, cudaStream_t st);
+
 // forward NTT of `data` (in place, ll.src must equal ll.data) whose row pass ends in the EpiArgs epilogue
 cudaError_t ntt_forward_epilogue(const NttPlan &p, u64 *data, const LimbList &ll, const EpiArgs &ea, cudaStream_t st);
 
