@@ -12,7 +12,8 @@ pytestmark = pytest.mark.gpu
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 CASES = ["tests/test_gpu_parity.py::test_ntt_forward_inverse", "tests/test_gpu_parity.py::test_ntt_start_index_and_linearity",
-         "tests/test_gpu_parity.py::test_ntt_config1_known_answer"]
+         "tests/test_gpu_parity.py::test_ntt_config1_known_answer",
+         "tests/test_gpu_parity.py::test_against_unmodified_reference"]   # 20 limbs of N = 2^16: enough tiles for the persistent form
 
 
 @pytest.mark.parametrize("switch", ["PFHE_NTT_CLUSTER=16", "PFHE_NTT_CLUSTER=8", "PFHE_NTT_FUSED=1"])
