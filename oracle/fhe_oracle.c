@@ -22,6 +22,10 @@ typedef uint64_t u64;
 static int g_threads = 1;
 void orc_set_threads(int nthreads) { g_threads = nthreads < 1 ? 1 : nthreads; }
 int orc_get_threads(void) { return g_threads; }
+/* diagnosis only (tests/test_bfv_hps_alpha_case.py): 1 = reduce the UNREDUCED alpha under every r_j in the HPS scale-and-round
+ * step instead of restating the reference's limb-after-limb re-reduction (rns.cu:1699-1733) */
+static int g_hps_alpha_per_limb = 0;
+void orc_set_hps_alpha_per_limb(int on) { g_hps_alpha_per_limb = on != 0; }
 
 /* ------------------------------------------------------------------------------------------------------
  * scalar modular arithmetic
@@ -1212,13 +1216,14 @@ int orc_bfv_multiply_hps(const orc_ctx *c, const u64 *ct1, const u64 *ct2, u64 *
         for (size_t k = 0; k < n; k++) {
             double nu = 0.5;
             for (int i = 0; i < lq; i++) nu = fma((double)x[(size_t)i * n + k], fr[i], nu);
-            u64 alpha = sat_u64(nu);
+            const u64 alpha0 = sat_u64(nu);
+            u64 alpha = alpha0;
             for (int j = 0; j < nR; j++) {
                 u64 rj = R[j];
                 u128 cur = 0;
                 for (int i = 0; i < lq; i++) cur = (cur + (u128)x[(size_t)i * n + k] * tab[(size_t)j * (lq + 1) + i]) % rj;
                 cur = (cur + (u128)x[(size_t)(lq + j) * n + k] * tab[(size_t)j * (lq + 1) + lq]) % rj;
-                alpha %= rj;
+                alpha = (g_hps_alpha_per_limb ? alpha0 : alpha) % rj;
                 tmpR[(size_t)j * n + k] = addmod((u64)cur, alpha, rj);
             }
         }

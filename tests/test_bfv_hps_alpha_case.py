@@ -66,6 +66,14 @@ def test_oracle_reproduces_the_wrong_coefficient():
     assert o.orc_decrypt(oc, l, P(prod), 2, P(sk), 2, 1, P(dec)) == 0
     bad = np.nonzero(dec % ps.t != want)[0]
     assert list(bad) == [case["wrong_coefficient"]] and int(dec[bad[0]] % ps.t) == case["decrypts_to"]
+    # the cause: with the unreduced alpha reduced under every r_j the same product decrypts correctly
+    o.orc_set_hps_alpha_per_limb(1)
+    try:
+        assert o.orc_bfv_multiply_relin_hps(oc, P(ca), P(cb), P(rlk), P(prod)) == 0
+        assert o.orc_decrypt(oc, l, P(prod), 2, P(sk), 2, 1, P(dec)) == 0
+        assert np.array_equal(dec % ps.t, want)
+    finally:
+        o.orc_set_hps_alpha_per_limb(0)
     # the BEHZ product of the same ciphertexts (no floating-point correction, no base R) decrypts to the product
     assert o.orc_bfv_multiply_relin_behz(oc, P(ca), P(cb), P(rlk), P(prod)) == 0
     assert o.orc_decrypt(oc, l, P(prod), 2, P(sk), 1, 1, P(dec)) == 0
