@@ -21,6 +21,7 @@ o, oc = H.oracle(), ps.octx()
 l, m, t = ps.size_Q, ps.size_QP, ps.t
 dnum = l // ps.size_P
 rng = np.random.default_rng(int(sys.argv[3]) if len(sys.argv) > 3 else 1)
+mul_tech = int(sys.argv[4]) if len(sys.argv) > 4 else 2   # 1 behz, 2 hps, 3 hps_overq
 a = np.zeros(n, dtype=np.uint64); a[0], a[1] = 3, 5
 b = np.zeros(n, dtype=np.uint64); b[0], b[n - 1] = 7, 2
 want = np.zeros(n, dtype=np.uint64); want[0], want[1], want[n - 1] = 11, 35, 6
@@ -43,9 +44,14 @@ for rep in range(int(sys.argv[1]) if len(sys.argv) > 1 else 20):
     assert o.orc_encrypt_zero_asymmetric(oc, P(pk), sd[5], sd[6], P(cb)) == 0
     assert o.orc_encrypt_add_plain(oc, l, P(cb), P(b)) == 0
     prod = np.zeros((2, l, n), dtype=np.uint64)
-    assert o.orc_bfv_multiply_relin_hps(oc, P(ca), P(cb), P(rlk), P(prod)) == 0
+    if mul_tech == 2:
+        assert o.orc_bfv_multiply_relin_hps(oc, P(ca), P(cb), P(rlk), P(prod)) == 0
+    elif mul_tech == 3:
+        assert o.orc_bfv_multiply_relin_hps_overq(oc, P(ca), P(cb), P(rlk), P(prod), 0) == 0
+    else:
+        assert o.orc_bfv_multiply_relin_behz(oc, P(ca), P(cb), P(rlk), P(prod)) == 0
     dec = np.zeros(n, dtype=np.uint64)
-    assert o.orc_decrypt(oc, l, P(prod), 2, P(sk), 2, 1, P(dec)) == 0
+    assert o.orc_decrypt(oc, l, P(prod), 2, P(sk), mul_tech, 1, P(dec)) == 0
     bad = np.nonzero(dec % t != want)[0]
     if len(bad):
         bad_runs += 1
